@@ -1,0 +1,172 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes wrapper over oracle/libthompson_oracle.so, the CPU restatement of the reference scheme
+(/root/reference/module_mp_thompson09n.f90 = "M:", mphys_thompson09n.f90 = "I:").
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  PARITY UNPINNED by the reference (it ships no tests or vectors).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libthompson_oracle.so")
+_fp = C.POINTER(C.c_float)
+_dp = C.POINTER(C.c_double)
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("thompson_oracle.cpp", "thompson_oracle_step.inc", "thompson_oracle.h")]
+    if force or not os.path.exists(_LIB) or any(
+            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        subprocess.check_call(["make", "-C", _HERE, "-s"], env=env)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.kor_create.restype = C.c_void_p
+        L.kor_create.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.kor_destroy.argtypes = [C.c_void_p]
+        L.kor_init_seconds.restype = C.c_double
+        L.kor_init_seconds.argtypes = [C.c_void_p]
+        L.kor_table_size.restype = C.c_long
+        L.kor_table_size.argtypes = [C.c_void_p, C.c_char_p]
+        L.kor_get_table.restype = C.c_long
+        L.kor_get_table.argtypes = [C.c_void_p, C.c_char_p, _dp, C.c_long]
+        L.kor_mp_thompson.restype = C.c_int
+        L.kor_mp_thompson.argtypes = [C.c_void_p, C.c_int, C.c_float] + [_fp] * 10 + [_fp, _fp, _fp, _dp]
+        L.kor_step.restype = C.c_int
+        L.kor_step.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_int] + [_fp] * 9 + [_fp, _fp, _fp, C.c_int]
+        L.kor_rate_names.restype = C.c_char_p
+        for n in ("kor_rslf", "kor_rsif"):
+            getattr(L, n).restype = C.c_float
+            getattr(L, n).argtypes = [C.c_float, C.c_float]
+        for n in ("kor_gammln", "kor_wgamma"):
+            getattr(L, n).restype = C.c_float
+            getattr(L, n).argtypes = [C.c_float]
+        L.kor_gammp.restype = C.c_float
+        L.kor_gammp.argtypes = [C.c_float, C.c_float]
+        L.kor_decade_index.restype = C.c_int
+        L.kor_decade_index.argtypes = [C.c_float, C.c_int, C.c_int]
+        _lib = L
+    return _lib
+
+
+def default_cache_path():
+    d = os.environ.get("KOR_CACHE_DIR", os.path.join(_HERE, "_cache"))
+    os.makedirs(d, exist_ok=True)
+    return os.path.join(d, "collection_tables.bin")
+
+
+FIELDS = ("qv", "qc", "qi", "qr", "qs", "qg", "ni", "nr", "t")
+TABLES_4D_G = ("tcg_racg", "tmr_racg", "tcr_gacr", "tmg_gacr", "tnr_racg", "tnr_gacr")
+TABLES_4D_S = ("tcs_racs1", "tmr_racs1", "tcs_racs2", "tmr_racs2", "tcr_sacr1", "tms_sacr1",
+               "tcr_sacr2", "tms_sacr2", "tnr_racs1", "tnr_racs2", "tnr_sacr1", "tnr_sacr2")
+TABLES_SMALL = ("tpi_qcfz", "tni_qcfz", "tpi_qrfz", "tpg_qrfz", "tni_qrfz", "tnr_qrfz",
+                "tps_iaus", "tni_iaus", "tpi_ide", "t_Efrw", "t_Efsw")
+TABLE_SHAPES = {  # Fortran (column-major) shapes, M:386-423
+    **{n: (28, 28, 37, 37) for n in TABLES_4D_G},
+    **{n: (28, 9, 37, 37) for n in TABLES_4D_S},
+    "tpi_qcfz": (37, 45), "tni_qcfz": (37, 45),
+    "tpi_qrfz": (37, 37, 45), "tpg_qrfz": (37, 37, 45), "tni_qrfz": (37, 37, 45), "tnr_qrfz": (37, 37, 45),
+    "tps_iaus": (64, 55), "tni_iaus": (64, 55), "tpi_ide": (64, 55),
+    "t_Efrw": (100, 100), "t_Efsw": (100, 100),
+}
+
+
+class Oracle:
+    """thompson_init (M:374-797) + mp_thompson (M:1156-3688) on the CPU."""
+
+    def __init__(self, set_Nc=100.0, iiwarm=False, l_sediment=True, wp_double=False, cache=True, nthreads=None):
+        L = lib()
+        self.nthreads = nthreads or os.cpu_count() or 1
+        cp = default_cache_path().encode() if cache else None
+        self.h = L.kor_create(float(set_Nc), int(iiwarm), int(l_sediment), int(wp_double), cp, self.nthreads)
+        self.iiwarm = bool(iiwarm)
+        self.rate_names = L.kor_rate_names().decode().split(",")
+
+    def close(self):
+        if self.h:
+            lib().kor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def init_seconds(self):
+        return lib().kor_init_seconds(self.h)
+
+    def get(self, name):
+        L = lib()
+        n = L.kor_table_size(self.h, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, dtype=np.float64)
+        L.kor_get_table(self.h, name.encode(), out.ctypes.data_as(_dp), n)
+        if name in TABLE_SHAPES:
+            out = out.reshape(TABLE_SHAPES[name], order="F")
+        return out
+
+    def column(self, dt, qv, qc, qi, qr, qs, qg, ni, nr, t, p, dz, nc=None, ppt=None, want_rates=False):
+        """One mp_thompson call.  Arrays of nz (index 0 = lowest level); returns dict of new arrays."""
+        nz = len(t)
+        a = {k: np.ascontiguousarray(v, dtype=np.float32).copy()
+             for k, v in zip(FIELDS, (qv, qc, qi, qr, qs, qg, ni, nr, t))}
+        p = np.ascontiguousarray(p, dtype=np.float32)
+        dz = np.ascontiguousarray(dz, dtype=np.float32)
+        ppt4 = np.zeros(4, np.float32) if ppt is None else np.asarray(ppt, np.float32).copy()
+        ncp = None
+        if nc is not None:
+            a["nc"] = np.ascontiguousarray(nc, dtype=np.float32).copy()
+            ncp = a["nc"].ctypes.data_as(_fp)
+        rates = np.zeros((36, nz), np.float64) if want_rates else None
+        rc = lib().kor_mp_thompson(
+            self.h, nz, float(dt), *[a[k].ctypes.data_as(_fp) for k in ("qv", "qc", "qi", "qr", "qs", "qg", "ni", "nr")],
+            ncp, a["t"].ctypes.data_as(_fp), p.ctypes.data_as(_fp), dz.ctypes.data_as(_fp),
+            ppt4.ctypes.data_as(_fp), rates.ctypes.data_as(_dp) if want_rates else None)
+        if rc:
+            raise RuntimeError("kor_mp_thompson rc=%d" % rc)
+        a["ppt"] = ppt4
+        if want_rates:
+            a["rates"] = rates
+        return a
+
+    def step(self, dt, state, p, dz, layout="col_fastest", nthreads=None):
+        """I:54-246 over many columns, in place on the float32 arrays in `state` (dict by FIELDS).
+        layout 'k_fastest': arrays (ncol, nz); 'col_fastest': arrays (nz, ncol).  Returns ppt[4, ncol]."""
+        lay = 0 if layout == "k_fastest" else 1
+        t = state["t"]
+        ncol, nz = (t.shape if lay == 0 else t.shape[::-1])
+        for k in FIELDS:
+            assert state[k].dtype == np.float32 and state[k].flags.c_contiguous and state[k].shape == t.shape
+        assert p.dtype == np.float32 and p.flags.c_contiguous and p.shape == t.shape
+        dz = np.ascontiguousarray(dz, np.float32)
+        ppt = np.zeros((4, ncol), np.float32)
+        rc = lib().kor_step(self.h, ncol, nz, float(dt), lay, *[state[k].ctypes.data_as(_fp) for k in FIELDS],
+                            p.ctypes.data_as(_fp), dz.ctypes.data_as(_fp), ppt.ctypes.data_as(_fp),
+                            int(nthreads or self.nthreads))
+        if rc:
+            raise RuntimeError("kor_step rc=%d" % rc)
+        return ppt
+
+
+def rslf(p, t):
+    return float(lib().kor_rslf(p, t))
+
+
+def rsif(p, t):
+    return float(lib().kor_rsif(p, t))

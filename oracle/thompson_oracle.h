@@ -1,0 +1,55 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// CPU restatement of the reference Thompson scheme driven by KiD:
+//   M: = /root/reference/module_mp_thompson09n.f90   I: = /root/reference/mphys_thompson09n.f90
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+// load this library.  The product (kid_b200/) never includes, links or calls anything here.
+//
+// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
+// and no Fortran compiler exists in the build container, so this restatement is pinned only by
+// the source-derived known-answer values in tests/test_oracle_kat.py.
+#pragma once
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kor_handle kor_handle;
+
+// M:374-797 thompson_init.  wp_double: kind of DFLOAT() at M:8 (0 = f32 default, U5).
+// cache_path: optional binary cache for the two 4-D collection tables (may be NULL).
+kor_handle* kor_create(float set_Nc, int iiwarm, int l_sediment, int wp_double,
+                       const char* cache_path, int nthreads);
+void kor_destroy(kor_handle*);
+double kor_init_seconds(const kor_handle*);
+
+// named access to constants and tables (column-major, Fortran order), returns element count or -1
+long kor_table_size(const kor_handle*, const char* name);
+long kor_get_table(const kor_handle*, const char* name, double* out, long n);
+
+// M:1156-3688 mp_thompson for one column (arrays of nz, index 0 = kts).  nc may be NULL: then
+// nc1d = Nt_c/rho as mp_gt_driver does (M:957-964, decision U1).  rates (optional) receives
+// [36][nz] doubles in the order of kor_rate_names().
+int kor_mp_thompson(const kor_handle*, int nz, float dt,
+                    float* qv, float* qc, float* qi, float* qr, float* qs, float* qg,
+                    float* ni, float* nr, float* nc, float* t,
+                    const float* p, const float* dz, float* ppt4, double* rates);
+
+// I:54-246 loop over columns.  layout 0: K_FASTEST a[col*nz+k] (KiD (k,i)); 1: COL_FASTEST
+// a[k*ncol+col].  ppt is [4][ncol] (rain, ice, snow, graupel).  dz is one shared nz vector.
+int kor_step(const kor_handle*, long ncol, int nz, float dt, int layout,
+             float* qv, float* qc, float* qi, float* qr, float* qs, float* qg,
+             float* ni, float* nr, float* t, const float* p, const float* dz,
+             float* ppt, int nthreads);
+
+const char* kor_rate_names(void);   // comma-separated, 36 names (M:2963-3120)
+
+// M:4598-4717 helpers, exposed for known-answer tests
+float kor_rslf(float p, float t);
+float kor_rsif(float p, float t);
+float kor_gammln(float x);
+float kor_wgamma(float x);
+float kor_gammp(float a, float x);
+int   kor_decade_index(float x, int n2, int ntb);   // M:1762-1774 pattern
+
+#ifdef __cplusplus
+}
+#endif
