@@ -1,0 +1,108 @@
+/* kidmp.h - C ABI of the B200-native Thompson microphysics step for the KiD kinematic driver.
+ *
+ * Reference files (read-only upstream):
+ *   M: = module_mp_thompson09n.f90      I: = mphys_thompson09n.f90
+ * The Fortran host keeps `module mphys_thompson09n` / `mphys_thompson09_interfacen` (I:9, I:28) and
+ * binds these entry points through iso_c_binding (kid_b200/fortran/mphys_thompson09n.f90,
+ * INTEGRATION.md).  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Conventions
+ *   - all reals are IEEE f32 (the reference's default REAL), sums returned by kidmp_diag are f64
+ *   - nine prognostic fields, always in this order (M:1168-1170 minus the aerosol/nc inputs):
+ *       0 qv  1 qc  2 qi  3 qr  4 qs  5 qg  6 ni  7 nr  8 t      (t = temperature in K, I:60)
+ *   - layouts of a field holding ncol columns of nz levels (level 0 = lowest, kts):
+ *       KIDMP_K_FASTEST   a[col*nz + k]   KiD's (k,i) arrays (I:33-35, column_variables)
+ *       KIDMP_COL_FASTEST a[k*ncol + col] WRF/MPAS (i,k,j) order (M:806-853); the device layout
+ *   - precipitation ppt is [4][ncol]: 0 rain, 1 ice, 2 snow, 3 graupel  (I:162-177); it is
+ *     OVERWRITTEN with this step's amounts (the reference zeroes its accumulators per call, I:55-58)
+ *   - every function returns 0 on success, non-zero on error; kidmp_last_error() has the text.
+ *     Nothing here prints, exits or throws.  No CPU fallback exists: without a CUDA device
+ *     kidmp_init fails.
+ */
+#ifndef KIDMP_H
+#define KIDMP_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KIDMP_NFIELDS 9
+#define KIDMP_K_FASTEST 0
+#define KIDMP_COL_FASTEST 1
+#define KIDMP_NDIAG 8
+#define KIDMP_NRATES 36
+
+typedef struct kidmp_handle kidmp_handle;
+
+/* Host switches read by the reference at init (M:20-22, M:381, M:773) */
+typedef struct kidmp_config {
+  float set_Nc;            /* namelists:set_Nc, cloud droplets per cm^3 (M:381)                  */
+  int iiwarm;              /* namelists:iiwarm, warm-rain only (M:773, M:1545, M:1749 ...)       */
+  int l_sediment;          /* switches:l_sediment, gates ice/snow/graupel fall (M:3449,3506,3555)*/
+  int wp_double;           /* kind of DFLOAT() in the bin grids (M:8, M:616); 0 = f32 (default)  */
+  int device;              /* CUDA device ordinal                                                */
+  int reuse_tables;        /* switches:l_reuse_thompson_lookup (M:3720): read table_cache_path   */
+  const char* table_cache_path; /* binary cache of the lookup tables, may be NULL (M:3710-3728)  */
+} kidmp_config;
+
+/* replaces thompson_init (M:374-797): constants on the host, every lookup table built by CUDA
+ * kernels on the device (or read from the binary cache). */
+int kidmp_init(const kidmp_config* cfg, kidmp_handle** out);
+int kidmp_finalize(kidmp_handle* h);
+const char* kidmp_last_error(const kidmp_handle* h);   /* h may be NULL: last init error */
+double kidmp_table_build_ms(const kidmp_handle* h);    /* device time of the table-build kernels */
+
+/* lookup tables and init constants by their reference names ("tcg_racg", "t_Efrw", "crg", ...),
+ * Fortran column-major order (M:386-423).  For parity tests and the table cache. */
+long kidmp_table_size(const kidmp_handle* h, const char* name);
+int kidmp_get_table(const kidmp_handle* h, const char* name, double* out, long n);
+int kidmp_save_tables(const kidmp_handle* h, const char* path);
+
+/* exact single-column twin of mp_thompson (M:1156-1162): host arrays of nz, in place; ppt4 is
+ * rain, ice, snow, graupel and is ACCUMULATED into like the reference's INOUT scalars (M:1172). */
+int kidmp_column(kidmp_handle* h, int nz, float dt,
+                 float* qv, float* qc, float* qi, float* qr, float* qs, float* qg,
+                 float* ni, float* nr, float* t,
+                 const float* p, const float* dz, float* ppt4);
+
+/* the body of `do i = 1, nx` (I:54-246) for ncol independent columns: host arrays in, host
+ * arrays out (H2D, kernels, D2H inside the call).  dz is one shared vector of nz (I:63). */
+int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout,
+               float* const fields[KIDMP_NFIELDS], const float* p, const float* dz, float* ppt);
+
+/* device-resident state: upload once, step many times, download when needed */
+int kidmp_state_alloc(kidmp_handle* h, long ncol, int nz);
+int kidmp_upload(kidmp_handle* h, int layout, const float* const fields[KIDMP_NFIELDS],
+                 const float* p, const float* dz);
+int kidmp_step_resident(kidmp_handle* h, float dt);
+int kidmp_download(kidmp_handle* h, int layout, float* const fields[KIDMP_NFIELDS], float* ppt);
+
+/* same step on caller-owned DEVICE buffers in KIDMP_COL_FASTEST layout, enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = the handle's stream).  Does not synchronise. */
+int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt,
+                      float* const d_fields[KIDMP_NFIELDS], const float* d_p, const float* d_dz,
+                      float* d_ppt, void* stream);
+
+/* optional per-level process-rate buffer (the 36 save_dg rates of M:2963-3120): device buffer
+ * [36][nz][ncol] f32, NULL switches it off (default).  Names: kidmp_rate_names(). */
+int kidmp_set_rates_buffer(kidmp_handle* h, float* d_rates);
+const char* kidmp_rate_names(void);
+
+/* domain sums accumulated by the sedimentation kernel since the last call (f64, this device):
+ * 0 rain 1 ice 2 snow 3 graupel surface precipitation [sum over columns of ppt],
+ * 4 liquid water path 5 ice water path [kg m^-2 summed over columns], 6 active columns,
+ * 7 columns processed.  Multi-GPU hosts all-reduce these 8 numbers (NCCL, 64 bytes). */
+int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]);
+
+/* bookkeeping for benchmarks */
+long kidmp_gpu_launches(const kidmp_handle* h);         /* kernels launched so far          */
+int kidmp_sync(kidmp_handle* h);                        /* wait for the handle's stream     */
+int kidmp_last_step_ms(kidmp_handle* h, float* step_ms);  /* CUDA events around the last step */
+int kidmp_tables_from_cache(const kidmp_handle* h);     /* 1 if init read the table cache   */
+void* kidmp_stream(kidmp_handle* h);                    /* the handle's cudaStream_t        */
+/* device pointers of the resident state ([nz][ncol] each), for callers that fill it on the device */
+int kidmp_device_state(kidmp_handle* h, float* d_fields[KIDMP_NFIELDS], float** d_p, float** d_dz, float** d_ppt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

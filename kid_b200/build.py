@@ -1,0 +1,56 @@
+"""Build kid_b200/libkidmp.so (the C-ABI library of include/kidmp.h) in-tree with nvcc for sm_100a.
+
+The .so is git-ignored but travels to the GPU box with the repo snapshot.  Flags that matter for
+parity (DESIGN.md "Arithmetic"): -fmad=false (no FMA contraction, like gfortran on x86-64),
+IEEE division / sqrt and no flush-to-zero (nvcc defaults, restated explicitly).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libkidmp.so")
+SOURCES = ["kidmp_api.cu"]
+DEPS = ["kidmp_api.cu", "kidmp_column.cuh", "kidmp_tables.cuh", "kidmp_math.cuh", "kidmp_hostinit.h",
+        "kidmp_internal.h", os.path.join("..", "..", "include", "kidmp.h")]
+
+
+def nvcc_path():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def flags(extra=()):
+    return ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+            "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fno-fast-math", "-shared", "-lcudart",
+            *extra]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False, extra=()):
+    """Compile if any source is newer than the library.  Returns the library path."""
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc_path(), *flags(extra), "-o", LIB + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    os.replace(LIB + ".tmp", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose="-v" in sys.argv)
+    print(LIB)

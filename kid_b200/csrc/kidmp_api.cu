@@ -1,0 +1,545 @@
+// kidmp_api.cu - the C ABI of include/kidmp.h over the CUDA kernels.
+// One translation unit: kidmp_tables.cuh (K3 table build) + kidmp_column.cuh (K1+K2 column step).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see kid_b200/build.py).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <map>
+#include <mutex>
+#include "kidmp_internal.h"
+#include "kidmp_hostinit.h"
+#include "kidmp_tables.cuh"
+#include "kidmp_column.cuh"
+
+using namespace kidmp;
+
+struct kidmp_handle {
+  kidmp_config cfg;
+  std::string cache_path;
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  KConst kc;
+  HostBins hb;
+  TableSet tabs{};
+  float table_ms = 0.f;
+  bool tables_from_cache = false;
+  long launches = 0;
+  std::string err;
+  // resident state
+  long ncol = 0; int nz = 0;
+  float* d_state = nullptr;      // [9][nz][ncol] fields, then p [nz][ncol]
+  float* d_dz = nullptr;         // [nz]
+  float* d_ppt = nullptr;        // [4][ncol]
+  float* d_stage = nullptr;      // staging for layout conversion, [nz][ncol]
+  double* d_partial = nullptr; long partial_blocks = 0;
+  double* d_diag = nullptr;
+  float* d_rates = nullptr;
+  float last_ms = 0.f;
+  std::map<std::string, std::vector<double>> consts;   // named init constants for parity tests
+};
+
+namespace {
+
+std::string g_init_error;
+const kidmp_handle* g_const_owner = nullptr;
+std::mutex g_mu;
+
+int fail(kidmp_handle* h, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (h) h->err = buf; else g_init_error = buf;
+  return 1;
+}
+#define CK(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+template <class T> cudaError_t to_dev(const std::vector<T>& v, const T** out, std::vector<void*>& keep) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, v.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  keep.push_back(p);
+  *out = (const T*)p;
+  return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+template <class T> cudaError_t to_dev(const T* v, size_t n, const T** out, std::vector<void*>& keep) {
+  return to_dev(std::vector<T>(v, v + n), out, keep);
+}
+
+uint64_t fnv(const void* p, size_t n, uint64_t h) {
+  const unsigned char* c = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+  return h;
+}
+// everything the table builders read: a cache written under other constants is refused
+uint64_t table_key(const kidmp_handle* h) {
+  uint64_t k = 1469598103934665603ull;
+  k = fnv(&h->hb, sizeof h->hb, k);
+  k = fnv(h->kc.cre, sizeof h->kc.cre, k); k = fnv(h->kc.crg, sizeof h->kc.crg, k);
+  k = fnv(h->kc.cge, sizeof h->kc.cge, k); k = fnv(h->kc.cgg, sizeof h->kc.cgg, k);
+  k = fnv(h->kc.cse, sizeof h->kc.cse, k); k = fnv(h->kc.cie, sizeof h->kc.cie, k);
+  k = fnv(h->kc.ccg, sizeof h->kc.ccg, k);
+  const int iw = h->kc.iiwarm; k = fnv(&iw, sizeof iw, k);
+  return k ^ 0x6b69646d70743031ull;   // format tag "kidmpt01"
+}
+struct TabDesc { const void* base; long n; int stride; int member; bool f32; };
+bool find_table(const kidmp_handle* h, const std::string& name, TabDesc& d) {
+  static const char* g6[] = {"tcg_racg", "tmr_racg", "tcr_gacr", "tmg_gacr", "tnr_racg", "tnr_gacr"};
+  static const char* s12[] = {"tcs_racs1", "tmr_racs1", "tcs_racs2", "tmr_racs2", "tcr_sacr1", "tms_sacr1",
+                              "tcr_sacr2", "tms_sacr2", "tnr_racs1", "tnr_racs2", "tnr_sacr1", "tnr_sacr2"};
+  static const char* f4[] = {"tpi_qrfz", "tpg_qrfz", "tni_qrfz", "tnr_qrfz"};
+  static const char* c2[] = {"tpi_qcfz", "tni_qcfz"};
+  static const char* i3[] = {"tps_iaus", "tni_iaus", "tpi_ide"};
+  for (int q = 0; q < G_N; ++q) if (name == g6[q]) { d = {h->tabs.racg, N_RACG, G_N, q, false}; return true; }
+  for (int q = 0; q < S_N; ++q) if (name == s12[q]) { d = {h->tabs.racs, N_RACS, S_N, q, false}; return true; }
+  for (int q = 0; q < F_N; ++q) if (name == f4[q]) { d = {h->tabs.qrfz, N_QRFZ, F_N, q, false}; return true; }
+  for (int q = 0; q < C_N; ++q) if (name == c2[q]) { d = {h->tabs.qcfz, N_QCFZ, C_N, q, false}; return true; }
+  for (int q = 0; q < I_N; ++q) if (name == i3[q]) { d = {h->tabs.iaus, N_IAUS, I_N, q, false}; return true; }
+  if (name == "t_Efrw") { d = {h->tabs.efrw, N_EF, 1, 0, true}; return true; }
+  if (name == "t_Efsw") { d = {h->tabs.efsw, N_EF, 1, 0, true}; return true; }
+  return false;
+}
+
+void publish_constants(kidmp_handle* h) {
+  const KConst& k = h->kc;
+  auto put = [&](const char* n, const float* a, int c) { h->consts[n] = std::vector<double>(a, a + c); };
+  auto putd = [&](const char* n, const double* a, int c) { h->consts[n] = std::vector<double>(a, a + c); };
+  put("cre", k.cre, 13); put("crg", k.crg, 13); put("cse", k.cse, 18); put("csg", k.csg, 18);
+  put("cge", k.cge, 12); put("cgg", k.cgg, 12); put("cie", k.cie, 7); put("cig", k.cig, 7);
+  for (int q = 0; q < 5; ++q) {
+    put(("cce" + std::to_string(q + 1)).c_str(), k.cce[q], 15);
+    put(("ccg" + std::to_string(q + 1)).c_str(), k.ccg[q], 15);
+  }
+  put("ocg1", k.ocg1, 15); put("ocg2", k.ocg2, 15);
+  const float sc[] = {k.Nt_c, k.Sc3, k.D0i, k.xm0s, k.xm0g, k.rho_not, k.t1_qr_qc, k.t1_qr_qi, k.t2_qr_qi, k.t1_qg_qc,
+                      k.t1_qs_qc, k.t1_qs_qi, k.t1_qr_ev, k.t2_qr_ev, k.t1_qs_sd, k.t2_qs_sd, k.t1_qg_sd, k.t2_qg_sd,
+                      k.t1_qs_me, k.t2_qs_me, k.t1_qg_me, k.t2_qg_me, k.oig1, k.oig2, k.obmi, k.ore1, k.org1, k.org2,
+                      k.org3, k.obmr, k.oams, k.obms, k.ocms, k.oge1, k.ogg1, k.ogg2, k.ogg3, k.oamg, k.obmg, k.ocmg,
+                      k.am_r, k.am_g, k.am_i};
+  put("scalars", sc, (int)(sizeof sc / sizeof sc[0]));
+  const float of[] = {(float)k.nic1, (float)k.nic2, (float)k.nii2, (float)k.nii3, (float)k.nir2, (float)k.nir3,
+                      (float)k.nis2, (float)k.nig2, (float)k.nig3, (float)k.niIN2};
+  put("offsets", of, 10);
+  const HostBins& b = h->hb;
+  putd("Dc", b.Dc, NBINS); putd("Di", b.Di, NBINS); putd("Dr", b.Dr, NBINS); putd("Ds", b.Ds, NBINS); putd("Dg", b.Dg, NBINS);
+  putd("t_Nc", b.t_Nc, NBINS); putd("dtc", b.dtc, NBINS); putd("dti", b.dti, NBINS); putd("dtr", b.dtr, NBINS);
+  putd("dts", b.dts, NBINS); putd("dtg", b.dtg, NBINS);
+}
+
+struct TabAlloc { void** p; size_t bytes; };
+std::vector<TabAlloc> table_allocs(kidmp_handle* h) {
+  return {{(void**)&h->tabs.racg, (size_t)N_RACG * G_N * 8}, {(void**)&h->tabs.racs, (size_t)N_RACS * S_N * 8},
+          {(void**)&h->tabs.qrfz, (size_t)N_QRFZ * F_N * 8}, {(void**)&h->tabs.qcfz, (size_t)N_QCFZ * C_N * 8},
+          {(void**)&h->tabs.iaus, (size_t)N_IAUS * I_N * 8}, {(void**)&h->tabs.efrw, (size_t)N_EF * 4},
+          {(void**)&h->tabs.efsw, (size_t)N_EF * 4}};
+}
+
+int load_cache(kidmp_handle* h) {   // 0 = loaded
+  FILE* f = fopen(h->cache_path.c_str(), "rb");
+  if (!f) return 1;
+  uint64_t key = 0;
+  bool ok = fread(&key, 8, 1, f) == 1 && key == table_key(h);
+  std::vector<char> buf;
+  for (auto& a : table_allocs(h)) {
+    if (!ok) break;
+    buf.resize(a.bytes);
+    ok = fread(buf.data(), 1, a.bytes, f) == a.bytes &&
+         cudaMemcpy(*a.p, buf.data(), a.bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  fclose(f);
+  return ok ? 0 : 1;
+}
+
+int build_device_tables(kidmp_handle* h, const hostinit::Prep& pp) {
+  std::vector<void*> keep;
+  TablePrep tp{};
+  TableScratch sc{};
+  cudaError_t e = cudaSuccess;
+  auto up = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  up(to_dev(pp.lamr, &tp.lamr, keep)); up(to_dev(pp.N0_r, &tp.N0_r, keep));
+  up(to_dev(pp.lamg, &tp.lamg, keep)); up(to_dev(pp.N0_g, &tp.N0_g, keep));
+  up(to_dev(pp.s_Mrat, &tp.s_Mrat, keep)); up(to_dev(pp.s_M0, &tp.s_M0, keep));
+  up(to_dev(pp.s_slam1, &tp.s_slam1, keep)); up(to_dev(pp.s_slam2, &tp.s_slam2, keep));
+  up(to_dev(pp.lamc, &tp.lamc, keep)); up(to_dev(pp.N0_c, &tp.N0_c, keep));
+  up(to_dev(pp.i_lami, &tp.i_lami, keep)); up(to_dev(pp.i_N0, &tp.i_N0, keep));
+  up(to_dev(pp.i_tpi_ide, &tp.i_tpi_ide, keep)); up(to_dev(pp.i_branch, &tp.i_branch, keep));
+  const HostBins& b = h->hb;
+  up(to_dev(b.Dc, NBINS, &tp.Dc, keep)); up(to_dev(b.dtc, NBINS, &tp.dtc, keep));
+  up(to_dev(b.Di, NBINS, &tp.Di, keep)); up(to_dev(b.dti, NBINS, &tp.dti, keep));
+  up(to_dev(b.Dr, NBINS, &tp.Dr, keep)); up(to_dev(b.dtr, NBINS, &tp.dtr, keep));
+  up(to_dev(b.Ds, NBINS, &tp.Ds, keep)); up(to_dev(b.dts, NBINS, &tp.dts, keep));
+  up(to_dev(b.Dg, NBINS, &tp.Dg, keep)); up(to_dev(b.dtg, NBINS, &tp.dtg, keep));
+  up(to_dev(b.r_r, NTB_R, &tp.r_r, keep)); up(to_dev(b.r_c, NTB_C, &tp.r_c, keep));
+  up(to_dev(b.r_i, NTB_I, &tp.r_i, keep)); up(to_dev(b.Nt_i, NTB_I1, &tp.Nt_i, keep));
+  tp.t_Nc1 = b.t_Nc[0]; tp.nu_c_fz = pp.nu_c_fz; tp.xm0g = h->kc.xm0g; tp.obmr = h->kc.obmr; tp.D0s = KP_D0S;
+  tp.am_r = h->kc.am_r; tp.am_g = h->kc.am_g; tp.am_i = h->kc.am_i; tp.am_s = pp.am_s;
+  memcpy(tp.Texp, pp.Texp, sizeof tp.Texp);
+  const size_t nR = (size_t)NTB_R * NTB_R1 * NBINS, nG = (size_t)NTB_G * NTB_G1 * NBINS, nS = (size_t)NTB_T * NTB_S * NBINS;
+  void* p = nullptr;
+  up(cudaMalloc(&p, nR * 8)); keep.push_back(p); sc.N_r = (double*)p;
+  up(cudaMalloc(&p, nG * 8)); keep.push_back(p); sc.N_g = (double*)p;
+  up(cudaMalloc(&p, nS * 8)); keep.push_back(p); sc.N_s = (double*)p;
+  if (e == cudaSuccess) e = build_tables_dev(tp, h->tabs, sc, !h->kc.iiwarm, h->stream, &h->table_ms, &h->launches);
+  for (void* q : keep) cudaFree(q);
+  if (e != cudaSuccess) return fail(h, "table build: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int ensure_constants(kidmp_handle* h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_const_owner != h) {
+    CK(h, cudaMemcpyToSymbolAsync(ck, &h->kc, sizeof(KConst), 0, cudaMemcpyHostToDevice, h->stream));
+    g_const_owner = h;
+  }
+  return 0;
+}
+
+int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
+  if (a0.nz < 2 || a0.nz > 256) return fail(h, "nz=%d outside [2,256]", a0.nz);
+  if (a0.ncol < 1) return fail(h, "ncol=%ld", a0.ncol);
+  if (!(a0.dt > 0.f)) return fail(h, "dt must be positive");
+  if (ensure_constants(h)) return 1;
+  StepArgs a = a0;
+  const int threads = 128;
+  const long blocks = (a.ncol + threads - 1) / threads;
+  if (blocks > h->partial_blocks) {
+    if (h->d_partial) cudaFree(h->d_partial);
+    h->d_partial = nullptr; h->partial_blocks = 0;
+    CK(h, cudaMalloc((void**)&h->d_partial, (size_t)blocks * KIDMP_NDIAG * 8));
+    h->partial_blocks = blocks;
+  }
+  a.diag_partial = h->d_partial;
+  a.rates = h->d_rates;
+  if (a.nz <= 64) k_column_step<64><<<(unsigned)blocks, threads, 0, s>>>(a);
+  else if (a.nz <= 128) k_column_step<128><<<(unsigned)blocks, threads, 0, s>>>(a);
+  else k_column_step<256><<<(unsigned)blocks, threads, 0, s>>>(a);
+  k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)blocks, h->d_diag);
+  h->launches += 2;
+  CK(h, cudaGetLastError());
+  return 0;
+}
+
+void free_state(kidmp_handle* h) {
+  if (h->d_state) cudaFree(h->d_state);
+  if (h->d_dz) cudaFree(h->d_dz);
+  if (h->d_ppt) cudaFree(h->d_ppt);
+  if (h->d_stage) cudaFree(h->d_stage);
+  h->d_state = h->d_dz = h->d_ppt = h->d_stage = nullptr;
+  h->ncol = 0; h->nz = 0;
+}
+
+inline float* field_ptr(kidmp_handle* h, int q) { return h->d_state + (size_t)q * h->nz * h->ncol; }
+
+StepArgs resident_args(kidmp_handle* h, float dt) {
+  StepArgs a{};
+  a.ncol = h->ncol; a.nz = h->nz; a.dt = dt;
+  for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = field_ptr(h, q);
+  a.p = field_ptr(h, KIDMP_NFIELDS);
+  a.dz = h->d_dz; a.ppt = h->d_ppt;
+  return a;
+}
+
+// host <-> device copy of one field with layout conversion
+int put_field(kidmp_handle* h, int layout, const float* src, float* dst) {
+  const size_t bytes = (size_t)h->ncol * h->nz * 4;
+  if (layout == KIDMP_COL_FASTEST || h->ncol == 1) {
+    CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    CK(h, cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    dim3 g((unsigned)((h->ncol + 31) / 32), (unsigned)((h->nz + 31) / 32)), b(32, 8);
+    k_transpose<<<g, b, 0, h->stream>>>(h->d_stage, dst, h->ncol, h->nz, 1);
+    ++h->launches;
+  }
+  return 0;
+}
+int get_field(kidmp_handle* h, int layout, const float* src, float* dst) {
+  const size_t bytes = (size_t)h->ncol * h->nz * 4;
+  if (layout == KIDMP_COL_FASTEST || h->ncol == 1) {
+    CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    dim3 g((unsigned)((h->ncol + 31) / 32), (unsigned)((h->nz + 31) / 32)), b(32, 8);
+    k_transpose<<<g, b, 0, h->stream>>>(src, h->d_stage, h->ncol, h->nz, 0);
+    ++h->launches;
+    CK(h, cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));   // d_stage is reused by the next field
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
+  if (!cfg || !out) return fail(nullptr, "kidmp_init: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1)
+    return fail(nullptr, "kidmp_init: no CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "kidmp_init: device %d of %d", cfg->device, ndev);
+  if (!(cfg->set_Nc > 0.f)) return fail(nullptr, "kidmp_init: set_Nc must be positive");
+  kidmp_handle* h = new kidmp_handle();
+  h->cfg = *cfg;
+  h->device = cfg->device;
+  if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
+  h->cfg.table_cache_path = nullptr;
+  auto bail = [&](int) { g_init_error = h->err; kidmp_finalize(h); return 1; };
+  if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(1); }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, h->device);
+  if (prop.major < 10) { fail(h, "kidmp_init: built for sm_100a, device is sm_%d%d", prop.major, prop.minor); return bail(1); }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    h->err = "stream/event creation failed"; return bail(1);
+  }
+  memset(&h->kc, 0, sizeof h->kc);
+  memset(&h->hb, 0, sizeof h->hb);
+  hostinit::Prep pp;
+  hostinit::compute(h->cfg, h->kc, h->hb, pp);
+  publish_constants(h);
+  for (auto& a : table_allocs(h)) {
+    if (cudaMalloc(a.p, a.bytes) != cudaSuccess || cudaMemset(*a.p, 0, a.bytes) != cudaSuccess) {
+      h->err = "table allocation failed"; return bail(1);
+    }
+  }
+  if (cudaMalloc((void**)&h->d_diag, KIDMP_NDIAG * 8) != cudaSuccess || cudaMemset(h->d_diag, 0, KIDMP_NDIAG * 8) != cudaSuccess) {
+    h->err = "diag allocation failed"; return bail(1);
+  }
+  bool loaded = false;
+  if (cfg->reuse_tables && !h->cache_path.empty()) loaded = load_cache(h) == 0;   // l_reuse_thompson_lookup, M:3720
+  h->tables_from_cache = loaded;
+  if (!loaded) {
+    if (build_device_tables(h, pp)) return bail(1);
+    if (cfg->reuse_tables && !h->cache_path.empty()) kidmp_save_tables(h, h->cache_path.c_str());
+  }
+  h->kc.racg = h->tabs.racg; h->kc.racs = h->tabs.racs; h->kc.qrfz = h->tabs.qrfz; h->kc.qcfz = h->tabs.qcfz;
+  h->kc.iaus = h->tabs.iaus; h->kc.efrw = h->tabs.efrw; h->kc.efsw = h->tabs.efsw;
+  *out = h;
+  return 0;
+}
+
+int kidmp_finalize(kidmp_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_const_owner == h) g_const_owner = nullptr;
+  }
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_state(h);
+  for (auto& a : table_allocs(h)) if (*a.p) cudaFree(*a.p);
+  if (h->d_partial) cudaFree(h->d_partial);
+  if (h->d_diag) cudaFree(h->d_diag);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_in) cudaStreamDestroy(h->copy_in);
+  if (h->copy_out) cudaStreamDestroy(h->copy_out);
+  delete h;
+  return 0;
+}
+
+const char* kidmp_last_error(const kidmp_handle* h) { return h ? h->err.c_str() : g_init_error.c_str(); }
+double kidmp_table_build_ms(const kidmp_handle* h) { return h ? (double)h->table_ms : -1.0; }
+int kidmp_tables_from_cache(const kidmp_handle* h) { return h && h->tables_from_cache ? 1 : 0; }
+
+long kidmp_table_size(const kidmp_handle* h, const char* name) {
+  if (!h || !name) return -1;
+  TabDesc d;
+  if (find_table(h, name, d)) return d.n;
+  auto it = h->consts.find(name);
+  return it == h->consts.end() ? -1 : (long)it->second.size();
+}
+
+int kidmp_get_table(const kidmp_handle* hc, const char* name, double* out, long n) {
+  kidmp_handle* h = const_cast<kidmp_handle*>(hc);
+  if (!h || !name || !out) return 1;
+  TabDesc d;
+  if (!find_table(h, name, d)) {
+    auto it = h->consts.find(name);
+    if (it == h->consts.end()) return fail(h, "unknown table '%s'", name);
+    for (long i = 0; i < n && i < (long)it->second.size(); ++i) out[i] = it->second[i];
+    return 0;
+  }
+  cudaSetDevice(h->device);
+  CK(h, cudaStreamSynchronize(h->stream));
+  const long m = n < d.n ? n : d.n;
+  if (d.f32) {
+    std::vector<float> tmp(d.n);
+    CK(h, cudaMemcpy(tmp.data(), d.base, (size_t)d.n * 4, cudaMemcpyDeviceToHost));
+    for (long i = 0; i < m; ++i) out[i] = (double)tmp[i];
+  } else {
+    std::vector<double> tmp((size_t)d.n * d.stride);
+    CK(h, cudaMemcpy(tmp.data(), d.base, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    for (long i = 0; i < m; ++i) out[i] = tmp[(size_t)i * d.stride + d.member];
+  }
+  return 0;
+}
+
+int kidmp_save_tables(const kidmp_handle* hc, const char* path) {
+  kidmp_handle* h = const_cast<kidmp_handle*>(hc);
+  if (!h || !path) return 1;
+  cudaSetDevice(h->device);
+  CK(h, cudaStreamSynchronize(h->stream));
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return fail(h, "cannot write %s", tmp.c_str());
+  const uint64_t key = table_key(h);
+  bool ok = fwrite(&key, 8, 1, f) == 1;
+  std::vector<char> buf;
+  for (auto& a : table_allocs(h)) {
+    if (!ok) break;
+    buf.resize(a.bytes);
+    ok = cudaMemcpy(buf.data(), *a.p, a.bytes, cudaMemcpyDeviceToHost) == cudaSuccess &&
+         fwrite(buf.data(), 1, a.bytes, f) == a.bytes;
+  }
+  fclose(f);
+  if (!ok) { remove(tmp.c_str()); return fail(h, "writing %s failed", path); }
+  if (rename(tmp.c_str(), path) != 0) return fail(h, "rename to %s failed", path);
+  return 0;
+}
+
+int kidmp_state_alloc(kidmp_handle* h, long ncol, int nz) {
+  if (!h) return 1;
+  if (ncol < 1 || nz < 2 || nz > 256) return fail(h, "state_alloc: ncol=%ld nz=%d", ncol, nz);
+  cudaSetDevice(h->device);
+  if (h->ncol == ncol && h->nz == nz && h->d_state) return 0;
+  free_state(h);
+  const size_t n = (size_t)ncol * nz;
+  CK(h, cudaMalloc((void**)&h->d_state, n * 4 * (KIDMP_NFIELDS + 1)));
+  CK(h, cudaMalloc((void**)&h->d_stage, n * 4));
+  CK(h, cudaMalloc((void**)&h->d_dz, (size_t)nz * 4));
+  CK(h, cudaMalloc((void**)&h->d_ppt, (size_t)ncol * 4 * 4));
+  CK(h, cudaMemset(h->d_ppt, 0, (size_t)ncol * 4 * 4));
+  h->ncol = ncol; h->nz = nz;
+  return 0;
+}
+
+int kidmp_upload(kidmp_handle* h, int layout, const float* const fields[KIDMP_NFIELDS], const float* p, const float* dz) {
+  if (!h || !h->d_state) return h ? fail(h, "upload before state_alloc") : 1;
+  if (!fields || !p || !dz) return fail(h, "upload: null pointer");
+  cudaSetDevice(h->device);
+  for (int q = 0; q < KIDMP_NFIELDS; ++q) {
+    if (!fields[q]) return fail(h, "upload: field %d is null", q);
+    if (put_field(h, layout, fields[q], field_ptr(h, q))) return 1;
+    if (layout != KIDMP_COL_FASTEST && h->ncol > 1) CK(h, cudaStreamSynchronize(h->stream));
+  }
+  if (put_field(h, layout, p, field_ptr(h, KIDMP_NFIELDS))) return 1;
+  CK(h, cudaMemcpyAsync(h->d_dz, dz, (size_t)h->nz * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int kidmp_step_resident(kidmp_handle* h, float dt) {
+  if (!h || !h->d_state) return h ? fail(h, "step before state_alloc") : 1;
+  cudaSetDevice(h->device);
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  if (launch_step(h, resident_args(h, dt), h->stream)) return 1;
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  return 0;
+}
+
+int kidmp_download(kidmp_handle* h, int layout, float* const fields[KIDMP_NFIELDS], float* ppt) {
+  if (!h || !h->d_state) return h ? fail(h, "download before state_alloc") : 1;
+  cudaSetDevice(h->device);
+  if (fields)
+    for (int q = 0; q < KIDMP_NFIELDS; ++q)
+      if (fields[q] && get_field(h, layout, field_ptr(h, q), fields[q])) return 1;
+  if (ppt) CK(h, cudaMemcpyAsync(ppt, h->d_ppt, (size_t)h->ncol * 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout, float* const fields[KIDMP_NFIELDS],
+               const float* p, const float* dz, float* ppt) {
+  if (!h) return 1;
+  if (kidmp_state_alloc(h, ncol, nz)) return 1;
+  if (kidmp_upload(h, layout, fields, p, dz)) return 1;
+  if (kidmp_step_resident(h, dt)) return 1;
+  return kidmp_download(h, layout, fields, ppt);
+}
+
+int kidmp_column(kidmp_handle* h, int nz, float dt, float* qv, float* qc, float* qi, float* qr, float* qs, float* qg,
+                 float* ni, float* nr, float* t, const float* p, const float* dz, float* ppt4) {
+  if (!h) return 1;
+  if (!ppt4) return fail(h, "column: ppt4 is null");
+  float* f[KIDMP_NFIELDS] = {qv, qc, qi, qr, qs, qg, ni, nr, t};
+  float inc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (kidmp_step(h, 1, nz, dt, KIDMP_K_FASTEST, f, p, dz, inc)) return 1;
+  for (int q = 0; q < 4; ++q) ppt4[q] = ppt4[q] + inc[q];   // INOUT accumulators, M:1172
+  return 0;
+}
+
+int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt, float* const d_fields[KIDMP_NFIELDS],
+                      const float* d_p, const float* d_dz, float* d_ppt, void* stream) {
+  if (!h) return 1;
+  if (!d_fields || !d_p || !d_dz || !d_ppt) return fail(h, "step_device: null pointer");
+  cudaSetDevice(h->device);
+  StepArgs a{};
+  a.ncol = ncol; a.nz = nz; a.dt = dt;
+  for (int q = 0; q < KIDMP_NFIELDS; ++q) { if (!d_fields[q]) return fail(h, "step_device: field %d is null", q); a.f[q] = d_fields[q]; }
+  a.p = d_p; a.dz = d_dz; a.ppt = d_ppt;
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  if (s == h->stream) CK(h, cudaEventRecord(h->ev0, s));
+  if (launch_step(h, a, s)) return 1;
+  if (s == h->stream) CK(h, cudaEventRecord(h->ev1, s));
+  return 0;
+}
+
+int kidmp_set_rates_buffer(kidmp_handle* h, float* d_rates) {
+  if (!h) return 1;
+  h->d_rates = d_rates;
+  return 0;
+}
+
+const char* kidmp_rate_names(void) {
+  return "pri_inu,pri_ide,prs_ide,prs_sde,prg_gde,pri_wfz,prs_scw,prg_scw,prg_gcw,pri_ihm,pri_rfz,prs_iau,"
+         "prs_sci,pri_rci,pni_inu,pni_ihm,pni_wfz,pni_rfz,pni_ide,pni_iau,pni_sci,pni_rci,prr_sml,prr_gml,"
+         "pnr_rcs,pnr_rcg,pnr_rci,pnr_sml,pnr_gml,pnr_rfz,prr_wau,prr_rcw,prv_rev,pnr_wau,pnr_rev,pnr_rcr";
+}
+
+int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
+  if (!h || !out) return 1;
+  cudaSetDevice(h->device);
+  CK(h, cudaMemcpyAsync(out, h->d_diag, KIDMP_NDIAG * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemsetAsync(h->d_diag, 0, KIDMP_NDIAG * 8, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+long kidmp_gpu_launches(const kidmp_handle* h) { return h ? h->launches : 0; }
+
+int kidmp_sync(kidmp_handle* h) {
+  if (!h) return 1;
+  cudaSetDevice(h->device);
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int kidmp_last_step_ms(kidmp_handle* h, float* step_ms) {
+  if (!h || !step_ms) return 1;
+  cudaSetDevice(h->device);
+  CK(h, cudaEventSynchronize(h->ev1));
+  CK(h, cudaEventElapsedTime(step_ms, h->ev0, h->ev1));
+  return 0;
+}
+
+void* kidmp_stream(kidmp_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int kidmp_device_state(kidmp_handle* h, float* d_fields[KIDMP_NFIELDS], float** d_p, float** d_dz, float** d_ppt) {
+  if (!h || !h->d_state) return h ? fail(h, "device_state before state_alloc") : 1;
+  for (int q = 0; q < KIDMP_NFIELDS; ++q) if (d_fields) d_fields[q] = field_ptr(h, q);
+  if (d_p) *d_p = field_ptr(h, KIDMP_NFIELDS);
+  if (d_dz) *d_dz = h->d_dz;
+  if (d_ppt) *d_ppt = h->d_ppt;
+  return 0;
+}
+
+}  // extern "C"

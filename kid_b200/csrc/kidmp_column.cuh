@@ -1,0 +1,1216 @@
+// kidmp_column.cuh - K1+K2: the Thompson column step, one thread per column.
+//
+// Replaces the body of `do i = 1, nx` around `call mp_thompson` (I:54-246) and mp_thompson itself
+// (M:1156-3688).  Data layout: every field is [nz][ncol] f32 (columns fastest), so the 32 lanes
+// of a warp read 128 contiguous bytes per level.
+//
+// Structure (DESIGN.md "Column kernel"):
+//   pass 0  one bottom-up read of the ten fields decides `no_micro` (M:1396-1521, the early
+//           RETURN at M:1540); clear-sky columns only write back the species <= R1 that the
+//           reference zeroes in the caller's arrays (M:1412-1489) and leave.
+//   pass 1  ONE top-down sweep does stages S1..S13 of SURVEY.md section 3.2 level by level: every
+//           vertical dependency of the scheme runs from the top (graupel N0 running minimum
+//           M:1648, `k_0` M:1635, fall-speed carry-down M:3235) so it is carried in registers.
+//           Per-level results that sedimentation needs are parked in per-thread local arrays.
+//   pass 2  sub-stepped upwind sedimentation (M:3365-3578), instant melt/freeze (M:3584-3606),
+//           apply tendencies and final clamps (M:3623-3686), coalesced stores, block-reduced
+//           domain sums.
+#pragma once
+#include "kidmp_internal.h"
+#include "kidmp_math.cuh"
+
+namespace kidmp {
+
+__constant__ KConst ck;
+
+#define R1 KP_R1
+#define R2 KP_R2
+#define EPSF KP_EPS
+#define T_0 KP_T_0
+#define D0r KP_D0R
+#define D0c KP_D0C
+#define D0s KP_D0S
+#define D0g KP_D0G
+
+// Field et al. (2005) moment relation coefficients, M:305-312
+__device__ __constant__ float c_sa[11] = {0, 5.065339f, -0.062659f, -3.032362f, 0.029469f, -0.000285f,
+                                          0.31255f, 0.000204f, 0.003199f, 0.0f, -0.015952f};
+__device__ __constant__ float c_sb[11] = {0, 0.476221f, -0.015896f, 0.165977f, 0.007468f, -0.000141f,
+                                          0.060366f, 0.000079f, 0.000594f, 0.0f, -0.003577f};
+
+// loga_/b_ for moment order c at tc0, M:1590-1599 (term order kept)
+__device__ __forceinline__ void field_ab(float tc0, float c, float& loga_, float& b_) {
+  const float* sa = c_sa; const float* sb = c_sb;
+  loga_ = sa[1] + sa[2] * tc0 + sa[3] * c + sa[4] * tc0 * c + sa[5] * tc0 * tc0 + sa[6] * c * c
+          + sa[7] * tc0 * tc0 * c + sa[8] * tc0 * c * c + sa[9] * tc0 * tc0 * tc0 + sa[10] * c * c * c;
+  b_ = sb[1] + sb[2] * tc0 + sb[3] * c + sb[4] * tc0 * c + sb[5] * tc0 * tc0 + sb[6] * c * c
+       + sb[7] * tc0 * tc0 * c + sb[8] * tc0 * c * c + sb[9] * tc0 * tc0 * tc0 + sb[10] * c * c * c;
+}
+__device__ __forceinline__ float field_moment(float tc0, float c, float smo2) {
+  float loga_, b_;
+  field_ab(tc0, c, loga_, b_);
+  return pow10_f(loga_) * pow_f(smo2, b_);
+}
+
+// decade-mantissa table index, M:1762-1774 (f32) / M:1824-1833 (f64 argument).  The reference
+// starts its three-candidate search at NINT(log10 x); the candidate that matches does not depend
+// on how that logarithm rounds, so a bit-level estimate is enough.
+__device__ __forceinline__ int decade_guess(float x) {
+  const int b = __float_as_int(x);
+  const float l2 = (float)((b >> 23) - 127) + __int_as_float((b & 0x007fffff) | 0x3f800000) - 1.0f;
+  return __float2int_rn(l2 * 0.30103f);
+}
+__device__ __forceinline__ int decade_idx_f(float x, int n2, int ntb) {
+  const int n0 = decade_guess(x);
+  int n = n0 + 1;
+#pragma unroll
+  for (int nn = -1; nn <= 1; ++nn) {
+    const float q = x / ck.p10[n0 + nn + 32];
+    if (q >= 1.0f && q < 10.0f) { n = n0 + nn; break; }
+  }
+  const int idx = (int)(x / ck.p10[n + 32]) + 9 * (n - n2);
+  return max(1, min(idx, ntb));
+}
+__device__ __forceinline__ int decade_idx_d(double x, int n2, int ntb) {
+  const int n0 = decade_guess((float)x);
+  int n = n0 + 1;
+#pragma unroll
+  for (int nn = -1; nn <= 1; ++nn) {
+    const double q = x / (double)ck.p10[n0 + nn + 32];
+    if (q >= 1.0 && q < 10.0) { n = n0 + nn; break; }
+  }
+  const int idx = (int)(x / (double)ck.p10[n + 32]) + 9 * (n - n2);
+  return max(1, min(idx, ntb));
+}
+
+// rain number from mass at a clamped median volume diameter, M:1452-1454
+__device__ __forceinline__ float nr_from_mvd(float rr, float mvd_r) {
+  const double lamr = (double)((3.0f + 0.0f + 0.672f) / mvd_r);
+  return (float)((double)(ck.crg[1] * ck.org3 * rr) * cube_d(lamr) / (double)ck.am_r);
+}
+// lamr = (am_r*crg(3)*org2*nr/rr)**obmr, M:1457
+__device__ __forceinline__ double rain_lam(float nr, float rr) {
+  return (double)pow_f(ck.am_r * ck.crg[2] * ck.org2 * nr / rr, ck.obmr);
+}
+__device__ __forceinline__ double ice_lam(float ni, float ri) {   // M:1429
+  return (double)pow_f(ck.am_i * ck.cig[1] * ck.oig1 * ni / ri, ck.obmi);
+}
+
+// graupel intercept at one level given the running minimum from above, M:1639-1653
+__device__ __forceinline__ void graupel_n0(bool above_k0, bool L_qr, float mvd_r, float rg, double& N0_min,
+                                           double& ilamg, double& N0_g) {
+  float xslw1 = 0.01f;
+  if (above_k0 && L_qr && mvd_r > 100.E-6f) xslw1 = 4.01f + log10_f(mvd_r);
+  const float ygra1 = 4.31f + log10_f(fmaxf(5.E-5f, rg));
+  const float zans1 = 3.1f + (100.f / (300.f * xslw1 * ygra1 / (10.f / xslw1 + 1.f + 0.25f * ygra1) + 30.f + 10.f * ygra1));
+  double N0_exp = (double)pow10_f(zans1);
+  N0_exp = fmax((double)KP_GONV_MIN, fmin(N0_exp, (double)KP_GONV_MAX));
+  N0_min = fmin(N0_exp, N0_min);
+  N0_exp = N0_min;
+  const double lam_exp = sqrt(sqrt(N0_exp * (double)ck.am_g * (double)ck.cgg[0] / (double)rg));   // **oge1, oge1 = 1/4
+  const double lamg = lam_exp * (double)pow_f(ck.cgg[2] * ck.ogg2 * ck.ogg1, ck.obmg);
+  ilamg = (double)1.f / lamg;
+  N0_g = N0_exp / ((double)ck.cgg[1] * lam_exp) * lamg;                                         // lamg**cge(2), cge(2) = 1
+}
+
+struct ColPtrs {
+  float* f[KIDMP_NFIELDS];   // qv qc qi qr qs qg ni nr t
+  const float* p;
+};
+enum { F_QV = 0, F_QC, F_QI, F_QR, F_QS, F_QG, F_NI, F_NR, F_T };
+
+template <int NZMAX>
+__global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
+  const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = col < a.ncol;
+  const int nz = a.nz;
+  const long ncol = a.ncol;
+  const float DT = a.dt;
+  const float odt = 1.f / DT, odts = 1.f / DT;
+  const float Nt_c = ck.Nt_c;
+  const bool iiwarm = ck.iiwarm != 0;
+  float ppt_r = 0.f, ppt_i = 0.f, ppt_s = 0.f, ppt_g = 0.f;
+  double lwp = 0.0, iwp = 0.0;
+  bool active = false;
+
+  if (in_range) {
+    const float* __restrict__ Gp = a.p + col;
+    float* Gqv = a.f[F_QV] + col; float* Gqc = a.f[F_QC] + col; float* Gqi = a.f[F_QI] + col;
+    float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
+    float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
+
+    // ---- pass 0: no_micro, M:1396-1521 --------------------------------------------------------
+    bool no_micro = true;
+#pragma unroll 4
+    for (int k = 0; k < nz; ++k) {
+      const long o = (long)k * ncol;
+      const float qc = Gqc[o], qi = Gqi[o], qr = Gqr[o], qs = Gqs[o], qg = Gqg[o];
+      const float ni = Gni[o], nr = Gnr[o];
+      const float t = Gt[o], pr = Gp[o], qv = fmaxf(1.E-10f, Gqv[o]);
+      if (qc > R1 || qi > R1 || qr > R1 || qs > R1 || qg > R1) no_micro = false;
+      // species at or below R1 are zeroed in the caller's arrays before the early return (U9)
+      if (!(qc > R1) && qc != 0.0f) Gqc[o] = 0.0f;
+      if (!(qi > R1) && (qi != 0.0f || ni != 0.0f)) { Gqi[o] = 0.0f; Gni[o] = 0.0f; }
+      if (!(qr > R1) && (qr != 0.0f || nr != 0.0f)) { Gqr[o] = 0.0f; Gnr[o] = 0.0f; }
+      if (!(qs > R1) && qs != 0.0f) Gqs[o] = 0.0f;
+      if (!(qg > R1) && qg != 0.0f) Gqg[o] = 0.0f;
+      const float tempc = t - 273.15f;
+      const float qvsi = (tempc <= 0.0f) ? rsif(pr, t) : rslf(pr, t);
+      float ssati = qv / qvsi - 1.f;
+      if (fabsf(ssati) < EPSF) ssati = 0.0f;
+      if (ssati > 0.0f) no_micro = false;
+    }
+    active = !no_micro;
+
+    if (active) {
+      // per-level values handed from pass 1 to pass 2 (thread-private, cached in L1/L2)
+      float tten[NZMAX], qvten[NZMAX], qcten[NZMAX], qiten[NZMAX], qrten[NZMAX], qsten[NZMAX], qgten[NZMAX],
+          niten[NZMAX], nrten[NZMAX], ncten[NZMAX];
+      float a_rr[NZMAX], a_nr[NZMAX], a_ri[NZMAX], a_ni[NZMAX], a_rs[NZMAX], a_rg[NZMAX];
+      float vtrk[NZMAX], vtnrk[NZMAX], vtik[NZMAX], vtnik[NZMAX], vtsk[NZMAX], vtgk[NZMAX];
+      float a_rho[NZMAX], a_temp[NZMAX], a_ocp[NZMAX], a_lvap[NZMAX];
+
+      // carried from the level above
+      double N0_min_a = (double)KP_GONV_MAX, N0_min_b = (double)KP_GONV_MAX;
+      bool warm_above_a = false, warm_above_b = false;     // any level >= k with temp >= 270.65 (k_0, M:1635)
+      float vtr_up = 0.f, vtnr_up = 0.f, vti_up = 0.f, vtni_up = 0.f, vts_up = 0.f, vtg_up = 0.f;
+      int nstep_r = 0, nstep_i = 0, nstep_s = 0, nstep_g = 0;
+      int ksed_r = 1, ksed_i = 1, ksed_s = 1, ksed_g = 1;   // 1-based like the reference
+
+      // ================= pass 1: top-down, S1..S13 per level ====================================
+#pragma unroll 1
+      for (int k = nz - 1; k >= 0; --k) {
+        const long o = (long)k * ncol;
+        const float t1d = Gt[o], qv1d = Gqv[o], pres = Gp[o];
+        float qc1d = Gqc[o], qi1d = Gqi[o], qr1d = Gqr[o], qs1d = Gqs[o], qg1d = Gqg[o];
+        float ni1d = Gni[o], nr1d = Gnr[o];
+        const float dzq = a.dz[k];
+        // U1: nc1d as the WRF driver sets it when the scheme is not aerosol aware, M:957-964
+        float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));
+
+        // rates, M:1184-1211 (zeroed M:1282-1363)
+        double prw_vcd = 0., pnc_wcd = 0., pnc_wau = 0., pnc_rcw = 0., pnc_scw = 0., pnc_gcw = 0.;
+        double prv_rev = 0., prr_wau = 0., prr_rcw = 0., prr_rcs = 0., prr_rcg = 0., prr_sml = 0., prr_gml = 0., prr_rci = 0.;
+        double pnr_wau = 0., pnr_rcs = 0., pnr_rcg = 0., pnr_rci = 0., pnr_sml = 0., pnr_gml = 0., pnr_rev = 0., pnr_rcr = 0., pnr_rfz = 0.;
+        double pri_inu = 0., pni_inu = 0., pri_ihm = 0., pni_ihm = 0., pri_wfz = 0., pni_wfz = 0., pri_rfz = 0., pni_rfz = 0.;
+        double pri_ide = 0., pni_ide = 0., pri_rci = 0., pni_rci = 0., pni_sci = 0., pni_iau = 0.;
+        double prs_iau = 0., prs_sci = 0., prs_rcs = 0., prs_scw = 0., prs_sde = 0., prs_ihm = 0., prs_ide = 0.;
+        double prg_scw = 0., prg_rfz = 0., prg_gde = 0., prg_gcw = 0., prg_rci = 0., prg_rcs = 0., prg_rcg = 0., prg_ihm = 0.;
+        float smo0 = 0.f, smo1 = 0.f, smob = 0.f, smoc = 0.f, smoe = 0.f, smof = 0.f;
+        float mvd_r = 0.f, mvd_c = 0.f, vts_boost = 0.f;
+        double ilamg = 0., N0_g = 0., ilamr, N0_r, lamr, lamc = 0., lami, ilami;
+        int nu_c = 0;
+        float xDc = 0.f;
+
+        // ---- S1, M:1387-1493 -------------------------------------------------------------------
+        float temp = t1d;
+        float qv = fmaxf(1.E-10f, qv1d);
+        float rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+        float rc, nc, ri, ni, rr, nr, rs, rg;
+        bool L_qc, L_qi, L_qr, L_qs, L_qg;
+        if (qc1d > R1) {
+          rc = qc1d * rho;
+          L_qc = true;
+          nc = Nt_c;   // the lamc/xDc clamps of M:1399-1408 only feed nc, overwritten at M:1410
+        } else {
+          qc1d = 0.0f; nc1d = 0.0f; rc = R1; nc = 2.f; L_qc = false;
+        }
+        if (qi1d > R1) {
+          ri = qi1d * rho;
+          ni = fmaxf(R2, ni1d * rho);
+          if (ni <= R2) {
+            lami = (double)(ck.cie[1] / 25.E-6f);
+            ni = (float)fmin(499.E3, (double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(lami));
+          }
+          L_qi = true;
+          lami = ice_lam(ni, ri);
+          ilami = (double)1.f / lami;
+          const float xDi = (float)((double)(3.f + 0.f + 1.f) * ilami);
+          if (xDi < 5.E-6f) {
+            lami = (double)(ck.cie[1] / 5.E-6f);
+            ni = (float)fmin(499.E3, (double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(lami));
+          } else if (xDi > 300.E-6f) {
+            lami = (double)(ck.cie[1] / 300.E-6f);
+            ni = (float)((double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(lami));
+          }
+        } else {
+          qi1d = 0.0f; ni1d = 0.0f; ri = R1; ni = R2; L_qi = false;
+        }
+        if (qr1d > R1) {
+          rr = qr1d * rho;
+          nr = fmaxf(R2, nr1d * rho);
+          if (nr <= R2) { mvd_r = 1.0E-3f; nr = nr_from_mvd(rr, mvd_r); }
+          L_qr = true;
+          lamr = rain_lam(nr, rr);
+          mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+          if (mvd_r > 2.5E-3f) { mvd_r = 2.5E-3f; nr = nr_from_mvd(rr, mvd_r); }
+          else if (mvd_r < D0r * 0.75f) { mvd_r = D0r * 0.75f; nr = nr_from_mvd(rr, mvd_r); }
+        } else {
+          qr1d = 0.0f; nr1d = 0.0f; rr = R1; nr = R2; L_qr = false;
+        }
+        if (qs1d > R1) { rs = qs1d * rho; L_qs = true; } else { qs1d = 0.0f; rs = R1; L_qs = false; }
+        if (qg1d > R1) { rg = qg1d * rho; L_qg = true; } else { qg1d = 0.0f; rg = R1; L_qg = false; }
+
+        // ---- S2, M:1503-1533 -------------------------------------------------------------------
+        float tempc = temp - 273.15f;
+        float rhof = sqrtf(ck.rho_not / rho);
+        float rhof2 = sqrtf(rhof);
+        float qvs = rslf(pres, temp);
+        const float delQvs = fmaxf(0.0f, rslf(pres, 273.15f) - qv);
+        const float qvsi = (tempc <= 0.0f) ? rsif(pres, temp) : qvs;
+        float ssatw = qv / qvs - 1.f;
+        float ssati = qv / qvsi - 1.f;
+        if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
+        if (fabsf(ssati) < EPSF) ssati = 0.0f;
+        float diffu = 2.11E-5f * pow_f(temp / 273.15f, 1.94f) * (101325.f / pres);
+        float visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
+                                      : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
+        float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+        float vsc2 = sqrtf(rho / visco);
+        float lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+        float tcond = (5.69f + 0.0168f * tempc) * 1.0E-5f * 418.936f;
+
+        if (!iiwarm) {
+          // ---- S3, M:1545-1628 snow moments ----------------------------------------------------
+          if (L_qs) {
+            const float tc0 = fminf(-0.1f, temp - 273.15f);
+            smob = rs * ck.oams;
+            const float smo2 = smob;                    // bm_s = 2 branch of M:1553
+            const float* sa = c_sa; const float* sb = c_sb;
+            float loga_ = sa[1] + sa[2] * tc0 + sa[5] * tc0 * tc0 + sa[9] * tc0 * tc0 * tc0;
+            float b_ = sb[1] + sb[2] * tc0 + sb[5] * tc0 * tc0 + sb[9] * tc0 * tc0 * tc0;
+            smo0 = pow10_f(loga_) * pow_f(smo2, b_);
+            loga_ = sa[1] + sa[2] * tc0 + sa[3] + sa[4] * tc0 + sa[5] * tc0 * tc0 + sa[6] + sa[7] * tc0 * tc0
+                    + sa[8] * tc0 + sa[9] * tc0 * tc0 * tc0 + sa[10];
+            b_ = sb[1] + sb[2] * tc0 + sb[3] + sb[4] * tc0 + sb[5] * tc0 * tc0 + sb[6] + sb[7] * tc0 * tc0
+                 + sb[8] * tc0 + sb[9] * tc0 * tc0 * tc0 + sb[10];
+            smo1 = pow10_f(loga_) * pow_f(smo2, b_);
+            smoc = field_moment(tc0, ck.cse[0], smo2);
+            smoe = field_moment(tc0, ck.cse[12], smo2);
+            smof = field_moment(tc0, ck.cse[15], smo2);
+          }
+          // ---- S4, M:1633-1654 graupel intercept ------------------------------------------------
+          if (temp >= 270.65f) warm_above_a = true;
+          graupel_n0(!warm_above_a && k > 0, L_qr, mvd_r, rg, N0_min_a, ilamg, N0_g);
+        }
+        // M:1661-1666 rain slope and intercept
+        lamr = rain_lam(nr, rr);
+        ilamr = (double)1.f / lamr;
+        mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+        N0_r = (double)(nr * ck.org2) * lamr;                                  // lamr**cre(2), cre(2) = 1
+
+        // ---- S5, M:1676-1742 warm rain -----------------------------------------------------------
+        if (L_qr && mvd_r > D0r) {
+          const float Ef_rr = 1.0f - exp_f(2300.0f * (mvd_r - 1950.0E-6f));
+          pnr_rcr = (double)(Ef_rr * 2.0f * nr * rr);
+        }
+        mvd_c = D0c;
+        if (L_qc) {
+          nu_c = min(15, nint_f(1000.E6f / nc) + 2);
+          xDc = fmaxf(D0c * 1.E6f, pow_f(rc / (ck.am_r * nc), ck.obmr) * 1.E6f);
+          lamc = (double)pow_f(nc * ck.am_r * ck.ccg[1][nu_c - 1] * ck.ocg1[nu_c - 1] / rc, ck.obmr);
+          mvd_c = (float)((double)(3.0f + (float)nu_c + 0.672f) / lamc);
+        }
+        if (rc > 0.01e-3f) {
+          const float Dc_g = (float)(((double)pow_f(ck.ccg[2][nu_c - 1] * ck.ocg2[nu_c - 1], ck.obmr) / lamc) * (double)1.E6f);
+          const float Dc_b = pow_f(xDc * xDc * xDc * Dc_g * Dc_g * Dc_g - xDc * xDc * xDc * xDc * xDc * xDc, 1.f / 6.f);
+          const float zeta1 = 0.5f * ((6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f) + fabsf(6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f));
+          const float zeta = 0.027f * rc * zeta1;
+          const float taud = 0.5f * ((0.5f * Dc_b - 7.5f) + fabsf(0.5f * Dc_b - 7.5f)) + R1;
+          const float tau = 3.72f / (rc * taud);
+          prr_wau = (double)(zeta / tau);
+          prr_wau = fmin((double)(rc * odts), prr_wau);
+          pnr_wau = prr_wau / (double)(ck.am_r * (float)nu_c * D0r * D0r * D0r);
+          pnc_wau = fmin((double)(nc * odts), prr_wau / (double)(ck.am_r * mvd_c * mvd_c * mvd_c));
+        }
+        if (L_qr && mvd_r > D0r && mvd_c > D0c) {
+          lamr = (double)1.f / ilamr;
+          int idx = 1 + (int)((double)NBINS * log((double)mvd_r / ck.Dr1) / ck.lnDr);
+          idx = min(idx, (int)NBINS);
+          int jc = (int)(mvd_c * 1.E6f);
+          jc = max(1, min(jc, (int)NBINS));                                   // U11: bound the unbounded subscript
+          const float Ef_rw = ck.efrw[(idx - 1) + NBINS * (jc - 1)];
+          const double lf4 = 1.0 / sq_d(sq_d(lamr + (double)KP_FV_R));          // (lamr+fv_r)**(-cre(9)), cre(9) = 4
+          prr_rcw = (double)(rhof * ck.t1_qr_qc * Ef_rw * rc) * N0_r * lf4;
+          prr_rcw = fmin((double)(rc * odts), prr_rcw);
+          pnc_rcw = (double)(rhof * ck.t1_qr_qc * Ef_rw * nc) * N0_r * lf4;
+          pnc_rcw = fmin((double)(nc * odts), pnc_rcw);
+        }
+
+        // ---- S6, M:1749-2286 ice-phase processes --------------------------------------------------
+        if (!iiwarm) {
+          vts_boost = 1.5f;
+          tempc = temp - 273.15f;
+          const int idx_tc = max(1, min(nint_f(-tempc), 45));
+          int idx_t = (int)((tempc - 2.5f) / 5.f) - 1;
+          idx_t = max(1, -idx_t);
+          idx_t = min(idx_t, (int)NTB_T);
+          const int idx_c = (rc > ck.r_c1) ? decade_idx_f(rc, ck.nic2, NTB_C) : 1;
+          const int idx_i = (ri > ck.r_i1) ? decade_idx_f(ri, ck.nii2, NTB_I) : 1;
+          const int idx_i1 = (ni > ck.Nt_i1) ? decade_idx_f(ni, ck.nii3, NTB_I1) : 1;
+          int idx_r = 1, idx_r1 = NTB_R1, idx_s, idx_g = 1, idx_g1 = NTB_G1;
+          if (rr > ck.r_r1) {
+            idx_r = decade_idx_f(rr, ck.nir2, NTB_R);
+            lamr = (double)1.f / ilamr;
+            const double lam_exp = lamr * (double)cube_f(ck.crg[2] * ck.org2 * ck.org1);
+            const double N0_exp = (double)(ck.org1 * rr / ck.am_r) * sq_d(sq_d(lam_exp));   // **cre(1), cre(1) = 4
+            idx_r1 = decade_idx_d(N0_exp, ck.nir3, NTB_R1);
+          }
+          idx_s = (rs > ck.r_s1) ? decade_idx_f(rs, ck.nis2, NTB_S) : 1;
+          if (rg > ck.r_g1) {
+            idx_g = decade_idx_f(rg, ck.nig2, NTB_G);
+            const double lamg = (double)1.f / ilamg;
+            const double lam_exp = lamg * (double)cube_f(ck.cgg[2] * ck.ogg2 * ck.ogg1);
+            const double N0_exp = (double)(ck.ogg1 * rg / ck.am_g) * sq_d(sq_d(lam_exp));   // **cge(1), cge(1) = 4
+            idx_g1 = decade_idx_d(N0_exp, ck.nig3, NTB_G1);
+          }
+
+          // M:1884-1900 sublimation/deposition prefactor
+          const float otemp = 1.f / temp;
+          const float lsub = KP_LSUB, oRv = ck.oRv;
+          const float rvs = rho * qvsi;
+          const float rvs_p = rvs * otemp * (lsub * otemp * oRv - 1.f);
+          const float rvs_pp = rvs * (otemp * (lsub * otemp * oRv - 1.f) * otemp * (lsub * otemp * oRv - 1.f)
+                                      + (-2.f * lsub * otemp * otemp * otemp * oRv) + otemp * otemp);
+          const float gamsc = lsub * diffu / tcond * rvs_p;
+          float alphsc = 0.5f * (gamsc / (1.f + gamsc)) * (gamsc / (1.f + gamsc)) * rvs_pp / rvs_p * rvs / rvs_p;
+          alphsc = fmaxf(1.E-9f, alphsc);
+          float xsat = ssati;
+          if (fabsf(xsat) < 1.E-9f) xsat = 0.f;
+          const float t1_subl = 4.f * KP_PI * (1.0f - alphsc * xsat + 2.f * alphsc * alphsc * xsat * xsat
+                                               - 5.f * alphsc * alphsc * alphsc * xsat * xsat * xsat) / (1.f + gamsc);
+
+          // M:1903-1935 riming of snow and graupel
+          if (L_qc && mvd_c > D0c) {
+            float xDs = 0.0f;
+            if (L_qs) xDs = smoc / smob;
+            if (xDs > D0s) {
+              int idx = 1 + (int)((double)NBINS * log((double)xDs / ck.Ds1) / ck.lnDs);
+              idx = min(idx, (int)NBINS);
+              int jc = (int)(mvd_c * 1.E6f);
+              jc = max(1, min(jc, (int)NBINS));                               // U11
+              const float Ef_sw = ck.efsw[(idx - 1) + NBINS * (jc - 1)];
+              prs_scw = (double)(rhof * ck.t1_qs_qc * Ef_sw * rc * smoe);
+              pnc_scw = (double)(rhof * ck.t1_qs_qc * Ef_sw * nc * smoe);
+              pnc_scw = fmin((double)(nc * odts), pnc_scw);
+            }
+            if (rg >= ck.r_g1 && mvd_c > D0c) {
+              const float xDg = (float)((double)(3.f + 0.f + 1.f) * ilamg);
+              const float vtg = (float)((double)(rhof * KP_AV_G * ck.cgg[5] * ck.ogg3) * pow_d(ilamg, (double)KP_BV_G));
+              const float stoke_g = mvd_c * mvd_c * vtg * KP_RHO_W / (9.f * visco * xDg);
+              if (xDg > D0g) {
+                float Ef_gw = 0.0f;
+                if (stoke_g >= 0.4f && stoke_g <= 10.f) Ef_gw = 0.55f * log10_f(2.51f * stoke_g);
+                else if (stoke_g < 0.4f) Ef_gw = 0.0f;
+                else if (stoke_g > 10.f) Ef_gw = 0.77f;
+                const double il9 = pow_d(ilamg, (double)ck.cge[8]);
+                prg_gcw = (double)(rhof * ck.t1_qg_qc * Ef_gw * rc) * N0_g * il9;
+                pnc_gcw = (double)(rhof * ck.t1_qg_qc * Ef_gw * nc) * N0_g * il9;
+                pnc_gcw = fmin((double)(nc * odts), pnc_gcw);
+              }
+            }
+          }
+
+          // M:1964-2019 rain-snow and rain-graupel collection tables (interleaved records)
+          if (rr >= ck.r_r1) {
+            if (rs >= ck.r_s1) {
+              const double* rec = ck.racs + ((size_t)(idx_s - 1) + (size_t)NTB_S * ((idx_t - 1) + (size_t)NTB_T * ((idx_r1 - 1) + (size_t)NTB_R1 * (idx_r - 1)))) * S_N;
+              const double tmr2 = rec[S_TMR_RACS2], tcr2 = rec[S_TCR_SACR2], tmr1 = rec[S_TMR_RACS1], tcr1 = rec[S_TCR_SACR1];
+              const double tcs1 = rec[S_TCS_RACS1], tms1 = rec[S_TMS_SACR1];
+              if (temp < T_0) {
+                prr_rcs = -(tmr2 + tcr2 + tmr1 + tcr1);
+                prs_rcs = tmr2 + tcr2 - tcs1 - tms1;
+                prg_rcs = tmr1 + tcr1 + tcs1 + tms1;
+                prr_rcs = fmax((double)(-rr * odts), prr_rcs);
+                prs_rcs = fmax((double)(-rs * odts), prs_rcs);
+                prg_rcs = fmin((double)((rr + rs) * odts), prg_rcs);
+                pnr_rcs = rec[S_TNR_RACS1] + rec[S_TNR_RACS2] + rec[S_TNR_SACR1] + rec[S_TNR_SACR2];
+              } else {
+                prs_rcs = -tcs1 - tms1 + tmr2 + tcr2;
+                prs_rcs = fmax((double)(-rs * odts), prs_rcs);
+                prr_rcs = -prs_rcs;
+                pnr_rcs = rec[S_TNR_RACS2] + rec[S_TNR_SACR2];
+              }
+              pnr_rcs = fmin((double)(nr * odts), pnr_rcs);
+            }
+            if (rg >= ck.r_g1) {
+              const double* rec = ck.racg + ((size_t)(idx_g1 - 1) + (size_t)NTB_G1 * ((idx_g - 1) + (size_t)NTB_G * ((idx_r1 - 1) + (size_t)NTB_R1 * (idx_r - 1)))) * G_N;
+              if (temp < T_0) {
+                prg_rcg = rec[G_TMR_RACG] + rec[G_TCR_GACR];
+                prg_rcg = fmin((double)(rr * odts), prg_rcg);
+                prr_rcg = -prg_rcg;
+                pnr_rcg = rec[G_TNR_RACG] + rec[G_TNR_GACR];
+                pnr_rcg = fmin((double)(nr * odts), pnr_rcg);
+              } else {
+                prr_rcg = rec[G_TCG_RACG];
+                prr_rcg = fmin((double)(rg * odts), prr_rcg);
+                prg_rcg = -prr_rcg;
+                pnr_rcg = (double)-5.f * rec[G_TNR_GACR];
+              }
+            }
+          }
+
+          if (temp < T_0) {
+            // ---- below freezing, M:2025-2231 ---------------------------------------------------
+            vts_boost = 1.0f;
+            const float rate_max = (qv - qvsi) * rho * odts * 0.999f;
+            if (rr > ck.r_r1) {
+              const double* rec = ck.qrfz + ((size_t)(idx_r - 1) + (size_t)NTB_R * ((idx_r1 - 1) + (size_t)NTB_R1 * (idx_tc - 1))) * F_N;
+              prg_rfz = rec[F_TPG] * (double)odts;
+              pri_rfz = rec[F_TPI] * (double)odts;
+              pni_rfz = rec[F_TNI] * (double)odts;
+              pnr_rfz = rec[F_TNR] * (double)odts;
+              pnr_rfz = fmin((double)(nr * odts), pnr_rfz);
+            } else if (rr > R1 && temp < KP_HGFR) {
+              pri_rfz = (double)(rr * odts);
+              pnr_rfz = (double)(nr * odts);
+              pni_rfz = pnr_rfz;
+            }
+            if (rc > ck.r_c1) {
+              const double* rec = ck.qcfz + ((size_t)(idx_c - 1) + (size_t)NTB_C * (idx_tc - 1)) * C_N;
+              pri_wfz = rec[C_TPI] * (double)odts;
+              pri_wfz = fmin((double)(rc * odts), pri_wfz);
+              pni_wfz = rec[C_TNI] * (double)odts;
+              pni_wfz = fmin(fmin((double)(Nt_c * odts), pri_wfz / (double)(2.f * KP_XM0I)), pni_wfz);
+            } else if (rc > R1 && temp < KP_HGFR) {
+              pri_wfz = (double)(rc * odts);
+              pni_wfz = (double)(nc * odts);
+            }
+            // M:2090-2101 Cooper nucleation
+            if ((ssati >= 0.25f) || (ssatw > EPSF && temp < 253.15f)) {
+              const float xnc = fminf(250.E3f, KP_TNO * exp_f(KP_ATO * (T_0 - temp)));
+              const float xni = (float)((double)ni + (pni_rfz + pni_wfz) * (double)DT);
+              pni_inu = (double)(0.5f * (xnc - xni + fabsf(xnc - xni)) * odts);
+              pri_inu = fmin((double)rate_max, (double)KP_XM0I * pni_inu);
+              pni_inu = pri_inu / (double)KP_XM0I;
+            }
+            // M:2116-2149 deposition / sublimation of cloud ice, ice -> snow
+            float oxmi = 0.f, xDi = 0.f;
+            if (L_qi) {
+              lami = ice_lam(ni, ri);
+              ilami = (double)1.f / lami;
+              xDi = (float)fmax((double)ck.D0i, (double)(3.f + 0.f + 1.f) * ilami);
+              const float xmi = ck.am_i * cube_f(xDi);
+              oxmi = 1.f / xmi;
+              pri_ide = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs * ck.oig1 * ck.cig[4] * ni) * ilami;
+              const double* rec = ck.iaus + ((size_t)(idx_i - 1) + (size_t)NTB_I * (idx_i1 - 1)) * I_N;
+              if (pri_ide < 0.0) {
+                pri_ide = fmax(fmax((double)(-ri * odts), pri_ide), (double)rate_max);
+                pni_ide = pri_ide * (double)oxmi;
+                pni_ide = fmax((double)(-ni * odts), pni_ide);
+              } else {
+                pri_ide = fmin(pri_ide, (double)rate_max);
+                prs_ide = (1.0 - rec[I_TPI_IDE]) * pri_ide;
+                pri_ide = rec[I_TPI_IDE] * pri_ide;
+              }
+              if ((idx_i == NTB_I) || (xDi > 5.0f * D0s)) {
+                prs_iau = (double)(ri * .99f * odts);
+                pni_iau = (double)(ni * .95f * odts);
+              } else if (xDi < 0.1f * D0s) {
+                prs_iau = 0.; pni_iau = 0.;
+              } else {
+                prs_iau = rec[I_TPS] * (double)odts;
+                prs_iau = fmin((double)(ri * .99f * odts), prs_iau);
+                pni_iau = rec[I_TNI] * (double)odts;
+                pni_iau = fmin((double)(ni * .95f * odts), pni_iau);
+              }
+            }
+            // M:2153-2175 deposition / sublimation of snow, sublimation of graupel
+            if (L_qs) {
+              float C_snow = KP_C_SQRD + (tempc + 1.5f) * (KP_C_CUBE - KP_C_SQRD) / (-30.f + 1.5f);
+              C_snow = fmaxf(KP_C_SQRD, fminf(C_snow, KP_C_CUBE));
+              prs_sde = (double)(C_snow * t1_subl * diffu * ssati * rvs
+                                 * (ck.t1_qs_sd * smo1 + ck.t2_qs_sd * rhof2 * vsc2 * smof));
+              if (prs_sde < 0.) prs_sde = fmax(fmax((double)(-rs * odts), prs_sde), (double)rate_max);
+              else prs_sde = fmin(prs_sde, (double)rate_max);
+            }
+            if (L_qg && ssati < -EPSF) {
+              prg_gde = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs) * N0_g
+                        * ((double)ck.t1_qg_sd * sq_d(ilamg)
+                           + (double)(ck.t2_qg_sd * vsc2 * rhof2) * pow_d(ilamg, (double)ck.cge[10]));
+              if (prg_gde < 0.) prg_gde = fmax(fmax((double)(-rg * odts), prg_gde), (double)rate_max);
+              else prg_gde = fmin(prg_gde, (double)rate_max);
+            }
+            // M:2178-2202 snow and rain collecting cloud ice (lami/xDi/oxmi as recomputed at M:2179-2183)
+            if (L_qi) {
+              if (rs >= ck.r_s1) {
+                prs_sci = (double)(ck.t1_qs_qi * rhof * KP_EF_SI * ri * smoe);
+                pni_sci = prs_sci * (double)oxmi;
+              }
+              if (rr >= ck.r_r1 && mvd_r > 4.f * xDi) {
+                lamr = (double)1.f / ilamr;
+                const double lf = lamr + (double)KP_FV_R;
+                const double lf2 = lf * lf, lf4 = 1.0 / (lf2 * lf2), lf7 = 1.0 / (lf2 * lf2 * lf2 * lf);
+                pri_rci = (double)(rhof * ck.t1_qr_qi * KP_EF_RI * ri) * N0_r * lf4;
+                pnr_rci = (double)(rhof * ck.t1_qr_qi * KP_EF_RI * ni) * N0_r * lf4;
+                pni_rci = pri_rci * (double)oxmi;
+                prr_rci = (double)(rhof * ck.t2_qr_qi * KP_EF_RI * ni) * N0_r * lf7;       // cre(8) = 7
+                prr_rci = fmin((double)(rr * odts), prr_rci);
+                prg_rci = pri_rci + prr_rci;
+              }
+            }
+            // M:2205-2218 Hallett-Mossop
+            if (prg_gcw > (double)EPSF && tempc > -8.0f) {
+              float tf = 0.f;
+              if (tempc >= -5.0f && tempc < -3.0f) tf = 0.5f * (-3.0f - tempc);
+              else if (tempc > -8.0f && tempc < -5.0f) tf = 0.33333333f * (8.0f + tempc);
+              pni_ihm = (double)(3.5E8f * tf) * prg_gcw;
+              pri_ihm = (double)KP_XM0I * pni_ihm;
+              prs_ihm = prs_scw / (prs_scw + prg_gcw) * pri_ihm;
+              prg_ihm = prg_gcw / (prs_scw + prg_gcw) * pri_ihm;
+            }
+            // M:2224-2231 rimed snow -> graupel
+            if (prs_scw > (double)2.0f * prs_sde && prs_sde > (double)EPSF) {
+              const float r_frac = (float)fmin(30.0, prs_scw / prs_sde);
+              const float g_frac = fminf(0.95f, 0.15f + (r_frac - 2.f) * .028f);
+              vts_boost = fminf(1.5f, 1.1f + (r_frac - 2.f) * .016f);
+              prg_scw = (double)g_frac * prs_scw;
+              prs_scw = (double)(1.f - g_frac) * prs_scw;
+            }
+          } else {
+            // ---- at or above freezing, M:2237-2281 ----------------------------------------------
+            if (L_qs) {
+              prr_sml = (double)((tempc * tcond - KP_LVAP0 * diffu * delQvs)
+                                 * (ck.t1_qs_me * smo1 + ck.t2_qs_me * rhof2 * vsc2 * smof));
+              prr_sml = prr_sml + (double)(4218.f * ck.olfus * tempc) * (prr_rcs + prs_scw);
+              prr_sml = fmin((double)(rs * odts), fmax(0., prr_sml));
+              pnr_sml = (double)(smo0 / rs) * prr_sml * (double)pow10_f(-0.25f * tempc);
+              pnr_sml = fmin((double)(smo0 * odts), pnr_sml);
+              if (ssati < 0.f) {
+                prs_sde = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs
+                                   * (ck.t1_qs_sd * smo1 + ck.t2_qs_sd * rhof2 * vsc2 * smof));
+                prs_sde = fmax((double)(-rs * odts), prs_sde);
+              }
+            }
+            if (L_qg) {
+              const double il10 = sq_d(ilamg), il11 = pow_d(ilamg, (double)ck.cge[10]);
+              prr_gml = (double)(tempc * tcond - KP_LVAP0 * diffu * delQvs) * N0_g
+                        * ((double)ck.t1_qg_me * il10 + (double)(ck.t2_qg_me * rhof2 * vsc2) * il11);
+              prr_gml = fmin((double)(rg * odts), fmax(0., prr_gml));
+              pnr_gml = N0_g * (double)ck.cgg[1] * ilamg / (double)rg * prr_gml * (double)pow10_f(-0.5f * tempc);
+              if (ssati < 0.f) {
+                prg_gde = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs) * N0_g
+                          * ((double)ck.t1_qg_sd * il10 + (double)(ck.t2_qg_sd * vsc2 * rhof2) * il11);
+                prg_gde = fmax((double)(-rg * odts), prg_gde);
+              }
+            }
+            if (DT > 120.f) {
+              prr_rcw = prr_rcw + prs_scw + prg_gcw;
+              prs_scw = 0.; prg_gcw = 0.;
+            }
+          }
+        }
+
+        // ---- S7, M:2291-2387 conservation limiters -----------------------------------------------
+        {
+          float sump = (float)(pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + 0.0);
+          float rate_max = (qv - qvsi) * odts * 0.999f;                          // U7: no rho factor here
+          if ((sump > EPSF && sump > rate_max) || (sump < -EPSF && sump < rate_max)) {
+            const double ratio = (double)(rate_max / sump);
+            pri_inu *= ratio; pri_ide *= ratio; pni_ide *= ratio; prs_ide *= ratio; prs_sde *= ratio; prg_gde *= ratio;
+          }
+          sump = (float)(-prr_wau - pri_wfz - prr_rcw - prs_scw - prg_scw - prg_gcw);
+          rate_max = -rc * odts;
+          if (sump < rate_max && L_qc) {
+            const double ratio = (double)(rate_max / sump);
+            prr_wau *= ratio; pri_wfz *= ratio; prr_rcw *= ratio; prs_scw *= ratio; prg_scw *= ratio; prg_gcw *= ratio;
+          }
+          sump = (float)(pri_ide - prs_iau - prs_sci - pri_rci);
+          rate_max = -ri * odts;
+          if (sump < rate_max && L_qi) {
+            const double ratio = (double)(rate_max / sump);
+            pri_ide *= ratio; prs_iau *= ratio; prs_sci *= ratio; pri_rci *= ratio;
+          }
+          sump = (float)(-prg_rfz - pri_rfz - prr_rci + prr_rcs + prr_rcg);
+          rate_max = -rr * odts;
+          if (sump < rate_max && L_qr) {
+            const double ratio = (double)(rate_max / sump);
+            prg_rfz *= ratio; pri_rfz *= ratio; prr_rci *= ratio; prr_rcs *= ratio; prr_rcg *= ratio;
+          }
+          sump = (float)(prs_sde - prs_ihm - prr_sml + prs_rcs);
+          rate_max = -rs * odts;
+          if (sump < rate_max && L_qs) {
+            const double ratio = (double)(rate_max / sump);
+            prs_sde *= ratio; prs_ihm *= ratio; prr_sml *= ratio; prs_rcs *= ratio;
+          }
+          sump = (float)(prg_gde - prg_ihm - prr_gml + prg_rcg);
+          rate_max = -rg * odts;
+          if (sump < rate_max && L_qg) {
+            const double ratio = (double)(rate_max / sump);
+            prg_gde *= ratio; prg_ihm *= ratio; prr_gml *= ratio; prg_rcg *= ratio;
+          }
+          pri_ihm = prs_ihm + prg_ihm;
+          float ratio = (float)fmin(fabs(prr_rcg), fabs(prg_rcg));
+          prr_rcg = (double)(ratio * copysignf(1.0f, (float)prr_rcg));
+          prg_rcg = -prr_rcg;
+          if (temp > T_0) {
+            ratio = (float)fmin(fabs(prr_rcs), fabs(prs_rcs));
+            prr_rcs = (double)(ratio * copysignf(1.0f, (float)prr_rcs));
+            prs_rcs = -prr_rcs;
+          }
+        }
+
+        // ---- S8, M:2393-2569 tendencies and number/mass balances ------------------------------------
+        float tt, qvt, qct, qit, qrt, qst, qgt, nit, nrt, nct;
+        {
+          const float orho = 1.f / rho;
+          const float lfus2 = KP_LSUB - lvap;
+          qvt = (float)((-pri_inu - pri_ide - prs_ide - prs_sde - prg_gde) * (double)orho);
+          qct = (float)((-prr_wau - pri_wfz - prr_rcw - prs_scw - prg_scw - prg_gcw) * (double)orho);
+          nct = (float)((-pnc_wau - pnc_rcw - pni_wfz - pnc_scw - pnc_gcw) * (double)orho);
+          float xrc = fmaxf(R1, (qc1d + qct * DT) * rho);
+          float xnc = fmaxf(2.f, (nc1d + nct * DT) * rho);
+          if (xrc > R1) {
+            const int nu = min(15, nint_f(1000.E6f / xnc) + 2);
+            const double lc = (double)pow_f(xnc * ck.am_r * ck.ccg[1][nu - 1] * ck.ocg1[nu - 1] / rc, ck.obmr);
+            const float xD = (float)((double)(3.f + (float)nu + 1.f) / lc);
+            if (xD < D0c) {
+              const double l2 = (double)(ck.cce[1][nu - 1] / D0c);
+              xnc = (float)((double)(ck.ccg[0][nu - 1] * ck.ocg2[nu - 1] * xrc / ck.am_r) * cube_d(l2));
+              nct = (xnc - nc1d * rho) * odts * orho;
+            } else if (xD > D0r * 2.f) {
+              const double l2 = (double)(ck.cce[1][nu - 1] / (D0r * 2.f));
+              xnc = (float)((double)(ck.ccg[0][nu - 1] * ck.ocg2[nu - 1] * xrc / ck.am_r) * cube_d(l2));
+              nct = (xnc - nc1d * rho) * odts * orho;
+            }
+          } else {
+            nct = -nc1d * odts;
+          }
+          xnc = fmaxf(0.f, (nc1d + nct * DT) * rho);
+          if (xnc > KP_NT_C_MAX) nct = (KP_NT_C_MAX - nc1d * rho) * odts * orho;
+
+          qit = (float)((pri_inu + pri_ihm + pri_wfz + pri_rfz + pri_ide - prs_iau - prs_sci - pri_rci) * (double)orho);
+          nit = (float)((pni_inu + pni_ihm + pni_wfz + pni_rfz + pni_ide - pni_iau - pni_sci - pni_rci) * (double)orho);
+          const float xri = fmaxf(R1, (qi1d + qit * DT) * rho);
+          float xni = fmaxf(R2, (ni1d + nit * DT) * rho);
+          if (xri > R1) {
+            lami = ice_lam(xni, xri);
+            ilami = (double)1.f / lami;
+            const float xD = (float)((double)(3.f + 0.f + 1.f) * ilami);
+            if (xD < 5.E-6f) {
+              lami = (double)(ck.cie[1] / 5.E-6f);
+              xni = (float)fmin(499.E3, (double)(ck.cig[0] * ck.oig2 * xri / ck.am_i) * cube_d(lami));
+              nit = (xni - ni1d * rho) * odts * orho;
+            } else if (xD > 300.E-6f) {
+              lami = (double)(ck.cie[1] / 300.E-6f);
+              xni = (float)((double)(ck.cig[0] * ck.oig2 * xri / ck.am_i) * cube_d(lami));
+              nit = (xni - ni1d * rho) * odts * orho;
+            }
+          } else {
+            nit = -ni1d * odts;
+          }
+          xni = fmaxf(0.f, (ni1d + nit * DT) * rho);
+          if (xni > 499.E3f) nit = (499.E3f - ni1d * rho) * odts * orho;
+
+          qrt = (float)((prr_wau + prr_rcw + prr_sml + prr_gml + prr_rcs + prr_rcg - prg_rfz - pri_rfz - prr_rci) * (double)orho);
+          nrt = (float)((pnr_wau + pnr_sml + pnr_gml - (pnr_rfz + pnr_rcr + pnr_rcg + pnr_rcs + pnr_rci)) * (double)orho);
+          const float xrr = fmaxf(R1, (qr1d + qrt * DT) * rho);
+          float xnr = fmaxf(R2, (nr1d + nrt * DT) * rho);
+          if (xrr > R1) {
+            lamr = rain_lam(xnr, xrr);
+            mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+            if (mvd_r > 2.5E-3f) {
+              mvd_r = 2.5E-3f;
+              xnr = nr_from_mvd(xrr, mvd_r);
+              nrt = (xnr - nr1d * rho) * odts * orho;
+            } else if (mvd_r < D0r * 0.75f) {
+              mvd_r = D0r * 0.75f;
+              xnr = nr_from_mvd(xrr, mvd_r);
+              nrt = (xnr - nr1d * rho) * odts * orho;
+            }
+          } else {
+            qrt = -qr1d * odts;
+            nrt = -nr1d * odts;
+          }
+          qst = (float)((prs_iau + prs_sde + prs_sci + prs_scw + prs_rcs + prs_ide - prs_ihm - prr_sml) * (double)orho);
+          qgt = (float)((prg_scw + prg_rfz + prg_gde + prg_rcg + prg_gcw + prg_rci + prg_rcs - prg_ihm - prr_gml) * (double)orho);
+          if (temp < T_0) {
+            tt = (float)(((double)(KP_LSUB * ocp) * (pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + 0.0)
+                          + (double)(lfus2 * ocp) * (pri_wfz + pri_rfz + prg_rfz + prs_scw + prg_scw + prg_gcw + prg_rcs
+                                                     + prs_rcs + prr_rci + prg_rcg))
+                         * (double)orho * (double)1);
+          } else {
+            tt = (float)(((double)(ck.lfus * ocp) * (-prr_sml - prr_gml - prr_rcg - prr_rcs)
+                          + (double)(KP_LSUB * ocp) * (prs_sde + prg_gde))
+                         * (double)orho * (double)1);
+          }
+        }
+
+        // ---- S9, M:2574-2656 state at tau+1 -------------------------------------------------------
+        float lvt2;
+        {
+          temp = t1d + DT * tt;
+          const float otemp = 1.f / temp;
+          tempc = temp - 273.15f;
+          qv = fmaxf(1.E-10f, qv1d + DT * qvt);
+          rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+          rhof = sqrtf(ck.rho_not / rho);
+          rhof2 = sqrtf(rhof);
+          qvs = rslf(pres, temp);
+          ssatw = qv / qvs - 1.f;
+          if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
+          diffu = 2.11E-5f * pow_f(temp / 273.15f, 1.94f) * (101325.f / pres);
+          visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
+                                  : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
+          vsc2 = sqrtf(rho / visco);
+          lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+          tcond = (5.69f + 0.0168f * tempc) * 1.0E-5f * 418.936f;
+          ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+          lvt2 = lvap * lvap * ocp * ck.oRv * otemp * otemp;
+
+          if ((qc1d + qct * DT) > R1) { rc = (qc1d + qct * DT) * rho; nc = Nt_c; L_qc = true; }
+          else { rc = R1; nc = 2.f; L_qc = false; }
+          if ((qi1d + qit * DT) > R1) { ri = (qi1d + qit * DT) * rho; ni = fmaxf(R2, (ni1d + nit * DT) * rho); L_qi = true; }
+          else { ri = R1; ni = R2; L_qi = false; }
+          if ((qr1d + qrt * DT) > R1) {
+            rr = (qr1d + qrt * DT) * rho;
+            nr = fmaxf(R2, (nr1d + nrt * DT) * rho);
+            L_qr = true;
+            lamr = rain_lam(nr, rr);
+            mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+            if (mvd_r > 2.5E-3f) { mvd_r = 2.5E-3f; nr = nr_from_mvd(rr, mvd_r); }
+            else if (mvd_r < D0r * 0.75f) { mvd_r = D0r * 0.75f; nr = nr_from_mvd(rr, mvd_r); }
+          } else { rr = R1; nr = R2; L_qr = false; }
+          if ((qs1d + qst * DT) > R1) { rs = (qs1d + qst * DT) * rho; L_qs = true; } else { rs = R1; L_qs = false; }
+          if ((qg1d + qgt * DT) > R1) { rg = (qg1d + qgt * DT) * rho; L_qg = true; } else { rg = R1; L_qg = false; }
+        }
+
+        // ---- S10, M:2662-2750 snow moments and intercepts again -------------------------------------
+        if (!iiwarm) {
+          if (L_qs) {
+            const float tc0 = fminf(-0.1f, temp - 273.15f);
+            smob = rs * ck.oams;
+            smoc = field_moment(tc0, ck.cse[0], smob);
+            // smod (M:2706-2717) is not read again by any live code
+          }
+          if (temp >= 270.65f) warm_above_b = true;
+          graupel_n0(!warm_above_b && k > 0, L_qr, mvd_r, rg, N0_min_b, ilamg, N0_g);
+        }
+        lamr = rain_lam(nr, rr);
+        ilamr = (double)1.f / lamr;
+        mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+        N0_r = (double)(nr * ck.org2) * lamr;
+
+        // ---- S11, M:2780-2874 cloud condensation / evaporation ---------------------------------------
+        if ((ssatw > EPSF) || (ssatw < -EPSF && L_qc)) {
+          const float orho = 1.f / rho;
+          float clap = (qv - qvs) / (1.f + lvt2 * qvs);
+#pragma unroll
+          for (int n = 0; n < 3; ++n) {
+            const float e = exp_f(lvt2 * clap);
+            const float fcd = qvs * e - qv + clap;
+            const float dfcd = qvs * lvt2 * e + 1.f;
+            clap = clap - fcd / dfcd;
+          }
+          const float xrc = rc + clap * rho;
+          if (xrc > R1) {
+            prw_vcd = (double)(clap * odt);
+            if (clap > EPSF) {
+              const float xnc = Nt_c;
+              pnc_wcd = (double)(0.5f * (xnc - nc + fabsf(xnc - nc)) * odts * orho);
+            }
+          } else {
+            prw_vcd = (double)(-rc * orho * odt);
+            pnc_wcd = (double)(-nc * orho * odt);
+          }
+          qvt = (float)((double)qvt - prw_vcd);
+          qct = (float)((double)qct + prw_vcd);
+          nct = (float)((double)nct + pnc_wcd);
+          tt = (float)((double)tt + (double)(lvap * ocp) * prw_vcd * (double)1);
+          rc = fmaxf(R1, (qc1d + DT * qct) * rho);
+          nc = Nt_c;
+          qv = fmaxf(1.E-10f, qv1d + DT * qvt);
+          temp = t1d + DT * tt;
+          rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+          qvs = rslf(pres, temp);
+          ssatw = qv / qvs - 1.f;
+        }
+
+        // ---- S12, M:2880-2960 rain evaporation -------------------------------------------------------
+        if ((ssatw < -EPSF) && L_qr && (!(prw_vcd > 0.))) {
+          tempc = temp - 273.15f;
+          const float otemp = 1.f / temp;
+          const float orho = 1.f / rho;
+          rhof = sqrtf(ck.rho_not * orho);
+          rhof2 = sqrtf(rhof);
+          diffu = 2.11E-5f * pow_f(temp / 273.15f, 1.94f) * (101325.f / pres);
+          visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
+                                  : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
+          vsc2 = sqrtf(rho / visco);
+          lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+          tcond = (5.69f + 0.0168f * tempc) * 1.0E-5f * 418.936f;
+          ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+          const float oRv = ck.oRv;
+          const float rvs = rho * qvs;
+          const float rvs_p = rvs * otemp * (lvap * otemp * oRv - 1.f);
+          const float rvs_pp = rvs * (otemp * (lvap * otemp * oRv - 1.f) * otemp * (lvap * otemp * oRv - 1.f)
+                                      + (-2.f * lvap * otemp * otemp * otemp * oRv) + otemp * otemp);
+          const float gamsc = lvap * diffu / tcond * rvs_p;
+          float alphsc = 0.5f * (gamsc / (1.f + gamsc)) * (gamsc / (1.f + gamsc)) * rvs_pp / rvs_p * rvs / rvs_p;
+          alphsc = fmaxf(1.E-9f, alphsc);
+          const float xsat = fminf(-1.E-9f, ssatw);
+          const float t1_evap = 2.f * KP_PI * (1.0f - alphsc * xsat + 2.f * alphsc * alphsc * xsat * xsat
+                                               - 5.f * alphsc * alphsc * alphsc * xsat * xsat * xsat) / (1.f + gamsc);
+          lamr = (double)1.f / ilamr;
+          if (qv / qvs < 0.95f && rr * orho <= 1.E-8f) {
+            prv_rev = (double)(rr * orho * odts);
+          } else {
+            const double lh = lamr + (double)(0.5f * KP_FV_R);
+            prv_rev = (double)(t1_evap * diffu * (-ssatw)) * N0_r * (double)rvs
+                      * ((double)ck.t1_qr_ev * sq_d(ilamr)                                     // ilamr**cre(10), = 2
+                         + (double)(ck.t2_qr_ev * vsc2 * rhof2) * (1.0 / (lh * lh * lh)));      // **(-cre(11)), = 3
+            const float rate_max = fminf((rr * orho * odts), (qvs - qv) * odts);
+            prv_rev = fmin((double)rate_max, prv_rev * (double)orho);
+            if (prr_gml > 0.0) {
+              const float eva_factor = fminf(1.0f, 0.01f + (0.99f - 0.01f) * (tempc / 20.0f));
+              prv_rev = prv_rev * (double)eva_factor;
+            }
+          }
+          pnr_rev = fmin((double)(nr * 0.99f * orho * odts), prv_rev * (double)nr / (double)rr);
+          qrt = (float)((double)qrt - prv_rev);
+          qvt = (float)((double)qvt + prv_rev);
+          nrt = (float)((double)nrt - pnr_rev);
+          tt = (float)((double)tt - (double)(lvap * ocp) * prv_rev * (double)1);
+          rr = fmaxf(R1, (qr1d + DT * qrt) * rho);
+          qv = fmaxf(1.E-10f, qv1d + DT * qvt);
+          nr = fmaxf(R2, (nr1d + DT * nrt) * rho);
+          temp = t1d + DT * tt;
+          rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+        }
+
+        // M:2963-3120 the 36 process rates KiD saves with save_dg (optional buffer [36][nz][ncol])
+        if (a.rates) {
+          float* rp = a.rates + o + col;
+          const long st = (long)nz * ncol;
+          const double rv[KIDMP_NRATES] = {pri_inu, pri_ide, prs_ide, prs_sde, prg_gde, pri_wfz, prs_scw, prg_scw, prg_gcw, pri_ihm,
+                                           pri_rfz, prs_iau, prs_sci, pri_rci, pni_inu, pni_ihm, pni_wfz, pni_rfz, pni_ide, pni_iau,
+                                           pni_sci, pni_rci, prr_sml, prr_gml, pnr_rcs, pnr_rcg, pnr_rci, pnr_sml, pnr_gml, pnr_rfz,
+                                           prr_wau, prr_rcw, prv_rev, pnr_wau, pnr_rev, pnr_rcr};
+#pragma unroll
+          for (int q = 0; q < KIDMP_NRATES; ++q) rp[q * st] = (float)rv[q];
+        }
+
+        // ---- S13, M:3206-3354 fall speeds, substep counts (top-down carry) -----------------------------
+        rhof = sqrtf(ck.rho_not / rho);
+        float v_r, v_nr, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;
+        if (rr > R1) {
+          lamr = rain_lam(nr, rr);
+          const double lf = lamr + (double)KP_FV_R;
+          const double l2 = lamr * lamr, lf2 = lf * lf;
+          // lamr**cre(3) * (lamr+fv_r)**(-cre(6)), cre(3) = 4, cre(6) = 5
+          v_r = (float)((double)(rhof * KP_AV_R * ck.crg[5] * ck.org3) * (l2 * l2) * (1.0 / (lf2 * lf2 * lf)));
+          // lamr**cre(12) * (lamr+fv_r)**(-cre(7)), cre(12) = 2.5, cre(7) = 3.5
+          v_nr = (float)((double)(rhof * KP_AV_R * ck.crg[6] / ck.crg[11]) * (l2 * sqrt(lamr)) * (1.0 / (lf2 * lf * sqrt(lf))));
+        } else {
+          v_r = vtr_up; v_nr = vtnr_up;
+        }
+        if (fmaxf(v_r, v_nr) > 1.E-3f) {
+          ksed_r = max(ksed_r, k + 1);
+          const float delta_tp = dzq / (fmaxf(v_r, v_nr));
+          nstep_r = max(nstep_r, (int)(DT / delta_tp + 1.f));
+        }
+        if (!iiwarm) {
+          if (ri > R1) {
+            lami = ice_lam(ni, ri);
+            ilami = (double)1.f / lami;
+            v_i = (float)((double)(rhof * KP_AV_I * ck.cig[2] * ck.oig2) * ilami);               // ilami**bv_i, bv_i = 1
+            v_ni = (float)((double)(rhof * KP_AV_I * ck.cig[5] / ck.cig[6]) * ilami);
+          } else {
+            v_i = vti_up; v_ni = vtni_up;
+          }
+          if (v_i > 1.E-3f) {
+            ksed_i = max(ksed_i, k + 1);
+            const float delta_tp = dzq / v_i;
+            nstep_i = max(nstep_i, (int)(DT / delta_tp + 1.f));
+          }
+          if (rs > R1) {
+            const float xDs = smoc / smob;
+            const float Mrat = 1.f / xDs;
+            float ils1 = 1.f / (Mrat * KP_LAM0 + KP_FV_S);
+            float ils2 = 1.f / (Mrat * KP_LAM1 + KP_FV_S);
+            const float mm = pow_f(Mrat, KP_MU_S);
+            const float t1_vts = KP_KAP0 * ck.csg[3] * pow_f(ils1, ck.cse[3]);
+            const float t2_vts = KP_KAP1 * mm * ck.csg[9] * pow_f(ils2, ck.cse[9]);
+            ils1 = 1.f / (Mrat * KP_LAM0);
+            ils2 = 1.f / (Mrat * KP_LAM1);
+            const float t3_vts = KP_KAP0 * ck.csg[0] * pow_f(ils1, ck.cse[0]);
+            const float t4_vts = KP_KAP1 * mm * ck.csg[6] * pow_f(ils2, ck.cse[6]);
+            const float vts = rhof * KP_AV_S * (t1_vts + t2_vts) / (t3_vts + t4_vts);
+            if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * ((v_r - vts * vts_boost) / (temp - T_0)));
+            else v_s = vts * vts_boost;
+          } else {
+            v_s = vts_up;
+          }
+          if (v_s > 1.E-3f) {
+            ksed_s = max(ksed_s, k + 1);
+            const float delta_tp = dzq / v_s;
+            nstep_s = max(nstep_s, (int)(DT / delta_tp + 1.f));
+          }
+          if (rg > R1) {
+            const float vtg = (float)((double)(rhof * KP_AV_G * ck.cgg[5] * ck.ogg3) * pow_d(ilamg, (double)KP_BV_G));
+            v_g = (temp > T_0) ? fmaxf(vtg, v_r) : vtg;
+          } else {
+            v_g = vtg_up;
+          }
+          if (v_g > 1.E-3f) {
+            ksed_g = max(ksed_g, k + 1);
+            const float delta_tp = dzq / v_g;
+            nstep_g = max(nstep_g, (int)(DT / delta_tp + 1.f));
+          }
+        }
+        vtr_up = v_r; vtnr_up = v_nr; vti_up = v_i; vtni_up = v_ni; vts_up = v_s; vtg_up = v_g;
+
+        tten[k] = tt; qvten[k] = qvt; qcten[k] = qct; qiten[k] = qit; qrten[k] = qrt; qsten[k] = qst; qgten[k] = qgt;
+        niten[k] = nit; nrten[k] = nrt; ncten[k] = nct;
+        a_rr[k] = rr; a_nr[k] = nr; a_ri[k] = ri; a_ni[k] = ni; a_rs[k] = rs; a_rg[k] = rg;
+        vtrk[k] = v_r; vtnrk[k] = v_nr; vtik[k] = v_i; vtnik[k] = v_ni; vtsk[k] = v_s; vtgk[k] = v_g;
+        a_rho[k] = rho; a_temp[k] = temp; a_ocp[k] = ocp; a_lvap[k] = lvap;
+      }
+
+      // ================= pass 2: S14 sedimentation, M:3365-3578 =======================================
+      const int kte = nz;   // 1-based top
+      if (ksed_r == kte) ksed_r = kte - 1;
+      if (ksed_i == kte) ksed_i = kte - 1;
+      if (ksed_s == kte) ksed_s = kte - 1;
+      if (ksed_g == kte) ksed_g = kte - 1;
+      {
+        // rain (U6: never gated by l_sediment)
+        const float onstep = nstep_r > 0 ? 1.f / (float)nstep_r : 1.0f;
+        const int nstep = nint_f(1.f / onstep);
+        for (int n = 0; n < nstep; ++n) {
+          float sr_up = 0.f, sn_up = 0.f, sr_k = 0.f;
+#pragma unroll 1
+          for (int k = nz - 1; k >= 0; --k) {
+            const float sr = vtrk[k] * a_rr[k], sn = vtnrk[k] * a_nr[k];
+            const float odzq = 1.f / a.dz[k], orho = 1.f / a_rho[k];
+            if (k == nz - 1) {
+              qrten[k] = qrten[k] - sr * odzq * onstep * orho;
+              nrten[k] = nrten[k] - sn * odzq * onstep * orho;
+              a_rr[k] = fmaxf(R1, a_rr[k] - sr * odzq * DT * onstep);
+              a_nr[k] = fmaxf(R2, a_nr[k] - sn * odzq * DT * onstep);
+            } else if (k + 1 <= ksed_r) {
+              qrten[k] = qrten[k] + (sr_up - sr) * odzq * onstep * orho;
+              nrten[k] = nrten[k] + (sn_up - sn) * odzq * onstep * orho;
+              a_rr[k] = fmaxf(R1, a_rr[k] + (sr_up - sr) * odzq * DT * onstep);
+              a_nr[k] = fmaxf(R2, a_nr[k] + (sn_up - sn) * odzq * DT * onstep);
+            }
+            sr_up = sr; sn_up = sn; sr_k = sr;
+          }
+          if (a_rr[0] > R1 * 10.f) ppt_r = ppt_r + sr_k * DT * onstep;
+        }
+      }
+      // cloud-water stub M:3414-3425: vtck/vtnck are never assigned (U2) => no-op.
+      {
+        const float onstep = nstep_i > 0 ? 1.f / (float)nstep_i : 1.0f;
+        const int nstep = nint_f(1.f / onstep);
+        const bool sedi = ck.l_sediment != 0;
+        for (int n = 0; n < nstep; ++n) {
+          float si_up = 0.f, sn_up = 0.f, si_k = 0.f;
+#pragma unroll 1
+          for (int k = nz - 1; k >= 0; --k) {
+            const float si = sedi ? vtik[k] * a_ri[k] : 0.f, sn = sedi ? vtnik[k] * a_ni[k] : 0.f;
+            const float odzq = 1.f / a.dz[k], orho = 1.f / a_rho[k];
+            if (k == nz - 1) {
+              qiten[k] = qiten[k] - si * odzq * onstep * orho;
+              niten[k] = niten[k] - sn * odzq * onstep * orho;
+              a_ri[k] = fmaxf(R1, a_ri[k] - si * odzq * DT * onstep);
+              a_ni[k] = fmaxf(R2, a_ni[k] - sn * odzq * DT * onstep);
+            } else if (k + 1 <= ksed_i) {
+              qiten[k] = qiten[k] + (si_up - si) * odzq * onstep * orho;
+              niten[k] = niten[k] + (sn_up - sn) * odzq * onstep * orho;
+              a_ri[k] = fmaxf(R1, a_ri[k] + (si_up - si) * odzq * DT * onstep);
+              a_ni[k] = fmaxf(R2, a_ni[k] + (sn_up - sn) * odzq * DT * onstep);
+            }
+            si_up = si; sn_up = sn; si_k = si;
+          }
+          if (a_ri[0] > R1 * 10.f) ppt_i = ppt_i + si_k * DT * onstep;
+        }
+      }
+      {
+        const float onstep = nstep_s > 0 ? 1.f / (float)nstep_s : 1.0f;
+        const int nstep = nint_f(1.f / onstep);
+        const bool sedi = ck.l_sediment != 0;
+        for (int n = 0; n < nstep; ++n) {
+          float ss_up = 0.f, ss_k = 0.f;
+#pragma unroll 1
+          for (int k = nz - 1; k >= 0; --k) {
+            const float ss = sedi ? vtsk[k] * a_rs[k] : 0.f;
+            const float odzq = 1.f / a.dz[k], orho = 1.f / a_rho[k];
+            if (k == nz - 1) {
+              qsten[k] = qsten[k] - ss * odzq * onstep * orho;
+              a_rs[k] = fmaxf(R1, a_rs[k] - ss * odzq * DT * onstep);
+            } else if (k + 1 <= ksed_s) {
+              qsten[k] = qsten[k] + (ss_up - ss) * odzq * onstep * orho;
+              a_rs[k] = fmaxf(R1, a_rs[k] + (ss_up - ss) * odzq * DT * onstep);
+            }
+            ss_up = ss; ss_k = ss;
+          }
+          if (a_rs[0] > R1 * 10.f) ppt_s = ppt_s + ss_k * DT * onstep;
+        }
+      }
+      {
+        const float onstep = nstep_g > 0 ? 1.f / (float)nstep_g : 1.0f;
+        const int nstep = nint_f(1.f / onstep);
+        const bool sedi = ck.l_sediment != 0;
+        for (int n = 0; n < nstep; ++n) {
+          float sg_up = 0.f, sg_k = 0.f;
+#pragma unroll 1
+          for (int k = nz - 1; k >= 0; --k) {
+            const float sg = sedi ? vtgk[k] * a_rg[k] : 0.f;
+            const float odzq = 1.f / a.dz[k], orho = 1.f / a_rho[k];
+            if (k == nz - 1) {
+              qgten[k] = qgten[k] - sg * odzq * onstep * orho;
+              a_rg[k] = fmaxf(R1, a_rg[k] - sg * odzq * DT * onstep);
+            } else if (k + 1 <= ksed_g) {
+              qgten[k] = qgten[k] + (sg_up - sg) * odzq * onstep * orho;
+              a_rg[k] = fmaxf(R1, a_rg[k] + (sg_up - sg) * odzq * DT * onstep);
+            }
+            sg_up = sg; sg_k = sg;
+          }
+          if (a_rg[0] > R1 * 10.f) ppt_g = ppt_g + sg_k * DT * onstep;
+        }
+      }
+
+      // ================= S15 + S16, M:3584-3686, and the stores ==========================================
+#pragma unroll 1
+      for (int k = 0; k < nz; ++k) {
+        const long o = (long)k * ncol;
+        float t1d = Gt[o], qv1d = Gqv[o], qc1d = Gqc[o], qi1d = Gqi[o], qr1d = Gqr[o], qs1d = Gqs[o], qg1d = Gqg[o];
+        float ni1d = Gni[o], nr1d = Gnr[o];
+        const float pres = Gp[o];
+        float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));
+        if (!(qc1d > R1)) { qc1d = 0.f; nc1d = 0.f; }
+        if (!(qi1d > R1)) { qi1d = 0.f; ni1d = 0.f; }
+        if (!(qr1d > R1)) { qr1d = 0.f; nr1d = 0.f; }
+        if (!(qs1d > R1)) qs1d = 0.f;
+        if (!(qg1d > R1)) qg1d = 0.f;
+        float tt = tten[k], qct = qcten[k], nct = ncten[k], qit = qiten[k], nit = niten[k];
+        const float rho = a_rho[k];
+        if (!iiwarm) {
+          const float xri = fmaxf(0.0f, qi1d + qit * DT);
+          if ((a_temp[k] > T_0) && (xri > 0.0f)) {
+            qct = qct + xri * odt;
+            nct = nct + ni1d * odt;
+            qit = qit - xri * odt;
+            nit = -ni1d * odt;
+            tt = tt - ck.lfus * a_ocp[k] * xri * odt * 1.0f;
+          }
+          const float xrc = fmaxf(0.0f, qc1d + qct * DT);
+          if ((a_temp[k] < KP_HGFR) && (xrc > 0.0f)) {
+            const float lfus2 = KP_LSUB - a_lvap[k];
+            const float xnc = nc1d + nct * DT;
+            qit = qit + xrc * odt;
+            nit = nit + xnc * odt;
+            qct = qct - xrc * odt;
+            nct = nct - xnc * odt;
+            tt = tt + lfus2 * a_ocp[k] * xrc * odt * 1.0f;
+          }
+        }
+        t1d = t1d + tt * DT;
+        qv1d = fmaxf(1.E-10f, qv1d + qvten[k] * DT);
+        qc1d = qc1d + qct * DT;
+        if (qc1d <= R1) qc1d = 0.0f;              // nc1d is not returned to the host (I:143-152, I:198-245)
+        qi1d = qi1d + qit * DT;
+        ni1d = fmaxf(R2 / rho, ni1d + nit * DT);
+        if (qi1d <= R1) {
+          qi1d = 0.0f; ni1d = 0.0f;
+        } else {
+          double lami = ice_lam(ni1d, qi1d);
+          const double ilami = (double)1.f / lami;
+          const float xDi = (float)((double)(3.f + 0.f + 1.f) * ilami);
+          if (xDi < 5.E-6f) lami = (double)(ck.cie[1] / 5.E-6f);
+          else if (xDi > 300.E-6f) lami = (double)(ck.cie[1] / 300.E-6f);
+          ni1d = (float)fmin((double)(ck.cig[0] * ck.oig2 * qi1d / ck.am_i) * cube_d(lami), 499.E3 / (double)rho);
+        }
+        qr1d = qr1d + qrten[k] * DT;
+        nr1d = fmaxf(R2 / rho, nr1d + nrten[k] * DT);
+        if (qr1d <= R1) {
+          qr1d = 0.0f; nr1d = 0.0f;
+        } else {
+          const double lamr = rain_lam(nr1d, qr1d);
+          float mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+          if (mvd_r > 2.5E-3f) mvd_r = 2.5E-3f;
+          else if (mvd_r < D0r * 0.75f) mvd_r = D0r * 0.75f;
+          nr1d = nr_from_mvd(qr1d, mvd_r);
+        }
+        qs1d = qs1d + qsten[k] * DT;
+        if (qs1d <= R1) qs1d = 0.0f;
+        qg1d = qg1d + qgten[k] * DT;
+        if (qg1d <= R1) qg1d = 0.0f;
+        Gt[o] = t1d; Gqv[o] = qv1d; Gqc[o] = qc1d; Gqi[o] = qi1d; Gqr[o] = qr1d; Gqs[o] = qs1d; Gqg[o] = qg1d;
+        Gni[o] = ni1d; Gnr[o] = nr1d;
+        // domain diagnostics: liquid / ice water paths of the new state
+        const float rho_new = 0.622f * pres / (KP_R * t1d * (qv1d + 0.622f));
+        lwp += (double)((qc1d + qr1d) * rho_new * a.dz[k]);
+        iwp += (double)((qi1d + qs1d + qg1d) * rho_new * a.dz[k]);
+      }
+    }
+
+    // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
+    a.ppt[col] = ppt_r; a.ppt[ncol + col] = ppt_i; a.ppt[2 * ncol + col] = ppt_s; a.ppt[3 * ncol + col] = ppt_g;
+  }
+
+  // ---- block partial sums for the domain diagnostics (fixed order => run-to-run identical) ----------
+  if (a.diag_partial) {
+    __shared__ double s_red[4][KIDMP_NDIAG];
+    double v[KIDMP_NDIAG] = {(double)ppt_r, (double)ppt_i, (double)ppt_s, (double)ppt_g, lwp, iwp,
+                             active ? 1.0 : 0.0, in_range ? 1.0 : 0.0};
+#pragma unroll
+    for (int q = 0; q < KIDMP_NDIAG; ++q) {
+      double x = v[q];
+      for (int s = 16; s > 0; s >>= 1) x += __shfl_down_sync(0xffffffffu, x, s);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][q] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < KIDMP_NDIAG) {
+      double x = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += s_red[w][threadIdx.x];
+      a.diag_partial[(size_t)blockIdx.x * KIDMP_NDIAG + threadIdx.x] = x;
+    }
+  }
+}
+
+// fixed-order reduction of the block partials into diag[8] (accumulates: kidmp_diag reads and clears)
+__global__ void k_diag_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ diag) {
+  __shared__ double s[256];
+  const int q = blockIdx.x;
+  double x = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) x += partial[(size_t)b * KIDMP_NDIAG + q];
+  s[threadIdx.x] = x;
+  __syncthreads();
+  for (int st = blockDim.x >> 1; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st) s[threadIdx.x] += s[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) diag[q] += s[0];
+}
+
+// layout conversion between KiD's (k,i) arrays [col][nz] and the device layout [nz][ncol]
+__global__ void k_transpose(const float* __restrict__ src, float* __restrict__ dst, long ncol, int nz, int to_col_fastest) {
+  __shared__ float tile[32][33];
+  // src is [R][C] row-major, dst is [C][R]
+  // blockIdx.x tiles the columns, blockIdx.y the levels
+  const long R = to_col_fastest ? ncol : nz, Cn = to_col_fastest ? nz : ncol;
+  const long tc = (long)blockIdx.x * 32, tk = (long)blockIdx.y * 32;
+  const long r0 = to_col_fastest ? tc : tk, c0 = to_col_fastest ? tk : tc;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < Cn) tile[j][threadIdx.x] = src[r * Cn + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < Cn) dst[c * R + r] = tile[threadIdx.x][j];
+  }
+}
+
+#undef R1
+#undef R2
+#undef EPSF
+#undef T_0
+#undef D0r
+#undef D0c
+#undef D0s
+#undef D0g
+
+}  // namespace kidmp

@@ -1,0 +1,122 @@
+// kidmp_internal.h - shared declarations of the CUDA implementation (not part of the ABI).
+// Reference: M: = module_mp_thompson09n.f90.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/kidmp.h"
+
+namespace kidmp {
+
+// ---- PARAMETERs of the scheme (M:30-204) ------------------------------------------------------
+#define KP_T_0 273.15f
+#define KP_PI 3.1415926536f
+#define KP_RHO_W 1000.0f
+#define KP_RHO_G 500.0f
+#define KP_RHO_I 890.0f
+#define KP_NT_C_MAX 1999.E6f
+#define KP_MU_S 0.6357f
+#define KP_KAP0 490.6f
+#define KP_KAP1 17.46f
+#define KP_LAM0 20.78f
+#define KP_LAM1 3.29f
+#define KP_GONV_MIN 1.E4f
+#define KP_GONV_MAX 3.E6f
+#define KP_AM_S 0.069f
+#define KP_AV_R 4854.0f
+#define KP_FV_R 195.0f
+#define KP_AV_S 40.0f
+#define KP_BV_S 0.55f
+#define KP_FV_S 100.0f
+#define KP_AV_G 442.0f
+#define KP_BV_G 0.89f
+#define KP_AV_I 1847.5f
+#define KP_C_CUBE 0.5f
+#define KP_C_SQRD 0.15f
+#define KP_EF_SI 0.05f
+#define KP_EF_RS 0.95f
+#define KP_EF_RG 0.75f
+#define KP_EF_RI 0.95f
+#define KP_R1 1.E-12f
+#define KP_R2 1.E-6f
+#define KP_EPS 1.E-15f
+#define KP_TNO 5.0f
+#define KP_ATO 0.304f
+#define KP_HGFR 235.16f
+#define KP_R 287.04f
+#define KP_CP 1004.0f
+#define KP_LSUB 2.834E6f
+#define KP_LVAP0 2.5E6f
+#define KP_XM0I 1.E-12f
+#define KP_D0C 1.E-6f
+#define KP_D0R 50.E-6f
+#define KP_D0S 200.E-6f
+#define KP_D0G 250.E-6f
+
+enum { NBINS = 100, NTB_C = 37, NTB_I = 64, NTB_R = 37, NTB_S = 28, NTB_G = 28, NTB_G1 = 28, NTB_R1 = 37,
+       NTB_I1 = 55, NTB_T = 9, NTB_TC = 45 };
+enum : long { N_RACG = (long)NTB_G1 * NTB_G * NTB_R1 * NTB_R, N_RACS = (long)NTB_S * NTB_T * NTB_R1 * NTB_R,
+              N_QRFZ = (long)NTB_R * NTB_R1 * NTB_TC, N_QCFZ = (long)NTB_C * NTB_TC, N_IAUS = (long)NTB_I * NTB_I1,
+              N_EF = (long)NBINS * NBINS };
+
+// interleaved (array-of-structs) table records: every lookup of the step reads all members at
+// one index (M:1967-1985, M:2004-2016, M:2067-2070), so one gather touches one contiguous record.
+enum { G_TCG_RACG = 0, G_TMR_RACG, G_TCR_GACR, G_TMG_GACR, G_TNR_RACG, G_TNR_GACR, G_N };
+enum { S_TCS_RACS1 = 0, S_TMR_RACS1, S_TCS_RACS2, S_TMR_RACS2, S_TCR_SACR1, S_TMS_SACR1, S_TCR_SACR2, S_TMS_SACR2,
+       S_TNR_RACS1, S_TNR_RACS2, S_TNR_SACR1, S_TNR_SACR2, S_N };
+enum { F_TPI = 0, F_TPG, F_TNI, F_TNR, F_N };        // qrfz
+enum { C_TPI = 0, C_TNI, C_N };                      // qcfz
+enum { I_TPS = 0, I_TNI, I_TPI_IDE, I_N };           // iaus
+
+// constants written by the host part of init (M:381-670) and read by every kernel
+struct KConst {
+  float Nt_c, Sc3, D0i, xm0s, xm0g, rho_not;
+  float am_r, am_g, am_i, oRv, lfus, olfus;
+  float cce[5][15], ccg[5][15], ocg1[15], ocg2[15];
+  float cie[7], cig[7], oig1, oig2, obmi;
+  float cre[13], crg[13], ore1, org1, org2, org3, obmr;
+  float cse[18], csg[18], oams, obms, ocms;
+  float cge[12], cgg[12], oge1, ogg1, ogg2, ogg3, oamg, obmg, ocmg;
+  float t1_qr_qc, t1_qr_qi, t2_qr_qi, t1_qg_qc, t1_qs_qc, t1_qs_qi, t1_qr_ev, t2_qr_ev;
+  float t1_qs_sd, t2_qs_sd, t1_qg_sd, t2_qg_sd, t1_qs_me, t2_qs_me, t1_qg_me, t2_qg_me;
+  int nic1, nic2, nii2, nii3, nir2, nir3, nis2, nig2, nig3, niIN2;
+  int iiwarm, l_sediment;
+  float r_c1, r_i1, r_r1, r_s1, r_g1, Nt_i1;        // first axis nodes (M:215-279)
+  float p10[64];                                    // 10.**n as libgcc powi builds it, n = -32..31
+  double Dr1, Ds1, lnDr, lnDs;                      // Dr(1), Ds(1), DLOG(Dr(nbr)/Dr(1)), DLOG(Ds(nbs)/Ds(1))
+  // device tables
+  const double* racg;   // [N_RACG][G_N]
+  const double* racs;   // [N_RACS][S_N]
+  const double* qrfz;   // [N_QRFZ][F_N]
+  const double* qcfz;   // [N_QCFZ][C_N]
+  const double* iaus;   // [N_IAUS][I_N]
+  const float* efrw;    // [100][100] column-major (idx_r, idx_c)
+  const float* efsw;
+};
+
+struct StepArgs {
+  long ncol;
+  int nz;
+  float dt;
+  float* f[KIDMP_NFIELDS];     // qv qc qi qr qs qg ni nr t, [nz][ncol]
+  const float* p;              // [nz][ncol]
+  const float* dz;             // [nz]
+  float* ppt;                  // [4][ncol]
+  float* rates;                // optional [36][nz][ncol]
+  double* diag_partial;        // optional [gridDim.x][KIDMP_NDIAG] block sums
+};
+
+// device tables (kidmp_tables.cuh fills them)
+struct TableSet {
+  double *racg, *racs, *qrfz, *qcfz, *iaus;
+  float *efrw, *efsw;
+};
+struct HostBins {
+  double Dc[NBINS], dtc[NBINS], Di[NBINS], dti[NBINS], Dr[NBINS], dtr[NBINS], Ds[NBINS], dts[NBINS], Dg[NBINS],
+      dtg[NBINS], t_Nc[NBINS];
+  float r_c[NTB_C], r_i[NTB_I], r_r[NTB_R], r_g[NTB_G], r_s[NTB_S], N0r_exp[NTB_R1], N0g_exp[NTB_G1], Nt_i[NTB_I1];
+};
+
+}  // namespace kidmp

@@ -1,0 +1,324 @@
+// kidmp_tables.cuh - K3: one-time lookup-table build on the device.
+// Replaces qr_acr_qg (M:3698-3833), qr_acr_qs (M:3842-4082), freezeH2O (M:4092-4175),
+// qi_aut_qs (M:4190-4233), table_Efrw (M:4243-4299), table_Efsw (M:4307-4343).
+//
+// Split of work: the per-axis-node scalars (slopes and intercepts of the 1369 rain, 784 graupel and
+// 252 snow size distributions, i.e. a few thousand f32 powf results, M:3755-3757, M:3764-3766,
+// M:3937-3971) are evaluated once on the host in kidmp_api.cuh; the 1.4e10-term bin integrals that
+// make the build slow in the reference run here, one thread per table entry, the (rain, N0r) pair
+// of a block shared through shared memory.  Summation order inside an entry is the reference's
+// (n2 outer, n inner), so tables agree with a CPU evaluation to a few f64 ulps.
+#pragma once
+#include "kidmp_internal.h"
+
+namespace kidmp {
+
+struct TablePrep {            // host-evaluated per-axis-node scalars, device copies
+  const double* lamr;         // [NTB_R*NTB_R1]  index km = (m-1)*NTB_R1 + (k-1)   (m: r_r, k: N0r_exp)
+  const double* N0_r;
+  const double* lamg;         // [NTB_G*NTB_G1]  index (j-1)*NTB_G1 + (i-1)        (j: r_g, i: N0g_exp)
+  const double* N0_g;
+  const double* s_Mrat;       // [NTB_T*NTB_S]   index (j-1)*NTB_S + (i-1)         (j: Tc, i: r_s)
+  const double* s_M0;
+  const double* s_slam1;
+  const double* s_slam2;
+  const double* lamc;         // [NTB_C] freezeH2O cloud part (M:4157-4158)
+  const double* N0_c;
+  const double* i_lami;       // [NTB_I1*NTB_I]  index (j-1)*NTB_I + (i-1)
+  const double* i_N0;
+  const double* i_tpi_ide;    // GAMMP value or 0/1 (M:4209-4219)
+  const int* i_branch;        // 0: all to snow, 1: none, 2: integrate bins
+  const double* Dc; const double* dtc; const double* Di; const double* dti; const double* Dr; const double* dtr;
+  const double* Ds; const double* dts; const double* Dg; const double* dtg;
+  const float* r_r; const float* r_c; const float* r_i; const float* Nt_i;
+  double t_Nc1; int nu_c_fz; float xm0g; float obmr; float D0s; float am_r, am_g, am_i, am_s;
+  double Texp[NTB_TC];        // DEXP(k - T_adjust) - 1 at m = ntb_IN (M:4119-4122)
+};
+
+__device__ __forceinline__ double vr_poly_d(double D) {   // M:3733-3735
+  return (double)-0.1021f + (double)4.932E3f * D - (double)0.9551E6f * D * D + (double)0.07934E9f * D * D * D
+         - (double)0.002362E12f * D * D * D * D;
+}
+
+// size distributions on the bins: N_r[km][n2], N_g[n][ij] and N_s[n][ij] (transposed so that the
+// threads of a block, which differ in ij, read consecutive addresses)
+__global__ void k_table_psd(TablePrep tp, double* __restrict__ N_r, double* __restrict__ N_g, double* __restrict__ N_s) {
+  const int nR = NTB_R * NTB_R1, nG = NTB_G * NTB_G1, nS = NTB_T * NTB_S;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nR * NBINS) {
+    int km = t / NBINS, n2 = t % NBINS;
+    // mu_r = 0: Dr**mu_r = 1 (M:3759)
+    N_r[t] = tp.N0_r[km] * 1.0 * exp(-tp.lamr[km] * tp.Dr[n2]) * tp.dtr[n2];
+  } else if ((t -= nR * NBINS) < nG * NBINS) {
+    int n = t / nG, ij = t % nG;
+    N_g[t] = tp.N0_g[ij] * 1.0 * exp(-tp.lamg[ij] * tp.Dg[n]) * tp.dtg[n];             // M:3768
+  } else if ((t -= nG * NBINS) < nS * NBINS) {
+    int n = t / nS, ij = t % nS;
+    N_s[t] = tp.s_Mrat[ij] * ((double)KP_KAP0 * exp(-tp.s_slam1[ij] * tp.Ds[n])
+                              + (double)KP_KAP1 * tp.s_M0[ij] * pow(tp.Ds[n], (double)KP_MU_S)
+                                    * exp(-tp.s_slam2[ij] * tp.Ds[n])) * tp.dts[n];    // M:3974-3975
+  }
+}
+
+// rain <-> graupel: grid = 1369 (rain content, rain intercept) pairs, block = 784 graupel pairs
+__global__ void __launch_bounds__(NTB_G* NTB_G1) k_table_racg(TablePrep tp, const double* __restrict__ N_r,
+                                                               const double* __restrict__ N_g, double* __restrict__ racg) {
+  __shared__ double sNr[NBINS], sDr[NBINS], sVr[NBINS], sMr[NBINS], sDg[NBINS], sVg[NBINS], sMg[NBINS];
+  const int km = blockIdx.x;            // km = (m-1)*NTB_R1 + (k-1)   (M:3751-3753)
+  const int m = km / NTB_R1, k = km % NTB_R1;
+  const int ij = threadIdx.x;           // (j-1)*NTB_G1 + (i-1)
+  const int nG = NTB_G * NTB_G1;
+  for (int n = threadIdx.x; n < NBINS; n += blockDim.x) {
+    sNr[n] = N_r[km * NBINS + n];
+    sDr[n] = tp.Dr[n];
+    sVr[n] = vr_poly_d(tp.Dr[n]);
+    sMr[n] = (double)tp.am_r * pow(tp.Dr[n], 3.0);                       // M:3778
+    sDg[n] = tp.Dg[n];
+    sVg[n] = (double)KP_AV_G * pow(tp.Dg[n], (double)KP_BV_G);            // M:3738
+    sMg[n] = (double)tp.am_g * pow(tp.Dg[n], 3.0);                       // M:3780
+  }
+  __syncthreads();
+  const double c0 = (double)(KP_PI * .25f * KP_EF_RG);
+  double t1 = 0, t2 = 0, z1 = 0, z2 = 0, y1 = 0, y2 = 0;
+  for (int n2 = 0; n2 < NBINS; ++n2) {
+    const double massr = sMr[n2], vr = sVr[n2], Dr = sDr[n2], Nr = sNr[n2];
+    for (int n = 0; n < NBINS; ++n) {
+      const double Ng = N_g[n * nG + ij];
+      const double d = vr - sVg[n];
+      const double s = sDg[n] + Dr;
+      const double base = c0 * s * s;            // same association as PI*.25*Ef_rg*(Dg+Dr)*(Dg+Dr)
+      if (d > 0.0) {                             // dvg = d, dvr = +0 (M:3782-3783): the dvr terms add +0
+        t1 = t1 + base * d * sMg[n] * Ng * Nr;
+        z1 = z1 + base * d * massr * Ng * Nr;
+        y1 = y1 + base * d * Ng * Nr;
+      } else if (d < 0.0) {
+        const double dvr = -d;
+        t2 = t2 + base * dvr * massr * Ng * Nr;
+        y2 = y2 + base * dvr * Ng * Nr;
+        z2 = z2 + base * dvr * sMg[n] * Ng * Nr;
+      }
+    }
+  }
+  // record index: Fortran (i,j,k,m) column-major = ij + nG*km
+  double* rec = racg + ((size_t)ij + (size_t)nG * km) * G_N;
+  rec[G_TCG_RACG] = t1;
+  rec[G_TMR_RACG] = fmin(z1, (double)tp.r_r[m] * 1.0);                     // M:3802
+  rec[G_TCR_GACR] = t2;
+  rec[G_TMG_GACR] = z2;
+  rec[G_TNR_RACG] = y1;
+  rec[G_TNR_GACR] = y2;
+  (void)k;
+}
+
+// rain <-> snow: grid = 1369, block = 252 (snow content, temperature) pairs
+__global__ void __launch_bounds__(NTB_S* NTB_T) k_table_racs(TablePrep tp, const double* __restrict__ N_r,
+                                                              const double* __restrict__ N_s, double* __restrict__ racs) {
+  __shared__ double sNr[NBINS], sDr[NBINS], sVr[NBINS], sMr[NBINS], sDs[NBINS], sVs[NBINS], sMs[NBINS];
+  const int km = blockIdx.x;
+  const int m = km / NTB_R1;
+  const int ij = threadIdx.x;           // (j-1)*NTB_S + (i-1)
+  const int nS = NTB_S * NTB_T;
+  for (int n = threadIdx.x; n < NBINS; n += blockDim.x) {
+    sNr[n] = N_r[km * NBINS + n];
+    sDr[n] = tp.Dr[n];
+    sVr[n] = vr_poly_d(tp.Dr[n]);
+    sMr[n] = (double)tp.am_r * pow(tp.Dr[n], 3.0);                                             // M:3991
+    sDs[n] = tp.Ds[n];
+    sVs[n] = (double)(1.5f * KP_AV_S) * pow(tp.Ds[n], (double)KP_BV_S) * exp(-(double)KP_FV_S * tp.Ds[n]);  // M:3906
+    sMs[n] = (double)tp.am_s * pow(tp.Ds[n], 2.0);                                             // M:3993
+  }
+  __syncthreads();
+  const double c0 = (double)(KP_PI * .25f * KP_EF_RS);
+  double t1 = 0, t2 = 0, t3 = 0, t4 = 0, z1 = 0, z2 = 0, z3 = 0, z4 = 0, y1 = 0, y2 = 0, y3 = 0, y4 = 0;
+  for (int n2 = 0; n2 < NBINS; ++n2) {
+    const double massr = sMr[n2], vr = sVr[n2], Dr = sDr[n2], Nr = sNr[n2];
+    for (int n = 0; n < NBINS; ++n) {
+      const double Ns = N_s[n * nS + ij];
+      const double masss = sMs[n];
+      const double d = vr - sVs[n];
+      const double s = sDs[n] + Dr;
+      const double base = c0 * s * s;
+      const bool big = massr > (double)1.5f * masss;                     // M:3998
+      if (d > 0.0) {
+        if (big) { t1 = t1 + base * d * masss * Ns * Nr; z1 = z1 + base * d * massr * Ns * Nr; y1 = y1 + base * d * Ns * Nr; }
+        else     { t3 = t3 + base * d * masss * Ns * Nr; z3 = z3 + base * d * massr * Ns * Nr; y3 = y3 + base * d * Ns * Nr; }
+      } else if (d < 0.0) {
+        const double dvr = -d;
+        if (big) { t2 = t2 + base * dvr * massr * Ns * Nr; y2 = y2 + base * dvr * Ns * Nr; z2 = z2 + base * dvr * masss * Ns * Nr; }
+        else     { t4 = t4 + base * dvr * massr * Ns * Nr; y4 = y4 + base * dvr * Ns * Nr; z4 = z4 + base * dvr * masss * Ns * Nr; }
+      }
+    }
+  }
+  double* rec = racs + ((size_t)ij + (size_t)nS * km) * S_N;
+  rec[S_TCS_RACS1] = t1;
+  rec[S_TMR_RACS1] = fmin(z1, (double)tp.r_r[m] * 1.0);                    // M:4033
+  rec[S_TCS_RACS2] = t3;
+  rec[S_TMR_RACS2] = z3;
+  rec[S_TCR_SACR1] = t2;
+  rec[S_TMS_SACR1] = z2;
+  rec[S_TCR_SACR2] = t4;
+  rec[S_TMS_SACR2] = z4;
+  rec[S_TNR_RACS1] = y1;
+  rec[S_TNR_RACS2] = y3;
+  rec[S_TNR_SACR1] = y2;
+  rec[S_TNR_SACR2] = y4;
+}
+
+// Bigg freezing of rain: thread per (i = r_r, j = N0r_exp, k = -T), M:4123-4149 at m = ntb_IN
+__global__ void k_table_qrfz(TablePrep tp, const double* __restrict__ N_r, double* __restrict__ qrfz) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int)N_QRFZ) return;
+  const int i = t % NTB_R, j = (t / NTB_R) % NTB_R1, k = t / (NTB_R * NTB_R1);
+  const int km = i * NTB_R1 + j;                     // lam_exp uses N0r_exp(j), r_r(i): the (m=i,k=j) node
+  const double orho_w = (double)(1.f / KP_RHO_W);
+  const double Texp = tp.Texp[k];
+  double sum1 = 0, sum2 = 0, sumn1 = 0, sumn2 = 0;
+  for (int n2 = NBINS - 1; n2 >= 0; --n2) {
+    const double massr = (double)tp.am_r * pow(tp.Dr[n2], 3.0);
+    const double Nr = N_r[km * NBINS + n2];
+    const double vol = massr * orho_w;
+    const double prob = 1.0 - exp(-120.0 * vol * 5.2E-4 * Texp);
+    if (massr < (double)tp.xm0g) { sumn1 = sumn1 + prob * Nr; sum1 = sum1 + prob * Nr * massr; }
+    else                         { sumn2 = sumn2 + prob * Nr; sum2 = sum2 + prob * Nr * massr; }
+  }
+  double* rec = qrfz + (size_t)t * F_N;              // t = i + NTB_R*(j + NTB_R1*k): column-major (i,j,k)
+  rec[F_TPI] = sum1; rec[F_TNI] = sumn1; rec[F_TPG] = sum2; rec[F_TNR] = sumn2;
+}
+
+__device__ __forceinline__ double powi_dd(double x, int m) {   // libgcc __powidf2: Dc(n)**nu_c (M:4164)
+  unsigned n = m < 0 ? (unsigned)(-m) : (unsigned)m;
+  double y = (n % 2) ? x : 1.0;
+  while (n >>= 1) { x = x * x; if (n % 2) y *= x; }
+  return m < 0 ? 1.0 / y : y;
+}
+
+// Bigg freezing of cloud water: thread per (i = r_c, k = -T), M:4155-4171
+__global__ void k_table_qcfz(TablePrep tp, double* __restrict__ qcfz) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int)N_QCFZ) return;
+  const int i = t % NTB_C, k = t / NTB_C;
+  const double orho_w = (double)(1.f / KP_RHO_W);
+  const double Texp = tp.Texp[k];
+  double sum1 = 0, sumn2 = 0;
+  for (int n = NBINS - 1; n >= 0; --n) {
+    const double massc = (double)tp.am_r * pow(tp.Dc[n], 3.0);
+    const double vol = massc * orho_w;
+    const double prob = 1.0 - exp(-120.0 * vol * 5.2E-4 * Texp);
+    const double N_c = tp.N0_c[i] * powi_dd(tp.Dc[n], tp.nu_c_fz) * exp(-tp.lamc[i] * tp.Dc[n]) * tp.dtc[n];
+    sumn2 = fmin(tp.t_Nc1, sumn2 + prob * N_c);
+    sum1 = sum1 + prob * N_c * massc;
+    if (sum1 >= (double)tp.r_c[i]) break;
+  }
+  qcfz[(size_t)t * C_N + C_TPI] = sum1;
+  qcfz[(size_t)t * C_N + C_TNI] = sumn2;
+}
+
+// cloud ice -> snow: thread per (i = r_i, j = Nt_i), M:4202-4231
+__global__ void k_table_iaus(TablePrep tp, double* __restrict__ iaus) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int)N_IAUS) return;
+  const int i = t % NTB_I, j = t / NTB_I;
+  double t1 = 0, t2 = 0;
+  const int br = tp.i_branch[t];
+  if (br == 0) { t1 = (double)tp.r_i[i]; t2 = (double)tp.Nt_i[j]; }
+  else if (br == 2) {
+    const double lami = tp.i_lami[t], N0_i = tp.i_N0[t];
+    for (int n2 = 0; n2 < NBINS; ++n2) {
+      const double N_i = N0_i * 1.0 * exp(-lami * tp.Di[n2]) * tp.dti[n2];          // mu_i = 0
+      if (tp.Di[n2] >= (double)tp.D0s) {
+        t1 = t1 + N_i * (double)tp.am_i * pow(tp.Di[n2], 3.0);
+        t2 = t2 + N_i;
+      }
+    }
+  }
+  iaus[(size_t)t * I_N + I_TPS] = t1;
+  iaus[(size_t)t * I_N + I_TNI] = t2;
+  iaus[(size_t)t * I_N + I_TPI_IDE] = tp.i_tpi_ide[t];
+}
+
+// collision efficiencies: thread per (i = collector bin, j = cloud bin)
+__device__ __forceinline__ double ef_stokes(double stokes, double p) {   // M:4282-4290, M:4327-4335
+  const double reynolds = (double)9.f * stokes / (p * p * (double)KP_RHO_W);
+  const double F = log(reynolds);
+  const double G = -0.1007 - 0.358 * F + 0.0261 * F * F;
+  const double K0 = exp(G);
+  const double z = log(stokes / (K0 + 1.E-15));
+  const double H = 0.1465 + 1.302 * z - 0.607 * z * z + 0.293 * z * z * z;
+  const double yc0 = 2.0 / (double)KP_PI * atan(H);
+  return (yc0 + p) * (yc0 + p) / (((double)1.f + p) * ((double)1.f + p));
+}
+__global__ void k_table_ef(TablePrep tp, float* __restrict__ efrw, float* __restrict__ efsw) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int)N_EF) return;
+  const int i = t % NBINS, j = t / NBINS;
+  const double Dc = tp.Dc[j];
+  {  // table_Efrw
+    const double Dr = tp.Dr[i];
+    double Ef = 0.0;
+    const double p = Dc / Dr;
+    if (Dr < (double)50.E-6f || Dc < (double)3.E-6f) {
+      Ef = 0.0;
+    } else if (p > (double)0.25f) {
+      const double X = Dc * 1.E6;
+      if (Dr < (double)75.e-6f) Ef = (double)0.026794f * X - (double)0.20604f;
+      else if (Dr < (double)125.e-6f) Ef = (double)-0.00066842f * X * X + (double)0.061542f * X - (double)0.37089f;
+      else if (Dr < (double)175.e-6f)
+        Ef = (double)4.091e-06f * X * X * X * X - (double)0.00030908f * X * X * X + (double)0.0066237f * X * X
+             - (double)0.0013687f * X - (double)0.073022f;
+      else if (Dr < (double)250.e-6f)
+        Ef = (double)9.6719e-5f * X * X * X - (double)0.0068901f * X * X + (double)0.17305f * X - (double)0.65988f;
+      else if (Dr < (double)350.e-6f)
+        Ef = (double)9.0488e-5f * X * X * X - (double)0.006585f * X * X + (double)0.16606f * X - (double)0.56125f;
+      else
+        Ef = (double)0.00010721f * X * X * X - (double)0.0072962f * X * X + (double)0.1704f * X - (double)0.46929f;
+    } else {
+      const double vtr = vr_poly_d(Dr);
+      const double stokes = Dc * Dc * vtr * (double)KP_RHO_W / ((double)(9.f * 1.718E-5f) * Dr);
+      Ef = ef_stokes(stokes, p);
+    }
+    efrw[t] = fmaxf(0.0f, fminf((float)Ef, 0.95f));                        // M:4294
+  }
+  {  // table_Efsw
+    const double Ds = tp.Ds[i];
+    const double vtc = 1.19E4 * (1.0E4 * Dc * Dc * 0.25);
+    const double vts = (double)KP_AV_S * pow(Ds, (double)KP_BV_S) * exp(-(double)KP_FV_S * Ds) - vtc;
+    const double Ds_m = pow((double)tp.am_s * pow(Ds, 2.0) / (double)tp.am_r, (double)tp.obmr);
+    const double p = Dc / Ds_m;
+    float e = 0.0f;
+    if (!(p > (double)0.25f || Ds < (double)tp.D0s || Dc < (double)6.E-6f || vts < (double)1.E-3f)) {
+      const double stokes = Dc * Dc * vts * (double)KP_RHO_W / ((double)(9.f * 1.718E-5f) * Ds_m);
+      e = fmaxf(0.0f, fminf((float)ef_stokes(stokes, p), 0.95f));
+    }
+    efsw[t] = e;
+  }
+}
+
+struct TableScratch { double *N_r, *N_g, *N_s; };
+
+inline cudaError_t build_tables_dev(const TablePrep& tp, const TableSet& t, const TableScratch& sc, bool ice_tables,
+                                    cudaStream_t s, float* ms, long* launches) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, s);
+  long nl = 0;
+  k_table_ef<<<(N_EF + 255) / 256, 256, 0, s>>>(tp, t.efrw, t.efsw); ++nl;
+  if (ice_tables) {
+    const int nR = NTB_R * NTB_R1, nG = NTB_G * NTB_G1, nS = NTB_T * NTB_S;
+    const int ntot = (nR + nG + nS) * NBINS;
+    k_table_psd<<<(ntot + 255) / 256, 256, 0, s>>>(tp, sc.N_r, sc.N_g, sc.N_s); ++nl;
+    k_table_racg<<<nR, nG, 0, s>>>(tp, sc.N_r, sc.N_g, t.racg); ++nl;
+    k_table_racs<<<nR, nS, 0, s>>>(tp, sc.N_r, sc.N_s, t.racs); ++nl;
+    k_table_qrfz<<<((int)N_QRFZ + 127) / 128, 128, 0, s>>>(tp, sc.N_r, t.qrfz); ++nl;
+    k_table_qcfz<<<((int)N_QCFZ + 127) / 128, 128, 0, s>>>(tp, t.qcfz); ++nl;
+    k_table_iaus<<<((int)N_IAUS + 127) / 128, 128, 0, s>>>(tp, t.iaus); ++nl;
+  }
+  cudaEventRecord(e1, s);
+  cudaError_t err = cudaEventSynchronize(e1);
+  if (err == cudaSuccess) err = cudaGetLastError();
+  if (err == cudaSuccess && ms) cudaEventElapsedTime(ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (launches) *launches += nl;
+  return err;
+}
+
+}  // namespace kidmp

@@ -1,0 +1,233 @@
+"""ctypes binding of kid_b200/libkidmp.so (include/kidmp.h), used by the tests and bench.py.
+
+This is plumbing only: every compute call goes through the C ABI into the CUDA kernels.  There is
+no CPU path - on a machine without a CUDA device `Thompson(...)` raises `KidmpError`.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import build as _build
+
+NFIELDS = 9
+FIELDS = ("qv", "qc", "qi", "qr", "qs", "qg", "ni", "nr", "t")
+K_FASTEST, COL_FASTEST = 0, 1
+NDIAG = 8
+DIAG_NAMES = ("ppt_rain", "ppt_ice", "ppt_snow", "ppt_graupel", "lwp", "iwp", "active_columns", "columns")
+
+_fp = C.POINTER(C.c_float)
+_dp = C.POINTER(C.c_double)
+_fpp = C.POINTER(_fp)
+
+
+class KidmpError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("set_Nc", C.c_float), ("iiwarm", C.c_int), ("l_sediment", C.c_int), ("wp_double", C.c_int),
+                ("device", C.c_int), ("reuse_tables", C.c_int), ("table_cache_path", C.c_char_p)]
+
+
+# every symbol include/kidmp.h declares: (restype, argtypes)
+SYMBOLS = {
+    "kidmp_init": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "kidmp_finalize": (C.c_int, [C.c_void_p]),
+    "kidmp_last_error": (C.c_char_p, [C.c_void_p]),
+    "kidmp_table_build_ms": (C.c_double, [C.c_void_p]),
+    "kidmp_table_size": (C.c_long, [C.c_void_p, C.c_char_p]),
+    "kidmp_get_table": (C.c_int, [C.c_void_p, C.c_char_p, _dp, C.c_long]),
+    "kidmp_save_tables": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "kidmp_column": (C.c_int, [C.c_void_p, C.c_int, C.c_float] + [_fp] * 9 + [_fp, _fp, _fp]),
+    "kidmp_step": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_int, _fpp, _fp, _fp, _fp]),
+    "kidmp_state_alloc": (C.c_int, [C.c_void_p, C.c_long, C.c_int]),
+    "kidmp_upload": (C.c_int, [C.c_void_p, C.c_int, _fpp, _fp, _fp]),
+    "kidmp_step_resident": (C.c_int, [C.c_void_p, C.c_float]),
+    "kidmp_download": (C.c_int, [C.c_void_p, C.c_int, _fpp, _fp]),
+    "kidmp_step_device": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_float, C.POINTER(C.c_void_p), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kidmp_set_rates_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "kidmp_rate_names": (C.c_char_p, []),
+    "kidmp_diag": (C.c_int, [C.c_void_p, _dp]),
+    "kidmp_gpu_launches": (C.c_long, [C.c_void_p]),
+    "kidmp_sync": (C.c_int, [C.c_void_p]),
+    "kidmp_last_step_ms": (C.c_int, [C.c_void_p, _fp]),
+    "kidmp_tables_from_cache": (C.c_int, [C.c_void_p]),
+    "kidmp_stream": (C.c_void_p, [C.c_void_p]),
+    "kidmp_device_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+}
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """dlopen the library (building it first when a source is newer and nvcc is available)."""
+    global _lib
+    if _lib is None:
+        if build_if_missing:
+            try:
+                _build.build()
+            except Exception:
+                if not os.path.exists(_build.LIB):
+                    raise
+        L = C.CDLL(_build.LIB)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ptrs(arrs):
+    return (_fp * len(arrs))(*[a.ctypes.data_as(_fp) for a in arrs])
+
+
+def _f32c(a):
+    a = np.asarray(a)
+    if a.dtype != np.float32 or not a.flags.c_contiguous:
+        raise ValueError("float32 C-contiguous array required")
+    return a
+
+
+class Thompson:
+    """One handle = thompson_init (M:374-797) done on one GPU, plus the column step entry points."""
+
+    def __init__(self, set_Nc=100.0, iiwarm=False, l_sediment=True, wp_double=False, device=0,
+                 table_cache=None, reuse_tables=False):
+        L = load()
+        self._L = L
+        cfg = Config(float(set_Nc), int(iiwarm), int(l_sediment), int(wp_double), int(device),
+                     int(bool(reuse_tables and table_cache)), table_cache.encode() if table_cache else None)
+        h = C.c_void_p()
+        rc = L.kidmp_init(C.byref(cfg), C.byref(h))
+        if rc:
+            raise KidmpError(L.kidmp_last_error(None).decode())
+        self.h = h
+        self.iiwarm = bool(iiwarm)
+
+    # -- lifecycle ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.kidmp_finalize(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise KidmpError(self._L.kidmp_last_error(self.h).decode())
+
+    # -- tables -----------------------------------------------------------------------------------
+    @property
+    def table_build_ms(self):
+        return self._L.kidmp_table_build_ms(self.h)
+
+    @property
+    def tables_from_cache(self):
+        return bool(self._L.kidmp_tables_from_cache(self.h))
+
+    def get(self, name):
+        n = self._L.kidmp_table_size(self.h, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        out = np.empty(n, np.float64)
+        self._ck(self._L.kidmp_get_table(self.h, name.encode(), out.ctypes.data_as(_dp), n))
+        return out
+
+    def save_tables(self, path):
+        self._ck(self._L.kidmp_save_tables(self.h, path.encode()))
+
+    # -- steps --------------------------------------------------------------------------------------
+    def column(self, dt, qv, qc, qi, qr, qs, qg, ni, nr, t, p, dz, ppt=None):
+        """Twin of `call mp_thompson(...)` for one column (M:1156-1162); returns dict of new arrays."""
+        a = {k: np.ascontiguousarray(v, np.float32).copy() for k, v in zip(FIELDS, (qv, qc, qi, qr, qs, qg, ni, nr, t))}
+        p = np.ascontiguousarray(p, np.float32)
+        dz = np.ascontiguousarray(dz, np.float32)
+        ppt4 = np.zeros(4, np.float32) if ppt is None else np.asarray(ppt, np.float32).copy()
+        self._ck(self._L.kidmp_column(self.h, len(p), float(dt), *[a[k].ctypes.data_as(_fp) for k in FIELDS],
+                                      p.ctypes.data_as(_fp), dz.ctypes.data_as(_fp), ppt4.ctypes.data_as(_fp)))
+        a["ppt"] = ppt4
+        return a
+
+    def step(self, dt, state, p, dz, layout="col_fastest"):
+        """Host arrays in, host arrays out (in place).  state: dict by FIELDS of float32 arrays,
+        (nz, ncol) for 'col_fastest' or (ncol, nz) for 'k_fastest'.  Returns ppt[4, ncol]."""
+        lay = K_FASTEST if layout == "k_fastest" else COL_FASTEST
+        t = _f32c(state["t"])
+        ncol, nz = (t.shape if lay == K_FASTEST else t.shape[::-1])
+        arrs = [_f32c(state[k]) for k in FIELDS]
+        ppt = np.zeros((4, ncol), np.float32)
+        self._ck(self._L.kidmp_step(self.h, ncol, nz, float(dt), lay, _ptrs(arrs), _f32c(p).ctypes.data_as(_fp),
+                                    np.ascontiguousarray(dz, np.float32).ctypes.data_as(_fp), ppt.ctypes.data_as(_fp)))
+        return ppt
+
+    def state_alloc(self, ncol, nz):
+        self._ck(self._L.kidmp_state_alloc(self.h, int(ncol), int(nz)))
+        self.ncol, self.nz = int(ncol), int(nz)
+
+    def upload(self, state, p, dz, layout="col_fastest"):
+        lay = K_FASTEST if layout == "k_fastest" else COL_FASTEST
+        arrs = [_f32c(state[k]) for k in FIELDS]
+        self._ck(self._L.kidmp_upload(self.h, lay, _ptrs(arrs), _f32c(p).ctypes.data_as(_fp),
+                                      np.ascontiguousarray(dz, np.float32).ctypes.data_as(_fp)))
+
+    def step_resident(self, dt):
+        self._ck(self._L.kidmp_step_resident(self.h, float(dt)))
+
+    def download(self, state=None, layout="col_fastest", want_ppt=True):
+        lay = K_FASTEST if layout == "k_fastest" else COL_FASTEST
+        ppt = np.zeros((4, self.ncol), np.float32) if want_ppt else None
+        fp = _ptrs([_f32c(state[k]) for k in FIELDS]) if state is not None else None
+        self._ck(self._L.kidmp_download(self.h, lay, fp, ppt.ctypes.data_as(_fp) if want_ppt else None))
+        return ppt
+
+    def step_device(self, ncol, nz, dt, field_ptrs, p_ptr, dz_ptr, ppt_ptr, stream=None):
+        """Device pointers (ints, e.g. torch.Tensor.data_ptr()), COL_FASTEST layout; asynchronous."""
+        fp = (C.c_void_p * NFIELDS)(*[C.c_void_p(int(x)) for x in field_ptrs])
+        self._ck(self._L.kidmp_step_device(self.h, int(ncol), int(nz), float(dt), fp, C.c_void_p(int(p_ptr)),
+                                           C.c_void_p(int(dz_ptr)), C.c_void_p(int(ppt_ptr)),
+                                           C.c_void_p(int(stream)) if stream else None))
+
+    def device_state(self):
+        f = (C.c_void_p * NFIELDS)()
+        p, dz, ppt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self._L.kidmp_device_state(self.h, f, C.byref(p), C.byref(dz), C.byref(ppt)))
+        return [int(x) for x in f], int(p.value), int(dz.value), int(ppt.value)
+
+    def set_rates_buffer(self, ptr):
+        self._ck(self._L.kidmp_set_rates_buffer(self.h, C.c_void_p(int(ptr)) if ptr else None))
+
+    @property
+    def rate_names(self):
+        return self._L.kidmp_rate_names().decode().split(",")
+
+    def diag(self):
+        out = np.zeros(NDIAG, np.float64)
+        self._ck(self._L.kidmp_diag(self.h, out.ctypes.data_as(_dp)))
+        return out
+
+    def sync(self):
+        self._ck(self._L.kidmp_sync(self.h))
+
+    @property
+    def gpu_launches(self):
+        return int(self._L.kidmp_gpu_launches(self.h))
+
+    @property
+    def stream(self):
+        return int(self._L.kidmp_stream(self.h) or 0)
+
+    def last_step_ms(self):
+        ms = C.c_float()
+        self._ck(self._L.kidmp_last_step_ms(self.h, C.byref(ms)))
+        return float(ms.value)
