@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py - column-steps/s of the Thompson microphysics step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference ...                     (the reference's CPU path: the oracle)
+
+Workload (BASELINE.json configs[3]): synthetic 1024x1024 = 1 048 576 columns x 60 levels per GPU from
+the seeded CONUS-like convective domain of kid_b200/synth.py (about 30 % cloudy columns), dt = 10 s.
+Weak scaling: every rank owns its own 1 048 576 columns [rank*ncol, (rank+1)*ncol) of one global
+domain; columns are independent, so there is no data-path collective - NCCL only reduces the eight
+domain diagnostics once per run.
+
+A "step" = one kidmp_step_device call (one column-kernel launch + the 8-block diagnostics reduce)
+over all resident columns; the state evolves in place from step to step like a model time loop.
+Inputs (2.8 GB per GPU) are far larger than L2, so no flush is needed between steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "column-steps/sec (60-lev Thompson)"
+UNIT = "column-steps/s"
+ALG_BYTES_PER_COLUMN = 4576          # 10 fields read + 9 written + 4 precip scalars, nz=60
+NZ = 60
+DT = 10.0
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for j, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(r[j].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+def cpu_reference_run(ncol, steps, warmup, nthreads, col0=0):
+    """The reference's CPU path (the C++ restatement under oracle/: no Fortran compiler exists here)
+    on `ncol` columns of the bench domain, all host threads.  Returns (column-steps/s, ms/step, init_s)."""
+    from kid_b200 import synth
+    from oracle.oracle import Oracle
+    o = Oracle(set_Nc=100.0, iiwarm=False, l_sediment=True, nthreads=nthreads)
+    st, p, dz = synth.make_domain(ncol, nz=NZ, col0=col0, nx=1024)
+    state = {k: v.numpy().copy() for k, v in st.items()}
+    pn, dzn = p.numpy().copy(), dz.numpy().copy()
+    for _ in range(warmup):
+        o.step(DT, state, pn, dzn, nthreads=nthreads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(DT, state, pn, dzn, nthreads=nthreads)
+    el = time.perf_counter() - t0
+    init_s = o.init_seconds
+    o.close()
+    return ncol * steps / el, el / steps * 1e3, init_s
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ncol = args.cpu_columns
+    v, ms, init_s = cpu_reference_run(ncol, args.steps, args.warmup, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": "synthetic 1024x1024 columns x 60 levels, CONUS-like convective domain, dt=10s",
+                   "sample_columns": ncol, "nz": NZ, "dt": DT},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "first %d columns of the bench domain x %d steps, OpenMP over columns; C++ restatement "
+                                   "of the reference (no Fortran compiler on the box), table init %.1f s excluded"
+                                   % (ncol, args.steps, init_s)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kidmp", choices=["kidmp", "reference"])
+    ap.add_argument("--columns", type=int, default=1024 * 1024, help="columns per GPU")
+    ap.add_argument("--cpu-columns", type=int, default=262144, help="columns of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "kidmp" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from kid_b200 import synth
+    from kid_b200.kidmp import Thompson, FIELDS
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the kidmp arm has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ncol = args.columns
+    th = Thompson(set_Nc=100.0, iiwarm=False, l_sediment=True, device=local)
+    # synthetic state generated directly in HBM, this rank's shard of the global domain
+    st, p, dz = synth.make_domain(ncol, nz=NZ, col0=rank * ncol, nx=1024, device=dev)
+    presence = synth.stats(st)
+    ppt = torch.zeros((4, ncol), dtype=torch.float32, device=dev)
+    tstream = torch.cuda.Stream(device=dev)             # the launching stream: kernels and timing events both go here
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    fptr = [st[k].data_ptr() for k in FIELDS]
+
+    def one_step():
+        th.step_device(ncol, NZ, DT, fptr, p.data_ptr(), dz.data_ptr(), ppt.data_ptr(), stream=stream)
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    th.diag()
+    launches0 = th.gpu_launches
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    for i in range(args.steps):
+        ev[i].record()
+        one_step()
+    ev[args.steps].record()
+    torch.cuda.synchronize()
+    diag = torch.from_numpy(th.diag()).to(dev)          # the 8 domain sums accumulated over the K steps
+    if world > 1:
+        dist.all_reduce(diag)                           # the only collective: 64 bytes of diagnostics
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.summary()
+    launches = th.gpu_launches - launches0
+
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    ms_per_step = total_ms / args.steps
+    value = world * ncol * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernel + D2H every step) --------
+    e2e = None
+    if args.e2e_steps > 0:
+        host = {k: torch.empty((NZ, ncol), dtype=torch.float32).pin_memory() for k in FIELDS}
+        st0, p0, dz0 = synth.make_domain(ncol, nz=NZ, col0=rank * ncol, nx=1024, device=dev)
+        for k in FIELDS:
+            host[k].copy_(st0[k])
+        hp = torch.empty((NZ, ncol), dtype=torch.float32).pin_memory()
+        hp.copy_(p0)
+        del st0, p0
+        hstate = {k: host[k].numpy() for k in FIELDS}
+        hpn, hdz = hp.numpy(), dz0.cpu().numpy()
+        th.step(DT, hstate, hpn, hdz)                    # warm-up (allocates the resident buffers)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            th.step(DT, hstate, hpn, hdz)
+        el = time.perf_counter() - t0
+        tm = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        el = float(tm.item())
+        e2e = {"value": world * ncol * args.e2e_steps / el, "unit": UNIT,
+               "h2d_bytes_per_step": int(ncol * NZ * 4 * 10 + NZ * 4), "d2h_bytes_per_step": int(ncol * NZ * 4 * 9 + ncol * 16),
+               "steps": args.e2e_steps, "ms_per_step": el / args.e2e_steps * 1e3,
+               "api": "kidmp_step (host arrays, COL_FASTEST, pinned)"}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        kern_ms = float(np.mean(per_step))
+        achieved = ALG_BYTES_PER_COLUMN * ncol / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": "synthetic 1024x1024 columns x 60 levels per GPU, CONUS-like convective domain "
+                                   "(kid_b200/synth.py seed 20261018), dt=10s, state evolves in place",
+                       "columns_per_gpu": ncol, "nz": NZ, "dt": DT, "l2": "inputs (2.8 GB/GPU) larger than L2, no flush",
+                       "presence": presence,
+                       "active_column_fraction": float(diag[6].item() / max(diag[7].item(), 1.0))},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_column_step<64>",
+                         "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_COLUMN * ncol},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "diag": {"names": ["ppt_rain", "ppt_ice", "ppt_snow", "ppt_graupel", "lwp", "iwp", "active", "columns"],
+                     "sum_over_steps": [float(x) for x in diag.tolist()]},
+            "table_build_ms": th.table_build_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, ms, init_s = cpu_reference_run(args.cpu_columns, 3, 1, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "first %d columns of the bench domain x 3 steps, OpenMP over columns; C++ "
+                                              "restatement of the reference (no Fortran compiler), init %.1f s excluded"
+                                              % (args.cpu_columns, init_s)}
+        print(json.dumps(line), flush=True)
+    th.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,23 @@ const char* kidmp_rate_names(void);
  * 7 columns processed.  Multi-GPU hosts all-reduce these 8 numbers (NCCL, 64 bytes). */
 int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]);
 
+/* The KiD-facing entry: everything mphys_thompson09_interfacen does for its nx columns except
+ * save_dg (I:54-246).  Arrays are KiD's column_variables in (k,i) order, a[i*nz + k]:
+ * state + (advective + divergence tendency)*dt goes in, theta -> T and exner -> p (I:59-97), the
+ * column step runs, and the new state comes back as microphysics tendencies (I:198-245).
+ * hyd / dhyd_* hold one plane per prognostic moment of hydrometeors(k,i,ih)%moments(1,im), in the
+ * order qc (ih=1,im=1), qr (2,1), nr (2,2), qi (3,1), ni (3,2), qs (4,1), qg (5,1); planes 3..6 may
+ * be NULL when iiwarm.  ppt is [4][nx]: pptrain_2d, pptice_2d, pptsnow_2d, pptgraul_2d (I:183-186). */
+typedef struct kidmp_kid_columns {
+  long nx; int nz;
+  const float *theta, *dtheta_adv, *dtheta_div, *exner, *qv, *dqv_adv, *dqv_div;
+  const float *dz;                       /* dz(k), nz values (I:63) */
+  const float *hyd[7], *dhyd_adv[7], *dhyd_div[7];
+  float *dtheta_mphys, *dqv_mphys, *dhyd_mphys[7];
+  float *ppt;
+} kidmp_kid_columns;
+int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, float p0, float r_on_cp);
+
 /* bookkeeping for benchmarks */
 long kidmp_gpu_launches(const kidmp_handle* h);         /* kernels launched so far          */
 int kidmp_sync(kidmp_handle* h);                        /* wait for the handle's stream     */

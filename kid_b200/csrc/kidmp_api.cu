@@ -3,6 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see kid_b200/build.py).
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cstdarg>
 #include <cstdint>
@@ -14,6 +15,7 @@
 #include "kidmp_hostinit.h"
 #include "kidmp_tables.cuh"
 #include "kidmp_column.cuh"
+#include "kidmp_kid.cuh"
 
 using namespace kidmp;
 
@@ -37,8 +39,11 @@ struct kidmp_handle {
   float* d_ppt = nullptr;        // [4][ncol]
   float* d_stage = nullptr;      // staging for layout conversion, [nz][ncol]
   double* d_partial = nullptr; long partial_blocks = 0;
+  float* d_scratch = nullptr; size_t scratch_cells = 0;   // [SC_N][nz][ncol] hand-off between the two step kernels
+  int* d_colint = nullptr; long scratch_cols = 0;
   double* d_diag = nullptr;
   float* d_rates = nullptr;
+  float* d_kid = nullptr; size_t kid_floats = 0;   // staging of the KiD (k,i) arrays
   float last_ms = 0.f;
   std::map<std::string, std::vector<double>> consts;   // named init constants for parity tests
 };
@@ -203,21 +208,42 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   if (!(a0.dt > 0.f)) return fail(h, "dt must be positive");
   if (ensure_constants(h)) return 1;
   StepArgs a = a0;
-  const int threads = 128;
+  // launch shape (DESIGN.md "Column kernel"): KIDMP_SHAPE = 0: one warp per block; 1: 256-thread lockstep blocks
+  static const int shape = getenv("KIDMP_SHAPE") ? atoi(getenv("KIDMP_SHAPE")) : 0;
+  static const int minb = getenv("KIDMP_MINB") ? atoi(getenv("KIDMP_MINB")) : 8;
+  const int threads = (shape == 1 && a.nz <= 64) ? 256 : 32;
   const long blocks = (a.ncol + threads - 1) / threads;
-  if (blocks > h->partial_blocks) {
+  const int sthreads = 128;
+  const long sblocks = (a.ncol + sthreads - 1) / sthreads;
+  if (sblocks > h->partial_blocks) {
     if (h->d_partial) cudaFree(h->d_partial);
     h->d_partial = nullptr; h->partial_blocks = 0;
-    CK(h, cudaMalloc((void**)&h->d_partial, (size_t)blocks * KIDMP_NDIAG * 8));
-    h->partial_blocks = blocks;
+    CK(h, cudaMalloc((void**)&h->d_partial, (size_t)sblocks * KIDMP_NDIAG * 8));
+    h->partial_blocks = sblocks;
   }
+  const size_t need = (size_t)a.ncol * a.nz;
+  if (need > h->scratch_cells || a.ncol > h->scratch_cols) {
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    if (h->d_colint) cudaFree(h->d_colint);
+    h->d_scratch = nullptr; h->d_colint = nullptr; h->scratch_cells = 0; h->scratch_cols = 0;
+    CK(h, cudaMalloc((void**)&h->d_scratch, need * SC_N * 4));
+    CK(h, cudaMalloc((void**)&h->d_colint, (size_t)a.ncol * 8 * 4));
+    h->scratch_cells = need; h->scratch_cols = a.ncol;
+  }
+  a.scratch = h->d_scratch;
+  a.colint = h->d_colint;
   a.diag_partial = h->d_partial;
   a.rates = h->d_rates;
-  if (a.nz <= 64) k_column_step<64><<<(unsigned)blocks, threads, 0, s>>>(a);
-  else if (a.nz <= 128) k_column_step<128><<<(unsigned)blocks, threads, 0, s>>>(a);
-  else k_column_step<256><<<(unsigned)blocks, threads, 0, s>>>(a);
-  k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)blocks, h->d_diag);
-  h->launches += 2;
+  if (a.nz <= 64) {
+    if (threads == 256) k_column_step<64, 256, 1, true><<<(unsigned)blocks, threads, 0, s>>>(a);
+    else if (minb >= 16) k_column_step<64, 32, 16, false><<<(unsigned)blocks, threads, 0, s>>>(a);
+    else if (minb >= 12) k_column_step<64, 32, 12, false><<<(unsigned)blocks, threads, 0, s>>>(a);
+    else k_column_step<64, 32, 8, false><<<(unsigned)blocks, threads, 0, s>>>(a);
+  } else if (a.nz <= 128) k_column_step<128, 32, 8, false><<<(unsigned)blocks, threads, 0, s>>>(a);
+  else k_column_step<256, 32, 8, false><<<(unsigned)blocks, threads, 0, s>>>(a);
+  k_sediment<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
+  k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)sblocks, h->d_diag);
+  h->launches += 3;
   CK(h, cudaGetLastError());
   return 0;
 }
@@ -337,6 +363,9 @@ int kidmp_finalize(kidmp_handle* h) {
   for (auto& a : table_allocs(h)) if (*a.p) cudaFree(*a.p);
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_diag) cudaFree(h->d_diag);
+  if (h->d_kid) cudaFree(h->d_kid);
+  if (h->d_scratch) cudaFree(h->d_scratch);
+  if (h->d_colint) cudaFree(h->d_colint);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -528,6 +557,72 @@ int kidmp_last_step_ms(kidmp_handle* h, float* step_ms) {
   cudaSetDevice(h->device);
   CK(h, cudaEventSynchronize(h->ev1));
   CK(h, cudaEventElapsedTime(step_ms, h->ev0, h->ev1));
+  return 0;
+}
+
+int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, float p0, float r_on_cp) {
+  if (!h) return 1;
+  if (!c) return fail(h, "kid_interface: null argument");
+  if (!c->theta || !c->dtheta_adv || !c->dtheta_div || !c->exner || !c->qv || !c->dqv_adv || !c->dqv_div || !c->dz ||
+      !c->dtheta_mphys || !c->dqv_mphys || !c->ppt)
+    return fail(h, "kid_interface: null array");
+  const bool warm = h->kc.iiwarm != 0;
+  for (int m = 0; m < 7; ++m) {
+    const bool need = m < 3 || !warm;
+    if (need && (!c->hyd[m] || !c->dhyd_adv[m] || !c->dhyd_div[m] || !c->dhyd_mphys[m]))
+      return fail(h, "kid_interface: hydrometeor plane %d is null", m);
+  }
+  if (!(r_on_cp > 0.f) || !(dt > 0.f)) return fail(h, "kid_interface: dt and r_on_cp must be positive");
+  if (kidmp_state_alloc(h, c->nx, c->nz)) return 1;
+  cudaSetDevice(h->device);
+  const size_t n = (size_t)c->nx * c->nz;
+  const int nplanes = 7 + 21 + 9;
+  if (h->kid_floats < n * nplanes) {
+    if (h->d_kid) cudaFree(h->d_kid);
+    h->d_kid = nullptr; h->kid_floats = 0;
+    CK(h, cudaMalloc((void**)&h->d_kid, n * nplanes * 4));
+    h->kid_floats = n * nplanes;
+  }
+  int slot = 0;
+  cudaError_t ce = cudaSuccess;
+  auto in = [&](const float* src) -> const float* {
+    float* d = h->d_kid + n * (size_t)slot++;
+    if (!src) return nullptr;
+    cudaError_t e = cudaMemcpyAsync(d, src, n * 4, cudaMemcpyHostToDevice, h->stream);
+    if (ce == cudaSuccess) ce = e;
+    return d;
+  };
+  auto out = [&]() { return h->d_kid + n * (size_t)slot++; };
+  KidArgs a{};
+  a.nx = c->nx; a.nz = c->nz; a.dt = dt; a.p0 = p0; a.ooroc = 1.f / r_on_cp; a.iiwarm = warm ? 1 : 0;
+  a.theta = in(c->theta); a.dtheta_adv = in(c->dtheta_adv); a.dtheta_div = in(c->dtheta_div); a.exner = in(c->exner);
+  a.qv = in(c->qv); a.dqv_adv = in(c->dqv_adv); a.dqv_div = in(c->dqv_div);
+  for (int m = 0; m < 7; ++m) {
+    const bool use = m < 3 || !warm;
+    a.hyd[m] = in(use ? c->hyd[m] : nullptr); a.dhyd_adv[m] = in(use ? c->dhyd_adv[m] : nullptr);
+    a.dhyd_div[m] = in(use ? c->dhyd_div[m] : nullptr);
+  }
+  a.dtheta_mphys = out(); a.dqv_mphys = out();
+  for (int m = 0; m < 7; ++m) a.dhyd_mphys[m] = out();
+  if (ce != cudaSuccess) return fail(h, "kid_interface: H2D copy: %s", cudaGetErrorString(ce));
+  for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = field_ptr(h, q);
+  a.p = field_ptr(h, KIDMP_NFIELDS);
+  CK(h, cudaMemcpyAsync(h->d_dz, c->dz, (size_t)c->nz * 4, cudaMemcpyHostToDevice, h->stream));
+  dim3 g((unsigned)((c->nx + 31) / 32), (unsigned)((c->nz + 31) / 32)), b(32, 8);
+  k_kid_gather<<<g, b, 0, h->stream>>>(a);
+  ++h->launches;
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  if (launch_step(h, resident_args(h, dt), h->stream)) return 1;
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  k_kid_scatter<<<g, b, 0, h->stream>>>(a);
+  ++h->launches;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(c->dtheta_mphys, a.dtheta_mphys, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(c->dqv_mphys, a.dqv_mphys, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  for (int m = 0; m < 7; ++m)
+    if (m < 3 || !warm) CK(h, cudaMemcpyAsync(c->dhyd_mphys[m], a.dhyd_mphys[m], n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(c->ppt, h->d_ppt, (size_t)c->nx * 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
 

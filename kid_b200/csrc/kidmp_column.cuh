@@ -108,7 +108,7 @@ __device__ __forceinline__ void graupel_n0(bool above_k0, bool L_qr, float mvd_r
   N0_min = fmin(N0_exp, N0_min);
   N0_exp = N0_min;
   const double lam_exp = sqrt(sqrt(N0_exp * (double)ck.am_g * (double)ck.cgg[0] / (double)rg));   // **oge1, oge1 = 1/4
-  const double lamg = lam_exp * (double)pow_f(ck.cgg[2] * ck.ogg2 * ck.ogg1, ck.obmg);
+  const double lamg = lam_exp * (double)ck.lamg_fac;
   ilamg = (double)1.f / lamg;
   N0_g = N0_exp / ((double)ck.cgg[1] * lam_exp) * lamg;                                         // lamg**cge(2), cge(2) = 1
 }
@@ -119,8 +119,15 @@ struct ColPtrs {
 };
 enum { F_QV = 0, F_QC, F_QI, F_QR, F_QS, F_QG, F_NI, F_NR, F_T };
 
-template <int NZMAX>
-__global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
+// One warp per block: a warp of clear-sky columns retires at once and its slot goes to the next
+// block instead of waiting at a block barrier for a cloudy neighbour (profiles/r01).
+// LOCKSTEP (block of several warps): the cloudy warps of a block meet at a named barrier at every
+// level of the pass-1 sweep, so they run the same ~170 KB of straight-line code at the same time
+// and share its instruction-cache lines instead of each streaming it from L2 on its own.
+template <int NZMAX, int BLOCK, int MINB, bool LOCKSTEP>
+__global__ void __launch_bounds__(BLOCK, MINB) k_column_step(StepArgs a) {
+  __shared__ int s_active_warps;
+  if (LOCKSTEP) { if (threadIdx.x == 0) s_active_warps = 0; __syncthreads(); }
   const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = col < a.ncol;
   const int nz = a.nz;
@@ -129,8 +136,6 @@ __global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
   const float odt = 1.f / DT, odts = 1.f / DT;
   const float Nt_c = ck.Nt_c;
   const bool iiwarm = ck.iiwarm != 0;
-  float ppt_r = 0.f, ppt_i = 0.f, ppt_s = 0.f, ppt_g = 0.f;
-  double lwp = 0.0, iwp = 0.0;
   bool active = false;
 
   if (in_range) {
@@ -161,15 +166,20 @@ __global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
       if (ssati > 0.0f) no_micro = false;
     }
     active = !no_micro;
-
-    if (active) {
-      // per-level values handed from pass 1 to pass 2 (thread-private, cached in L1/L2)
-      float tten[NZMAX], qvten[NZMAX], qcten[NZMAX], qiten[NZMAX], qrten[NZMAX], qsten[NZMAX], qgten[NZMAX],
-          niten[NZMAX], nrten[NZMAX], ncten[NZMAX];
-      float a_rr[NZMAX], a_nr[NZMAX], a_ri[NZMAX], a_ni[NZMAX], a_rs[NZMAX], a_rg[NZMAX];
-      float vtrk[NZMAX], vtnrk[NZMAX], vtik[NZMAX], vtnik[NZMAX], vtsk[NZMAX], vtgk[NZMAX];
-      float a_rho[NZMAX], a_temp[NZMAX], a_ocp[NZMAX], a_lvap[NZMAX];
-
+  }
+  const bool warp_active = __any_sync(0xffffffffu, active);
+  int lock_threads = 0;
+  if (LOCKSTEP) {
+    if (warp_active && (threadIdx.x & 31) == 0) atomicAdd(&s_active_warps, 1);
+    __syncthreads();
+    lock_threads = s_active_warps * 32;
+  }
+  if (warp_active) {
+    const float* __restrict__ Gp = a.p + col;
+    float* Gqv = a.f[F_QV] + col; float* Gqc = a.f[F_QC] + col; float* Gqi = a.f[F_QI] + col;
+    float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
+    float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
+    {
       // carried from the level above
       double N0_min_a = (double)KP_GONV_MAX, N0_min_b = (double)KP_GONV_MAX;
       bool warm_above_a = false, warm_above_b = false;     // any level >= k with temp >= 270.65 (k_0, M:1635)
@@ -180,6 +190,8 @@ __global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
       // ================= pass 1: top-down, S1..S13 per level ====================================
 #pragma unroll 1
       for (int k = nz - 1; k >= 0; --k) {
+        if (LOCKSTEP) { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"r"(lock_threads) : "memory"); }
+        if (active) {
         const long o = (long)k * ncol;
         const float t1d = Gt[o], qv1d = Gqv[o], pres = Gp[o];
         float qc1d = Gqc[o], qi1d = Gqi[o], qr1d = Gqr[o], qs1d = Gqs[o], qg1d = Gqg[o];
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
           mvd_c = (float)((double)(3.0f + (float)nu_c + 0.672f) / lamc);
         }
         if (rc > 0.01e-3f) {
-          const float Dc_g = (float)(((double)pow_f(ck.ccg[2][nu_c - 1] * ck.ocg2[nu_c - 1], ck.obmr) / lamc) * (double)1.E6f);
+          const float Dc_g = (float)(((double)ck.dcg_fac[nu_c - 1] / lamc) * (double)1.E6f);
           const float Dc_b = pow_f(xDc * xDc * xDc * Dc_g * Dc_g * Dc_g - xDc * xDc * xDc * xDc * xDc * xDc, 1.f / 6.f);
           const float zeta1 = 0.5f * ((6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f) + fabsf(6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f));
           const float zeta = 0.027f * rc * zeta1;
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
           if (rr > ck.r_r1) {
             idx_r = decade_idx_f(rr, ck.nir2, NTB_R);
             lamr = (double)1.f / ilamr;
-            const double lam_exp = lamr * (double)cube_f(ck.crg[2] * ck.org2 * ck.org1);
+            const double lam_exp = lamr * (double)ck.n0r_fac;
             const double N0_exp = (double)(ck.org1 * rr / ck.am_r) * sq_d(sq_d(lam_exp));   // **cre(1), cre(1) = 4
             idx_r1 = decade_idx_d(N0_exp, ck.nir3, NTB_R1);
           }
@@ -360,7 +372,7 @@ __global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
           if (rg > ck.r_g1) {
             idx_g = decade_idx_f(rg, ck.nig2, NTB_G);
             const double lamg = (double)1.f / ilamg;
-            const double lam_exp = lamg * (double)cube_f(ck.cgg[2] * ck.ogg2 * ck.ogg1);
+            const double lam_exp = lamg * (double)ck.n0g_fac;
             const double N0_exp = (double)(ck.ogg1 * rg / ck.am_g) * sq_d(sq_d(lam_exp));   // **cge(1), cge(1) = 4
             idx_g1 = decade_idx_d(N0_exp, ck.nig3, NTB_G1);
           }
@@ -960,159 +972,201 @@ __global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
         }
         vtr_up = v_r; vtnr_up = v_nr; vti_up = v_i; vtni_up = v_ni; vts_up = v_s; vtg_up = v_g;
 
-        tten[k] = tt; qvten[k] = qvt; qcten[k] = qct; qiten[k] = qit; qrten[k] = qrt; qsten[k] = qst; qgten[k] = qgt;
-        niten[k] = nit; nrten[k] = nrt; ncten[k] = nct;
-        a_rr[k] = rr; a_nr[k] = nr; a_ri[k] = ri; a_ni[k] = ni; a_rs[k] = rs; a_rg[k] = rg;
-        vtrk[k] = v_r; vtnrk[k] = v_nr; vtik[k] = v_i; vtnik[k] = v_ni; vtsk[k] = v_s; vtgk[k] = v_g;
-        a_rho[k] = rho; a_temp[k] = temp; a_ocp[k] = ocp; a_lvap[k] = lvap;
+        // hand-off to the sedimentation kernel: [SC_N][nz][ncol], coalesced fire-and-forget stores.
+        // S15 (M:3584-3606) needs lfus*ocp where the level ends above T_0 and lfus2*ocp where it ends
+        // below HGFR (never both): one signed value carries the product and the case.
+        {
+          float s15 = 0.0f;
+          if (temp > T_0) s15 = ck.lfus * ocp;
+          else if (temp < KP_HGFR) s15 = -((KP_LSUB - lvap) * ocp);
+          float* sc = a.scratch + o + col;
+          const long ss = (long)nz * ncol;
+          sc[SC_TTEN * ss] = tt; sc[SC_QVTEN * ss] = qvt; sc[SC_QCTEN * ss] = qct; sc[SC_QITEN * ss] = qit;
+          sc[SC_QRTEN * ss] = qrt; sc[SC_QSTEN * ss] = qst; sc[SC_QGTEN * ss] = qgt; sc[SC_NITEN * ss] = nit;
+          sc[SC_NRTEN * ss] = nrt; sc[SC_NCTEN * ss] = nct;
+          sc[SC_RR * ss] = rr; sc[SC_NR * ss] = nr; sc[SC_RI * ss] = ri; sc[SC_NI * ss] = ni; sc[SC_RS * ss] = rs; sc[SC_RG * ss] = rg;
+          sc[SC_VTR * ss] = v_r; sc[SC_VTNR * ss] = v_nr; sc[SC_VTI * ss] = v_i; sc[SC_VTNI * ss] = v_ni;
+          sc[SC_VTS * ss] = v_s; sc[SC_VTG * ss] = v_g; sc[SC_RHO * ss] = rho; sc[SC_S15 * ss] = s15;
+        }
+        }
       }
 
-      // ================= pass 2: S14 sedimentation, M:3365-3578 =======================================
-      const int kte = nz;   // 1-based top
+      // column summary for the sedimentation kernel: [8][ncol] substep counts and top sedimenting levels
+      if (active) {
+        int* ci = a.colint + col;
+        ci[0] = nstep_r; ci[ncol] = nstep_i; ci[2 * ncol] = nstep_s; ci[3 * ncol] = nstep_g;
+        ci[4 * ncol] = ksed_r; ci[5 * ncol] = ksed_i; ci[6 * ncol] = ksed_s; ci[7 * ncol] = ksed_g;
+      }
+    }
+  }
+  if (in_range && !active) a.colint[col] = -1;      // clear-sky column: nothing left to do
+}
+
+// ---- K2: sub-stepped upwind sedimentation (M:3365-3578), instant melt / freeze (M:3584-3606), apply
+// tendencies and final clamps (M:3623-3686).  One thread per column, light on registers, so many
+// warps per SM hide the latency of streaming the hand-off arrays.  All but the last sub-step of a
+// species update the hand-off arrays in place; the last sub-step of all four species is fused with
+// S15/S16 and the output stores in one top-down sweep (the common nstep = 1 case is that sweep only).
+__device__ __forceinline__ void sed_substeps(float* __restrict__ r, float* __restrict__ rten, const float* __restrict__ v,
+                                             float* __restrict__ n, float* __restrict__ nten, const float* __restrict__ vn,
+                                             const float* __restrict__ rhoa, const float* __restrict__ dz, int nz, long ncol,
+                                             int nsub, int ksed, float onstep, float DT, bool on, float nfloor, float& ppt) {
+  for (int it = 0; it < nsub; ++it) {
+    float sr_up = 0.f, sn_up = 0.f, sr_k = 0.f, r0 = 0.f;
+#pragma unroll 1
+    for (int k = nz - 1; k >= 0; --k) {
+      const long o = (long)k * ncol;
+      const float rk = r[o];
+      const float sr = on ? v[o] * rk : 0.f;
+      const float odzq = 1.f / dz[k], orho = 1.f / rhoa[o];
+      float nk = 0.f, sn = 0.f;
+      if (n) { nk = n[o]; sn = on ? vn[o] * nk : 0.f; }
+      if (k == nz - 1) {
+        rten[o] = rten[o] - sr * odzq * onstep * orho;
+        r0 = fmaxf(KP_R1, rk - sr * odzq * DT * onstep);
+        r[o] = r0;
+        if (n) { nten[o] = nten[o] - sn * odzq * onstep * orho; n[o] = fmaxf(nfloor, nk - sn * odzq * DT * onstep); }
+      } else if (k + 1 <= ksed) {
+        rten[o] = rten[o] + (sr_up - sr) * odzq * onstep * orho;
+        r0 = fmaxf(KP_R1, rk + (sr_up - sr) * odzq * DT * onstep);
+        r[o] = r0;
+        if (n) { nten[o] = nten[o] + (sn_up - sn) * odzq * onstep * orho; n[o] = fmaxf(nfloor, nk + (sn_up - sn) * odzq * DT * onstep); }
+      } else {
+        r0 = rk;
+      }
+      sr_up = sr; sn_up = sn; sr_k = sr;
+    }
+    if (r0 > KP_R1 * 10.f) ppt = ppt + sr_k * DT * onstep;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_sediment(StepArgs a) {
+  const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = col < a.ncol;
+  const int nz = a.nz;
+  const long ncol = a.ncol;
+  const float DT = a.dt, odt = 1.f / DT;
+  float ppt_r = 0.f, ppt_i = 0.f, ppt_s = 0.f, ppt_g = 0.f;
+  double lwp = 0.0, iwp = 0.0;
+  bool active = false;
+  if (in_range) {
+    const int* ci = a.colint + col;
+    int nstep_r = ci[0];
+    active = nstep_r >= 0;
+    if (active) {
+      const int nstep_i = ci[ncol], nstep_s = ci[2 * ncol], nstep_g = ci[3 * ncol];
+      int ksed_r = ci[4 * ncol], ksed_i = ci[5 * ncol], ksed_s = ci[6 * ncol], ksed_g = ci[7 * ncol];
+      const int kte = nz;
       if (ksed_r == kte) ksed_r = kte - 1;
       if (ksed_i == kte) ksed_i = kte - 1;
       if (ksed_s == kte) ksed_s = kte - 1;
       if (ksed_g == kte) ksed_g = kte - 1;
-      {
-        // rain (U6: never gated by l_sediment)
-        const float onstep = nstep_r > 0 ? 1.f / (float)nstep_r : 1.0f;
-        const int nstep = nint_f(1.f / onstep);
-        for (int n = 0; n < nstep; ++n) {
-          float sr_up = 0.f, sn_up = 0.f, sr_k = 0.f;
-#pragma unroll 1
-          for (int k = nz - 1; k >= 0; --k) {
-            const float sr = vtrk[k] * a_rr[k], sn = vtnrk[k] * a_nr[k];
-            const float odzq = 1.f / a.dz[k], orho = 1.f / a_rho[k];
-            if (k == nz - 1) {
-              qrten[k] = qrten[k] - sr * odzq * onstep * orho;
-              nrten[k] = nrten[k] - sn * odzq * onstep * orho;
-              a_rr[k] = fmaxf(R1, a_rr[k] - sr * odzq * DT * onstep);
-              a_nr[k] = fmaxf(R2, a_nr[k] - sn * odzq * DT * onstep);
-            } else if (k + 1 <= ksed_r) {
-              qrten[k] = qrten[k] + (sr_up - sr) * odzq * onstep * orho;
-              nrten[k] = nrten[k] + (sn_up - sn) * odzq * onstep * orho;
-              a_rr[k] = fmaxf(R1, a_rr[k] + (sr_up - sr) * odzq * DT * onstep);
-              a_nr[k] = fmaxf(R2, a_nr[k] + (sn_up - sn) * odzq * DT * onstep);
-            }
-            sr_up = sr; sn_up = sn; sr_k = sr;
-          }
-          if (a_rr[0] > R1 * 10.f) ppt_r = ppt_r + sr_k * DT * onstep;
-        }
-      }
-      // cloud-water stub M:3414-3425: vtck/vtnck are never assigned (U2) => no-op.
-      {
-        const float onstep = nstep_i > 0 ? 1.f / (float)nstep_i : 1.0f;
-        const int nstep = nint_f(1.f / onstep);
-        const bool sedi = ck.l_sediment != 0;
-        for (int n = 0; n < nstep; ++n) {
-          float si_up = 0.f, sn_up = 0.f, si_k = 0.f;
-#pragma unroll 1
-          for (int k = nz - 1; k >= 0; --k) {
-            const float si = sedi ? vtik[k] * a_ri[k] : 0.f, sn = sedi ? vtnik[k] * a_ni[k] : 0.f;
-            const float odzq = 1.f / a.dz[k], orho = 1.f / a_rho[k];
-            if (k == nz - 1) {
-              qiten[k] = qiten[k] - si * odzq * onstep * orho;
-              niten[k] = niten[k] - sn * odzq * onstep * orho;
-              a_ri[k] = fmaxf(R1, a_ri[k] - si * odzq * DT * onstep);
-              a_ni[k] = fmaxf(R2, a_ni[k] - sn * odzq * DT * onstep);
-            } else if (k + 1 <= ksed_i) {
-              qiten[k] = qiten[k] + (si_up - si) * odzq * onstep * orho;
-              niten[k] = niten[k] + (sn_up - sn) * odzq * onstep * orho;
-              a_ri[k] = fmaxf(R1, a_ri[k] + (si_up - si) * odzq * DT * onstep);
-              a_ni[k] = fmaxf(R2, a_ni[k] + (sn_up - sn) * odzq * DT * onstep);
-            }
-            si_up = si; sn_up = sn; si_k = si;
-          }
-          if (a_ri[0] > R1 * 10.f) ppt_i = ppt_i + si_k * DT * onstep;
-        }
-      }
-      {
-        const float onstep = nstep_s > 0 ? 1.f / (float)nstep_s : 1.0f;
-        const int nstep = nint_f(1.f / onstep);
-        const bool sedi = ck.l_sediment != 0;
-        for (int n = 0; n < nstep; ++n) {
-          float ss_up = 0.f, ss_k = 0.f;
-#pragma unroll 1
-          for (int k = nz - 1; k >= 0; --k) {
-            const float ss = sedi ? vtsk[k] * a_rs[k] : 0.f;
-            const float odzq = 1.f / a.dz[k], orho = 1.f / a_rho[k];
-            if (k == nz - 1) {
-              qsten[k] = qsten[k] - ss * odzq * onstep * orho;
-              a_rs[k] = fmaxf(R1, a_rs[k] - ss * odzq * DT * onstep);
-            } else if (k + 1 <= ksed_s) {
-              qsten[k] = qsten[k] + (ss_up - ss) * odzq * onstep * orho;
-              a_rs[k] = fmaxf(R1, a_rs[k] + (ss_up - ss) * odzq * DT * onstep);
-            }
-            ss_up = ss; ss_k = ss;
-          }
-          if (a_rs[0] > R1 * 10.f) ppt_s = ppt_s + ss_k * DT * onstep;
-        }
-      }
-      {
-        const float onstep = nstep_g > 0 ? 1.f / (float)nstep_g : 1.0f;
-        const int nstep = nint_f(1.f / onstep);
-        const bool sedi = ck.l_sediment != 0;
-        for (int n = 0; n < nstep; ++n) {
-          float sg_up = 0.f, sg_k = 0.f;
-#pragma unroll 1
-          for (int k = nz - 1; k >= 0; --k) {
-            const float sg = sedi ? vtgk[k] * a_rg[k] : 0.f;
-            const float odzq = 1.f / a.dz[k], orho = 1.f / a_rho[k];
-            if (k == nz - 1) {
-              qgten[k] = qgten[k] - sg * odzq * onstep * orho;
-              a_rg[k] = fmaxf(R1, a_rg[k] - sg * odzq * DT * onstep);
-            } else if (k + 1 <= ksed_g) {
-              qgten[k] = qgten[k] + (sg_up - sg) * odzq * onstep * orho;
-              a_rg[k] = fmaxf(R1, a_rg[k] + (sg_up - sg) * odzq * DT * onstep);
-            }
-            sg_up = sg; sg_k = sg;
-          }
-          if (a_rg[0] > R1 * 10.f) ppt_g = ppt_g + sg_k * DT * onstep;
-        }
-      }
+      const float on_r = nstep_r > 0 ? 1.f / (float)nstep_r : 1.0f, on_i = nstep_i > 0 ? 1.f / (float)nstep_i : 1.0f;
+      const float on_s = nstep_s > 0 ? 1.f / (float)nstep_s : 1.0f, on_g = nstep_g > 0 ? 1.f / (float)nstep_g : 1.0f;
+      const int n_r = nint_f(1.f / on_r), n_i = nint_f(1.f / on_i), n_s = nint_f(1.f / on_s), n_g = nint_f(1.f / on_g);
+      const bool sedi = ck.l_sediment != 0;
+      const long ss = (long)nz * ncol;
+      float* sc = a.scratch + col;
+      const float* rhoa = sc + SC_RHO * ss;
+      // all but the last sub-step (rain is never gated by l_sediment, U6; the cloud-water stub M:3414-3425 is a no-op, U2)
+      if (n_r > 1) sed_substeps(sc + SC_RR * ss, sc + SC_QRTEN * ss, sc + SC_VTR * ss, sc + SC_NR * ss, sc + SC_NRTEN * ss,
+                                sc + SC_VTNR * ss, rhoa, a.dz, nz, ncol, n_r - 1, ksed_r, on_r, DT, true, KP_R2, ppt_r);
+      if (n_i > 1) sed_substeps(sc + SC_RI * ss, sc + SC_QITEN * ss, sc + SC_VTI * ss, sc + SC_NI * ss, sc + SC_NITEN * ss,
+                                sc + SC_VTNI * ss, rhoa, a.dz, nz, ncol, n_i - 1, ksed_i, on_i, DT, sedi, KP_R2, ppt_i);
+      if (n_s > 1) sed_substeps(sc + SC_RS * ss, sc + SC_QSTEN * ss, sc + SC_VTS * ss, nullptr, nullptr, nullptr, rhoa, a.dz,
+                                nz, ncol, n_s - 1, ksed_s, on_s, DT, sedi, 0.f, ppt_s);
+      if (n_g > 1) sed_substeps(sc + SC_RG * ss, sc + SC_QGTEN * ss, sc + SC_VTG * ss, nullptr, nullptr, nullptr, rhoa, a.dz,
+                                nz, ncol, n_g - 1, ksed_g, on_g, DT, sedi, 0.f, ppt_g);
 
-      // ================= S15 + S16, M:3584-3686, and the stores ==========================================
+      // last sub-step of every species + S15 + S16, one top-down sweep
+      const float* __restrict__ Gp = a.p + col;
+      float* Gqv = a.f[F_QV] + col; float* Gqc = a.f[F_QC] + col; float* Gqi = a.f[F_QI] + col;
+      float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
+      float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
+      const bool iiwarm = ck.iiwarm != 0;
+      const float Nt_c = ck.Nt_c;
+      float sr_up = 0.f, snr_up = 0.f, si_up = 0.f, sni_up = 0.f, ss_up = 0.f, sg_up = 0.f;
 #pragma unroll 1
-      for (int k = 0; k < nz; ++k) {
+      for (int k = nz - 1; k >= 0; --k) {
         const long o = (long)k * ncol;
+        const float* q = sc + o;
+        float tt = q[SC_TTEN * ss], qvt = q[SC_QVTEN * ss], qct = q[SC_QCTEN * ss], qit = q[SC_QITEN * ss];
+        float qrt = q[SC_QRTEN * ss], qst = q[SC_QSTEN * ss], qgt = q[SC_QGTEN * ss], nit = q[SC_NITEN * ss];
+        float nrt = q[SC_NRTEN * ss], nct = q[SC_NCTEN * ss];
+        const float rho = q[SC_RHO * ss], s15 = q[SC_S15 * ss];
+        const float rr = q[SC_RR * ss], nr = q[SC_NR * ss], ri = q[SC_RI * ss], ni = q[SC_NI * ss], rs = q[SC_RS * ss], rg = q[SC_RG * ss];
+        const float odzq = 1.f / a.dz[k], orho = 1.f / rho;
+        const float sr = q[SC_VTR * ss] * rr, snr = q[SC_VTNR * ss] * nr;
+        const float si = sedi ? q[SC_VTI * ss] * ri : 0.f, sni = sedi ? q[SC_VTNI * ss] * ni : 0.f;
+        const float ssn = sedi ? q[SC_VTS * ss] * rs : 0.f, sg = sedi ? q[SC_VTG * ss] * rg : 0.f;
+        float rr_n = rr, ri_n = ri, rs_n = rs, rg_n = rg;
+        if (k == nz - 1) {
+          qrt = qrt - sr * odzq * on_r * orho;   nrt = nrt - snr * odzq * on_r * orho;
+          rr_n = fmaxf(KP_R1, rr - sr * odzq * DT * on_r);
+          qit = qit - si * odzq * on_i * orho;   nit = nit - sni * odzq * on_i * orho;
+          ri_n = fmaxf(KP_R1, ri - si * odzq * DT * on_i);
+          qst = qst - ssn * odzq * on_s * orho;  rs_n = fmaxf(KP_R1, rs - ssn * odzq * DT * on_s);
+          qgt = qgt - sg * odzq * on_g * orho;   rg_n = fmaxf(KP_R1, rg - sg * odzq * DT * on_g);
+        } else {
+          if (k + 1 <= ksed_r) {
+            qrt = qrt + (sr_up - sr) * odzq * on_r * orho;   nrt = nrt + (snr_up - snr) * odzq * on_r * orho;
+            rr_n = fmaxf(KP_R1, rr + (sr_up - sr) * odzq * DT * on_r);
+          }
+          if (k + 1 <= ksed_i) {
+            qit = qit + (si_up - si) * odzq * on_i * orho;   nit = nit + (sni_up - sni) * odzq * on_i * orho;
+            ri_n = fmaxf(KP_R1, ri + (si_up - si) * odzq * DT * on_i);
+          }
+          if (k + 1 <= ksed_s) {
+            qst = qst + (ss_up - ssn) * odzq * on_s * orho;  rs_n = fmaxf(KP_R1, rs + (ss_up - ssn) * odzq * DT * on_s);
+          }
+          if (k + 1 <= ksed_g) {
+            qgt = qgt + (sg_up - sg) * odzq * on_g * orho;   rg_n = fmaxf(KP_R1, rg + (sg_up - sg) * odzq * DT * on_g);
+          }
+        }
+        sr_up = sr; snr_up = snr; si_up = si; sni_up = sni; ss_up = ssn; sg_up = sg;
+        if (k == 0) {                                         // surface precipitation of the last sub-step, M:3391-3392
+          if (rr_n > KP_R1 * 10.f) ppt_r = ppt_r + sr * DT * on_r;
+          if (ri_n > KP_R1 * 10.f) ppt_i = ppt_i + si * DT * on_i;
+          if (rs_n > KP_R1 * 10.f) ppt_s = ppt_s + ssn * DT * on_s;
+          if (rg_n > KP_R1 * 10.f) ppt_g = ppt_g + sg * DT * on_g;
+        }
+
+        // ---- S15 + S16 for this level ----------------------------------------------------------------
         float t1d = Gt[o], qv1d = Gqv[o], qc1d = Gqc[o], qi1d = Gqi[o], qr1d = Gqr[o], qs1d = Gqs[o], qg1d = Gqg[o];
         float ni1d = Gni[o], nr1d = Gnr[o];
         const float pres = Gp[o];
-        float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));
-        if (!(qc1d > R1)) { qc1d = 0.f; nc1d = 0.f; }
-        if (!(qi1d > R1)) { qi1d = 0.f; ni1d = 0.f; }
-        if (!(qr1d > R1)) { qr1d = 0.f; nr1d = 0.f; }
-        if (!(qs1d > R1)) qs1d = 0.f;
-        if (!(qg1d > R1)) qg1d = 0.f;
-        float tt = tten[k], qct = qcten[k], nct = ncten[k], qit = qiten[k], nit = niten[k];
-        const float rho = a_rho[k];
+        float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));   // U1
+        if (!(qc1d > KP_R1)) { qc1d = 0.f; nc1d = 0.f; }
+        if (!(qi1d > KP_R1)) { qi1d = 0.f; ni1d = 0.f; }
+        if (!(qr1d > KP_R1)) { qr1d = 0.f; nr1d = 0.f; }
+        if (!(qs1d > KP_R1)) qs1d = 0.f;
+        if (!(qg1d > KP_R1)) qg1d = 0.f;
         if (!iiwarm) {
           const float xri = fmaxf(0.0f, qi1d + qit * DT);
-          if ((a_temp[k] > T_0) && (xri > 0.0f)) {
+          if ((s15 > 0.f) && (xri > 0.0f)) {                  // temp > T_0
             qct = qct + xri * odt;
             nct = nct + ni1d * odt;
             qit = qit - xri * odt;
             nit = -ni1d * odt;
-            tt = tt - ck.lfus * a_ocp[k] * xri * odt * 1.0f;
+            tt = tt - s15 * xri * odt * 1.0f;
           }
           const float xrc = fmaxf(0.0f, qc1d + qct * DT);
-          if ((a_temp[k] < KP_HGFR) && (xrc > 0.0f)) {
-            const float lfus2 = KP_LSUB - a_lvap[k];
+          if ((s15 < 0.f) && (xrc > 0.0f)) {                  // temp < HGFR
             const float xnc = nc1d + nct * DT;
             qit = qit + xrc * odt;
             nit = nit + xnc * odt;
             qct = qct - xrc * odt;
             nct = nct - xnc * odt;
-            tt = tt + lfus2 * a_ocp[k] * xrc * odt * 1.0f;
+            tt = tt + (-s15) * xrc * odt * 1.0f;
           }
         }
         t1d = t1d + tt * DT;
-        qv1d = fmaxf(1.E-10f, qv1d + qvten[k] * DT);
+        qv1d = fmaxf(1.E-10f, qv1d + qvt * DT);
         qc1d = qc1d + qct * DT;
-        if (qc1d <= R1) qc1d = 0.0f;              // nc1d is not returned to the host (I:143-152, I:198-245)
+        if (qc1d <= KP_R1) qc1d = 0.0f;              // nc1d is not returned to the host (I:143-152, I:198-245)
         qi1d = qi1d + qit * DT;
-        ni1d = fmaxf(R2 / rho, ni1d + nit * DT);
-        if (qi1d <= R1) {
+        ni1d = fmaxf(KP_R2 / rho, ni1d + nit * DT);
+        if (qi1d <= KP_R1) {
           qi1d = 0.0f; ni1d = 0.0f;
         } else {
           double lami = ice_lam(ni1d, qi1d);
@@ -1122,21 +1176,21 @@ __global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
           else if (xDi > 300.E-6f) lami = (double)(ck.cie[1] / 300.E-6f);
           ni1d = (float)fmin((double)(ck.cig[0] * ck.oig2 * qi1d / ck.am_i) * cube_d(lami), 499.E3 / (double)rho);
         }
-        qr1d = qr1d + qrten[k] * DT;
-        nr1d = fmaxf(R2 / rho, nr1d + nrten[k] * DT);
-        if (qr1d <= R1) {
+        qr1d = qr1d + qrt * DT;
+        nr1d = fmaxf(KP_R2 / rho, nr1d + nrt * DT);
+        if (qr1d <= KP_R1) {
           qr1d = 0.0f; nr1d = 0.0f;
         } else {
           const double lamr = rain_lam(nr1d, qr1d);
           float mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
           if (mvd_r > 2.5E-3f) mvd_r = 2.5E-3f;
-          else if (mvd_r < D0r * 0.75f) mvd_r = D0r * 0.75f;
+          else if (mvd_r < KP_D0R * 0.75f) mvd_r = KP_D0R * 0.75f;
           nr1d = nr_from_mvd(qr1d, mvd_r);
         }
-        qs1d = qs1d + qsten[k] * DT;
-        if (qs1d <= R1) qs1d = 0.0f;
-        qg1d = qg1d + qgten[k] * DT;
-        if (qg1d <= R1) qg1d = 0.0f;
+        qs1d = qs1d + qst * DT;
+        if (qs1d <= KP_R1) qs1d = 0.0f;
+        qg1d = qg1d + qgt * DT;
+        if (qg1d <= KP_R1) qg1d = 0.0f;
         Gt[o] = t1d; Gqv[o] = qv1d; Gqc[o] = qc1d; Gqi[o] = qi1d; Gqr[o] = qr1d; Gqs[o] = qs1d; Gqg[o] = qg1d;
         Gni[o] = ni1d; Gnr[o] = nr1d;
         // domain diagnostics: liquid / ice water paths of the new state
@@ -1145,7 +1199,6 @@ __global__ void __launch_bounds__(128) k_column_step(StepArgs a) {
         iwp += (double)((qi1d + qs1d + qg1d) * rho_new * a.dz[k]);
       }
     }
-
     // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
     a.ppt[col] = ppt_r; a.ppt[ncol + col] = ppt_i; a.ppt[2 * ncol + col] = ppt_s; a.ppt[3 * ncol + col] = ppt_g;
   }

@@ -198,6 +198,11 @@ inline void compute(const kidmp_config& cfg, KConst& kc, HostBins& hb, Prep& pp)
   kc.Dr1 = hb.Dr[0]; kc.Ds1 = hb.Ds[0];
   kc.lnDr = std::log(hb.Dr[NBINS - 1] / hb.Dr[0]); kc.lnDs = std::log(hb.Ds[NBINS - 1] / hb.Ds[0]);
 
+  kc.n0r_fac = std::pow(kc.crg[2] * kc.org2 * kc.org1, bm_r);
+  kc.n0g_fac = std::pow(kc.cgg[2] * kc.ogg2 * kc.ogg1, bm_g);
+  kc.lamg_fac = std::pow(kc.cgg[2] * kc.ogg2 * kc.ogg1, kc.obmg);
+  for (int n = 0; n < 15; ++n) kc.dcg_fac[n] = std::pow(kc.ccg[2][n] * kc.ocg2[n], kc.obmr);
+
   // ---- per-axis-node scalars of the table builders ------------------------------------------------
   pp.am_s = am_s;
   pp.lamr.resize(NTB_R * NTB_R1); pp.N0_r.resize(NTB_R * NTB_R1);

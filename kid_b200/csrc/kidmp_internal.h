@@ -85,6 +85,10 @@ struct KConst {
   int iiwarm, l_sediment;
   float r_c1, r_i1, r_r1, r_s1, r_g1, Nt_i1;        // first axis nodes (M:215-279)
   float p10[64];                                    // 10.**n as libgcc powi builds it, n = -32..31
+  // constant sub-expressions of the column step, evaluated once on the host with libm like the
+  // reference evaluates them every level: (crg(3)*org2*org1)**bm_r M:1844, (cgg(3)*ogg2*ogg1)**bm_g
+  // M:1888, (cgg(3)*ogg2*ogg1)**obmg M:1651, (ccg(3,nu_c)*ocg2(nu_c))**obmr M:1701
+  float n0r_fac, n0g_fac, lamg_fac, dcg_fac[15];
   double Dr1, Ds1, lnDr, lnDs;                      // Dr(1), Ds(1), DLOG(Dr(nbr)/Dr(1)), DLOG(Ds(nbs)/Ds(1))
   // device tables
   const double* racg;   // [N_RACG][G_N]
@@ -96,6 +100,10 @@ struct KConst {
   const float* efsw;
 };
 
+// hand-off arrays written by the column-physics kernel and consumed by the sedimentation kernel
+enum { SC_TTEN = 0, SC_QVTEN, SC_QCTEN, SC_QITEN, SC_QRTEN, SC_QSTEN, SC_QGTEN, SC_NITEN, SC_NRTEN, SC_NCTEN,
+       SC_RR, SC_NR, SC_RI, SC_NI, SC_RS, SC_RG, SC_VTR, SC_VTNR, SC_VTI, SC_VTNI, SC_VTS, SC_VTG, SC_RHO, SC_S15, SC_N };
+
 struct StepArgs {
   long ncol;
   int nz;
@@ -104,6 +112,8 @@ struct StepArgs {
   const float* p;              // [nz][ncol]
   const float* dz;             // [nz]
   float* ppt;                  // [4][ncol]
+  float* scratch;              // [SC_N][nz][ncol] hand-off, touched for cloudy columns only
+  int* colint;                 // [8][ncol] substep counts / top sedimenting level per species; [0] = -1: clear sky
   float* rates;                // optional [36][nz][ncol]
   double* diag_partial;        // optional [gridDim.x][KIDMP_NDIAG] block sums
 };

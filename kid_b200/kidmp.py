@@ -58,6 +58,19 @@ SYMBOLS = {
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
 }
 
+
+
+class KidColumns(C.Structure):
+    """kidmp_kid_columns of include/kidmp.h."""
+    _fields_ = [("nx", C.c_long), ("nz", C.c_int)] + [(n, _fp) for n in (
+        "theta", "dtheta_adv", "dtheta_div", "exner", "qv", "dqv_adv", "dqv_div", "dz")] + [
+        ("hyd", _fp * 7), ("dhyd_adv", _fp * 7), ("dhyd_div", _fp * 7),
+        ("dtheta_mphys", _fp), ("dqv_mphys", _fp), ("dhyd_mphys", _fp * 7), ("ppt", _fp)]
+
+
+SYMBOLS["kidmp_kid_interface"] = (C.c_int, [C.c_void_p, C.POINTER(KidColumns), C.c_float, C.c_float, C.c_float])
+HYD_PLANES = ("qc", "qr", "nr", "qi", "ni", "qs", "qg")
+
 _lib = None
 
 
@@ -203,6 +216,28 @@ class Thompson:
         p, dz, ppt = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ck(self._L.kidmp_device_state(self.h, f, C.byref(p), C.byref(dz), C.byref(ppt)))
         return [int(x) for x in f], int(p.value), int(dz.value), int(ppt.value)
+
+    def kid_interface(self, kid, dt, p0=1.0e5, r_on_cp=287.05 / 1005.0):
+        """mphys_thompson09_interfacen (I:28-246) without save_dg.  kid: dict of float32 (nx, nz) arrays 'theta',
+        'dtheta_adv', 'dtheta_div', 'exner', 'qv', 'dqv_adv', 'dqv_div', '<m>', 'd<m>_adv', 'd<m>_div' for m in
+        HYD_PLANES, and 'dz' (nz).  Returns 'dtheta_mphys', 'dqv_mphys', 'd<m>_mphys', 'ppt' [4, nx]."""
+        nx, nz = kid["theta"].shape
+        a = {k: np.ascontiguousarray(v, np.float32) for k, v in kid.items()}
+        out = {"dtheta_mphys": np.zeros((nx, nz), np.float32), "dqv_mphys": np.zeros((nx, nz), np.float32),
+               "ppt": np.zeros((4, nx), np.float32)}
+        for m in HYD_PLANES:
+            out["d%s_mphys" % m] = np.zeros((nx, nz), np.float32)
+        P = lambda x: x.ctypes.data_as(_fp)
+        c = KidColumns()
+        c.nx, c.nz = nx, nz
+        for n in ("theta", "dtheta_adv", "dtheta_div", "exner", "qv", "dqv_adv", "dqv_div", "dz"):
+            setattr(c, n, P(a[n]))
+        for j, m in enumerate(HYD_PLANES):
+            c.hyd[j], c.dhyd_adv[j], c.dhyd_div[j] = P(a[m]), P(a["d%s_adv" % m]), P(a["d%s_div" % m])
+            c.dhyd_mphys[j] = P(out["d%s_mphys" % m])
+        c.dtheta_mphys, c.dqv_mphys, c.ppt = P(out["dtheta_mphys"]), P(out["dqv_mphys"]), P(out["ppt"])
+        self._ck(self._L.kidmp_kid_interface(self.h, C.byref(c), float(dt), float(p0), float(r_on_cp)))
+        return out
 
     def set_rates_buffer(self, ptr):
         self._ck(self._L.kidmp_set_rates_buffer(self.h, C.c_void_p(int(ptr)) if ptr else None))

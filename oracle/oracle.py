@@ -47,6 +47,9 @@ def lib():
         L.kor_mp_thompson.argtypes = [C.c_void_p, C.c_int, C.c_float] + [_fp] * 10 + [_fp, _fp, _fp, _dp]
         L.kor_step.restype = C.c_int
         L.kor_step.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_int] + [_fp] * 9 + [_fp, _fp, _fp, C.c_int]
+        L.kor_kid_interface.restype = C.c_int
+        L.kor_kid_interface.argtypes = ([C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_float, C.c_float] + [_fp] * 8
+                                        + [C.POINTER(_fp)] * 3 + [_fp, _fp, C.POINTER(_fp), _fp])
         L.kor_rate_names.restype = C.c_char_p
         for n in ("kor_rslf", "kor_rsif"):
             getattr(L, n).restype = C.c_float
@@ -162,6 +165,33 @@ class Oracle:
         if rc:
             raise RuntimeError("kor_step rc=%d" % rc)
         return ppt
+
+
+HYD_PLANES = ("qc", "qr", "nr", "qi", "ni", "qs", "qg")
+
+
+def kid_interface(o, kid, dt, p0=1.0e5, r_on_cp=287.05 / 1005.0):
+    """I:28-246 on the oracle.  kid: dict of float32 (nx, nz) arrays 'theta', 'dtheta_adv', 'dtheta_div', 'exner',
+    'qv', 'dqv_adv', 'dqv_div', plus '<m>', 'd<m>_adv', 'd<m>_div' for m in HYD_PLANES, and 'dz' (nz).
+    Returns dict: 'dtheta_mphys', 'dqv_mphys', 'd<m>_mphys', 'ppt' [4, nx]."""
+    nx, nz = kid["theta"].shape
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    a = {k: f(v) for k, v in kid.items()}
+    out = {"dtheta_mphys": np.zeros((nx, nz), np.float32), "dqv_mphys": np.zeros((nx, nz), np.float32),
+           "ppt": np.zeros((4, nx), np.float32)}
+    for m in HYD_PLANES:
+        out["d%s_mphys" % m] = np.zeros((nx, nz), np.float32)
+    P = lambda x: x.ctypes.data_as(_fp)
+    arr = lambda names: (_fp * 7)(*[P(a[n]) for n in names])
+    hyd_out = (_fp * 7)(*[P(out["d%s_mphys" % m]) for m in HYD_PLANES])
+    rc = lib().kor_kid_interface(o.h, nx, nz, float(dt), float(p0), float(r_on_cp), P(a["theta"]), P(a["dtheta_adv"]),
+                                 P(a["dtheta_div"]), P(a["exner"]), P(a["qv"]), P(a["dqv_adv"]), P(a["dqv_div"]),
+                                 P(a["dz"]), arr(HYD_PLANES), arr(["d%s_adv" % m for m in HYD_PLANES]),
+                                 arr(["d%s_div" % m for m in HYD_PLANES]), P(out["dtheta_mphys"]), P(out["dqv_mphys"]),
+                                 hyd_out, P(out["ppt"]))
+    if rc:
+        raise RuntimeError("kor_kid_interface rc=%d" % rc)
+    return out
 
 
 def rslf(p, t):

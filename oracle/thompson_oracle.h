@@ -40,6 +40,15 @@ int kor_step(const kor_handle*, long ncol, int nz, float dt, int layout,
              float* ni, float* nr, float* t, const float* p, const float* dz,
              float* ppt, int nthreads);
 
+// I:28-246 mphys_thompson09_interfacen (gather, mp_thompson per column, tendencies back) without
+// save_dg.  KiD (k,i) arrays a[i*nz+k]; hyd planes: qc, qr, nr, qi, ni, qs, qg; ppt [4][nx].
+int kor_kid_interface(const kor_handle*, long nx, int nz, float dt, float p0, float r_on_cp,
+                      const float* theta, const float* dtheta_adv, const float* dtheta_div,
+                      const float* exner, const float* qv, const float* dqv_adv, const float* dqv_div,
+                      const float* dz, const float* const* hyd, const float* const* dhyd_adv,
+                      const float* const* dhyd_div, float* dtheta_mphys, float* dqv_mphys,
+                      float* const* dhyd_mphys, float* ppt);
+
 const char* kor_rate_names(void);   // comma-separated, 36 names (M:2963-3120)
 
 // M:4598-4717 helpers, exposed for known-answer tests

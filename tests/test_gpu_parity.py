@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json): <= 1e-5 relative per hydrometeor mass / number after one step, except for a
+counted handful of index / threshold flip cells (parity_util.FLIP_FRACTION); lookup tables to
+1e-12 relative; init constants bit-exact.  M:/I: cite the reference files.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from parity_util import assert_parity, compare_states, FIELDS
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "columns.npz")
+
+
+def _domain(ncol, nz=60, **kw):
+    from kid_b200 import synth
+    st, p, dz = synth.make_domain(ncol, nz=nz, **kw)
+    return {k: v.numpy().copy() for k, v in st.items()}, p.numpy().copy(), dz.numpy().copy()
+
+
+def _both(g, o, dt, st, p, dz, layout="col_fastest"):
+    a = {k: v.copy() for k, v in st.items()}
+    b = {k: v.copy() for k, v in st.items()}
+    pa = g.step(dt, a, p, dz, layout=layout)
+    pb = o.step(dt, b, p, dz, layout=layout)
+    return a, pa, b, pb
+
+
+# ---- thompson_init: constants and lookup tables (M:374-797, M:3698-4343) ------------------------------
+def test_init_constants_bit_exact(gpu_mixed, oracle_mixed):
+    for name in ("cre", "crg", "cse", "csg", "cge", "cgg", "cie", "cig", "cce1", "cce2", "cce3", "cce4", "cce5",
+                 "ccg1", "ccg2", "ccg3", "ccg4", "ccg5", "ocg1", "ocg2", "scalars", "offsets",
+                 "Dc", "Di", "Dr", "Ds", "Dg", "t_Nc", "dtc", "dti", "dtr", "dts", "dtg"):
+        assert np.array_equal(gpu_mixed.get(name), oracle_mixed.get(name).ravel()), name
+
+
+def test_lookup_tables(gpu_mixed, oracle_mixed):
+    from oracle.oracle import TABLE_SHAPES
+    for name in TABLE_SHAPES:
+        a = gpu_mixed.get(name)
+        b = oracle_mixed.get(name).ravel(order="F")
+        assert a.shape == b.shape, name
+        rel = np.where(a == b, 0.0, np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+        assert rel.max() < 1e-12, (name, rel.max())
+    assert gpu_mixed.table_build_ms > 0
+
+
+def test_tables_against_golden_samples(gpu_mixed):
+    g = np.load(GOLD)
+    for key in g.files:
+        if key.startswith("table/") and key.endswith("/sample"):
+            name = key.split("/")[1]
+            t = gpu_mixed.get(name)
+            s = t[:: max(1, t.size // 257)][:257]
+            np.testing.assert_allclose(s, g[key], rtol=1e-12, atol=0, err_msg=name)
+            tot = g["table/%s/sum" % name]
+            np.testing.assert_allclose(t.sum(), tot[0], rtol=1e-11)
+            assert float((t != 0).sum()) == tot[2]
+
+
+def test_table_cache_roundtrip(gpu_mixed, tmp_path):
+    from kid_b200.kidmp import Thompson
+    path = str(tmp_path / "tables.bin")
+    gpu_mixed.save_tables(path)
+    t2 = Thompson(set_Nc=100.0, iiwarm=False, table_cache=path, reuse_tables=True)
+    assert t2.tables_from_cache
+    for name in ("tcg_racg", "tnr_sacr2", "tpg_qrfz", "tni_qcfz", "tpi_ide", "t_Efsw"):
+        assert np.array_equal(t2.get(name), gpu_mixed.get(name)), name
+    t2.close()
+    # a cache written under other constants is refused and the tables are rebuilt (M:3874-3881 warns, we check)
+    t3 = Thompson(set_Nc=100.0, iiwarm=False, wp_double=True, table_cache=path, reuse_tables=True)
+    assert not t3.tables_from_cache
+    t3.close()
+
+
+# ---- mp_thompson (M:1156-3688) ---------------------------------------------------------------------------
+def test_golden_columns(gpu_mixed, gpu_warm):
+    g = np.load(GOLD)
+    for th, tag, dt in ((gpu_mixed, "mixed_dt10", 10.0), (gpu_mixed, "mixed_dt60", 60.0), (gpu_warm, "warm_dt10", 10.0)):
+        s = {k: g["in/" + k].copy() for k in FIELDS}
+        ppt = th.step(dt, s, g["in/p"].copy(), g["in/dz"])
+        ref = {k: g["%s/%s" % (tag, k)] for k in FIELDS}
+        assert_parity(s, ref, what=tag, flip_fraction=1e-3)
+        np.testing.assert_allclose(ppt, g[tag + "/ppt"], rtol=1e-5, atol=1e-12)
+
+
+def test_no_sedimentation_switch(tmp_path):
+    from kid_b200.kidmp import Thompson
+    g = np.load(GOLD)
+    th = Thompson(set_Nc=300.0, iiwarm=False, l_sediment=False)
+    s = {k: g["in/" + k].copy() for k in FIELDS}
+    ppt = th.step(10.0, s, g["in/p"].copy(), g["in/dz"])
+    assert_parity(s, {k: g["nosed_dt10/" + k] for k in FIELDS}, what="l_sediment=F", flip_fraction=1e-3)
+    assert not ppt[1:].any()                       # ice, snow, graupel do not fall (M:3449, M:3506, M:3555)
+    assert ppt[0].any()                            # rain still does (U6)
+    th.close()
+
+
+def test_deep_mixed_phase_column(gpu_mixed, oracle_mixed):
+    """BASELINE config 2: one deep column with every species present, through the mp_thompson twin."""
+    from kid_b200 import synth
+    st, p, dz = synth.deep_column()
+    args = [st[k] for k in FIELDS]
+    a = gpu_mixed.column(10.0, *args, p, dz, ppt=[1.0, 2.0, 3.0, 4.0])
+    b = oracle_mixed.column(10.0, *args, p, dz, ppt=[1.0, 2.0, 3.0, 4.0])
+    assert_parity(a, b, what="deep column", flip_fraction=0.0)
+    np.testing.assert_allclose(a["ppt"], b["ppt"], rtol=1e-6)        # INOUT accumulators (M:1172)
+    assert a["ppt"][0] > 1.0
+
+
+def test_mixed_domain_one_step(gpu_mixed, oracle_mixed):
+    st, p, dz = _domain(4096, cloudy_fraction=1.0, coherent=False)
+    for dt in (10.0, 60.0):                        # dt = 60 s drives nstep > 1 in the sedimentation sub-stepping
+        a, pa, b, pb = _both(gpu_mixed, oracle_mixed, dt, st, p, dz)
+        stt = assert_parity(a, b, what="4096 mixed dt=%g" % dt)
+        assert stt["_all"]["exact_frac"] > 0.995
+        np.testing.assert_allclose(pa, pb, rtol=1e-5, atol=1e-10)
+
+
+def test_conus_domain_one_step(gpu_mixed, oracle_mixed):
+    st, p, dz = _domain(8192, col0=300000, nx=1024)            # the bench domain: ~30 % cloudy, coherent
+    a, pa, b, pb = _both(gpu_mixed, oracle_mixed, 10.0, st, p, dz)
+    assert_parity(a, b, what="bench domain")
+    np.testing.assert_allclose(pa, pb, rtol=1e-5, atol=1e-10)
+
+
+def test_warm_rain_domain(gpu_warm, oracle_warm):
+    """BASELINE config 1 regime (iiwarm): S1,S2,S5,S7-S9,S11-S14,S16 only."""
+    st, p, dz = _domain(2048, cloudy_fraction=1.0, coherent=False)
+    a, pa, b, pb = _both(gpu_warm, oracle_warm, 1.0, st, p, dz)
+    assert_parity(a, b, what="warm dt=1")
+    for k in ("qs", "qg"):
+        assert np.array_equal(a[k], st[k])         # ice species untouched when iiwarm
+    np.testing.assert_allclose(pa, pb, rtol=1e-5, atol=1e-10)
+
+
+def test_clear_sky_columns_bit_unchanged(gpu_mixed):
+    st, p, dz = _domain(1000, cloudy_fraction=0.0, coherent=False)
+    a = {k: v.copy() for k, v in st.items()}
+    gpu_mixed.diag()                               # clear the accumulated domain sums
+    ppt = gpu_mixed.step(10.0, a, p, dz)
+    for k in FIELDS:
+        assert np.array_equal(a[k], st[k]), k      # early RETURN at M:1540
+    assert not ppt.any()
+    d = gpu_mixed.diag()
+    assert d[6] == 0 and d[7] == 1000
+
+
+def test_tiny_species_are_zeroed_before_the_early_return(gpu_mixed, oracle_mixed):
+    # U9: species <= R1 are zeroed in the caller's arrays even when the column takes the clear-sky exit
+    st, p, dz = _domain(64, cloudy_fraction=0.0, coherent=False)
+    st["qc"][5, :] = 5e-13; st["qi"][40, :] = 9e-13; st["ni"][40, :] = 10.0; st["nr"][3, :] = 2.0
+    a, pa, b, pb = _both(gpu_mixed, oracle_mixed, 10.0, st, p, dz)
+    for k in FIELDS:
+        assert np.array_equal(a[k], b[k]), k
+    assert not a["qc"].any() and not a["ni"].any() and not a["nr"].any()
+
+
+def test_layouts_and_ragged_sizes(gpu_mixed, oracle_mixed):
+    for ncol in (1, 31, 129, 1000):
+        st, p, dz = _domain(ncol, cloudy_fraction=1.0, coherent=False)
+        a, pa, b, pb = _both(gpu_mixed, oracle_mixed, 10.0, st, p, dz)
+        assert_parity(a, b, what="ncol=%d" % ncol, flip_fraction=1e-3)
+        # KiD (k,i) layout gives bitwise the same numbers as the device layout
+        kt = {k: np.ascontiguousarray(v.T) for k, v in st.items()}
+        pk = gpu_mixed.step(10.0, kt, np.ascontiguousarray(p.T), dz, layout="k_fastest")
+        for k in FIELDS:
+            assert np.array_equal(kt[k].T, a[k]), (ncol, k)
+        assert np.array_equal(pk, pa)
+
+
+def test_other_level_counts(gpu_mixed, oracle_mixed):
+    """nz = 120 (BASELINE config 3, 2-D cumulus grid run as 120 independent columns) and odd sizes."""
+    for nz, dzv in ((120, 125.0), (2, 400.0), (37, 400.0), (200, 75.0)):
+        st, p, dz = _domain(120, nz=nz, dz=dzv, cloudy_fraction=1.0, coherent=False)
+        a, pa, b, pb = _both(gpu_mixed, oracle_mixed, 5.0, st, p, dz)
+        assert_parity(a, b, what="nz=%d" % nz, flip_fraction=1e-3)
+        np.testing.assert_allclose(pa, pb, rtol=1e-5, atol=1e-10)
+
+
+def test_errors_are_returned_not_raised_across_the_abi(gpu_mixed):
+    from kid_b200.kidmp import KidmpError
+    st, p, dz = _domain(4, nz=60)
+    with pytest.raises(KidmpError):
+        gpu_mixed.step(-1.0, st, p, dz)
+    big = {k: np.zeros((300, 2), np.float32) for k in FIELDS}
+    with pytest.raises(KidmpError) as e:
+        gpu_mixed.step(1.0, big, np.ones((300, 2), np.float32), np.ones(300, np.float32))
+    assert "nz" in str(e.value)
+    with pytest.raises(KeyError):
+        gpu_mixed.get("no_such_table")
+
+
+def test_resident_time_series(gpu_mixed, oracle_mixed):
+    """Surface precipitation and LWP / IWP series over 60 steps of dt = 10 s stay within 0.1 % (north_star)."""
+    from kid_b200.shard import diag_from_state
+    st, p, dz = _domain(1024, col0=300000, nx=1024)
+    ref = {k: v.copy() for k, v in st.items()}
+    gpu_mixed.state_alloc(1024, 60)
+    gpu_mixed.upload(st, p, dz)
+    gpu_mixed.diag()
+    series_g, series_o = [], []
+    cur = {k: v.copy() for k, v in st.items()}
+    for n in range(60):
+        gpu_mixed.step_resident(10.0)
+        series_g.append(gpu_mixed.diag())
+        ppt = oracle_mixed.step(10.0, ref, p, dz)
+        series_o.append(diag_from_state(ref, p, dz, ppt))
+    sg, so = np.array(series_g), np.array(series_o)
+    for j, name in ((0, "rain"), (2, "snow"), (3, "graupel"), (4, "lwp"), (5, "iwp")):
+        scale = np.abs(so[:, j]).max()
+        if scale > 0:
+            assert np.abs(sg[:, j] - so[:, j]).max() <= 1e-3 * scale, name
+    gpu_mixed.download(cur)
+    assert_parity(cur, ref, what="state after 60 steps", flip_fraction=5e-3)
+
+
+def test_process_rate_buffer(gpu_mixed, oracle_mixed):
+    """The 36 save_dg rates of M:2963-3120 through the optional device buffer."""
+    import torch
+    g = np.load(GOLD)
+    ncol, nz = g["in/p"].shape[1], 60
+    rates = torch.full((36, nz, ncol), float("nan"), dtype=torch.float32, device="cuda")
+    gpu_mixed.set_rates_buffer(rates.data_ptr())
+    s = {k: g["in/" + k].copy() for k in FIELDS}
+    gpu_mixed.step(10.0, s, g["in/p"].copy(), g["in/dz"])
+    gpu_mixed.set_rates_buffer(0)
+    got = rates.cpu().numpy()
+    assert gpu_mixed.rate_names == oracle_mixed.rate_names
+    nbad = 0
+    for j in range(ncol):
+        out = oracle_mixed.column(10.0, *[g["in/" + k][:, j] for k in FIELDS], g["in/p"][:, j], g["in/dz"], want_rates=True)
+        ref = out["rates"].astype(np.float32)
+        active = np.isfinite(got[:, :, j]).all()
+        if not active:                             # clear-sky column: kernel left the buffer untouched
+            assert not ref.any()
+            continue
+        rel = np.abs(got[:, :, j] - ref) / np.maximum(np.abs(ref), 1e-30)
+        rel = np.where(got[:, :, j] == ref, 0.0, rel)
+        nbad += int((rel > 1e-5).sum())
+    assert nbad <= 5
+
+
+def test_step_device_on_a_torch_stream(gpu_mixed, oracle_mixed):
+    import torch
+    from kid_b200 import synth
+    st, p, dz = synth.make_domain(3000, nz=60, cloudy_fraction=1.0, coherent=False, device="cuda")
+    ref = {k: v.cpu().numpy().copy() for k, v in st.items()}
+    ppt = torch.zeros((4, 3000), dtype=torch.float32, device="cuda")
+    s = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        gpu_mixed.step_device(3000, 60, 10.0, [st[k].data_ptr() for k in FIELDS], p.data_ptr(), dz.data_ptr(),
+                              ppt.data_ptr(), stream=s.cuda_stream)
+    s.synchronize()
+    pb = oracle_mixed.step(10.0, ref, p.cpu().numpy(), dz.cpu().numpy())
+    assert_parity({k: st[k].cpu().numpy() for k in FIELDS}, ref, what="step_device")
+    np.testing.assert_allclose(ppt.cpu().numpy(), pb, rtol=1e-5, atol=1e-10)
+
+
+def test_shards_equal_whole_domain(gpu_mixed):
+    """An N-way column split must reproduce the whole-domain run column for column, bitwise."""
+    from kid_b200.shard import shard_range
+    st, p, dz = _domain(5000, col0=300000, nx=1024)
+    whole = {k: v.copy() for k, v in st.items()}
+    gpu_mixed.diag()
+    pw = gpu_mixed.step(10.0, whole, p, dz)
+    dw = gpu_mixed.diag()
+    dsum = np.zeros(8)
+    for r in range(3):
+        c0, c1 = shard_range(5000, r, 3)
+        part = {k: np.ascontiguousarray(v[:, c0:c1]) for k, v in st.items()}
+        pp = gpu_mixed.step(10.0, part, np.ascontiguousarray(p[:, c0:c1]), dz)
+        for k in FIELDS:
+            assert np.array_equal(part[k], whole[k][:, c0:c1]), (r, k)
+        assert np.array_equal(pp, pw[:, c0:c1])
+        dsum += gpu_mixed.diag()
+    np.testing.assert_allclose(dsum, dw, rtol=1e-12)
+
+
+# ---- mphys_thompson09_interfacen (I:28-246) -----------------------------------------------------------------
+def _kid_case(nx, nz, seed=7):
+    from kid_b200 import synth
+    rng = np.random.default_rng(seed)
+    st, p, dz = synth.make_domain(nx, nz=nz, cloudy_fraction=1.0, coherent=False)
+    p0, r_on_cp = 1.0e5, 287.05 / 1005.0
+    T = st["t"].numpy().T.copy(); pk = p.numpy().T.copy()
+    exner = ((pk / p0) ** r_on_cp).astype(np.float32)
+    kid = {"theta": (T / exner).astype(np.float32), "exner": exner, "qv": st["qv"].numpy().T.copy(), "dz": dz.numpy()}
+    kid["dtheta_adv"] = (1e-3 * rng.standard_normal((nx, nz))).astype(np.float32)
+    kid["dtheta_div"] = (1e-4 * rng.standard_normal((nx, nz))).astype(np.float32)
+    kid["dqv_adv"] = (1e-7 * rng.standard_normal((nx, nz))).astype(np.float32)
+    kid["dqv_div"] = (1e-8 * rng.standard_normal((nx, nz))).astype(np.float32)
+    for m in ("qc", "qr", "nr", "qi", "ni", "qs", "qg"):
+        x = st[m].numpy().T.copy()
+        kid[m] = x
+        kid["d%s_adv" % m] = (x * 1e-3 * rng.standard_normal((nx, nz))).astype(np.float32)
+        kid["d%s_div" % m] = (x * 1e-4 * rng.standard_normal((nx, nz))).astype(np.float32)
+    return kid, p0, r_on_cp
+
+
+def test_kid_interface_tendencies(gpu_mixed, oracle_mixed, gpu_warm, oracle_warm):
+    from oracle.oracle import kid_interface, HYD_PLANES
+    for g, o, nx, nz in ((gpu_mixed, oracle_mixed, 120, 120), (gpu_warm, oracle_warm, 1, 60), (gpu_mixed, oracle_mixed, 77, 60)):
+        kid, p0, roc = _kid_case(nx, nz)
+        a = g.kid_interface(kid, 5.0, p0, roc)
+        b = kid_interface(o, kid, 5.0, p0, roc)
+        warm = g.iiwarm
+        names = ["dtheta_mphys", "dqv_mphys"] + ["d%s_mphys" % m for m in (HYD_PLANES[:3] if warm else HYD_PLANES)]
+        # tendencies are differences of nearly equal states: compare them on the scale of state/dt
+        scale = {"dtheta_mphys": 300.0 / 5.0, "dqv_mphys": kid["qv"].max() / 5.0}
+        for m in HYD_PLANES:
+            scale["d%s_mphys" % m] = max(float(np.abs(kid[m]).max()), 1e-12) / 5.0
+        for n in names:
+            err = np.abs(a[n].astype(np.float64) - b[n]).max() / scale[n]
+            assert err < 2e-6, (n, err)
+            assert (a[n] == b[n]).mean() > 0.98, n
+        np.testing.assert_allclose(a["ppt"], b["ppt"], rtol=1e-5, atol=1e-10)

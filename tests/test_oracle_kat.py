@@ -1,0 +1,191 @@
+"""CPU tests of the oracle: known-answer values derived from the reference source text (SURVEY.md
+section 4), properties the reference guarantees, and the committed golden fixtures.
+
+M: = /root/reference/module_mp_thompson09n.f90.  The reference has no tests of its own
+(PARITY UNPINNED): these pins are what the oracle is anchored to.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle.oracle import FIELDS
+from kid_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "columns.npz")
+
+
+def test_gamma_exponents_and_values(oracle_mixed):
+    o = oracle_mixed
+    # exponents, M:485-497, M:532-543, M:467-473, M:507-524
+    np.testing.assert_allclose(o.get("cre"), [4, 1, 4, 7, 2, 5, 3.5, 7, 4, 2, 3, 2.5, 8], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(o.get("cge"), [4, 1, 4, 7, 7.89, 4.89, 5.89, 6.89, 3.89, 2, 2.945, 2.945], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(o.get("cie"), [1, 4, 5, 2, 2, 3.5, 2.5], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(o.get("cse"), [3, 4, 4, 3.55, 5.55, 5, 3.6357, 4.6357, 5.6357, 4.1857, 6.1857, 5.6357,
+                                              2.55, 2.55, 1.6357, 1.775, 3.4107, 4.1857], rtol=0, atol=2e-6)
+    crg, cgg, csg = o.get("crg"), o.get("cgg"), o.get("csg")
+    # gamma(n) = (n-1)! through the NR Lanczos GAMMLN (M:4598-4620) in f32
+    np.testing.assert_allclose(crg[[0, 3, 12]], [6.0, 720.0, 5040.0], rtol=2e-6)
+    np.testing.assert_allclose(crg[[6, 11]], [3.3233511, 1.3293403], rtol=2e-6)
+    np.testing.assert_allclose(cgg[[4, 5, 8, 10]], [4041.009, 20.363228, 5.2347646, 1.9021707], rtol=3e-6)
+    np.testing.assert_allclose(csg[[3, 9, 12, 15]], [3.5132518, 7.612799, 1.377746, 0.9249857], rtol=3e-6)
+
+
+def test_scalar_constants(oracle_mixed):
+    s = oracle_mixed.get("scalars")
+    Nt_c, Sc3, D0i, xm0s, xm0g, rho_not, t1_qr_qc, t1_qr_qi, t2_qr_qi, t1_qg_qc = s[:10]
+    assert Nt_c == 100.0e6                                             # M:381
+    np.testing.assert_allclose(Sc3, 0.85816807, rtol=1e-6)             # M:442
+    np.testing.assert_allclose(D0i, 1.28984e-5, rtol=1e-5)             # M:445
+    np.testing.assert_allclose(xm0s, 2.76e-9, rtol=1e-6)
+    np.testing.assert_allclose(xm0g, 4.09062e-9, rtol=1e-5)
+    np.testing.assert_allclose(rho_not, 1.1845211, rtol=1e-6)          # M:141
+    np.testing.assert_allclose(t1_qr_qc, 22873.94, rtol=1e-6)          # M:560
+    np.testing.assert_allclose(t2_qr_qi, 1.437212e9, rtol=1e-5)        # M:562
+    np.testing.assert_allclose(t1_qg_qc, 1817.2275, rtol=2e-6)         # M:565
+    np.testing.assert_allclose(s[13], 36.830105, rtol=2e-6)            # t2_qr_ev, M:575
+    off = oracle_mixed.get("offsets")
+    assert list(off.astype(int)) == [7, -6, -10, 0, -6, 6, -5, -5, 4, 0]   # nic1, nic2 ... niIN2, M:594-602, M:670
+
+
+def test_bins(oracle_mixed):
+    Dr, tN = oracle_mixed.get("Dr"), oracle_mixed.get("t_Nc")
+    np.testing.assert_allclose(Dr[0], 5.1165e-5, rtol=1e-4)            # M:625-634
+    np.testing.assert_allclose(Dr[99], 4.8862e-3, rtol=1e-4)
+    np.testing.assert_allclose(tN[0], 1.0408e6, rtol=1e-4)
+    assert np.all(np.diff(Dr) > 0)
+    # geometric grid: constant ratio
+    np.testing.assert_allclose(Dr[1:] / Dr[:-1], (0.005 / 50e-6) ** 0.01, rtol=1e-6)
+
+
+def test_saturation(oracle_mixed):
+    np.testing.assert_allclose(orc.rslf(1e5, 293.15), 0.0148923, rtol=1e-5)      # M:4656-4686
+    np.testing.assert_allclose(orc.rslf(8e4, 273.15), 0.00478818, rtol=1e-5)
+    np.testing.assert_allclose(orc.rsif(5e4, 253.15), 0.00128693, rtol=1e-5)     # M:4688-4717
+    np.testing.assert_allclose(orc.rsif(3e4, 233.15), 0.000266049, rtol=1e-5)
+    # ice saturation below water saturation under 0 C
+    assert orc.rsif(6e4, 263.15) < orc.rslf(6e4, 263.15)
+
+
+def test_decade_index():
+    L = orc.lib()
+    # r_r axis: 1e-6..1e-2, 37 nodes, nir2 = -6 (M:235-240, M:1840-1852)
+    assert L.kor_decade_index(1.5e-6, -6, 37) == 1
+    assert L.kor_decade_index(9.99e-6, -6, 37) == 9
+    assert L.kor_decade_index(1.0e-5, -6, 37) in (9, 10)      # exactly on a decade: f32 rounding decides
+    assert L.kor_decade_index(3.3e-4, -6, 37) == 9 * 2 + 3
+    assert L.kor_decade_index(0.5, -6, 37) == 37              # clamped
+    # monotone non-decreasing over the axis
+    xs = np.exp(np.linspace(np.log(1.1e-6), np.log(9e-3), 4000)).astype(np.float32)
+    idx = np.array([L.kor_decade_index(float(x), -6, 37) for x in xs])
+    assert np.all(np.diff(idx) >= 0) and idx.min() == 1 and idx.max() <= 37
+
+
+def test_tables_properties(oracle_mixed):
+    o = oracle_mixed
+    ef = o.get("t_Efrw")
+    Dr, Dc = o.get("Dr"), o.get("Dc")
+    assert ef.min() >= 0.0 and ef.max() <= 0.95 + 1e-7                               # M:4294
+    assert np.all(ef[:, Dc < 3e-6] == 0.0) and np.all(ef[Dr < 50e-6, :] == 0.0)     # M:4256-4257
+    ide = o.get("tpi_ide")
+    assert ide.min() >= 0.0 and ide.max() <= 1.0                                     # M:4209-4219
+    r_r = np.array([m * 10.0 ** d for d in range(-6, -2) for m in range(1, 10)] + [1e-2], np.float32)
+    tmr = o.get("tmr_racg")                                                          # (g1, g, r1, r)
+    assert np.all(tmr <= r_r[None, None, None, :].astype(np.float64) * (1 + 1e-12))  # M:3802
+    # freezing probability grows as it gets colder (third axis = -T), M:4118-4150
+    tpg = o.get("tpg_qrfz")
+    assert np.all(np.diff(tpg, axis=2) >= -1e-30)
+    # the sacr1 family is identically zero: a snowflake heavier than 2/3 of the drop never falls slower (M:3998-4028)
+    assert not o.get("tcr_sacr1").any()
+
+
+def _col(st, p, j):
+    return [st[k][:, j].copy() for k in FIELDS], p[:, j].copy()
+
+
+def test_no_micro_columns_unchanged(oracle_mixed):
+    st, p, dz = synth.make_domain(512, nz=60, cloudy_fraction=0.0, coherent=False)
+    ref = {k: v.numpy().copy() for k, v in st.items()}
+    new = {k: v.copy() for k, v in ref.items()}
+    ppt = oracle_mixed.step(10.0, new, p.numpy(), dz.numpy())
+    for k in FIELDS:
+        assert np.array_equal(new[k], ref[k]), k                        # early RETURN at M:1540 (U9)
+    assert not ppt.any()
+
+
+def test_warm_leaves_ice_untouched(oracle_warm):
+    st, p, dz = synth.make_domain(256, nz=60, cloudy_fraction=1.0, coherent=False)
+    ref = {k: v.numpy().copy() for k, v in st.items()}
+    new = {k: v.copy() for k, v in ref.items()}
+    oracle_warm.step(10.0, new, p.numpy(), dz.numpy())
+    for k in ("qs", "qg"):
+        assert np.array_equal(new[k], ref[k]), k                        # iiwarm gates S3/S4/S6/S10/S15
+    assert not np.array_equal(new["qr"], ref["qr"])
+
+
+def test_output_clamps(oracle_mixed):
+    st, p, dz = synth.make_domain(512, nz=60, cloudy_fraction=1.0, coherent=False)
+    new = {k: v.numpy().copy() for k, v in st.items()}
+    oracle_mixed.step(10.0, new, p.numpy(), dz.numpy())
+    assert new["qv"].min() >= 1e-10                                      # M:3624
+    for k in ("qc", "qi", "qr", "qs", "qg"):
+        q = new[k]
+        assert np.all((q == 0) | (q > 1e-12)), k                         # M:3628-3685
+    assert np.all(new["ni"][new["qi"] == 0] == 0) and np.all(new["nr"][new["qr"] == 0] == 0)
+    rho = 0.622 * p.numpy() / (287.04 * new["t"] * (new["qv"] + 0.622))
+    assert np.all(new["ni"] * rho <= 499e3 * 1.001)                      # M:3650
+    assert np.isfinite(np.stack([new[k] for k in FIELDS])).all()
+
+
+def test_water_budget(oracle_mixed):
+    # total water (vapour + condensate) + surface precipitation is conserved up to the clamp leaks
+    st, p, dz = synth.make_domain(256, nz=60, cloudy_fraction=1.0, coherent=False)
+    old = {k: v.numpy().astype(np.float64) for k, v in st.items()}
+    new32 = {k: v.numpy().copy() for k, v in st.items()}
+    ppt = oracle_mixed.step(10.0, new32, p.numpy(), dz.numpy()).astype(np.float64)
+    new = {k: v.astype(np.float64) for k, v in new32.items()}
+    pn, dzn = p.numpy().astype(np.float64), dz.numpy().astype(np.float64)[:, None]
+
+    def column_water(s):
+        rho = 0.622 * pn / (287.04 * s["t"] * (s["qv"] + 0.622))
+        return ((s["qv"] + s["qc"] + s["qr"] + s["qi"] + s["qs"] + s["qg"]) * rho * dzn).sum(0)
+    before, after = column_water(old), column_water(new) + ppt.sum(0)
+    # air density changes with the latent heating at fixed pressure, so the budget closes to ~1e-3
+    np.testing.assert_allclose(after, before, rtol=5e-3)
+
+
+def test_golden_fixtures_reproduced():
+    g = np.load(GOLD)
+    p, dz = g["in/p"], g["in/dz"]
+    for tag, kw, dt in (("mixed_dt10", dict(set_Nc=100.0, iiwarm=False), 10.0),
+                        ("warm_dt10", dict(set_Nc=50.0, iiwarm=True), 10.0),
+                        ("nosed_dt10", dict(set_Nc=300.0, iiwarm=False, l_sediment=False), 10.0)):
+        o = orc.Oracle(**kw)
+        s = {k: g["in/" + k].copy() for k in FIELDS}
+        ppt = o.step(dt, s, p.copy(), dz)
+        for k in FIELDS:
+            assert np.array_equal(s[k], g["%s/%s" % (tag, k)]), (tag, k)
+        assert np.array_equal(ppt, g[tag + "/ppt"])
+        o.close()
+
+
+def test_single_column_equals_batched(oracle_mixed):
+    g = np.load(GOLD)
+    j = 3
+    out = oracle_mixed.column(10.0, *[g["in/" + k][:, j] for k in FIELDS], g["in/p"][:, j], g["in/dz"])
+    for k in FIELDS:
+        assert np.array_equal(out[k], g["mixed_dt10/" + k][:, j]), k
+    # layouts: K_FASTEST (KiD (k,i)) and COL_FASTEST give the same numbers
+    s = {k: np.ascontiguousarray(g["in/" + k].T) for k in FIELDS}
+    oracle_mixed.step(10.0, s, np.ascontiguousarray(g["in/p"].T), g["in/dz"], layout="k_fastest")
+    for k in FIELDS:
+        assert np.array_equal(s[k].T, g["mixed_dt10/" + k]), k
+
+
+def test_rates_buffer(oracle_mixed):
+    g = np.load(GOLD)
+    j = 0
+    out = oracle_mixed.column(10.0, *[g["in/" + k][:, j] for k in FIELDS], g["in/p"][:, j], g["in/dz"], want_rates=True)
+    assert out["rates"].shape == (36, 60) and len(oracle_mixed.rate_names) == 36
+    assert np.isfinite(out["rates"]).all() and np.abs(out["rates"]).max() > 0
