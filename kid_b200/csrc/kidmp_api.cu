@@ -44,6 +44,9 @@ struct kidmp_handle {
   double* d_diag = nullptr;
   float* d_rates = nullptr;
   float* d_kid = nullptr; size_t kid_floats = 0;   // staging of the KiD (k,i) arrays
+  float* d_pipe = nullptr; size_t pipe_floats = 0; int pipe_nz = 0; float* d_pipe_dz = nullptr;   // chunk pipeline of kidmp_step
+  long pipe_chunk = 65536;
+  cudaEvent_t pipe_ev[3][3] = {};
   float last_ms = 0.f;
   std::map<std::string, std::vector<double>> consts;   // named init constants for parity tests
 };
@@ -210,7 +213,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   StepArgs a = a0;
   // launch shape (DESIGN.md "Column kernel"): KIDMP_SHAPE = 0: one warp per block; 1: 256-thread lockstep blocks
   static const int shape = getenv("KIDMP_SHAPE") ? atoi(getenv("KIDMP_SHAPE")) : 0;
-  static const int minb = getenv("KIDMP_MINB") ? atoi(getenv("KIDMP_MINB")) : 8;
+  static const int minb = getenv("KIDMP_MINB") ? atoi(getenv("KIDMP_MINB")) : 12;
   const int threads = (shape == 1 && a.nz <= 64) ? 256 : 32;
   const long blocks = (a.ncol + threads - 1) / threads;
   const int sthreads = 128;
@@ -312,6 +315,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   kidmp_handle* h = new kidmp_handle();
   h->cfg = *cfg;
   h->device = cfg->device;
+  if (getenv("KIDMP_PIPE_CHUNK")) h->pipe_chunk = atol(getenv("KIDMP_PIPE_CHUNK")) > 1024 ? atol(getenv("KIDMP_PIPE_CHUNK")) : 1024;
   if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
   h->cfg.table_cache_path = nullptr;
   auto bail = [&](int) { g_init_error = h->err; kidmp_finalize(h); return 1; };
@@ -366,6 +370,9 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_kid) cudaFree(h->d_kid);
   if (h->d_scratch) cudaFree(h->d_scratch);
   if (h->d_colint) cudaFree(h->d_colint);
+  if (h->d_pipe) cudaFree(h->d_pipe);
+  if (h->d_pipe_dz) cudaFree(h->d_pipe_dz);
+  for (int b = 0; b < 3; ++b) for (int e = 0; e < 3; ++e) if (h->pipe_ev[b][e]) cudaEventDestroy(h->pipe_ev[b][e]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -486,9 +493,69 @@ int kidmp_download(kidmp_handle* h, int layout, float* const fields[KIDMP_NFIELD
   return 0;
 }
 
+// Large column-fastest domains: the columns are cut into chunks that flow through three streams
+// (H2D copy, the two step kernels, D2H copy) on double buffers, so both PCIe directions and the
+// SMs work at the same time.  Columns are independent, so chunking does not change any result.
+static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* const fields[KIDMP_NFIELDS],
+                          const float* p, const float* dz, float* ppt) {
+  const long chunk = h->pipe_chunk;
+  const int NB = 3;
+  const size_t cells = (size_t)chunk * nz;
+  const size_t per_buf = cells * (KIDMP_NFIELDS + 1) + (size_t)chunk * 4;
+  if (h->pipe_floats < per_buf * NB || h->pipe_nz != nz) {
+    if (h->d_pipe) cudaFree(h->d_pipe);
+    h->d_pipe = nullptr; h->pipe_floats = 0;
+    CK(h, cudaMalloc((void**)&h->d_pipe, per_buf * NB * 4));
+    h->pipe_floats = per_buf * NB; h->pipe_nz = nz;
+    if (!h->d_pipe_dz) CK(h, cudaMalloc((void**)&h->d_pipe_dz, 256 * 4));
+    for (int b = 0; b < NB; ++b)
+      for (int e = 0; e < 3; ++e)
+        if (!h->pipe_ev[b][e]) CK(h, cudaEventCreateWithFlags(&h->pipe_ev[b][e], cudaEventDisableTiming));
+  }
+  CK(h, cudaMemcpyAsync(h->d_pipe_dz, dz, (size_t)nz * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  const size_t hpitch = (size_t)ncol * 4;
+  long c0 = 0;
+  for (int it = 0; c0 < ncol; ++it, c0 += chunk) {
+    const int b = it % NB;
+    const long n = (ncol - c0 < chunk) ? (ncol - c0) : chunk;
+    float* base = h->d_pipe + per_buf * b;
+    float* d_ppt = base + cells * (KIDMP_NFIELDS + 1);
+    const size_t dpitch = (size_t)n * 4;
+    if (it >= NB) CK(h, cudaStreamWaitEvent(h->copy_in, h->pipe_ev[b][2], 0));     // buffer drained by its D2H
+    for (int q = 0; q <= KIDMP_NFIELDS; ++q) {
+      const float* src = (q < KIDMP_NFIELDS ? fields[q] : p) + c0;
+      CK(h, cudaMemcpy2DAsync(base + cells * q, dpitch, src, hpitch, dpitch, nz, cudaMemcpyHostToDevice, h->copy_in));
+    }
+    CK(h, cudaEventRecord(h->pipe_ev[b][0], h->copy_in));
+    CK(h, cudaStreamWaitEvent(h->stream, h->pipe_ev[b][0], 0));
+    StepArgs a{};
+    a.ncol = n; a.nz = nz; a.dt = dt;
+    for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = base + cells * q;
+    a.p = base + cells * KIDMP_NFIELDS; a.dz = h->d_pipe_dz; a.ppt = d_ppt;
+    if (launch_step(h, a, h->stream)) return 1;
+    CK(h, cudaEventRecord(h->pipe_ev[b][1], h->stream));
+    CK(h, cudaStreamWaitEvent(h->copy_out, h->pipe_ev[b][1], 0));
+    for (int q = 0; q < KIDMP_NFIELDS; ++q)
+      CK(h, cudaMemcpy2DAsync(fields[q] + c0, hpitch, base + cells * q, dpitch, dpitch, nz, cudaMemcpyDeviceToHost, h->copy_out));
+    if (ppt) CK(h, cudaMemcpy2DAsync(ppt + c0, hpitch, d_ppt, dpitch, dpitch, 4, cudaMemcpyDeviceToHost, h->copy_out));
+    CK(h, cudaEventRecord(h->pipe_ev[b][2], h->copy_out));
+  }
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  CK(h, cudaStreamSynchronize(h->copy_out));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout, float* const fields[KIDMP_NFIELDS],
                const float* p, const float* dz, float* ppt) {
   if (!h) return 1;
+  if (!fields || !p || !dz) return fail(h, "step: null pointer");
+  if (layout == KIDMP_COL_FASTEST && ncol >= 2 * h->pipe_chunk && nz >= 2 && nz <= 256 && dt > 0.f) {
+    for (int q = 0; q < KIDMP_NFIELDS; ++q) if (!fields[q]) return fail(h, "step: field %d is null", q);
+    cudaSetDevice(h->device);
+    return step_pipelined(h, ncol, nz, dt, fields, p, dz, ppt);
+  }
   if (kidmp_state_alloc(h, ncol, nz)) return 1;
   if (kidmp_upload(h, layout, fields, p, dz)) return 1;
   if (kidmp_step_resident(h, dt)) return 1;

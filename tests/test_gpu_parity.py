@@ -320,3 +320,22 @@ def test_kid_interface_tendencies(gpu_mixed, oracle_mixed, gpu_warm, oracle_warm
             assert err < 2e-6, (n, err)
             assert (a[n] == b[n]).mean() > 0.98, n
         np.testing.assert_allclose(a["ppt"], b["ppt"], rtol=1e-5, atol=1e-10)
+
+
+def test_pipelined_host_step_equals_resident_step(gpu_mixed, monkeypatch):
+    """kidmp_step cuts large column-fastest domains into chunks that overlap H2D, kernels and D2H;
+    chunking must not change a single bit (columns are independent)."""
+    from kid_b200.kidmp import Thompson
+    st, p, dz = _domain(5000, col0=300000, nx=1024)
+    whole = {k: v.copy() for k, v in st.items()}
+    pw = gpu_mixed.step(10.0, whole, p, dz)                    # 5000 < 2 * 65536: plain path
+    monkeypatch.setenv("KIDMP_PIPE_CHUNK", "1024")
+    t2 = Thompson(set_Nc=100.0, iiwarm=False, l_sediment=True)
+    piped = {k: v.copy() for k, v in st.items()}
+    pp = t2.step(10.0, piped, p, dz)                           # 5 chunks through the three-stream pipeline
+    for k in FIELDS:
+        assert np.array_equal(piped[k], whole[k]), k
+    assert np.array_equal(pp, pw)
+    d = t2.diag()
+    assert d[7] == 5000
+    t2.close()
