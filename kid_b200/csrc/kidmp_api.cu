@@ -41,11 +41,12 @@ struct kidmp_handle {
   double* d_partial = nullptr; long partial_blocks = 0;
   float* d_scratch = nullptr; size_t scratch_cells = 0;   // [SC_N][nz][ncol] hand-off between the two step kernels
   int* d_colint = nullptr; long scratch_cols = 0;
+  int* d_work = nullptr;                                  // [count | list | mask] of cloudy 32-column groups
   double* d_diag = nullptr;
   float* d_rates = nullptr;
   float* d_kid = nullptr; size_t kid_floats = 0;   // staging of the KiD (k,i) arrays
   float* d_pipe = nullptr; size_t pipe_floats = 0; int pipe_nz = 0; float* d_pipe_dz = nullptr;   // chunk pipeline of kidmp_step
-  long pipe_chunk = 65536;
+  long pipe_chunk = 262144;
   cudaEvent_t pipe_ev[3][3] = {};
   float last_ms = 0.f;
   std::map<std::string, std::vector<double>> consts;   // named init constants for parity tests
@@ -211,13 +212,12 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   if (!(a0.dt > 0.f)) return fail(h, "dt must be positive");
   if (ensure_constants(h)) return 1;
   StepArgs a = a0;
-  // launch shape (DESIGN.md "Column kernel"): KIDMP_SHAPE = 0: one warp per block; 1: 256-thread lockstep blocks
-  static const int shape = getenv("KIDMP_SHAPE") ? atoi(getenv("KIDMP_SHAPE")) : 0;
-  static const int minb = getenv("KIDMP_MINB") ? atoi(getenv("KIDMP_MINB")) : 12;
-  const int threads = (shape == 1 && a.nz <= 64) ? 256 : 32;
-  const long blocks = (a.ncol + threads - 1) / threads;
+  // launch shape: warps per lockstep block of the physics kernel; 16 warps at 128
+  // registers, 12 at 168 or 8 at 255 fill one SM.  KIDMP_WARPS overrides (tuning knob).
+  static const int warps = getenv("KIDMP_WARPS") ? atoi(getenv("KIDMP_WARPS")) : 12;
   const int sthreads = 128;
   const long sblocks = (a.ncol + sthreads - 1) / sthreads;
+  const long ngroups = (a.ncol + 31) / 32;
   if (sblocks > h->partial_blocks) {
     if (h->d_partial) cudaFree(h->d_partial);
     h->d_partial = nullptr; h->partial_blocks = 0;
@@ -228,25 +228,30 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   if (need > h->scratch_cells || a.ncol > h->scratch_cols) {
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->d_colint) cudaFree(h->d_colint);
-    h->d_scratch = nullptr; h->d_colint = nullptr; h->scratch_cells = 0; h->scratch_cols = 0;
+    if (h->d_work) cudaFree(h->d_work);
+    h->d_scratch = nullptr; h->d_colint = nullptr; h->d_work = nullptr; h->scratch_cells = 0; h->scratch_cols = 0;
     CK(h, cudaMalloc((void**)&h->d_scratch, need * SC_N * 4));
     CK(h, cudaMalloc((void**)&h->d_colint, (size_t)a.ncol * 8 * 4));
+    CK(h, cudaMalloc((void**)&h->d_work, (size_t)(2 * ngroups + 8) * 4));
     h->scratch_cells = need; h->scratch_cols = a.ncol;
   }
   a.scratch = h->d_scratch;
   a.colint = h->d_colint;
+  a.work_count = h->d_work;
+  a.work_list = h->d_work + 8;
+  a.work_mask = (unsigned*)(h->d_work + 8 + ngroups);
   a.diag_partial = h->d_partial;
   a.rates = h->d_rates;
-  if (a.nz <= 64) {
-    if (threads == 256) k_column_step<64, 256, 1, true><<<(unsigned)blocks, threads, 0, s>>>(a);
-    else if (minb >= 16) k_column_step<64, 32, 16, false><<<(unsigned)blocks, threads, 0, s>>>(a);
-    else if (minb >= 12) k_column_step<64, 32, 12, false><<<(unsigned)blocks, threads, 0, s>>>(a);
-    else k_column_step<64, 32, 8, false><<<(unsigned)blocks, threads, 0, s>>>(a);
-  } else if (a.nz <= 128) k_column_step<128, 32, 8, false><<<(unsigned)blocks, threads, 0, s>>>(a);
-  else k_column_step<256, 32, 8, false><<<(unsigned)blocks, threads, 0, s>>>(a);
+  CK(h, cudaMemsetAsync(h->d_work, 0, 4, s));
+  k_classify<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
+  // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
+  if (warps >= 16) k_column_step<16, 1><<<(unsigned)((ngroups + 15) / 16), 512, 0, s>>>(a);
+  else if (warps >= 12) k_column_step<12, 1><<<(unsigned)((ngroups + 11) / 12), 384, 0, s>>>(a);
+  else if (warps >= 8) k_column_step<8, 1><<<(unsigned)((ngroups + 7) / 8), 256, 0, s>>>(a);
+  else k_column_step<1, 12><<<(unsigned)ngroups, 32, 0, s>>>(a);
   k_sediment<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
   k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)sblocks, h->d_diag);
-  h->launches += 3;
+  h->launches += 4;
   CK(h, cudaGetLastError());
   return 0;
 }
@@ -342,6 +347,14 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   if (cudaMalloc((void**)&h->d_diag, KIDMP_NDIAG * 8) != cudaSuccess || cudaMemset(h->d_diag, 0, KIDMP_NDIAG * 8) != cudaSuccess) {
     h->err = "diag allocation failed"; return bail(1);
   }
+  {
+    static double et[KFM_N];
+    static LogNode lt[KFM_N];
+    kfm_build_tables(et, lt);
+    if (cudaMemcpyToSymbol(g_exp_tab, et, sizeof et) != cudaSuccess || cudaMemcpyToSymbol(g_log_tab, lt, sizeof lt) != cudaSuccess) {
+      h->err = "math table upload failed"; return bail(1);
+    }
+  }
   bool loaded = false;
   if (cfg->reuse_tables && !h->cache_path.empty()) loaded = load_cache(h) == 0;   // l_reuse_thompson_lookup, M:3720
   h->tables_from_cache = loaded;
@@ -370,6 +383,7 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_kid) cudaFree(h->d_kid);
   if (h->d_scratch) cudaFree(h->d_scratch);
   if (h->d_colint) cudaFree(h->d_colint);
+  if (h->d_work) cudaFree(h->d_work);
   if (h->d_pipe) cudaFree(h->d_pipe);
   if (h->d_pipe_dz) cudaFree(h->d_pipe_dz);
   for (int b = 0; b < 3; ++b) for (int e = 0; e < 3; ++e) if (h->pipe_ev[b][e]) cudaEventDestroy(h->pipe_ev[b][e]);

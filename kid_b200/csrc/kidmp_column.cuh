@@ -23,6 +23,12 @@ namespace kidmp {
 
 __constant__ KConst ck;
 
+// Helpers that appear at many call sites are kept out of line: one copy stays resident in the SM
+// instruction cache instead of ~2 000 inlined instructions streamed from L2.
+#ifndef KIDMP_HELPER
+#define KIDMP_HELPER __device__ __noinline__
+#endif
+
 #define R1 KP_R1
 #define R2 KP_R2
 #define EPSF KP_EPS
@@ -46,7 +52,7 @@ __device__ __forceinline__ void field_ab(float tc0, float c, float& loga_, float
   b_ = sb[1] + sb[2] * tc0 + sb[3] * c + sb[4] * tc0 * c + sb[5] * tc0 * tc0 + sb[6] * c * c
        + sb[7] * tc0 * tc0 * c + sb[8] * tc0 * c * c + sb[9] * tc0 * tc0 * tc0 + sb[10] * c * c * c;
 }
-__device__ __forceinline__ float field_moment(float tc0, float c, float smo2) {
+KIDMP_HELPER float field_moment(float tc0, float c, float smo2) {
   float loga_, b_;
   field_ab(tc0, c, loga_, b_);
   return pow10_f(loga_) * pow_f(smo2, b_);
@@ -60,7 +66,7 @@ __device__ __forceinline__ int decade_guess(float x) {
   const float l2 = (float)((b >> 23) - 127) + __int_as_float((b & 0x007fffff) | 0x3f800000) - 1.0f;
   return __float2int_rn(l2 * 0.30103f);
 }
-__device__ __forceinline__ int decade_idx_f(float x, int n2, int ntb) {
+KIDMP_HELPER int decade_idx_f(float x, int n2, int ntb) {
   const int n0 = decade_guess(x);
   int n = n0 + 1;
 #pragma unroll
@@ -71,7 +77,7 @@ __device__ __forceinline__ int decade_idx_f(float x, int n2, int ntb) {
   const int idx = (int)(x / ck.p10[n + 32]) + 9 * (n - n2);
   return max(1, min(idx, ntb));
 }
-__device__ __forceinline__ int decade_idx_d(double x, int n2, int ntb) {
+KIDMP_HELPER int decade_idx_d(double x, int n2, int ntb) {
   const int n0 = decade_guess((float)x);
   int n = n0 + 1;
 #pragma unroll
@@ -84,20 +90,20 @@ __device__ __forceinline__ int decade_idx_d(double x, int n2, int ntb) {
 }
 
 // rain number from mass at a clamped median volume diameter, M:1452-1454
-__device__ __forceinline__ float nr_from_mvd(float rr, float mvd_r) {
+KIDMP_HELPER float nr_from_mvd(float rr, float mvd_r) {
   const double lamr = (double)((3.0f + 0.0f + 0.672f) / mvd_r);
   return (float)((double)(ck.crg[1] * ck.org3 * rr) * cube_d(lamr) / (double)ck.am_r);
 }
 // lamr = (am_r*crg(3)*org2*nr/rr)**obmr, M:1457
-__device__ __forceinline__ double rain_lam(float nr, float rr) {
+KIDMP_HELPER double rain_lam(float nr, float rr) {
   return (double)pow_f(ck.am_r * ck.crg[2] * ck.org2 * nr / rr, ck.obmr);
 }
-__device__ __forceinline__ double ice_lam(float ni, float ri) {   // M:1429
+KIDMP_HELPER double ice_lam(float ni, float ri) {   // M:1429
   return (double)pow_f(ck.am_i * ck.cig[1] * ck.oig1 * ni / ri, ck.obmi);
 }
 
 // graupel intercept at one level given the running minimum from above, M:1639-1653
-__device__ __forceinline__ void graupel_n0(bool above_k0, bool L_qr, float mvd_r, float rg, double& N0_min,
+KIDMP_HELPER void graupel_n0(bool above_k0, bool L_qr, float mvd_r, float rg, double& N0_min,
                                            double& ilamg, double& N0_g) {
   float xslw1 = 0.01f;
   if (above_k0 && L_qr && mvd_r > 100.E-6f) xslw1 = 4.01f + log10_f(mvd_r);
@@ -119,32 +125,23 @@ struct ColPtrs {
 };
 enum { F_QV = 0, F_QC, F_QI, F_QR, F_QS, F_QG, F_NI, F_NR, F_T };
 
-// One warp per block: a warp of clear-sky columns retires at once and its slot goes to the next
-// block instead of waiting at a block barrier for a cloudy neighbour (profiles/r01).
-// LOCKSTEP (block of several warps): the cloudy warps of a block meet at a named barrier at every
-// level of the pass-1 sweep, so they run the same ~170 KB of straight-line code at the same time
-// and share its instruction-cache lines instead of each streaming it from L2 on its own.
-template <int NZMAX, int BLOCK, int MINB, bool LOCKSTEP>
-__global__ void __launch_bounds__(BLOCK, MINB) k_column_step(StepArgs a) {
-  __shared__ int s_active_warps;
-  if (LOCKSTEP) { if (threadIdx.x == 0) s_active_warps = 0; __syncthreads(); }
+// ---- K0: classification (pass 0).  One thread per column reads the ten fields once, decides
+// `no_micro` (M:1396-1521; the early RETURN at M:1540), writes back the species <= R1 that the
+// reference zeroes in the caller's arrays before returning (M:1412-1489, U9), marks clear-sky columns
+// in colint[0] and appends every 32-column group that holds a cloudy column to the work list of the
+// physics kernel.  Light on registers: many warps per SM keep the HBM pipe full for the ~70 % of
+// columns that need nothing else.
+__global__ void __launch_bounds__(128) k_classify(StepArgs a) {
   const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = col < a.ncol;
   const int nz = a.nz;
   const long ncol = a.ncol;
-  const float DT = a.dt;
-  const float odt = 1.f / DT, odts = 1.f / DT;
-  const float Nt_c = ck.Nt_c;
-  const bool iiwarm = ck.iiwarm != 0;
   bool active = false;
-
   if (in_range) {
     const float* __restrict__ Gp = a.p + col;
     float* Gqv = a.f[F_QV] + col; float* Gqc = a.f[F_QC] + col; float* Gqi = a.f[F_QI] + col;
     float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
     float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
-
-    // ---- pass 0: no_micro, M:1396-1521 --------------------------------------------------------
     bool no_micro = true;
 #pragma unroll 4
     for (int k = 0; k < nz; ++k) {
@@ -153,7 +150,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_column_step(StepArgs a) {
       const float ni = Gni[o], nr = Gnr[o];
       const float t = Gt[o], pr = Gp[o], qv = fmaxf(1.E-10f, Gqv[o]);
       if (qc > R1 || qi > R1 || qr > R1 || qs > R1 || qg > R1) no_micro = false;
-      // species at or below R1 are zeroed in the caller's arrays before the early return (U9)
       if (!(qc > R1) && qc != 0.0f) Gqc[o] = 0.0f;
       if (!(qi > R1) && (qi != 0.0f || ni != 0.0f)) { Gqi[o] = 0.0f; Gni[o] = 0.0f; }
       if (!(qr > R1) && (qr != 0.0f || nr != 0.0f)) { Gqr[o] = 0.0f; Gnr[o] = 0.0f; }
@@ -166,19 +162,44 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_column_step(StepArgs a) {
       if (ssati > 0.0f) no_micro = false;
     }
     active = !no_micro;
+    if (!active) a.colint[col] = -1;               // clear-sky column: nothing left to do
   }
-  const bool warp_active = __any_sync(0xffffffffu, active);
-  int lock_threads = 0;
-  if (LOCKSTEP) {
-    if (warp_active && (threadIdx.x & 31) == 0) atomicAdd(&s_active_warps, 1);
-    __syncthreads();
-    lock_threads = s_active_warps * 32;
+  const unsigned mask = __ballot_sync(0xffffffffu, active);
+  if (mask && (threadIdx.x & 31) == 0) {
+    const int pos = atomicAdd(a.work_count, 1);
+    a.work_list[pos] = (int)(col >> 5);
+    a.work_mask[pos] = mask;
   }
-  if (warp_active) {
-    const float* __restrict__ Gp = a.p + col;
-    float* Gqv = a.f[F_QV] + col; float* Gqc = a.f[F_QC] + col; float* Gqi = a.f[F_QI] + col;
-    float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
-    float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
+}
+
+// ---- K1: column physics, S1..S13, on the cloudy 32-column groups of the work list.  A block is
+// WARPS warps = WARPS groups; its warps meet at a named barrier at every level of the top-down sweep,
+// so they run the same ~120 KB of straight-line code at the same time and share its instruction-cache
+// lines (profiles/r01: with independent warps the GPC instruction cache sat at 98 % of its request
+// peak and `no_instruction` was 8 of 13 stall cycles per issue).
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
+  const int count = *a.work_count;
+  const int first = blockIdx.x * WARPS;
+  if (first >= count) return;
+  const int slot = first + (threadIdx.x >> 5);
+  const int lock_threads = min(WARPS, count - first) * 32;
+  if (slot >= count) return;
+  const long col = (long)a.work_list[slot] * 32 + (threadIdx.x & 31);
+  const bool active = (a.work_mask[slot] >> (threadIdx.x & 31)) & 1u;
+  const int nz = a.nz;
+  const long ncol = a.ncol;
+  const float DT = a.dt;
+  const float odt = 1.f / DT, odts = 1.f / DT;
+  const float Nt_c = ck.Nt_c;
+  const bool iiwarm = ck.iiwarm != 0;
+  constexpr bool LOCKSTEP = WARPS > 1;
+  {
+    const long colc = active ? col : 0;            // idle lanes of a cloudy group never dereference these
+    const float* __restrict__ Gp = a.p + colc;
+    float* Gqv = a.f[F_QV] + colc; float* Gqc = a.f[F_QC] + colc; float* Gqi = a.f[F_QI] + colc;
+    float* Gqr = a.f[F_QR] + colc; float* Gqs = a.f[F_QS] + colc; float* Gqg = a.f[F_QG] + colc;
+    float* Gni = a.f[F_NI] + colc; float* Gnr = a.f[F_NR] + colc; float* Gt = a.f[F_T] + colc;
     {
       // carried from the level above
       double N0_min_a = (double)KP_GONV_MAX, N0_min_b = (double)KP_GONV_MAX;
@@ -999,7 +1020,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_column_step(StepArgs a) {
       }
     }
   }
-  if (in_range && !active) a.colint[col] = -1;      // clear-sky column: nothing left to do
 }
 
 // ---- K2: sub-stepped upwind sedimentation (M:3365-3578), instant melt / freeze (M:3584-3606), apply

@@ -14,14 +14,19 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include "kidmp_fastmath.h"
 
 namespace kidmp {
+
+// node tables of kidmp_fastmath.h, filled by kidmp_init (read-only afterwards, L1-resident)
+__device__ double g_exp_tab[KFM_N];
+__device__ LogNode g_log_tab[KFM_N];
 
 // One copy of the f64 logarithm and exponential in the kernel image: the column kernel has ~130
 // call sites and its working set must stay near the instruction cache (profiles/r01: inlining
 // them made a 254 KB kernel that stalled 13 cycles per issue on instruction fetch).
-__device__ __noinline__ double dlog(double x) { return log(x); }
-__device__ __noinline__ double dexp(double x) { return exp(x); }
+__device__ __noinline__ double dlog(double x) { return kfm_log(x, g_log_tab); }
+__device__ __noinline__ double dexp(double x) { return kfm_exp(x, g_exp_tab); }
 // x**y for x > 0 (x = 0 gives 0 for y > 0, NaN propagates), f64
 __device__ __forceinline__ double pow_d(double x, double y) { return dexp(y * dlog(x)); }
 // f32 result: REAL ** REAL of the reference (a libm powf call under gfortran)
@@ -38,7 +43,7 @@ __device__ __forceinline__ int nint_f(float x) { return (int)lroundf(x); }     /
 __device__ __forceinline__ int nint_d(double x) { return (int)lround(x); }
 
 // RSLF / RSIF, M:4656-4717 (Flatau et al. polynomials, Horner form, f32)
-__device__ __forceinline__ float rslf(float P, float T) {
+__device__ __noinline__ float rslf(float P, float T) {
   const float C0 = .611583699E03f, C1 = .444606896E02f, C2 = .143177157E01f, C3 = .264224321E-1f,
               C4 = .299291081E-3f, C5 = .203154182E-5f, C6 = .702620698E-8f, C7 = .379534310E-11f,
               C8 = -.321582393E-13f;
@@ -47,7 +52,7 @@ __device__ __forceinline__ float rslf(float P, float T) {
   ESL = fminf(ESL, P * 0.15f);
   return .622f * ESL / (P - ESL);
 }
-__device__ __forceinline__ float rsif(float P, float T) {
+__device__ __noinline__ float rsif(float P, float T) {
   const float C0 = .609868993E03f, C1 = .499320233E02f, C2 = .184672631E01f, C3 = .402737184E-1f,
               C4 = .565392987E-3f, C5 = .521693933E-5f, C6 = .307839583E-7f, C7 = .105785160E-9f,
               C8 = .161444444E-12f;
