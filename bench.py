@@ -10,8 +10,8 @@ Weak scaling: every rank owns its own 1 048 576 columns [rank*ncol, (rank+1)*nco
 domain; columns are independent, so there is no data-path collective - NCCL only reduces the eight
 domain diagnostics once per run.
 
-A "step" = one kidmp_step_device call (one column-kernel launch + the 8-block diagnostics reduce)
-over all resident columns; the state evolves in place from step to step like a model time loop.
+A "step" = one kidmp_step_device call (four launches: classification, column physics on the cloudy
+32-column groups, sedimentation + final clamps, 8-block diagnostics reduce) over all resident columns; the state evolves in place from step to step like a model time loop.
 Inputs (2.8 GB per GPU) are far larger than L2, so no flush is needed between steps.
 """
 import argparse
@@ -32,6 +32,9 @@ UNIT = "column-steps/s"
 ALG_BYTES_PER_COLUMN = 4576          # 10 fields read + 9 written + 4 precip scalars, nz=60
 NZ = 60
 DT = 10.0
+# dram__bytes_read.sum + dram__bytes_write.sum of the three step kernels from the ncu --set full capture of the same
+# workload (profiles/r01_ncu_step_kernels.md): 2.52+0.01 (classify) + 1.24+1.97 (physics) + 3.28+0.72 (sedimentation) GB
+TRAFFIC_BYTES_PER_LAUNCH = 9.74e9
 
 
 def peaks():
@@ -247,7 +250,8 @@ def main():
                        "presence": presence,
                        "active_column_fraction": float(diag[6].item() / max(diag[7].item(), 1.0))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_column_step<64>",
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
+                         "kernel": "k_classify + k_column_step<16,1> + k_sediment (one step; k_column_step is 82 % of it)",
                          "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_COLUMN * ncol},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "diag": {"names": ["ppt_rain", "ppt_ice", "ppt_snow", "ppt_graupel", "lwp", "iwp", "active", "columns"],

@@ -214,15 +214,15 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   StepArgs a = a0;
   // launch shape: warps per lockstep block of the physics kernel; 16 warps at 128
   // registers, 12 at 168 or 8 at 255 fill one SM.  KIDMP_WARPS overrides (tuning knob).
-  static const int warps = getenv("KIDMP_WARPS") ? atoi(getenv("KIDMP_WARPS")) : 12;
+  static const int warps = getenv("KIDMP_WARPS") ? atoi(getenv("KIDMP_WARPS")) : 16;
   const int sthreads = 128;
   const long sblocks = (a.ncol + sthreads - 1) / sthreads;
   const long ngroups = (a.ncol + 31) / 32;
-  if (sblocks > h->partial_blocks) {
+  if (ngroups > h->partial_blocks) {
     if (h->d_partial) cudaFree(h->d_partial);
     h->d_partial = nullptr; h->partial_blocks = 0;
-    CK(h, cudaMalloc((void**)&h->d_partial, (size_t)sblocks * KIDMP_NDIAG * 8));
-    h->partial_blocks = sblocks;
+    CK(h, cudaMalloc((void**)&h->d_partial, (size_t)ngroups * KIDMP_NDIAG * 8));
+    h->partial_blocks = ngroups;
   }
   const size_t need = (size_t)a.ncol * a.nz;
   if (need > h->scratch_cells || a.ncol > h->scratch_cols) {
@@ -247,10 +247,11 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
   if (warps >= 16) k_column_step<16, 1><<<(unsigned)((ngroups + 15) / 16), 512, 0, s>>>(a);
   else if (warps >= 12) k_column_step<12, 1><<<(unsigned)((ngroups + 11) / 12), 384, 0, s>>>(a);
+  else if (warps == 9) k_column_step<8, 2><<<(unsigned)((ngroups + 7) / 8), 256, 0, s>>>(a);     // two 8-warp blocks per SM
   else if (warps >= 8) k_column_step<8, 1><<<(unsigned)((ngroups + 7) / 8), 256, 0, s>>>(a);
   else k_column_step<1, 12><<<(unsigned)ngroups, 32, 0, s>>>(a);
-  k_sediment<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
-  k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)sblocks, h->d_diag);
+  k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
+  k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)ngroups, h->d_diag);
   h->launches += 4;
   CK(h, cudaGetLastError());
   return 0;

@@ -131,7 +131,7 @@ enum { F_QV = 0, F_QC, F_QI, F_QR, F_QS, F_QG, F_NI, F_NR, F_T };
 // in colint[0] and appends every 32-column group that holds a cloudy column to the work list of the
 // physics kernel.  Light on registers: many warps per SM keep the HBM pipe full for the ~70 % of
 // columns that need nothing else.
-__global__ void __launch_bounds__(128) k_classify(StepArgs a) {
+__global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
   const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = col < a.ncol;
   const int nz = a.nz;
@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
   const int lock_threads = min(WARPS, count - first) * 32;
   if (slot >= count) return;
   const long col = (long)a.work_list[slot] * 32 + (threadIdx.x & 31);
-  const bool active = (a.work_mask[slot] >> (threadIdx.x & 31)) & 1u;
+  const unsigned gmask = a.work_mask[slot];
+  const bool active = (gmask >> (threadIdx.x & 31)) & 1u;
   const int nz = a.nz;
   const long ncol = a.ncol;
   const float DT = a.dt;
@@ -194,8 +195,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
   const float Nt_c = ck.Nt_c;
   const bool iiwarm = ck.iiwarm != 0;
   constexpr bool LOCKSTEP = WARPS > 1;
+  // stage barrier of the lockstep block: the warps stay within one instruction-cache window of each other
+#define LOCKBAR() do { if (LOCKSTEP) { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"r"(lock_threads) : "memory"); } } while (0)
   {
-    const long colc = active ? col : 0;            // idle lanes of a cloudy group never dereference these
+    // Clear-sky lanes of a cloudy group shadow the group's first cloudy column: they execute exactly
+    // the same branches as that lane (no extra divergence, nothing stored), which keeps every warp
+    // convergent at the stage barriers below.
+    const long colc = active ? col : (col - (threadIdx.x & 31) + (__ffs(gmask) - 1));
     const float* __restrict__ Gp = a.p + colc;
     float* Gqv = a.f[F_QV] + colc; float* Gqc = a.f[F_QC] + colc; float* Gqi = a.f[F_QI] + colc;
     float* Gqr = a.f[F_QR] + colc; float* Gqs = a.f[F_QS] + colc; float* Gqg = a.f[F_QG] + colc;
@@ -211,8 +217,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
       // ================= pass 1: top-down, S1..S13 per level ====================================
 #pragma unroll 1
       for (int k = nz - 1; k >= 0; --k) {
-        if (LOCKSTEP) { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"r"(lock_threads) : "memory"); }
-        if (active) {
+        LOCKBAR();
+        {
         const long o = (long)k * ncol;
         const float t1d = Gt[o], qv1d = Gqv[o], pres = Gp[o];
         float qc1d = Gqc[o], qi1d = Gqi[o], qr1d = Gqr[o], qs1d = Gqs[o], qg1d = Gqg[o];
@@ -370,6 +376,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           pnc_rcw = fmin((double)(nc * odts), pnc_rcw);
         }
 
+        LOCKBAR();
         // ---- S6, M:1749-2286 ice-phase processes --------------------------------------------------
         if (!iiwarm) {
           vts_boost = 1.5f;
@@ -634,6 +641,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           }
         }
 
+        LOCKBAR();
         // ---- S7, M:2291-2387 conservation limiters -----------------------------------------------
         {
           float sump = (float)(pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + 0.0);
@@ -769,6 +777,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           }
         }
 
+        LOCKBAR();
         // ---- S9, M:2574-2656 state at tau+1 -------------------------------------------------------
         float lvt2;
         {
@@ -824,6 +833,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
         N0_r = (double)(nr * ck.org2) * lamr;
 
+        LOCKBAR();
         // ---- S11, M:2780-2874 cloud condensation / evaporation ---------------------------------------
         if ((ssatw > EPSF) || (ssatw < -EPSF && L_qc)) {
           const float orho = 1.f / rho;
@@ -912,7 +922,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         }
 
         // M:2963-3120 the 36 process rates KiD saves with save_dg (optional buffer [36][nz][ncol])
-        if (a.rates) {
+        if (a.rates && active) {
           float* rp = a.rates + o + col;
           const long st = (long)nz * ncol;
           const double rv[KIDMP_NRATES] = {pri_inu, pri_ide, prs_ide, prs_sde, prg_gde, pri_wfz, prs_scw, prg_scw, prg_gcw, pri_ihm,
@@ -923,6 +933,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           for (int q = 0; q < KIDMP_NRATES; ++q) rp[q * st] = (float)rv[q];
         }
 
+        LOCKBAR();
         // ---- S13, M:3206-3354 fall speeds, substep counts (top-down carry) -----------------------------
         rhof = sqrtf(ck.rho_not / rho);
         float v_r, v_nr, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;
@@ -996,7 +1007,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         // hand-off to the sedimentation kernel: [SC_N][nz][ncol], coalesced fire-and-forget stores.
         // S15 (M:3584-3606) needs lfus*ocp where the level ends above T_0 and lfus2*ocp where it ends
         // below HGFR (never both): one signed value carries the product and the case.
-        {
+        if (active) {
           float s15 = 0.0f;
           if (temp > T_0) s15 = ck.lfus * ocp;
           else if (temp < KP_HGFR) s15 = -((KP_LSUB - lvap) * ocp);
@@ -1021,6 +1032,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
     }
   }
 }
+
+#undef LOCKBAR
 
 // ---- K2: sub-stepped upwind sedimentation (M:3365-3578), instant melt / freeze (M:3584-3606), apply
 // tendencies and final clamps (M:3623-3686).  One thread per column, light on registers, so many
@@ -1060,7 +1073,7 @@ __device__ __forceinline__ void sed_substeps(float* __restrict__ r, float* __res
   }
 }
 
-__global__ void __launch_bounds__(128) k_sediment(StepArgs a) {
+__global__ void __launch_bounds__(32) k_sediment(StepArgs a) {
   const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = col < a.ncol;
   const int nz = a.nz;
@@ -1223,22 +1236,18 @@ __global__ void __launch_bounds__(128) k_sediment(StepArgs a) {
     a.ppt[col] = ppt_r; a.ppt[ncol + col] = ppt_i; a.ppt[2 * ncol + col] = ppt_s; a.ppt[3 * ncol + col] = ppt_g;
   }
 
-  // ---- block partial sums for the domain diagnostics (fixed order => run-to-run identical) ----------
+  // ---- warp partial sums for the domain diagnostics (fixed order => run-to-run identical); one warp per
+  // block, so a warp of clear-sky columns retires at once
   if (a.diag_partial) {
-    __shared__ double s_red[4][KIDMP_NDIAG];
+    const bool any = __any_sync(0xffffffffu, active);
     double v[KIDMP_NDIAG] = {(double)ppt_r, (double)ppt_i, (double)ppt_s, (double)ppt_g, lwp, iwp,
                              active ? 1.0 : 0.0, in_range ? 1.0 : 0.0};
 #pragma unroll
     for (int q = 0; q < KIDMP_NDIAG; ++q) {
       double x = v[q];
-      for (int s = 16; s > 0; s >>= 1) x += __shfl_down_sync(0xffffffffu, x, s);
-      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][q] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < KIDMP_NDIAG) {
-      double x = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += s_red[w][threadIdx.x];
-      a.diag_partial[(size_t)blockIdx.x * KIDMP_NDIAG + threadIdx.x] = x;
+      if (any || q == KIDMP_NDIAG - 1)
+        for (int s = 16; s > 0; s >>= 1) x += __shfl_down_sync(0xffffffffu, x, s);
+      if (threadIdx.x == 0) a.diag_partial[(size_t)blockIdx.x * KIDMP_NDIAG + q] = x;
     }
   }
 }
