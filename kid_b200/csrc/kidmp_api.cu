@@ -245,11 +245,20 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   CK(h, cudaMemsetAsync(h->d_work, 0, 4, s));
   k_classify<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
   // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
-  if (warps >= 16) k_column_step<16, 1><<<(unsigned)((ngroups + 15) / 16), 512, 0, s>>>(a);
-  else if (warps >= 12) k_column_step<12, 1><<<(unsigned)((ngroups + 11) / 12), 384, 0, s>>>(a);
-  else if (warps == 9) k_column_step<8, 2><<<(unsigned)((ngroups + 7) / 8), 256, 0, s>>>(a);     // two 8-warp blocks per SM
-  else if (warps >= 8) k_column_step<8, 1><<<(unsigned)((ngroups + 7) / 8), 256, 0, s>>>(a);
-  else k_column_step<1, 12><<<(unsigned)ngroups, 32, 0, s>>>(a);
+  static const int bars = getenv("KIDMP_BARS") ? atoi(getenv("KIDMP_BARS")) : 11;
+  const unsigned g16 = (unsigned)((ngroups + 15) / 16), g8 = (unsigned)((ngroups + 7) / 8);
+  if (warps >= 16) {
+    if (bars == 63) k_column_step<16, 1, 63><<<g16, 512, 0, s>>>(a);
+    else if (bars == 11) k_column_step<16, 1, 11><<<g16, 512, 0, s>>>(a);      // level top, before S6, before S9
+    else if (bars == 3) k_column_step<16, 1, 3><<<g16, 512, 0, s>>>(a);
+    else k_column_step<16, 1, 1><<<g16, 512, 0, s>>>(a);
+  } else if (warps >= 12) k_column_step<12, 1, 63><<<(unsigned)((ngroups + 11) / 12), 384, 0, s>>>(a);
+  else if (warps == 9) {                                                         // two 8-warp blocks per SM
+    if (bars == 63) k_column_step<8, 2, 63><<<g8, 256, 0, s>>>(a);
+    else if (bars == 11) k_column_step<8, 2, 11><<<g8, 256, 0, s>>>(a);
+    else k_column_step<8, 2, 1><<<g8, 256, 0, s>>>(a);
+  } else if (warps >= 8) k_column_step<8, 1, 63><<<g8, 256, 0, s>>>(a);
+  else k_column_step<1, 12, 0><<<(unsigned)ngroups, 32, 0, s>>>(a);
   k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
   k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)ngroups, h->d_diag);
   h->launches += 4;

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
 // so they run the same ~120 KB of straight-line code at the same time and share its instruction-cache
 // lines (profiles/r01: with independent warps the GPC instruction cache sat at 98 % of its request
 // peak and `no_instruction` was 8 of 13 stall cycles per issue).
-template <int WARPS, int MINB>
+template <int WARPS, int MINB, int BARS>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
   const int count = *a.work_count;
   const int first = blockIdx.x * WARPS;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
   const bool iiwarm = ck.iiwarm != 0;
   constexpr bool LOCKSTEP = WARPS > 1;
   // stage barrier of the lockstep block: the warps stay within one instruction-cache window of each other
-#define LOCKBAR() do { if (LOCKSTEP) { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"r"(lock_threads) : "memory"); } } while (0)
+#define LOCKBAR(i) do { if (LOCKSTEP && ((BARS >> (i)) & 1)) { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"r"(lock_threads) : "memory"); } } while (0)
   {
     // Clear-sky lanes of a cloudy group shadow the group's first cloudy column: they execute exactly
     // the same branches as that lane (no extra divergence, nothing stored), which keeps every warp
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
       // ================= pass 1: top-down, S1..S13 per level ====================================
 #pragma unroll 1
       for (int k = nz - 1; k >= 0; --k) {
-        LOCKBAR();
+        LOCKBAR(0);
         {
         const long o = (long)k * ncol;
         const float t1d = Gt[o], qv1d = Gqv[o], pres = Gp[o];
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           pnc_rcw = fmin((double)(nc * odts), pnc_rcw);
         }
 
-        LOCKBAR();
+        LOCKBAR(1);
         // ---- S6, M:1749-2286 ice-phase processes --------------------------------------------------
         if (!iiwarm) {
           vts_boost = 1.5f;
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           }
         }
 
-        LOCKBAR();
+        LOCKBAR(2);
         // ---- S7, M:2291-2387 conservation limiters -----------------------------------------------
         {
           float sump = (float)(pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + 0.0);
@@ -777,7 +777,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           }
         }
 
-        LOCKBAR();
+        LOCKBAR(3);
         // ---- S9, M:2574-2656 state at tau+1 -------------------------------------------------------
         float lvt2;
         {
@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
         N0_r = (double)(nr * ck.org2) * lamr;
 
-        LOCKBAR();
+        LOCKBAR(4);
         // ---- S11, M:2780-2874 cloud condensation / evaporation ---------------------------------------
         if ((ssatw > EPSF) || (ssatw < -EPSF && L_qc)) {
           const float orho = 1.f / rho;
@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           for (int q = 0; q < KIDMP_NRATES; ++q) rp[q * st] = (float)rv[q];
         }
 
-        LOCKBAR();
+        LOCKBAR(5);
         // ---- S13, M:3206-3354 fall speeds, substep counts (top-down carry) -----------------------------
         rhof = sqrtf(ck.rho_not / rho);
         float v_r, v_nr, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;
