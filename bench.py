@@ -46,7 +46,9 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (B200_PROFILING.md recipe): one
+    streaming `nvidia-smi -lms 100` process, started before the warm-up so that samples exist inside a
+    timed region of a few hundred milliseconds; `mark()` brackets the timed region."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -55,31 +57,46 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self.stop_flag = False
+        self.t0 = self.t1 = None
+        self.proc = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                parts = [x.strip() for x in line.strip().split(",")]
                 if len(parts) >= 7:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            time.sleep(0.15)
+                    self.rows.append((time.perf_counter(), parts))
+        except Exception:
+            pass
+
+    def mark(self, start):
+        if start:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
 
     def summary(self):
-        self.stop_flag = True
-        if not self.rows:
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e99)]
+        where = "timed region"
+        if not inside:                 # region shorter than the sampling period: samples of the warm-up just before it
+            inside = [r for t, r in self.rows if self.t0 is None or t <= self.t0][-5:]
+            where = "warm-up just before the timed region"
+        if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(float(r[0]) for r in inside)
         reasons = []
         for j, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
-            if any(r[j].lower().startswith("active") for r in self.rows):
+            if any(r[j].lower().startswith("active") for r in inside):
                 reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][1]), "reasons": reasons,
+                "samples": len(inside), "sampled_in": where, "power_w_max": max(float(r[2]) for r in inside)}
 
 
 def cpu_reference_run(ncol, steps, warmup, nthreads, col0=0):
@@ -127,12 +144,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kidmp", choices=["kidmp", "reference"])
     ap.add_argument("--columns", type=int, default=1024 * 1024, help="columns per GPU")
     ap.add_argument("--cpu-columns", type=int, default=262144, help="columns of the bounded CPU sample")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kidmp" else args.warmup
@@ -173,23 +190,25 @@ def main():
     def one_step():
         th.step_device(ncol, NZ, DT, fptr, p.data_ptr(), dz.data_ptr(), ppt.data_ptr(), stream=stream)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
     th.diag()
     launches0 = th.gpu_launches
 
-    sampler = ClockSampler(local)
-    sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark(True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     for i in range(args.steps):
         ev[i].record()
         one_step()
     ev[args.steps].record()
     torch.cuda.synchronize()
+    sampler.mark(False)
     diag = torch.from_numpy(th.diag()).to(dev)          # the 8 domain sums accumulated over the K steps
     if world > 1:
         dist.all_reduce(diag)                           # the only collective: 64 bytes of diagnostics
@@ -260,9 +279,9 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            v, ms, init_s = cpu_reference_run(args.cpu_columns, 3, 1, cores)
+            v, ms, init_s = cpu_reference_run(args.cpu_columns, 10, 1, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "first %d columns of the bench domain x 3 steps, OpenMP over columns; C++ "
+                                    "sample": "first %d columns of the bench domain x 10 steps, OpenMP over columns; C++ "
                                               "restatement of the reference (no Fortran compiler), init %.1f s excluded"
                                               % (args.cpu_columns, init_s)}
         print(json.dumps(line), flush=True)

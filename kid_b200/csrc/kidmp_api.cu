@@ -47,6 +47,7 @@ struct kidmp_handle {
   float* d_kid = nullptr; size_t kid_floats = 0;   // staging of the KiD (k,i) arrays
   float* d_pipe = nullptr; size_t pipe_floats = 0; int pipe_nz = 0; float* d_pipe_dz = nullptr;   // chunk pipeline of kidmp_step
   long pipe_chunk = 262144;
+  float* h_ppt = nullptr; size_t h_ppt_floats = 0;       // pinned staging of ppt for the chunk pipeline
   cudaEvent_t pipe_ev[3][3] = {};
   float last_ms = 0.f;
   std::map<std::string, std::vector<double>> consts;   // named init constants for parity tests
@@ -396,6 +397,7 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_work) cudaFree(h->d_work);
   if (h->d_pipe) cudaFree(h->d_pipe);
   if (h->d_pipe_dz) cudaFree(h->d_pipe_dz);
+  if (h->h_ppt) cudaFreeHost(h->h_ppt);
   for (int b = 0; b < 3; ++b) for (int e = 0; e < 3; ++e) if (h->pipe_ev[b][e]) cudaEventDestroy(h->pipe_ev[b][e]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -536,6 +538,14 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
       for (int e = 0; e < 3; ++e)
         if (!h->pipe_ev[b][e]) CK(h, cudaEventCreateWithFlags(&h->pipe_ev[b][e], cudaEventDisableTiming));
   }
+  // ppt goes through a pinned staging buffer: a D2H copy into pageable memory would block the host at every
+  // chunk and serialise the pipeline
+  if (ppt && h->h_ppt_floats < (size_t)ncol * 4) {
+    if (h->h_ppt) cudaFreeHost(h->h_ppt);
+    h->h_ppt = nullptr; h->h_ppt_floats = 0;
+    CK(h, cudaHostAlloc((void**)&h->h_ppt, (size_t)ncol * 16, cudaHostAllocDefault));
+    h->h_ppt_floats = (size_t)ncol * 4;
+  }
   CK(h, cudaMemcpyAsync(h->d_pipe_dz, dz, (size_t)nz * 4, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaEventRecord(h->ev0, h->stream));
   const size_t hpitch = (size_t)ncol * 4;
@@ -562,12 +572,13 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
     CK(h, cudaStreamWaitEvent(h->copy_out, h->pipe_ev[b][1], 0));
     for (int q = 0; q < KIDMP_NFIELDS; ++q)
       CK(h, cudaMemcpy2DAsync(fields[q] + c0, hpitch, base + cells * q, dpitch, dpitch, nz, cudaMemcpyDeviceToHost, h->copy_out));
-    if (ppt) CK(h, cudaMemcpy2DAsync(ppt + c0, hpitch, d_ppt, dpitch, dpitch, 4, cudaMemcpyDeviceToHost, h->copy_out));
+    if (ppt) CK(h, cudaMemcpy2DAsync(h->h_ppt + c0, hpitch, d_ppt, dpitch, dpitch, 4, cudaMemcpyDeviceToHost, h->copy_out));
     CK(h, cudaEventRecord(h->pipe_ev[b][2], h->copy_out));
   }
   CK(h, cudaEventRecord(h->ev1, h->stream));
   CK(h, cudaStreamSynchronize(h->copy_out));
   CK(h, cudaStreamSynchronize(h->stream));
+  if (ppt) memcpy(ppt, h->h_ppt, (size_t)ncol * 16);
   return 0;
 }
 
