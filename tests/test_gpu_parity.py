@@ -339,3 +339,29 @@ def test_pipelined_host_step_equals_resident_step(gpu_mixed, monkeypatch):
     d = t2.diag()
     assert d[7] == 5000
     t2.close()
+
+
+@pytest.mark.parametrize("name", ["warm1", "deep1", "cu2d"])
+def test_kinematic_case_time_series(name):
+    """BASELINE configs 1-3 through the KiD-facing entry (kidmp_kid_interface) under a minimal kinematic host:
+    surface precipitation and LWP / IWP time series of the CUDA path stay within 0.1 % of the oracle's over the
+    whole case (north_star acceptance criterion; the host is kid_b200/kinematic.py because KiD's is not in the reference)."""
+    from kid_b200 import kinematic as km
+    from kid_b200.kidmp import Thompson
+    from oracle.oracle import Oracle, kid_interface
+    c = km.CASES[name]()
+    g = Thompson(set_Nc=c.set_Nc, iiwarm=c.iiwarm)
+    o = Oracle(set_Nc=c.set_Nc, iiwarm=c.iiwarm)
+    rg = km.run(c, g.kid_interface)
+    ro = km.run(c, lambda kid, dt, p0, roc: kid_interface(o, kid, dt, p0, roc))
+    for key in ("lwp", "iwp"):
+        scale = np.abs(ro[key]).max()
+        if scale > 0:
+            assert np.abs(rg[key] - ro[key]).max() <= 1e-3 * scale, (name, key, np.abs(rg[key] - ro[key]).max() / scale)
+    acc_g, acc_o = np.cumsum(rg["ppt"], axis=0), np.cumsum(ro["ppt"], axis=0)      # accumulated surface precipitation
+    for j in range(4):
+        scale = np.abs(acc_o[:, j]).max()
+        if scale > 0:
+            assert np.abs(acc_g[:, j] - acc_o[:, j]).max() <= 1e-3 * scale, (name, "ppt", j)
+    assert ro["lwp"].max() > 0.1 and (c.iiwarm or ro["iwp"].max() > 0.01)          # the case actually rained / glaciated
+    g.close(); o.close()
