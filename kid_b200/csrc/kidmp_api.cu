@@ -233,14 +233,13 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     h->d_scratch = nullptr; h->d_colint = nullptr; h->d_work = nullptr; h->scratch_cells = 0; h->scratch_cols = 0;
     CK(h, cudaMalloc((void**)&h->d_scratch, need * SC_N * 4));
     CK(h, cudaMalloc((void**)&h->d_colint, (size_t)a.ncol * 8 * 4));
-    CK(h, cudaMalloc((void**)&h->d_work, (size_t)(2 * ngroups + 8) * 4));
+    CK(h, cudaMalloc((void**)&h->d_work, (size_t)(a.ncol + 8) * 4));
     h->scratch_cells = need; h->scratch_cols = a.ncol;
   }
   a.scratch = h->d_scratch;
   a.colint = h->d_colint;
   a.work_count = h->d_work;
   a.work_list = h->d_work + 8;
-  a.work_mask = (unsigned*)(h->d_work + 8 + ngroups);
   a.diag_partial = h->d_partial;
   a.rates = h->d_rates;
   CK(h, cudaMemsetAsync(h->d_work, 0, 4, s));
@@ -248,7 +247,9 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
   static const int bars = getenv("KIDMP_BARS") ? atoi(getenv("KIDMP_BARS")) : 11;
   const unsigned g16 = (unsigned)((ngroups + 15) / 16), g8 = (unsigned)((ngroups + 7) / 8);
-  if (warps >= 16) {
+  if (warps >= 24) k_column_step<24, 1, 11><<<(unsigned)((ngroups + 23) / 24), 768, 0, s>>>(a);
+  else if (warps >= 20) k_column_step<20, 1, 11><<<(unsigned)((ngroups + 19) / 20), 640, 0, s>>>(a);
+  else if (warps >= 16) {
     if (bars == 63) k_column_step<16, 1, 63><<<g16, 512, 0, s>>>(a);
     else if (bars == 11) k_column_step<16, 1, 11><<<g16, 512, 0, s>>>(a);      // level top, before S6, before S9
     else if (bars == 3) k_column_step<16, 1, 3><<<g16, 512, 0, s>>>(a);

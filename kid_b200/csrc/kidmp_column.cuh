@@ -164,11 +164,14 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
     active = !no_micro;
     if (!active) a.colint[col] = -1;               // clear-sky column: nothing left to do
   }
+  // append the cloudy columns of this warp to the work list (one atomic per warp, order within the warp kept)
   const unsigned mask = __ballot_sync(0xffffffffu, active);
-  if (mask && (threadIdx.x & 31) == 0) {
-    const int pos = atomicAdd(a.work_count, 1);
-    a.work_list[pos] = (int)(col >> 5);
-    a.work_mask[pos] = mask;
+  if (mask) {
+    const int lane = threadIdx.x & 31;
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(a.work_count, __popc(mask));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (active) a.work_list[pos + __popc(mask & ((1u << lane) - 1u))] = (int)col;
   }
 }
 
@@ -179,15 +182,17 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
 // peak and `no_instruction` was 8 of 13 stall cycles per issue).
 template <int WARPS, int MINB, int BARS>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
-  const int count = *a.work_count;
-  const int first = blockIdx.x * WARPS;
+  const int count = *a.work_count;                     // cloudy columns, compacted: every warp but the last is full
+  const int first = blockIdx.x * WARPS * 32;
   if (first >= count) return;
-  const int slot = first + (threadIdx.x >> 5);
-  const int lock_threads = min(WARPS, count - first) * 32;
-  if (slot >= count) return;
-  const long col = (long)a.work_list[slot] * 32 + (threadIdx.x & 31);
-  const unsigned gmask = a.work_mask[slot];
-  const bool active = (gmask >> (threadIdx.x & 31)) & 1u;
+  const int wfirst = first + (threadIdx.x & ~31);
+  const int lock_threads = min(WARPS, (count - first + 31) / 32) * 32;
+  if (wfirst >= count) return;
+  const int slot = wfirst + (threadIdx.x & 31);
+  const bool active = slot < count;
+  // lanes past the end of the list shadow the warp's first column: same branches, nothing stored, and the warp
+  // stays convergent at the stage barriers
+  const long col = (long)a.work_list[active ? slot : wfirst];
   const int nz = a.nz;
   const long ncol = a.ncol;
   const float DT = a.dt;
@@ -198,10 +203,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
   // stage barrier of the lockstep block: the warps stay within one instruction-cache window of each other
 #define LOCKBAR(i) do { if (LOCKSTEP && ((BARS >> (i)) & 1)) { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"r"(lock_threads) : "memory"); } } while (0)
   {
-    // Clear-sky lanes of a cloudy group shadow the group's first cloudy column: they execute exactly
-    // the same branches as that lane (no extra divergence, nothing stored), which keeps every warp
-    // convergent at the stage barriers below.
-    const long colc = active ? col : (col - (threadIdx.x & 31) + (__ffs(gmask) - 1));
+    const long colc = col;
     const float* __restrict__ Gp = a.p + colc;
     float* Gqv = a.f[F_QV] + colc; float* Gqc = a.f[F_QC] + colc; float* Gqi = a.f[F_QI] + colc;
     float* Gqr = a.f[F_QR] + colc; float* Gqs = a.f[F_QS] + colc; float* Gqg = a.f[F_QG] + colc;

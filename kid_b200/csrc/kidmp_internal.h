@@ -114,9 +114,8 @@ struct StepArgs {
   float* ppt;                  // [4][ncol]
   float* scratch;              // [SC_N][nz][ncol] hand-off, touched for cloudy columns only
   int* colint;                 // [8][ncol] substep counts / top sedimenting level per species; [0] = -1: clear sky
-  int* work_count;             // number of cloudy 32-column groups found by the classification kernel
-  int* work_list;              // their group indices (column / 32), in discovery order
-  unsigned* work_mask;         // ballot of the cloudy lanes of each listed group
+  int* work_count;             // number of cloudy columns found by the classification kernel
+  int* work_list;              // their column indices, compacted (warp-sized runs in discovery order)
   float* rates;                // optional [36][nz][ncol]
   double* diag_partial;        // optional [gridDim.x][KIDMP_NDIAG] block sums
 };

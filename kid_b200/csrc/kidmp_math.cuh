@@ -22,15 +22,77 @@ namespace kidmp {
 __device__ double g_exp_tab[KFM_N];
 __device__ LogNode g_log_tab[KFM_N];
 
-// One copy of the f64 logarithm and exponential in the kernel image: the column kernel has ~130
-// call sites and its working set must stay near the instruction cache (profiles/r01: inlining
-// them made a 254 KB kernel that stalled 13 cycles per issue on instruction fetch).
-__device__ __noinline__ double dlog(double x) { return kfm_log(x, g_log_tab); }
-__device__ __noinline__ double dexp(double x) { return kfm_exp(x, g_exp_tab); }
-// x**y for x > 0 (x = 0 gives 0 for y > 0, NaN propagates), f64
-__device__ __forceinline__ double pow_d(double x, double y) { return dexp(y * dlog(x)); }
+// One copy of the f64 logarithm / exponential / power in the kernel image: the column kernel has ~130
+// call sites and its working set must stay near the instruction cache (profiles/r01: inlining them made
+// a 254 KB kernel that stalled 13 cycles per issue on instruction fetch).  The bodies are the
+// table-driven algorithms of kidmp_fastmath.h with the polynomial coefficients read straight from the
+// constant bank (no immediate materialisation) and, for x**y, one fused routine (one call, one
+// descriptor set-up, no intermediate special-case test).
+__constant__ double c_fm[16] = {
+    184.6649652337873,            // 0  128/ln2
+    6755399441055744.0,           // 1  1.5*2^52
+    -0.005415212333900854,        // 2  -ln2/128 hi
+    -1.4223718738313642e-11,      // 3  -ln2/128 lo
+    8.3333333333333332e-03,       // 4  1/120
+    4.1666666666666664e-02,       // 5  1/24
+    1.6666666666666666e-01,       // 6  1/6
+    1.4285714285714285e-01,       // 7  1/7
+    -1.6666666666666666e-01,      // 8  -1/6
+    0.2,                          // 9
+    3.3333333333333331e-01,       // 10
+    6.9314718055989033e-01,       // 11 ln2 hi
+    5.4979230187083712e-14,       // 12 ln2 lo
+    0.0, 0.0, 0.0};
+
+__device__ __forceinline__ double fm_exp_core(double x) {          // |x| < 704
+  const double kd0 = x * c_fm[0] + c_fm[1];
+  const int k = __double2loint(kd0);
+  const double kd = kd0 - c_fm[1];
+  double r = fma(kd, c_fm[2], x);
+  r = fma(kd, c_fm[3], r);
+  const double r2 = r * r;
+  double p = fma(r, c_fm[4], c_fm[5]);
+  const double q = fma(r, c_fm[6], 0.5);
+  p = fma(r2, p, q);
+  p = fma(r2, p, r);
+  const double t = __ldg(g_exp_tab + (k & (KFM_N - 1)));
+  const double s = __hiloint2double(__double2hiint(t) + ((k >> 7) << 20), __double2loint(t));
+  return fma(s, p, s);
+}
+__device__ __forceinline__ double fm_log_core(double x) {          // x positive, normal, finite
+  const int hx = __double2hiint(x);
+  const int tmp = hx - 0x3fe60000;
+  const int i = (tmp >> 13) & (KFM_N - 1);
+  const double z = __hiloint2double(hx - (tmp & (int)0xfff00000), __double2loint(x));
+  const double2 nd = __ldg(reinterpret_cast<const double2*>(g_log_tab) + i);
+  const double r = fma(z, nd.x, -1.0);
+  const double kd = (double)(tmp >> 20);
+  double p = fma(r, c_fm[7], c_fm[8]);
+  p = fma(r, p, c_fm[9]);
+  p = fma(r, p, -0.25);
+  p = fma(r, p, c_fm[10]);
+  p = fma(r, p, -0.5);
+  const double hi = fma(kd, c_fm[11], nd.y);
+  const double lo = fma(kd, c_fm[12], r);
+  return hi + fma(r * r, p, lo);
+}
+__device__ __forceinline__ bool fm_log_fast(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u; }
+__device__ __forceinline__ bool fm_exp_fast(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x40860000; }
+
+__device__ __noinline__ double dlog(double x) { return fm_log_fast(x) ? fm_log_core(x) : log(x); }
+__device__ __noinline__ double dexp(double x) { return fm_exp_fast(x) ? fm_exp_core(x) : exp(x); }
+// x**y = exp(y*log(x)) for x > 0 (x = 0 gives 0 for y > 0, NaN propagates), f64
+__device__ __noinline__ double dpow(double x, double y) {
+  if (fm_log_fast(x)) {
+    const double e = y * fm_log_core(x);
+    if (fm_exp_fast(e)) return fm_exp_core(e);
+    return exp(e);
+  }
+  return exp(y * log(x));
+}
+__device__ __forceinline__ double pow_d(double x, double y) { return dpow(x, y); }
 // f32 result: REAL ** REAL of the reference (a libm powf call under gfortran)
-__device__ __forceinline__ float pow_f(float x, float y) { return (float)dexp((double)y * dlog((double)x)); }
+__device__ __forceinline__ float pow_f(float x, float y) { return (float)dpow((double)x, (double)y); }
 __device__ __forceinline__ float exp_f(float x) { return (float)dexp((double)x); }
 __device__ __forceinline__ float log10_f(float x) { return (float)(dlog((double)x) * 0.43429448190325182765); }
 // 10.**y with REAL y (M:1560, M:1646, M:2242 ...)
