@@ -215,7 +215,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   StepArgs a = a0;
   // launch shape: warps per lockstep block of the physics kernel; 16 warps at 128
   // registers, 12 at 168 or 8 at 255 fill one SM.  KIDMP_WARPS overrides (tuning knob).
-  static const int warps = getenv("KIDMP_WARPS") ? atoi(getenv("KIDMP_WARPS")) : 16;
+  static const int warps = getenv("KIDMP_WARPS") ? atoi(getenv("KIDMP_WARPS")) : 24;
   const int sthreads = 128;
   const long sblocks = (a.ncol + sthreads - 1) / sthreads;
   const long ngroups = (a.ncol + 31) / 32;
@@ -247,20 +247,23 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
   static const int bars = getenv("KIDMP_BARS") ? atoi(getenv("KIDMP_BARS")) : 11;
   const unsigned g16 = (unsigned)((ngroups + 15) / 16), g8 = (unsigned)((ngroups + 7) / 8);
-  if (warps >= 24) k_column_step<24, 1, 11><<<(unsigned)((ngroups + 23) / 24), 768, 0, s>>>(a);
-  else if (warps >= 20) k_column_step<20, 1, 11><<<(unsigned)((ngroups + 19) / 20), 640, 0, s>>>(a);
+  if (a.rates) k_column_step<16, 1, 11, true><<<(unsigned)((ngroups + 15) / 16), 512, 0, s>>>(a);   // with the 36 save_dg rates
+  else if (warps >= 32) k_column_step<32, 1, 11, false><<<(unsigned)((ngroups + 31) / 32), 1024, 0, s>>>(a);
+  else if (warps >= 28) k_column_step<28, 1, 11, false><<<(unsigned)((ngroups + 27) / 28), 896, 0, s>>>(a);
+  else if (warps >= 24) k_column_step<24, 1, 11, false><<<(unsigned)((ngroups + 23) / 24), 768, 0, s>>>(a);
+  else if (warps >= 20) k_column_step<20, 1, 11, false><<<(unsigned)((ngroups + 19) / 20), 640, 0, s>>>(a);
   else if (warps >= 16) {
-    if (bars == 63) k_column_step<16, 1, 63><<<g16, 512, 0, s>>>(a);
-    else if (bars == 11) k_column_step<16, 1, 11><<<g16, 512, 0, s>>>(a);      // level top, before S6, before S9
-    else if (bars == 3) k_column_step<16, 1, 3><<<g16, 512, 0, s>>>(a);
-    else k_column_step<16, 1, 1><<<g16, 512, 0, s>>>(a);
-  } else if (warps >= 12) k_column_step<12, 1, 63><<<(unsigned)((ngroups + 11) / 12), 384, 0, s>>>(a);
+    if (bars == 63) k_column_step<16, 1, 63, false><<<g16, 512, 0, s>>>(a);
+    else if (bars == 11) k_column_step<16, 1, 11, false><<<g16, 512, 0, s>>>(a);      // level top, before S6, before S9
+    else if (bars == 3) k_column_step<16, 1, 3, false><<<g16, 512, 0, s>>>(a);
+    else k_column_step<16, 1, 1, false><<<g16, 512, 0, s>>>(a);
+  } else if (warps >= 12) k_column_step<12, 1, 63, false><<<(unsigned)((ngroups + 11) / 12), 384, 0, s>>>(a);
   else if (warps == 9) {                                                         // two 8-warp blocks per SM
-    if (bars == 63) k_column_step<8, 2, 63><<<g8, 256, 0, s>>>(a);
-    else if (bars == 11) k_column_step<8, 2, 11><<<g8, 256, 0, s>>>(a);
-    else k_column_step<8, 2, 1><<<g8, 256, 0, s>>>(a);
-  } else if (warps >= 8) k_column_step<8, 1, 63><<<g8, 256, 0, s>>>(a);
-  else k_column_step<1, 12, 0><<<(unsigned)ngroups, 32, 0, s>>>(a);
+    if (bars == 63) k_column_step<8, 2, 63, false><<<g8, 256, 0, s>>>(a);
+    else if (bars == 11) k_column_step<8, 2, 11, false><<<g8, 256, 0, s>>>(a);
+    else k_column_step<8, 2, 1, false><<<g8, 256, 0, s>>>(a);
+  } else if (warps >= 8) k_column_step<8, 1, 63, false><<<g8, 256, 0, s>>>(a);
+  else k_column_step<1, 12, 0, false><<<(unsigned)ngroups, 32, 0, s>>>(a);
   k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
   k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)ngroups, h->d_diag);
   h->launches += 4;

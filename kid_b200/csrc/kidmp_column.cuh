@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
 // so they run the same ~120 KB of straight-line code at the same time and share its instruction-cache
 // lines (profiles/r01: with independent warps the GPC instruction cache sat at 98 % of its request
 // peak and `no_instruction` was 8 of 13 stall cycles per issue).
-template <int WARPS, int MINB, int BARS>
+template <int WARPS, int MINB, int BARS, bool RATES>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
   const int count = *a.work_count;                     // cloudy columns, compacted: every warp but the last is full
   const int first = blockIdx.x * WARPS * 32;
@@ -242,6 +242,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         double ilamg = 0., N0_g = 0., ilamr, N0_r, lamr, lamc = 0., lami, ilami;
         int nu_c = 0;
         float xDc = 0.f;
+        // number tendencies are summed as their terms appear (M:2417, M:2453, M:2503 add them up later): the
+        // 22 individual number rates need not stay in registers until S8
+        double nc_acc = 0., ni_acc = 0., nr_acc = 0.;
 
         // ---- S1, M:1387-1493 -------------------------------------------------------------------
         float temp = t1d;
@@ -344,6 +347,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         if (L_qr && mvd_r > D0r) {
           const float Ef_rr = 1.0f - exp_f(2300.0f * (mvd_r - 1950.0E-6f));
           pnr_rcr = (double)(Ef_rr * 2.0f * nr * rr);
+          nr_acc -= pnr_rcr;
         }
         mvd_c = D0c;
         if (L_qc) {
@@ -363,6 +367,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           prr_wau = fmin((double)(rc * odts), prr_wau);
           pnr_wau = prr_wau / (double)(ck.am_r * (float)nu_c * D0r * D0r * D0r);
           pnc_wau = fmin((double)(nc * odts), prr_wau / (double)(ck.am_r * mvd_c * mvd_c * mvd_c));
+          nr_acc += pnr_wau; nc_acc -= pnc_wau;
         }
         if (L_qr && mvd_r > D0r && mvd_c > D0c) {
           lamr = (double)1.f / ilamr;
@@ -376,6 +381,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           prr_rcw = fmin((double)(rc * odts), prr_rcw);
           pnc_rcw = (double)(rhof * ck.t1_qr_qc * Ef_rw * nc) * N0_r * lf4;
           pnc_rcw = fmin((double)(nc * odts), pnc_rcw);
+          nc_acc -= pnc_rcw;
         }
 
         LOCKBAR(1);
@@ -435,6 +441,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
               prs_scw = (double)(rhof * ck.t1_qs_qc * Ef_sw * rc * smoe);
               pnc_scw = (double)(rhof * ck.t1_qs_qc * Ef_sw * nc * smoe);
               pnc_scw = fmin((double)(nc * odts), pnc_scw);
+              nc_acc -= pnc_scw;
             }
             if (rg >= ck.r_g1 && mvd_c > D0c) {
               const float xDg = (float)((double)(3.f + 0.f + 1.f) * ilamg);
@@ -449,6 +456,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
                 prg_gcw = (double)(rhof * ck.t1_qg_qc * Ef_gw * rc) * N0_g * il9;
                 pnc_gcw = (double)(rhof * ck.t1_qg_qc * Ef_gw * nc) * N0_g * il9;
                 pnc_gcw = fmin((double)(nc * odts), pnc_gcw);
+                nc_acc -= pnc_gcw;
               }
             }
           }
@@ -474,6 +482,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
                 pnr_rcs = rec[S_TNR_RACS2] + rec[S_TNR_SACR2];
               }
               pnr_rcs = fmin((double)(nr * odts), pnr_rcs);
+              nr_acc -= pnr_rcs;
             }
             if (rg >= ck.r_g1) {
               const double* rec = ck.racg + ((size_t)(idx_g1 - 1) + (size_t)NTB_G1 * ((idx_g - 1) + (size_t)NTB_G * ((idx_r1 - 1) + (size_t)NTB_R1 * (idx_r - 1)))) * G_N;
@@ -483,11 +492,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
                 prr_rcg = -prg_rcg;
                 pnr_rcg = rec[G_TNR_RACG] + rec[G_TNR_GACR];
                 pnr_rcg = fmin((double)(nr * odts), pnr_rcg);
+                nr_acc -= pnr_rcg;
               } else {
                 prr_rcg = rec[G_TCG_RACG];
                 prr_rcg = fmin((double)(rg * odts), prr_rcg);
                 prg_rcg = -prr_rcg;
                 pnr_rcg = (double)-5.f * rec[G_TNR_GACR];
+                nr_acc -= pnr_rcg;
               }
             }
           }
@@ -503,10 +514,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
               pni_rfz = rec[F_TNI] * (double)odts;
               pnr_rfz = rec[F_TNR] * (double)odts;
               pnr_rfz = fmin((double)(nr * odts), pnr_rfz);
+              nr_acc -= pnr_rfz; ni_acc += pni_rfz;
             } else if (rr > R1 && temp < KP_HGFR) {
               pri_rfz = (double)(rr * odts);
               pnr_rfz = (double)(nr * odts);
               pni_rfz = pnr_rfz;
+              nr_acc -= pnr_rfz; ni_acc += pni_rfz;
             }
             if (rc > ck.r_c1) {
               const double* rec = ck.qcfz + ((size_t)(idx_c - 1) + (size_t)NTB_C * (idx_tc - 1)) * C_N;
@@ -514,9 +527,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
               pri_wfz = fmin((double)(rc * odts), pri_wfz);
               pni_wfz = rec[C_TNI] * (double)odts;
               pni_wfz = fmin(fmin((double)(Nt_c * odts), pri_wfz / (double)(2.f * KP_XM0I)), pni_wfz);
+              ni_acc += pni_wfz; nc_acc -= pni_wfz;
             } else if (rc > R1 && temp < KP_HGFR) {
               pri_wfz = (double)(rc * odts);
               pni_wfz = (double)(nc * odts);
+              ni_acc += pni_wfz; nc_acc -= pni_wfz;
             }
             // M:2090-2101 Cooper nucleation
             if ((ssati >= 0.25f) || (ssatw > EPSF && temp < 253.15f)) {
@@ -525,6 +540,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
               pni_inu = (double)(0.5f * (xnc - xni + fabsf(xnc - xni)) * odts);
               pri_inu = fmin((double)rate_max, (double)KP_XM0I * pni_inu);
               pni_inu = pri_inu / (double)KP_XM0I;
+              ni_acc += pni_inu;
             }
             // M:2116-2149 deposition / sublimation of cloud ice, ice -> snow
             float oxmi = 0.f, xDi = 0.f;
@@ -556,6 +572,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
                 pni_iau = rec[I_TNI] * (double)odts;
                 pni_iau = fmin((double)(ni * .95f * odts), pni_iau);
               }
+              ni_acc -= pni_iau;
             }
             // M:2153-2175 deposition / sublimation of snow, sublimation of graupel
             if (L_qs) {
@@ -578,6 +595,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
               if (rs >= ck.r_s1) {
                 prs_sci = (double)(ck.t1_qs_qi * rhof * KP_EF_SI * ri * smoe);
                 pni_sci = prs_sci * (double)oxmi;
+                ni_acc -= pni_sci;
               }
               if (rr >= ck.r_r1 && mvd_r > 4.f * xDi) {
                 lamr = (double)1.f / ilamr;
@@ -586,6 +604,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
                 pri_rci = (double)(rhof * ck.t1_qr_qi * KP_EF_RI * ri) * N0_r * lf4;
                 pnr_rci = (double)(rhof * ck.t1_qr_qi * KP_EF_RI * ni) * N0_r * lf4;
                 pni_rci = pri_rci * (double)oxmi;
+                nr_acc -= pnr_rci; ni_acc -= pni_rci;
                 prr_rci = (double)(rhof * ck.t2_qr_qi * KP_EF_RI * ni) * N0_r * lf7;       // cre(8) = 7
                 prr_rci = fmin((double)(rr * odts), prr_rci);
                 prg_rci = pri_rci + prr_rci;
@@ -598,6 +617,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
               else if (tempc > -8.0f && tempc < -5.0f) tf = 0.33333333f * (8.0f + tempc);
               pni_ihm = (double)(3.5E8f * tf) * prg_gcw;
               pri_ihm = (double)KP_XM0I * pni_ihm;
+              ni_acc += pni_ihm;
               prs_ihm = prs_scw / (prs_scw + prg_gcw) * pri_ihm;
               prg_ihm = prg_gcw / (prs_scw + prg_gcw) * pri_ihm;
             }
@@ -618,6 +638,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
               prr_sml = fmin((double)(rs * odts), fmax(0., prr_sml));
               pnr_sml = (double)(smo0 / rs) * prr_sml * (double)pow10_f(-0.25f * tempc);
               pnr_sml = fmin((double)(smo0 * odts), pnr_sml);
+              nr_acc += pnr_sml;
               if (ssati < 0.f) {
                 prs_sde = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs
                                    * (ck.t1_qs_sd * smo1 + ck.t2_qs_sd * rhof2 * vsc2 * smof));
@@ -630,6 +651,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
                         * ((double)ck.t1_qg_me * il10 + (double)(ck.t2_qg_me * rhof2 * vsc2) * il11);
               prr_gml = fmin((double)(rg * odts), fmax(0., prr_gml));
               pnr_gml = N0_g * (double)ck.cgg[1] * ilamg / (double)rg * prr_gml * (double)pow10_f(-0.5f * tempc);
+              nr_acc += pnr_gml;
               if (ssati < 0.f) {
                 prg_gde = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs) * N0_g
                           * ((double)ck.t1_qg_sd * il10 + (double)(ck.t2_qg_sd * vsc2 * rhof2) * il11);
@@ -700,7 +722,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           const float lfus2 = KP_LSUB - lvap;
           qvt = (float)((-pri_inu - pri_ide - prs_ide - prs_sde - prg_gde) * (double)orho);
           qct = (float)((-prr_wau - pri_wfz - prr_rcw - prs_scw - prg_scw - prg_gcw) * (double)orho);
-          nct = (float)((-pnc_wau - pnc_rcw - pni_wfz - pnc_scw - pnc_gcw) * (double)orho);
+          nct = (float)(nc_acc * (double)orho);
           float xrc = fmaxf(R1, (qc1d + qct * DT) * rho);
           float xnc = fmaxf(2.f, (nc1d + nct * DT) * rho);
           if (xrc > R1) {
@@ -723,7 +745,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           if (xnc > KP_NT_C_MAX) nct = (KP_NT_C_MAX - nc1d * rho) * odts * orho;
 
           qit = (float)((pri_inu + pri_ihm + pri_wfz + pri_rfz + pri_ide - prs_iau - prs_sci - pri_rci) * (double)orho);
-          nit = (float)((pni_inu + pni_ihm + pni_wfz + pni_rfz + pni_ide - pni_iau - pni_sci - pni_rci) * (double)orho);
+          nit = (float)((ni_acc + pni_ide) * (double)orho);
           const float xri = fmaxf(R1, (qi1d + qit * DT) * rho);
           float xni = fmaxf(R2, (ni1d + nit * DT) * rho);
           if (xri > R1) {
@@ -746,7 +768,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           if (xni > 499.E3f) nit = (499.E3f - ni1d * rho) * odts * orho;
 
           qrt = (float)((prr_wau + prr_rcw + prr_sml + prr_gml + prr_rcs + prr_rcg - prg_rfz - pri_rfz - prr_rci) * (double)orho);
-          nrt = (float)((pnr_wau + pnr_sml + pnr_gml - (pnr_rfz + pnr_rcr + pnr_rcg + pnr_rcs + pnr_rci)) * (double)orho);
+          nrt = (float)(nr_acc * (double)orho);
           const float xrr = fmaxf(R1, (qr1d + qrt * DT) * rho);
           float xnr = fmaxf(R2, (nr1d + nrt * DT) * rho);
           if (xrr > R1) {
@@ -924,7 +946,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         }
 
         // M:2963-3120 the 36 process rates KiD saves with save_dg (optional buffer [36][nz][ncol])
-        if (a.rates && active) {
+        if (RATES && a.rates && active) {
           float* rp = a.rates + o + col;
           const long st = (long)nz * ncol;
           const double rv[KIDMP_NRATES] = {pri_inu, pri_ide, prs_ide, prs_sde, prg_gde, pri_wfz, prs_scw, prg_scw, prg_gcw, pri_ihm,
