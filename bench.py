@@ -32,9 +32,9 @@ UNIT = "column-steps/s"
 ALG_BYTES_PER_COLUMN = 4576          # 10 fields read + 9 written + 4 precip scalars, nz=60
 NZ = 60
 DT = 10.0
-# dram__bytes_read.sum + dram__bytes_write.sum of the three step kernels from the ncu --set full capture of the same
-# workload (profiles/r01_ncu_step_kernels.md): 2.52+0.01 (classify) + 1.24+1.97 (physics) + 3.28+0.72 (sedimentation) GB
-TRAFFIC_BYTES_PER_LAUNCH = 9.74e9
+# dram__bytes_read.sum + dram__bytes_write.sum of the three step kernels from the ncu --set full captures of the same
+# workload (profiles/r01_ncu_step_kernels.md): 2.52+0.01 (classify) + 1.28+3.09 (physics) + 3.28+0.72 (sedimentation) GB
+TRAFFIC_BYTES_PER_LAUNCH = 10.9e9
 
 
 def peaks():
@@ -270,7 +270,8 @@ def main():
                        "active_column_fraction": float(diag[6].item() / max(diag[7].item(), 1.0))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                         "kernel": "k_classify + k_column_step<16,1> + k_sediment (one step; k_column_step is 82 % of it)",
+                         "kernel": "one step = k_classify + k_column_step<24,1,11> + k_sediment + k_diag_reduce (k_column_step is 77 % of it); "
+                                   "achieved and traffic are for the whole step, the unit the algorithmic bytes are defined on",
                          "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_COLUMN * ncol},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "diag": {"names": ["ppt_rain", "ppt_ice", "ppt_snow", "ppt_graupel", "lwp", "iwp", "active", "columns"],
