@@ -216,6 +216,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
       int nstep_r = 0, nstep_i = 0, nstep_s = 0, nstep_g = 0;
       int ksed_r = 1, ksed_i = 1, ksed_s = 1, ksed_g = 1;   // 1-based like the reference
 
+      // graupel intercept of a level without rain and graupel (xslw1 = 0.01, rg = R1 in M:1639-1646): the only
+      // thing such a level contributes to the running minimum of M:1648
+      double n0_empty;
+      {
+        const float xslw1 = 0.01f;
+        const float ygra1 = 4.31f + log10_f(fmaxf(5.E-5f, R1));
+        const float zans1 = 3.1f + (100.f / (300.f * xslw1 * ygra1 / (10.f / xslw1 + 1.f + 0.25f * ygra1) + 30.f + 10.f * ygra1));
+        n0_empty = fmax((double)KP_GONV_MIN, fmin((double)pow10_f(zans1), (double)KP_GONV_MAX));
+      }
+
       // ================= pass 1: top-down, S1..S13 per level ====================================
 #pragma unroll 1
       for (int k = nz - 1; k >= 0; --k) {
@@ -228,6 +238,61 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         const float dzq = a.dz[k];
         // U1: nc1d as the WRF driver sets it when the scheme is not aerosol aware, M:957-964
         float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));
+
+        // ---- empty level: no hydrometeor in any of the warp's columns and none at or above ice saturation.
+        // Every process rate is then exactly zero (each is gated by a species flag or by ssati / ssatw,
+        // M:1676-2286, M:2780, M:2880) and the state at tau+1 equals the input, so only the vertical carries
+        // (graupel N0 minimum, k_0, fall speeds from above, substep counts) and the hand-off need doing.
+        if (!__any_sync(0xffffffffu, qc1d > R1 || qi1d > R1 || qr1d > R1 || qs1d > R1 || qg1d > R1)) {
+          const float temp = t1d;
+          const float qv = fmaxf(1.E-10f, qv1d);
+          const float rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+          const float tempc = temp - 273.15f;
+          const float qvs = rslf(pres, temp);
+          const float qvsi = (tempc <= 0.0f) ? rsif(pres, temp) : qvs;
+          float ssatw = qv / qvs - 1.f;
+          float ssati = qv / qvsi - 1.f;
+          if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
+          if (fabsf(ssati) < EPSF) ssati = 0.0f;
+          if (__all_sync(0xffffffffu, !(ssati > 0.0f) && !(ssatw > EPSF))) {
+            if (!iiwarm) {
+              if (temp >= 270.65f) { warm_above_a = true; warm_above_b = true; }
+              N0_min_a = fmin(n0_empty, N0_min_a);
+              N0_min_b = fmin(n0_empty, N0_min_b);
+            }
+            const float v_r = vtr_up, v_nr = vtnr_up, v_i = vti_up, v_ni = vtni_up, v_s = vts_up, v_g = vtg_up;
+            if (fmaxf(v_r, v_nr) > 1.E-3f) {
+              ksed_r = max(ksed_r, k + 1);
+              const float delta_tp = dzq / (fmaxf(v_r, v_nr));
+              nstep_r = max(nstep_r, (int)(DT / delta_tp + 1.f));
+            }
+            if (!iiwarm) {
+              if (v_i > 1.E-3f) { ksed_i = max(ksed_i, k + 1); const float d = dzq / v_i; nstep_i = max(nstep_i, (int)(DT / d + 1.f)); }
+              if (v_s > 1.E-3f) { ksed_s = max(ksed_s, k + 1); const float d = dzq / v_s; nstep_s = max(nstep_s, (int)(DT / d + 1.f)); }
+              if (v_g > 1.E-3f) { ksed_g = max(ksed_g, k + 1); const float d = dzq / v_g; nstep_g = max(nstep_g, (int)(DT / d + 1.f)); }
+            }
+            if (active) {
+              const float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+              const float lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+              float s15 = 0.0f;
+              if (temp > T_0) s15 = ck.lfus * ocp;
+              else if (temp < KP_HGFR) s15 = -((KP_LSUB - lvap) * ocp);
+              float* sc = a.scratch + o + col;
+              const long ss = (long)nz * ncol;
+#pragma unroll
+              for (int q = SC_TTEN; q <= SC_NCTEN; ++q) sc[q * ss] = 0.0f;
+              sc[SC_RR * ss] = R1; sc[SC_NR * ss] = R2; sc[SC_RI * ss] = R1; sc[SC_NI * ss] = R2; sc[SC_RS * ss] = R1; sc[SC_RG * ss] = R1;
+              sc[SC_VTR * ss] = v_r; sc[SC_VTNR * ss] = v_nr; sc[SC_VTI * ss] = v_i; sc[SC_VTNI * ss] = v_ni;
+              sc[SC_VTS * ss] = v_s; sc[SC_VTG * ss] = v_g; sc[SC_RHO * ss] = rho; sc[SC_S15 * ss] = s15;
+              if (RATES && a.rates) {
+                float* rp = a.rates + o + col;
+                for (int q = 0; q < KIDMP_NRATES; ++q) rp[q * ss] = 0.0f;
+              }
+            }
+            LOCKBAR(1); LOCKBAR(2); LOCKBAR(3); LOCKBAR(4); LOCKBAR(5);   // keep the block's barrier count in step
+            continue;
+          }
+        }
 
         // rates, M:1184-1211 (zeroed M:1282-1363)
         double prw_vcd = 0., pnc_wcd = 0., pnc_wau = 0., pnc_rcw = 0., pnc_scw = 0., pnc_gcw = 0.;
