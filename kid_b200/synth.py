@@ -79,7 +79,7 @@ def _bump(z, lo, hi):
 
 
 def make_domain(ncol, nz=60, col0=0, nx=None, device="cpu", seed=SEED, dz=250.0, cloudy_fraction=0.30,
-                coherent=True):
+                coherent=True, structure_block=1):
     """Columns [col0, col0+ncol) of a domain whose rows are nx columns wide (default 1024, or ncol
     when smaller).  Returns (state dict of (nz, ncol) float32 tensors, p (nz, ncol), dz (nz,))."""
     dev = torch.device(device)
@@ -90,7 +90,9 @@ def make_domain(ncol, nz=60, col0=0, nx=None, device="cpu", seed=SEED, dz=250.0,
     ny = max(1024, 1)
     z1, T1, p1 = sounding(nz, dz)
     z = z1.to(dev, torch.float32).unsqueeze(1)
-    U = lambda s: hash_uniform(ids, s, seed).unsqueeze(0)          # (1, ncol)
+    # structure_block > 1 (experiments only): runs of that many neighbouring columns share their random numbers
+    hid = ids if structure_block <= 1 else (ids // structure_block) * structure_block
+    U = lambda s: hash_uniform(hid, s, seed).unsqueeze(0)          # (1, ncol)
     if coherent:
         sel = _smooth_field(ix, iy, nx, ny, 1, seed=seed)
         typ = _smooth_field(ix, iy, nx, ny, 2, seed=seed)

@@ -15,9 +15,10 @@ ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--col0", type=int, default=0)
 ap.add_argument("--dt", type=float, default=10.0)
 ap.add_argument("--cloudy", type=float, default=0.30)
+ap.add_argument("--structure-block", type=int, default=1)
 a = ap.parse_args()
 th = Thompson(set_Nc=100.0, iiwarm=False, l_sediment=True)
-st, p, dz = synth.make_domain(a.columns, nz=60, col0=a.col0, nx=1024, device="cuda", cloudy_fraction=a.cloudy)
+st, p, dz = synth.make_domain(a.columns, nz=60, col0=a.col0, nx=1024, device="cuda", cloudy_fraction=a.cloudy, structure_block=a.structure_block)
 ppt = torch.zeros((4, a.columns), dtype=torch.float32, device="cuda")
 s = torch.cuda.Stream()
 torch.cuda.synchronize()
