@@ -41,6 +41,7 @@ struct kidmp_handle {
   double* d_partial = nullptr; long partial_blocks = 0;
   float* d_scratch = nullptr; size_t scratch_cells = 0;   // [SC_N][nz][ncol] hand-off between the two step kernels
   int* d_colint = nullptr; long scratch_cols = 0;
+  double* d_coldiag = nullptr;                            // [2][ncol] per-column water paths for the ordered domain sums
   int* d_work = nullptr;                                  // [count | list | mask] of cloudy 32-column groups
   double* d_diag = nullptr;
   float* d_rates = nullptr;
@@ -219,27 +220,25 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   const int sthreads = 128;
   const long sblocks = (a.ncol + sthreads - 1) / sthreads;
   const long ngroups = (a.ncol + 31) / 32;
-  if (ngroups > h->partial_blocks) {
-    if (h->d_partial) cudaFree(h->d_partial);
-    h->d_partial = nullptr; h->partial_blocks = 0;
-    CK(h, cudaMalloc((void**)&h->d_partial, (size_t)ngroups * KIDMP_NDIAG * 8));
-    h->partial_blocks = ngroups;
-  }
+  if (!h->d_partial) CK(h, cudaMalloc((void**)&h->d_partial, (size_t)DIAG_BLOCKS * KIDMP_NDIAG * 8));
   const size_t need = (size_t)a.ncol * a.nz;
   if (need > h->scratch_cells || a.ncol > h->scratch_cols) {
     if (h->d_scratch) cudaFree(h->d_scratch);
     if (h->d_colint) cudaFree(h->d_colint);
     if (h->d_work) cudaFree(h->d_work);
-    h->d_scratch = nullptr; h->d_colint = nullptr; h->d_work = nullptr; h->scratch_cells = 0; h->scratch_cols = 0;
+    if (h->d_coldiag) cudaFree(h->d_coldiag);
+    h->d_scratch = nullptr; h->d_colint = nullptr; h->d_work = nullptr; h->d_coldiag = nullptr; h->scratch_cells = 0; h->scratch_cols = 0;
     CK(h, cudaMalloc((void**)&h->d_scratch, need * SC_N * 4));
     CK(h, cudaMalloc((void**)&h->d_colint, (size_t)a.ncol * 8 * 4));
     CK(h, cudaMalloc((void**)&h->d_work, (size_t)(a.ncol + 8) * 4));
+    CK(h, cudaMalloc((void**)&h->d_coldiag, (size_t)a.ncol * 2 * 8));
     h->scratch_cells = need; h->scratch_cols = a.ncol;
   }
   a.scratch = h->d_scratch;
   a.colint = h->d_colint;
   a.work_count = h->d_work;
   a.work_list = h->d_work + 8;
+  a.coldiag = h->d_coldiag;
   a.diag_partial = h->d_partial;
   a.rates = h->d_rates;
   CK(h, cudaMemsetAsync(h->d_work, 0, 4, s));
@@ -250,7 +249,14 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   if (a.rates) k_column_step<16, 1, 11, true><<<(unsigned)((ngroups + 15) / 16), 512, 0, s>>>(a);   // with the 36 save_dg rates
   else if (warps >= 32) k_column_step<32, 1, 11, false><<<(unsigned)((ngroups + 31) / 32), 1024, 0, s>>>(a);
   else if (warps >= 28) k_column_step<28, 1, 11, false><<<(unsigned)((ngroups + 27) / 28), 896, 0, s>>>(a);
-  else if (warps >= 24) k_column_step<24, 1, 11, false><<<(unsigned)((ngroups + 23) / 24), 768, 0, s>>>(a);
+  else if (warps >= 24) {
+    const unsigned g24 = (unsigned)((ngroups + 23) / 24);
+    if (bars == 63) k_column_step<24, 1, 63, false><<<g24, 768, 0, s>>>(a);
+    else if (bars == 3) k_column_step<24, 1, 3, false><<<g24, 768, 0, s>>>(a);
+    else if (bars == 1) k_column_step<24, 1, 1, false><<<g24, 768, 0, s>>>(a);
+    else if (bars == 9) k_column_step<24, 1, 9, false><<<g24, 768, 0, s>>>(a);
+    else k_column_step<24, 1, 11, false><<<g24, 768, 0, s>>>(a);
+  }
   else if (warps >= 20) k_column_step<20, 1, 11, false><<<(unsigned)((ngroups + 19) / 20), 640, 0, s>>>(a);
   else if (warps >= 16) {
     if (bars == 63) k_column_step<16, 1, 63, false><<<g16, 512, 0, s>>>(a);
@@ -265,8 +271,9 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   } else if (warps >= 8) k_column_step<8, 1, 63, false><<<g8, 256, 0, s>>>(a);
   else k_column_step<1, 12, 0, false><<<(unsigned)ngroups, 32, 0, s>>>(a);
   k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
-  k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)ngroups, h->d_diag);
-  h->launches += 4;
+  k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
+  k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
+  h->launches += 5;
   CK(h, cudaGetLastError());
   return 0;
 }
@@ -399,6 +406,7 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_scratch) cudaFree(h->d_scratch);
   if (h->d_colint) cudaFree(h->d_colint);
   if (h->d_work) cudaFree(h->d_work);
+  if (h->d_coldiag) cudaFree(h->d_coldiag);
   if (h->d_pipe) cudaFree(h->d_pipe);
   if (h->d_pipe_dz) cudaFree(h->d_pipe_dz);
   if (h->h_ppt) cudaFreeHost(h->h_ppt);

@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
       if (ssati > 0.0f) no_micro = false;
     }
     active = !no_micro;
-    if (!active) a.colint[col] = -1;               // clear-sky column: nothing left to do
+    if (!active) {                                 // clear-sky column: nothing left to do
+      a.colint[col] = -1;
+      a.ppt[col] = 0.f; a.ppt[ncol + col] = 0.f; a.ppt[2 * ncol + col] = 0.f; a.ppt[3 * ncol + col] = 0.f;   // I:55-58
+    }
   }
   // append the cloudy columns of this warp to the work list (one atomic per warp, order within the warp kept)
   const unsigned mask = __ballot_sync(0xffffffffu, active);
@@ -1163,19 +1166,18 @@ __device__ __forceinline__ void sed_substeps(float* __restrict__ r, float* __res
 }
 
 __global__ void __launch_bounds__(32) k_sediment(StepArgs a) {
-  const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = col < a.ncol;
+  const int slot = blockIdx.x * 32 + threadIdx.x;          // cloudy columns only: the compacted work list
+  if (slot >= *a.work_count) return;
+  const long col = a.work_list[slot];
   const int nz = a.nz;
   const long ncol = a.ncol;
   const float DT = a.dt, odt = 1.f / DT;
   float ppt_r = 0.f, ppt_i = 0.f, ppt_s = 0.f, ppt_g = 0.f;
   double lwp = 0.0, iwp = 0.0;
-  bool active = false;
-  if (in_range) {
+  {
     const int* ci = a.colint + col;
-    int nstep_r = ci[0];
-    active = nstep_r >= 0;
-    if (active) {
+    const int nstep_r = ci[0];
+    {
       const int nstep_i = ci[ncol], nstep_s = ci[2 * ncol], nstep_g = ci[3 * ncol];
       int ksed_r = ci[4 * ncol], ksed_i = ci[5 * ncol], ksed_s = ci[6 * ncol], ksed_g = ci[7 * ncol];
       const int kte = nz;
@@ -1323,21 +1325,34 @@ __global__ void __launch_bounds__(32) k_sediment(StepArgs a) {
     }
     // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
     a.ppt[col] = ppt_r; a.ppt[ncol + col] = ppt_i; a.ppt[2 * ncol + col] = ppt_s; a.ppt[3 * ncol + col] = ppt_g;
+    a.coldiag[col] = lwp; a.coldiag[ncol + col] = iwp;      // summed in column order by k_diag_columns
   }
+}
 
-  // ---- warp partial sums for the domain diagnostics (fixed order => run-to-run identical); one warp per
-  // block, so a warp of clear-sky columns retires at once
-  if (a.diag_partial) {
-    const bool any = __any_sync(0xffffffffu, active);
-    double v[KIDMP_NDIAG] = {(double)ppt_r, (double)ppt_i, (double)ppt_s, (double)ppt_g, lwp, iwp,
-                             active ? 1.0 : 0.0, in_range ? 1.0 : 0.0};
-#pragma unroll
-    for (int q = 0; q < KIDMP_NDIAG; ++q) {
-      double x = v[q];
-      if (any || q == KIDMP_NDIAG - 1)
-        for (int s = 16; s > 0; s >>= 1) x += __shfl_down_sync(0xffffffffu, x, s);
-      if (threadIdx.x == 0) a.diag_partial[(size_t)blockIdx.x * KIDMP_NDIAG + q] = x;
+// Domain sums in COLUMN order, whatever order the work list had: bitwise reproducible run to run and across
+// different work-list orders.  Fixed grid: block b sums the columns [b*chunk, (b+1)*chunk) (thread-strided, then a
+// tree), the per-block partials are added up by k_diag_reduce.
+__global__ void __launch_bounds__(256) k_diag_columns(StepArgs a, long chunk) {
+  __shared__ double s[256];
+  const long c0 = (long)blockIdx.x * chunk, c1 = min(c0 + chunk, a.ncol);
+  const long ncol = a.ncol;
+  double v[KIDMP_NDIAG] = {0., 0., 0., 0., 0., 0., 0., 0.};
+  for (long c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+    v[7] += 1.0;
+    if (a.colint[c] < 0) continue;                          // clear sky: ppt = 0, no condensate
+    v[0] += (double)a.ppt[c]; v[1] += (double)a.ppt[ncol + c]; v[2] += (double)a.ppt[2 * ncol + c]; v[3] += (double)a.ppt[3 * ncol + c];
+    v[4] += a.coldiag[c]; v[5] += a.coldiag[ncol + c];
+    v[6] += 1.0;
+  }
+  for (int q = 0; q < KIDMP_NDIAG; ++q) {
+    s[threadIdx.x] = v[q];
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if ((int)threadIdx.x < st) s[threadIdx.x] += s[threadIdx.x + st];
+      __syncthreads();
     }
+    if (threadIdx.x == 0) a.diag_partial[(size_t)blockIdx.x * KIDMP_NDIAG + q] = s[0];
+    __syncthreads();
   }
 }
 

@@ -104,6 +104,8 @@ struct KConst {
 enum { SC_TTEN = 0, SC_QVTEN, SC_QCTEN, SC_QITEN, SC_QRTEN, SC_QSTEN, SC_QGTEN, SC_NITEN, SC_NRTEN, SC_NCTEN,
        SC_RR, SC_NR, SC_RI, SC_NI, SC_RS, SC_RG, SC_VTR, SC_VTNR, SC_VTI, SC_VTNI, SC_VTS, SC_VTG, SC_RHO, SC_S15, SC_N };
 
+enum { DIAG_BLOCKS = 296 };
+
 struct StepArgs {
   long ncol;
   int nz;
@@ -117,7 +119,8 @@ struct StepArgs {
   int* work_count;             // number of cloudy columns found by the classification kernel
   int* work_list;              // their column indices, compacted (warp-sized runs in discovery order)
   float* rates;                // optional [36][nz][ncol]
-  double* diag_partial;        // optional [gridDim.x][KIDMP_NDIAG] block sums
+  double* coldiag;             // [2][ncol] liquid / ice water path of each cloudy column
+  double* diag_partial;        // [DIAG_BLOCKS][KIDMP_NDIAG] block sums of k_diag_columns
 };
 
 // device tables (kidmp_tables.cuh fills them)
