@@ -51,6 +51,22 @@ def build(force=False, verbose=False, extra=()):
     return LIB
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_EXE = os.path.join(HOST_DIR, "kid_driver")
+
+
+def build_host(force=False):
+    """g++ build of the C++ twin of KiD's interface module and its little driver (kid_b200/host/)."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("kid_driver.cpp", "mphys_thompson09n.cpp")]
+    deps = srcs + [os.path.join(HOST_DIR, "mphys_thompson09n.hpp"), LIB]
+    if not force and os.path.exists(HOST_EXE) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_EXE) for d in deps):
+        return HOST_EXE
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", HOST_EXE, *srcs, "-L" + HERE, "-lkidmp",
+                           "-Wl,-rpath,$ORIGIN/.."])
+    return HOST_EXE
+
+
 if __name__ == "__main__":
     build(force=True, verbose="-v" in sys.argv)
+    build_host(force=True)
     print(LIB)

@@ -71,3 +71,20 @@ def test_product_does_not_reference_the_oracle():
     from kid_b200 import build
     ldd = subprocess.run(["ldd", build.LIB], capture_output=True, text=True).stdout
     assert "oracle" not in ldd
+
+
+def test_cxx_host_twin_builds_and_fails_cleanly_without_a_gpu(tmp_path):
+    """kid_b200/host: the C++ restatement of `module mphys_thompson09n` links against the C ABI; without a CUDA device the
+    no-argument interface call returns the library's error instead of crashing or falling back to a CPU path."""
+    import numpy as np
+    import torch
+    from kid_b200 import build
+    exe = build.build_host()
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    nx, nz = 2, 10
+    src = tmp_path / "in.bin"
+    np.zeros(7 * nx * nz + nz + 21 * nx * nz, np.float32).tofile(src)
+    r = subprocess.run([exe, str(src), str(tmp_path / "out.bin"), str(nx), str(nz), "1.0", "0"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU path" in r.stderr

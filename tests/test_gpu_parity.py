@@ -365,3 +365,32 @@ def test_kinematic_case_time_series(name):
             assert np.abs(acc_g[:, j] - acc_o[:, j]).max() <= 1e-3 * scale, (name, "ppt", j)
     assert ro["lwp"].max() > 0.1 and (c.iiwarm or ro["iwp"].max() > 0.01)          # the case actually rained / glaciated
     g.close(); o.close()
+
+
+def test_cxx_host_twin(gpu_mixed, tmp_path):
+    """The C++ twin of KiD's `module mphys_thompson09n` (kid_b200/host): a no-argument `mphys_thompson09_interfacen()` over
+    module-style state gives exactly what the library returns for the same columns, and reports the same save_dg records."""
+    import subprocess
+    from kid_b200 import build
+    from kid_b200.kidmp import HYD_PLANES
+    exe = build.build_host()
+    nx, nz, dt = 40, 60, 5.0
+    kid, p0, roc = _kid_case(nx, nz, seed=11)
+    order = ["theta", "dtheta_adv", "dtheta_div", "exner", "qv", "dqv_adv", "dqv_div", "dz"]
+    for m in HYD_PLANES:
+        order += [m, "d%s_adv" % m, "d%s_div" % m]
+    with open(tmp_path / "in.bin", "wb") as f:
+        for name in order:
+            np.ascontiguousarray(kid[name], np.float32).tofile(f)
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(nx), str(nz), str(dt), "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "save_dg_calls=11" in r.stdout          # nx > 1: 5 means + 5 per-column records + total_ppt_level (I:248-308)
+    out = np.fromfile(tmp_path / "out.bin", np.float32)
+    roc = float(np.float32(287.05) / np.float32(1005.0))             # the driver's physconst defaults, evaluated in f32
+    ref = gpu_mixed.kid_interface(kid, dt, 1.0e5, roc)
+    n = nx * nz
+    names = ["dtheta_mphys", "dqv_mphys"] + ["d%s_mphys" % m for m in HYD_PLANES]
+    for j, name in enumerate(names):
+        assert np.array_equal(out[j * n:(j + 1) * n].reshape(nx, nz), ref[name]), name
+    assert np.array_equal(out[9 * n:].reshape(4, nx), ref["ppt"])
