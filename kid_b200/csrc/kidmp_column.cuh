@@ -213,11 +213,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
     float* Gni = a.f[F_NI] + colc; float* Gnr = a.f[F_NR] + colc; float* Gt = a.f[F_T] + colc;
     {
       // carried from the level above
-      double N0_min_a = (double)KP_GONV_MAX, N0_min_b = (double)KP_GONV_MAX;
+      // They are touched once per level and live for the whole sweep: kept in shared memory (72 bytes per
+      // thread) instead of 20 registers that the register allocator would have to spill around the rates.
+      extern __shared__ double smem_carry[];
+      constexpr int NT = WARPS * 32;
+      double* const s_d = smem_carry;                                   // [2][NT]
+      float* const s_f = reinterpret_cast<float*>(smem_carry + 2 * NT); // [6][NT]
+      int* const s_i = reinterpret_cast<int*>(s_f + 6 * NT);            // [8][NT]
+      const int tid = threadIdx.x;
+#define N0_min_a s_d[tid]
+#define N0_min_b s_d[NT + tid]
+#define vtr_up s_f[tid]
+#define vtnr_up s_f[NT + tid]
+#define vti_up s_f[2 * NT + tid]
+#define vtni_up s_f[3 * NT + tid]
+#define vts_up s_f[4 * NT + tid]
+#define vtg_up s_f[5 * NT + tid]
+#define nstep_r s_i[tid]
+#define nstep_i s_i[NT + tid]
+#define nstep_s s_i[2 * NT + tid]
+#define nstep_g s_i[3 * NT + tid]
+#define ksed_r s_i[4 * NT + tid]
+#define ksed_i s_i[5 * NT + tid]
+#define ksed_s s_i[6 * NT + tid]
+#define ksed_g s_i[7 * NT + tid]
+      N0_min_a = (double)KP_GONV_MAX; N0_min_b = (double)KP_GONV_MAX;
       bool warm_above_a = false, warm_above_b = false;     // any level >= k with temp >= 270.65 (k_0, M:1635)
-      float vtr_up = 0.f, vtnr_up = 0.f, vti_up = 0.f, vtni_up = 0.f, vts_up = 0.f, vtg_up = 0.f;
-      int nstep_r = 0, nstep_i = 0, nstep_s = 0, nstep_g = 0;
-      int ksed_r = 1, ksed_i = 1, ksed_s = 1, ksed_g = 1;   // 1-based like the reference
+      vtr_up = 0.f; vtnr_up = 0.f; vti_up = 0.f; vtni_up = 0.f; vts_up = 0.f; vtg_up = 0.f;
+      nstep_r = 0; nstep_i = 0; nstep_s = 0; nstep_g = 0;
+      ksed_r = 1; ksed_i = 1; ksed_s = 1; ksed_g = 1;      // 1-based like the reference
 
       // graupel intercept of a level without rain and graupel (xslw1 = 0.01, rg = R1 in M:1639-1646): the only
       // thing such a level contributes to the running minimum of M:1648
@@ -403,7 +427,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           }
           // ---- S4, M:1633-1654 graupel intercept ------------------------------------------------
           if (temp >= 270.65f) warm_above_a = true;
-          graupel_n0(!warm_above_a && k > 0, L_qr, mvd_r, rg, N0_min_a, ilamg, N0_g);
+          { double nm = N0_min_a; graupel_n0(!warm_above_a && k > 0, L_qr, mvd_r, rg, nm, ilamg, N0_g); N0_min_a = nm; }
         }
         // M:1661-1666 rain slope and intercept
         lamr = rain_lam(nr, rr);
@@ -918,7 +942,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             // smod (M:2706-2717) is not read again by any live code
           }
           if (temp >= 270.65f) warm_above_b = true;
-          graupel_n0(!warm_above_b && k > 0, L_qr, mvd_r, rg, N0_min_b, ilamg, N0_g);
+          { double nm = N0_min_b; graupel_n0(!warm_above_b && k > 0, L_qr, mvd_r, rg, nm, ilamg, N0_g); N0_min_b = nm; }
         }
         lamr = rain_lam(nr, rr);
         ilamr = (double)1.f / lamr;
@@ -1126,6 +1150,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
 }
 
 #undef LOCKBAR
+#undef N0_min_a
+#undef N0_min_b
+#undef vtr_up
+#undef vtnr_up
+#undef vti_up
+#undef vtni_up
+#undef vts_up
+#undef vtg_up
+#undef nstep_r
+#undef nstep_i
+#undef nstep_s
+#undef nstep_g
+#undef ksed_r
+#undef ksed_i
+#undef ksed_s
+#undef ksed_g
 
 // ---- K2: sub-stepped upwind sedimentation (M:3365-3578), instant melt / freeze (M:3584-3606), apply
 // tendencies and final clamps (M:3623-3686).  One thread per column, light on registers, so many
