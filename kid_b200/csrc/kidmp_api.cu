@@ -244,12 +244,12 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   CK(h, cudaMemsetAsync(h->d_work, 0, 4, s));
   k_classify<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
   // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
-  // dynamic shared memory of the physics kernel: 72 bytes of vertical carries per thread (above 48 KB needs the opt-in)
+  // dynamic shared memory of the physics kernel: 116 bytes per thread (vertical carries, parked inputs) (above 48 KB needs the opt-in)
 #define LAUNCH_K1(KERNEL, GRID, THREADS)                                                                          \
   do {                                                                                                            \
     static bool attr_set = false;                                                                                 \
-    if (!attr_set) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (THREADS) * 72); attr_set = true; } \
-    KERNEL<<<(GRID), (THREADS), (THREADS) * 72, s>>>(a);                                                          \
+    if (!attr_set) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (THREADS) * 116); attr_set = true; } \
+    KERNEL<<<(GRID), (THREADS), (THREADS) * 116, s>>>(a);                                                          \
   } while (0)
   static const int bars = getenv("KIDMP_BARS") ? atoi(getenv("KIDMP_BARS")) : 11;
   const unsigned g16 = (unsigned)((ngroups + 15) / 16), g8 = (unsigned)((ngroups + 7) / 8);

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
       double* const s_d = smem_carry;                                   // [2][NT]
       float* const s_f = reinterpret_cast<float*>(smem_carry + 2 * NT); // [6][NT]
       int* const s_i = reinterpret_cast<int*>(s_f + 6 * NT);            // [8][NT]
+      float* const s_in = reinterpret_cast<float*>(s_i + 8 * NT);       // [11][NT] this level's inputs, parked over S3..S7
       const int tid = threadIdx.x;
 #define N0_min_a s_d[tid]
 #define N0_min_b s_d[NT + tid]
@@ -386,6 +387,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         }
         if (qs1d > R1) { rs = qs1d * rho; L_qs = true; } else { qs1d = 0.0f; rs = R1; L_qs = false; }
         if (qg1d > R1) { rg = qg1d * rho; L_qg = true; } else { qg1d = 0.0f; rg = R1; L_qg = false; }
+
+        // the inputs are not needed again before S8: parked in shared memory while the rates fill the registers
+        s_in[tid] = t1d; s_in[NT + tid] = qv1d; s_in[2 * NT + tid] = qc1d; s_in[3 * NT + tid] = qi1d; s_in[4 * NT + tid] = qr1d;
+        s_in[5 * NT + tid] = qs1d; s_in[6 * NT + tid] = qg1d; s_in[7 * NT + tid] = ni1d; s_in[8 * NT + tid] = nr1d;
+        s_in[9 * NT + tid] = nc1d; s_in[10 * NT + tid] = dzq;
 
         // ---- S2, M:1503-1533 -------------------------------------------------------------------
         float tempc = temp - 273.15f;
@@ -807,6 +813,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           }
         }
 
+        {   // inputs back from shared memory (these names shadow the ones loaded at the top of the level)
+        const float t1d = s_in[tid], qv1d = s_in[NT + tid], qc1d = s_in[2 * NT + tid], qi1d = s_in[3 * NT + tid],
+                    qr1d = s_in[4 * NT + tid], qs1d = s_in[5 * NT + tid], qg1d = s_in[6 * NT + tid], ni1d = s_in[7 * NT + tid],
+                    nr1d = s_in[8 * NT + tid], nc1d = s_in[9 * NT + tid], dzq = s_in[10 * NT + tid];
         // ---- S8, M:2393-2569 tendencies and number/mass balances ------------------------------------
         float tt, qvt, qct, qit, qrt, qst, qgt, nit, nrt, nct;
         {
@@ -1136,6 +1146,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           sc[SC_VTR * ss] = v_r; sc[SC_VTNR * ss] = v_nr; sc[SC_VTI * ss] = v_i; sc[SC_VTNI * ss] = v_ni;
           sc[SC_VTS * ss] = v_s; sc[SC_VTG * ss] = v_g; sc[SC_RHO * ss] = rho; sc[SC_S15 * ss] = s15;
         }
+        }   // shadowed inputs
         }
       }
 
