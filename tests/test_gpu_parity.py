@@ -394,3 +394,25 @@ def test_cxx_host_twin(gpu_mixed, tmp_path):
     for j, name in enumerate(names):
         assert np.array_equal(out[j * n:(j + 1) * n].reshape(nx, nz), ref[name]), name
     assert np.array_equal(out[9 * n:].reshape(4, nx), ref["ppt"])
+
+
+def test_negative_and_tiny_inputs_follow_the_reference_clamps(gpu_mixed, oracle_mixed):
+    """No error path exists in the reference: negative or tiny hydrometeor values are clamped / zeroed exactly like
+    M:1387-1493 does (species <= R1 zeroed with their numbers, qv floored at 1e-10), never rejected."""
+    st, p, dz = _domain(2048, cloudy_fraction=1.0, coherent=False)
+    rng = np.random.default_rng(3)
+    for k in ("qc", "qi", "qr", "qs", "qg", "ni", "nr"):
+        m = rng.random(st[k].shape) < 0.05
+        st[k][m] = -np.abs(st[k][m]) - np.float32(1e-9)
+        m = rng.random(st[k].shape) < 0.05
+        st[k][m] = np.float32(3e-13)
+    m = rng.random(st["qv"].shape) < 0.01
+    st["qv"][m] = np.float32(-1e-6)
+    st["nr"][rng.random(st["nr"].shape) < 0.05] = 0.0            # rain mass without a number: M:1447-1451 rebuilds it
+    st["ni"][rng.random(st["ni"].shape) < 0.05] = 0.0
+    a, pa, b, pb = _both(gpu_mixed, oracle_mixed, 10.0, st, p, dz)
+    assert_parity(a, b, what="clamped inputs")
+    np.testing.assert_allclose(pa, pb, rtol=1e-5, atol=1e-10)
+    for k in ("qc", "qi", "qr", "qs", "qg", "ni", "nr"):
+        assert a[k].min() >= 0.0, k
+    assert a["qv"].min() >= 1e-10
