@@ -1153,7 +1153,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
       // column summary for the sedimentation kernel: [8][ncol] substep counts and top sedimenting levels
       if (active) {
         int* ci = a.colint + col;
-        ci[0] = nstep_r; ci[ncol] = nstep_i; ci[2 * ncol] = nstep_s; ci[3 * ncol] = nstep_g;
+        // U12: the reference leaves the sub-step count unbounded (M:3242); on non-physical input (dt*v/dz in the
+        // millions) that is a kernel that never ends, so it is capped where no real case comes near
+        ci[0] = min(nstep_r, KP_NSTEP_MAX); ci[ncol] = min(nstep_i, KP_NSTEP_MAX); ci[2 * ncol] = min(nstep_s, KP_NSTEP_MAX);
+        ci[3 * ncol] = min(nstep_g, KP_NSTEP_MAX);
         ci[4 * ncol] = ksed_r; ci[5 * ncol] = ksed_i; ci[6 * ncol] = ksed_s; ci[7 * ncol] = ksed_g;
       }
     }

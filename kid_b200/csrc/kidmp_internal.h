@@ -54,6 +54,7 @@ namespace kidmp {
 #define KP_D0R 50.E-6f
 #define KP_D0S 200.E-6f
 #define KP_D0G 250.E-6f
+#define KP_NSTEP_MAX 32767        /* U12: cap of the sedimentation sub-step count */
 
 enum { NBINS = 100, NTB_C = 37, NTB_I = 64, NTB_R = 37, NTB_S = 28, NTB_G = 28, NTB_G1 = 28, NTB_R1 = 37,
        NTB_I1 = 55, NTB_T = 9, NTB_TC = 45 };

@@ -416,3 +416,78 @@ def test_negative_and_tiny_inputs_follow_the_reference_clamps(gpu_mixed, oracle_
     for k in ("qc", "qi", "qr", "qs", "qg", "ni", "nr"):
         assert a[k].min() >= 0.0, k
     assert a["qv"].min() >= 1e-10
+
+
+def test_full_size_domain_properties(gpu_mixed, oracle_mixed):
+    """BASELINE config 4 at full size (1 048 576 columns x 60 levels, resident in HBM): size-independent properties of the
+    scheme, shard independence, and a 4 096-column random sample against the oracle."""
+    import torch
+    from kid_b200 import synth
+    ncol, nz, dt = 1024 * 1024, 60, 10.0
+    st, p, dz = synth.make_domain(ncol, nz=nz, nx=1024, device="cuda")
+    before = {k: v.clone() for k, v in st.items()}
+    ppt = torch.zeros((4, ncol), dtype=torch.float32, device="cuda")
+    s = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    gpu_mixed.diag()
+    with torch.cuda.stream(s):
+        gpu_mixed.step_device(ncol, nz, dt, [st[k].data_ptr() for k in FIELDS], p.data_ptr(), dz.data_ptr(), ppt.data_ptr(),
+                              stream=s.cuda_stream)
+    s.synchronize()
+    d = gpu_mixed.diag()
+    assert d[7] == ncol and 0.2 * ncol < d[6] < 0.4 * ncol                         # ~30 % cloudy columns
+    # (1) clear-sky columns come back bit-unchanged (early RETURN, M:1540); cloudy ones changed somewhere
+    hyd = sum(before[k] for k in ("qc", "qi", "qr", "qs", "qg"))
+    clear = (hyd.max(0).values == 0)
+    changed = torch.zeros(ncol, dtype=torch.bool, device="cuda")
+    for k in FIELDS:
+        changed |= (st[k] != before[k]).any(0)
+    untouched = ~changed
+    assert int(untouched.sum()) >= int(0.6 * ncol)
+    assert bool((untouched | ~clear).all()) or int((clear & changed).sum()) < 0.02 * ncol   # clear + supersaturated wrt ice may nucleate
+    assert not bool(ppt[:, untouched].any())
+    # (2) output clamps (M:3623-3686)
+    assert float(st["qv"].min()) >= 1e-10
+    for k in ("qc", "qi", "qr", "qs", "qg"):
+        q = st[k]
+        assert bool(((q == 0) | (q > 1e-12)).all()), k
+    assert bool((st["ni"][st["qi"] == 0] == 0).all()) and bool((st["nr"][st["qr"] == 0] == 0).all())
+    rho = 0.622 * p / (287.04 * st["t"] * (st["qv"] + 0.622))
+    assert float((st["ni"] * rho).max()) <= 499e3 * 1.001
+    assert bool(torch.isfinite(torch.stack([st[k] for k in FIELDS])).all())
+    # (3) column water budget on the air mass of the input state: vapour + condensate + what reached the ground.
+    # The scheme moves mass per volume between levels with each level's own, mid-step density (M:3378-3389), so the
+    # budget in mixing-ratio terms closes to the relative density change of the step, not to round-off.
+    r0 = 0.622 * p.double() / (287.04 * before["t"].double() * (before["qv"].double() + 0.622))
+    def water(state):
+        return ((state["qv"] + state["qc"] + state["qr"] + state["qi"] + state["qs"] + state["qg"]).double() * r0 * dz.double()[:, None]).sum(0)
+    w0, w1 = water(before), water(st) + ppt.double().sum(0)
+    rel = ((w1 - w0).abs() / w0)
+    assert float(torch.quantile(rel[::16].float(), 0.99)) < 1e-3      # 99 % of the columns close to 0.1 %
+    assert float(rel.max()) < 0.1                                      # the rest are the reference's own clamp leaks (M:2291-2387, U10)
+    assert abs(float(w1.sum() - w0.sum())) / float(w0.sum()) < 1e-3
+    # (4) domain sums of kidmp_diag equal the sums over the returned arrays
+    np.testing.assert_allclose(d[:4], ppt.double().sum(1).cpu().numpy(), rtol=1e-9)
+    # (5) the two halves of the domain give bitwise the same columns as the whole (SURVEY 8e)
+    half = ncol // 2
+    for h0 in (0, half):
+        part = {k: before[k][:, h0:h0 + half].contiguous() for k in FIELDS}
+        pp = torch.zeros((4, half), dtype=torch.float32, device="cuda")
+        ph = p[:, h0:h0 + half].contiguous()
+        torch.cuda.synchronize()                   # the slices were made on torch's default stream, the step runs on `s`
+        with torch.cuda.stream(s):
+            gpu_mixed.step_device(half, nz, dt, [part[k].data_ptr() for k in FIELDS], ph.data_ptr(), dz.data_ptr(), pp.data_ptr(),
+                                  stream=s.cuda_stream)
+        s.synchronize()
+        for k in FIELDS:
+            assert torch.equal(part[k], st[k][:, h0:h0 + half]), (h0, k)
+        assert torch.equal(pp, ppt[:, h0:h0 + half])
+    # (6) a random sample of cloudy columns against the oracle
+    g = torch.Generator(device="cpu").manual_seed(5)
+    cloudy_idx = torch.nonzero(changed).flatten().cpu()
+    pick = cloudy_idx[torch.randperm(cloudy_idx.numel(), generator=g)[:4096]].sort().values
+    sample_in = {k: before[k][:, pick.cuda()].cpu().numpy().copy() for k in FIELDS}
+    sample_out = {k: st[k][:, pick.cuda()].cpu().numpy() for k in FIELDS}
+    pb = oracle_mixed.step(dt, sample_in, p[:, pick.cuda()].cpu().numpy().copy(), dz.cpu().numpy())
+    assert_parity(sample_out, sample_in, what="4096 cloudy columns of the 1M-column run")
+    np.testing.assert_allclose(ppt[:, pick.cuda()].cpu().numpy(), pb, rtol=1e-5, atol=1e-10)
