@@ -232,7 +232,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     h->d_scratch = nullptr; h->d_colint = nullptr; h->d_work = nullptr; h->d_coldiag = nullptr; h->scratch_cells = 0; h->scratch_cols = 0;
     CK(h, cudaMalloc((void**)&h->d_scratch, need * SC_N * 4));
     CK(h, cudaMalloc((void**)&h->d_colint, (size_t)a.ncol * 8 * 4));
-    CK(h, cudaMalloc((void**)&h->d_work, (size_t)(a.ncol + 8) * 4));
+    CK(h, cudaMalloc((void**)&h->d_work, (size_t)(a.ncol + 8 + 2 * ngroups) * 4));
     CK(h, cudaMalloc((void**)&h->d_coldiag, (size_t)a.ncol * 2 * 8));
     h->scratch_cells = need; h->scratch_cols = a.ncol;
   }
@@ -240,11 +240,14 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   a.colint = h->d_colint;
   a.work_count = h->d_work;
   a.work_list = h->d_work + 8;
+  a.work_mask = (unsigned*)(h->d_work + 8 + a.ncol);
+  a.work_offset = h->d_work + 8 + a.ncol + ngroups;
   a.coldiag = h->d_coldiag;
   a.diag_partial = h->d_partial;
   a.rates = h->d_rates;
-  CK(h, cudaMemsetAsync(h->d_work, 0, 4, s));
   k_classify<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
+  k_list_scan<<<1, 1024, 0, s>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
+  k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
   // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
   // dynamic shared memory of the physics kernel: 116 bytes per thread (vertical carries, parked inputs) (above 48 KB needs the opt-in)
 #define LAUNCH_K1(KERNEL, GRID, THREADS)                                                                          \
@@ -282,7 +285,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
   k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
   k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
-  h->launches += 5;
+  h->launches += 7;
   CK(h, cudaGetLastError());
   return 0;
 }

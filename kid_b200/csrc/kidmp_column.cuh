@@ -167,15 +167,40 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
       a.ppt[col] = 0.f; a.ppt[ncol + col] = 0.f; a.ppt[2 * ncol + col] = 0.f; a.ppt[3 * ncol + col] = 0.f;   // I:55-58
     }
   }
-  // append the cloudy columns of this warp to the work list (one atomic per warp, order within the warp kept)
+  // ballot of the cloudy lanes of this 32-column group; k_list_scan / k_list_fill turn the ballots into the
+  // compacted work list IN COLUMN ORDER (neighbouring lanes of the physics kernel are neighbouring columns: coalesced
+  // accesses, similar branches, and a list that is identical from run to run)
   const unsigned mask = __ballot_sync(0xffffffffu, active);
-  if (mask) {
-    const int lane = threadIdx.x & 31;
-    int pos = 0;
-    if (lane == 0) pos = atomicAdd(a.work_count, __popc(mask));
-    pos = __shfl_sync(0xffffffffu, pos, 0);
-    if (active) a.work_list[pos + __popc(mask & ((1u << lane) - 1u))] = (int)col;
+  if ((threadIdx.x & 31) == 0 && in_range) a.work_mask[col >> 5] = mask;
+}
+
+// exclusive prefix sum of the per-group cloudy-column counts (one block; ngroups is at most a few 10^5)
+__global__ void __launch_bounds__(1024) k_list_scan(const unsigned* __restrict__ mask, int ngroups, int* __restrict__ offset,
+                                                    int* __restrict__ count) {
+  __shared__ int s_sum[1024];
+  const int per = (ngroups + 1023) / 1024;
+  const int g0 = threadIdx.x * per, g1 = min(g0 + per, ngroups);
+  int sum = 0;
+  for (int g = g0; g < g1; ++g) sum += __popc(mask[g]);
+  s_sum[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {                     // Hillis-Steele inclusive scan
+    const int v = (int)threadIdx.x >= d ? s_sum[threadIdx.x - d] : 0;
+    __syncthreads();
+    s_sum[threadIdx.x] += v;
+    __syncthreads();
   }
+  int run = s_sum[threadIdx.x] - sum;
+  for (int g = g0; g < g1; ++g) { offset[g] = run; run += __popc(mask[g]); }
+  if (threadIdx.x == 1023) *count = s_sum[1023];
+}
+
+__global__ void __launch_bounds__(256) k_list_fill(const unsigned* __restrict__ mask, const int* __restrict__ offset, int ngroups,
+                                                   int* __restrict__ list) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= ngroups) return;
+  const unsigned m = mask[g];
+  if ((m >> lane) & 1u) list[offset[g] + __popc(m & ((1u << lane) - 1u))] = g * 32 + lane;
 }
 
 // ---- K1: column physics, S1..S13, on the cloudy 32-column groups of the work list.  A block is

@@ -118,7 +118,9 @@ struct StepArgs {
   float* scratch;              // [SC_N][nz][ncol] hand-off, touched for cloudy columns only
   int* colint;                 // [8][ncol] substep counts / top sedimenting level per species; [0] = -1: clear sky
   int* work_count;             // number of cloudy columns found by the classification kernel
-  int* work_list;              // their column indices, compacted (warp-sized runs in discovery order)
+  int* work_list;              // their column indices, compacted in column order
+  unsigned* work_mask;         // [ngroups] ballot of the cloudy lanes of every 32-column group
+  int* work_offset;            // [ngroups] exclusive prefix sum of the ballots' popcounts
   float* rates;                // optional [36][nz][ncol]
   double* coldiag;             // [2][ncol] liquid / ice water path of each cloudy column
   double* diag_partial;        // [DIAG_BLOCKS][KIDMP_NDIAG] block sums of k_diag_columns
