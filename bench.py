@@ -10,8 +10,8 @@ Weak scaling: every rank owns its own 1 048 576 columns [rank*ncol, (rank+1)*nco
 domain; columns are independent, so there is no data-path collective - NCCL only reduces the eight
 domain diagnostics once per run.
 
-A "step" = one kidmp_step_device call (five launches: classification, column physics and sedimentation + final
-clamps on the compacted list of cloudy columns, ordered domain sums, their 8-block reduce) over all resident columns; the state evolves in place from step to step like a model time loop.
+A "step" = one kidmp_step_device call (seven launches: classification, scan + fill of the work list, column physics
+and sedimentation + final clamps on the compacted list of cloudy columns, ordered domain sums and their reduce) over all resident columns; the state evolves in place from step to step like a model time loop.
 Inputs (2.8 GB per GPU) are far larger than L2, so no flush is needed between steps.
 """
 import argparse
@@ -32,10 +32,10 @@ UNIT = "column-steps/s"
 ALG_BYTES_PER_COLUMN = 4576          # 10 fields read + 9 written + 4 precip scalars, nz=60
 NZ = 60
 DT = 10.0
-# dram__bytes_read.sum + dram__bytes_write.sum of the three step kernels from the ncu --set full captures of the same
-# workload (profiles/r01_ncu_step_kernels.md, report prof_r1g): 2.52+0.02 (classify) + 1.28+3.10 (physics) +
-# 3.52+0.72 (sedimentation) + 0.02 (ordered domain sums) GB
-TRAFFIC_BYTES_PER_LAUNCH = 11.17e9
+# dram__bytes_read.sum + dram__bytes_write.sum of the step kernels from the ncu --set full captures of the same workload
+# (profiles/r01_ncu_step_kernels.md, reports prof_r1g / prof_r1i): 2.52+0.02 (classify) + 1.24+2.35 (physics) +
+# 3.46+0.71 (sedimentation) + 0.02 (ordered domain sums) GB
+TRAFFIC_BYTES_PER_LAUNCH = 10.32e9
 
 
 def peaks():
@@ -271,7 +271,7 @@ def main():
                        "active_column_fraction": float(diag[6].item() / max(diag[7].item(), 1.0))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                         "kernel": "one step = k_classify + k_column_step<24,1,11> + k_sediment + k_diag_columns + k_diag_reduce (k_column_step is 80 % of it); "
+                         "kernel": "one step = k_classify + k_list_scan/fill + k_column_step<24,1,11> + k_sediment + k_diag_columns/reduce (k_column_step is 79 % of it); "
                                    "achieved and traffic are for the whole step, the unit the algorithmic bytes are defined on",
                          "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_COLUMN * ncol},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
