@@ -256,31 +256,11 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     if (!attr_set) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (THREADS) * 116); attr_set = true; } \
     KERNEL<<<(GRID), (THREADS), (THREADS) * 116, s>>>(a);                                                          \
   } while (0)
-  static const int bars = getenv("KIDMP_BARS") ? atoi(getenv("KIDMP_BARS")) : 11;
-  const unsigned g16 = (unsigned)((ngroups + 15) / 16), g8 = (unsigned)((ngroups + 7) / 8);
+  // measured alternatives (profiles/r01_ncu_step_kernels.md): 16 / 20 / 28 / 32 warps, 2x12 and 3x8 warps per SM, other barrier sets
   if (a.rates) LAUNCH_K1((k_column_step<16, 1, 11, true>), (unsigned)((ngroups + 15) / 16), 512);   // with the 36 save_dg rates
-  else if (warps >= 32) LAUNCH_K1((k_column_step<32, 1, 11, false>), (unsigned)((ngroups + 31) / 32), 1024);
-  else if (warps >= 28) LAUNCH_K1((k_column_step<28, 1, 11, false>), (unsigned)((ngroups + 27) / 28), 896);
-  else if (warps >= 24) {
-    const unsigned g24 = (unsigned)((ngroups + 23) / 24);
-    if (bars == 63) LAUNCH_K1((k_column_step<24, 1, 63, false>), g24, 768);
-    else if (bars == 3) LAUNCH_K1((k_column_step<24, 1, 3, false>), g24, 768);
-    else if (bars == 1) LAUNCH_K1((k_column_step<24, 1, 1, false>), g24, 768);
-    else if (bars == 9) LAUNCH_K1((k_column_step<24, 1, 9, false>), g24, 768);
-    else LAUNCH_K1((k_column_step<24, 1, 11, false>), g24, 768);
-  }
-  else if (warps >= 20) LAUNCH_K1((k_column_step<20, 1, 11, false>), (unsigned)((ngroups + 19) / 20), 640);
-  else if (warps >= 16) {
-    if (bars == 63) LAUNCH_K1((k_column_step<16, 1, 63, false>), g16, 512);
-    else if (bars == 11) LAUNCH_K1((k_column_step<16, 1, 11, false>), g16, 512);      // level top, before S6, before S9
-    else if (bars == 3) LAUNCH_K1((k_column_step<16, 1, 3, false>), g16, 512);
-    else LAUNCH_K1((k_column_step<16, 1, 1, false>), g16, 512);
-  } else if (warps >= 12) LAUNCH_K1((k_column_step<12, 1, 63, false>), (unsigned)((ngroups + 11) / 12), 384);
-  else if (warps == 9) {                                                         // two 8-warp blocks per SM
-    if (bars == 63) LAUNCH_K1((k_column_step<8, 2, 63, false>), g8, 256);
-    else if (bars == 11) LAUNCH_K1((k_column_step<8, 2, 11, false>), g8, 256);
-    else LAUNCH_K1((k_column_step<8, 2, 1, false>), g8, 256);
-  } else if (warps >= 8) LAUNCH_K1((k_column_step<8, 1, 63, false>), g8, 256);
+  else if (warps >= 24) LAUNCH_K1((k_column_step<24, 1, 11, false>), (unsigned)((ngroups + 23) / 24), 768);
+  else if (warps >= 16) LAUNCH_K1((k_column_step<16, 1, 11, false>), (unsigned)((ngroups + 15) / 16), 512);
+  else if (warps >= 8) LAUNCH_K1((k_column_step<8, 2, 11, false>), (unsigned)((ngroups + 7) / 8), 256);   // two 8-warp blocks per SM
   else LAUNCH_K1((k_column_step<1, 12, 0, false>), (unsigned)ngroups, 32);
   k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
   k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
