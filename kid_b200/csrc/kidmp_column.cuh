@@ -1,20 +1,22 @@
-// kidmp_column.cuh - K1+K2: the Thompson column step, one thread per column.
+// kidmp_column.cuh - the Thompson column step on the device, one thread per column.
 //
 // Replaces the body of `do i = 1, nx` around `call mp_thompson` (I:54-246) and mp_thompson itself
 // (M:1156-3688).  Data layout: every field is [nz][ncol] f32 (columns fastest), so the 32 lanes
 // of a warp read 128 contiguous bytes per level.
 //
-// Structure (DESIGN.md "Column kernel"):
-//   pass 0  one bottom-up read of the ten fields decides `no_micro` (M:1396-1521, the early
-//           RETURN at M:1540); clear-sky columns only write back the species <= R1 that the
-//           reference zeroes in the caller's arrays (M:1412-1489) and leave.
-//   pass 1  ONE top-down sweep does stages S1..S13 of SURVEY.md section 3.2 level by level: every
-//           vertical dependency of the scheme runs from the top (graupel N0 running minimum
-//           M:1648, `k_0` M:1635, fall-speed carry-down M:3235) so it is carried in registers.
-//           Per-level results that sedimentation needs are parked in per-thread local arrays.
-//   pass 2  sub-stepped upwind sedimentation (M:3365-3578), instant melt/freeze (M:3584-3606),
-//           apply tendencies and final clamps (M:3623-3686), coalesced stores, block-reduced
-//           domain sums.
+// Kernels:
+//   k_classify     one bottom-up read of the ten fields decides `no_micro` (M:1396-1521, the early RETURN
+//                  at M:1540); clear-sky columns only get back the species <= R1 that the reference
+//                  zeroes in the caller's arrays (M:1412-1489) and are done.
+//   k_list_scan /  the ballots of the cloudy lanes become a compacted work list in column order.
+//   k_list_fill
+//   k_column_step  ONE top-down sweep over the cloudy columns does stages S1..S13 of SURVEY.md section 3.2
+//                  level by level: every vertical dependency of the scheme runs from the top (graupel N0
+//                  running minimum M:1648, `k_0` M:1635, fall-speed carry-down M:3235), so it is carried
+//                  along the sweep.  24 values per level are handed to the sedimentation kernel.
+//   k_sediment     sub-stepped upwind sedimentation (M:3365-3578), instant melt/freeze (M:3584-3606),
+//                  apply tendencies and final clamps (M:3623-3686), coalesced stores.
+//   k_diag_columns the eight domain sums in column order (bitwise reproducible), k_diag_reduce adds the blocks.
 #pragma once
 #include "kidmp_internal.h"
 #include "kidmp_math.cuh"
@@ -119,10 +121,6 @@ KIDMP_HELPER void graupel_n0(bool above_k0, bool L_qr, float mvd_r, float rg, do
   N0_g = N0_exp / ((double)ck.cgg[1] * lam_exp) * lamg;                                         // lamg**cge(2), cge(2) = 1
 }
 
-struct ColPtrs {
-  float* f[KIDMP_NFIELDS];   // qv qc qi qr qs qg ni nr t
-  const float* p;
-};
 enum { F_QV = 0, F_QC, F_QI, F_QR, F_QS, F_QG, F_NI, F_NR, F_T };
 
 // ---- K0: classification (pass 0).  One thread per column reads the ten fields once, decides

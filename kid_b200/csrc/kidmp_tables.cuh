@@ -4,7 +4,7 @@
 //
 // Split of work: the per-axis-node scalars (slopes and intercepts of the 1369 rain, 784 graupel and
 // 252 snow size distributions, i.e. a few thousand f32 powf results, M:3755-3757, M:3764-3766,
-// M:3937-3971) are evaluated once on the host in kidmp_api.cuh; the 1.4e10-term bin integrals that
+// M:3937-3971) are evaluated once on the host in kidmp_hostinit.h; the 1.4e10-term bin integrals that
 // make the build slow in the reference run here, one thread per table entry, the (rain, N0r) pair
 // of a block shared through shared memory.  Summation order inside an entry is the reference's
 // (n2 outer, n inner), so tables agree with a CPU evaluation to a few f64 ulps.
