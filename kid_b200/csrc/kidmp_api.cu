@@ -47,7 +47,7 @@ struct kidmp_handle {
   float* d_rates = nullptr;
   float* d_kid = nullptr; size_t kid_floats = 0;   // staging of the KiD (k,i) arrays
   float* d_pipe = nullptr; size_t pipe_floats = 0; int pipe_nz = 0; float* d_pipe_dz = nullptr;   // chunk pipeline of kidmp_step
-  long pipe_chunk = 131072;
+  long pipe_chunk = 65536;
   float* h_ppt = nullptr; size_t h_ppt_floats = 0;       // pinned staging of ppt for the chunk pipeline
   cudaEvent_t pipe_ev[3][3] = {};
   float last_ms = 0.f;
