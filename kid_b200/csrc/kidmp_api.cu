@@ -46,6 +46,7 @@ struct kidmp_handle {
   double* d_diag = nullptr;
   float* d_rates = nullptr;
   float* d_kid = nullptr; size_t kid_floats = 0;   // staging of the KiD (k,i) arrays
+  float* h_kid = nullptr; size_t h_kid_floats = 0; // pinned host twin of it
   float* d_pipe = nullptr; size_t pipe_floats = 0; int pipe_nz = 0; float* d_pipe_dz = nullptr;   // chunk pipeline of kidmp_step
   long pipe_chunk = 65536;
   float* h_ppt = nullptr; size_t h_ppt_floats = 0;       // pinned staging of ppt for the chunk pipeline
@@ -395,6 +396,7 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_diag) cudaFree(h->d_diag);
   if (h->d_kid) cudaFree(h->d_kid);
+  if (h->h_kid) cudaFreeHost(h->h_kid);
   if (h->d_scratch) cudaFree(h->d_scratch);
   if (h->d_colint) cudaFree(h->d_colint);
   if (h->d_work) cudaFree(h->d_work);
@@ -689,14 +691,22 @@ int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, f
     CK(h, cudaMalloc((void**)&h->d_kid, n * nplanes * 4));
     h->kid_floats = n * nplanes;
   }
+  // All planes go through ONE pinned staging buffer and one copy each way: KiD calls this every time step with a
+  // handful of columns, where forty small cudaMemcpy calls would cost more than the kernels.
+  const size_t nin = 28, nout = 9;
+  const size_t hfloats = (nin + nout) * n + (size_t)c->nz + (size_t)c->nx * 4;
+  if (h->h_kid_floats < hfloats) {
+    if (h->h_kid) cudaFreeHost(h->h_kid);
+    h->h_kid = nullptr; h->h_kid_floats = 0;
+    CK(h, cudaHostAlloc((void**)&h->h_kid, hfloats * 4, cudaHostAllocDefault));
+    h->h_kid_floats = hfloats;
+  }
   int slot = 0;
-  cudaError_t ce = cudaSuccess;
   auto in = [&](const float* src) -> const float* {
-    float* d = h->d_kid + n * (size_t)slot++;
+    const size_t off = n * (size_t)slot++;
     if (!src) return nullptr;
-    cudaError_t e = cudaMemcpyAsync(d, src, n * 4, cudaMemcpyHostToDevice, h->stream);
-    if (ce == cudaSuccess) ce = e;
-    return d;
+    memcpy(h->h_kid + off, src, n * 4);
+    return h->d_kid + off;
   };
   auto out = [&]() { return h->d_kid + n * (size_t)slot++; };
   KidArgs a{};
@@ -708,12 +718,16 @@ int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, f
     a.hyd[m] = in(use ? c->hyd[m] : nullptr); a.dhyd_adv[m] = in(use ? c->dhyd_adv[m] : nullptr);
     a.dhyd_div[m] = in(use ? c->dhyd_div[m] : nullptr);
   }
+  float* const d_out0 = h->d_kid + n * nin;
   a.dtheta_mphys = out(); a.dqv_mphys = out();
   for (int m = 0; m < 7; ++m) a.dhyd_mphys[m] = out();
-  if (ce != cudaSuccess) return fail(h, "kid_interface: H2D copy: %s", cudaGetErrorString(ce));
+  float* const h_dz = h->h_kid + (nin + nout) * n;
+  float* const h_ppt = h_dz + c->nz;
+  memcpy(h_dz, c->dz, (size_t)c->nz * 4);
   for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = field_ptr(h, q);
   a.p = field_ptr(h, KIDMP_NFIELDS);
-  CK(h, cudaMemcpyAsync(h->d_dz, c->dz, (size_t)c->nz * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_kid, h->h_kid, (warm ? (7 + 9) : nin) * n * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_dz, h_dz, (size_t)c->nz * 4, cudaMemcpyHostToDevice, h->stream));
   dim3 g((unsigned)((c->nx + 31) / 32), (unsigned)((c->nz + 31) / 32)), b(32, 8);
   k_kid_gather<<<g, b, 0, h->stream>>>(a);
   ++h->launches;
@@ -723,12 +737,15 @@ int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, f
   k_kid_scatter<<<g, b, 0, h->stream>>>(a);
   ++h->launches;
   CK(h, cudaGetLastError());
-  CK(h, cudaMemcpyAsync(c->dtheta_mphys, a.dtheta_mphys, n * 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaMemcpyAsync(c->dqv_mphys, a.dqv_mphys, n * 4, cudaMemcpyDeviceToHost, h->stream));
-  for (int m = 0; m < 7; ++m)
-    if (m < 3 || !warm) CK(h, cudaMemcpyAsync(c->dhyd_mphys[m], a.dhyd_mphys[m], n * 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaMemcpyAsync(c->ppt, h->d_ppt, (size_t)c->nx * 16, cudaMemcpyDeviceToHost, h->stream));
+  float* const h_out0 = h->h_kid + n * nin;
+  CK(h, cudaMemcpyAsync(h_out0, d_out0, (warm ? 5 : nout) * n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(h_ppt, h->d_ppt, (size_t)c->nx * 16, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
+  memcpy(c->dtheta_mphys, h_out0, n * 4);
+  memcpy(c->dqv_mphys, h_out0 + n, n * 4);
+  for (int m = 0; m < 7; ++m)
+    if (m < 3 || !warm) memcpy(c->dhyd_mphys[m], h_out0 + n * (size_t)(2 + m), n * 4);
+  memcpy(c->ppt, h_ppt, (size_t)c->nx * 16);
   return 0;
 }
 
