@@ -57,6 +57,14 @@ long kidmp_table_size(const kidmp_handle* h, const char* name);
 int kidmp_get_table(const kidmp_handle* h, const char* name, double* out, long n);
 int kidmp_save_tables(const kidmp_handle* h, const char* path);
 
+/* KiD's own lookup-table cache (M:3710-3728, M:3823-3828, M:3857-3894, M:4066-4077): list-directed text, the six rain-graupel
+ * tables in run_data/racg_thompson09.data and the twelve rain-snow tables in run_data/racs_thompson09.data, each written as one
+ * `write(unit,*) table` record in Fortran element order.  The writer prints 17 significant digits (what gfortran prints for
+ * REAL(8), exact on re-reading); the reader takes anything `read(unit,*)` takes (blanks, commas, line breaks, D/E exponents,
+ * r*c repeats).  With these the Fortran reference and this library can run on the same tables. */
+int kidmp_write_kid_cache(const kidmp_handle* h, const char* racg_path, const char* racs_path);
+int kidmp_read_kid_cache(kidmp_handle* h, const char* racg_path, const char* racs_path);
+
 /* exact single-column twin of mp_thompson (M:1156-1162): host arrays of nz, in place; ppt4 is
  * rain, ice, snow, graupel and is ACCUMULATED into like the reference's INOUT scalars (M:1172). */
 int kidmp_column(kidmp_handle* h, int nz, float dt,

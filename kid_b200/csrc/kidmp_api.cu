@@ -474,6 +474,86 @@ int kidmp_save_tables(const kidmp_handle* hc, const char* path) {
   return 0;
 }
 
+// ---- KiD's list-directed text cache ------------------------------------------------------------------------------
+namespace {
+// one Fortran list-directed record per table, three values per line like gfortran's REAL(8) output
+bool write_records(FILE* f, const std::vector<double>& rec, long n, int members) {
+  for (int q = 0; q < members; ++q) {
+    for (long i = 0; i < n; ++i) {
+      if (fprintf(f, "%26.16E%s", rec[(size_t)i * members + q], (i % 3 == 2 || i == n - 1) ? "\n" : "") < 0) return false;
+    }
+  }
+  return true;
+}
+// list-directed input: values separated by blanks, commas or line breaks; r*c repeats; D exponents
+bool read_records(FILE* f, std::vector<double>& rec, long n, int members) {
+  std::vector<char> tok;
+  long have = 0;
+  const long want = n * members;
+  auto put = [&](double v, long rep) {
+    for (long r = 0; r < rep && have < want; ++r, ++have) {
+      const long q = have / n, i = have % n;          // records are table after table, elements in Fortran order
+      rec[(size_t)i * members + q] = v;
+    }
+  };
+  int c;
+  while (have < want && (c = fgetc(f)) != EOF) {
+    if (c == ' ' || c == ',' || c == '\n' || c == '\r' || c == '\t') continue;
+    tok.clear();
+    while (c != EOF && c != ' ' && c != ',' && c != '\n' && c != '\r' && c != '\t') { tok.push_back((char)((c == 'D' || c == 'd') ? 'E' : c)); c = fgetc(f); }
+    tok.push_back(0);
+    long rep = 1;
+    char* star = strchr(tok.data(), '*');
+    const char* val = tok.data();
+    if (star) { *star = 0; rep = atol(tok.data()); val = star + 1; if (rep < 1) return false; }
+    char* end = nullptr;
+    const double v = strtod(val, &end);
+    if (end == val) return false;
+    put(v, rep);
+  }
+  return have == want;
+}
+}  // namespace
+
+int kidmp_write_kid_cache(const kidmp_handle* hc, const char* racg_path, const char* racs_path) {
+  kidmp_handle* h = const_cast<kidmp_handle*>(hc);
+  if (!h || !racg_path || !racs_path) return 1;
+  if (h->kc.iiwarm) return fail(h, "write_kid_cache: the collection tables are not built when iiwarm (M:773)");
+  cudaSetDevice(h->device);
+  CK(h, cudaStreamSynchronize(h->stream));
+  const struct { const char* path; const double* dev; long n; int members; } files[2] = {
+      {racg_path, h->tabs.racg, (long)N_RACG, G_N}, {racs_path, h->tabs.racs, (long)N_RACS, S_N}};
+  for (const auto& t : files) {
+    std::vector<double> rec((size_t)t.n * t.members);
+    CK(h, cudaMemcpy(rec.data(), t.dev, rec.size() * 8, cudaMemcpyDeviceToHost));
+    // member order inside a record = order of the write statements (M:3823-3828, M:4066-4077)
+    FILE* f = fopen(t.path, "w");
+    if (!f) return fail(h, "cannot write %s", t.path);
+    const bool ok = write_records(f, rec, t.n, t.members);
+    if (fclose(f) != 0 || !ok) return fail(h, "writing %s failed", t.path);
+  }
+  return 0;
+}
+
+int kidmp_read_kid_cache(kidmp_handle* h, const char* racg_path, const char* racs_path) {
+  if (!h || !racg_path || !racs_path) return 1;
+  if (h->kc.iiwarm) return fail(h, "read_kid_cache: the collection tables are not used when iiwarm (M:773)");
+  cudaSetDevice(h->device);
+  CK(h, cudaStreamSynchronize(h->stream));
+  const struct { const char* path; double* dev; long n; int members; } files[2] = {
+      {racg_path, h->tabs.racg, (long)N_RACG, G_N}, {racs_path, h->tabs.racs, (long)N_RACS, S_N}};
+  for (const auto& t : files) {
+    FILE* f = fopen(t.path, "r");
+    if (!f) return fail(h, "cannot read %s", t.path);
+    std::vector<double> rec((size_t)t.n * t.members);
+    const bool ok = read_records(f, rec, t.n, t.members);
+    fclose(f);
+    if (!ok) return fail(h, "%s does not hold %d tables of %ld values", t.path, t.members, t.n);
+    CK(h, cudaMemcpy(t.dev, rec.data(), rec.size() * 8, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
 int kidmp_state_alloc(kidmp_handle* h, long ncol, int nz) {
   if (!h) return 1;
   if (ncol < 1 || nz < 2 || nz > 256) return fail(h, "state_alloc: ncol=%ld nz=%d", ncol, nz);

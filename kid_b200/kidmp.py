@@ -38,6 +38,8 @@ SYMBOLS = {
     "kidmp_table_size": (C.c_long, [C.c_void_p, C.c_char_p]),
     "kidmp_get_table": (C.c_int, [C.c_void_p, C.c_char_p, _dp, C.c_long]),
     "kidmp_save_tables": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "kidmp_write_kid_cache": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "kidmp_read_kid_cache": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "kidmp_column": (C.c_int, [C.c_void_p, C.c_int, C.c_float] + [_fp] * 9 + [_fp, _fp, _fp]),
     "kidmp_step": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_int, _fpp, _fp, _fp, _fp]),
     "kidmp_state_alloc": (C.c_int, [C.c_void_p, C.c_long, C.c_int]),
@@ -159,6 +161,13 @@ class Thompson:
 
     def save_tables(self, path):
         self._ck(self._L.kidmp_save_tables(self.h, path.encode()))
+
+    def write_kid_cache(self, racg_path, racs_path):
+        """KiD's list-directed text cache files run_data/racg_thompson09.data / racs_thompson09.data (M:3710-3728 ...)."""
+        self._ck(self._L.kidmp_write_kid_cache(self.h, racg_path.encode(), racs_path.encode()))
+
+    def read_kid_cache(self, racg_path, racs_path):
+        self._ck(self._L.kidmp_read_kid_cache(self.h, racg_path.encode(), racs_path.encode()))
 
     # -- steps --------------------------------------------------------------------------------------
     def column(self, dt, qv, qc, qi, qr, qs, qg, ni, nr, t, p, dz, ppt=None):

@@ -491,3 +491,31 @@ def test_full_size_domain_properties(gpu_mixed, oracle_mixed):
     pb = oracle_mixed.step(dt, sample_in, p[:, pick.cuda()].cpu().numpy().copy(), dz.cpu().numpy())
     assert_parity(sample_out, sample_in, what="4096 cloudy columns of the 1M-column run")
     np.testing.assert_allclose(ppt[:, pick.cuda()].cpu().numpy(), pb, rtol=1e-5, atol=1e-10)
+
+
+def test_kid_text_cache_roundtrip(gpu_mixed, tmp_path):
+    """KiD's list-directed lookup-table files (run_data/racg_thompson09.data, racs_thompson09.data; M:3710-3728,
+    M:3857-3894): written in the order and element order of the reference's write statements, and read back exactly."""
+    import subprocess
+    from kid_b200.kidmp import Thompson
+    racg, racs = str(tmp_path / "racg_thompson09.data"), str(tmp_path / "racs_thompson09.data")
+    gpu_mixed.write_kid_cache(racg, racs)
+    n_racg, n_racs = 28 * 28 * 37 * 37, 28 * 9 * 37 * 37
+    assert int(subprocess.run(["wc", "-w", racg], capture_output=True, text=True).stdout.split()[0]) == 6 * n_racg
+    assert int(subprocess.run(["wc", "-w", racs], capture_output=True, text=True).stdout.split()[0]) == 12 * n_racs
+    head = np.array(open(racg).readline().split(), np.float64)          # first record starts with tcg_racg(1,1,1,1), (2,1,1,1) ...
+    assert np.array_equal(head, gpu_mixed.get("tcg_racg")[:3])
+    with open(racs) as f:                                               # second table of the file starts after n_racs values
+        vals = []
+        for line in f:
+            vals.extend(line.split())
+            if len(vals) > n_racs + 3:
+                break
+    assert np.array_equal(np.array(vals[n_racs:n_racs + 3], np.float64), gpu_mixed.get("tmr_racs1")[:3])
+    t2 = Thompson(set_Nc=100.0, iiwarm=False, wp_double=True)           # slightly different bins => different tables
+    assert not np.array_equal(t2.get("tcr_gacr"), gpu_mixed.get("tcr_gacr"))
+    t2.read_kid_cache(racg, racs)
+    for name in ("tcg_racg", "tmr_racg", "tcr_gacr", "tmg_gacr", "tnr_racg", "tnr_gacr", "tcs_racs1", "tmr_racs2", "tms_sacr2",
+                 "tnr_racs1", "tnr_sacr2"):
+        assert np.array_equal(t2.get(name), gpu_mixed.get(name)), name
+    t2.close()
