@@ -104,21 +104,34 @@ KIDMP_HELPER double ice_lam(float ni, float ri) {   // M:1429
   return (double)pow_f(ck.am_i * ck.cig[1] * ck.oig1 * ni / ri, ck.obmi);
 }
 
-// graupel intercept at one level given the running minimum from above, M:1639-1653
-KIDMP_HELPER void graupel_n0(bool above_k0, bool L_qr, float mvd_r, float rg, double& N0_min,
-                                           double& ilamg, double& N0_g) {
-  float xslw1 = 0.01f;
-  if (above_k0 && L_qr && mvd_r > 100.E-6f) xslw1 = 4.01f + log10_f(mvd_r);
+// graupel intercept at one level given the running minimum from above, M:1639-1653.
+// xslw1 = 0.01 and MAX(5.E-5, rg) = 5.E-5 (no supercooled rain above k_0, graupel content at most 5.E-5) make
+// N0_exp the per-run constant `n0_lo` (evaluated once per thread by graupel_n0_lo with the same expressions);
+// lam_exp, lamg, ilamg and N0_g (M:1649-1653) are only read where rg > R1 (M:1862, M:1921, M:2168, M:2254, M:3318).
+__device__ __forceinline__ double graupel_n0_exp(float xslw1, float rg) {
   const float ygra1 = 4.31f + log10_f(fmaxf(5.E-5f, rg));
   const float zans1 = 3.1f + (100.f / (300.f * xslw1 * ygra1 / (10.f / xslw1 + 1.f + 0.25f * ygra1) + 30.f + 10.f * ygra1));
-  double N0_exp = (double)pow10_f(zans1);
-  N0_exp = fmax((double)KP_GONV_MIN, fmin(N0_exp, (double)KP_GONV_MAX));
+  const double N0_exp = (double)pow10_f(zans1);
+  return fmax((double)KP_GONV_MIN, fmin(N0_exp, (double)KP_GONV_MAX));
+}
+KIDMP_HELPER double graupel_n0_lo() { return graupel_n0_exp(0.01f, R1); }
+KIDMP_HELPER void graupel_n0(bool above_k0, bool L_qr, bool L_qg, float mvd_r, float rg, double n0_lo, double& N0_min,
+                             double& ilamg, double& N0_g) {
+  const bool slw = above_k0 && L_qr && mvd_r > 100.E-6f;
+  double N0_exp = n0_lo;
+  if (slw || rg > 5.E-5f) {
+    float xslw1 = 0.01f;
+    if (slw) xslw1 = 4.01f + log10_f(mvd_r);
+    N0_exp = graupel_n0_exp(xslw1, rg);
+  }
   N0_min = fmin(N0_exp, N0_min);
   N0_exp = N0_min;
-  const double lam_exp = sqrt(sqrt(N0_exp * (double)ck.am_g * (double)ck.cgg[0] / (double)rg));   // **oge1, oge1 = 1/4
-  const double lamg = lam_exp * (double)ck.lamg_fac;
-  ilamg = (double)1.f / lamg;
-  N0_g = N0_exp / ((double)ck.cgg[1] * lam_exp) * lamg;                                         // lamg**cge(2), cge(2) = 1
+  if (L_qg) {
+    const double lam_exp = sqrt(sqrt(N0_exp * (double)ck.am_g * (double)ck.cgg[0] / (double)rg));   // **oge1, oge1 = 1/4
+    const double lamg = lam_exp * (double)ck.lamg_fac;
+    ilamg = (double)1.f / lamg;
+    N0_g = N0_exp / ((double)ck.cgg[1] * lam_exp) * lamg;                                         // lamg**cge(2), cge(2) = 1
+  }
 }
 
 enum { F_QV = 0, F_QC, F_QI, F_QR, F_QS, F_QG, F_NI, F_NR, F_T };
@@ -269,13 +282,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
 
       // graupel intercept of a level without rain and graupel (xslw1 = 0.01, rg = R1 in M:1639-1646): the only
       // thing such a level contributes to the running minimum of M:1648
-      double n0_empty;
-      {
-        const float xslw1 = 0.01f;
-        const float ygra1 = 4.31f + log10_f(fmaxf(5.E-5f, R1));
-        const float zans1 = 3.1f + (100.f / (300.f * xslw1 * ygra1 / (10.f / xslw1 + 1.f + 0.25f * ygra1) + 30.f + 10.f * ygra1));
-        n0_empty = fmax((double)KP_GONV_MIN, fmin((double)pow10_f(zans1), (double)KP_GONV_MAX));
-      }
+      const double n0_empty = graupel_n0_lo();
 
       // ================= pass 1: top-down, S1..S13 per level ====================================
 #pragma unroll 1
@@ -361,6 +368,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         // number tendencies are summed as their terms appear (M:2417, M:2453, M:2503 add them up later): the
         // 22 individual number rates need not stay in registers until S8
         double nc_acc = 0., ni_acc = 0., nr_acc = 0.;
+        // lamr / lami hold rain_lam(nr, rr) / ice_lam(ni, ri) of the current nr, rr / ni, ri unless the number was
+        // re-diagnosed after they were evaluated: the reference evaluates the same power again at M:1661, M:2118,
+        // M:2750 and M:3227 from unchanged arguments, which is the same number
+        bool lamr_stale = false, lami_stale = false;
 
         // ---- S1, M:1387-1493 -------------------------------------------------------------------
         float temp = t1d;
@@ -387,11 +398,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           ilami = (double)1.f / lami;
           const float xDi = (float)((double)(3.f + 0.f + 1.f) * ilami);
           if (xDi < 5.E-6f) {
-            lami = (double)(ck.cie[1] / 5.E-6f);
-            ni = (float)fmin(499.E3, (double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(lami));
+            const double l2 = (double)(ck.cie[1] / 5.E-6f);
+            ni = (float)fmin(499.E3, (double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(l2));
+            lami_stale = true;
           } else if (xDi > 300.E-6f) {
-            lami = (double)(ck.cie[1] / 300.E-6f);
-            ni = (float)((double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(lami));
+            const double l2 = (double)(ck.cie[1] / 300.E-6f);
+            ni = (float)((double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(l2));
+            lami_stale = true;
           }
         } else {
           qi1d = 0.0f; ni1d = 0.0f; ri = R1; ni = R2; L_qi = false;
@@ -403,8 +416,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           L_qr = true;
           lamr = rain_lam(nr, rr);
           mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
-          if (mvd_r > 2.5E-3f) { mvd_r = 2.5E-3f; nr = nr_from_mvd(rr, mvd_r); }
-          else if (mvd_r < D0r * 0.75f) { mvd_r = D0r * 0.75f; nr = nr_from_mvd(rr, mvd_r); }
+          if (mvd_r > 2.5E-3f) { mvd_r = 2.5E-3f; nr = nr_from_mvd(rr, mvd_r); lamr_stale = true; }
+          else if (mvd_r < D0r * 0.75f) { mvd_r = D0r * 0.75f; nr = nr_from_mvd(rr, mvd_r); lamr_stale = true; }
         } else {
           qr1d = 0.0f; nr1d = 0.0f; rr = R1; nr = R2; L_qr = false;
         }
@@ -421,13 +434,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         float rhof = sqrtf(ck.rho_not / rho);
         float rhof2 = sqrtf(rhof);
         float qvs = rslf(pres, temp);
-        const float delQvs = fmaxf(0.0f, rslf(pres, 273.15f) - qv);
         const float qvsi = (tempc <= 0.0f) ? rsif(pres, temp) : qvs;
         float ssatw = qv / qvs - 1.f;
         float ssati = qv / qvsi - 1.f;
         if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
         if (fabsf(ssati) < EPSF) ssati = 0.0f;
-        float diffu = 2.11E-5f * pow_f(temp / 273.15f, 1.94f) * (101325.f / pres);
+        // diffu (M:1512) is read by vapour deposition / sublimation and melting of ice, snow and graupel only (M:1896,
+        // M:2126, M:2156, M:2166, M:2238, M:2255); rain evaporation evaluates its own (M:2888)
+        const bool ice_any = !iiwarm && (L_qi || L_qs || L_qg);
+        float diffu = 0.f;
+        if (ice_any) diffu = 2.11E-5f * pow_f(temp / 273.15f, 1.94f) * (101325.f / pres);
         float visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
                                       : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
         float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
@@ -456,13 +472,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           }
           // ---- S4, M:1633-1654 graupel intercept ------------------------------------------------
           if (temp >= 270.65f) warm_above_a = true;
-          { double nm = N0_min_a; graupel_n0(!warm_above_a && k > 0, L_qr, mvd_r, rg, nm, ilamg, N0_g); N0_min_a = nm; }
+          { double nm = N0_min_a; graupel_n0(!warm_above_a && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_a = nm; }
         }
-        // M:1661-1666 rain slope and intercept
-        lamr = rain_lam(nr, rr);
-        ilamr = (double)1.f / lamr;
-        mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
-        N0_r = (double)(nr * ck.org2) * lamr;                                  // lamr**cre(2), cre(2) = 1
+        // M:1661-1666 rain slope and intercept.  Without rain (rr = R1, nr = R2) every reader of lamr, ilamr, N0_r
+        // and mvd_r is switched off (L_qr at M:1676, M:1724, M:2880; rr >= r_r(1) at M:1818, M:1964, M:2028, M:2188)
+        if (L_qr) {
+          if (lamr_stale) { lamr = rain_lam(nr, rr); mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr); }
+          ilamr = (double)1.f / lamr;
+          N0_r = (double)(nr * ck.org2) * lamr;                                // lamr**cre(2), cre(2) = 1
+        }
 
         // ---- S5, M:1676-1742 warm rain -----------------------------------------------------------
         if (L_qr && mvd_r > D0r) {
@@ -535,19 +553,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           }
 
           // M:1884-1900 sublimation/deposition prefactor
-          const float otemp = 1.f / temp;
-          const float lsub = KP_LSUB, oRv = ck.oRv;
-          const float rvs = rho * qvsi;
-          const float rvs_p = rvs * otemp * (lsub * otemp * oRv - 1.f);
-          const float rvs_pp = rvs * (otemp * (lsub * otemp * oRv - 1.f) * otemp * (lsub * otemp * oRv - 1.f)
-                                      + (-2.f * lsub * otemp * otemp * otemp * oRv) + otemp * otemp);
-          const float gamsc = lsub * diffu / tcond * rvs_p;
-          float alphsc = 0.5f * (gamsc / (1.f + gamsc)) * (gamsc / (1.f + gamsc)) * rvs_pp / rvs_p * rvs / rvs_p;
-          alphsc = fmaxf(1.E-9f, alphsc);
-          float xsat = ssati;
-          if (fabsf(xsat) < 1.E-9f) xsat = 0.f;
-          const float t1_subl = 4.f * KP_PI * (1.0f - alphsc * xsat + 2.f * alphsc * alphsc * xsat * xsat
-                                               - 5.f * alphsc * alphsc * alphsc * xsat * xsat * xsat) / (1.f + gamsc);
+          // (rvs and t1_subl are read by the deposition / sublimation rates of ice, snow and graupel only)
+          float rvs = 0.f, t1_subl = 0.f;
+          if (ice_any) {
+            const float otemp = 1.f / temp;
+            const float lsub = KP_LSUB, oRv = ck.oRv;
+            rvs = rho * qvsi;
+            const float rvs_p = rvs * otemp * (lsub * otemp * oRv - 1.f);
+            const float rvs_pp = rvs * (otemp * (lsub * otemp * oRv - 1.f) * otemp * (lsub * otemp * oRv - 1.f)
+                                        + (-2.f * lsub * otemp * otemp * otemp * oRv) + otemp * otemp);
+            const float gamsc = lsub * diffu / tcond * rvs_p;
+            float alphsc = 0.5f * (gamsc / (1.f + gamsc)) * (gamsc / (1.f + gamsc)) * rvs_pp / rvs_p * rvs / rvs_p;
+            alphsc = fmaxf(1.E-9f, alphsc);
+            float xsat = ssati;
+            if (fabsf(xsat) < 1.E-9f) xsat = 0.f;
+            t1_subl = 4.f * KP_PI * (1.0f - alphsc * xsat + 2.f * alphsc * alphsc * xsat * xsat
+                                     - 5.f * alphsc * alphsc * alphsc * xsat * xsat * xsat) / (1.f + gamsc);
+          }
 
           // M:1903-1935 riming of snow and graupel
           if (L_qc && mvd_c > D0c) {
@@ -666,7 +688,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             // M:2116-2149 deposition / sublimation of cloud ice, ice -> snow
             float oxmi = 0.f, xDi = 0.f;
             if (L_qi) {
-              lami = ice_lam(ni, ri);
+              if (lami_stale) lami = ice_lam(ni, ri);
               ilami = (double)1.f / lami;
               xDi = (float)fmax((double)ck.D0i, (double)(3.f + 0.f + 1.f) * ilami);
               const float xmi = ck.am_i * cube_f(xDi);
@@ -752,6 +774,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             }
           } else {
             // ---- at or above freezing, M:2237-2281 ----------------------------------------------
+            float delQvs = 0.f;                                                // M:1508, read by the melting terms only
+            if (L_qs || L_qg) delQvs = fmaxf(0.0f, rslf(pres, 273.15f) - qv);
             if (L_qs) {
               prr_sml = (double)((tempc * tcond - KP_LVAP0 * diffu * delQvs)
                                  * (ck.t1_qs_me * smo1 + ck.t2_qs_me * rhof2 * vsc2 * smof));
@@ -935,17 +959,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           tempc = temp - 273.15f;
           qv = fmaxf(1.E-10f, qv1d + DT * qvt);
           rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
-          rhof = sqrtf(ck.rho_not / rho);
-          rhof2 = sqrtf(rhof);
           qvs = rslf(pres, temp);
           ssatw = qv / qvs - 1.f;
           if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
-          diffu = 2.11E-5f * pow_f(temp / 273.15f, 1.94f) * (101325.f / pres);
-          visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
-                                  : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
-          vsc2 = sqrtf(rho / visco);
+          // rhof, rhof2, diffu, visco, vsc2, tcond of M:2588-2600 are read by rain evaporation (which evaluates them
+          // again from the post-condensation state here, S12) and the fall speeds (rhof, S13) only
           lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
-          tcond = (5.69f + 0.0168f * tempc) * 1.0E-5f * 418.936f;
           ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
           lvt2 = lvap * lvap * ocp * ck.oRv * otemp * otemp;
 
@@ -958,9 +977,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             nr = fmaxf(R2, (nr1d + nrt * DT) * rho);
             L_qr = true;
             lamr = rain_lam(nr, rr);
+            lamr_stale = false;
             mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
-            if (mvd_r > 2.5E-3f) { mvd_r = 2.5E-3f; nr = nr_from_mvd(rr, mvd_r); }
-            else if (mvd_r < D0r * 0.75f) { mvd_r = D0r * 0.75f; nr = nr_from_mvd(rr, mvd_r); }
+            if (mvd_r > 2.5E-3f) { mvd_r = 2.5E-3f; nr = nr_from_mvd(rr, mvd_r); lamr_stale = true; }
+            else if (mvd_r < D0r * 0.75f) { mvd_r = D0r * 0.75f; nr = nr_from_mvd(rr, mvd_r); lamr_stale = true; }
           } else { rr = R1; nr = R2; L_qr = false; }
           if ((qs1d + qst * DT) > R1) { rs = (qs1d + qst * DT) * rho; L_qs = true; } else { rs = R1; L_qs = false; }
           if ((qg1d + qgt * DT) > R1) { rg = (qg1d + qgt * DT) * rho; L_qg = true; } else { rg = R1; L_qg = false; }
@@ -975,12 +995,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             // smod (M:2706-2717) is not read again by any live code
           }
           if (temp >= 270.65f) warm_above_b = true;
-          { double nm = N0_min_b; graupel_n0(!warm_above_b && k > 0, L_qr, mvd_r, rg, nm, ilamg, N0_g); N0_min_b = nm; }
+          { double nm = N0_min_b; graupel_n0(!warm_above_b && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_b = nm; }
         }
-        lamr = rain_lam(nr, rr);
-        ilamr = (double)1.f / lamr;
-        mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
-        N0_r = (double)(nr * ck.org2) * lamr;
+        if (L_qr) {                                                             // M:2750-2755, as at M:1661
+          if (lamr_stale) { lamr = rain_lam(nr, rr); mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr); lamr_stale = false; }
+          ilamr = (double)1.f / lamr;
+          N0_r = (double)(nr * ck.org2) * lamr;
+        }
 
         LOCKBAR(4);
         // ---- S11, M:2780-2874 cloud condensation / evaporation ---------------------------------------
@@ -1043,11 +1064,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           const float xsat = fminf(-1.E-9f, ssatw);
           const float t1_evap = 2.f * KP_PI * (1.0f - alphsc * xsat + 2.f * alphsc * alphsc * xsat * xsat
                                                - 5.f * alphsc * alphsc * alphsc * xsat * xsat * xsat) / (1.f + gamsc);
-          lamr = (double)1.f / ilamr;
+          const double lamr_ev = (double)1.f / ilamr;
           if (qv / qvs < 0.95f && rr * orho <= 1.E-8f) {
             prv_rev = (double)(rr * orho * odts);
           } else {
-            const double lh = lamr + (double)(0.5f * KP_FV_R);
+            const double lh = lamr_ev + (double)(0.5f * KP_FV_R);
             prv_rev = (double)(t1_evap * diffu * (-ssatw)) * N0_r * (double)rvs
                       * ((double)ck.t1_qr_ev * sq_d(ilamr)                                     // ilamr**cre(10), = 2
                          + (double)(ck.t2_qr_ev * vsc2 * rhof2) * (1.0 / (lh * lh * lh)));      // **(-cre(11)), = 3
@@ -1066,6 +1087,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           rr = fmaxf(R1, (qr1d + DT * qrt) * rho);
           qv = fmaxf(1.E-10f, qv1d + DT * qvt);
           nr = fmaxf(R2, (nr1d + DT * nrt) * rho);
+          lamr_stale = true;
           temp = t1d + DT * tt;
           rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
         }
@@ -1087,7 +1109,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         rhof = sqrtf(ck.rho_not / rho);
         float v_r, v_nr, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;
         if (rr > R1) {
-          lamr = rain_lam(nr, rr);
+          if (!L_qr || lamr_stale) lamr = rain_lam(nr, rr);                   // M:3227: same nr, rr as at M:2750 otherwise
           const double lf = lamr + (double)KP_FV_R;
           const double l2 = lamr * lamr, lf2 = lf * lf;
           // lamr**cre(3) * (lamr+fv_r)**(-cre(6)), cre(3) = 4, cre(6) = 5
