@@ -20,6 +20,7 @@
 using namespace kidmp;
 
 struct kidmp_handle {
+  int nsm = 148;
   kidmp_config cfg;
   std::string cache_path;
   int device = 0;
@@ -246,6 +247,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   a.coldiag = h->d_coldiag;
   a.diag_partial = h->d_partial;
   a.rates = h->d_rates;
+  a.nsm = h->nsm;
   k_classify<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
   k_list_scan<<<1, 1024, 0, s>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
   k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
@@ -258,11 +260,13 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     KERNEL<<<(GRID), (THREADS), (THREADS) * 116, s>>>(a);                                                          \
   } while (0)
   // measured alternatives (profiles/r01_ncu_step_kernels.md): 16 / 20 / 28 / 32 warps, 2x12 and 3x8 warps per SM, other barrier sets
-  if (a.rates) LAUNCH_K1((k_column_step<16, 1, 11, true>), (unsigned)((ngroups + 15) / 16), 512);   // with the 36 save_dg rates
-  else if (warps >= 24) LAUNCH_K1((k_column_step<24, 1, 11, false>), (unsigned)((ngroups + 23) / 24), 768);
-  else if (warps >= 16) LAUNCH_K1((k_column_step<16, 1, 11, false>), (unsigned)((ngroups + 15) / 16), 512);
-  else if (warps >= 8) LAUNCH_K1((k_column_step<8, 2, 11, false>), (unsigned)((ngroups + 7) / 8), 256);   // two 8-warp blocks per SM
-  else LAUNCH_K1((k_column_step<1, 12, 0, false>), (unsigned)ngroups, 32);
+  // grid: worst case (every column cloudy), rounded up to whole waves of `minb` blocks per SM (see the kernel)
+  auto grid = [&](int w, int minb) { const long wave = (long)h->nsm * minb; return (unsigned)(((ngroups + w - 1) / w + wave - 1) / wave * wave); };
+  if (a.rates) LAUNCH_K1((k_column_step<16, 1, 11, true>), grid(16, 1), 512);   // with the 36 save_dg rates
+  else if (warps >= 24) LAUNCH_K1((k_column_step<24, 1, 11, false>), grid(24, 1), 768);
+  else if (warps >= 16) LAUNCH_K1((k_column_step<16, 1, 11, false>), grid(16, 1), 512);
+  else if (warps >= 8) LAUNCH_K1((k_column_step<8, 2, 11, false>), grid(8, 2), 256);   // two 8-warp blocks per SM
+  else LAUNCH_K1((k_column_step<1, 12, 0, false>), grid(1, 12), 32);
   k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
   k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
   k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
@@ -342,6 +346,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(1); }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, h->device);
+  h->nsm = prop.multiProcessorCount;
   if (prop.major < 10) { fail(h, "kidmp_init: built for sm_100a, device is sm_%d%d", prop.major, prop.minor); return bail(1); }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||

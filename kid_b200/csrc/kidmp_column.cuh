@@ -222,11 +222,19 @@ __global__ void __launch_bounds__(256) k_list_fill(const unsigned* __restrict__ 
 template <int WARPS, int MINB, int BARS, bool RATES>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
   const int count = *a.work_count;                     // cloudy columns, compacted: every warp but the last is full
-  const int first = blockIdx.x * WARPS * 32;
-  if (first >= count) return;
-  const int wfirst = first + (threadIdx.x & ~31);
-  const int lock_threads = min(WARPS, (count - first + 31) / 32) * 32;
-  if (wfirst >= count) return;
+  // The warps of the list are dealt evenly to a whole number of waves of blocks (one wave = MINB blocks on each SM):
+  // a block runs for milliseconds, so a last wave that fills only part of the SMs would leave the others idle for
+  // that long.  Blocks get WARPS or fewer warps; surplus blocks and warps leave at once.
+  const int total_warps = (count + 31) >> 5;
+  int nblocks = (total_warps + WARPS - 1) / WARPS;
+  const int wave = a.nsm * MINB;
+  nblocks = min((int)gridDim.x, (nblocks + wave - 1) / wave * wave);
+  if ((int)blockIdx.x >= nblocks) return;
+  const int w0 = (int)((long)blockIdx.x * total_warps / nblocks), w1 = (int)((long)(blockIdx.x + 1) * total_warps / nblocks);
+  const int mywarp = threadIdx.x >> 5;
+  if (mywarp >= w1 - w0) return;
+  const int lock_threads = (w1 - w0) * 32;
+  const int wfirst = (w0 + mywarp) * 32;
   const int slot = wfirst + (threadIdx.x & 31);
   const bool active = slot < count;
   // lanes past the end of the list shadow the warp's first column: same branches, nothing stored, and the warp

@@ -124,6 +124,7 @@ struct StepArgs {
   float* rates;                // optional [36][nz][ncol]
   double* coldiag;             // [2][ncol] liquid / ice water path of each cloudy column
   double* diag_partial;        // [DIAG_BLOCKS][KIDMP_NDIAG] block sums of k_diag_columns
+  int nsm;                     // SMs of the device: the physics kernel spreads its warps over whole waves of blocks
 };
 
 // device tables (kidmp_tables.cuh fills them)
