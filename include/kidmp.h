@@ -118,6 +118,25 @@ typedef struct kidmp_kid_columns {
 } kidmp_kid_columns;
 int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, float p0, float r_on_cp);
 
+/* The WRF / MPAS-facing entry: what mp_gt_driver (M:806-1143) does for a tile of ni x nj columns of nk levels.
+ * 3-D arrays are WRF's (i,k,j) order, a[i + ni*(k + nk*j)]; 2-D arrays are (i,j), a[i + ni*j].  INOUT: the nine
+ * prognostic fields with potential temperature `th` (T = th*pii goes into the step, th = T/pii comes back, M:941,
+ * M:1022); IN: pii (Exner function), p, dz (per-column layer depths, M:944).  RAINNC / SNOWNC / GRAUPELNC are
+ * accumulated, RAINNCV / SNOWNCV / GRAUPELNCV / SR overwritten (M:991-1003); the snow and graupel pairs may be NULL
+ * (OPTIONAL in the reference).  re_cloud, re_ice, re_snow receive the effective radii of calc_effectRad (M:4834-4935)
+ * clamped as at M:1118-1122 when all three are non-NULL (has_reqc, has_reqi, has_reqs), else they are not touched.
+ * w, nc, nwfa, nifa, nwfa2d, refl_10cm and the WRF_CHEM arguments are not part of this ABI: they are only read or
+ * written under is_aerosol_aware / WRF_CHEM / do_radar_ref, none of which exists in the KiD build of the scheme. */
+typedef struct kidmp_wrf_fields {
+  int ni, nk, nj;
+  float *qv, *qc, *qr, *qi, *qs, *qg, *ni_, *nr, *th;    /* (i,k,j) INOUT, argument order of M:806 (ni_ = ni) */
+  const float *pii, *p, *dz;                               /* (i,k,j) IN                                      */
+  float *rainnc, *rainncv, *sr;                            /* (i,j)                                           */
+  float *snownc, *snowncv, *graupelnc, *graupelncv;        /* (i,j), optional                                 */
+  float *re_cloud, *re_ice, *re_snow;                      /* (i,k,j), optional                               */
+} kidmp_wrf_fields;
+int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in);
+
 /* bookkeeping for benchmarks */
 long kidmp_gpu_launches(const kidmp_handle* h);         /* kernels launched so far          */
 int kidmp_sync(kidmp_handle* h);                        /* wait for the handle's stream     */

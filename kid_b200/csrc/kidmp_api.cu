@@ -16,6 +16,7 @@
 #include "kidmp_tables.cuh"
 #include "kidmp_column.cuh"
 #include "kidmp_kid.cuh"
+#include "kidmp_wrf.cuh"
 
 using namespace kidmp;
 
@@ -733,6 +734,80 @@ int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
   CK(h, cudaMemcpyAsync(out, h->d_diag, KIDMP_NDIAG * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemsetAsync(h->d_diag, 0, KIDMP_NDIAG * 8, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// mp_gt_driver, M:806-1143 (see kidmp_wrf.cuh)
+int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in) {
+  if (!h) return 1;
+  if (!w) return fail(h, "mp_gt_driver: null argument");
+  if (w->ni < 1 || w->nj < 1 || w->nk < 2) return fail(h, "mp_gt_driver: bad dimensions %d x %d x %d", w->ni, w->nk, w->nj);
+  float* const io[9] = {w->qv, w->qc, w->qi, w->qr, w->qs, w->qg, w->ni_, w->nr, w->th};      // state-field order
+  for (int q = 0; q < 9; ++q) if (!io[q]) return fail(h, "mp_gt_driver: null field %d", q);
+  if (!w->pii || !w->p || !w->dz || !w->rainnc || !w->rainncv || !w->sr) return fail(h, "mp_gt_driver: null array");
+  if (!(dt_in > 0.f)) return fail(h, "mp_gt_driver: dt must be positive");
+  const bool radii = w->re_cloud && w->re_ice && w->re_snow;
+  const long ncol = (long)w->ni * w->nj;
+  if (kidmp_state_alloc(h, ncol, w->nk)) return 1;
+  cudaSetDevice(h->device);
+  const size_t n = (size_t)ncol * w->nk, n2 = (size_t)ncol;
+  // device staging: 12 three-dimensional inputs, the per-column dz in step layout, 3 radii, 7 two-dimensional arrays
+  const size_t dfloats = (12 + 1 + 3) * n + 7 * n2;
+  if (h->kid_floats < dfloats) {
+    if (h->d_kid) cudaFree(h->d_kid);
+    h->d_kid = nullptr; h->kid_floats = 0;
+    CK(h, cudaMalloc((void**)&h->d_kid, dfloats * 4));
+    h->kid_floats = dfloats;
+  }
+  const size_t hfloats = 12 * n + 7 * n2;            // one pinned buffer, one copy each way (as kidmp_kid_interface)
+  if (h->h_kid_floats < hfloats) {
+    if (h->h_kid) cudaFreeHost(h->h_kid);
+    h->h_kid = nullptr; h->h_kid_floats = 0;
+    CK(h, cudaHostAlloc((void**)&h->h_kid, hfloats * 4, cudaHostAllocDefault));
+    h->h_kid_floats = hfloats;
+  }
+  WrfArgs a{};
+  a.ni = w->ni; a.nk = w->nk; a.nj = w->nj;
+  const float* const in3[12] = {w->qv, w->qc, w->qi, w->qr, w->qs, w->qg, w->ni_, w->nr, w->th, w->pii, w->p, w->dz};
+  for (int q = 0; q < 12; ++q) memcpy(h->h_kid + n * q, in3[q], n * 4);
+  for (int q = 0; q < 9; ++q) a.a3[q] = h->d_kid + n * q;
+  a.pii = h->d_kid + n * 9; a.p3 = h->d_kid + n * 10; a.dz3 = h->d_kid + n * 11;
+  a.dz_col = h->d_kid + n * 12;
+  float* const d_re = h->d_kid + n * 13;
+  if (radii) { a.re_cloud = d_re; a.re_ice = d_re + n; a.re_snow = d_re + 2 * n; }
+  float* const d_2d = h->d_kid + n * 16;
+  float* const h_2d = h->h_kid + n * 12;
+  float* const acc[7] = {w->rainnc, w->rainncv, w->sr, w->snownc, w->snowncv, w->graupelnc, w->graupelncv};
+  for (int q = 0; q < 7; ++q) if (acc[q]) memcpy(h_2d + n2 * q, acc[q], n2 * 4);
+  a.rainnc = d_2d; a.rainncv = d_2d + n2; a.sr = d_2d + 2 * n2;
+  if (w->snownc && w->snowncv) { a.snownc = d_2d + 3 * n2; a.snowncv = d_2d + 4 * n2; }
+  if (w->graupelnc && w->graupelncv) { a.graupelnc = d_2d + 5 * n2; a.graupelncv = d_2d + 6 * n2; }
+  for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = field_ptr(h, q);
+  a.p = field_ptr(h, KIDMP_NFIELDS);
+  a.ppt = h->d_ppt;
+  CK(h, cudaMemcpyAsync(h->d_kid, h->h_kid, 12 * n * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(d_2d, h_2d, 7 * n2 * 4, cudaMemcpyHostToDevice, h->stream));
+  const dim3 b(128), g((unsigned)((w->ni + 127) / 128), (unsigned)w->nk, (unsigned)w->nj);
+  k_wrf_gather<<<g, b, 0, h->stream>>>(a);
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  StepArgs sa = resident_args(h, dt_in);
+  sa.dz_col = a.dz_col;
+  if (launch_step(h, sa, h->stream)) return 1;
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  k_wrf_scatter<<<g, b, 0, h->stream>>>(a, h->kc.Nt_c);
+  k_wrf_accumulate<<<(unsigned)((ncol + 255) / 256), 256, 0, h->stream>>>(a);
+  h->launches += 3;
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpyAsync(h->h_kid, h->d_kid, 9 * n * 4, cudaMemcpyDeviceToHost, h->stream));
+  float* const h_re = h->h_kid + n * 9;               // pii, p, dz slots of the pinned buffer are free again
+  if (radii) CK(h, cudaMemcpyAsync(h_re, d_re, 3 * n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(h_2d, d_2d, 7 * n2 * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  for (int q = 0; q < 9; ++q) memcpy(io[q], h->h_kid + n * q, n * 4);
+  if (radii) { memcpy(w->re_cloud, h_re, n * 4); memcpy(w->re_ice, h_re + n, n * 4); memcpy(w->re_snow, h_re + 2 * n, n * 4); }
+  memcpy(w->rainnc, h_2d, n2 * 4); memcpy(w->rainncv, h_2d + n2, n2 * 4); memcpy(w->sr, h_2d + 2 * n2, n2 * 4);
+  if (a.snownc) { memcpy(w->snownc, h_2d + 3 * n2, n2 * 4); memcpy(w->snowncv, h_2d + 4 * n2, n2 * 4); }
+  if (a.graupelnc) { memcpy(w->graupelnc, h_2d + 5 * n2, n2 * 4); memcpy(w->graupelncv, h_2d + 6 * n2, n2 * 4); }
   return 0;
 }
 

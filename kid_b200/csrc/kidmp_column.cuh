@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         const float t1d = Gt[o], qv1d = Gqv[o], pres = Gp[o];
         float qc1d = Gqc[o], qi1d = Gqi[o], qr1d = Gqr[o], qs1d = Gqs[o], qg1d = Gqg[o];
         float ni1d = Gni[o], nr1d = Gnr[o];
-        const float dzq = a.dz[k];
+        const float dzq = a.dz_col ? a.dz_col[o + col] : a.dz[k];
         // U1: nc1d as the WRF driver sets it when the scheme is not aerosol aware, M:957-964
         float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));
 
@@ -1241,7 +1241,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
 // S15/S16 and the output stores in one top-down sweep (the common nstep = 1 case is that sweep only).
 __device__ __forceinline__ void sed_substeps(float* __restrict__ r, float* __restrict__ rten, const float* __restrict__ v,
                                              float* __restrict__ n, float* __restrict__ nten, const float* __restrict__ vn,
-                                             const float* __restrict__ rhoa, const float* __restrict__ dz, int nz, long ncol,
+                                             const float* __restrict__ rhoa, const float* __restrict__ dz, long dzs, int nz, long ncol,
                                              int nsub, int ksed, float onstep, float DT, bool on, float nfloor, float& ppt) {
   for (int it = 0; it < nsub; ++it) {
     float sr_up = 0.f, sn_up = 0.f, sr_k = 0.f, r0 = 0.f;
@@ -1250,7 +1250,7 @@ __device__ __forceinline__ void sed_substeps(float* __restrict__ r, float* __res
       const long o = (long)k * ncol;
       const float rk = r[o];
       const float sr = on ? v[o] * rk : 0.f;
-      const float odzq = 1.f / dz[k], orho = 1.f / rhoa[o];
+      const float odzq = 1.f / dz[k * dzs], orho = 1.f / rhoa[o];
       float nk = 0.f, sn = 0.f;
       if (n) { nk = n[o]; sn = on ? vn[o] * nk : 0.f; }
       if (k == nz - 1) {
@@ -1299,14 +1299,17 @@ __global__ void __launch_bounds__(32) k_sediment(StepArgs a) {
       const long ss = (long)nz * ncol;
       float* sc = a.scratch + col;
       const float* rhoa = sc + SC_RHO * ss;
+      // layer depths: one vector shared by all columns (KiD) or this column's own (WRF entry)
+      const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;
+      const long dzs = a.dz_col ? ncol : 1;
       // all but the last sub-step (rain is never gated by l_sediment, U6; the cloud-water stub M:3414-3425 is a no-op, U2)
       if (n_r > 1) sed_substeps(sc + SC_RR * ss, sc + SC_QRTEN * ss, sc + SC_VTR * ss, sc + SC_NR * ss, sc + SC_NRTEN * ss,
-                                sc + SC_VTNR * ss, rhoa, a.dz, nz, ncol, n_r - 1, ksed_r, on_r, DT, true, KP_R2, ppt_r);
+                                sc + SC_VTNR * ss, rhoa, dzp, dzs, nz, ncol, n_r - 1, ksed_r, on_r, DT, true, KP_R2, ppt_r);
       if (n_i > 1) sed_substeps(sc + SC_RI * ss, sc + SC_QITEN * ss, sc + SC_VTI * ss, sc + SC_NI * ss, sc + SC_NITEN * ss,
-                                sc + SC_VTNI * ss, rhoa, a.dz, nz, ncol, n_i - 1, ksed_i, on_i, DT, sedi, KP_R2, ppt_i);
-      if (n_s > 1) sed_substeps(sc + SC_RS * ss, sc + SC_QSTEN * ss, sc + SC_VTS * ss, nullptr, nullptr, nullptr, rhoa, a.dz,
+                                sc + SC_VTNI * ss, rhoa, dzp, dzs, nz, ncol, n_i - 1, ksed_i, on_i, DT, sedi, KP_R2, ppt_i);
+      if (n_s > 1) sed_substeps(sc + SC_RS * ss, sc + SC_QSTEN * ss, sc + SC_VTS * ss, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
                                 nz, ncol, n_s - 1, ksed_s, on_s, DT, sedi, 0.f, ppt_s);
-      if (n_g > 1) sed_substeps(sc + SC_RG * ss, sc + SC_QGTEN * ss, sc + SC_VTG * ss, nullptr, nullptr, nullptr, rhoa, a.dz,
+      if (n_g > 1) sed_substeps(sc + SC_RG * ss, sc + SC_QGTEN * ss, sc + SC_VTG * ss, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
                                 nz, ncol, n_g - 1, ksed_g, on_g, DT, sedi, 0.f, ppt_g);
 
       // last sub-step of every species + S15 + S16, one top-down sweep
@@ -1326,7 +1329,7 @@ __global__ void __launch_bounds__(32) k_sediment(StepArgs a) {
         float nrt = q[SC_NRTEN * ss], nct = q[SC_NCTEN * ss];
         const float rho = q[SC_RHO * ss], s15 = q[SC_S15 * ss];
         const float rr = q[SC_RR * ss], nr = q[SC_NR * ss], ri = q[SC_RI * ss], ni = q[SC_NI * ss], rs = q[SC_RS * ss], rg = q[SC_RG * ss];
-        const float odzq = 1.f / a.dz[k], orho = 1.f / rho;
+        const float odzq = 1.f / dzp[k * dzs], orho = 1.f / rho;
         const float sr = q[SC_VTR * ss] * rr, snr = q[SC_VTNR * ss] * nr;
         const float si = sedi ? q[SC_VTI * ss] * ri : 0.f, sni = sedi ? q[SC_VTNI * ss] * ni : 0.f;
         const float ssn = sedi ? q[SC_VTS * ss] * rs : 0.f, sg = sedi ? q[SC_VTG * ss] * rg : 0.f;
@@ -1426,8 +1429,8 @@ __global__ void __launch_bounds__(32) k_sediment(StepArgs a) {
         Gni[o] = ni1d; Gnr[o] = nr1d;
         // domain diagnostics: liquid / ice water paths of the new state
         const float rho_new = 0.622f * pres / (KP_R * t1d * (qv1d + 0.622f));
-        lwp += (double)((qc1d + qr1d) * rho_new * a.dz[k]);
-        iwp += (double)((qi1d + qs1d + qg1d) * rho_new * a.dz[k]);
+        lwp += (double)((qc1d + qr1d) * rho_new * dzp[k * dzs]);
+        iwp += (double)((qi1d + qs1d + qg1d) * rho_new * dzp[k * dzs]);
       }
     }
     // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)

@@ -113,7 +113,8 @@ struct StepArgs {
   float dt;
   float* f[KIDMP_NFIELDS];     // qv qc qi qr qs qg ni nr t, [nz][ncol]
   const float* p;              // [nz][ncol]
-  const float* dz;             // [nz]
+  const float* dz;             // [nz] layer depths shared by all columns (KiD, I:63) ...
+  const float* dz_col;         // ... or [nz][ncol] per column (WRF's dz(i,k,j), M:944); NULL when dz is used
   float* ppt;                  // [4][ncol]
   float* scratch;              // [SC_N][nz][ncol] hand-off, touched for cloudy columns only
   int* colint;                 // [8][ncol] substep counts / top sedimenting level per species; [0] = -1: clear sky

@@ -70,6 +70,14 @@ class KidColumns(C.Structure):
         ("dtheta_mphys", _fp), ("dqv_mphys", _fp), ("dhyd_mphys", _fp * 7), ("ppt", _fp)]
 
 
+class WrfFields(C.Structure):
+    """kidmp_wrf_fields of include/kidmp.h."""
+    _fields_ = [("ni", C.c_int), ("nk", C.c_int), ("nj", C.c_int)] + [(n, _fp) for n in (
+        "qv", "qc", "qr", "qi", "qs", "qg", "ni_", "nr", "th", "pii", "p", "dz", "rainnc", "rainncv", "sr",
+        "snownc", "snowncv", "graupelnc", "graupelncv", "re_cloud", "re_ice", "re_snow")]
+
+
+SYMBOLS["kidmp_mp_gt_driver"] = (C.c_int, [C.c_void_p, C.POINTER(WrfFields), C.c_float])
 SYMBOLS["kidmp_kid_interface"] = (C.c_int, [C.c_void_p, C.POINTER(KidColumns), C.c_float, C.c_float, C.c_float])
 HYD_PLANES = ("qc", "qr", "nr", "qi", "ni", "qs", "qg")
 
@@ -228,6 +236,37 @@ class Thompson:
         p, dz, ppt = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ck(self._L.kidmp_device_state(self.h, f, C.byref(p), C.byref(dz), C.byref(ppt)))
         return [int(x) for x in f], int(p.value), int(dz.value), int(ppt.value)
+
+    def mp_gt_driver(self, dt, f3, pii, p, dz, acc, radii=True):
+        """mp_gt_driver (M:806-1143) through kidmp_mp_gt_driver.  f3: dict qv qc qr qi qs qg ni nr th of (nj, nk, ni)
+        float32 arrays (C order = WRF's (i,k,j) Fortran order), updated in place; pii, p, dz the same shape; acc: dict
+        rainnc rainncv sr [snownc snowncv graupelnc graupelncv] of (nj, ni) arrays, updated in place.
+        Returns dict re_cloud re_ice re_snow (empty when radii is False)."""
+        nj, nk, ni = f3["qv"].shape
+        w = WrfFields()
+        w.ni, w.nk, w.nj = ni, nk, nj
+        keep = []
+
+        def ptr(a, shape):
+            a = _f32c(a)
+            if a.shape != shape:
+                raise ValueError("array shape %r, expected %r" % (a.shape, shape))
+            keep.append(a)
+            return a.ctypes.data_as(_fp)
+        for name, key in (("qv", "qv"), ("qc", "qc"), ("qr", "qr"), ("qi", "qi"), ("qs", "qs"), ("qg", "qg"),
+                          ("ni_", "ni"), ("nr", "nr"), ("th", "th")):
+            setattr(w, name, ptr(f3[key], (nj, nk, ni)))
+        w.pii, w.p, w.dz = ptr(pii, (nj, nk, ni)), ptr(p, (nj, nk, ni)), ptr(dz, (nj, nk, ni))
+        for name in ("rainnc", "rainncv", "sr"):
+            setattr(w, name, ptr(acc[name], (nj, ni)))
+        for name in ("snownc", "snowncv", "graupelnc", "graupelncv"):
+            if acc.get(name) is not None:
+                setattr(w, name, ptr(acc[name], (nj, ni)))
+        re = {k: np.zeros((nj, nk, ni), np.float32) for k in ("re_cloud", "re_ice", "re_snow")} if radii else {}
+        for name, a in re.items():
+            setattr(w, name, ptr(a, (nj, nk, ni)))
+        self._ck(self._L.kidmp_mp_gt_driver(self.h, C.byref(w), float(dt)))
+        return re
 
     def kid_interface(self, kid, dt, p0=1.0e5, r_on_cp=287.05 / 1005.0):
         """mphys_thompson09_interfacen (I:28-246) without save_dg.  kid: dict of float32 (nx, nz) arrays 'theta',

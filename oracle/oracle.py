@@ -59,6 +59,10 @@ def lib():
             getattr(L, n).argtypes = [C.c_float]
         L.kor_gammp.restype = C.c_float
         L.kor_gammp.argtypes = [C.c_float, C.c_float]
+        L.kor_calc_effect_rad.restype = C.c_int
+        L.kor_calc_effect_rad.argtypes = [C.c_void_p, C.c_int] + [_fp] * 11
+        L.kor_mp_gt_driver.restype = C.c_int
+        L.kor_mp_gt_driver.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float] + [_fp] * 22
         L.kor_decade_index.restype = C.c_int
         L.kor_decade_index.argtypes = [C.c_float, C.c_int, C.c_int]
         _lib = L
@@ -123,6 +127,37 @@ class Oracle:
         if name in TABLE_SHAPES:
             out = out.reshape(TABLE_SHAPES[name], order="F")
         return out
+
+    def effect_rad(self, t, p, qv, qc, qi, ni, qs):
+        """calc_effectRad (M:4834-4935) for one column preset as at M:1112-1114; returns (re_qc, re_qi, re_qs)."""
+        nz = len(t)
+        arrs = [np.ascontiguousarray(v, dtype=np.float32) for v in (t, p, qv, qc, qi, ni, qs)]
+        t, p, qv, qc, qi, ni, qs = arrs
+        rc, ri, rs = (np.full(nz, v, np.float32) for v in (2.49e-6, 4.99e-6, 9.99e-6))
+        P = lambda a: a.ctypes.data_as(_fp)
+        r = lib().kor_calc_effect_rad(self.h, nz, P(t), P(p), P(qv), P(qc), None, P(qi), P(ni), P(qs), P(rc), P(ri), P(rs))
+        if r:
+            raise RuntimeError("kor_calc_effect_rad failed")
+        return rc, ri, rs
+
+    def mp_gt_driver(self, dt, f3, pii, p, dz, acc, radii=True):
+        """mp_gt_driver (M:806-1143).  f3: dict qv qc qr qi qs qg ni nr th of (nj, nk, ni) float32 arrays (C order =
+        WRF's (i,k,j) Fortran order), updated in place; acc: dict rainnc rainncv sr [snownc snowncv graupelnc
+        graupelncv] of (nj, ni) arrays, updated in place.  Returns dict re_cloud re_ice re_snow (or {})."""
+        nj, nk, ni = f3["qv"].shape
+        P = lambda a: a.ctypes.data_as(_fp) if a is not None else None
+        for k in ("qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr", "th"):
+            assert f3[k].dtype == np.float32 and f3[k].flags.c_contiguous and f3[k].shape == (nj, nk, ni)
+        re = {k: np.zeros((nj, nk, ni), np.float32) for k in ("re_cloud", "re_ice", "re_snow")} if radii else {}
+        r = lib().kor_mp_gt_driver(
+            self.h, ni, nk, nj, float(dt), *[P(f3[k]) for k in ("qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr", "th")],
+            P(np.ascontiguousarray(pii, np.float32)), P(np.ascontiguousarray(p, np.float32)),
+            P(np.ascontiguousarray(dz, np.float32)), P(acc["rainnc"]), P(acc["rainncv"]), P(acc.get("snownc")),
+            P(acc.get("snowncv")), P(acc.get("graupelnc")), P(acc.get("graupelncv")), P(acc["sr"]),
+            P(re.get("re_cloud")), P(re.get("re_ice")), P(re.get("re_snow")))
+        if r:
+            raise RuntimeError("kor_mp_gt_driver failed")
+        return re
 
     def column(self, dt, qv, qc, qi, qr, qs, qg, ni, nr, t, p, dz, nc=None, ppt=None, want_rates=False):
         """One mp_thompson call.  Arrays of nz (index 0 = lowest level); returns dict of new arrays."""

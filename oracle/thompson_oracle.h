@@ -49,6 +49,18 @@ int kor_kid_interface(const kor_handle*, long nx, int nz, float dt, float p0, fl
                       const float* const* dhyd_div, float* dtheta_mphys, float* dqv_mphys,
                       float* const* dhyd_mphys, float* ppt);
 
+// M:4834-4935 calc_effectRad, one column; re_* INOUT (preset by the caller, M:1112-1114); nc1d may be NULL.
+int kor_calc_effect_rad(const kor_handle*, int nz, const float* t1d, const float* p1d, const float* qv1d,
+                        const float* qc1d, const float* nc1d, const float* qi1d, const float* ni1d, const float* qs1d,
+                        float* re_qc1d, float* re_qi1d, float* re_qs1d);
+
+// M:806-1143 mp_gt_driver over ni x nj columns; 3-D arrays a[i + ni*(k + nk*j)], 2-D a[i + ni*j]; the snow / graupel
+// accumulators and the three radii may be NULL.
+int kor_mp_gt_driver(const kor_handle*, int ni, int nk, int nj, float dt, float* qv, float* qc, float* qr, float* qi,
+                     float* qs, float* qg, float* ni_, float* nr, float* th, const float* pii, const float* p,
+                     const float* dz, float* rainnc, float* rainncv, float* snownc, float* snowncv, float* graupelnc,
+                     float* graupelncv, float* sr, float* re_cloud, float* re_ice, float* re_snow);
+
 const char* kor_rate_names(void);   // comma-separated, 36 names (M:2963-3120)
 
 // M:4598-4717 helpers, exposed for known-answer tests

@@ -519,3 +519,65 @@ def test_kid_text_cache_roundtrip(gpu_mixed, tmp_path):
                  "tnr_racs1", "tnr_sacr2"):
         assert np.array_equal(t2.get(name), gpu_mixed.get(name)), name
     t2.close()
+
+
+# ---- the WRF / MPAS-shaped entry, mp_gt_driver (M:806-1143) + calc_effectRad (M:4834-4935) ----------------------
+def _wrf_case(ni, nk, nj, seed=3):
+    """(i,k,j) arrays from the synthetic cloudy domain: theta and Exner function instead of T, layer depths that
+    differ from column to column (terrain-following levels), accumulators with a history."""
+    rng = np.random.default_rng(seed)
+    st, p, dz = _domain(ni * nj, nz=nk, coherent=False, cloudy_fraction=0.6)
+    to3 = lambda a: np.ascontiguousarray(a.reshape(nk, nj, ni).transpose(1, 0, 2))     # [k][col] -> (nj, nk, ni)
+    f3 = {k: to3(st[k]) for k in ("qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr")}
+    p3 = to3(p)
+    pii = ((p3 / 1.0e5) ** (287.04 / 1004.0)).astype(np.float32)
+    f3["th"] = (to3(st["t"]) / pii).astype(np.float32)
+    stretch = (0.8 + 0.4 * rng.random((nj, 1, ni))).astype(np.float32)
+    dz3 = np.ascontiguousarray(np.broadcast_to(dz.reshape(1, nk, 1), (nj, nk, ni)) * stretch).astype(np.float32)
+    acc = {k: (rng.random((nj, ni)) * 3.0).astype(np.float32) for k in
+           ("rainnc", "rainncv", "sr", "snownc", "snowncv", "graupelnc", "graupelncv")}
+    return f3, pii, p3, dz3, acc
+
+
+def test_wrf_driver_entry(gpu_mixed, oracle_mixed):
+    ni, nk, nj = 50, 60, 9
+    f3, pii, p3, dz3, acc = _wrf_case(ni, nk, nj)
+    a3 = {k: v.copy() for k, v in f3.items()}
+    b3 = {k: v.copy() for k, v in f3.items()}
+    aa = {k: v.copy() for k, v in acc.items()}
+    ab = {k: v.copy() for k, v in acc.items()}
+    ra = gpu_mixed.mp_gt_driver(20.0, a3, pii, p3, dz3, aa)
+    rb = oracle_mixed.mp_gt_driver(20.0, b3, pii, p3, dz3, ab)
+    flat = lambda d: {k: v.reshape(-1) for k, v in d.items()}
+    names = ("qv", "qc", "qi", "qr", "qs", "qg", "ni", "nr", "th")
+    assert_parity(flat(a3), flat(b3), fields=names, what="mp_gt_driver state")
+    for k in ("rainnc", "rainncv", "sr", "snownc", "snowncv", "graupelnc", "graupelncv"):
+        np.testing.assert_allclose(aa[k], ab[k], rtol=1e-5, atol=1e-9, err_msg=k)
+    assert (aa["rainncv"] > 0).any()                                      # (no frozen precipitation reaches this 303 K surface)
+    assert (aa["rainnc"] >= acc["rainnc"]).all()                         # accumulated, not overwritten
+    # radii: inside the clamps of M:1118-1122, equal to the oracle's, and not all at the presets
+    lim = {"re_cloud": (2.49e-6, 50e-6), "re_ice": (4.99e-6, 125e-6), "re_snow": (9.99e-6, 999e-6)}
+    for k, (lo, hi) in lim.items():
+        assert ra[k].min() >= np.float32(lo) and ra[k].max() <= np.float32(hi), k
+        assert (ra[k] > np.float32(lo) * 1.01).any(), k
+        # where the state agrees to the bit the radius must too (up to the f32 rounding of one power)
+        np.testing.assert_allclose(ra[k], rb[k], rtol=2e-5, err_msg=k)
+    # optional arguments absent: snow / graupel accumulators and radii are simply not produced
+    a4 = {k: v.copy() for k, v in f3.items()}
+    a_min = {k: acc[k].copy() for k in ("rainnc", "rainncv", "sr")}
+    r4 = gpu_mixed.mp_gt_driver(20.0, a4, pii, p3, dz3, a_min, radii=False)
+    assert r4 == {}
+    for k in names:
+        assert np.array_equal(a4[k], a3[k]), k
+    assert np.array_equal(a_min["rainnc"], aa["rainnc"])
+    # a shared dz vector through kidmp_step gives the same columns as the same depths passed per column
+    f5, _, _, _, acc5 = _wrf_case(ni, nk, nj)
+    dz_same = np.ascontiguousarray(np.broadcast_to(dz3[0, :, 0].reshape(1, nk, 1), (nj, nk, ni))).astype(np.float32)
+    a5 = {k: v.copy() for k, v in f5.items()}
+    gpu_mixed.mp_gt_driver(20.0, a5, pii, p3, dz_same, acc5, radii=False)
+    st = {k: np.ascontiguousarray(f5[k].transpose(1, 0, 2).reshape(nk, nj * ni)) for k in f5 if k != "th"}
+    st["t"] = np.ascontiguousarray((f5["th"] * pii).transpose(1, 0, 2).reshape(nk, nj * ni))
+    pcol = np.ascontiguousarray(p3.transpose(1, 0, 2).reshape(nk, nj * ni))
+    gpu_mixed.step(20.0, st, pcol, np.ascontiguousarray(dz3[0, :, 0]))
+    for k in ("qv", "qc", "qi", "qr", "qs", "qg", "ni", "nr"):
+        assert np.array_equal(st[k], a5[k].transpose(1, 0, 2).reshape(nk, nj * ni)), k

@@ -189,3 +189,80 @@ def test_rates_buffer(oracle_mixed):
     out = oracle_mixed.column(10.0, *[g["in/" + k][:, j] for k in FIELDS], g["in/p"][:, j], g["in/dz"], want_rates=True)
     assert out["rates"].shape == (36, 60) and len(oracle_mixed.rate_names) == 36
     assert np.isfinite(out["rates"]).all() and np.abs(out["rates"]).max() > 0
+
+
+# ---- calc_effectRad (M:4834-4935) and the mp_gt_driver algebra (M:986-1003, M:1110-1123) -------------------------
+def test_effective_radii_known_answers(oracle_mixed):
+    """Source-derived values: with is_aerosol_aware = .false. the droplet number is Nt_c (M:4875); for Nt_c = 100 cm^-3
+    inu_c = MIN(15, NINT(1000.E6/Nt_c) + 2) = 12 and lamc = (Nt_c*am_r*g_ratio(12)/rc)**obmr (M:4892-4897), so the
+    cloud radius is 0.5*(3+12)/lamc; the ice radius is 0.5*(3+mu_i)/lami with lami of M:4902; cells without the
+    species keep the presets of M:1112-1114."""
+    o = oracle_mixed
+    nz = 6
+    t = np.array([290., 285., 270., 255., 240., 225.], np.float32)
+    p = np.array([9.5e4, 9.0e4, 7.0e4, 5.5e4, 4.0e4, 3.0e4], np.float32)
+    qv = np.full(nz, 5e-3, np.float32)
+    qc = np.array([0., 1e-3, 2e-4, 0., 0., 0.], np.float32)
+    qi = np.array([0., 0., 0., 1e-5, 5e-5, 1e-6], np.float32)
+    ni = np.array([0., 0., 0., 5e3, 2e4, 1e3], np.float32)
+    qs = np.array([0., 0., 1e-4, 5e-4, 1e-3, 0.], np.float32)
+    rc, ri, rs = o.effect_rad(t, p, qv, qc, qi, ni, qs)
+    rho = 0.622 * p.astype(np.float64) / (287.04 * t * (qv + 0.622))
+    am_r, am_i = np.pi * 1000.0 / 6.0, np.pi * 890.0 / 6.0
+    g12 = 2730.0                                             # g_ratio(12), M:4857 (= (nu+3)(nu+2)(nu+1)... for nu = 12)
+    for k in range(nz):
+        if qc[k] > 0:
+            lamc = (100.0e6 * am_r * g12 / (qc[k] * rho[k])) ** (1.0 / 3.0)
+            want = min(max(0.5 * 15.0 / lamc, 2.51e-6), 50e-6)
+            assert abs(rc[k] - want) / want < 1e-5
+        else:
+            assert rc[k] == np.float32(2.49e-6)
+        if qi[k] > 0:
+            lami = (am_i * 6.0 * ni[k] / qi[k]) ** (1.0 / 3.0)   # cig(2)*oig1 = Gamma(4)/Gamma(1) = 6 (mu_i = 0, bm_i = 3)
+            want = min(max(0.5 * 3.0 / lami, 5.01e-6), 125e-6)
+            assert abs(ri[k] - want) / want < 1e-5
+        else:
+            assert ri[k] == np.float32(4.99e-6)
+        if qs[k] > 0:
+            # M:4911-4946: 0.5 * M3/M2 with the Field et al. (2005) moment relation for order cse(1) = bm_s + 1 = 3
+            sa = [5.065339, -0.062659, -3.032362, 0.029469, -0.000285, 0.31255, 0.000204, 0.003199, 0.0, -0.015952]
+            sb = [0.476221, -0.015896, 0.165977, 0.007468, -0.000141, 0.060366, 0.000079, 0.000594, 0.0, -0.003577]
+            tc0, c = min(-0.1, float(t[k]) - 273.15), 3.0
+            poly = lambda s: (s[0] + s[1] * tc0 + s[2] * c + s[3] * tc0 * c + s[4] * tc0 * tc0 + s[5] * c * c
+                              + s[6] * tc0 * tc0 * c + s[7] * tc0 * c * c + s[8] * tc0 ** 3 + s[9] * c ** 3)
+            smob = qs[k] * rho[k] / 0.069
+            want = min(max(0.5 * 10.0 ** poly(sa) * smob ** poly(sb) / smob, 10e-6), 999e-6)
+            assert abs(rs[k] - want) / want < 2e-4, (k, rs[k], want)
+        else:
+            assert rs[k] == np.float32(9.99e-6)
+
+
+def test_wrf_driver_algebra_on_the_oracle(oracle_mixed):
+    """mp_gt_driver around one column equals mp_thompson on T = th*pii with that column's dz, th = T/pii back,
+    and the accumulator formulas of M:990-1003."""
+    from kid_b200 import synth
+    o = oracle_mixed
+    st, p, dz = synth.deep_column(nz=40)
+    nk = 40
+    pii = ((p / 1.0e5) ** (287.04 / 1004.0)).astype(np.float32)
+    f3 = {k: st[k].reshape(1, nk, 1).copy() for k in ("qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr")}
+    f3["th"] = (st["t"] / pii).astype(np.float32).reshape(1, nk, 1)
+    t_in = (f3["th"].reshape(nk) * pii).astype(np.float32)
+    dz3 = (dz * np.float32(1.1)).astype(np.float32).reshape(1, nk, 1)
+    acc = {k: np.full((1, 1), v, np.float32) for k, v in
+           (("rainnc", 2.0), ("rainncv", 9.0), ("sr", 9.0), ("snownc", 1.0), ("snowncv", 9.0), ("graupelnc", 0.5), ("graupelncv", 9.0))}
+    re = o.mp_gt_driver(15.0, f3, pii.reshape(1, nk, 1), p.reshape(1, nk, 1), dz3, acc)
+    ref = o.column(15.0, st["qv"], st["qc"], st["qi"], st["qr"], st["qs"], st["qg"], st["ni"], st["nr"], t_in, p, dz3.reshape(nk))
+    for k in ("qv", "qc", "qr", "qi", "qs", "qg", "ni", "nr"):
+        assert np.array_equal(f3[k].reshape(nk), ref[k]), k
+    assert np.array_equal(f3["th"].reshape(nk), (ref["t"] / pii).astype(np.float32))
+    rain, ice, snow, grau = [np.float32(x) for x in ref["ppt"]]
+    ncv = np.float32(np.float32(np.float32(rain + snow) + grau) + ice)
+    assert acc["rainncv"][0, 0] == ncv
+    assert acc["rainnc"][0, 0] == np.float32(np.float32(np.float32(np.float32(np.float32(2.0) + rain) + snow) + grau) + ice)
+    assert acc["snowncv"][0, 0] == np.float32(snow + ice) and acc["graupelncv"][0, 0] == grau
+    assert acc["sr"][0, 0] == np.float32(np.float32(np.float32(snow + grau) + ice) / np.float32(ncv + np.float32(1e-12)))
+    rc, ri, rs = o.effect_rad(ref["t"], p, ref["qv"], ref["qc"], ref["qi"], ref["ni"], ref["qs"])
+    assert np.array_equal(re["re_cloud"].reshape(nk), np.clip(rc, np.float32(2.49e-6), np.float32(50e-6)))
+    assert np.array_equal(re["re_ice"].reshape(nk), np.clip(ri, np.float32(4.99e-6), np.float32(125e-6)))
+    assert np.array_equal(re["re_snow"].reshape(nk), np.clip(rs, np.float32(9.99e-6), np.float32(999e-6)))
