@@ -22,7 +22,7 @@ def test_header_declares_the_expected_entry_points():
     names = declared_functions()
     for must in ("kidmp_init", "kidmp_finalize", "kidmp_column", "kidmp_step", "kidmp_step_resident", "kidmp_upload",
                  "kidmp_download", "kidmp_step_device", "kidmp_diag", "kidmp_last_error", "kidmp_get_table",
-                 "kidmp_kid_interface"):
+                 "kidmp_kid_interface", "kidmp_mp_gt_driver"):
         assert must in names, must
 
 
