@@ -137,6 +137,13 @@ typedef struct kidmp_wrf_fields {
 } kidmp_wrf_fields;
 int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in);
 
+/* Tuning knobs; results do not depend on them.  "fuse": how the step treats sedimentation - 0 = physics and
+ * sedimentation as two kernels with a hand-off buffer, 2 = sedimentation fused into the physics kernel and the
+ * columns that need sub-steps (nstep > 1, M:3242) redone by the two-kernel path, 1 = fused when the step before
+ * had no column with sub-steps, else two kernels (default, or the KIDMP_FUSE environment variable), -1 = back to
+ * the default. */
+int kidmp_set_option(kidmp_handle* h, const char* name, int value);
+
 /* bookkeeping for benchmarks */
 long kidmp_gpu_launches(const kidmp_handle* h);         /* kernels launched so far          */
 int kidmp_sync(kidmp_handle* h);                        /* wait for the handle's stream     */

@@ -44,6 +44,11 @@ struct kidmp_handle {
   float* d_scratch = nullptr; size_t scratch_cells = 0;   // [SC_N][nz][ncol] hand-off between the two step kernels
   int* d_colint = nullptr; long scratch_cols = 0;
   double* d_coldiag = nullptr;                            // [2][ncol] per-column water paths for the ordered domain sums
+  int* d_redo = nullptr;                                  // [count, spare, ..., list] columns the fused kernel hands to the split kernels
+  int* h_redo = nullptr;                                  // pinned: {redo count, cloudy count} of the last step
+  cudaEvent_t ev_redo = nullptr; bool redo_pending = false;
+  int fuse_mode = -1;                                     // kidmp_set_option("fuse"): -1 = KIDMP_FUSE or adaptive
+  bool prefer_split = true;                               // until a step has shown that few columns need sub-steps
   int* d_work = nullptr;                                  // [count | list | mask] of cloudy 32-column groups
   double* d_diag = nullptr;
   float* d_rates = nullptr;
@@ -232,11 +237,14 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     if (h->d_colint) cudaFree(h->d_colint);
     if (h->d_work) cudaFree(h->d_work);
     if (h->d_coldiag) cudaFree(h->d_coldiag);
+    if (h->d_redo) cudaFree(h->d_redo);
+    h->d_redo = nullptr;
     h->d_scratch = nullptr; h->d_colint = nullptr; h->d_work = nullptr; h->d_coldiag = nullptr; h->scratch_cells = 0; h->scratch_cols = 0;
     CK(h, cudaMalloc((void**)&h->d_scratch, need * SC_N * 4));
     CK(h, cudaMalloc((void**)&h->d_colint, (size_t)a.ncol * 8 * 4));
     CK(h, cudaMalloc((void**)&h->d_work, (size_t)(a.ncol + 8 + 2 * ngroups) * 4));
     CK(h, cudaMalloc((void**)&h->d_coldiag, (size_t)a.ncol * 2 * 8));
+    CK(h, cudaMalloc((void**)&h->d_redo, (size_t)(a.ncol + 8) * 4));
     h->scratch_cells = need; h->scratch_cols = a.ncol;
   }
   a.scratch = h->d_scratch;
@@ -249,29 +257,80 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   a.diag_partial = h->d_partial;
   a.rates = h->d_rates;
   a.nsm = h->nsm;
+  a.redo_count = h->d_redo; a.redo_list = h->d_redo + 8;
+  // Mode of this step.  Fused (sedimentation inside the physics kernel) is right for columns whose sub-step counts are
+  // <= 1 and redoes the others with the split kernels.  Measured on a B200 (profiles/r01_ncu_step_kernels.md): the
+  // fused kernel costs 0.6 ms more than the split physics kernel and saves the 1.05 ms sedimentation kernel, but a redo
+  // pass costs ~2 ms however few columns it holds (a block walks its 60 levels at ~30 us each whether it has one warp
+  // or 24).  So the step is fused only when the step before it had NO column with sub-steps (KiD's 1-D cases, warm
+  // rain, small dt / thick layers; not the bench domain, whose fast graupel aloft gives 24 % of the columns nstep = 2).
+  // The first step runs split and counts.  The result is the same bit for bit either way.
+  // KIDMP_FUSE: 0 = never, 1 = adaptive (default), 2 = always.
+  static const int fuse_default = getenv("KIDMP_FUSE") ? atoi(getenv("KIDMP_FUSE")) : 1;
+  const int fuse_env = h->fuse_mode >= 0 ? h->fuse_mode : fuse_default;
+  if (!h->h_redo) {
+    CK(h, cudaHostAlloc((void**)&h->h_redo, 16, cudaHostAllocDefault));
+    h->h_redo[0] = 0; h->h_redo[1] = 0;
+    CK(h, cudaEventCreateWithFlags(&h->ev_redo, cudaEventDisableTiming));
+  }
+  if (h->redo_pending && cudaEventQuery(h->ev_redo) == cudaSuccess) {
+    h->redo_pending = false;
+    h->prefer_split = h->h_redo[0] > 0;
+  }
+  const bool fuse = fuse_env != 0 && !a.rates && !(fuse_env == 1 && h->prefer_split);
+  CK(h, cudaMemsetAsync(h->d_redo, 0, 8, s));
   k_classify<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
   k_list_scan<<<1, 1024, 0, s>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
   k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
   // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
   // dynamic shared memory of the physics kernel: 116 bytes per thread (vertical carries, parked inputs) (above 48 KB needs the opt-in)
-#define LAUNCH_K1(KERNEL, GRID, THREADS)                                                                          \
+#define LAUNCH_K1(KERNEL, GRID, THREADS, SMEM, ARGS)                                                              \
   do {                                                                                                            \
     static bool attr_set = false;                                                                                 \
-    if (!attr_set) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (THREADS) * 116); attr_set = true; } \
-    KERNEL<<<(GRID), (THREADS), (THREADS) * 116, s>>>(a);                                                          \
+    if (!attr_set) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (THREADS) * (SMEM)); attr_set = true; } \
+    KERNEL<<<(GRID), (THREADS), (THREADS) * (SMEM), s>>>(ARGS);                                                    \
   } while (0)
-  // measured alternatives (profiles/r01_ncu_step_kernels.md): 16 / 20 / 28 / 32 warps, 2x12 and 3x8 warps per SM, other barrier sets
   // grid: worst case (every column cloudy), rounded up to whole waves of `minb` blocks per SM (see the kernel)
   auto grid = [&](int w, int minb) { const long wave = (long)h->nsm * minb; return (unsigned)(((ngroups + w - 1) / w + wave - 1) / wave * wave); };
-  if (a.rates) LAUNCH_K1((k_column_step<16, 1, 11, true>), grid(16, 1), 512);   // with the 36 save_dg rates
-  else if (warps >= 24) LAUNCH_K1((k_column_step<24, 1, 11, false>), grid(24, 1), 768);
-  else if (warps >= 16) LAUNCH_K1((k_column_step<16, 1, 11, false>), grid(16, 1), 512);
-  else if (warps >= 8) LAUNCH_K1((k_column_step<8, 2, 11, false>), grid(8, 2), 256);   // two 8-warp blocks per SM
-  else LAUNCH_K1((k_column_step<1, 12, 0, false>), grid(1, 12), 32);
-  k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
+  // measured alternatives (profiles/r01_ncu_step_kernels.md): 16 / 20 / 28 / 32 warps, 2x12 and 3x8 warps per SM, other barrier sets
+  auto physics = [&](const StepArgs& x, bool fused) {
+    if (x.rates) LAUNCH_K1((k_column_step<16, 1, 11, true, false>), grid(16, 1), 512, 116, x);   // with the 36 save_dg rates
+    else if (warps >= 24) {
+      if (fused) LAUNCH_K1((k_column_step<24, 1, 11, false, true>), grid(24, 1), 768, 156, x);
+      else LAUNCH_K1((k_column_step<24, 1, 11, false, false>), grid(24, 1), 768, 116, x);
+    } else if (warps >= 16) {
+      if (fused) LAUNCH_K1((k_column_step<16, 1, 11, false, true>), grid(16, 1), 512, 156, x);
+      else LAUNCH_K1((k_column_step<16, 1, 11, false, false>), grid(16, 1), 512, 116, x);
+    } else if (warps >= 8) {                                                                     // two 8-warp blocks per SM
+      if (fused) LAUNCH_K1((k_column_step<8, 2, 11, false, true>), grid(8, 2), 256, 156, x);
+      else LAUNCH_K1((k_column_step<8, 2, 11, false, false>), grid(8, 2), 256, 116, x);
+    } else {
+      if (fused) LAUNCH_K1((k_column_step<1, 12, 0, false, true>), grid(1, 12), 32, 156, x);
+      else LAUNCH_K1((k_column_step<1, 12, 0, false, false>), grid(1, 12), 32, 116, x);
+    }
+  };
+  if (fuse) {
+    physics(a, true);
+    StepArgs r = a;                                  // the columns that need sub-steps, again, with the split kernels
+    r.work_count = h->d_redo; r.work_list = h->d_redo + 8; r.redo_count = h->d_redo + 1;
+    k_restore<<<(unsigned)ngroups, 32, 0, s>>>(r);
+    physics(r, false);
+    k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(r);
+    h->launches += 3;
+  } else {
+    physics(a, false);
+    k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
+    h->launches += 1;
+  }
+  if (!h->redo_pending) {                            // {columns with sub-steps, cloudy columns} for the next step's choice
+    CK(h, cudaMemcpyAsync(h->h_redo, h->d_redo, 4, cudaMemcpyDeviceToHost, s));
+    CK(h, cudaMemcpyAsync(h->h_redo + 1, a.work_count, 4, cudaMemcpyDeviceToHost, s));
+    CK(h, cudaEventRecord(h->ev_redo, s));
+    h->redo_pending = true;
+  }
   k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
   k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
-  h->launches += 7;
+  h->launches += 6;
   CK(h, cudaGetLastError());
   return 0;
 }
@@ -406,6 +465,9 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_scratch) cudaFree(h->d_scratch);
   if (h->d_colint) cudaFree(h->d_colint);
   if (h->d_work) cudaFree(h->d_work);
+  if (h->d_redo) cudaFree(h->d_redo);
+  if (h->h_redo) cudaFreeHost(h->h_redo);
+  if (h->ev_redo) cudaEventDestroy(h->ev_redo);
   if (h->d_coldiag) cudaFree(h->d_coldiag);
   if (h->d_pipe) cudaFree(h->d_pipe);
   if (h->d_pipe_dz) cudaFree(h->d_pipe_dz);
@@ -809,6 +871,16 @@ int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in) 
   if (a.snownc) { memcpy(w->snownc, h_2d + 3 * n2, n2 * 4); memcpy(w->snowncv, h_2d + 4 * n2, n2 * 4); }
   if (a.graupelnc) { memcpy(w->graupelnc, h_2d + 5 * n2, n2 * 4); memcpy(w->graupelncv, h_2d + 6 * n2, n2 * 4); }
   return 0;
+}
+
+int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
+  if (!h) return 1;
+  if (!name) return fail(h, "set_option: null name");
+  if (!strcmp(name, "fuse")) {
+    if (value < -1 || value > 2) return fail(h, "set_option: fuse must be -1, 0, 1 or 2");
+    h->fuse_mode = value; h->prefer_split = true; return 0;
+  }
+  return fail(h, "set_option: unknown option '%s'", name);
 }
 
 long kidmp_gpu_launches(const kidmp_handle* h) { return h ? h->launches : 0; }

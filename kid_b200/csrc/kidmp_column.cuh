@@ -214,12 +214,141 @@ __global__ void __launch_bounds__(256) k_list_fill(const unsigned* __restrict__ 
   if ((m >> lane) & 1u) list[offset[g] + __popc(m & ((1u << lane) - 1u))] = g * 32 + lane;
 }
 
+// ---- the last (or only) sedimentation sub-step of the four species at one level (M:3365-3578), the instant melting /
+// freezing of cloud ice and cloud water (S15, M:3584-3606), the tendencies applied with the final clamps (S16,
+// M:3623-3686), the nine output stores and the water paths of the new state.  Walked top-down: the fluxes of the level
+// above come in `c`.  Shared by k_sediment (after the extra sub-steps) and by the fused physics kernel.
+struct SedParams {            // per column, fixed over the sweep
+  float DT, odt, on_r, on_i, on_s, on_g, Nt_c;
+  int top_r, top_i, top_s, top_g;   // ksed1(1..4): top sedimenting level of rain, ice, snow, graupel (M:3208)
+  bool sedi, iiwarm;
+};
+struct SedCarry {             // carried down the column
+  float sr_up, snr_up, si_up, sni_up, ss_up, sg_up;     // fluxes leaving the level above
+  float ppt_r, ppt_i, ppt_s, ppt_g;
+  double lwp, iwp;
+};
+struct HandOff {              // what S1..S13 leave for a level (SC_* order)
+  float tt, qvt, qct, qit, qrt, qst, qgt, nit, nrt, nct, rr, nr, ri, ni, rs, rg, v_r, v_nr, v_i, v_ni, v_s, v_g, rho, s15;
+};
+__device__ __forceinline__ void finish_level(const StepArgs& a, const SedParams& p, SedCarry& c, const HandOff& h, int k, int nz,
+                                             long g, float dzk, float t1d, float qv1d, float qc1d, float qi1d, float qr1d,
+                                             float qs1d, float qg1d, float ni1d, float nr1d, float pres) {
+  float tt = h.tt, qvt = h.qvt, qct = h.qct, qit = h.qit, qrt = h.qrt, qst = h.qst, qgt = h.qgt, nit = h.nit, nrt = h.nrt, nct = h.nct;
+  const float rho = h.rho, s15 = h.s15, rr = h.rr, nr = h.nr, ri = h.ri, ni = h.ni, rs = h.rs, rg = h.rg;
+  const float odzq = 1.f / dzk, orho = 1.f / rho;
+  const float sr = h.v_r * rr, snr = h.v_nr * nr;
+  const float si = p.sedi ? h.v_i * ri : 0.f, sni = p.sedi ? h.v_ni * ni : 0.f;
+  const float ssn = p.sedi ? h.v_s * rs : 0.f, sg = p.sedi ? h.v_g * rg : 0.f;
+  float rr_n = rr, ri_n = ri, rs_n = rs, rg_n = rg;
+  if (k == nz - 1) {
+    qrt = qrt - sr * odzq * p.on_r * orho;   nrt = nrt - snr * odzq * p.on_r * orho;
+    rr_n = fmaxf(KP_R1, rr - sr * odzq * p.DT * p.on_r);
+    qit = qit - si * odzq * p.on_i * orho;   nit = nit - sni * odzq * p.on_i * orho;
+    ri_n = fmaxf(KP_R1, ri - si * odzq * p.DT * p.on_i);
+    qst = qst - ssn * odzq * p.on_s * orho;  rs_n = fmaxf(KP_R1, rs - ssn * odzq * p.DT * p.on_s);
+    qgt = qgt - sg * odzq * p.on_g * orho;   rg_n = fmaxf(KP_R1, rg - sg * odzq * p.DT * p.on_g);
+  } else {
+    if (k + 1 <= p.top_r) {
+      qrt = qrt + (c.sr_up - sr) * odzq * p.on_r * orho;   nrt = nrt + (c.snr_up - snr) * odzq * p.on_r * orho;
+      rr_n = fmaxf(KP_R1, rr + (c.sr_up - sr) * odzq * p.DT * p.on_r);
+    }
+    if (k + 1 <= p.top_i) {
+      qit = qit + (c.si_up - si) * odzq * p.on_i * orho;   nit = nit + (c.sni_up - sni) * odzq * p.on_i * orho;
+      ri_n = fmaxf(KP_R1, ri + (c.si_up - si) * odzq * p.DT * p.on_i);
+    }
+    if (k + 1 <= p.top_s) {
+      qst = qst + (c.ss_up - ssn) * odzq * p.on_s * orho;  rs_n = fmaxf(KP_R1, rs + (c.ss_up - ssn) * odzq * p.DT * p.on_s);
+    }
+    if (k + 1 <= p.top_g) {
+      qgt = qgt + (c.sg_up - sg) * odzq * p.on_g * orho;   rg_n = fmaxf(KP_R1, rg + (c.sg_up - sg) * odzq * p.DT * p.on_g);
+    }
+  }
+  c.sr_up = sr; c.snr_up = snr; c.si_up = si; c.sni_up = sni; c.ss_up = ssn; c.sg_up = sg;
+  if (k == 0) {                                         // surface precipitation of the last sub-step, M:3391-3392
+    if (rr_n > KP_R1 * 10.f) c.ppt_r = c.ppt_r + sr * p.DT * p.on_r;
+    if (ri_n > KP_R1 * 10.f) c.ppt_i = c.ppt_i + si * p.DT * p.on_i;
+    if (rs_n > KP_R1 * 10.f) c.ppt_s = c.ppt_s + ssn * p.DT * p.on_s;
+    if (rg_n > KP_R1 * 10.f) c.ppt_g = c.ppt_g + sg * p.DT * p.on_g;
+  }
+
+  // ---- S15 + S16 for this level ----------------------------------------------------------------
+  float nc1d = p.Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));   // U1
+  if (!(qc1d > KP_R1)) { qc1d = 0.f; nc1d = 0.f; }
+  if (!(qi1d > KP_R1)) { qi1d = 0.f; ni1d = 0.f; }
+  if (!(qr1d > KP_R1)) { qr1d = 0.f; nr1d = 0.f; }
+  if (!(qs1d > KP_R1)) qs1d = 0.f;
+  if (!(qg1d > KP_R1)) qg1d = 0.f;
+  if (!p.iiwarm) {
+    const float xri = fmaxf(0.0f, qi1d + qit * p.DT);
+    if ((s15 > 0.f) && (xri > 0.0f)) {                  // temp > T_0
+      qct = qct + xri * p.odt;
+      nct = nct + ni1d * p.odt;
+      qit = qit - xri * p.odt;
+      nit = -ni1d * p.odt;
+      tt = tt - s15 * xri * p.odt * 1.0f;
+    }
+    const float xrc = fmaxf(0.0f, qc1d + qct * p.DT);
+    if ((s15 < 0.f) && (xrc > 0.0f)) {                  // temp < HGFR
+      const float xnc = nc1d + nct * p.DT;
+      qit = qit + xrc * p.odt;
+      nit = nit + xnc * p.odt;
+      qct = qct - xrc * p.odt;
+      nct = nct - xnc * p.odt;
+      tt = tt + (-s15) * xrc * p.odt * 1.0f;
+    }
+  }
+  t1d = t1d + tt * p.DT;
+  qv1d = fmaxf(1.E-10f, qv1d + qvt * p.DT);
+  qc1d = qc1d + qct * p.DT;
+  if (qc1d <= KP_R1) qc1d = 0.0f;              // nc1d is not returned to the host (I:143-152, I:198-245)
+  qi1d = qi1d + qit * p.DT;
+  ni1d = fmaxf(KP_R2 / rho, ni1d + nit * p.DT);
+  if (qi1d <= KP_R1) {
+    qi1d = 0.0f; ni1d = 0.0f;
+  } else {
+    double lami = ice_lam(ni1d, qi1d);
+    const double ilami = (double)1.f / lami;
+    const float xDi = (float)((double)(3.f + 0.f + 1.f) * ilami);
+    if (xDi < 5.E-6f) lami = (double)(ck.cie[1] / 5.E-6f);
+    else if (xDi > 300.E-6f) lami = (double)(ck.cie[1] / 300.E-6f);
+    ni1d = (float)fmin((double)(ck.cig[0] * ck.oig2 * qi1d / ck.am_i) * cube_d(lami), 499.E3 / (double)rho);
+  }
+  qr1d = qr1d + qrt * p.DT;
+  nr1d = fmaxf(KP_R2 / rho, nr1d + nrt * p.DT);
+  if (qr1d <= KP_R1) {
+    qr1d = 0.0f; nr1d = 0.0f;
+  } else {
+    const double lamr = rain_lam(nr1d, qr1d);
+    float mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+    if (mvd_r > 2.5E-3f) mvd_r = 2.5E-3f;
+    else if (mvd_r < KP_D0R * 0.75f) mvd_r = KP_D0R * 0.75f;
+    nr1d = nr_from_mvd(qr1d, mvd_r);
+  }
+  qs1d = qs1d + qst * p.DT;
+  if (qs1d <= KP_R1) qs1d = 0.0f;
+  qg1d = qg1d + qgt * p.DT;
+  if (qg1d <= KP_R1) qg1d = 0.0f;
+  a.f[F_T][g] = t1d; a.f[F_QV][g] = qv1d; a.f[F_QC][g] = qc1d; a.f[F_QI][g] = qi1d; a.f[F_QR][g] = qr1d; a.f[F_QS][g] = qs1d; a.f[F_QG][g] = qg1d;
+  a.f[F_NI][g] = ni1d; a.f[F_NR][g] = nr1d;
+  // domain diagnostics: liquid / ice water paths of the new state
+  const float rho_new = 0.622f * pres / (KP_R * t1d * (qv1d + 0.622f));
+  c.lwp += (double)((qc1d + qr1d) * rho_new * dzk);
+  c.iwp += (double)((qi1d + qs1d + qg1d) * rho_new * dzk);
+}
+
 // ---- K1: column physics, S1..S13, on the cloudy 32-column groups of the work list.  A block is
 // WARPS warps = WARPS groups; its warps meet at a named barrier at every level of the top-down sweep,
 // so they run the same ~120 KB of straight-line code at the same time and share its instruction-cache
 // lines (profiles/r01: with independent warps the GPC instruction cache sat at 98 % of its request
 // peak and `no_instruction` was 8 of 13 stall cycles per issue).
-template <int WARPS, int MINB, int BARS, bool RATES>
+// FUSE: the single-sub-step sedimentation, S15 and S16 of a level follow its S1..S13 at once (finish_level) and the
+// new state is stored in place, so the 24-value hand-off is neither written nor read and k_sediment does not run.
+// That is only right for columns whose four sub-step counts end up <= 1, which is known at the bottom of the sweep:
+// the inputs of every level are therefore parked in the (otherwise unused) hand-off buffer first, and a column that
+// turns out to need sub-steps is put on the redo list - k_restore brings its inputs back and the split kernels
+// (FUSE = false, then k_sediment) do it again.
+template <int WARPS, int MINB, int BARS, bool RATES, bool FUSE>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
   const int count = *a.work_count;                     // cloudy columns, compacted: every warp but the last is full
   // The warps of the list are dealt evenly to a whole number of waves of blocks (one wave = MINB blocks on each SM):
@@ -265,6 +394,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
       float* const s_f = reinterpret_cast<float*>(smem_carry + 2 * NT); // [6][NT]
       int* const s_i = reinterpret_cast<int*>(s_f + 6 * NT);            // [8][NT]
       float* const s_in = reinterpret_cast<float*>(s_i + 8 * NT);       // [11][NT] this level's inputs, parked over S3..S7
+      double* const s_wp = reinterpret_cast<double*>(s_in + 11 * NT);   // FUSE: [2][NT] liquid / ice water path so far
+      float* const s_flux = reinterpret_cast<float*>(s_wp + 2 * NT);    // FUSE: [6][NT] sedimentation fluxes of the level above
       const int tid = threadIdx.x;
 #define N0_min_a s_d[tid]
 #define N0_min_b s_d[NT + tid]
@@ -287,6 +418,32 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
       vtr_up = 0.f; vtnr_up = 0.f; vti_up = 0.f; vtni_up = 0.f; vts_up = 0.f; vtg_up = 0.f;
       nstep_r = 0; nstep_i = 0; nstep_s = 0; nstep_g = 0;
       ksed_r = 1; ksed_i = 1; ksed_s = 1; ksed_g = 1;      // 1-based like the reference
+      if (FUSE) {
+        s_wp[tid] = 0.0; s_wp[NT + tid] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) s_flux[q * NT + tid] = 0.f;
+      }
+      // S14..S16 of one level right after its S1..S13 (FUSE)
+      auto finish = [&](const HandOff& h, int k, long o, float dzq, float t1d, float qv1d, float qc1d, float qi1d, float qr1d,
+                        float qs1d, float qg1d, float ni1d, float nr1d, float pres) {
+        SedParams sp;
+        sp.DT = DT; sp.odt = odt; sp.on_r = 1.f; sp.on_i = 1.f; sp.on_s = 1.f; sp.on_g = 1.f; sp.Nt_c = Nt_c;
+        sp.top_r = ksed_r; sp.top_i = ksed_i; sp.top_s = ksed_s; sp.top_g = ksed_g;   // so far = final for this level
+        sp.sedi = ck.l_sediment != 0; sp.iiwarm = iiwarm;
+        SedCarry c;
+        c.sr_up = s_flux[tid]; c.snr_up = s_flux[NT + tid]; c.si_up = s_flux[2 * NT + tid]; c.sni_up = s_flux[3 * NT + tid];
+        c.ss_up = s_flux[4 * NT + tid]; c.sg_up = s_flux[5 * NT + tid];
+        c.ppt_r = 0.f; c.ppt_i = 0.f; c.ppt_s = 0.f; c.ppt_g = 0.f;
+        c.lwp = s_wp[tid]; c.iwp = s_wp[NT + tid];
+        finish_level(a, sp, c, h, k, nz, o + col, dzq, t1d, qv1d, qc1d, qi1d, qr1d, qs1d, qg1d, ni1d, nr1d, pres);
+        s_flux[tid] = c.sr_up; s_flux[NT + tid] = c.snr_up; s_flux[2 * NT + tid] = c.si_up; s_flux[3 * NT + tid] = c.sni_up;
+        s_flux[4 * NT + tid] = c.ss_up; s_flux[5 * NT + tid] = c.sg_up;
+        s_wp[tid] = c.lwp; s_wp[NT + tid] = c.iwp;
+        if (k == 0) {     // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
+          a.ppt[col] = c.ppt_r; a.ppt[ncol + col] = c.ppt_i; a.ppt[2 * ncol + col] = c.ppt_s; a.ppt[3 * ncol + col] = c.ppt_g;
+          a.coldiag[col] = c.lwp; a.coldiag[ncol + col] = c.iwp;
+        }
+      };
 
       // graupel intercept of a level without rain and graupel (xslw1 = 0.01, rg = R1 in M:1639-1646): the only
       // thing such a level contributes to the running minimum of M:1648
@@ -302,6 +459,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         float qc1d = Gqc[o], qi1d = Gqi[o], qr1d = Gqr[o], qs1d = Gqs[o], qg1d = Gqg[o];
         float ni1d = Gni[o], nr1d = Gnr[o];
         const float dzq = a.dz_col ? a.dz_col[o + col] : a.dz[k];
+        if (FUSE && active) {                              // the inputs of the level, in case the column must be redone
+          float* sc = a.scratch + o + col;
+          const long ss = (long)nz * ncol;
+          sc[0] = qv1d; sc[ss] = qc1d; sc[2 * ss] = qi1d; sc[3 * ss] = qr1d; sc[4 * ss] = qs1d; sc[5 * ss] = qg1d;
+          sc[6 * ss] = ni1d; sc[7 * ss] = nr1d; sc[8 * ss] = t1d;
+        }
         // U1: nc1d as the WRF driver sets it when the scheme is not aerosol aware, M:957-964
         float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));
 
@@ -337,7 +500,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
               if (v_s > 1.E-3f) { ksed_s = max(ksed_s, k + 1); const float d = dzq / v_s; nstep_s = max(nstep_s, (int)(DT / d + 1.f)); }
               if (v_g > 1.E-3f) { ksed_g = max(ksed_g, k + 1); const float d = dzq / v_g; nstep_g = max(nstep_g, (int)(DT / d + 1.f)); }
             }
-            if (active) {
+            if (FUSE && active) {
+              const float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+              const float lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+              HandOff h;
+              h.tt = 0.f; h.qvt = 0.f; h.qct = 0.f; h.qit = 0.f; h.qrt = 0.f; h.qst = 0.f; h.qgt = 0.f; h.nit = 0.f; h.nrt = 0.f; h.nct = 0.f;
+              h.rr = R1; h.nr = R2; h.ri = R1; h.ni = R2; h.rs = R1; h.rg = R1;
+              h.v_r = v_r; h.v_nr = v_nr; h.v_i = v_i; h.v_ni = v_ni; h.v_s = v_s; h.v_g = v_g; h.rho = rho;
+              h.s15 = 0.0f;
+              if (temp > T_0) h.s15 = ck.lfus * ocp;
+              else if (temp < KP_HGFR) h.s15 = -((KP_LSUB - lvap) * ocp);
+              finish(h, k, o, dzq, t1d, qv1d, qc1d, qi1d, qr1d, qs1d, qg1d, ni1d, nr1d, pres);
+            } else if (active) {
               const float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
               const float lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
               float s15 = 0.0f;
@@ -1186,7 +1360,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         // hand-off to the sedimentation kernel: [SC_N][nz][ncol], coalesced fire-and-forget stores.
         // S15 (M:3584-3606) needs lfus*ocp where the level ends above T_0 and lfus2*ocp where it ends
         // below HGFR (never both): one signed value carries the product and the case.
-        if (active) {
+        if (FUSE && active) {
+          HandOff h;
+          h.tt = tt; h.qvt = qvt; h.qct = qct; h.qit = qit; h.qrt = qrt; h.qst = qst; h.qgt = qgt; h.nit = nit; h.nrt = nrt; h.nct = nct;
+          h.rr = rr; h.nr = nr; h.ri = ri; h.ni = ni; h.rs = rs; h.rg = rg;
+          h.v_r = v_r; h.v_nr = v_nr; h.v_i = v_i; h.v_ni = v_ni; h.v_s = v_s; h.v_g = v_g; h.rho = rho;
+          h.s15 = 0.0f;
+          if (temp > T_0) h.s15 = ck.lfus * ocp;
+          else if (temp < KP_HGFR) h.s15 = -((KP_LSUB - lvap) * ocp);
+          finish(h, k, o, dzq, t1d, qv1d, qc1d, qi1d, qr1d, qs1d, qg1d, ni1d, nr1d, pres);
+        } else if (active) {
           float s15 = 0.0f;
           if (temp > T_0) s15 = ck.lfus * ocp;
           else if (temp < KP_HGFR) s15 = -((KP_LSUB - lvap) * ocp);
@@ -1211,6 +1394,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         ci[0] = min(nstep_r, KP_NSTEP_MAX); ci[ncol] = min(nstep_i, KP_NSTEP_MAX); ci[2 * ncol] = min(nstep_s, KP_NSTEP_MAX);
         ci[3 * ncol] = min(nstep_g, KP_NSTEP_MAX);
         ci[4 * ncol] = ksed_r; ci[5 * ncol] = ksed_i; ci[6 * ncol] = ksed_s; ci[7 * ncol] = ksed_g;
+        if (max(max(nstep_r, nstep_i), max(nstep_s, nstep_g)) > 1) {     // counted in both modes: the host picks the mode of the next step
+          const int at = atomicAdd(a.redo_count, 1);
+          if (FUSE) a.redo_list[at] = (int)col;
+        }
       }
     }
   }
@@ -1233,6 +1420,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
 #undef ksed_i
 #undef ksed_s
 #undef ksed_g
+
+// ---- inputs of the columns on the redo list back from the hand-off buffer (see FUSE above) ----------------------------
+__global__ void __launch_bounds__(32) k_restore(StepArgs a) {
+  const int slot = blockIdx.x * 32 + threadIdx.x;
+  if (slot >= *a.work_count) return;
+  const long col = a.work_list[slot];
+  const long ncol = a.ncol, ss = (long)a.nz * ncol;
+  for (int k = 0; k < a.nz; ++k) {
+    const long g = (long)k * ncol + col;
+#pragma unroll
+    for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q][g] = a.scratch[q * ss + g];
+  }
+}
 
 // ---- K2: sub-stepped upwind sedimentation (M:3365-3578), instant melt / freeze (M:3584-3606), apply
 // tendencies and final clamps (M:3623-3686).  One thread per column, light on registers, so many
@@ -1317,121 +1517,27 @@ __global__ void __launch_bounds__(32) k_sediment(StepArgs a) {
       float* Gqv = a.f[F_QV] + col; float* Gqc = a.f[F_QC] + col; float* Gqi = a.f[F_QI] + col;
       float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
       float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
-      const bool iiwarm = ck.iiwarm != 0;
-      const float Nt_c = ck.Nt_c;
-      float sr_up = 0.f, snr_up = 0.f, si_up = 0.f, sni_up = 0.f, ss_up = 0.f, sg_up = 0.f;
+      SedParams sp;
+      sp.DT = DT; sp.odt = odt; sp.on_r = on_r; sp.on_i = on_i; sp.on_s = on_s; sp.on_g = on_g; sp.Nt_c = ck.Nt_c;
+      sp.top_r = ksed_r; sp.top_i = ksed_i; sp.top_s = ksed_s; sp.top_g = ksed_g; sp.sedi = sedi; sp.iiwarm = ck.iiwarm != 0;
+      SedCarry c;
+      c.sr_up = 0.f; c.snr_up = 0.f; c.si_up = 0.f; c.sni_up = 0.f; c.ss_up = 0.f; c.sg_up = 0.f;
+      c.ppt_r = ppt_r; c.ppt_i = ppt_i; c.ppt_s = ppt_s; c.ppt_g = ppt_g; c.lwp = 0.0; c.iwp = 0.0;
 #pragma unroll 1
       for (int k = nz - 1; k >= 0; --k) {
         const long o = (long)k * ncol;
         const float* q = sc + o;
-        float tt = q[SC_TTEN * ss], qvt = q[SC_QVTEN * ss], qct = q[SC_QCTEN * ss], qit = q[SC_QITEN * ss];
-        float qrt = q[SC_QRTEN * ss], qst = q[SC_QSTEN * ss], qgt = q[SC_QGTEN * ss], nit = q[SC_NITEN * ss];
-        float nrt = q[SC_NRTEN * ss], nct = q[SC_NCTEN * ss];
-        const float rho = q[SC_RHO * ss], s15 = q[SC_S15 * ss];
-        const float rr = q[SC_RR * ss], nr = q[SC_NR * ss], ri = q[SC_RI * ss], ni = q[SC_NI * ss], rs = q[SC_RS * ss], rg = q[SC_RG * ss];
-        const float odzq = 1.f / dzp[k * dzs], orho = 1.f / rho;
-        const float sr = q[SC_VTR * ss] * rr, snr = q[SC_VTNR * ss] * nr;
-        const float si = sedi ? q[SC_VTI * ss] * ri : 0.f, sni = sedi ? q[SC_VTNI * ss] * ni : 0.f;
-        const float ssn = sedi ? q[SC_VTS * ss] * rs : 0.f, sg = sedi ? q[SC_VTG * ss] * rg : 0.f;
-        float rr_n = rr, ri_n = ri, rs_n = rs, rg_n = rg;
-        if (k == nz - 1) {
-          qrt = qrt - sr * odzq * on_r * orho;   nrt = nrt - snr * odzq * on_r * orho;
-          rr_n = fmaxf(KP_R1, rr - sr * odzq * DT * on_r);
-          qit = qit - si * odzq * on_i * orho;   nit = nit - sni * odzq * on_i * orho;
-          ri_n = fmaxf(KP_R1, ri - si * odzq * DT * on_i);
-          qst = qst - ssn * odzq * on_s * orho;  rs_n = fmaxf(KP_R1, rs - ssn * odzq * DT * on_s);
-          qgt = qgt - sg * odzq * on_g * orho;   rg_n = fmaxf(KP_R1, rg - sg * odzq * DT * on_g);
-        } else {
-          if (k + 1 <= ksed_r) {
-            qrt = qrt + (sr_up - sr) * odzq * on_r * orho;   nrt = nrt + (snr_up - snr) * odzq * on_r * orho;
-            rr_n = fmaxf(KP_R1, rr + (sr_up - sr) * odzq * DT * on_r);
-          }
-          if (k + 1 <= ksed_i) {
-            qit = qit + (si_up - si) * odzq * on_i * orho;   nit = nit + (sni_up - sni) * odzq * on_i * orho;
-            ri_n = fmaxf(KP_R1, ri + (si_up - si) * odzq * DT * on_i);
-          }
-          if (k + 1 <= ksed_s) {
-            qst = qst + (ss_up - ssn) * odzq * on_s * orho;  rs_n = fmaxf(KP_R1, rs + (ss_up - ssn) * odzq * DT * on_s);
-          }
-          if (k + 1 <= ksed_g) {
-            qgt = qgt + (sg_up - sg) * odzq * on_g * orho;   rg_n = fmaxf(KP_R1, rg + (sg_up - sg) * odzq * DT * on_g);
-          }
-        }
-        sr_up = sr; snr_up = snr; si_up = si; sni_up = sni; ss_up = ssn; sg_up = sg;
-        if (k == 0) {                                         // surface precipitation of the last sub-step, M:3391-3392
-          if (rr_n > KP_R1 * 10.f) ppt_r = ppt_r + sr * DT * on_r;
-          if (ri_n > KP_R1 * 10.f) ppt_i = ppt_i + si * DT * on_i;
-          if (rs_n > KP_R1 * 10.f) ppt_s = ppt_s + ssn * DT * on_s;
-          if (rg_n > KP_R1 * 10.f) ppt_g = ppt_g + sg * DT * on_g;
-        }
-
-        // ---- S15 + S16 for this level ----------------------------------------------------------------
-        float t1d = Gt[o], qv1d = Gqv[o], qc1d = Gqc[o], qi1d = Gqi[o], qr1d = Gqr[o], qs1d = Gqs[o], qg1d = Gqg[o];
-        float ni1d = Gni[o], nr1d = Gnr[o];
-        const float pres = Gp[o];
-        float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));   // U1
-        if (!(qc1d > KP_R1)) { qc1d = 0.f; nc1d = 0.f; }
-        if (!(qi1d > KP_R1)) { qi1d = 0.f; ni1d = 0.f; }
-        if (!(qr1d > KP_R1)) { qr1d = 0.f; nr1d = 0.f; }
-        if (!(qs1d > KP_R1)) qs1d = 0.f;
-        if (!(qg1d > KP_R1)) qg1d = 0.f;
-        if (!iiwarm) {
-          const float xri = fmaxf(0.0f, qi1d + qit * DT);
-          if ((s15 > 0.f) && (xri > 0.0f)) {                  // temp > T_0
-            qct = qct + xri * odt;
-            nct = nct + ni1d * odt;
-            qit = qit - xri * odt;
-            nit = -ni1d * odt;
-            tt = tt - s15 * xri * odt * 1.0f;
-          }
-          const float xrc = fmaxf(0.0f, qc1d + qct * DT);
-          if ((s15 < 0.f) && (xrc > 0.0f)) {                  // temp < HGFR
-            const float xnc = nc1d + nct * DT;
-            qit = qit + xrc * odt;
-            nit = nit + xnc * odt;
-            qct = qct - xrc * odt;
-            nct = nct - xnc * odt;
-            tt = tt + (-s15) * xrc * odt * 1.0f;
-          }
-        }
-        t1d = t1d + tt * DT;
-        qv1d = fmaxf(1.E-10f, qv1d + qvt * DT);
-        qc1d = qc1d + qct * DT;
-        if (qc1d <= KP_R1) qc1d = 0.0f;              // nc1d is not returned to the host (I:143-152, I:198-245)
-        qi1d = qi1d + qit * DT;
-        ni1d = fmaxf(KP_R2 / rho, ni1d + nit * DT);
-        if (qi1d <= KP_R1) {
-          qi1d = 0.0f; ni1d = 0.0f;
-        } else {
-          double lami = ice_lam(ni1d, qi1d);
-          const double ilami = (double)1.f / lami;
-          const float xDi = (float)((double)(3.f + 0.f + 1.f) * ilami);
-          if (xDi < 5.E-6f) lami = (double)(ck.cie[1] / 5.E-6f);
-          else if (xDi > 300.E-6f) lami = (double)(ck.cie[1] / 300.E-6f);
-          ni1d = (float)fmin((double)(ck.cig[0] * ck.oig2 * qi1d / ck.am_i) * cube_d(lami), 499.E3 / (double)rho);
-        }
-        qr1d = qr1d + qrt * DT;
-        nr1d = fmaxf(KP_R2 / rho, nr1d + nrt * DT);
-        if (qr1d <= KP_R1) {
-          qr1d = 0.0f; nr1d = 0.0f;
-        } else {
-          const double lamr = rain_lam(nr1d, qr1d);
-          float mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
-          if (mvd_r > 2.5E-3f) mvd_r = 2.5E-3f;
-          else if (mvd_r < KP_D0R * 0.75f) mvd_r = KP_D0R * 0.75f;
-          nr1d = nr_from_mvd(qr1d, mvd_r);
-        }
-        qs1d = qs1d + qst * DT;
-        if (qs1d <= KP_R1) qs1d = 0.0f;
-        qg1d = qg1d + qgt * DT;
-        if (qg1d <= KP_R1) qg1d = 0.0f;
-        Gt[o] = t1d; Gqv[o] = qv1d; Gqc[o] = qc1d; Gqi[o] = qi1d; Gqr[o] = qr1d; Gqs[o] = qs1d; Gqg[o] = qg1d;
-        Gni[o] = ni1d; Gnr[o] = nr1d;
-        // domain diagnostics: liquid / ice water paths of the new state
-        const float rho_new = 0.622f * pres / (KP_R * t1d * (qv1d + 0.622f));
-        lwp += (double)((qc1d + qr1d) * rho_new * dzp[k * dzs]);
-        iwp += (double)((qi1d + qs1d + qg1d) * rho_new * dzp[k * dzs]);
+        HandOff h;
+        h.tt = q[SC_TTEN * ss]; h.qvt = q[SC_QVTEN * ss]; h.qct = q[SC_QCTEN * ss]; h.qit = q[SC_QITEN * ss];
+        h.qrt = q[SC_QRTEN * ss]; h.qst = q[SC_QSTEN * ss]; h.qgt = q[SC_QGTEN * ss]; h.nit = q[SC_NITEN * ss];
+        h.nrt = q[SC_NRTEN * ss]; h.nct = q[SC_NCTEN * ss];
+        h.rho = q[SC_RHO * ss]; h.s15 = q[SC_S15 * ss];
+        h.rr = q[SC_RR * ss]; h.nr = q[SC_NR * ss]; h.ri = q[SC_RI * ss]; h.ni = q[SC_NI * ss]; h.rs = q[SC_RS * ss]; h.rg = q[SC_RG * ss];
+        h.v_r = q[SC_VTR * ss]; h.v_nr = q[SC_VTNR * ss]; h.v_i = q[SC_VTI * ss]; h.v_ni = q[SC_VTNI * ss];
+        h.v_s = q[SC_VTS * ss]; h.v_g = q[SC_VTG * ss];
+        finish_level(a, sp, c, h, k, nz, o + col, dzp[k * dzs], Gt[o], Gqv[o], Gqc[o], Gqi[o], Gqr[o], Gqs[o], Gqg[o], Gni[o], Gnr[o], Gp[o]);
       }
+      ppt_r = c.ppt_r; ppt_i = c.ppt_i; ppt_s = c.ppt_s; ppt_g = c.ppt_g; lwp = c.lwp; iwp = c.iwp;
     }
     // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
     a.ppt[col] = ppt_r; a.ppt[ncol + col] = ppt_i; a.ppt[2 * ncol + col] = ppt_s; a.ppt[3 * ncol + col] = ppt_g;

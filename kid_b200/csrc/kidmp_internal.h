@@ -125,6 +125,8 @@ struct StepArgs {
   float* rates;                // optional [36][nz][ncol]
   double* coldiag;             // [2][ncol] liquid / ice water path of each cloudy column
   double* diag_partial;        // [DIAG_BLOCKS][KIDMP_NDIAG] block sums of k_diag_columns
+  int* redo_count;             // fused physics kernel: columns that need sedimentation sub-steps ...
+  int* redo_list;              // ... and are done again by the split kernels
   int nsm;                     // SMs of the device: the physics kernel spreads its warps over whole waves of blocks
 };
 

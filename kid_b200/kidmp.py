@@ -51,6 +51,7 @@ SYMBOLS = {
     "kidmp_set_rates_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kidmp_rate_names": (C.c_char_p, []),
     "kidmp_diag": (C.c_int, [C.c_void_p, _dp]),
+    "kidmp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "kidmp_gpu_launches": (C.c_long, [C.c_void_p]),
     "kidmp_sync": (C.c_int, [C.c_void_p]),
     "kidmp_last_step_ms": (C.c_int, [C.c_void_p, _fp]),
@@ -236,6 +237,10 @@ class Thompson:
         p, dz, ppt = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ck(self._L.kidmp_device_state(self.h, f, C.byref(p), C.byref(dz), C.byref(ppt)))
         return [int(x) for x in f], int(p.value), int(dz.value), int(ppt.value)
+
+    def set_option(self, name, value):
+        """kidmp_set_option: tuning knobs that do not change results ("fuse": 0 split, 1 adaptive, 2 always fused)."""
+        self._ck(self._L.kidmp_set_option(self.h, name.encode(), int(value)))
 
     def mp_gt_driver(self, dt, f3, pii, p, dz, acc, radii=True):
         """mp_gt_driver (M:806-1143) through kidmp_mp_gt_driver.  f3: dict qv qc qr qi qs qg ni nr th of (nj, nk, ni)
