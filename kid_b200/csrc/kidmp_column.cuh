@@ -25,10 +25,12 @@ namespace kidmp {
 
 __constant__ KConst ck;
 
-// Helpers that appear at many call sites are kept out of line: one copy stays resident in the SM
-// instruction cache instead of ~2 000 inlined instructions streamed from L2.
+// The f64 logarithm / exponential / power stay out of line (kidmp_math.cuh): ~130 call sites, and in line they made a
+// kernel whose instruction fetch was the limit (profiles/r01; still 6 % slower in line under the lockstep barriers).
+// The small helpers below are in line again since the lockstep blocks share their instruction-cache lines: measured
+// 2 % faster than out of line (a call costs two branch latencies on a path that is latency-bound).
 #ifndef KIDMP_HELPER
-#define KIDMP_HELPER __device__ __noinline__
+#define KIDMP_HELPER __device__ __forceinline__
 #endif
 
 #define R1 KP_R1
