@@ -35,7 +35,7 @@ DT = 10.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the step kernels from the ncu --set full captures of the same workload
 # (profiles/r01_ncu_step_kernels.md, reports prof_r1g / prof_r1i): 2.52+0.02 (classify) + 1.24+2.35 (physics) +
 # 3.46+0.71 (sedimentation) + 0.02 (ordered domain sums) GB
-TRAFFIC_BYTES_PER_LAUNCH = 10.32e9
+TRAFFIC_BYTES_PER_LAUNCH = 10.15e9
 
 
 def peaks():

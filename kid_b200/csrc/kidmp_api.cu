@@ -284,6 +284,9 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
   // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
   // dynamic shared memory of the physics kernel: 116 bytes per thread (vertical carries, parked inputs) (above 48 KB needs the opt-in)
+#ifndef K1_BARS
+#define K1_BARS 11           // stage barriers of the lockstep blocks: level top, before S6, before S9 (bit i = LOCKBAR(i))
+#endif
 #define LAUNCH_K1(KERNEL, GRID, THREADS, SMEM, ARGS)                                                              \
   do {                                                                                                            \
     static bool attr_set = false;                                                                                 \
@@ -294,16 +297,16 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   auto grid = [&](int w, int minb) { const long wave = (long)h->nsm * minb; return (unsigned)(((ngroups + w - 1) / w + wave - 1) / wave * wave); };
   // measured alternatives (profiles/r01_ncu_step_kernels.md): 16 / 20 / 28 / 32 warps, 2x12 and 3x8 warps per SM, other barrier sets
   auto physics = [&](const StepArgs& x, bool fused) {
-    if (x.rates) LAUNCH_K1((k_column_step<16, 1, 11, true, false>), grid(16, 1), 512, 116, x);   // with the 36 save_dg rates
+    if (x.rates) LAUNCH_K1((k_column_step<16, 1, K1_BARS, true, false>), grid(16, 1), 512, 116, x);   // with the 36 save_dg rates
     else if (warps >= 24) {
-      if (fused) LAUNCH_K1((k_column_step<24, 1, 11, false, true>), grid(24, 1), 768, 156, x);
-      else LAUNCH_K1((k_column_step<24, 1, 11, false, false>), grid(24, 1), 768, 116, x);
+      if (fused) LAUNCH_K1((k_column_step<24, 1, K1_BARS, false, true>), grid(24, 1), 768, 156, x);
+      else LAUNCH_K1((k_column_step<24, 1, K1_BARS, false, false>), grid(24, 1), 768, 116, x);
     } else if (warps >= 16) {
-      if (fused) LAUNCH_K1((k_column_step<16, 1, 11, false, true>), grid(16, 1), 512, 156, x);
-      else LAUNCH_K1((k_column_step<16, 1, 11, false, false>), grid(16, 1), 512, 116, x);
+      if (fused) LAUNCH_K1((k_column_step<16, 1, K1_BARS, false, true>), grid(16, 1), 512, 156, x);
+      else LAUNCH_K1((k_column_step<16, 1, K1_BARS, false, false>), grid(16, 1), 512, 116, x);
     } else if (warps >= 8) {                                                                     // two 8-warp blocks per SM
-      if (fused) LAUNCH_K1((k_column_step<8, 2, 11, false, true>), grid(8, 2), 256, 156, x);
-      else LAUNCH_K1((k_column_step<8, 2, 11, false, false>), grid(8, 2), 256, 116, x);
+      if (fused) LAUNCH_K1((k_column_step<8, 2, K1_BARS, false, true>), grid(8, 2), 256, 156, x);
+      else LAUNCH_K1((k_column_step<8, 2, K1_BARS, false, false>), grid(8, 2), 256, 116, x);
     } else {
       if (fused) LAUNCH_K1((k_column_step<1, 12, 0, false, true>), grid(1, 12), 32, 156, x);
       else LAUNCH_K1((k_column_step<1, 12, 0, false, false>), grid(1, 12), 32, 116, x);
