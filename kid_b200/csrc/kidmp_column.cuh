@@ -1474,7 +1474,10 @@ __device__ __forceinline__ void sed_substeps(float* __restrict__ r, float* __res
   }
 }
 
-__global__ void __launch_bounds__(32) k_sediment(StepArgs a) {
+#ifndef K2_MINB
+#define K2_MINB 20         // 96 registers, no spills: 20 one-warp blocks per SM
+#endif
+__global__ void __launch_bounds__(32, K2_MINB) k_sediment(StepArgs a) {
   const int slot = blockIdx.x * 32 + threadIdx.x;          // cloudy columns only: the compacted work list
   if (slot >= *a.work_count) return;
   const long col = a.work_list[slot];
