@@ -584,25 +584,28 @@ def test_wrf_driver_entry(gpu_mixed, oracle_mixed):
 
 
 # ---- sedimentation fused into the physics kernel, with the redo path for columns that need sub-steps ----------------
-@pytest.mark.parametrize("dt,dz,warm", [(10.0, 250.0, False), (60.0, 100.0, False), (30.0, 120.0, False), (20.0, 60.0, True)])
-def test_fused_and_split_steps_are_bit_identical(dt, dz, warm):
+@pytest.mark.parametrize("dt,dz,warm,ncol,nz", [(10.0, 250.0, False, 20000, 60), (60.0, 100.0, False, 20000, 60),
+                                                (30.0, 120.0, False, 20000, 60), (20.0, 60.0, True, 20000, 60),
+                                                (10.0, 125.0, False, 77, 120), (5.0, 250.0, False, 1, 60),
+                                                (10.0, 250.0, False, 140001, 37)])
+def test_fused_and_split_steps_are_bit_identical(dt, dz, warm, ncol, nz):
     """kidmp_set_option("fuse"): 0 = two kernels with a hand-off, 2 = fused + redo of the columns whose sub-step count
     exceeds 1 (none at dt=10/dz=250, most rain columns at dt=60/dz=100), 1 = adaptive.  Same bits in every mode,
     over several steps (the adaptive mode switches after the first step when many columns were redone)."""
     import torch
     from kid_b200 import synth
     from kid_b200.kidmp import Thompson
-    ncol = 20000
     res = {}
     for mode in (0, 2, 1):
         th = Thompson(set_Nc=100.0, iiwarm=warm, l_sediment=True)
         th.set_option("fuse", mode)
-        st, p, dzv = synth.make_domain(ncol, nz=60, nx=1024, device="cuda", dz=dz, col0=200000)
+        kw = dict(col0=200000) if ncol >= 20000 else dict(coherent=False, cloudy_fraction=1.0 if ncol == 1 else 0.6)
+        st, p, dzv = synth.make_domain(ncol, nz=nz, nx=1024, device="cuda", dz=dz, **kw)
         ppt = torch.zeros((4, ncol), dtype=torch.float32, device="cuda")
         acc = torch.zeros((4, ncol), dtype=torch.float64, device="cuda")
         torch.cuda.synchronize()
         for _ in range(3):
-            th.step_device(ncol, 60, dt, [st[k].data_ptr() for k in FIELDS], p.data_ptr(), dzv.data_ptr(), ppt.data_ptr())
+            th.step_device(ncol, nz, dt, [st[k].data_ptr() for k in FIELDS], p.data_ptr(), dzv.data_ptr(), ppt.data_ptr())
             th.sync()
             acc += ppt.double()
             torch.cuda.synchronize()
@@ -613,4 +616,4 @@ def test_fused_and_split_steps_are_bit_identical(dt, dz, warm):
             assert np.array_equal(res[mode][0][k], res[0][0][k]), (mode, k)
         assert np.array_equal(res[mode][1], res[0][1]), mode
         assert np.array_equal(res[mode][2], res[0][2]), mode          # domain sums in column order: same bits too
-    assert res[0][1].sum() > 0
+    assert res[0][2][6] > 0                                           # some columns were active
