@@ -141,7 +141,10 @@ int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in);
  * sedimentation as two kernels with a hand-off buffer, 2 = sedimentation fused into the physics kernel and the
  * columns that need sub-steps (nstep > 1, M:3242) redone by the two-kernel path, 1 = fused when the step before
  * had no column with sub-steps, else two kernels (default, or the KIDMP_FUSE environment variable), -1 = back to
- * the default. */
+ * the default.
+ * "units": which physics kernel - 1 = the unit-parallel one (a warp's unit of work is 32 neighbouring columns x ONE
+ * level, only units with a busy cell run; the better choice up to ~130 000 columns, i.e. for every KiD case), 0 = the
+ * column-walk kernel, -1 = by domain size (default, or the KIDMP_UNITS environment variable). */
 int kidmp_set_option(kidmp_handle* h, const char* name, int value);
 
 /* bookkeeping for benchmarks */

@@ -103,7 +103,9 @@ struct KConst {
 
 // hand-off arrays written by the column-physics kernel and consumed by the sedimentation kernel
 enum { SC_TTEN = 0, SC_QVTEN, SC_QCTEN, SC_QITEN, SC_QRTEN, SC_QSTEN, SC_QGTEN, SC_NITEN, SC_NRTEN, SC_NCTEN,
-       SC_RR, SC_NR, SC_RI, SC_NI, SC_RS, SC_RG, SC_VTR, SC_VTNR, SC_VTI, SC_VTNI, SC_VTS, SC_VTG, SC_RHO, SC_S15, SC_N };
+       SC_RR, SC_NR, SC_RI, SC_NI, SC_RS, SC_RG, SC_VTR, SC_VTNR, SC_VTI, SC_VTNI, SC_VTS, SC_VTG, SC_RHO, SC_S15, SC_N,
+       // between the phases of the unit-parallel physics kernel only (kidmp_units.cuh)
+       SC_N0A = SC_N, SC_N0B_SLW, SC_VTS_RAW, SC_VTS_BOOST, SC_TEMP, SC_NX };
 
 enum { DIAG_BLOCKS = 296 };
 

@@ -589,16 +589,21 @@ def test_wrf_driver_entry(gpu_mixed, oracle_mixed):
                                                 (10.0, 125.0, False, 77, 120), (5.0, 250.0, False, 1, 60),
                                                 (10.0, 250.0, False, 140001, 37)])
 def test_fused_and_split_steps_are_bit_identical(dt, dz, warm, ncol, nz):
-    """kidmp_set_option("fuse"): 0 = two kernels with a hand-off, 2 = fused + redo of the columns whose sub-step count
+    """The physics-kernel variants give the same bits.  kidmp_set_option("units"): unit-parallel or column-walk kernel;
+    kidmp_set_option("fuse"): 0 = two kernels with a hand-off, 2 = fused + redo of the columns whose sub-step count
     exceeds 1 (none at dt=10/dz=250, most rain columns at dt=60/dz=100), 1 = adaptive.  Same bits in every mode,
     over several steps (the adaptive mode switches after the first step when many columns were redone)."""
     import torch
     from kid_b200 import synth
     from kid_b200.kidmp import Thompson
     res = {}
-    for mode in (0, 2, 1):
+    # 0: column-walk kernel + sedimentation kernel; 2: column walk with fused sedimentation + redo; 1: the adaptive choice;
+    # "u": the unit-parallel physics kernel
+    for mode in (0, 2, 1, "u"):
         th = Thompson(set_Nc=100.0, iiwarm=warm, l_sediment=True)
-        th.set_option("fuse", mode)
+        th.set_option("units", 1 if mode == "u" else 0)
+        if mode != "u":
+            th.set_option("fuse", mode)
         kw = dict(col0=200000) if ncol >= 20000 else dict(coherent=False, cloudy_fraction=1.0 if ncol == 1 else 0.6)
         st, p, dzv = synth.make_domain(ncol, nz=nz, nx=1024, device="cuda", dz=dz, **kw)
         ppt = torch.zeros((4, ncol), dtype=torch.float32, device="cuda")
@@ -611,7 +616,7 @@ def test_fused_and_split_steps_are_bit_identical(dt, dz, warm, ncol, nz):
             torch.cuda.synchronize()
         res[mode] = ({k: st[k].cpu().numpy() for k in FIELDS}, acc.cpu().numpy(), th.diag())
         th.close()
-    for mode in (2, 1):
+    for mode in (2, 1, "u"):
         for k in FIELDS:
             assert np.array_equal(res[mode][0][k], res[0][0][k]), (mode, k)
         assert np.array_equal(res[mode][1], res[0][1]), mode
