@@ -30,9 +30,9 @@ __device__ __forceinline__ void graupel_slope(double N0_exp, bool L_qg, float rg
   }
 }
 
-constexpr int KU_MAXW = 8;                                  // level-mask words per group: nz <= 256
+constexpr int KU_MAXNZ = 256;
 __host__ __device__ constexpr int ku_smem_bytes(int threads, int nz) {
-  return threads * 11 * 4 + (threads / 32) * KU_MAXW * 4 + (threads / 32) * nz * 2 + 64;
+  return threads * 11 * 4 + (threads / 32) * nz * 4 + (threads / 32) * nz * 2 + 64;
 }
 
 #define R1 KP_R1
@@ -44,7 +44,10 @@ __host__ __device__ constexpr int ku_smem_bytes(int threads, int nz) {
 #define D0s KP_D0S
 #define D0g KP_D0G
 
-template <int WARPS, int MINB, int BARS, bool RATES>
+// PACK: the busy cells of a level are packed, in column order, into as few warps as they need (the lanes of a warp are
+// then the busy cells of neighbouring columns, with the empty ones between them left out); without it a unit is a whole
+// group of 32 columns as soon as one of its cells is busy.
+template <int WARPS, int MINB, int BARS, bool RATES, bool PACK>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_unit_step(StepArgs a) {
   constexpr int NT = WARPS * 32;
   constexpr bool FUSE = false;
@@ -70,10 +73,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_unit_step(StepArgs a) {
   const int nw = (nz + 31) >> 5;
   extern __shared__ float smem_ku[];
   float* const s_in = smem_ku;                                                 // [11][NT] inputs of the cell, parked over S3..S7
-  unsigned* const s_gmask = reinterpret_cast<unsigned*>(s_in + 11 * NT);       // [WARPS][KU_MAXW] busy levels of every group
-  unsigned short* const s_unit = reinterpret_cast<unsigned short*>(s_gmask + WARPS * KU_MAXW);   // [<= WARPS*nz] busy units, level-major: k * WARPS + g
+  unsigned* const s_cmask = reinterpret_cast<unsigned*>(s_in + 11 * NT);       // [WARPS][nz] busy lanes of every (group, level)
+  unsigned short* const s_unit = reinterpret_cast<unsigned short*>(s_cmask + WARPS * nz);   // [<= WARPS*nz] units, level-major: k * WARPS + (group | packed warp)
   __shared__ int s_nunits;
-  for (int i = tid; i < WARPS * KU_MAXW; i += NT) s_gmask[i] = 0u;
+  for (int i = tid; i < WARPS * nz; i += NT) s_cmask[i] = 0u;
   const double n0_empty = graupel_n0_lo();
   __syncthreads();
 
@@ -121,18 +124,28 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_unit_step(StepArgs a) {
         n0_min = fmin(N0_exp, n0_min);
         if (active) a.scratch[SC_N0A * ss + g] = (float)n0_min;     // values of M:1646 are f32 numbers: exact
       }
-      if (__any_sync(0xffffffffu, busy && active) && lane == 0) s_gmask[warp * KU_MAXW + (k >> 5)] |= 1u << (k & 31);
+      const unsigned bm = __ballot_sync(0xffffffffu, busy && active);
+      if (lane == 0) s_cmask[warp * nz + k] = bm;
     }
   }
   __syncthreads();
-  // ---- the busy units of the block, level-major from the top: a round of phase 2 holds units of one or two levels ----
+  // ---- the units of the block, level-major from the top: a round of phase 2 holds units of one or two levels ----
   if (warp == 0) {
     int n = 0;
     for (int k = nz - 1; k >= 0; --k) {
-      const bool b = lane < ng && ((s_gmask[lane * KU_MAXW + (k >> 5)] >> (k & 31)) & 1u);
-      const unsigned m = __ballot_sync(0xffffffffu, b);
-      if (b) s_unit[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(k * WARPS + lane);
-      n += __popc(m);
+      const unsigned cm = lane < ng ? s_cmask[lane * nz + k] : 0u;
+      if (PACK) {
+        int cells = __popc(cm);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, d);
+        const int nw_k = (cells + 31) >> 5;              // <= WARPS
+        if (lane < nw_k) s_unit[n + lane] = (unsigned short)(k * WARPS + lane);
+        n += nw_k;
+      } else {
+        const unsigned m = __ballot_sync(0xffffffffu, cm != 0u);
+        if (cm != 0u) s_unit[n + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(k * WARPS + lane);
+        n += __popc(m);
+      }
     }
     if (lane == 0) s_nunits = n;
   }
@@ -149,10 +162,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_unit_step(StepArgs a) {
     const int lock_threads = busy_warps * 32;
     const int unit = s_unit[base + warp];
     const int k = unit / WARPS, gi = unit - k * WARPS;
-    const int slot = (w0 + gi) * 32 + lane;
-    const bool active = slot < count;
-    // lanes past the end of the list shadow their group's first column: same branches, nothing stored
-    const long col = (long)a.work_list[active ? slot : (w0 + gi) * 32];
+    int slot;
+    bool active;
+    if (PACK) {
+      // lane -> the (gi*32 + lane)-th busy cell of level k among the block's columns, in column order; lanes past the
+      // last busy cell shadow the warp's first one: same branches, nothing stored
+      int want = gi * 32 + lane, g = 0, before = 0, g_first = -1, r_first = 0;
+      int found_g = -1, found_r = 0;
+      for (g = 0; g < ng; ++g) {
+        const int c = __popc(s_cmask[g * nz + k]);
+        if (g_first < 0 && gi * 32 < before + c) { g_first = g; r_first = gi * 32 - before; }
+        if (found_g < 0 && want < before + c) { found_g = g; found_r = want - before; }
+        before += c;
+      }
+      active = found_g >= 0;
+      if (!active) { found_g = g_first; found_r = r_first; }
+      slot = (w0 + found_g) * 32 + (int)__fns(s_cmask[found_g * nz + k], 0u, found_r + 1);
+    } else {
+      slot = (w0 + gi) * 32 + lane;
+      active = slot < count;
+      // lanes past the end of the list shadow their group's first column: same branches, nothing stored
+      if (!active) slot = (w0 + gi) * 32;
+    }
+    const long col = (long)a.work_list[slot];
     LOCKBAR(0);
     {
       {
@@ -207,7 +239,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_unit_step(StepArgs a) {
       const long o = (long)k * ncol;
       float* sc = a.scratch + o + col;
       const float dzq = a.dz_col ? a.dz_col[o + col] : a.dz[k];
-      const bool handed = (s_gmask[warp * KU_MAXW + (k >> 5)] >> (k & 31)) & 1u;
+      const unsigned cm = s_cmask[warp * nz + k];
+      const bool handed = PACK ? ((cm >> lane) & 1u) != 0u : cm != 0u;
       float rho = 0.f, s15 = 0.f;
       if (handed) {
         const float rr = sc[SC_RR * ss], ri = sc[SC_RI * ss], rs = sc[SC_RS * ss], rg = sc[SC_RG * ss];
