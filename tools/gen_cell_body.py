@@ -1,4 +1,7 @@
-"""Generates kid_b200/csrc/kidmp_cell_body.inc, the carry-free cell code of the unit-parallel physics kernel, from the\nlevel body of k_column_step in kidmp_column.cuh: S4, S10 and S13 lose their vertical carries (kidmp_units.cuh phases 1 and 3\ntake them over).  Run it after changing the cell code in kidmp_column.cuh; the two kernels must give the same bits\n(tools/ab.sh, tests/test_gpu_parity.py::test_fused_and_split_steps_are_bit_identical)."""
+"""Generates kid_b200/csrc/kidmp_cell_body.inc, the carry-free cell code of the unit-parallel physics kernel, from the
+level body of k_column_step in kidmp_column.cuh: S4, S10 and S13 lose their vertical carries (kidmp_units.cuh phases 1 and 3
+take them over).  Run it after changing the cell code in kidmp_column.cuh; the two kernels must give the same bits
+(tools/ab.sh, tests/test_gpu_parity.py::test_fused_and_split_steps_are_bit_identical)."""
 import re
 import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
