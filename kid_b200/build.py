@@ -42,12 +42,17 @@ def build(force=False, verbose=False, extra=()):
     """Compile if any source is newer than the library.  Returns the library path."""
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), *flags(extra), "-o", LIB + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
+    tmp = "%s.tmp%d" % (LIB, os.getpid())          # several ranks may build at once: each writes its own file, the rename is atomic
+    cmd = [nvcc_path(), *flags(extra), "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
-    os.replace(LIB + ".tmp", LIB)
+    try:
+        subprocess.check_call(cmd)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB
 
 

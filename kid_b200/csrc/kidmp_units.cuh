@@ -50,7 +50,6 @@ __host__ __device__ constexpr int ku_smem_bytes(int threads, int nz) {
 template <int WARPS, int MINB, int BARS, bool RATES, bool PACK>
 __global__ void __launch_bounds__(WARPS * 32, MINB) k_unit_step(StepArgs a) {
   constexpr int NT = WARPS * 32;
-  constexpr bool FUSE = false;
   const int count = *a.work_count;                     // cloudy columns, compacted: every group but the last is full
   // the groups of the list are dealt evenly to a whole number of waves of blocks (see k_column_step)
   const int total_warps = (count + 31) >> 5;
@@ -70,7 +69,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_unit_step(StepArgs a) {
   constexpr bool LOCKSTEP = WARPS > 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long ss = (long)nz * ncol;
-  const int nw = (nz + 31) >> 5;
   extern __shared__ float smem_ku[];
   float* const s_in = smem_ku;                                                 // [11][NT] inputs of the cell, parked over S3..S7
   unsigned* const s_cmask = reinterpret_cast<unsigned*>(s_in + 11 * NT);       // [WARPS][nz] busy lanes of every (group, level)

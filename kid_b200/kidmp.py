@@ -96,6 +96,10 @@ def load(build_if_missing=True):
         path = os.environ.get("KIDMP_LIB")          # tools/state_hash.py: compare two builds of the library bit for bit
         if not path:
             path = _build.LIB
+            # under torchrun only local rank 0 rebuilds a stale library; the other ranks take the file that is there
+            # (one build instead of eight, and nobody dlopens a file that is being replaced)
+            if os.path.exists(path) and int(os.environ.get("LOCAL_RANK", "0")) != 0:
+                build_if_missing = False
             if build_if_missing:
                 try:
                     _build.build()

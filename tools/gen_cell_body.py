@@ -78,7 +78,8 @@ rep('''            if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * (
           }
         }
 ''')
-assert 'warm_above' not in body and '_up' not in body.replace('vts_up','X') or True
+rep("        float v_r, v_nr, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;", "        float v_r, v_nr, v_i = 0.f, v_ni = 0.f;")
+rep("nc1d = s_in[9 * NT + tid], dzq = s_in[10 * NT + tid];", "nc1d = s_in[9 * NT + tid];")
 for bad in ('warm_above','vtr_up','vtnr_up','vti_up','vtni_up','vts_up','vtg_up','nstep_','ksed_','N0_min_'):
     assert bad not in body, bad
 open(os.path.join(ROOT, 'kid_b200', 'csrc', 'kidmp_cell_body.inc'), 'w').write(body)
