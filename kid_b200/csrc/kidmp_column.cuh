@@ -14,6 +14,8 @@
 //                  level by level: every vertical dependency of the scheme runs from the top (graupel N0
 //                  running minimum M:1648, `k_0` M:1635, fall-speed carry-down M:3235), so it is carried
 //                  along the sweep.  24 values per level are handed to the sedimentation kernel.
+//                  (kidmp_units.cuh holds k_unit_step, the same cell code with (32 columns x ONE level) as a warp's
+//                  unit of work: the kernel of choice for domains that cannot fill the GPU with a column walk.)
 //   k_sediment     sub-stepped upwind sedimentation (M:3365-3578), instant melt/freeze (M:3584-3606),
 //                  apply tendencies and final clamps (M:3623-3686), coalesced stores.
 //   k_diag_columns the eight domain sums in column order (bitwise reproducible), k_diag_reduce adds the blocks.
