@@ -213,6 +213,7 @@ int ensure_constants(kidmp_handle* h) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_const_owner != h) {
     CK(h, cudaMemcpyToSymbolAsync(ck, &h->kc, sizeof(KConst), 0, cudaMemcpyHostToDevice, h->stream));
+    k_n0_lo<<<1, 1, 0, h->stream>>>();               // the per-run graupel intercept constant (kidmp_column.cuh)
     g_const_owner = h;
   }
   return 0;
@@ -285,33 +286,39 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   k_list_scan<<<1, 1024, 0, s>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
   k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
   // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
-  // dynamic shared memory of the physics kernel: 116 bytes per thread (vertical carries, parked inputs) (above 48 KB needs the opt-in)
+  // dynamic shared memory of the physics kernel: 84 bytes per thread (vertical carries, parked inputs; +40 fused)
 #ifndef K1_BARS
 #define K1_BARS 11           // stage barriers of the lockstep blocks: level top, before S6, before S9 (bit i = LOCKBAR(i))
 #endif
 #define LAUNCH_K1(KERNEL, GRID, THREADS, SMEM, ARGS)                                                              \
   do {                                                                                                            \
     static bool attr_set = false;                                                                                 \
-    if (!attr_set) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (THREADS) * (SMEM)); attr_set = true; } \
+    if (!attr_set) {                                                                                              \
+      cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (THREADS) * (SMEM));               \
+      /* the smallest carve-out that holds the block (+1 KB the system keeps): the rest of the 256 KB is L1 */     \
+      cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout,                                 \
+                           (int)((((size_t)(THREADS) * (SMEM) + 1024) * 100) / (228 * 1024)));                     \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
     KERNEL<<<(GRID), (THREADS), (THREADS) * (SMEM), s>>>(ARGS);                                                    \
   } while (0)
   // grid: worst case (every column cloudy), rounded up to whole waves of `minb` blocks per SM (see the kernel)
   auto grid = [&](int w, int minb) { const long wave = (long)h->nsm * minb; return (unsigned)(((ngroups + w - 1) / w + wave - 1) / wave * wave); };
   // measured alternatives (profiles/r01_ncu_step_kernels.md): 16 / 20 / 28 / 32 warps, 2x12 and 3x8 warps per SM, other barrier sets
   auto physics = [&](const StepArgs& x, bool fused) {
-    if (x.rates) LAUNCH_K1((k_column_step<16, 1, K1_BARS, true, false>), grid(16, 1), 512, 116, x);   // with the 36 save_dg rates
+    if (x.rates) LAUNCH_K1((k_column_step<16, 1, K1_BARS, true, false>), grid(16, 1), 512, 84, x);   // with the 36 save_dg rates
     else if (warps >= 24) {
-      if (fused) LAUNCH_K1((k_column_step<24, 1, K1_BARS, false, true>), grid(24, 1), 768, 156, x);
-      else LAUNCH_K1((k_column_step<24, 1, K1_BARS, false, false>), grid(24, 1), 768, 116, x);
+      if (fused) LAUNCH_K1((k_column_step<24, 1, K1_BARS, false, true>), grid(24, 1), 768, 124, x);
+      else LAUNCH_K1((k_column_step<24, 1, K1_BARS, false, false>), grid(24, 1), 768, 84, x);
     } else if (warps >= 16) {
-      if (fused) LAUNCH_K1((k_column_step<16, 1, K1_BARS, false, true>), grid(16, 1), 512, 156, x);
-      else LAUNCH_K1((k_column_step<16, 1, K1_BARS, false, false>), grid(16, 1), 512, 116, x);
+      if (fused) LAUNCH_K1((k_column_step<16, 1, K1_BARS, false, true>), grid(16, 1), 512, 124, x);
+      else LAUNCH_K1((k_column_step<16, 1, K1_BARS, false, false>), grid(16, 1), 512, 84, x);
     } else if (warps >= 8) {                                                                     // two 8-warp blocks per SM
-      if (fused) LAUNCH_K1((k_column_step<8, 2, K1_BARS, false, true>), grid(8, 2), 256, 156, x);
-      else LAUNCH_K1((k_column_step<8, 2, K1_BARS, false, false>), grid(8, 2), 256, 116, x);
+      if (fused) LAUNCH_K1((k_column_step<8, 2, K1_BARS, false, true>), grid(8, 2), 256, 124, x);
+      else LAUNCH_K1((k_column_step<8, 2, K1_BARS, false, false>), grid(8, 2), 256, 84, x);
     } else {
-      if (fused) LAUNCH_K1((k_column_step<1, 12, 0, false, true>), grid(1, 12), 32, 156, x);
-      else LAUNCH_K1((k_column_step<1, 12, 0, false, false>), grid(1, 12), 32, 116, x);
+      if (fused) LAUNCH_K1((k_column_step<1, 12, 0, false, true>), grid(1, 12), 32, 124, x);
+      else LAUNCH_K1((k_column_step<1, 12, 0, false, false>), grid(1, 12), 32, 84, x);
     }
   };
   // Which physics kernel.  The unit-parallel one (kidmp_units.cuh) runs a domain's (32 columns x 1 level) units side by

@@ -119,6 +119,8 @@ __device__ __forceinline__ double graupel_n0_exp(float xslw1, float rg) {
   return fmax((double)KP_GONV_MIN, fmin(N0_exp, (double)KP_GONV_MAX));
 }
 KIDMP_HELPER double graupel_n0_lo() { return graupel_n0_exp(0.01f, R1); }
+__device__ double g_n0_lo;                                 // graupel_n0_lo(), evaluated once at init by k_n0_lo
+__global__ void k_n0_lo() { g_n0_lo = graupel_n0_lo(); }
 KIDMP_HELPER void graupel_n0(bool above_k0, bool L_qr, bool L_qg, float mvd_r, float rg, double n0_lo, double& N0_min,
                              double& ilamg, double& N0_g) {
   const bool slw = above_k0 && L_qr && mvd_r > 100.E-6f;
@@ -392,17 +394,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
       // carried from the level above
       // They are touched once per level and live for the whole sweep: kept in shared memory (72 bytes per
       // thread) instead of 20 registers that the register allocator would have to spill around the rates.
+      // 84 bytes per thread: 768 threads fit the 64 KB shared-memory carve-out and leave 192 KB of the SM to L1, which
+      // the register spills and table gathers of the cell code live on
       extern __shared__ double smem_carry[];
       constexpr int NT = WARPS * 32;
-      double* const s_d = smem_carry;                                   // [2][NT]
-      float* const s_f = reinterpret_cast<float*>(smem_carry + 2 * NT); // [6][NT]
-      int* const s_i = reinterpret_cast<int*>(s_f + 6 * NT);            // [8][NT]
-      float* const s_in = reinterpret_cast<float*>(s_i + 8 * NT);       // [11][NT] this level's inputs, parked over S3..S7
-      double* const s_wp = reinterpret_cast<double*>(s_in + 11 * NT);   // FUSE: [2][NT] liquid / ice water path so far
+      float* const s_in = reinterpret_cast<float*>(smem_carry);         // [9][NT] this level's inputs, parked over S3..S7
+      float* const s_n0 = s_in + 9 * NT;                                // [2][NT] graupel N0 running minima (f32 numbers, M:1646-1648)
+      float* const s_f = s_n0 + 2 * NT;                                 // [6][NT] fall speeds of the level above
+      unsigned short* const s_i = reinterpret_cast<unsigned short*>(s_f + 6 * NT);   // [8][NT] sub-step counts (capped), top sedimenting levels
+      double* const s_wp = reinterpret_cast<double*>(s_i + 8 * NT);     // FUSE: [2][NT] liquid / ice water path so far
       float* const s_flux = reinterpret_cast<float*>(s_wp + 2 * NT);    // FUSE: [6][NT] sedimentation fluxes of the level above
       const int tid = threadIdx.x;
-#define N0_min_a s_d[tid]
-#define N0_min_b s_d[NT + tid]
+#define N0_min_a s_n0[tid]
+#define N0_min_b s_n0[NT + tid]
 #define vtr_up s_f[tid]
 #define vtnr_up s_f[NT + tid]
 #define vti_up s_f[2 * NT + tid]
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
 #define ksed_i s_i[5 * NT + tid]
 #define ksed_s s_i[6 * NT + tid]
 #define ksed_g s_i[7 * NT + tid]
-      N0_min_a = (double)KP_GONV_MAX; N0_min_b = (double)KP_GONV_MAX;
+      N0_min_a = KP_GONV_MAX; N0_min_b = KP_GONV_MAX;
       bool warm_above_a = false, warm_above_b = false;     // any level >= k with temp >= 270.65 (k_0, M:1635)
       vtr_up = 0.f; vtnr_up = 0.f; vti_up = 0.f; vtni_up = 0.f; vts_up = 0.f; vtg_up = 0.f;
       nstep_r = 0; nstep_i = 0; nstep_s = 0; nstep_g = 0;
@@ -450,8 +454,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
       };
 
       // graupel intercept of a level without rain and graupel (xslw1 = 0.01, rg = R1 in M:1639-1646): the only
-      // thing such a level contributes to the running minimum of M:1648
-      const double n0_empty = graupel_n0_lo();
+      // thing such a level contributes to the running minimum of M:1648.  A per-run constant: k_n0_lo evaluates it once
+      // at init with the routines used here, and the sweep reads it where needed instead of holding it in registers.
+#define n0_empty g_n0_lo
 
       // ================= pass 1: top-down, S1..S13 per level ====================================
 #pragma unroll 1
@@ -469,8 +474,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           sc[0] = qv1d; sc[ss] = qc1d; sc[2 * ss] = qi1d; sc[3 * ss] = qr1d; sc[4 * ss] = qs1d; sc[5 * ss] = qg1d;
           sc[6 * ss] = ni1d; sc[7 * ss] = nr1d; sc[8 * ss] = t1d;
         }
-        // U1: nc1d as the WRF driver sets it when the scheme is not aerosol aware, M:957-964
-        float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));
 
         // ---- empty level: no hydrometeor in any of the warp's columns and none at or above ice saturation.
         // Every process rate is then exactly zero (each is gated by a species flag or by ssati / ssatw,
@@ -490,19 +493,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           if (__all_sync(0xffffffffu, !(ssati > 0.0f) && !(ssatw > EPSF))) {
             if (!iiwarm) {
               if (temp >= 270.65f) { warm_above_a = true; warm_above_b = true; }
-              N0_min_a = fmin(n0_empty, N0_min_a);
-              N0_min_b = fmin(n0_empty, N0_min_b);
+              N0_min_a = (float)fmin(n0_empty, (double)N0_min_a);
+              N0_min_b = (float)fmin(n0_empty, (double)N0_min_b);
             }
             const float v_r = vtr_up, v_nr = vtnr_up, v_i = vti_up, v_ni = vtni_up, v_s = vts_up, v_g = vtg_up;
             if (fmaxf(v_r, v_nr) > 1.E-3f) {
-              ksed_r = max(ksed_r, k + 1);
+              ksed_r = (unsigned short)max((int)ksed_r, k + 1);
               const float delta_tp = dzq / (fmaxf(v_r, v_nr));
-              nstep_r = max(nstep_r, (int)(DT / delta_tp + 1.f));
+              nstep_r = (unsigned short)min(max((int)nstep_r, (int)(DT / delta_tp + 1.f)), KP_NSTEP_MAX);
             }
             if (!iiwarm) {
-              if (v_i > 1.E-3f) { ksed_i = max(ksed_i, k + 1); const float d = dzq / v_i; nstep_i = max(nstep_i, (int)(DT / d + 1.f)); }
-              if (v_s > 1.E-3f) { ksed_s = max(ksed_s, k + 1); const float d = dzq / v_s; nstep_s = max(nstep_s, (int)(DT / d + 1.f)); }
-              if (v_g > 1.E-3f) { ksed_g = max(ksed_g, k + 1); const float d = dzq / v_g; nstep_g = max(nstep_g, (int)(DT / d + 1.f)); }
+              if (v_i > 1.E-3f) { ksed_i = (unsigned short)max((int)ksed_i, k + 1); const float d = dzq / v_i; nstep_i = (unsigned short)min(max((int)nstep_i, (int)(DT / d + 1.f)), KP_NSTEP_MAX); }
+              if (v_s > 1.E-3f) { ksed_s = (unsigned short)max((int)ksed_s, k + 1); const float d = dzq / v_s; nstep_s = (unsigned short)min(max((int)nstep_s, (int)(DT / d + 1.f)), KP_NSTEP_MAX); }
+              if (v_g > 1.E-3f) { ksed_g = (unsigned short)max((int)ksed_g, k + 1); const float d = dzq / v_g; nstep_g = (unsigned short)min(max((int)nstep_g, (int)(DT / d + 1.f)), KP_NSTEP_MAX); }
             }
             if (FUSE && active) {
               const float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
@@ -570,7 +573,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           L_qc = true;
           nc = Nt_c;   // the lamc/xDc clamps of M:1399-1408 only feed nc, overwritten at M:1410
         } else {
-          qc1d = 0.0f; nc1d = 0.0f; rc = R1; nc = 2.f; L_qc = false;
+          qc1d = 0.0f; rc = R1; nc = 2.f; L_qc = false;
         }
         if (qi1d > R1) {
           ri = qi1d * rho;
@@ -613,7 +616,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         // the inputs are not needed again before S8: parked in shared memory while the rates fill the registers
         s_in[tid] = t1d; s_in[NT + tid] = qv1d; s_in[2 * NT + tid] = qc1d; s_in[3 * NT + tid] = qi1d; s_in[4 * NT + tid] = qr1d;
         s_in[5 * NT + tid] = qs1d; s_in[6 * NT + tid] = qg1d; s_in[7 * NT + tid] = ni1d; s_in[8 * NT + tid] = nr1d;
-        s_in[9 * NT + tid] = nc1d; s_in[10 * NT + tid] = dzq;
 
         // ---- S2, M:1503-1533 -------------------------------------------------------------------
         float tempc = temp - 273.15f;
@@ -658,7 +660,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           }
           // ---- S4, M:1633-1654 graupel intercept ------------------------------------------------
           if (temp >= 270.65f) warm_above_a = true;
-          { double nm = N0_min_a; graupel_n0(!warm_above_a && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_a = nm; }
+          { double nm = N0_min_a; graupel_n0(!warm_above_a && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_a = (float)nm; }
         }
         // M:1661-1666 rain slope and intercept.  Without rain (rr = R1, nr = R2) every reader of lamr, ilamr, N0_r
         // and mvd_r is switched off (L_qr at M:1676, M:1724, M:2880; rr >= r_r(1) at M:1818, M:1964, M:2028, M:2188)
@@ -1049,7 +1051,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         {   // inputs back from shared memory (these names shadow the ones loaded at the top of the level)
         const float t1d = s_in[tid], qv1d = s_in[NT + tid], qc1d = s_in[2 * NT + tid], qi1d = s_in[3 * NT + tid],
                     qr1d = s_in[4 * NT + tid], qs1d = s_in[5 * NT + tid], qg1d = s_in[6 * NT + tid], ni1d = s_in[7 * NT + tid],
-                    nr1d = s_in[8 * NT + tid], nc1d = s_in[9 * NT + tid], dzq = s_in[10 * NT + tid];
+                    nr1d = s_in[8 * NT + tid];
+        // U1 again (nc1d = 0 without cloud water, M:1409); dz of the level
+        const float nc1d = (qc1d > R1) ? Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f))) : 0.0f;
+        const float dzq = a.dz_col ? a.dz_col[o + col] : a.dz[k];
         // ---- S8, M:2393-2569 tendencies and number/mass balances ------------------------------------
         float tt, qvt, qct, qit, qrt, qst, qgt, nit, nrt, nct;
         {
@@ -1181,7 +1186,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             // smod (M:2706-2717) is not read again by any live code
           }
           if (temp >= 270.65f) warm_above_b = true;
-          { double nm = N0_min_b; graupel_n0(!warm_above_b && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_b = nm; }
+          { double nm = N0_min_b; graupel_n0(!warm_above_b && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_b = (float)nm; }
         }
         if (L_qr) {                                                             // M:2750-2755, as at M:1661
           if (lamr_stale) { lamr = rain_lam(nr, rr); mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr); lamr_stale = false; }
@@ -1306,9 +1311,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           v_r = vtr_up; v_nr = vtnr_up;
         }
         if (fmaxf(v_r, v_nr) > 1.E-3f) {
-          ksed_r = max(ksed_r, k + 1);
+          ksed_r = (unsigned short)max((int)ksed_r, k + 1);
           const float delta_tp = dzq / (fmaxf(v_r, v_nr));
-          nstep_r = max(nstep_r, (int)(DT / delta_tp + 1.f));
+          nstep_r = (unsigned short)min(max((int)nstep_r, (int)(DT / delta_tp + 1.f)), KP_NSTEP_MAX);
         }
         if (!iiwarm) {
           if (ri > R1) {
@@ -1320,9 +1325,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             v_i = vti_up; v_ni = vtni_up;
           }
           if (v_i > 1.E-3f) {
-            ksed_i = max(ksed_i, k + 1);
+            ksed_i = (unsigned short)max((int)ksed_i, k + 1);
             const float delta_tp = dzq / v_i;
-            nstep_i = max(nstep_i, (int)(DT / delta_tp + 1.f));
+            nstep_i = (unsigned short)min(max((int)nstep_i, (int)(DT / delta_tp + 1.f)), KP_NSTEP_MAX);
           }
           if (rs > R1) {
             const float xDs = smoc / smob;
@@ -1343,9 +1348,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             v_s = vts_up;
           }
           if (v_s > 1.E-3f) {
-            ksed_s = max(ksed_s, k + 1);
+            ksed_s = (unsigned short)max((int)ksed_s, k + 1);
             const float delta_tp = dzq / v_s;
-            nstep_s = max(nstep_s, (int)(DT / delta_tp + 1.f));
+            nstep_s = (unsigned short)min(max((int)nstep_s, (int)(DT / delta_tp + 1.f)), KP_NSTEP_MAX);
           }
           if (rg > R1) {
             const float vtg = (float)((double)(rhof * KP_AV_G * ck.cgg[5] * ck.ogg3) * pow_d(ilamg, (double)KP_BV_G));
@@ -1354,9 +1359,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             v_g = vtg_up;
           }
           if (v_g > 1.E-3f) {
-            ksed_g = max(ksed_g, k + 1);
+            ksed_g = (unsigned short)max((int)ksed_g, k + 1);
             const float delta_tp = dzq / v_g;
-            nstep_g = max(nstep_g, (int)(DT / delta_tp + 1.f));
+            nstep_g = (unsigned short)min(max((int)nstep_g, (int)(DT / delta_tp + 1.f)), KP_NSTEP_MAX);
           }
         }
         vtr_up = v_r; vtnr_up = v_nr; vti_up = v_i; vtni_up = v_ni; vts_up = v_s; vtg_up = v_g;
@@ -1395,10 +1400,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         int* ci = a.colint + col;
         // U12: the reference leaves the sub-step count unbounded (M:3242); on non-physical input (dt*v/dz in the
         // millions) that is a kernel that never ends, so it is capped where no real case comes near
-        ci[0] = min(nstep_r, KP_NSTEP_MAX); ci[ncol] = min(nstep_i, KP_NSTEP_MAX); ci[2 * ncol] = min(nstep_s, KP_NSTEP_MAX);
-        ci[3 * ncol] = min(nstep_g, KP_NSTEP_MAX);
+        ci[0] = nstep_r; ci[ncol] = nstep_i; ci[2 * ncol] = nstep_s; ci[3 * ncol] = nstep_g;      // capped when they were stored
         ci[4 * ncol] = ksed_r; ci[5 * ncol] = ksed_i; ci[6 * ncol] = ksed_s; ci[7 * ncol] = ksed_g;
-        if (max(max(nstep_r, nstep_i), max(nstep_s, nstep_g)) > 1) {     // counted in both modes: the host picks the mode of the next step
+        if (max(max((int)nstep_r, (int)nstep_i), max((int)nstep_s, (int)nstep_g)) > 1) {     // counted in both modes: the host picks the mode of the next step
           const int at = atomicAdd(a.redo_count, 1);
           if (FUSE) a.redo_list[at] = (int)col;
         }
@@ -1408,6 +1412,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
 }
 
 #undef LOCKBAR
+#undef n0_empty
 #undef N0_min_a
 #undef N0_min_b
 #undef vtr_up

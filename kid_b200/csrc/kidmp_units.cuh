@@ -32,7 +32,7 @@ __device__ __forceinline__ void graupel_slope(double N0_exp, bool L_qg, float rg
 
 constexpr int KU_MAXNZ = 256;
 __host__ __device__ constexpr int ku_smem_bytes(int threads, int nz) {
-  return threads * 11 * 4 + (threads / 32) * nz * 4 + (threads / 32) * nz * 2 + 64;
+  return threads * 9 * 4 + (threads / 32) * nz * 4 + (threads / 32) * nz * 2 + 64;
 }
 
 #define R1 KP_R1
@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_unit_step(StepArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long ss = (long)nz * ncol;
   extern __shared__ float smem_ku[];
-  float* const s_in = smem_ku;                                                 // [11][NT] inputs of the cell, parked over S3..S7
-  unsigned* const s_cmask = reinterpret_cast<unsigned*>(s_in + 11 * NT);       // [WARPS][nz] busy lanes of every (group, level)
+  float* const s_in = smem_ku;                                                 // [9][NT] inputs of the cell, parked over S3..S7
+  unsigned* const s_cmask = reinterpret_cast<unsigned*>(s_in + 9 * NT);       // [WARPS][nz] busy lanes of every (group, level)
   unsigned short* const s_unit = reinterpret_cast<unsigned short*>(s_cmask + WARPS * nz);   // [<= WARPS*nz] units, level-major: k * WARPS + (group | packed warp)
   __shared__ int s_nunits;
   for (int i = tid; i < WARPS * nz; i += NT) s_cmask[i] = 0u;
@@ -191,9 +191,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_unit_step(StepArgs a) {
         float qc1d = a.f[F_QC][o + col], qi1d = a.f[F_QI][o + col], qr1d = a.f[F_QR][o + col], qs1d = a.f[F_QS][o + col],
               qg1d = a.f[F_QG][o + col];
         float ni1d = a.f[F_NI][o + col], nr1d = a.f[F_NR][o + col];
-        const float dzq = a.dz_col ? a.dz_col[o + col] : a.dz[k];
-        // U1: nc1d as the WRF driver sets it when the scheme is not aerosol aware, M:957-964
-        float nc1d = Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));
         const double n0_min_a = iiwarm ? (double)KP_GONV_MAX : (double)a.scratch[SC_N0A * ss + o + col];
         bool warm9 = false;
         double n0b_lo = n0_empty, n0b_slw = n0_empty;

@@ -21,11 +21,11 @@ def rep(old,new,cnt=1):
     body=body.replace(old,new)
 # S4
 rep('''          if (temp >= 270.65f) warm_above_a = true;
-          { double nm = N0_min_a; graupel_n0(!warm_above_a && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_a = nm; }''',
+          { double nm = N0_min_a; graupel_n0(!warm_above_a && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_a = (float)nm; }''',
 '''          graupel_slope(n0_min_a, L_qg, rg, ilamg, N0_g);       // the running minimum of M:1648 comes from phase 1''')
 # S10
 rep('''          if (temp >= 270.65f) warm_above_b = true;
-          { double nm = N0_min_b; graupel_n0(!warm_above_b && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_b = nm; }''',
+          { double nm = N0_min_b; graupel_n0(!warm_above_b && k > 0, L_qr, L_qg, mvd_r, rg, n0_empty, nm, ilamg, N0_g); N0_min_b = (float)nm; }''',
 '''          // M:2721-2731: whether this level lies above k_0 depends on the updated temperatures of the levels above,
           // which phase 3 knows: both values of the intercept are handed to it (they differ only with supercooled rain),
           // and it evaluates the slope, which only the graupel fall speed of S13 reads
@@ -37,9 +37,9 @@ rep('''        } else {
           v_r = vtr_up; v_nr = vtnr_up;
         }
         if (fmaxf(v_r, v_nr) > 1.E-3f) {
-          ksed_r = max(ksed_r, k + 1);
+          ksed_r = (unsigned short)max((int)ksed_r, k + 1);
           const float delta_tp = dzq / (fmaxf(v_r, v_nr));
-          nstep_r = max(nstep_r, (int)(DT / delta_tp + 1.f));
+          nstep_r = (unsigned short)min(max((int)nstep_r, (int)(DT / delta_tp + 1.f)), KP_NSTEP_MAX);
         }''','''        } else {
           v_r = 0.f; v_nr = 0.f;                              // phase 3: the speeds of the level above (M:3235)
         }''')
@@ -47,9 +47,9 @@ rep('''          } else {
             v_i = vti_up; v_ni = vtni_up;
           }
           if (v_i > 1.E-3f) {
-            ksed_i = max(ksed_i, k + 1);
+            ksed_i = (unsigned short)max((int)ksed_i, k + 1);
             const float delta_tp = dzq / v_i;
-            nstep_i = max(nstep_i, (int)(DT / delta_tp + 1.f));
+            nstep_i = (unsigned short)min(max((int)nstep_i, (int)(DT / delta_tp + 1.f)), KP_NSTEP_MAX);
           }''','''          }''')
 rep('''            if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * ((v_r - vts * vts_boost) / (temp - T_0)));
             else v_s = vts * vts_boost;
@@ -57,9 +57,9 @@ rep('''            if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * (
             v_s = vts_up;
           }
           if (v_s > 1.E-3f) {
-            ksed_s = max(ksed_s, k + 1);
+            ksed_s = (unsigned short)max((int)ksed_s, k + 1);
             const float delta_tp = dzq / v_s;
-            nstep_s = max(nstep_s, (int)(DT / delta_tp + 1.f));
+            nstep_s = (unsigned short)min(max((int)nstep_s, (int)(DT / delta_tp + 1.f)), KP_NSTEP_MAX);
           }
           if (rg > R1) {
             const float vtg = (float)((double)(rhof * KP_AV_G * ck.cgg[5] * ck.ogg3) * pow_d(ilamg, (double)KP_BV_G));
@@ -68,9 +68,9 @@ rep('''            if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * (
             v_g = vtg_up;
           }
           if (v_g > 1.E-3f) {
-            ksed_g = max(ksed_g, k + 1);
+            ksed_g = (unsigned short)max((int)ksed_g, k + 1);
             const float delta_tp = dzq / v_g;
-            nstep_g = max(nstep_g, (int)(DT / delta_tp + 1.f));
+            nstep_g = (unsigned short)min(max((int)nstep_g, (int)(DT / delta_tp + 1.f)), KP_NSTEP_MAX);
           }
         }
         vtr_up = v_r; vtnr_up = v_nr; vti_up = v_i; vtni_up = v_ni; vts_up = v_s; vtg_up = v_g;
@@ -79,7 +79,7 @@ rep('''            if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * (
         }
 ''')
 rep("        float v_r, v_nr, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;", "        float v_r, v_nr, v_i = 0.f, v_ni = 0.f;")
-rep("nc1d = s_in[9 * NT + tid], dzq = s_in[10 * NT + tid];", "nc1d = s_in[9 * NT + tid];")
+
 for bad in ('warm_above','vtr_up','vtnr_up','vti_up','vtni_up','vts_up','vtg_up','nstep_','ksed_','N0_min_'):
     assert bad not in body, bad
 open(os.path.join(ROOT, 'kid_b200', 'csrc', 'kidmp_cell_body.inc'), 'w').write(body)
