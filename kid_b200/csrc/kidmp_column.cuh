@@ -550,6 +550,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
         double prs_iau = 0., prs_sci = 0., prs_rcs = 0., prs_scw = 0., prs_sde = 0., prs_ihm = 0., prs_ide = 0.;
         double prg_scw = 0., prg_rfz = 0., prg_gde = 0., prg_gcw = 0., prg_rci = 0., prg_rcs = 0., prg_rcg = 0., prg_ihm = 0.;
         float smo0 = 0.f, smo1 = 0.f, smob = 0.f, smoc = 0.f, smoe = 0.f, smof = 0.f;
+        bool have_smoe = false;
         float mvd_r = 0.f, mvd_c = 0.f, vts_boost = 0.f;
         double ilamg = 0., N0_g = 0., ilamr, N0_r, lamr, lamc = 0., lami, ilami;
         int nu_c = 0;
@@ -646,16 +647,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             smob = rs * ck.oams;
             const float smo2 = smob;                    // bm_s = 2 branch of M:1553
             const float* sa = c_sa; const float* sb = c_sb;
-            float loga_ = sa[1] + sa[2] * tc0 + sa[5] * tc0 * tc0 + sa[9] * tc0 * tc0 * tc0;
-            float b_ = sb[1] + sb[2] * tc0 + sb[5] * tc0 * tc0 + sb[9] * tc0 * tc0 * tc0;
-            smo0 = pow10_f(loga_) * pow_f(smo2, b_);
-            loga_ = sa[1] + sa[2] * tc0 + sa[3] + sa[4] * tc0 + sa[5] * tc0 * tc0 + sa[6] + sa[7] * tc0 * tc0
-                    + sa[8] * tc0 + sa[9] * tc0 * tc0 * tc0 + sa[10];
-            b_ = sb[1] + sb[2] * tc0 + sb[3] + sb[4] * tc0 + sb[5] * tc0 * tc0 + sb[6] + sb[7] * tc0 * tc0
-                 + sb[8] * tc0 + sb[9] * tc0 * tc0 * tc0 + sb[10];
+            // Of the six moments of M:1555-1626 the 1st and the (1+(bv_s+1)/2)-th feed deposition, sublimation and melting
+            // of every snow level.  The 0th is only read by the melting number rate (M:2242, at or above 0 C), the
+            // (bm_s+1)-th by riming (M:1905, with cloud water) and the (bv_s+2)-th by riming and by the collection of
+            // cloud ice (M:1910, M:2185): those three are evaluated where they are read.
+            float loga_ = sa[1] + sa[2] * tc0 + sa[3] + sa[4] * tc0 + sa[5] * tc0 * tc0 + sa[6] + sa[7] * tc0 * tc0
+                          + sa[8] * tc0 + sa[9] * tc0 * tc0 * tc0 + sa[10];
+            float b_ = sb[1] + sb[2] * tc0 + sb[3] + sb[4] * tc0 + sb[5] * tc0 * tc0 + sb[6] + sb[7] * tc0 * tc0
+                       + sb[8] * tc0 + sb[9] * tc0 * tc0 * tc0 + sb[10];
             smo1 = pow10_f(loga_) * pow_f(smo2, b_);
-            smoc = field_moment(tc0, ck.cse[0], smo2);
-            smoe = field_moment(tc0, ck.cse[12], smo2);
             smof = field_moment(tc0, ck.cse[15], smo2);
           }
           // ---- S4, M:1633-1654 graupel intercept ------------------------------------------------
@@ -762,8 +762,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           // M:1903-1935 riming of snow and graupel
           if (L_qc && mvd_c > D0c) {
             float xDs = 0.0f;
-            if (L_qs) xDs = smoc / smob;
+            if (L_qs) { smoc = field_moment(fminf(-0.1f, temp - 273.15f), ck.cse[0], smob); xDs = smoc / smob; }
             if (xDs > D0s) {
+              smoe = field_moment(fminf(-0.1f, temp - 273.15f), ck.cse[12], smob); have_smoe = true;
               int idx = 1 + (int)((double)NBINS * log((double)xDs / ck.Ds1) / ck.lnDs);
               idx = min(idx, (int)NBINS);
               int jc = (int)(mvd_c * 1.E6f);
@@ -924,6 +925,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
             // M:2178-2202 snow and rain collecting cloud ice (lami/xDi/oxmi as recomputed at M:2179-2183)
             if (L_qi) {
               if (rs >= ck.r_s1) {
+                if (!have_smoe) smoe = field_moment(fminf(-0.1f, temp - 273.15f), ck.cse[12], smob);
                 prs_sci = (double)(ck.t1_qs_qi * rhof * KP_EF_SI * ri * smoe);
                 pni_sci = prs_sci * (double)oxmi;
                 ni_acc -= pni_sci;
@@ -969,6 +971,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
                                  * (ck.t1_qs_me * smo1 + ck.t2_qs_me * rhof2 * vsc2 * smof));
               prr_sml = prr_sml + (double)(4218.f * ck.olfus * tempc) * (prr_rcs + prs_scw);
               prr_sml = fmin((double)(rs * odts), fmax(0., prr_sml));
+              {                                          // 0th moment, M:1557-1560
+                const float tc0 = fminf(-0.1f, temp - 273.15f);
+                const float* sa = c_sa; const float* sb = c_sb;
+                const float loga_ = sa[1] + sa[2] * tc0 + sa[5] * tc0 * tc0 + sa[9] * tc0 * tc0 * tc0;
+                const float b_ = sb[1] + sb[2] * tc0 + sb[5] * tc0 * tc0 + sb[9] * tc0 * tc0 * tc0;
+                smo0 = pow10_f(loga_) * pow_f(smob, b_);
+              }
               pnr_sml = (double)(smo0 / rs) * prr_sml * (double)pow10_f(-0.25f * tempc);
               pnr_sml = fmin((double)(smo0 * odts), pnr_sml);
               nr_acc += pnr_sml;
