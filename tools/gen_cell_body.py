@@ -79,6 +79,7 @@ rep('''            if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * (
         }
 ''')
 rep("        float v_r, v_nr, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;", "        float v_r, v_nr, v_i = 0.f, v_ni = 0.f;")
+rep("        const float dzq = a.dz_col ? a.dz_col[o + col] : a.dz[k];\n", "")      # the layer depth is only read by phase 3
 
 for bad in ('warm_above','vtr_up','vtnr_up','vti_up','vtni_up','vts_up','vtg_up','nstep_','ksed_','N0_min_'):
     assert bad not in body, bad
