@@ -41,6 +41,14 @@ module mphys_thompson09n
      type(c_ptr) :: ppt
   end type kidmp_kid_columns
 
+  ! include/kidmp.h :: kidmp_wrf_fields, (i,k,j) arrays as c_loc of (ims:ime,kms:kme,jms:jme) arrays
+  type, bind(C) :: kidmp_wrf_fields
+     integer(c_int) :: ni, nk, nj
+     type(c_ptr) :: qv, qc, qr, qi, qs, qg, ni_, nr, th, pii, p, dz
+     type(c_ptr) :: rainnc, rainncv, sr, snownc, snowncv, graupelnc, graupelncv
+     type(c_ptr) :: re_cloud, re_ice, re_snow
+  end type kidmp_wrf_fields
+
   interface
      integer(c_int) function kidmp_init(cfg, handle) bind(C, name='kidmp_init')
        import :: c_int, c_ptr, kidmp_config
@@ -61,6 +69,20 @@ module mphys_thompson09n
        import :: c_int, c_ptr
        type(c_ptr), value :: handle
      end function kidmp_finalize
+     ! tuning knobs that never change a result, e.g. kidmp_set_option(handle, 'units'//c_null_char, 1_c_int)
+     integer(c_int) function kidmp_set_option(handle, name, value) bind(C, name='kidmp_set_option')
+       import :: c_int, c_ptr, c_char
+       type(c_ptr), value :: handle
+       character(kind=c_char), intent(in) :: name(*)
+       integer(c_int), value :: value
+     end function kidmp_set_option
+     ! the WRF / MPAS shape of the same step (mp_gt_driver, M:806-1143); KiD itself does not call it
+     integer(c_int) function kidmp_mp_gt_driver(handle, w, dt_in) bind(C, name='kidmp_mp_gt_driver')
+       import :: c_int, c_ptr, c_float, kidmp_wrf_fields
+       type(c_ptr), value :: handle
+       type(kidmp_wrf_fields), intent(in) :: w
+       real(c_float), value :: dt_in
+     end function kidmp_mp_gt_driver
   end interface
 
   !Logical switches
