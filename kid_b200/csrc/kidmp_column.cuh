@@ -688,13 +688,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
           const float Dc_b = pow_f(xDc * xDc * xDc * Dc_g * Dc_g * Dc_g - xDc * xDc * xDc * xDc * xDc * xDc, 1.f / 6.f);
           const float zeta1 = 0.5f * ((6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f) + fabsf(6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f));
           const float zeta = 0.027f * rc * zeta1;
-          const float taud = 0.5f * ((0.5f * Dc_b - 7.5f) + fabsf(0.5f * Dc_b - 7.5f)) + R1;
-          const float tau = 3.72f / (rc * taud);
-          prr_wau = (double)(zeta / tau);
-          prr_wau = fmin((double)(rc * odts), prr_wau);
-          pnr_wau = prr_wau / (double)(ck.am_r * (float)nu_c * D0r * D0r * D0r);
-          pnc_wau = fmin((double)(nc * odts), prr_wau / (double)(ck.am_r * mvd_c * mvd_c * mvd_c));
-          nr_acc += pnr_wau; nc_acc -= pnc_wau;
+          // Below the autoconversion threshold zeta is exactly +0 (most cloudy cells) and so are the three rates: the
+          // divisions are skipped there (0/x takes the slow path of the division routines: 3 x ~60 instructions for
+          // nearly every cloud level, profiles/r01).  A NaN zeta (negative argument of the 6th root) takes the full path.
+          if (!(zeta == 0.0f)) {
+            const float taud = 0.5f * ((0.5f * Dc_b - 7.5f) + fabsf(0.5f * Dc_b - 7.5f)) + R1;
+            const float tau = 3.72f / (rc * taud);
+            prr_wau = (double)(zeta / tau);
+            prr_wau = fmin((double)(rc * odts), prr_wau);
+            pnr_wau = prr_wau / (double)(ck.am_r * (float)nu_c * D0r * D0r * D0r);
+            pnc_wau = fmin((double)(nc * odts), prr_wau / (double)(ck.am_r * mvd_c * mvd_c * mvd_c));
+            nr_acc += pnr_wau; nc_acc -= pnc_wau;
+          }
         }
         if (L_qr && mvd_r > D0r && mvd_c > D0c) {
           lamr = (double)1.f / ilamr;
@@ -871,7 +876,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_column_step(StepArgs a) {
               const float xni = (float)((double)ni + (pni_rfz + pni_wfz) * (double)DT);
               pni_inu = (double)(0.5f * (xnc - xni + fabsf(xnc - xni)) * odts);
               pri_inu = fmin((double)rate_max, (double)KP_XM0I * pni_inu);
-              pni_inu = pri_inu / (double)KP_XM0I;
+              pni_inu = (pri_inu == 0.0) ? pri_inu : pri_inu / (double)KP_XM0I;      // (a zero keeps its sign either way)
               ni_acc += pni_inu;
             }
             // M:2116-2149 deposition / sublimation of cloud ice, ice -> snow
