@@ -72,26 +72,41 @@ __device__ __forceinline__ int decade_guess(float x) {
   const float l2 = (float)((b >> 23) - 127) + __int_as_float((b & 0x007fffff) | 0x3f800000) - 1.0f;
   return __float2int_rn(l2 * 0.30103f);
 }
+// When x / 10.**n0 is well inside [1, 10) no other candidate can match (x / 10.**(n0-1) is ten times larger, x / 10.**(n0+1)
+// ten times smaller, and a division is off by half an ulp at most), so the search of the reference is only walked,
+// in its own order, when the quotient is within 1e-5 of a decade boundary or the guess is a decade off.
 KIDMP_HELPER int decade_idx_f(float x, int n2, int ntb) {
   const int n0 = decade_guess(x);
-  int n = n0 + 1;
+  const float q0 = x / ck.p10[n0 + 32];
+  int n = n0;
+  float qn = q0;
+  if (!(q0 > 1.00001f && q0 < 9.9999f)) {
+    n = n0 + 1;
 #pragma unroll
-  for (int nn = -1; nn <= 1; ++nn) {
-    const float q = x / ck.p10[n0 + nn + 32];
-    if (q >= 1.0f && q < 10.0f) { n = n0 + nn; break; }
+    for (int nn = -1; nn <= 1; ++nn) {
+      const float q = x / ck.p10[n0 + nn + 32];
+      if (q >= 1.0f && q < 10.0f) { n = n0 + nn; break; }
+    }
+    qn = x / ck.p10[n + 32];
   }
-  const int idx = (int)(x / ck.p10[n + 32]) + 9 * (n - n2);
+  const int idx = (int)qn + 9 * (n - n2);
   return max(1, min(idx, ntb));
 }
 KIDMP_HELPER int decade_idx_d(double x, int n2, int ntb) {
   const int n0 = decade_guess((float)x);
-  int n = n0 + 1;
+  const double q0 = x / (double)ck.p10[n0 + 32];
+  int n = n0;
+  double qn = q0;
+  if (!(q0 > 1.00001 && q0 < 9.9999)) {
+    n = n0 + 1;
 #pragma unroll
-  for (int nn = -1; nn <= 1; ++nn) {
-    const double q = x / (double)ck.p10[n0 + nn + 32];
-    if (q >= 1.0 && q < 10.0) { n = n0 + nn; break; }
+    for (int nn = -1; nn <= 1; ++nn) {
+      const double q = x / (double)ck.p10[n0 + nn + 32];
+      if (q >= 1.0 && q < 10.0) { n = n0 + nn; break; }
+    }
+    qn = x / (double)ck.p10[n + 32];
   }
-  const int idx = (int)(x / (double)ck.p10[n + 32]) + 9 * (n - n2);
+  const int idx = (int)qn + 9 * (n - n2);
   return max(1, min(idx, ntb));
 }
 

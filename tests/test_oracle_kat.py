@@ -266,3 +266,54 @@ def test_wrf_driver_algebra_on_the_oracle(oracle_mixed):
     assert np.array_equal(re["re_cloud"].reshape(nk), np.clip(rc, np.float32(2.49e-6), np.float32(50e-6)))
     assert np.array_equal(re["re_ice"].reshape(nk), np.clip(ri, np.float32(4.99e-6), np.float32(125e-6)))
     assert np.array_equal(re["re_snow"].reshape(nk), np.clip(rs, np.float32(9.99e-6), np.float32(999e-6)))
+
+
+def test_decade_index_shortcut_of_the_kernels_equals_the_reference_search():
+    """The kernels' decade-mantissa index (kidmp_column.cuh decade_idx_f: a bit-level guess of the decade, ONE division when
+    the quotient is well inside [1, 10), the reference's three-candidate search otherwise) restated in float32 numpy,
+    against the oracle's restatement of M:1762-1774 - on random values and on the ulps around every decade boundary."""
+    from oracle.oracle import lib
+    L = lib()
+
+    def powi10(m):                                   # libgcc __powisf2, as kidmp_hostinit.h
+        n = abs(m)
+        x = np.float32(10.0)
+        y = x if n % 2 else np.float32(1.0)
+        n >>= 1
+        while n:
+            x = np.float32(x * x)
+            if n % 2:
+                y = np.float32(y * x)
+            n >>= 1
+        return np.float32(1.0) / y if m < 0 else y
+    p10 = np.array([powi10(n) for n in range(-32, 32)], np.float32)
+
+    def kernel_index(x, n2, ntb):
+        x = np.float32(x)
+        b = int(x.view(np.int32))
+        l2 = np.float32(np.float32((b >> 23) - 127) + np.int32((b & 0x007fffff) | 0x3f800000).view(np.float32) - np.float32(1.0))
+        n0 = int(np.rint(np.float32(l2 * np.float32(0.30103))))
+        q0 = np.float32(x / p10[n0 + 32])
+        n, qn = n0, q0
+        if not (q0 > np.float32(1.00001) and q0 < np.float32(9.9999)):
+            n = n0 + 1
+            for nn in (-1, 0, 1):
+                q = np.float32(x / p10[n0 + nn + 32])
+                if q >= 1.0 and q < 10.0:
+                    n = n0 + nn
+                    break
+            qn = np.float32(x / p10[n + 32])
+        return max(1, min(int(qn) + 9 * (n - n2), ntb))
+
+    rng = np.random.default_rng(5)
+    vals = list(np.exp(rng.uniform(np.log(1e-9), np.log(1e7), 40000)).astype(np.float32))
+    for d in range(-9, 8):                           # every float within 40 ulps of 10**d, and of 10**d as powi builds it
+        for c in (np.float32(10.0) ** d, powi10(d)):
+            base = int(np.float32(c).view(np.int32))
+            vals += [np.int32(base + k).view(np.float32) for k in range(-40, 41)]
+    bad = 0
+    for x in vals:
+        for n2, ntb in ((-6, 37), (-10, 64), (-2, 55)):
+            if kernel_index(x, n2, ntb) != L.kor_decade_index(float(x), n2, ntb):
+                bad += 1
+    assert bad == 0, bad
