@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkidmp.so")
 SOURCES = ["kidmp_api.cu"]
-DEPS = ["kidmp_api.cu", "kidmp_column.cuh", "kidmp_tables.cuh", "kidmp_math.cuh", "kidmp_fastmath.h", "kidmp_kid.cuh", "kidmp_wrf.cuh", "kidmp_units.cuh", "kidmp_cell_body.inc", "kidmp_hostinit.h",
+DEPS = ["kidmp_api.cu", "kidmp_column.cuh", "kidmp_tables.cuh", "kidmp_math.cuh", "kidmp_fastmath.h", "kidmp_kid.cuh", "kidmp_wrf.cuh", "kidmp_cells.cuh", "kidmp_hostinit.h",
         "kidmp_internal.h", os.path.join("..", "..", "include", "kidmp.h")]
 
 

@@ -1,5 +1,5 @@
 // kidmp_api.cu - the C ABI of include/kidmp.h over the CUDA kernels.
-// One translation unit: kidmp_tables.cuh (K3 table build) + kidmp_column.cuh (K1+K2 column step).
+// One translation unit: kidmp_tables.cuh (K3 table build) + kidmp_column.cuh / kidmp_cells.cuh (the step).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (see kid_b200/build.py).
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -15,8 +15,8 @@
 #include "kidmp_hostinit.h"
 #include "kidmp_tables.cuh"
 #include "kidmp_column.cuh"
+#include "kidmp_cells.cuh"
 #include "kidmp_kid.cuh"
-#include "kidmp_units.cuh"
 #include "kidmp_wrf.cuh"
 
 using namespace kidmp;
@@ -42,16 +42,18 @@ struct kidmp_handle {
   float* d_ppt = nullptr;        // [4][ncol]
   float* d_stage = nullptr;      // staging for layout conversion, [nz][ncol]
   double* d_partial = nullptr; long partial_blocks = 0;
-  float* d_scratch = nullptr; size_t scratch_cells = 0;   // [SC_N][nz][ncol] hand-off between the two step kernels
-  int* d_colint = nullptr; long scratch_cols = 0;
-  double* d_coldiag = nullptr;                            // [2][ncol] per-column water paths for the ordered domain sums
-  int* d_redo = nullptr;                                  // [count, spare, ..., list] columns the fused kernel hands to the split kernels
-  int* h_redo = nullptr;                                  // pinned: {redo count, cloudy count} of the last step
-  cudaEvent_t ev_redo = nullptr; bool redo_pending = false;
-  int units_mode = -1; bool units_set = false;            // kidmp_set_option("units"): -1 = by domain size
-  int fuse_mode = -1;                                     // kidmp_set_option("fuse"): -1 = KIDMP_FUSE or adaptive
-  bool prefer_split = true;                               // until a step has shown that few columns need sub-steps
-  int* d_work = nullptr;                                  // [count | list | mask] of cloudy 32-column groups
+  // work buffers of one launch (a chunk of at most chunk_cols columns), sized for the worst case of the chunk
+  float* d_scratch = nullptr;                             // [SC_NX][nz][cols] hand-off between the cell kernels and k_finish
+  unsigned char* d_cls = nullptr;                         // [nz][cols] class byte of every cell
+  int* d_colflag = nullptr;                               // [cols]
+  int* d_work = nullptr;                                  // [count | list | mask | offset] of the cloudy columns
+  unsigned* d_cells = nullptr;                            // [nz*cols] busy cells, class after class
+  int* d_cellmeta = nullptr;                              // [8 | blocks*KC_N] class totals, per-block bases
+  double* d_coldiag = nullptr;                            // [2][cols] per-column water paths for the ordered domain sums
+  long work_cols = 0; int work_nz = 0;
+  long chunk_cols = 1048576;                              // columns per launch of the step kernels ("chunk" option, KIDMP_CHUNK)
+  cudaEvent_t ev_done = nullptr;                          // end of the last step, on whatever stream it ran
+  bool last_on_own_stream = true;
   double* d_diag = nullptr;
   float* d_rates = nullptr;
   float* d_kid = nullptr; size_t kid_floats = 0;   // staging of the KiD (k,i) arrays
@@ -67,7 +69,6 @@ struct kidmp_handle {
 namespace {
 
 std::string g_init_error;
-const kidmp_handle* g_const_owner = nullptr;
 std::mutex g_mu;
 
 int fail(kidmp_handle* h, const char* fmt, ...) {
@@ -209,163 +210,111 @@ int build_device_tables(kidmp_handle* h, const hostinit::Prep& pp) {
   return 0;
 }
 
-int ensure_constants(kidmp_handle* h) {
+// The scalars of thompson_init live in ONE __constant__ block per device (`ck`) and one __device__ double (the graupel
+// intercept constant): the handle that ran last on a device owns them.  A change of owner is ordered on the device: the
+// new owner's stream first waits for the previous owner's last step, then uploads on that same stream, so neither
+// handle's kernels can see the other's constants.
+constexpr int MAX_DEVICES = 64;
+kidmp_handle* g_const_owner[MAX_DEVICES] = {};
+int ensure_constants(kidmp_handle* h, cudaStream_t s) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_const_owner != h) {
-    CK(h, cudaMemcpyToSymbolAsync(ck, &h->kc, sizeof(KConst), 0, cudaMemcpyHostToDevice, h->stream));
-    k_n0_lo<<<1, 1, 0, h->stream>>>();               // the per-run graupel intercept constant (kidmp_column.cuh)
-    g_const_owner = h;
+  kidmp_handle*& owner = g_const_owner[h->device];
+  if (owner != h) {
+    if (owner && owner->ev_done) CK(h, cudaStreamWaitEvent(s, owner->ev_done, 0));
+    CK(h, cudaMemcpyToSymbolAsync(ck, &h->kc, sizeof(KConst), 0, cudaMemcpyHostToDevice, s));
+    k_n0_lo<<<1, 1, 0, s>>>();                       // the per-run graupel intercept constant (kidmp_column.cuh)
+    owner = h;
   }
   return 0;
 }
 
+int ensure_work(kidmp_handle* h, long cols, int nz) {
+  if (cols <= h->work_cols && nz <= h->work_nz) return 0;
+  const long C = cols > h->work_cols ? cols : h->work_cols;
+  const int Z = nz > h->work_nz ? nz : h->work_nz;
+  CK(h, cudaDeviceSynchronize());                    // nothing may still be reading the buffers that go away
+  void* old[] = {h->d_scratch, h->d_cls, h->d_colflag, h->d_work, h->d_cells, h->d_cellmeta, h->d_coldiag};
+  for (void* q : old) if (q) cudaFree(q);
+  h->d_scratch = nullptr; h->d_cls = nullptr; h->d_colflag = nullptr; h->d_work = nullptr; h->d_cells = nullptr;
+  h->d_cellmeta = nullptr; h->d_coldiag = nullptr; h->work_cols = 0; h->work_nz = 0;
+  const size_t cells = (size_t)C * Z;
+  const long ngroups = (C + 31) / 32, lblocks = (C + LIST_TILE - 1) / LIST_TILE;
+  CK(h, cudaMalloc((void**)&h->d_scratch, cells * SC_NX * 4));
+  CK(h, cudaMalloc((void**)&h->d_cls, cells));
+  CK(h, cudaMalloc((void**)&h->d_colflag, (size_t)C * 4));
+  CK(h, cudaMalloc((void**)&h->d_work, (size_t)(C + 8 + 2 * ngroups) * 4));
+  CK(h, cudaMalloc((void**)&h->d_cells, cells * 4));
+  CK(h, cudaMalloc((void**)&h->d_cellmeta, (size_t)(8 + lblocks * KC_N) * 4));
+  CK(h, cudaMalloc((void**)&h->d_coldiag, (size_t)C * 2 * 8));
+  h->work_cols = C; h->work_nz = Z;
+  return 0;
+}
+
+// launch shape of the cell kernels: threads per block, blocks per SM (kidmp_cells.cuh; measured in profiles/r02_*)
+#ifndef KC_WARM_T
+#define KC_WARM_T 128
+#define KC_WARM_B 6
+#define KC_ICE_T 128
+#define KC_ICE_B 4
+#define KC_MIXNR_T 128
+#define KC_MIXNR_B 4
+#define KC_FULL_T 128
+#define KC_FULL_B 4
+#define KC_BARS 0
+#endif
+
+template <bool RATES>
+void launch_cells(const StepArgs& a, int nsm, cudaStream_t s) {
+  k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, 0, RATES><<<nsm * KC_WARM_B, KC_WARM_T, 0, s>>>(a);
+  k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, 0, RATES><<<nsm * KC_ICE_B, KC_ICE_T, 0, s>>>(a);
+  k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_BARS, RATES><<<nsm * KC_MIXNR_B, KC_MIXNR_T, 0, s>>>(a);
+  k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_BARS, RATES><<<nsm * KC_FULL_B, KC_FULL_T, 0, s>>>(a);
+}
+
+// One step over [ncol] columns whose arrays have row stride ld, in launches of at most chunk_cols columns (the work
+// buffers are sized for one chunk: 29 hand-off planes would otherwise grow with the domain).  Columns are independent,
+// so the chunking changes no result.
 int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   if (a0.nz < 2 || a0.nz > 256) return fail(h, "nz=%d outside [2,256]", a0.nz);
   if (a0.ncol < 1) return fail(h, "ncol=%ld", a0.ncol);
   if (!(a0.dt > 0.f)) return fail(h, "dt must be positive");
-  if (ensure_constants(h)) return 1;
-  StepArgs a = a0;
-  // launch shape: warps per lockstep block of the physics kernel.  KIDMP_WARPS overrides (tuning knob).
-  // 24 lockstep warps per SM for large domains; below ~131 072 columns there are too few 768-thread blocks to fill
-  // 148 SMs, so two 8-warp blocks per SM are used (measured: 14 400 x 120 levels 3.9 -> 2.6 ms, 65 536 x 60 2.4 -> 1.6 ms)
-  static const int warps_env = getenv("KIDMP_WARPS") ? atoi(getenv("KIDMP_WARPS")) : 0;
-  const int warps = warps_env > 0 ? warps_env : (a.ncol <= 131072 ? 9 : 24);
-  const int sthreads = 128;
-  const long sblocks = (a.ncol + sthreads - 1) / sthreads;
-  const long ngroups = (a.ncol + 31) / 32;
+  const long chunk = h->chunk_cols;
+  const long cap = a0.ncol < chunk ? a0.ncol : chunk;
+  if ((double)cap * a0.nz >= 4.0e9) return fail(h, "chunk of %ld columns x %d levels does not fit the 32-bit cell index", cap, a0.nz);
+  if (ensure_work(h, cap, a0.nz)) return 1;
+  if (ensure_constants(h, s)) return 1;
   if (!h->d_partial) CK(h, cudaMalloc((void**)&h->d_partial, (size_t)DIAG_BLOCKS * KIDMP_NDIAG * 8));
-  const size_t need = (size_t)a.ncol * a.nz;
-  if (need > h->scratch_cells || a.ncol > h->scratch_cols) {
-    if (h->d_scratch) cudaFree(h->d_scratch);
-    if (h->d_colint) cudaFree(h->d_colint);
-    if (h->d_work) cudaFree(h->d_work);
-    if (h->d_coldiag) cudaFree(h->d_coldiag);
-    if (h->d_redo) cudaFree(h->d_redo);
-    h->d_redo = nullptr;
-    h->d_scratch = nullptr; h->d_colint = nullptr; h->d_work = nullptr; h->d_coldiag = nullptr; h->scratch_cells = 0; h->scratch_cols = 0;
-    CK(h, cudaMalloc((void**)&h->d_scratch, need * SC_NX * 4));
-    CK(h, cudaMalloc((void**)&h->d_colint, (size_t)a.ncol * 8 * 4));
-    CK(h, cudaMalloc((void**)&h->d_work, (size_t)(a.ncol + 8 + 2 * ngroups) * 4));
-    CK(h, cudaMalloc((void**)&h->d_coldiag, (size_t)a.ncol * 2 * 8));
-    CK(h, cudaMalloc((void**)&h->d_redo, (size_t)(a.ncol + 8) * 4));
-    h->scratch_cells = need; h->scratch_cols = a.ncol;
+  for (long c0 = 0; c0 < a0.ncol; c0 += chunk) {
+    StepArgs a = a0;
+    a.ncol = (a0.ncol - c0 < chunk) ? (a0.ncol - c0) : chunk;
+    for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = a0.f[q] + c0;
+    a.p = a0.p + c0; a.ppt = a0.ppt + c0;
+    if (a0.dz_col) a.dz_col = a0.dz_col + c0;
+    if (a0.rates) a.rates = a0.rates + c0;
+    const long ngroups = (a.ncol + 31) / 32, lblocks = (a.ncol + LIST_TILE - 1) / LIST_TILE;
+    a.scratch = h->d_scratch; a.cls = h->d_cls; a.colflag = h->d_colflag;
+    a.work_count = h->d_work; a.work_list = h->d_work + 8;
+    a.work_mask = (unsigned*)(h->d_work + 8 + a.ncol); a.work_offset = h->d_work + 8 + a.ncol + ngroups;
+    a.cell_list = h->d_cells; a.cell_count = h->d_cellmeta; a.cell_base = h->d_cellmeta + 8;
+    a.coldiag = h->d_coldiag; a.diag_partial = h->d_partial; a.nsm = h->nsm;
+    CK(h, cudaMemsetAsync(a.cell_count, 0, 8 * 4, s));
+    k_classify<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
+    k_list_scan<<<1, 1024, 0, s>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
+    k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
+    const int lsmem = (LIST_TILE / 32) * a.nz * KC_N * 2;
+    k_cell_count<<<(unsigned)lblocks, LIST_TILE, lsmem, s>>>(a);
+    k_cell_fill<<<(unsigned)lblocks, LIST_TILE, lsmem, s>>>(a);
+    // the number of cloudy columns is only known on the device: grids for the worst case, surplus blocks leave at once
+    if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
+    if (a.rates) { launch_cells<true>(a, h->nsm, s); k_finish<true><<<(unsigned)ngroups, 32, 0, s>>>(a); }
+    else { launch_cells<false>(a, h->nsm, s); k_finish<false><<<(unsigned)ngroups, 32, 0, s>>>(a); }
+    k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
+    k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
+    h->launches += h->kc.iiwarm ? 12 : 13;
   }
-  a.scratch = h->d_scratch;
-  a.colint = h->d_colint;
-  a.work_count = h->d_work;
-  a.work_list = h->d_work + 8;
-  a.work_mask = (unsigned*)(h->d_work + 8 + a.ncol);
-  a.work_offset = h->d_work + 8 + a.ncol + ngroups;
-  a.coldiag = h->d_coldiag;
-  a.diag_partial = h->d_partial;
-  a.rates = h->d_rates;
-  a.nsm = h->nsm;
-  a.redo_count = h->d_redo; a.redo_list = h->d_redo + 8;
-  // Mode of this step.  Fused (sedimentation inside the physics kernel) is right for columns whose sub-step counts are
-  // <= 1 and redoes the others with the split kernels.  Measured on a B200 (profiles/r01_ncu_step_kernels.md): the
-  // fused kernel costs 0.6 ms more than the split physics kernel and saves the 1.05 ms sedimentation kernel, but a redo
-  // pass costs ~2 ms however few columns it holds (a block walks its 60 levels at ~30 us each whether it has one warp
-  // or 24).  So the step is fused only when the step before it had NO column with sub-steps (KiD's 1-D cases, warm
-  // rain, small dt / thick layers; not the bench domain, whose fast graupel aloft gives 24 % of the columns nstep = 2).
-  // The first step runs split and counts.  The result is the same bit for bit either way.
-  // KIDMP_FUSE: 0 = never, 1 = adaptive (default), 2 = always.
-  static const int fuse_default = getenv("KIDMP_FUSE") ? atoi(getenv("KIDMP_FUSE")) : 1;
-  const int fuse_env = h->fuse_mode >= 0 ? h->fuse_mode : fuse_default;
-  if (!h->h_redo) {
-    CK(h, cudaHostAlloc((void**)&h->h_redo, 16, cudaHostAllocDefault));
-    h->h_redo[0] = 0; h->h_redo[1] = 0;
-    CK(h, cudaEventCreateWithFlags(&h->ev_redo, cudaEventDisableTiming));
-  }
-  if (h->redo_pending && cudaEventQuery(h->ev_redo) == cudaSuccess) {
-    h->redo_pending = false;
-    h->prefer_split = h->h_redo[0] > 0;
-  }
-  const bool fuse = fuse_env != 0 && !a.rates && !(fuse_env == 1 && h->prefer_split);
-  CK(h, cudaMemsetAsync(h->d_redo, 0, 8, s));
-  k_classify<<<(unsigned)sblocks, sthreads, 0, s>>>(a);
-  k_list_scan<<<1, 1024, 0, s>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
-  k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
-  // the number of cloudy groups is only known on the device: launch for the worst case, surplus blocks leave at once
-  // dynamic shared memory of the physics kernel: 84 bytes per thread (vertical carries, parked inputs; +40 fused)
-#ifndef K1_BARS
-#define K1_BARS 11           // stage barriers of the lockstep blocks: level top, before S6, before S9 (bit i = LOCKBAR(i))
-#endif
-#define LAUNCH_K1(KERNEL, GRID, THREADS, SMEM, ARGS)                                                              \
-  do {                                                                                                            \
-    static bool attr_set = false;                                                                                 \
-    if (!attr_set) {                                                                                              \
-      cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (THREADS) * (SMEM));               \
-      /* the smallest carve-out that holds the block (+1 KB the system keeps): the rest of the 256 KB is L1 */     \
-      cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout,                                 \
-                           (int)((((size_t)(THREADS) * (SMEM) + 1024) * 100) / (228 * 1024)));                     \
-      attr_set = true;                                                                                            \
-    }                                                                                                             \
-    KERNEL<<<(GRID), (THREADS), (THREADS) * (SMEM), s>>>(ARGS);                                                    \
-  } while (0)
-  // grid: worst case (every column cloudy), rounded up to whole waves of `minb` blocks per SM (see the kernel)
-  auto grid = [&](int w, int minb) { const long wave = (long)h->nsm * minb; return (unsigned)(((ngroups + w - 1) / w + wave - 1) / wave * wave); };
-  // measured alternatives (profiles/r01_ncu_step_kernels.md): 16 / 20 / 28 / 32 warps, 2x12 and 3x8 warps per SM, other barrier sets
-  auto physics = [&](const StepArgs& x, bool fused) {
-    if (x.rates) LAUNCH_K1((k_column_step<16, 1, K1_BARS, true, false>), grid(16, 1), 512, 84, x);   // with the 36 save_dg rates
-    else if (warps >= 24) {
-      if (fused) LAUNCH_K1((k_column_step<24, 1, K1_BARS, false, true>), grid(24, 1), 768, 124, x);
-      else LAUNCH_K1((k_column_step<24, 1, K1_BARS, false, false>), grid(24, 1), 768, 84, x);
-    } else if (warps >= 16) {
-      if (fused) LAUNCH_K1((k_column_step<16, 1, K1_BARS, false, true>), grid(16, 1), 512, 124, x);
-      else LAUNCH_K1((k_column_step<16, 1, K1_BARS, false, false>), grid(16, 1), 512, 84, x);
-    } else if (warps >= 8) {                                                                     // two 8-warp blocks per SM
-      if (fused) LAUNCH_K1((k_column_step<8, 2, K1_BARS, false, true>), grid(8, 2), 256, 124, x);
-      else LAUNCH_K1((k_column_step<8, 2, K1_BARS, false, false>), grid(8, 2), 256, 84, x);
-    } else {
-      if (fused) LAUNCH_K1((k_column_step<1, 12, 0, false, true>), grid(1, 12), 32, 124, x);
-      else LAUNCH_K1((k_column_step<1, 12, 0, false, false>), grid(1, 12), 32, 84, x);
-    }
-  };
-  // Which physics kernel.  The unit-parallel one (kidmp_units.cuh) runs a domain's (32 columns x 1 level) units side by
-  // side instead of walking each column's levels one after the other: measured on a B200 it is 3x faster for one column,
-  // 2.2x for 14 400 columns, 1.9x / 1.7x / 1.3x for 32 768 / 65 536 / 131 072, equal at 262 144 and 8 % slower at 1 048 576
-  // (where the column walk already fills every SM and the two extra light sweeps are pure overhead: 99 % of that
-  // domain's units hold a busy cell).  KIDMP_UNITS / kidmp_set_option("units"): 0 never, 1 always, -1 by size (default).
-  static const int units_default = getenv("KIDMP_UNITS") ? atoi(getenv("KIDMP_UNITS")) : -1;
-  const int units_mode = h->units_mode >= -1 && h->units_set ? h->units_mode : units_default;
-  const bool units = (units_mode > 0 || (units_mode < 0 && a.ncol <= 131072)) && a.nz <= KU_MAXNZ;
-  if (units) {
-    // always 24-warp blocks: a block with few columns still has many units
-    const int smem = ku_smem_bytes(768, a.nz);
-#define LAUNCH_KU(KERNEL)                                                                                          \
-  do {                                                                                                            \
-    static int set_to = 0;                                                                                        \
-    if (set_to < smem) { cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set_to = smem; } \
-    KERNEL<<<grid(24, 1), 768, smem, s>>>(a);                                                                      \
-  } while (0)
-    // busy cells packed into full warps (PACK): 7.23 against 7.52 ms on the bench domain, no difference on small ones
-    if (a.rates) LAUNCH_KU((k_unit_step<24, 1, K1_BARS, true, true>));
-    else LAUNCH_KU((k_unit_step<24, 1, K1_BARS, false, true>));
-    k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
-    h->launches += 1;
-  } else if (fuse) {
-    physics(a, true);
-    StepArgs r = a;                                  // the columns that need sub-steps, again, with the split kernels
-    r.work_count = h->d_redo; r.work_list = h->d_redo + 8; r.redo_count = h->d_redo + 1;
-    k_restore<<<(unsigned)ngroups, 32, 0, s>>>(r);
-    physics(r, false);
-    k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(r);
-    h->launches += 3;
-  } else {
-    physics(a, false);
-    k_sediment<<<(unsigned)ngroups, 32, 0, s>>>(a);
-    h->launches += 1;
-  }
-  if (!h->redo_pending) {                            // {columns with sub-steps, cloudy columns} for the next step's choice
-    CK(h, cudaMemcpyAsync(h->h_redo, h->d_redo, 4, cudaMemcpyDeviceToHost, s));
-    CK(h, cudaMemcpyAsync(h->h_redo + 1, a.work_count, 4, cudaMemcpyDeviceToHost, s));
-    CK(h, cudaEventRecord(h->ev_redo, s));
-    h->redo_pending = true;
-  }
-  k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
-  k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
-  h->launches += 6;
   CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(h->ev_done, s));
+  h->last_on_own_stream = (s == h->stream);
   return 0;
 }
 
@@ -382,10 +331,10 @@ inline float* field_ptr(kidmp_handle* h, int q) { return h->d_state + (size_t)q 
 
 StepArgs resident_args(kidmp_handle* h, float dt) {
   StepArgs a{};
-  a.ncol = h->ncol; a.nz = h->nz; a.dt = dt;
+  a.ncol = h->ncol; a.ld = h->ncol; a.nz = h->nz; a.dt = dt;
   for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = field_ptr(h, q);
   a.p = field_ptr(h, KIDMP_NFIELDS);
-  a.dz = h->d_dz; a.ppt = h->d_ppt;
+  a.dz = h->d_dz; a.ppt = h->d_ppt; a.rates = h->d_rates;
   return a;
 }
 
@@ -433,6 +382,8 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   kidmp_handle* h = new kidmp_handle();
   h->cfg = *cfg;
   h->device = cfg->device;
+  if (getenv("KIDMP_CHUNK") && atol(getenv("KIDMP_CHUNK")) >= 32) h->chunk_cols = atol(getenv("KIDMP_CHUNK"));
+  if (cfg->device >= MAX_DEVICES) { delete h; return fail(nullptr, "kidmp_init: device ordinal %d not supported", cfg->device); }
   if (getenv("KIDMP_PIPE_CHUNK")) h->pipe_chunk = atol(getenv("KIDMP_PIPE_CHUNK")) > 1024 ? atol(getenv("KIDMP_PIPE_CHUNK")) : 1024;
   if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
   h->cfg.table_cache_path = nullptr;
@@ -445,7 +396,8 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) {
     h->err = "stream/event creation failed"; return bail(1);
   }
   memset(&h->kc, 0, sizeof h->kc);
@@ -487,9 +439,9 @@ int kidmp_finalize(kidmp_handle* h) {
   cudaSetDevice(h->device);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_const_owner == h) g_const_owner = nullptr;
+    if (g_const_owner[h->device] == h) g_const_owner[h->device] = nullptr;
   }
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();                           // steps may have run on caller streams
   free_state(h);
   for (auto& a : table_allocs(h)) if (*a.p) cudaFree(*a.p);
   if (h->d_partial) cudaFree(h->d_partial);
@@ -497,12 +449,13 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_kid) cudaFree(h->d_kid);
   if (h->h_kid) cudaFreeHost(h->h_kid);
   if (h->d_scratch) cudaFree(h->d_scratch);
-  if (h->d_colint) cudaFree(h->d_colint);
+  if (h->d_cls) cudaFree(h->d_cls);
+  if (h->d_colflag) cudaFree(h->d_colflag);
   if (h->d_work) cudaFree(h->d_work);
-  if (h->d_redo) cudaFree(h->d_redo);
-  if (h->h_redo) cudaFreeHost(h->h_redo);
-  if (h->ev_redo) cudaEventDestroy(h->ev_redo);
+  if (h->d_cells) cudaFree(h->d_cells);
+  if (h->d_cellmeta) cudaFree(h->d_cellmeta);
   if (h->d_coldiag) cudaFree(h->d_coldiag);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->d_pipe) cudaFree(h->d_pipe);
   if (h->d_pipe_dz) cudaFree(h->d_pipe_dz);
   if (h->h_ppt) cudaFreeHost(h->h_ppt);
@@ -752,7 +705,7 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
     CK(h, cudaEventRecord(h->pipe_ev[b][0], h->copy_in));
     CK(h, cudaStreamWaitEvent(h->stream, h->pipe_ev[b][0], 0));
     StepArgs a{};
-    a.ncol = n; a.nz = nz; a.dt = dt;
+    a.ncol = n; a.ld = n; a.nz = nz; a.dt = dt;
     for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = base + cells * q;
     a.p = base + cells * KIDMP_NFIELDS; a.dz = h->d_pipe_dz; a.ppt = d_ppt;
     if (launch_step(h, a, h->stream)) return 1;
@@ -774,7 +727,8 @@ int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout, float* 
                const float* p, const float* dz, float* ppt) {
   if (!h) return 1;
   if (!fields || !p || !dz) return fail(h, "step: null pointer");
-  if (layout == KIDMP_COL_FASTEST && ncol >= 2 * h->pipe_chunk && nz >= 2 && nz <= 256 && dt > 0.f) {
+  // (with a process-rate buffer set the whole domain goes through the resident path: the buffer is [36][nz][ncol] of the domain)
+  if (layout == KIDMP_COL_FASTEST && ncol >= 2 * h->pipe_chunk && nz >= 2 && nz <= 256 && dt > 0.f && !h->d_rates) {
     for (int q = 0; q < KIDMP_NFIELDS; ++q) if (!fields[q]) return fail(h, "step: field %d is null", q);
     cudaSetDevice(h->device);
     return step_pipelined(h, ncol, nz, dt, fields, p, dz, ppt);
@@ -802,7 +756,7 @@ int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt, float* const
   if (!d_fields || !d_p || !d_dz || !d_ppt) return fail(h, "step_device: null pointer");
   cudaSetDevice(h->device);
   StepArgs a{};
-  a.ncol = ncol; a.nz = nz; a.dt = dt;
+  a.ncol = ncol; a.ld = ncol; a.nz = nz; a.dt = dt; a.rates = h->d_rates;
   for (int q = 0; q < KIDMP_NFIELDS; ++q) { if (!d_fields[q]) return fail(h, "step_device: field %d is null", q); a.f[q] = d_fields[q]; }
   a.p = d_p; a.dz = d_dz; a.ppt = d_ppt;
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
@@ -827,6 +781,7 @@ const char* kidmp_rate_names(void) {
 int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
   if (!h || !out) return 1;
   cudaSetDevice(h->device);
+  CK(h, cudaStreamWaitEvent(h->stream, h->ev_done, 0));   // the last step may have run on a caller's stream
   CK(h, cudaMemcpyAsync(out, h->d_diag, KIDMP_NDIAG * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemsetAsync(h->d_diag, 0, KIDMP_NDIAG * 8, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
@@ -910,14 +865,11 @@ int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in) 
 int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
   if (!h) return 1;
   if (!name) return fail(h, "set_option: null name");
-  if (!strcmp(name, "fuse")) {
-    if (value < -1 || value > 2) return fail(h, "set_option: fuse must be -1, 0, 1 or 2");
-    h->fuse_mode = value; h->prefer_split = true; return 0;
+  if (!strcmp(name, "chunk")) {
+    if (value < 32) return fail(h, "set_option: chunk must be at least 32 columns");
+    h->chunk_cols = value; return 0;
   }
-  if (!strcmp(name, "units")) {
-    if (value < -1 || value > 1) return fail(h, "set_option: units must be -1, 0 or 1");
-    h->units_mode = value; h->units_set = true; return 0;
-  }
+  if (!strcmp(name, "fuse") || !strcmp(name, "units")) return 0;      // knobs of the round-1 kernels: accepted, no effect
   return fail(h, "set_option: unknown option '%s'", name);
 }
 
@@ -933,6 +885,7 @@ int kidmp_sync(kidmp_handle* h) {
 int kidmp_last_step_ms(kidmp_handle* h, float* step_ms) {
   if (!h || !step_ms) return 1;
   cudaSetDevice(h->device);
+  if (!h->last_on_own_stream) return fail(h, "last_step_ms: the last step ran on a caller's stream; time it there");
   CK(h, cudaEventSynchronize(h->ev1));
   CK(h, cudaEventElapsedTime(step_ms, h->ev0, h->ev1));
   return 0;

@@ -1,0 +1,1336 @@
+// kidmp_cells.cuh - the physics of mp_thompson (S1..S13 of M:1156-3354) with ONE CELL as the unit of work, and the
+// column kernels around it.
+//
+// Why cells: the process rates of a level depend on that level's inputs only; what runs down a column is small (the
+// running minimum of the graupel intercept M:1648 / M:2731, the `k_0` test M:1635, the fall speed of a level without
+// the species M:3235, the sub-step counts M:3242).  A column walk spends its time in dependent instruction chains of
+// cells that mostly differ from their neighbours (profiles/r01: 19 of 32 lanes active, 45 % issue), and half of the
+// cells of a cloudy column are idle.  Here
+//   k_cell_count / k_cell_fill   turn the class bytes of k_classify into one list of busy cells per class, level-major
+//                                inside a 256-column tile, so the lanes of a warp are neighbouring columns of one level
+//                                that hold the same species;
+//   k_n0_sweep                   walks the columns that hold graupel top-down once: running minimum of M:1648;
+//   k_cells<KC>                  one thread per busy cell, one kernel per class.  The class is a template parameter:
+//                                code that cannot run for the class (every ice process for a warm cell, the collection
+//                                tables without rain ...) is not compiled into its kernel, so ptxas needs neither the
+//                                registers of the 35 f64 rates nor the 120 KB of instructions where they do not apply;
+//   k_finish                     one thread per cloudy column: sweep A settles what runs down the column (intercept
+//                                minimum of S10, fall speeds, sub-step counts), then S14 sedimentation (M:3365-3578),
+//                                S15 and S16 (finish_level).  Idle cells never had a hand-off record: their
+//                                tendencies are zero and their contents R1 / R2 by construction.
+// Pruning rule: a block is compiled out of a class kernel only when it cannot execute for any cell of the class, so
+// every class kernel computes bit for bit what the general code (KC_FULL) computes for the same cell.
+#pragma once
+#include "kidmp_column.cuh"
+
+namespace kidmp {
+
+// M:1649-1653 for a given intercept (the running minimum already taken)
+__device__ __forceinline__ void graupel_slope(double N0_exp, float rg, double& ilamg, double& N0_g) {
+  const double lam_exp = sqrt(sqrt(N0_exp * (double)ck.am_g * (double)ck.cgg[0] / (double)rg));   // **oge1, oge1 = 1/4
+  const double lamg = lam_exp * (double)ck.lamg_fac;
+  ilamg = (double)1.f / lamg;
+  N0_g = N0_exp / ((double)ck.cgg[1] * lam_exp) * lamg;                                         // lamg**cge(2), cge(2) = 1
+}
+
+// What a cell of each class can hold.  Input species (S1..S8 read the input flags) and species at tau+1 (S9 on).
+//   KC_WARM   no ice-phase species and (T >= T_0 or iiwarm): none can form (freezing and nucleation need T < T_0, M:2025)
+//   KC_ICE    T < T_0, no cloud water, rain or graupel: liquid cannot form before S11, graupel needs liquid (M:2224, M:1964)
+//   KC_MIXNR  anything without rain on input (rain may form: autoconversion, melting)
+//   KC_FULL   everything
+template <int KC> struct CellTraits {
+  static constexpr bool C = KC != KC_ICE, R = KC == KC_WARM || KC == KC_FULL, I = KC != KC_WARM, S = KC != KC_WARM,
+                        G = KC == KC_MIXNR || KC == KC_FULL;
+  static constexpr bool ICEPROC = KC != KC_WARM;          // the `if (.not. iiwarm)` blocks can do something
+  static constexpr bool COLD = KC == KC_ICE;              // T < T_0 is certain
+  static constexpr bool C9 = KC != KC_ICE, R9 = KC != KC_ICE, I9 = KC != KC_WARM, S9 = KC != KC_WARM,
+                        G9 = KC == KC_MIXNR || KC == KC_FULL;
+};
+
+#define R1 KP_R1
+#define R2 KP_R2
+#define EPSF KP_EPS
+#define T_0 KP_T_0
+#define D0r KP_D0R
+#define D0c KP_D0C
+#define D0s KP_D0S
+#define D0g KP_D0G
+
+// ---- per-class lists of busy cells ------------------------------------------------------------------------------
+// A block owns LIST_TILE consecutive columns; warp w owns 32 of them.  Entries of a class inside the block's range
+// are level-major from the top, then by column: 32 consecutive entries are cells of ONE level (mostly).
+// s_cnt[w][k][c] = cells of class c in warp w's columns at level k.
+__device__ __forceinline__ void list_tile_counts(const StepArgs& a, unsigned short* s_cnt, int nz, long col, bool in_range) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned char* cp = a.cls + col;
+  for (int k = 0; k < nz; ++k) {
+    const unsigned c = in_range ? cp[(long)k * a.ncol] : 0u;
+    const bool busy = (c & CLS_BUSY) != 0u;
+    const unsigned kc = c >> CLS_KC_SHIFT;
+#pragma unroll
+    for (int q = 0; q < KC_N; ++q) {
+      const unsigned m = __ballot_sync(0xffffffffu, busy && kc == (unsigned)q);
+      if (lane == 0) s_cnt[(warp * nz + k) * KC_N + q] = (unsigned short)__popc(m);
+    }
+  }
+}
+__global__ void __launch_bounds__(LIST_TILE) k_cell_count(StepArgs a) {
+  extern __shared__ unsigned short s_cnt[];               // [8][nz][KC_N]
+  __shared__ int s_tot[KC_N];
+  const int nz = a.nz;
+  const long col = (long)blockIdx.x * LIST_TILE + threadIdx.x;
+  if (threadIdx.x < KC_N) s_tot[threadIdx.x] = 0;
+  // a tile without a cloudy column has no busy cell
+  const int g0 = blockIdx.x * (LIST_TILE / 32);
+  bool any = false;
+  for (int g = 0; g < LIST_TILE / 32; ++g) if ((long)(g0 + g) * 32 < a.ncol && a.work_mask[g0 + g]) any = true;
+  __syncthreads();
+  if (any) {
+    list_tile_counts(a, s_cnt, nz, col, col < a.ncol);
+    __syncthreads();
+    const int n = (LIST_TILE / 32) * nz * KC_N;
+    int mine = 0;                                         // the stride is a multiple of KC_N: a thread only meets class tid % KC_N
+    for (int i = threadIdx.x; i < n; i += LIST_TILE) mine += s_cnt[i];
+    if (mine) atomicAdd(&s_tot[threadIdx.x & (KC_N - 1)], mine);
+    __syncthreads();
+  }
+  if (threadIdx.x < KC_N) {
+    const int t = any ? s_tot[threadIdx.x] : 0;
+    a.cell_base[(long)blockIdx.x * KC_N + threadIdx.x] = t ? atomicAdd(&a.cell_count[threadIdx.x], t) : 0;
+  }
+}
+__global__ void __launch_bounds__(LIST_TILE) k_cell_fill(StepArgs a) {
+  extern __shared__ unsigned short s_cnt[];               // [8][nz][KC_N]
+  __shared__ int s_lvl[KC_N];
+  const int nz = a.nz;
+  const long col = (long)blockIdx.x * LIST_TILE + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g0 = blockIdx.x * (LIST_TILE / 32);
+  bool any = false;
+  for (int g = 0; g < LIST_TILE / 32; ++g) if ((long)(g0 + g) * 32 < a.ncol && a.work_mask[g0 + g]) any = true;
+  if (!any) return;
+  const bool in_range = col < a.ncol;
+  list_tile_counts(a, s_cnt, nz, col, in_range);
+  // first entry of every class segment: classes follow each other in the list
+  int seg[KC_N];
+  {
+    int run = 0;
+#pragma unroll
+    for (int q = 0; q < KC_N; ++q) { seg[q] = run + a.cell_base[(long)blockIdx.x * KC_N + q]; run += a.cell_count[q]; }
+  }
+  if (threadIdx.x < KC_N) s_lvl[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned count = (unsigned)*a.work_count;
+  const unsigned gmask = in_range ? a.work_mask[col >> 5] : 0u;
+  const unsigned slot = (unsigned)a.work_offset[in_range ? (col >> 5) : 0] + __popc(gmask & ((1u << lane) - 1u));
+  const unsigned char* cp = a.cls + col;
+  for (int k = nz - 1; k >= 0; --k) {
+    const unsigned c = in_range ? cp[(long)k * a.ncol] : 0u;
+    const bool busy = (c & CLS_BUSY) != 0u;
+    const unsigned kc = c >> CLS_KC_SHIFT;
+    int before = 0, level_total = 0;                      // cells of my class at this level in the warps before mine / in all warps
+    if (busy) {
+      for (int w = 0; w < LIST_TILE / 32; ++w) {
+        const int v = s_cnt[(w * nz + k) * KC_N + kc];
+        if (w < warp) before += v;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < KC_N; ++q) {
+      const unsigned m = __ballot_sync(0xffffffffu, busy && kc == (unsigned)q);
+      if (busy && kc == (unsigned)q)
+        a.cell_list[seg[q] + s_lvl[q] + before + __popc(m & ((1u << lane) - 1u))] = (unsigned)k * count + slot;
+    }
+    __syncthreads();
+    if (threadIdx.x < KC_N) {
+      for (int w = 0; w < LIST_TILE / 32; ++w) level_total += s_cnt[(w * nz + k) * KC_N + threadIdx.x];
+      s_lvl[threadIdx.x] += level_total;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- running minimum of the graupel intercept of S4 (M:1633-1648), only for columns that hold graupel: the slope and
+// intercept it feeds (M:1649-1653) are read by graupel processes alone.  One thread per cloudy column, top-down; the value
+// of every graupel cell goes to the SC_N0A plane.  The rain of S1 is needed for the supercooled-drop test of M:1640.
+__global__ void __launch_bounds__(128) k_n0_sweep(StepArgs a) {
+  const int slot = blockIdx.x * 128 + threadIdx.x;
+  const int count = *a.work_count;
+  if (slot >= count || ck.iiwarm) return;
+  const long col = a.work_list[slot];
+  if (!(a.colflag[col] & 1)) return;
+  const int nz = a.nz;
+  const long ld = a.ld;
+  float* n0a = a.scratch + (size_t)SC_N0A * nz * count + slot;
+  const double n0_empty = g_n0_lo;
+  bool warm_a = false;                                    // a level at or above this one has T >= 270.65 K (k_0, M:1635)
+  double n0_min = (double)KP_GONV_MAX;
+#pragma unroll 1
+  for (int k = nz - 1; k >= 0; --k) {
+    const long g = (long)k * ld + col;
+    const float t1d = a.f[F_T][g], qg1d = a.f[F_QG][g], qr1d = a.f[F_QR][g];
+    if (t1d >= 270.65f) warm_a = true;
+    const bool cold_rain = !warm_a && k > 0 && qr1d > R1;
+    if (qg1d > R1 || cold_rain) {
+      const float pres = a.p[g], qv = fmaxf(1.E-10f, a.f[F_QV][g]);
+      const float rho = 0.622f * pres / (KP_R * t1d * (qv + 0.622f));
+      const float rg = (qg1d > R1) ? qg1d * rho : R1;
+      bool slw = false;
+      float mvd_r = 0.f;
+      if (cold_rain) {                                    // the rain of S1 (M:1445-1466) for the xslw1 of M:1640
+        const float rr = qr1d * rho;
+        float nr = fmaxf(R2, a.f[F_NR][g] * rho);
+        if (nr <= R2) { mvd_r = 1.0E-3f; nr = nr_from_mvd(rr, mvd_r); }
+        const double lamr = rain_lam(nr, rr);
+        mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+        if (mvd_r > 2.5E-3f) mvd_r = 2.5E-3f;
+        else if (mvd_r < D0r * 0.75f) mvd_r = D0r * 0.75f;
+        slw = mvd_r > 100.E-6f;
+      }
+      double N0_exp = n0_empty;
+      if (slw || rg > 5.E-5f) N0_exp = graupel_n0_exp(slw ? 4.01f + log10_f(mvd_r) : 0.01f, rg);
+      n0_min = fmin(N0_exp, n0_min);
+      if (qg1d > R1) n0a[(size_t)k * count] = (float)n0_min;     // values of M:1646 are f32 numbers: exact
+    } else {
+      n0_min = fmin(n0_empty, n0_min);
+    }
+  }
+}
+
+// ---- K1: S1..S13 of one busy cell ---------------------------------------------------------------------------------
+// LOCK: the warps of a block meet at named barriers between the stages, so they run the same straight-line code at the
+// same time and share its instruction-cache lines (the full cell code is ~100 KB of SASS; profiles/r01).  Used for the
+// classes with the long bodies; the short ones run free.
+template <int KC, int THREADS, int MINB, int BARS, bool RATES>
+__global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
+  using TR = CellTraits<KC>;
+  constexpr bool LOCK = BARS != 0;
+  int seg = 0;
+#pragma unroll
+  for (int q = 0; q < KC; ++q) seg += a.cell_count[q];
+  const int n = a.cell_count[KC];
+  const unsigned* __restrict__ list = a.cell_list + seg;
+  const int nz = a.nz;
+  const long ld = a.ld;
+  const unsigned count = (unsigned)*a.work_count;
+  const size_t ps = (size_t)nz * count;                   // plane stride of the hand-off
+  const float DT = a.dt;
+  const float odt = 1.f / DT, odts = 1.f / DT;
+  const float Nt_c = ck.Nt_c;
+  const bool iiwarm = ck.iiwarm != 0;
+  const double n0_empty = g_n0_lo;
+#define LOCKBAR(i) do { if (LOCK && ((BARS >> (i)) & 1)) { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"r"(lock_threads) : "memory"); } } while (0)
+#pragma unroll 1
+  for (int base = blockIdx.x * THREADS; base < n; base += gridDim.x * THREADS) {
+    if (LOCK && base != (int)blockIdx.x * THREADS) __syncthreads();      // the stage barriers of two rounds must not mix
+    const int wbase = base + (threadIdx.x & ~31);
+    if (wbase >= n) { if (LOCK) continue; else return; }
+    const int lock_threads = min(THREADS, ((n - base + 31) >> 5) << 5);
+    const int i = base + threadIdx.x;
+    const bool valid = i < n;                             // lanes past the end shadow the warp's first cell: same branches, nothing stored
+    const unsigned e = list[valid ? i : wbase];
+    const int k = (int)(e / count);
+    const unsigned slot = e - (unsigned)k * count;
+    const long col = a.work_list[slot];
+    const long o = (long)k * ld + col;
+    LOCKBAR(0);
+    const float t1d = a.f[F_T][o], qv1d = a.f[F_QV][o], pres = a.p[o];
+    float qc1d = TR::C ? a.f[F_QC][o] : 0.0f, qi1d = TR::I ? a.f[F_QI][o] : 0.0f, qr1d = TR::R ? a.f[F_QR][o] : 0.0f,
+          qs1d = TR::S ? a.f[F_QS][o] : 0.0f, qg1d = TR::G ? a.f[F_QG][o] : 0.0f;
+    float ni1d = TR::I ? a.f[F_NI][o] : 0.0f, nr1d = TR::R ? a.f[F_NR][o] : 0.0f;
+    float* const sc = a.scratch + (size_t)k * count + slot;
+
+    // rates, M:1184-1211 (zeroed M:1282-1363)
+    double prw_vcd = 0., pnc_wcd = 0., pnc_wau = 0., pnc_rcw = 0., pnc_scw = 0., pnc_gcw = 0.;
+    double prv_rev = 0., prr_wau = 0., prr_rcw = 0., prr_rcs = 0., prr_rcg = 0., prr_sml = 0., prr_gml = 0., prr_rci = 0.;
+    double pnr_wau = 0., pnr_rcs = 0., pnr_rcg = 0., pnr_rci = 0., pnr_sml = 0., pnr_gml = 0., pnr_rev = 0., pnr_rcr = 0., pnr_rfz = 0.;
+    double pri_inu = 0., pni_inu = 0., pri_ihm = 0., pni_ihm = 0., pri_wfz = 0., pni_wfz = 0., pri_rfz = 0., pni_rfz = 0.;
+    double pri_ide = 0., pni_ide = 0., pri_rci = 0., pni_rci = 0., pni_sci = 0., pni_iau = 0.;
+    double prs_iau = 0., prs_sci = 0., prs_rcs = 0., prs_scw = 0., prs_sde = 0., prs_ihm = 0., prs_ide = 0.;
+    double prg_scw = 0., prg_rfz = 0., prg_gde = 0., prg_gcw = 0., prg_rci = 0., prg_rcs = 0., prg_rcg = 0., prg_ihm = 0.;
+    float smo0 = 0.f, smo1 = 0.f, smob = 0.f, smoc = 0.f, smoe = 0.f, smof = 0.f;
+    bool have_smoe = false;
+    float mvd_r = 0.f, mvd_c = 0.f, vts_boost = 0.f;
+    double ilamg = 0., N0_g = 0., ilamr = 0., N0_r = 0., lamr = 0., lamc = 0., lami = 0., ilami = 0.;
+    int nu_c = 0;
+    float xDc = 0.f;
+    // number tendencies are summed as their terms appear (M:2417, M:2453, M:2503 add them up later): the
+    // 22 individual number rates need not stay in registers until S8
+    double nc_acc = 0., ni_acc = 0., nr_acc = 0.;
+    // lamr / lami hold rain_lam(nr, rr) / ice_lam(ni, ri) of the current nr, rr / ni, ri unless the number was
+    // re-diagnosed after they were evaluated: the reference evaluates the same power again at M:1661, M:2118,
+    // M:2750 and M:3227 from unchanged arguments, which is the same number
+    bool lamr_stale = false, lami_stale = false;
+
+    // ---- S1, M:1387-1493 -------------------------------------------------------------------
+    float temp = t1d;
+    float qv = fmaxf(1.E-10f, qv1d);
+    float rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+    float rc, nc, ri, ni, rr, nr, rs, rg;
+    bool L_qc, L_qi, L_qr, L_qs, L_qg;
+    if (TR::C && qc1d > R1) {
+      rc = qc1d * rho;
+      L_qc = true;
+      nc = Nt_c;   // the lamc/xDc clamps of M:1399-1408 only feed nc, overwritten at M:1410
+    } else {
+      qc1d = 0.0f; rc = R1; nc = 2.f; L_qc = false;
+    }
+    if (TR::I && qi1d > R1) {
+      ri = qi1d * rho;
+      ni = fmaxf(R2, ni1d * rho);
+      if (ni <= R2) {
+        lami = (double)(ck.cie[1] / 25.E-6f);
+        ni = (float)fmin(499.E3, (double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(lami));
+      }
+      L_qi = true;
+      lami = ice_lam(ni, ri);
+      ilami = (double)1.f / lami;
+      const float xDi = (float)((double)(3.f + 0.f + 1.f) * ilami);
+      if (xDi < 5.E-6f) {
+        const double l2 = (double)(ck.cie[1] / 5.E-6f);
+        ni = (float)fmin(499.E3, (double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(l2));
+        lami_stale = true;
+      } else if (xDi > 300.E-6f) {
+        const double l2 = (double)(ck.cie[1] / 300.E-6f);
+        ni = (float)((double)(ck.cig[0] * ck.oig2 * ri / ck.am_i) * cube_d(l2));
+        lami_stale = true;
+      }
+    } else {
+      qi1d = 0.0f; ni1d = 0.0f; ri = R1; ni = R2; L_qi = false;
+    }
+    if (TR::R && qr1d > R1) {
+      rr = qr1d * rho;
+      nr = fmaxf(R2, nr1d * rho);
+      if (nr <= R2) { mvd_r = 1.0E-3f; nr = nr_from_mvd(rr, mvd_r); }
+      L_qr = true;
+      lamr = rain_lam(nr, rr);
+      mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+      if (mvd_r > 2.5E-3f) { mvd_r = 2.5E-3f; nr = nr_from_mvd(rr, mvd_r); lamr_stale = true; }
+      else if (mvd_r < D0r * 0.75f) { mvd_r = D0r * 0.75f; nr = nr_from_mvd(rr, mvd_r); lamr_stale = true; }
+    } else {
+      qr1d = 0.0f; nr1d = 0.0f; rr = R1; nr = R2; L_qr = false;
+    }
+    if (TR::S && qs1d > R1) { rs = qs1d * rho; L_qs = true; } else { qs1d = 0.0f; rs = R1; L_qs = false; }
+    if (TR::G && qg1d > R1) { rg = qg1d * rho; L_qg = true; } else { qg1d = 0.0f; rg = R1; L_qg = false; }
+
+    // ---- S2, M:1503-1533 -------------------------------------------------------------------
+    float tempc = temp - 273.15f;
+    float rhof = sqrtf(ck.rho_not / rho);
+    float rhof2 = sqrtf(rhof);
+    float qvs = rslf(pres, temp);
+    const float qvsi = (tempc <= 0.0f) ? rsif(pres, temp) : qvs;
+    float ssatw = qv / qvs - 1.f;
+    float ssati = qv / qvsi - 1.f;
+    if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
+    if (fabsf(ssati) < EPSF) ssati = 0.0f;
+    // diffu (M:1512) is read by vapour deposition / sublimation and melting of ice, snow and graupel only (M:1896,
+    // M:2126, M:2156, M:2166, M:2238, M:2255); rain evaporation evaluates its own (M:2888)
+    const bool ice_any = TR::ICEPROC && !iiwarm && (L_qi || L_qs || L_qg);
+    float diffu = 0.f;
+    if (ice_any) diffu = 2.11E-5f * pow_f(temp / 273.15f, 1.94f) * (101325.f / pres);
+    float visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
+                                  : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
+    float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+    float vsc2 = sqrtf(rho / visco);
+    float lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+    float tcond = (5.69f + 0.0168f * tempc) * 1.0E-5f * 418.936f;
+
+    if (TR::ICEPROC && !iiwarm) {
+      // ---- S3, M:1545-1628 snow moments ----------------------------------------------------
+      if (L_qs) {
+        const float tc0 = fminf(-0.1f, temp - 273.15f);
+        smob = rs * ck.oams;
+        const float smo2 = smob;                    // bm_s = 2 branch of M:1553
+        const float* sa = c_sa; const float* sb = c_sb;
+        // Of the six moments of M:1555-1626 the 1st and the (1+(bv_s+1)/2)-th feed deposition, sublimation and melting
+        // of every snow level.  The 0th is only read by the melting number rate (M:2242, at or above 0 C), the
+        // (bm_s+1)-th by riming (M:1905, with cloud water) and the (bv_s+2)-th by riming and by the collection of
+        // cloud ice (M:1910, M:2185): those three are evaluated where they are read.
+        float loga_ = sa[1] + sa[2] * tc0 + sa[3] + sa[4] * tc0 + sa[5] * tc0 * tc0 + sa[6] + sa[7] * tc0 * tc0
+                      + sa[8] * tc0 + sa[9] * tc0 * tc0 * tc0 + sa[10];
+        float b_ = sb[1] + sb[2] * tc0 + sb[3] + sb[4] * tc0 + sb[5] * tc0 * tc0 + sb[6] + sb[7] * tc0 * tc0
+                   + sb[8] * tc0 + sb[9] * tc0 * tc0 * tc0 + sb[10];
+        smo1 = pow10_f(loga_) * pow_f(smo2, b_);
+        smof = field_moment(tc0, ck.cse[15], smo2);
+      }
+      // ---- S4, M:1633-1654 graupel intercept: the running minimum of M:1648 comes from k_n0_sweep -----------
+      if (TR::G && L_qg) graupel_slope((double)sc[SC_N0A * ps], rg, ilamg, N0_g);
+    }
+    // M:1661-1666 rain slope and intercept.  Without rain (rr = R1, nr = R2) every reader of lamr, ilamr, N0_r
+    // and mvd_r is switched off (L_qr at M:1676, M:1724, M:2880; rr >= r_r(1) at M:1818, M:1964, M:2028, M:2188)
+    if (TR::R && L_qr) {
+      if (lamr_stale) { lamr = rain_lam(nr, rr); mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr); }
+      ilamr = (double)1.f / lamr;
+      N0_r = (double)(nr * ck.org2) * lamr;                                // lamr**cre(2), cre(2) = 1
+    }
+
+    // ---- S5, M:1676-1742 warm rain -----------------------------------------------------------
+    if (TR::R && L_qr && mvd_r > D0r) {
+      const float Ef_rr = 1.0f - exp_f(2300.0f * (mvd_r - 1950.0E-6f));
+      pnr_rcr = (double)(Ef_rr * 2.0f * nr * rr);
+      nr_acc -= pnr_rcr;
+    }
+    mvd_c = D0c;
+    if (TR::C && L_qc) {
+      nu_c = min(15, nint_f(1000.E6f / nc) + 2);
+      xDc = fmaxf(D0c * 1.E6f, pow_f(rc / (ck.am_r * nc), ck.obmr) * 1.E6f);
+      lamc = (double)pow_f(nc * ck.am_r * ck.ccg[1][nu_c - 1] * ck.ocg1[nu_c - 1] / rc, ck.obmr);
+      mvd_c = (float)((double)(3.0f + (float)nu_c + 0.672f) / lamc);
+    }
+    if (TR::C && rc > 0.01e-3f) {
+      const float Dc_g = (float)(((double)ck.dcg_fac[nu_c - 1] / lamc) * (double)1.E6f);
+      const float Dc_b = pow_f(xDc * xDc * xDc * Dc_g * Dc_g * Dc_g - xDc * xDc * xDc * xDc * xDc * xDc, 1.f / 6.f);
+      const float zeta1 = 0.5f * ((6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f) + fabsf(6.25E-6f * xDc * Dc_b * Dc_b * Dc_b - 0.4f));
+      const float zeta = 0.027f * rc * zeta1;
+      // Below the autoconversion threshold zeta is exactly +0 (most cloudy cells) and so are the three rates: the
+      // divisions are skipped there (0/x takes the slow path of the division routines: 3 x ~60 instructions for
+      // nearly every cloud level, profiles/r01).  A NaN zeta (negative argument of the 6th root) takes the full path.
+      if (!(zeta == 0.0f)) {
+        const float taud = 0.5f * ((0.5f * Dc_b - 7.5f) + fabsf(0.5f * Dc_b - 7.5f)) + R1;
+        const float tau = 3.72f / (rc * taud);
+        prr_wau = (double)(zeta / tau);
+        prr_wau = fmin((double)(rc * odts), prr_wau);
+        pnr_wau = prr_wau / (double)(ck.am_r * (float)nu_c * D0r * D0r * D0r);
+        pnc_wau = fmin((double)(nc * odts), prr_wau / (double)(ck.am_r * mvd_c * mvd_c * mvd_c));
+        nr_acc += pnr_wau; nc_acc -= pnc_wau;
+      }
+    }
+    if (TR::R && TR::C && L_qr && mvd_r > D0r && mvd_c > D0c) {
+      lamr = (double)1.f / ilamr;
+      int idx = 1 + (int)((double)NBINS * log((double)mvd_r / ck.Dr1) / ck.lnDr);
+      idx = min(idx, (int)NBINS);
+      int jc = (int)(mvd_c * 1.E6f);
+      jc = max(1, min(jc, (int)NBINS));                                   // U11: bound the unbounded subscript
+      const float Ef_rw = ck.efrw[(idx - 1) + NBINS * (jc - 1)];
+      const double lf4 = 1.0 / sq_d(sq_d(lamr + (double)KP_FV_R));          // (lamr+fv_r)**(-cre(9)), cre(9) = 4
+      prr_rcw = (double)(rhof * ck.t1_qr_qc * Ef_rw * rc) * N0_r * lf4;
+      prr_rcw = fmin((double)(rc * odts), prr_rcw);
+      pnc_rcw = (double)(rhof * ck.t1_qr_qc * Ef_rw * nc) * N0_r * lf4;
+      pnc_rcw = fmin((double)(nc * odts), pnc_rcw);
+      nc_acc -= pnc_rcw;
+    }
+
+    LOCKBAR(1);
+    // ---- S6, M:1749-2286 ice-phase processes --------------------------------------------------
+    if (TR::ICEPROC && !iiwarm) {
+      vts_boost = 1.5f;
+      tempc = temp - 273.15f;
+      const int idx_tc = max(1, min(nint_f(-tempc), 45));
+      int idx_t = (int)((tempc - 2.5f) / 5.f) - 1;
+      idx_t = max(1, -idx_t);
+      idx_t = min(idx_t, (int)NTB_T);
+      const int idx_c = (TR::C && rc > ck.r_c1) ? decade_idx_f(rc, ck.nic2, NTB_C) : 1;
+      const int idx_i = (ri > ck.r_i1) ? decade_idx_f(ri, ck.nii2, NTB_I) : 1;
+      const int idx_i1 = (ni > ck.Nt_i1) ? decade_idx_f(ni, ck.nii3, NTB_I1) : 1;
+      int idx_r = 1, idx_r1 = NTB_R1, idx_s = 1, idx_g = 1, idx_g1 = NTB_G1;
+      if (TR::R && rr > ck.r_r1) {
+        idx_r = decade_idx_f(rr, ck.nir2, NTB_R);
+        lamr = (double)1.f / ilamr;
+        const double lam_exp = lamr * (double)ck.n0r_fac;
+        const double N0_exp = (double)(ck.org1 * rr / ck.am_r) * sq_d(sq_d(lam_exp));   // **cre(1), cre(1) = 4
+        idx_r1 = decade_idx_d(N0_exp, ck.nir3, NTB_R1);
+      }
+      if (TR::R) idx_s = (rs > ck.r_s1) ? decade_idx_f(rs, ck.nis2, NTB_S) : 1;          // only the rain-snow tables read it
+      if (TR::R && TR::G && rg > ck.r_g1) {                                              // only the rain-graupel tables read them
+        idx_g = decade_idx_f(rg, ck.nig2, NTB_G);
+        const double lamg = (double)1.f / ilamg;
+        const double lam_exp = lamg * (double)ck.n0g_fac;
+        const double N0_exp = (double)(ck.ogg1 * rg / ck.am_g) * sq_d(sq_d(lam_exp));   // **cge(1), cge(1) = 4
+        idx_g1 = decade_idx_d(N0_exp, ck.nig3, NTB_G1);
+      }
+
+      // M:1884-1900 sublimation/deposition prefactor
+      // (rvs and t1_subl are read by the deposition / sublimation rates of ice, snow and graupel only)
+      float rvs = 0.f, t1_subl = 0.f;
+      if (ice_any) {
+        const float otemp = 1.f / temp;
+        const float lsub = KP_LSUB, oRv = ck.oRv;
+        rvs = rho * qvsi;
+        const float rvs_p = rvs * otemp * (lsub * otemp * oRv - 1.f);
+        const float rvs_pp = rvs * (otemp * (lsub * otemp * oRv - 1.f) * otemp * (lsub * otemp * oRv - 1.f)
+                                    + (-2.f * lsub * otemp * otemp * otemp * oRv) + otemp * otemp);
+        const float gamsc = lsub * diffu / tcond * rvs_p;
+        float alphsc = 0.5f * (gamsc / (1.f + gamsc)) * (gamsc / (1.f + gamsc)) * rvs_pp / rvs_p * rvs / rvs_p;
+        alphsc = fmaxf(1.E-9f, alphsc);
+        float xsat = ssati;
+        if (fabsf(xsat) < 1.E-9f) xsat = 0.f;
+        t1_subl = 4.f * KP_PI * (1.0f - alphsc * xsat + 2.f * alphsc * alphsc * xsat * xsat
+                                 - 5.f * alphsc * alphsc * alphsc * xsat * xsat * xsat) / (1.f + gamsc);
+      }
+
+      // M:1903-1935 riming of snow and graupel
+      if (TR::C && L_qc && mvd_c > D0c) {
+        float xDs = 0.0f;
+        if (L_qs) { smoc = field_moment(fminf(-0.1f, temp - 273.15f), ck.cse[0], smob); xDs = smoc / smob; }
+        if (xDs > D0s) {
+          smoe = field_moment(fminf(-0.1f, temp - 273.15f), ck.cse[12], smob); have_smoe = true;
+          int idx = 1 + (int)((double)NBINS * log((double)xDs / ck.Ds1) / ck.lnDs);
+          idx = min(idx, (int)NBINS);
+          int jc = (int)(mvd_c * 1.E6f);
+          jc = max(1, min(jc, (int)NBINS));                               // U11
+          const float Ef_sw = ck.efsw[(idx - 1) + NBINS * (jc - 1)];
+          prs_scw = (double)(rhof * ck.t1_qs_qc * Ef_sw * rc * smoe);
+          pnc_scw = (double)(rhof * ck.t1_qs_qc * Ef_sw * nc * smoe);
+          pnc_scw = fmin((double)(nc * odts), pnc_scw);
+          nc_acc -= pnc_scw;
+        }
+        if (TR::G && rg >= ck.r_g1 && mvd_c > D0c) {
+          const float xDg = (float)((double)(3.f + 0.f + 1.f) * ilamg);
+          const float vtg = (float)((double)(rhof * KP_AV_G * ck.cgg[5] * ck.ogg3) * pow_d(ilamg, (double)KP_BV_G));
+          const float stoke_g = mvd_c * mvd_c * vtg * KP_RHO_W / (9.f * visco * xDg);
+          if (xDg > D0g) {
+            float Ef_gw = 0.0f;
+            if (stoke_g >= 0.4f && stoke_g <= 10.f) Ef_gw = 0.55f * log10_f(2.51f * stoke_g);
+            else if (stoke_g < 0.4f) Ef_gw = 0.0f;
+            else if (stoke_g > 10.f) Ef_gw = 0.77f;
+            const double il9 = pow_d(ilamg, (double)ck.cge[8]);
+            prg_gcw = (double)(rhof * ck.t1_qg_qc * Ef_gw * rc) * N0_g * il9;
+            pnc_gcw = (double)(rhof * ck.t1_qg_qc * Ef_gw * nc) * N0_g * il9;
+            pnc_gcw = fmin((double)(nc * odts), pnc_gcw);
+            nc_acc -= pnc_gcw;
+          }
+        }
+      }
+
+      // M:1964-2019 rain-snow and rain-graupel collection tables (interleaved records)
+      if (TR::R && rr >= ck.r_r1) {
+        if (rs >= ck.r_s1) {
+          const double* rec = ck.racs + ((size_t)(idx_s - 1) + (size_t)NTB_S * ((idx_t - 1) + (size_t)NTB_T * ((idx_r1 - 1) + (size_t)NTB_R1 * (idx_r - 1)))) * S_N;
+          const double tmr2 = rec[S_TMR_RACS2], tcr2 = rec[S_TCR_SACR2], tmr1 = rec[S_TMR_RACS1], tcr1 = rec[S_TCR_SACR1];
+          const double tcs1 = rec[S_TCS_RACS1], tms1 = rec[S_TMS_SACR1];
+          if (temp < T_0) {
+            prr_rcs = -(tmr2 + tcr2 + tmr1 + tcr1);
+            prs_rcs = tmr2 + tcr2 - tcs1 - tms1;
+            prg_rcs = tmr1 + tcr1 + tcs1 + tms1;
+            prr_rcs = fmax((double)(-rr * odts), prr_rcs);
+            prs_rcs = fmax((double)(-rs * odts), prs_rcs);
+            prg_rcs = fmin((double)((rr + rs) * odts), prg_rcs);
+            pnr_rcs = rec[S_TNR_RACS1] + rec[S_TNR_RACS2] + rec[S_TNR_SACR1] + rec[S_TNR_SACR2];
+          } else {
+            prs_rcs = -tcs1 - tms1 + tmr2 + tcr2;
+            prs_rcs = fmax((double)(-rs * odts), prs_rcs);
+            prr_rcs = -prs_rcs;
+            pnr_rcs = rec[S_TNR_RACS2] + rec[S_TNR_SACR2];
+          }
+          pnr_rcs = fmin((double)(nr * odts), pnr_rcs);
+          nr_acc -= pnr_rcs;
+        }
+        if (TR::G && rg >= ck.r_g1) {
+          const double* rec = ck.racg + ((size_t)(idx_g1 - 1) + (size_t)NTB_G1 * ((idx_g - 1) + (size_t)NTB_G * ((idx_r1 - 1) + (size_t)NTB_R1 * (idx_r - 1)))) * G_N;
+          if (temp < T_0) {
+            prg_rcg = rec[G_TMR_RACG] + rec[G_TCR_GACR];
+            prg_rcg = fmin((double)(rr * odts), prg_rcg);
+            prr_rcg = -prg_rcg;
+            pnr_rcg = rec[G_TNR_RACG] + rec[G_TNR_GACR];
+            pnr_rcg = fmin((double)(nr * odts), pnr_rcg);
+            nr_acc -= pnr_rcg;
+          } else {
+            prr_rcg = rec[G_TCG_RACG];
+            prr_rcg = fmin((double)(rg * odts), prr_rcg);
+            prg_rcg = -prr_rcg;
+            pnr_rcg = (double)-5.f * rec[G_TNR_GACR];
+            nr_acc -= pnr_rcg;
+          }
+        }
+      }
+
+      if (TR::COLD || temp < T_0) {
+        // ---- below freezing, M:2025-2231 ---------------------------------------------------
+        vts_boost = 1.0f;
+        const float rate_max = (qv - qvsi) * rho * odts * 0.999f;
+        if (TR::R && rr > ck.r_r1) {
+          const double* rec = ck.qrfz + ((size_t)(idx_r - 1) + (size_t)NTB_R * ((idx_r1 - 1) + (size_t)NTB_R1 * (idx_tc - 1))) * F_N;
+          prg_rfz = rec[F_TPG] * (double)odts;
+          pri_rfz = rec[F_TPI] * (double)odts;
+          pni_rfz = rec[F_TNI] * (double)odts;
+          pnr_rfz = rec[F_TNR] * (double)odts;
+          pnr_rfz = fmin((double)(nr * odts), pnr_rfz);
+          nr_acc -= pnr_rfz; ni_acc += pni_rfz;
+        } else if (TR::R && rr > R1 && temp < KP_HGFR) {
+          pri_rfz = (double)(rr * odts);
+          pnr_rfz = (double)(nr * odts);
+          pni_rfz = pnr_rfz;
+          nr_acc -= pnr_rfz; ni_acc += pni_rfz;
+        }
+        if (TR::C && rc > ck.r_c1) {
+          const double* rec = ck.qcfz + ((size_t)(idx_c - 1) + (size_t)NTB_C * (idx_tc - 1)) * C_N;
+          pri_wfz = rec[C_TPI] * (double)odts;
+          pri_wfz = fmin((double)(rc * odts), pri_wfz);
+          pni_wfz = rec[C_TNI] * (double)odts;
+          pni_wfz = fmin(fmin((double)(Nt_c * odts), pri_wfz / (double)(2.f * KP_XM0I)), pni_wfz);
+          ni_acc += pni_wfz; nc_acc -= pni_wfz;
+        } else if (TR::C && rc > R1 && temp < KP_HGFR) {
+          pri_wfz = (double)(rc * odts);
+          pni_wfz = (double)(nc * odts);
+          ni_acc += pni_wfz; nc_acc -= pni_wfz;
+        }
+        // M:2090-2101 Cooper nucleation
+        if ((ssati >= 0.25f) || (ssatw > EPSF && temp < 253.15f)) {
+          const float xnc = fminf(250.E3f, KP_TNO * exp_f(KP_ATO * (T_0 - temp)));
+          const float xni = (float)((double)ni + (pni_rfz + pni_wfz) * (double)DT);
+          pni_inu = (double)(0.5f * (xnc - xni + fabsf(xnc - xni)) * odts);
+          pri_inu = fmin((double)rate_max, (double)KP_XM0I * pni_inu);
+          pni_inu = (pri_inu == 0.0) ? pri_inu : pri_inu / (double)KP_XM0I;      // (a zero keeps its sign either way)
+          ni_acc += pni_inu;
+        }
+        // M:2116-2149 deposition / sublimation of cloud ice, ice -> snow
+        float oxmi = 0.f, xDi = 0.f;
+        if (L_qi) {
+          if (lami_stale) lami = ice_lam(ni, ri);
+          ilami = (double)1.f / lami;
+          xDi = (float)fmax((double)ck.D0i, (double)(3.f + 0.f + 1.f) * ilami);
+          const float xmi = ck.am_i * cube_f(xDi);
+          oxmi = 1.f / xmi;
+          pri_ide = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs * ck.oig1 * ck.cig[4] * ni) * ilami;
+          const double* rec = ck.iaus + ((size_t)(idx_i - 1) + (size_t)NTB_I * (idx_i1 - 1)) * I_N;
+          if (pri_ide < 0.0) {
+            pri_ide = fmax(fmax((double)(-ri * odts), pri_ide), (double)rate_max);
+            pni_ide = pri_ide * (double)oxmi;
+            pni_ide = fmax((double)(-ni * odts), pni_ide);
+          } else {
+            pri_ide = fmin(pri_ide, (double)rate_max);
+            prs_ide = (1.0 - rec[I_TPI_IDE]) * pri_ide;
+            pri_ide = rec[I_TPI_IDE] * pri_ide;
+          }
+          if ((idx_i == NTB_I) || (xDi > 5.0f * D0s)) {
+            prs_iau = (double)(ri * .99f * odts);
+            pni_iau = (double)(ni * .95f * odts);
+          } else if (xDi < 0.1f * D0s) {
+            prs_iau = 0.; pni_iau = 0.;
+          } else {
+            prs_iau = rec[I_TPS] * (double)odts;
+            prs_iau = fmin((double)(ri * .99f * odts), prs_iau);
+            pni_iau = rec[I_TNI] * (double)odts;
+            pni_iau = fmin((double)(ni * .95f * odts), pni_iau);
+          }
+          ni_acc -= pni_iau;
+        }
+        // M:2153-2175 deposition / sublimation of snow, sublimation of graupel
+        if (L_qs) {
+          float C_snow = KP_C_SQRD + (tempc + 1.5f) * (KP_C_CUBE - KP_C_SQRD) / (-30.f + 1.5f);
+          C_snow = fmaxf(KP_C_SQRD, fminf(C_snow, KP_C_CUBE));
+          prs_sde = (double)(C_snow * t1_subl * diffu * ssati * rvs
+                             * (ck.t1_qs_sd * smo1 + ck.t2_qs_sd * rhof2 * vsc2 * smof));
+          if (prs_sde < 0.) prs_sde = fmax(fmax((double)(-rs * odts), prs_sde), (double)rate_max);
+          else prs_sde = fmin(prs_sde, (double)rate_max);
+        }
+        if (TR::G && L_qg && ssati < -EPSF) {
+          prg_gde = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs) * N0_g
+                    * ((double)ck.t1_qg_sd * sq_d(ilamg)
+                       + (double)(ck.t2_qg_sd * vsc2 * rhof2) * pow_d(ilamg, (double)ck.cge[10]));
+          if (prg_gde < 0.) prg_gde = fmax(fmax((double)(-rg * odts), prg_gde), (double)rate_max);
+          else prg_gde = fmin(prg_gde, (double)rate_max);
+        }
+        // M:2178-2202 snow and rain collecting cloud ice (lami/xDi/oxmi as recomputed at M:2179-2183)
+        if (L_qi) {
+          if (rs >= ck.r_s1) {
+            if (!have_smoe) smoe = field_moment(fminf(-0.1f, temp - 273.15f), ck.cse[12], smob);
+            prs_sci = (double)(ck.t1_qs_qi * rhof * KP_EF_SI * ri * smoe);
+            pni_sci = prs_sci * (double)oxmi;
+            ni_acc -= pni_sci;
+          }
+          if (TR::R && rr >= ck.r_r1 && mvd_r > 4.f * xDi) {
+            lamr = (double)1.f / ilamr;
+            const double lf = lamr + (double)KP_FV_R;
+            const double lf2 = lf * lf, lf4 = 1.0 / (lf2 * lf2), lf7 = 1.0 / (lf2 * lf2 * lf2 * lf);
+            pri_rci = (double)(rhof * ck.t1_qr_qi * KP_EF_RI * ri) * N0_r * lf4;
+            pnr_rci = (double)(rhof * ck.t1_qr_qi * KP_EF_RI * ni) * N0_r * lf4;
+            pni_rci = pri_rci * (double)oxmi;
+            nr_acc -= pnr_rci; ni_acc -= pni_rci;
+            prr_rci = (double)(rhof * ck.t2_qr_qi * KP_EF_RI * ni) * N0_r * lf7;       // cre(8) = 7
+            prr_rci = fmin((double)(rr * odts), prr_rci);
+            prg_rci = pri_rci + prr_rci;
+          }
+        }
+        // M:2205-2218 Hallett-Mossop
+        if (TR::C && TR::G && prg_gcw > (double)EPSF && tempc > -8.0f) {
+          float tf = 0.f;
+          if (tempc >= -5.0f && tempc < -3.0f) tf = 0.5f * (-3.0f - tempc);
+          else if (tempc > -8.0f && tempc < -5.0f) tf = 0.33333333f * (8.0f + tempc);
+          pni_ihm = (double)(3.5E8f * tf) * prg_gcw;
+          pri_ihm = (double)KP_XM0I * pni_ihm;
+          ni_acc += pni_ihm;
+          prs_ihm = prs_scw / (prs_scw + prg_gcw) * pri_ihm;
+          prg_ihm = prg_gcw / (prs_scw + prg_gcw) * pri_ihm;
+        }
+        // M:2224-2231 rimed snow -> graupel
+        if (TR::C && prs_scw > (double)2.0f * prs_sde && prs_sde > (double)EPSF) {
+          const float r_frac = (float)fmin(30.0, prs_scw / prs_sde);
+          const float g_frac = fminf(0.95f, 0.15f + (r_frac - 2.f) * .028f);
+          vts_boost = fminf(1.5f, 1.1f + (r_frac - 2.f) * .016f);
+          prg_scw = (double)g_frac * prs_scw;
+          prs_scw = (double)(1.f - g_frac) * prs_scw;
+        }
+      } else if (!TR::COLD) {
+        // ---- at or above freezing, M:2237-2281 ----------------------------------------------
+        float delQvs = 0.f;                                                // M:1508, read by the melting terms only
+        if (L_qs || L_qg) delQvs = fmaxf(0.0f, rslf(pres, 273.15f) - qv);
+        if (L_qs) {
+          prr_sml = (double)((tempc * tcond - KP_LVAP0 * diffu * delQvs)
+                             * (ck.t1_qs_me * smo1 + ck.t2_qs_me * rhof2 * vsc2 * smof));
+          prr_sml = prr_sml + (double)(4218.f * ck.olfus * tempc) * (prr_rcs + prs_scw);
+          prr_sml = fmin((double)(rs * odts), fmax(0., prr_sml));
+          {                                          // 0th moment, M:1557-1560
+            const float tc0 = fminf(-0.1f, temp - 273.15f);
+            const float* sa = c_sa; const float* sb = c_sb;
+            const float loga_ = sa[1] + sa[2] * tc0 + sa[5] * tc0 * tc0 + sa[9] * tc0 * tc0 * tc0;
+            const float b_ = sb[1] + sb[2] * tc0 + sb[5] * tc0 * tc0 + sb[9] * tc0 * tc0 * tc0;
+            smo0 = pow10_f(loga_) * pow_f(smob, b_);
+          }
+          pnr_sml = (double)(smo0 / rs) * prr_sml * (double)pow10_f(-0.25f * tempc);
+          pnr_sml = fmin((double)(smo0 * odts), pnr_sml);
+          nr_acc += pnr_sml;
+          if (ssati < 0.f) {
+            prs_sde = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs
+                               * (ck.t1_qs_sd * smo1 + ck.t2_qs_sd * rhof2 * vsc2 * smof));
+            prs_sde = fmax((double)(-rs * odts), prs_sde);
+          }
+        }
+        if (TR::G && L_qg) {
+          const double il10 = sq_d(ilamg), il11 = pow_d(ilamg, (double)ck.cge[10]);
+          prr_gml = (double)(tempc * tcond - KP_LVAP0 * diffu * delQvs) * N0_g
+                    * ((double)ck.t1_qg_me * il10 + (double)(ck.t2_qg_me * rhof2 * vsc2) * il11);
+          prr_gml = fmin((double)(rg * odts), fmax(0., prr_gml));
+          pnr_gml = N0_g * (double)ck.cgg[1] * ilamg / (double)rg * prr_gml * (double)pow10_f(-0.5f * tempc);
+          nr_acc += pnr_gml;
+          if (ssati < 0.f) {
+            prg_gde = (double)(KP_C_CUBE * t1_subl * diffu * ssati * rvs) * N0_g
+                      * ((double)ck.t1_qg_sd * il10 + (double)(ck.t2_qg_sd * vsc2 * rhof2) * il11);
+            prg_gde = fmax((double)(-rg * odts), prg_gde);
+          }
+        }
+        if (DT > 120.f) {
+          prr_rcw = prr_rcw + prs_scw + prg_gcw;
+          prs_scw = 0.; prg_gcw = 0.;
+        }
+      }
+    }
+
+    LOCKBAR(2);
+    // ---- S7, M:2291-2387 conservation limiters -----------------------------------------------
+    // (a group is compiled for a class only when one of its rates can be non-zero there; the flag of the species guards it)
+    {
+      float sump, rate_max;
+      if (TR::ICEPROC) {
+        sump = (float)(pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + 0.0);
+        rate_max = (qv - qvsi) * odts * 0.999f;                                // U7: no rho factor here
+        if ((sump > EPSF && sump > rate_max) || (sump < -EPSF && sump < rate_max)) {
+          const double ratio = (double)(rate_max / sump);
+          pri_inu *= ratio; pri_ide *= ratio; pni_ide *= ratio; prs_ide *= ratio; prs_sde *= ratio;
+          if (TR::G) prg_gde *= ratio;
+        }
+      }
+      if (TR::C) {
+        sump = (float)(-prr_wau - pri_wfz - prr_rcw - prs_scw - prg_scw - prg_gcw);
+        rate_max = -rc * odts;
+        if (sump < rate_max && L_qc) {
+          const double ratio = (double)(rate_max / sump);
+          prr_wau *= ratio;
+          if (TR::R) prr_rcw *= ratio;
+          if (TR::ICEPROC) { pri_wfz *= ratio; prs_scw *= ratio; prg_scw *= ratio; }
+          if (TR::G) prg_gcw *= ratio;
+        }
+      }
+      if (TR::I) {
+        sump = (float)(pri_ide - prs_iau - prs_sci - pri_rci);
+        rate_max = -ri * odts;
+        if (sump < rate_max && L_qi) {
+          const double ratio = (double)(rate_max / sump);
+          pri_ide *= ratio; prs_iau *= ratio; prs_sci *= ratio;
+          if (TR::R) pri_rci *= ratio;
+        }
+      }
+      if (TR::R) {
+        sump = (float)(-prg_rfz - pri_rfz - prr_rci + prr_rcs + prr_rcg);
+        rate_max = -rr * odts;
+        if (sump < rate_max && L_qr) {
+          const double ratio = (double)(rate_max / sump);
+          if (TR::ICEPROC) { prg_rfz *= ratio; pri_rfz *= ratio; prr_rci *= ratio; prr_rcs *= ratio; prr_rcg *= ratio; }
+        }
+      }
+      if (TR::S) {
+        sump = (float)(prs_sde - prs_ihm - prr_sml + prs_rcs);
+        rate_max = -rs * odts;
+        if (sump < rate_max && L_qs) {
+          const double ratio = (double)(rate_max / sump);
+          prs_sde *= ratio; prs_ihm *= ratio; prr_sml *= ratio;
+          if (TR::R) prs_rcs *= ratio;
+        }
+      }
+      if (TR::G) {
+        sump = (float)(prg_gde - prg_ihm - prr_gml + prg_rcg);
+        rate_max = -rg * odts;
+        if (sump < rate_max && L_qg) {
+          const double ratio = (double)(rate_max / sump);
+          prg_gde *= ratio; prg_ihm *= ratio; prr_gml *= ratio;
+          if (TR::R) prg_rcg *= ratio;
+        }
+      }
+      pri_ihm = prs_ihm + prg_ihm;
+      if (TR::R && TR::G) {
+        float ratio = (float)fmin(fabs(prr_rcg), fabs(prg_rcg));
+        prr_rcg = (double)(ratio * copysignf(1.0f, (float)prr_rcg));
+        prg_rcg = -prr_rcg;
+      }
+      if (TR::R && TR::S && temp > T_0) {
+        float ratio = (float)fmin(fabs(prr_rcs), fabs(prs_rcs));
+        prr_rcs = (double)(ratio * copysignf(1.0f, (float)prr_rcs));
+        prs_rcs = -prr_rcs;
+      }
+    }
+
+    // U1 again (nc1d = 0 without cloud water, M:1409)
+    const float nc1d = (qc1d > R1) ? Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f))) : 0.0f;
+    // ---- S8, M:2393-2569 tendencies and number/mass balances ------------------------------------
+    float tt, qvt, qct, qit, qrt, qst, qgt, nit, nrt, nct;
+    {
+      const float orho = 1.f / rho;
+      const float lfus2 = KP_LSUB - lvap;
+      qvt = (float)((-pri_inu - pri_ide - prs_ide - prs_sde - prg_gde) * (double)orho);
+      qct = (float)((-prr_wau - pri_wfz - prr_rcw - prs_scw - prg_scw - prg_gcw) * (double)orho);
+      nct = (float)(nc_acc * (double)orho);
+      float xrc = fmaxf(R1, (qc1d + qct * DT) * rho);
+      float xnc = fmaxf(2.f, (nc1d + nct * DT) * rho);
+      if (TR::C && xrc > R1) {
+        const int nu = min(15, nint_f(1000.E6f / xnc) + 2);
+        const double lc = (double)pow_f(xnc * ck.am_r * ck.ccg[1][nu - 1] * ck.ocg1[nu - 1] / rc, ck.obmr);
+        const float xD = (float)((double)(3.f + (float)nu + 1.f) / lc);
+        if (xD < D0c) {
+          const double l2 = (double)(ck.cce[1][nu - 1] / D0c);
+          xnc = (float)((double)(ck.ccg[0][nu - 1] * ck.ocg2[nu - 1] * xrc / ck.am_r) * cube_d(l2));
+          nct = (xnc - nc1d * rho) * odts * orho;
+        } else if (xD > D0r * 2.f) {
+          const double l2 = (double)(ck.cce[1][nu - 1] / (D0r * 2.f));
+          xnc = (float)((double)(ck.ccg[0][nu - 1] * ck.ocg2[nu - 1] * xrc / ck.am_r) * cube_d(l2));
+          nct = (xnc - nc1d * rho) * odts * orho;
+        }
+      } else {
+        nct = -nc1d * odts;
+      }
+      xnc = fmaxf(0.f, (nc1d + nct * DT) * rho);
+      if (xnc > KP_NT_C_MAX) nct = (KP_NT_C_MAX - nc1d * rho) * odts * orho;
+
+      qit = (float)((pri_inu + pri_ihm + pri_wfz + pri_rfz + pri_ide - prs_iau - prs_sci - pri_rci) * (double)orho);
+      nit = (float)((ni_acc + pni_ide) * (double)orho);
+      const float xri = fmaxf(R1, (qi1d + qit * DT) * rho);
+      float xni = fmaxf(R2, (ni1d + nit * DT) * rho);
+      if (TR::I9 && xri > R1) {
+        lami = ice_lam(xni, xri);
+        ilami = (double)1.f / lami;
+        const float xD = (float)((double)(3.f + 0.f + 1.f) * ilami);
+        if (xD < 5.E-6f) {
+          lami = (double)(ck.cie[1] / 5.E-6f);
+          xni = (float)fmin(499.E3, (double)(ck.cig[0] * ck.oig2 * xri / ck.am_i) * cube_d(lami));
+          nit = (xni - ni1d * rho) * odts * orho;
+        } else if (xD > 300.E-6f) {
+          lami = (double)(ck.cie[1] / 300.E-6f);
+          xni = (float)((double)(ck.cig[0] * ck.oig2 * xri / ck.am_i) * cube_d(lami));
+          nit = (xni - ni1d * rho) * odts * orho;
+        }
+      } else {
+        nit = -ni1d * odts;
+      }
+      xni = fmaxf(0.f, (ni1d + nit * DT) * rho);
+      if (xni > 499.E3f) nit = (499.E3f - ni1d * rho) * odts * orho;
+
+      qrt = (float)((prr_wau + prr_rcw + prr_sml + prr_gml + prr_rcs + prr_rcg - prg_rfz - pri_rfz - prr_rci) * (double)orho);
+      nrt = (float)(nr_acc * (double)orho);
+      const float xrr = fmaxf(R1, (qr1d + qrt * DT) * rho);
+      float xnr = fmaxf(R2, (nr1d + nrt * DT) * rho);
+      if (TR::R9 && xrr > R1) {
+        lamr = rain_lam(xnr, xrr);
+        mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+        if (mvd_r > 2.5E-3f) {
+          mvd_r = 2.5E-3f;
+          xnr = nr_from_mvd(xrr, mvd_r);
+          nrt = (xnr - nr1d * rho) * odts * orho;
+        } else if (mvd_r < D0r * 0.75f) {
+          mvd_r = D0r * 0.75f;
+          xnr = nr_from_mvd(xrr, mvd_r);
+          nrt = (xnr - nr1d * rho) * odts * orho;
+        }
+      } else {
+        qrt = -qr1d * odts;
+        nrt = -nr1d * odts;
+      }
+      qst = (float)((prs_iau + prs_sde + prs_sci + prs_scw + prs_rcs + prs_ide - prs_ihm - prr_sml) * (double)orho);
+      qgt = (float)((prg_scw + prg_rfz + prg_gde + prg_rcg + prg_gcw + prg_rci + prg_rcs - prg_ihm - prr_gml) * (double)orho);
+      if (TR::COLD || temp < T_0) {
+        tt = (float)(((double)(KP_LSUB * ocp) * (pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + 0.0)
+                      + (double)(lfus2 * ocp) * (pri_wfz + pri_rfz + prg_rfz + prs_scw + prg_scw + prg_gcw + prg_rcs
+                                                 + prs_rcs + prr_rci + prg_rcg))
+                     * (double)orho * (double)1);
+      } else {
+        tt = (float)(((double)(ck.lfus * ocp) * (-prr_sml - prr_gml - prr_rcg - prr_rcs)
+                      + (double)(KP_LSUB * ocp) * (prs_sde + prg_gde))
+                     * (double)orho * (double)1);
+      }
+    }
+
+    // M:2963-3120 the rates KiD saves with save_dg that are final here (optional buffer [36][nz][ld]); the three of S11 /
+    // S12 follow below
+    if (RATES && valid) {
+      float* rp = a.rates + o;
+      const long st = (long)nz * ld;
+      const double rv[30] = {pri_inu, pri_ide, prs_ide, prs_sde, prg_gde, pri_wfz, prs_scw, prg_scw, prg_gcw, pri_ihm,
+                             pri_rfz, prs_iau, prs_sci, pri_rci, pni_inu, pni_ihm, pni_wfz, pni_rfz, pni_ide, pni_iau,
+                             pni_sci, pni_rci, prr_sml, prr_gml, pnr_rcs, pnr_rcg, pnr_rci, pnr_sml, pnr_gml, pnr_rfz};
+#pragma unroll
+      for (int q = 0; q < 30; ++q) rp[q * st] = (float)rv[q];
+      rp[30 * st] = (float)prr_wau; rp[31 * st] = (float)prr_rcw; rp[33 * st] = (float)pnr_wau; rp[35 * st] = (float)pnr_rcr;
+    }
+    const bool melted_graupel = TR::G && prr_gml > 0.0;      // M:2940 reads prr_gml after the limiters
+
+    LOCKBAR(3);
+    // ---- S9, M:2574-2656 state at tau+1 -------------------------------------------------------
+    float lvt2;
+    {
+      temp = t1d + DT * tt;
+      const float otemp = 1.f / temp;
+      tempc = temp - 273.15f;
+      qv = fmaxf(1.E-10f, qv1d + DT * qvt);
+      rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+      qvs = rslf(pres, temp);
+      ssatw = qv / qvs - 1.f;
+      if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
+      // rhof, rhof2, diffu, visco, vsc2, tcond of M:2588-2600 are read by rain evaporation (which evaluates them
+      // again from the post-condensation state here, S12) and the fall speeds (rhof, S13) only
+      lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+      ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+      lvt2 = lvap * lvap * ocp * ck.oRv * otemp * otemp;
+
+      if (TR::C9 && (qc1d + qct * DT) > R1) { rc = (qc1d + qct * DT) * rho; nc = Nt_c; L_qc = true; }
+      else { rc = R1; nc = 2.f; L_qc = false; }
+      if (TR::I9 && (qi1d + qit * DT) > R1) { ri = (qi1d + qit * DT) * rho; ni = fmaxf(R2, (ni1d + nit * DT) * rho); L_qi = true; }
+      else { ri = R1; ni = R2; L_qi = false; }
+      if (TR::R9 && (qr1d + qrt * DT) > R1) {
+        rr = (qr1d + qrt * DT) * rho;
+        nr = fmaxf(R2, (nr1d + nrt * DT) * rho);
+        L_qr = true;
+        lamr = rain_lam(nr, rr);
+        lamr_stale = false;
+        mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+        if (mvd_r > 2.5E-3f) { mvd_r = 2.5E-3f; nr = nr_from_mvd(rr, mvd_r); lamr_stale = true; }
+        else if (mvd_r < D0r * 0.75f) { mvd_r = D0r * 0.75f; nr = nr_from_mvd(rr, mvd_r); lamr_stale = true; }
+      } else { rr = R1; nr = R2; L_qr = false; }
+      if (TR::S9 && (qs1d + qst * DT) > R1) { rs = (qs1d + qst * DT) * rho; L_qs = true; } else { rs = R1; L_qs = false; }
+      if (TR::G9 && (qg1d + qgt * DT) > R1) { rg = (qg1d + qgt * DT) * rho; L_qg = true; } else { rg = R1; L_qg = false; }
+    }
+
+    // ---- S10, M:2662-2750 snow moments and intercepts again -------------------------------------
+    bool warm9 = false;
+    double n0b_lo = n0_empty, n0b_slw = n0_empty;
+    if (!iiwarm) {
+      if (TR::S9 && L_qs) {
+        const float tc0 = fminf(-0.1f, temp - 273.15f);
+        smob = rs * ck.oams;
+        smoc = field_moment(tc0, ck.cse[0], smob);
+        // smod (M:2706-2717) is not read again by any live code
+      }
+      // M:2721-2731: whether this level lies above k_0 depends on the updated temperatures of the levels above,
+      // which k_finish knows: both values of the intercept are handed to it (they differ only with supercooled rain),
+      // and it evaluates the slope, which only the graupel fall speed of S13 reads
+      warm9 = temp >= 270.65f;
+      if (TR::G9) n0b_lo = (rg > 5.E-5f) ? graupel_n0_exp(0.01f, rg) : n0_empty;
+      // (k_finish only reads the second one above k_0, i.e. where no level from here up has reached 270.65 K)
+      n0b_slw = (TR::R9 && !warm9 && L_qr && mvd_r > 100.E-6f) ? graupel_n0_exp(4.01f + log10_f(mvd_r), rg) : n0b_lo;
+    }
+    if (TR::R9 && L_qr) {                                                   // M:2750-2755, as at M:1661
+      if (lamr_stale) { lamr = rain_lam(nr, rr); mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr); lamr_stale = false; }
+      ilamr = (double)1.f / lamr;
+      N0_r = (double)(nr * ck.org2) * lamr;
+    }
+
+    LOCKBAR(4);
+    // ---- S11, M:2780-2874 cloud condensation / evaporation ---------------------------------------
+    if ((ssatw > EPSF) || (ssatw < -EPSF && L_qc)) {
+      const float orho = 1.f / rho;
+      float clap = (qv - qvs) / (1.f + lvt2 * qvs);
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        const float ex = exp_f(lvt2 * clap);
+        const float fcd = qvs * ex - qv + clap;
+        const float dfcd = qvs * lvt2 * ex + 1.f;
+        clap = clap - fcd / dfcd;
+      }
+      const float xrc = rc + clap * rho;
+      if (xrc > R1) {
+        prw_vcd = (double)(clap * odt);
+        if (clap > EPSF) {
+          const float xnc = Nt_c;
+          pnc_wcd = (double)(0.5f * (xnc - nc + fabsf(xnc - nc)) * odts * orho);
+        }
+      } else {
+        prw_vcd = (double)(-rc * orho * odt);
+        pnc_wcd = (double)(-nc * orho * odt);
+      }
+      qvt = (float)((double)qvt - prw_vcd);
+      qct = (float)((double)qct + prw_vcd);
+      nct = (float)((double)nct + pnc_wcd);
+      tt = (float)((double)tt + (double)(lvap * ocp) * prw_vcd * (double)1);
+      rc = fmaxf(R1, (qc1d + DT * qct) * rho);
+      nc = Nt_c;
+      qv = fmaxf(1.E-10f, qv1d + DT * qvt);
+      temp = t1d + DT * tt;
+      rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+      qvs = rslf(pres, temp);
+      ssatw = qv / qvs - 1.f;
+    }
+
+    // ---- S12, M:2880-2960 rain evaporation -------------------------------------------------------
+    if (TR::R9 && (ssatw < -EPSF) && L_qr && (!(prw_vcd > 0.))) {
+      tempc = temp - 273.15f;
+      const float otemp = 1.f / temp;
+      const float orho = 1.f / rho;
+      rhof = sqrtf(ck.rho_not * orho);
+      rhof2 = sqrtf(rhof);
+      diffu = 2.11E-5f * pow_f(temp / 273.15f, 1.94f) * (101325.f / pres);
+      visco = (tempc >= 0.0f) ? (1.718f + 0.0049f * tempc) * 1.0E-5f
+                              : (1.718f + 0.0049f * tempc - 1.2E-5f * tempc * tempc) * 1.0E-5f;
+      vsc2 = sqrtf(rho / visco);
+      lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+      tcond = (5.69f + 0.0168f * tempc) * 1.0E-5f * 418.936f;
+      ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+      const float oRv = ck.oRv;
+      const float rvs = rho * qvs;
+      const float rvs_p = rvs * otemp * (lvap * otemp * oRv - 1.f);
+      const float rvs_pp = rvs * (otemp * (lvap * otemp * oRv - 1.f) * otemp * (lvap * otemp * oRv - 1.f)
+                                  + (-2.f * lvap * otemp * otemp * otemp * oRv) + otemp * otemp);
+      const float gamsc = lvap * diffu / tcond * rvs_p;
+      float alphsc = 0.5f * (gamsc / (1.f + gamsc)) * (gamsc / (1.f + gamsc)) * rvs_pp / rvs_p * rvs / rvs_p;
+      alphsc = fmaxf(1.E-9f, alphsc);
+      const float xsat = fminf(-1.E-9f, ssatw);
+      const float t1_evap = 2.f * KP_PI * (1.0f - alphsc * xsat + 2.f * alphsc * alphsc * xsat * xsat
+                                           - 5.f * alphsc * alphsc * alphsc * xsat * xsat * xsat) / (1.f + gamsc);
+      const double lamr_ev = (double)1.f / ilamr;
+      if (qv / qvs < 0.95f && rr * orho <= 1.E-8f) {
+        prv_rev = (double)(rr * orho * odts);
+      } else {
+        const double lh = lamr_ev + (double)(0.5f * KP_FV_R);
+        prv_rev = (double)(t1_evap * diffu * (-ssatw)) * N0_r * (double)rvs
+                  * ((double)ck.t1_qr_ev * sq_d(ilamr)                                     // ilamr**cre(10), = 2
+                     + (double)(ck.t2_qr_ev * vsc2 * rhof2) * (1.0 / (lh * lh * lh)));      // **(-cre(11)), = 3
+        const float rate_max = fminf((rr * orho * odts), (qvs - qv) * odts);
+        prv_rev = fmin((double)rate_max, prv_rev * (double)orho);
+        if (melted_graupel) {
+          const float eva_factor = fminf(1.0f, 0.01f + (0.99f - 0.01f) * (tempc / 20.0f));
+          prv_rev = prv_rev * (double)eva_factor;
+        }
+      }
+      pnr_rev = fmin((double)(nr * 0.99f * orho * odts), prv_rev * (double)nr / (double)rr);
+      qrt = (float)((double)qrt - prv_rev);
+      qvt = (float)((double)qvt + prv_rev);
+      nrt = (float)((double)nrt - pnr_rev);
+      tt = (float)((double)tt - (double)(lvap * ocp) * prv_rev * (double)1);
+      rr = fmaxf(R1, (qr1d + DT * qrt) * rho);
+      qv = fmaxf(1.E-10f, qv1d + DT * qvt);
+      nr = fmaxf(R2, (nr1d + DT * nrt) * rho);
+      lamr_stale = true;
+      temp = t1d + DT * tt;
+      rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+    }
+    if (RATES && valid) {
+      float* rp = a.rates + o;
+      const long st = (long)nz * ld;
+      rp[32 * st] = (float)prv_rev; rp[34 * st] = (float)pnr_rev;
+    }
+
+    LOCKBAR(5);
+    // ---- S13, M:3206-3354 the cell's own fall speeds (k_finish applies what runs down the column) -------
+    rhof = sqrtf(ck.rho_not / rho);
+    float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, vts_h = 0.f;
+    if (TR::R9 && rr > R1) {
+      if (!L_qr || lamr_stale) lamr = rain_lam(nr, rr);                   // M:3227: same nr, rr as at M:2750 otherwise
+      const double lf = lamr + (double)KP_FV_R;
+      const double l2 = lamr * lamr, lf2 = lf * lf;
+      // lamr**cre(3) * (lamr+fv_r)**(-cre(6)), cre(3) = 4, cre(6) = 5
+      v_r = (float)((double)(rhof * KP_AV_R * ck.crg[5] * ck.org3) * (l2 * l2) * (1.0 / (lf2 * lf2 * lf)));
+      // lamr**cre(12) * (lamr+fv_r)**(-cre(7)), cre(12) = 2.5, cre(7) = 3.5
+      v_nr = (float)((double)(rhof * KP_AV_R * ck.crg[6] / ck.crg[11]) * (l2 * sqrt(lamr)) * (1.0 / (lf2 * lf * sqrt(lf))));
+    }
+    if (TR::ICEPROC && !iiwarm) {
+      if (TR::I9 && ri > R1) {
+        lami = ice_lam(ni, ri);
+        ilami = (double)1.f / lami;
+        v_i = (float)((double)(rhof * KP_AV_I * ck.cig[2] * ck.oig2) * ilami);               // ilami**bv_i, bv_i = 1
+        v_ni = (float)((double)(rhof * KP_AV_I * ck.cig[5] / ck.cig[6]) * ilami);
+      }
+      if (TR::S9 && rs > R1) {
+        const float xDs = smoc / smob;
+        const float Mrat = 1.f / xDs;
+        float ils1 = 1.f / (Mrat * KP_LAM0 + KP_FV_S);
+        float ils2 = 1.f / (Mrat * KP_LAM1 + KP_FV_S);
+        const float mm = pow_f(Mrat, KP_MU_S);
+        const float t1_vts = KP_KAP0 * ck.csg[3] * pow_f(ils1, ck.cse[3]);
+        const float t2_vts = KP_KAP1 * mm * ck.csg[9] * pow_f(ils2, ck.cse[9]);
+        ils1 = 1.f / (Mrat * KP_LAM0);
+        ils2 = 1.f / (Mrat * KP_LAM1);
+        const float t3_vts = KP_KAP0 * ck.csg[0] * pow_f(ils1, ck.cse[0]);
+        const float t4_vts = KP_KAP1 * mm * ck.csg[6] * pow_f(ils2, ck.cse[6]);
+        vts_h = rhof * KP_AV_S * (t1_vts + t2_vts) / (t3_vts + t4_vts);   // M:3301 needs the rain speed after the rule of M:3235: k_finish
+      }
+    }
+
+    // hand-off.  S15 (M:3584-3606) needs lfus*ocp where the level ends above T_0 and lfus2*ocp where it ends
+    // below HGFR (never both): one signed value carries the product and the case.
+    if (valid) {
+      float s15 = 0.0f;
+      if (temp > T_0) s15 = ck.lfus * ocp;
+      else if (temp < KP_HGFR) s15 = -((KP_LSUB - lvap) * ocp);
+      sc[SC_TTEN * ps] = tt; sc[SC_QVTEN * ps] = qvt; sc[SC_QCTEN * ps] = qct; sc[SC_QITEN * ps] = qit;
+      sc[SC_QRTEN * ps] = qrt; sc[SC_QSTEN * ps] = qst; sc[SC_QGTEN * ps] = qgt; sc[SC_NITEN * ps] = nit;
+      sc[SC_NRTEN * ps] = nrt; sc[SC_NCTEN * ps] = nct;
+      sc[SC_RR * ps] = rr; sc[SC_NR * ps] = nr; sc[SC_RI * ps] = ri; sc[SC_NI * ps] = ni; sc[SC_RS * ps] = rs; sc[SC_RG * ps] = rg;
+      sc[SC_VTR * ps] = v_r; sc[SC_VTNR * ps] = v_nr; sc[SC_VTI * ps] = v_i; sc[SC_VTNI * ps] = v_ni;
+      sc[SC_RHO * ps] = rho; sc[SC_S15 * ps] = s15;
+      // the sign of the first intercept carries the k_0 test of this level's updated temperature (intercepts are > 0)
+      sc[SC_N0A * ps] = warm9 ? -(float)n0b_lo : (float)n0b_lo; sc[SC_N0B_SLW * ps] = (float)n0b_slw;
+      sc[SC_VTS_RAW * ps] = vts_h; sc[SC_VTS_BOOST * ps] = vts_boost; sc[SC_TEMP * ps] = temp;
+    }
+  }
+#undef LOCKBAR
+}
+
+// ---- K2: what runs down the column, then S14 sedimentation (M:3365-3578), S15 instant melt / freeze (M:3584-3606) and
+// S16 (M:3623-3686).  One thread per cloudy column (slot), one warp per block.
+__device__ __forceinline__ void sed_substeps(float* __restrict__ r, float* __restrict__ rten, const float* __restrict__ v,
+                                             float* __restrict__ n, float* __restrict__ nten, const float* __restrict__ vn,
+                                             const float* __restrict__ rhoa, const float* __restrict__ dz, long dzs, int nz, long cs,
+                                             int nsub, int ksed, float onstep, float DT, bool on, float nfloor, float& ppt) {
+  for (int it = 0; it < nsub; ++it) {
+    float sr_up = 0.f, sn_up = 0.f, sr_k = 0.f, r0 = 0.f;
+#pragma unroll 1
+    for (int k = nz - 1; k >= 0; --k) {
+      const long o = (long)k * cs;
+      const float rk = r[o];
+      const float sr = on ? v[o] * rk : 0.f;
+      const float odzq = 1.f / dz[k * dzs], orho = 1.f / rhoa[o];
+      float nk = 0.f, sn = 0.f;
+      if (n) { nk = n[o]; sn = on ? vn[o] * nk : 0.f; }
+      if (k == nz - 1) {
+        rten[o] = rten[o] - sr * odzq * onstep * orho;
+        r0 = fmaxf(KP_R1, rk - sr * odzq * DT * onstep);
+        r[o] = r0;
+        if (n) { nten[o] = nten[o] - sn * odzq * onstep * orho; n[o] = fmaxf(nfloor, nk - sn * odzq * DT * onstep); }
+      } else if (k + 1 <= ksed) {
+        rten[o] = rten[o] + (sr_up - sr) * odzq * onstep * orho;
+        r0 = fmaxf(KP_R1, rk + (sr_up - sr) * odzq * DT * onstep);
+        r[o] = r0;
+        if (n) { nten[o] = nten[o] + (sn_up - sn) * odzq * onstep * orho; n[o] = fmaxf(nfloor, nk + (sn_up - sn) * odzq * DT * onstep); }
+      } else {
+        r0 = rk;
+      }
+      sr_up = sr; sn_up = sn; sr_k = sr;
+    }
+    if (r0 > KP_R1 * 10.f) ppt = ppt + sr_k * DT * onstep;
+  }
+}
+
+#ifndef K2_MINB
+#define K2_MINB 16
+#endif
+template <bool RATES>
+__global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
+  const int slot = blockIdx.x * 32 + threadIdx.x;
+  const int count = *a.work_count;
+  if (slot >= count) return;
+  const long col = a.work_list[slot];
+  const int nz = a.nz;
+  const long ld = a.ld, ncol = a.ncol;
+  const long cs = count;
+  const size_t ps = (size_t)nz * count;
+  const float DT = a.dt, odt = 1.f / DT;
+  const bool iiwarm = ck.iiwarm != 0;
+  const double n0_empty = g_n0_lo;
+  float* const sc0 = a.scratch + slot;
+  const unsigned char* const clsp = a.cls + col;
+  const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;     // one vector shared by all columns (KiD) or this column's own (WRF entry)
+  const long dzs = a.dz_col ? ld : 1;
+
+  // ================= sweep A: intercept minimum of S10 (M:2721-2731), fall speeds of levels without the species (M:3235,
+  // M:3267, M:3307, M:3333), snow above 0 C and graupel (M:3301, M:3328), sub-step counts and top levels (M:3242, M:3208)
+  int nstep_r = 0, nstep_i = 0, nstep_s = 0, nstep_g = 0, ksed_r = 1, ksed_i = 1, ksed_s = 1, ksed_g = 1;
+  {
+    double n0_min = (double)KP_GONV_MAX;
+    bool warm_b = false;
+    float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;     // speeds of the level above
+#pragma unroll 1
+    for (int k = nz - 1; k >= 0; --k) {
+      float* sc = sc0 + (size_t)k * cs;
+      const float dzq = dzp[k * dzs];
+      const bool handed = (clsp[(long)k * ncol] & CLS_BUSY) != 0;
+      if (handed) {
+        const float rr = sc[SC_RR * ps];
+        if (rr > R1) { v_r = sc[SC_VTR * ps]; v_nr = sc[SC_VTNR * ps]; }
+        if (!iiwarm) {
+          const float ri = sc[SC_RI * ps], rs = sc[SC_RS * ps], rg = sc[SC_RG * ps];
+          const float x1 = sc[SC_N0A * ps];
+          if (x1 < 0.f) warm_b = true;
+          const double N0_exp = (!warm_b && k > 0) ? (double)sc[SC_N0B_SLW * ps] : (double)fabsf(x1);
+          n0_min = fmin(N0_exp, n0_min);
+          if (ri > R1) { v_i = sc[SC_VTI * ps]; v_ni = sc[SC_VTNI * ps]; }
+          if (rs > R1) {
+            const float vts = sc[SC_VTS_RAW * ps], vts_boost = sc[SC_VTS_BOOST * ps], temp = sc[SC_TEMP * ps];
+            if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * ((v_r - vts * vts_boost) / (temp - T_0)));
+            else v_s = vts * vts_boost;
+            sc[SC_VTS * ps] = v_s;
+          }
+          if (rg > R1) {
+            const float rho = sc[SC_RHO * ps], s15 = sc[SC_S15 * ps];
+            const float rhof = sqrtf(ck.rho_not / rho);
+            double ilamg = 0., N0_g = 0.;
+            graupel_slope(n0_min, rg, ilamg, N0_g);
+            const float vtg = (float)((double)(rhof * KP_AV_G * ck.cgg[5] * ck.ogg3) * pow_d(ilamg, (double)KP_BV_G));
+            v_g = (s15 > 0.f) ? fmaxf(vtg, v_r) : vtg;         // temp > T_0 is what makes the S15 factor positive
+            sc[SC_VTG * ps] = v_g;
+          }
+        }
+      } else if (!iiwarm) {
+        if (a.f[F_T][(long)k * ld + col] >= 270.65f) warm_b = true;
+        n0_min = fmin(n0_empty, n0_min);
+      }
+      if (fmaxf(v_r, v_nr) > 1.E-3f) {
+        ksed_r = max(ksed_r, k + 1);
+        const float delta_tp = dzq / (fmaxf(v_r, v_nr));
+        nstep_r = max(nstep_r, (int)(DT / delta_tp + 1.f));
+      }
+      if (!iiwarm) {
+        if (v_i > 1.E-3f) { ksed_i = max(ksed_i, k + 1); const float d = dzq / v_i; nstep_i = max(nstep_i, (int)(DT / d + 1.f)); }
+        if (v_s > 1.E-3f) { ksed_s = max(ksed_s, k + 1); const float d = dzq / v_s; nstep_s = max(nstep_s, (int)(DT / d + 1.f)); }
+        if (v_g > 1.E-3f) { ksed_g = max(ksed_g, k + 1); const float d = dzq / v_g; nstep_g = max(nstep_g, (int)(DT / d + 1.f)); }
+      }
+    }
+    // U12: the reference leaves the sub-step count unbounded (M:3242); on non-physical input (dt*v/dz in the
+    // millions) that is a kernel that never ends, so it is capped where no real case comes near
+    nstep_r = min(nstep_r, KP_NSTEP_MAX); nstep_i = min(nstep_i, KP_NSTEP_MAX);
+    nstep_s = min(nstep_s, KP_NSTEP_MAX); nstep_g = min(nstep_g, KP_NSTEP_MAX);
+  }
+  const int kte = nz;
+  if (ksed_r == kte) ksed_r = kte - 1;
+  if (ksed_i == kte) ksed_i = kte - 1;
+  if (ksed_s == kte) ksed_s = kte - 1;
+  if (ksed_g == kte) ksed_g = kte - 1;
+  const float on_r = nstep_r > 0 ? 1.f / (float)nstep_r : 1.0f, on_i = nstep_i > 0 ? 1.f / (float)nstep_i : 1.0f;
+  const float on_s = nstep_s > 0 ? 1.f / (float)nstep_s : 1.0f, on_g = nstep_g > 0 ? 1.f / (float)nstep_g : 1.0f;
+  const int n_r = nint_f(1.f / on_r), n_i = nint_f(1.f / on_i), n_s = nint_f(1.f / on_s), n_g = nint_f(1.f / on_g);
+  const bool sedi = ck.l_sediment != 0;
+  const bool substeps = n_r > 1 || n_i > 1 || n_s > 1 || n_g > 1;
+
+  const float* __restrict__ Gp = a.p + col;
+  float* Gqv = a.f[F_QV] + col; float* Gqc = a.f[F_QC] + col; float* Gqi = a.f[F_QI] + col;
+  float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
+  float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
+
+  // the record of an idle cell: all rates zero, state unchanged, contents R1 / R2, speeds of the level above
+  auto idle_record = [&](int k, HandOff& h) {
+    const long o = (long)k * ld;
+    const float temp = Gt[o], pres = Gp[o];
+    const float qv = fmaxf(1.E-10f, Gqv[o]);
+    const float tempc = temp - 273.15f;
+    const float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+    const float lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+    h.tt = 0.f; h.qvt = 0.f; h.qct = 0.f; h.qit = 0.f; h.qrt = 0.f; h.qst = 0.f; h.qgt = 0.f; h.nit = 0.f; h.nrt = 0.f; h.nct = 0.f;
+    h.rr = R1; h.nr = R2; h.ri = R1; h.ni = R2; h.rs = R1; h.rg = R1;
+    h.rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+    h.s15 = 0.0f;
+    if (temp > T_0) h.s15 = ck.lfus * ocp;
+    else if (temp < KP_HGFR) h.s15 = -((KP_LSUB - lvap) * ocp);
+  };
+
+  float ppt_r = 0.f, ppt_i = 0.f, ppt_s = 0.f, ppt_g = 0.f;
+  if (substeps) {
+    // A column with sub-steps sediments in place in the hand-off planes, level by level: its idle cells get their
+    // records now, and every level the speeds that sweep A settled (M:3235 ...).
+    float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;
+#pragma unroll 1
+    for (int k = nz - 1; k >= 0; --k) {
+      float* sc = sc0 + (size_t)k * cs;
+      const bool handed = (clsp[(long)k * ncol] & CLS_BUSY) != 0;
+      if (handed) {
+        if (sc[SC_RR * ps] > R1) { v_r = sc[SC_VTR * ps]; v_nr = sc[SC_VTNR * ps]; }
+        if (!iiwarm) {
+          if (sc[SC_RI * ps] > R1) { v_i = sc[SC_VTI * ps]; v_ni = sc[SC_VTNI * ps]; }
+          if (sc[SC_RS * ps] > R1) v_s = sc[SC_VTS * ps];
+          if (sc[SC_RG * ps] > R1) v_g = sc[SC_VTG * ps];
+        }
+      } else {
+        HandOff h;
+        idle_record(k, h);
+#pragma unroll
+        for (int q = SC_TTEN; q <= SC_NCTEN; ++q) sc[q * ps] = 0.0f;
+        sc[SC_RR * ps] = R1; sc[SC_NR * ps] = R2; sc[SC_RI * ps] = R1; sc[SC_NI * ps] = R2; sc[SC_RS * ps] = R1; sc[SC_RG * ps] = R1;
+        sc[SC_RHO * ps] = h.rho; sc[SC_S15 * ps] = h.s15;
+      }
+      sc[SC_VTR * ps] = v_r; sc[SC_VTNR * ps] = v_nr; sc[SC_VTI * ps] = v_i; sc[SC_VTNI * ps] = v_ni;
+      sc[SC_VTS * ps] = v_s; sc[SC_VTG * ps] = v_g;
+    }
+    const float* rhoa = sc0 + SC_RHO * ps;
+    // all but the last sub-step (rain is never gated by l_sediment, U6; the cloud-water stub M:3414-3425 is a no-op, U2)
+    if (n_r > 1) sed_substeps(sc0 + SC_RR * ps, sc0 + SC_QRTEN * ps, sc0 + SC_VTR * ps, sc0 + SC_NR * ps, sc0 + SC_NRTEN * ps,
+                              sc0 + SC_VTNR * ps, rhoa, dzp, dzs, nz, cs, n_r - 1, ksed_r, on_r, DT, true, KP_R2, ppt_r);
+    if (n_i > 1) sed_substeps(sc0 + SC_RI * ps, sc0 + SC_QITEN * ps, sc0 + SC_VTI * ps, sc0 + SC_NI * ps, sc0 + SC_NITEN * ps,
+                              sc0 + SC_VTNI * ps, rhoa, dzp, dzs, nz, cs, n_i - 1, ksed_i, on_i, DT, sedi, KP_R2, ppt_i);
+    if (n_s > 1) sed_substeps(sc0 + SC_RS * ps, sc0 + SC_QSTEN * ps, sc0 + SC_VTS * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
+                              nz, cs, n_s - 1, ksed_s, on_s, DT, sedi, 0.f, ppt_s);
+    if (n_g > 1) sed_substeps(sc0 + SC_RG * ps, sc0 + SC_QGTEN * ps, sc0 + SC_VTG * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
+                              nz, cs, n_g - 1, ksed_g, on_g, DT, sedi, 0.f, ppt_g);
+  }
+
+  // ================= sweep B: last sub-step of every species + S15 + S16, top-down =========================================
+  SedParams sp;
+  sp.DT = DT; sp.odt = odt; sp.on_r = on_r; sp.on_i = on_i; sp.on_s = on_s; sp.on_g = on_g; sp.Nt_c = ck.Nt_c;
+  sp.top_r = ksed_r; sp.top_i = ksed_i; sp.top_s = ksed_s; sp.top_g = ksed_g; sp.sedi = sedi; sp.iiwarm = iiwarm;
+  SedCarry c;
+  c.sr_up = 0.f; c.snr_up = 0.f; c.si_up = 0.f; c.sni_up = 0.f; c.ss_up = 0.f; c.sg_up = 0.f;
+  c.ppt_r = ppt_r; c.ppt_i = ppt_i; c.ppt_s = ppt_s; c.ppt_g = ppt_g; c.lwp = 0.0; c.iwp = 0.0;
+  float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;       // speeds of the level above (no sub-steps)
+#pragma unroll 1
+  for (int k = nz - 1; k >= 0; --k) {
+    const long o = (long)k * ld;
+    const float* q = sc0 + (size_t)k * cs;
+    const bool busy = (clsp[(long)k * ncol] & CLS_BUSY) != 0;
+    const bool handed = substeps || busy;
+    HandOff h;
+    if (handed) {
+      h.tt = q[SC_TTEN * ps]; h.qvt = q[SC_QVTEN * ps]; h.qct = q[SC_QCTEN * ps]; h.qit = q[SC_QITEN * ps];
+      h.qrt = q[SC_QRTEN * ps]; h.qst = q[SC_QSTEN * ps]; h.qgt = q[SC_QGTEN * ps]; h.nit = q[SC_NITEN * ps];
+      h.nrt = q[SC_NRTEN * ps]; h.nct = q[SC_NCTEN * ps];
+      h.rho = q[SC_RHO * ps]; h.s15 = q[SC_S15 * ps];
+      h.rr = q[SC_RR * ps]; h.nr = q[SC_NR * ps]; h.ri = q[SC_RI * ps]; h.ni = q[SC_NI * ps]; h.rs = q[SC_RS * ps]; h.rg = q[SC_RG * ps];
+      if (substeps) {
+        v_r = q[SC_VTR * ps]; v_nr = q[SC_VTNR * ps]; v_i = q[SC_VTI * ps]; v_ni = q[SC_VTNI * ps];
+        v_s = q[SC_VTS * ps]; v_g = q[SC_VTG * ps];
+      } else {
+        if (h.rr > R1) { v_r = q[SC_VTR * ps]; v_nr = q[SC_VTNR * ps]; }
+        if (!iiwarm) {
+          if (h.ri > R1) { v_i = q[SC_VTI * ps]; v_ni = q[SC_VTNI * ps]; }
+          if (h.rs > R1) v_s = q[SC_VTS * ps];
+          if (h.rg > R1) v_g = q[SC_VTG * ps];
+        }
+      }
+    } else {
+      idle_record(k, h);
+    }
+    if (RATES && !busy) {                                 // an idle cell: every process rate is zero
+      float* rp = a.rates + o + col;
+      const long st = (long)nz * ld;
+      for (int r = 0; r < KIDMP_NRATES; ++r) rp[r * st] = 0.0f;
+    }
+    h.v_r = v_r; h.v_nr = v_nr; h.v_i = v_i; h.v_ni = v_ni; h.v_s = v_s; h.v_g = v_g;
+    finish_level(a, sp, c, h, k, nz, o + col, dzp[k * dzs], Gt[o], Gqv[o], Gqc[o], Gqi[o], Gqr[o], Gqs[o], Gqg[o], Gni[o], Gnr[o], Gp[o]);
+  }
+  // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
+  a.ppt[col] = c.ppt_r; a.ppt[ld + col] = c.ppt_i; a.ppt[2 * ld + col] = c.ppt_s; a.ppt[3 * ld + col] = c.ppt_g;
+  a.coldiag[col] = c.lwp; a.coldiag[ncol + col] = c.iwp;      // summed in column order by k_diag_columns
+}
+
+#undef R1
+#undef R2
+#undef EPSF
+#undef T_0
+#undef D0r
+#undef D0c
+#undef D0s
+#undef D0g
+
+}  // namespace kidmp

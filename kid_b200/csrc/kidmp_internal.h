@@ -101,35 +101,54 @@ struct KConst {
   const float* efsw;
 };
 
-// hand-off arrays written by the column-physics kernel and consumed by the sedimentation kernel
+// Hand-off between the cell kernels and the column-finish kernel: [SC_NX][nz][count] f32, `count` = cloudy columns of
+// the launch (slot-indexed: lane = slot, so every plane access of the column kernels is one 128-byte line per warp).
+// Written for BUSY cells only (a hydrometeor or supersaturation; every rate of an idle cell is exactly zero).
+//   SC_TTEN..SC_NCTEN  the ten tendencies after S12
+//   SC_RR..SC_RG       contents at tau+1 (M:2602-2656 and the in-place refreshes of S11 / S12)
+//   SC_VTR..SC_VTNI    the cell's own fall speeds (0 without the species: k_finish applies the rule of the level above)
+//   SC_VTS, SC_VTG     written by sweep A of k_finish (final snow / graupel speed of the level)
+//   SC_RHO, SC_S15     air density at tau+1; signed latent-heat factor of S15
+//   SC_N0A             in: running minimum of the graupel intercept of S4 (k_n0_sweep); out: S10's intercept without
+//                      supercooled rain, negated when the level's updated temperature is >= 270.65 K
+//   SC_N0B_SLW         S10's intercept with supercooled rain; SC_VTS_RAW / SC_VTS_BOOST / SC_TEMP for the snow speed rule
 enum { SC_TTEN = 0, SC_QVTEN, SC_QCTEN, SC_QITEN, SC_QRTEN, SC_QSTEN, SC_QGTEN, SC_NITEN, SC_NRTEN, SC_NCTEN,
        SC_RR, SC_NR, SC_RI, SC_NI, SC_RS, SC_RG, SC_VTR, SC_VTNR, SC_VTI, SC_VTNI, SC_VTS, SC_VTG, SC_RHO, SC_S15, SC_N,
-       // between the phases of the unit-parallel physics kernel only (kidmp_units.cuh)
        SC_N0A = SC_N, SC_N0B_SLW, SC_VTS_RAW, SC_VTS_BOOST, SC_TEMP, SC_NX };
+
+// Cell classes: every busy cell goes to the kernel specialised for the smallest species set that covers it
+// (kidmp_cells.cuh).  The class byte of a cell: bits 0-4 qc qi qr qs qg > R1 on input, bit 5 ice supersaturation,
+// bits 6-7 the kernel class; 0 = idle cell.
+enum { KC_WARM = 0, KC_ICE = 1, KC_MIXNR = 2, KC_FULL = 3, KC_N = 4 };
+enum { CLS_QC = 1, CLS_QI = 2, CLS_QR = 4, CLS_QS = 8, CLS_QG = 16, CLS_VAP = 32, CLS_BUSY = 63, CLS_KC_SHIFT = 6 };
+enum { LIST_TILE = 256 };          // columns per block of the cell-list kernels
 
 enum { DIAG_BLOCKS = 296 };
 
 struct StepArgs {
-  long ncol;
+  long ncol;                   // columns of this launch (one chunk of the domain)
+  long ld;                     // row stride of the caller's arrays (state, p, dz_col, rates: [nz][ld]; ppt: [4][ld])
   int nz;
   float dt;
-  float* f[KIDMP_NFIELDS];     // qv qc qi qr qs qg ni nr t, [nz][ncol]
-  const float* p;              // [nz][ncol]
+  float* f[KIDMP_NFIELDS];     // qv qc qi qr qs qg ni nr t, [nz][ld], pointing at the chunk's first column
+  const float* p;              // [nz][ld]
   const float* dz;             // [nz] layer depths shared by all columns (KiD, I:63) ...
-  const float* dz_col;         // ... or [nz][ncol] per column (WRF's dz(i,k,j), M:944); NULL when dz is used
-  float* ppt;                  // [4][ncol]
-  float* scratch;              // [SC_N][nz][ncol] hand-off, touched for cloudy columns only
-  int* colint;                 // [8][ncol] substep counts / top sedimenting level per species; [0] = -1: clear sky
+  const float* dz_col;         // ... or [nz][ld] per column (WRF's dz(i,k,j), M:944); NULL when dz is used
+  float* ppt;                  // [4][ld]
+  float* scratch;              // [SC_NX][nz][count] hand-off (see SC_*)
+  unsigned char* cls;          // [nz][ncol] class byte of every cell (0 = idle)
+  int* colflag;                // [ncol] -1 clear sky (the early RETURN of M:1540), else bit 0 = graupel somewhere in the column
   int* work_count;             // number of cloudy columns found by the classification kernel
-  int* work_list;              // their column indices, compacted in column order
+  int* work_list;              // their column indices, compacted in column order (slot -> column)
   unsigned* work_mask;         // [ngroups] ballot of the cloudy lanes of every 32-column group
   int* work_offset;            // [ngroups] exclusive prefix sum of the ballots' popcounts
-  float* rates;                // optional [36][nz][ncol]
+  unsigned* cell_list;         // [<= nz*ncol] busy cells, class after class, entry = k * count + slot
+  int* cell_count;             // [KC_N] busy cells of each class
+  int* cell_base;              // [list blocks][KC_N] first entry of a block's cells inside its class segment
+  float* rates;                // optional [36][nz][ld]
   double* coldiag;             // [2][ncol] liquid / ice water path of each cloudy column
   double* diag_partial;        // [DIAG_BLOCKS][KIDMP_NDIAG] block sums of k_diag_columns
-  int* redo_count;             // fused physics kernel: columns that need sedimentation sub-steps ...
-  int* redo_list;              // ... and are done again by the split kernels
-  int nsm;                     // SMs of the device: the physics kernel spreads its warps over whole waves of blocks
+  int nsm;                     // SMs of the device
 };
 
 // device tables (kidmp_tables.cuh fills them)

@@ -88,16 +88,3 @@ def test_cxx_host_twin_builds_and_fails_cleanly_without_a_gpu(tmp_path):
     np.zeros(7 * nx * nz + nz + 21 * nx * nz, np.float32).tofile(src)
     r = subprocess.run([exe, str(src), str(tmp_path / "out.bin"), str(nx), str(nz), "1.0", "0"], capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU path" in r.stderr
-
-
-def test_unit_kernel_cell_code_is_the_column_kernels(tmp_path):
-    """kid_b200/csrc/kidmp_cell_body.inc (the cell code of the unit-parallel physics kernel) is generated from the level body of
-    k_column_step by tools/gen_cell_body.py; the committed file must be what the generator makes of the current source."""
-    inc = os.path.join(ROOT, "kid_b200", "csrc", "kidmp_cell_body.inc")
-    before = open(inc).read()
-    try:
-        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_cell_body.py")], stdout=subprocess.DEVNULL)
-        assert open(inc).read() == before
-    finally:
-        if open(inc).read() != before:
-            open(inc, "w").write(before)

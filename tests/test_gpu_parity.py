@@ -583,27 +583,24 @@ def test_wrf_driver_entry(gpu_mixed, oracle_mixed):
         assert np.array_equal(st[k], a5[k].transpose(1, 0, 2).reshape(nk, nj * ni)), k
 
 
-# ---- sedimentation fused into the physics kernel, with the redo path for columns that need sub-steps ----------------
+# ---- the step is launched over chunks of columns: the chunking must not change a bit -------------------------------
 @pytest.mark.parametrize("dt,dz,warm,ncol,nz", [(10.0, 250.0, False, 20000, 60), (60.0, 100.0, False, 20000, 60),
                                                 (30.0, 120.0, False, 20000, 60), (20.0, 60.0, True, 20000, 60),
                                                 (10.0, 125.0, False, 77, 120), (5.0, 250.0, False, 1, 60),
                                                 (10.0, 250.0, False, 140001, 37)])
-def test_fused_and_split_steps_are_bit_identical(dt, dz, warm, ncol, nz):
-    """The physics-kernel variants give the same bits.  kidmp_set_option("units"): unit-parallel or column-walk kernel;
-    kidmp_set_option("fuse"): 0 = two kernels with a hand-off, 2 = fused + redo of the columns whose sub-step count
-    exceeds 1 (none at dt=10/dz=250, most rain columns at dt=60/dz=100), 1 = adaptive.  Same bits in every mode,
-    over several steps (the adaptive mode switches after the first step when many columns were redone)."""
+def test_chunked_steps_are_bit_identical(dt, dz, warm, ncol, nz):
+    """kidmp_set_option("chunk"): columns per launch of the step kernels (the work buffers are sized for one chunk).
+    Columns are independent, so the state after several steps is the same bit for bit for every chunk size; so are the
+    per-column precipitation amounts.  dt=60/dz=100 puts most rain columns on the sub-stepped sedimentation path."""
     import torch
     from kid_b200 import synth
     from kid_b200.kidmp import Thompson
     res = {}
-    # 0: column-walk kernel + sedimentation kernel; 2: column walk with fused sedimentation + redo; 1: the adaptive choice;
-    # "u": the unit-parallel physics kernel
-    for mode in (0, 2, 1, "u"):
+    for chunk in (1 << 20, 4096, 1000, 32):
+        if chunk == 32 and ncol > 20000:
+            continue
         th = Thompson(set_Nc=100.0, iiwarm=warm, l_sediment=True)
-        th.set_option("units", 1 if mode == "u" else 0)
-        if mode != "u":
-            th.set_option("fuse", mode)
+        th.set_option("chunk", chunk)
         kw = dict(col0=200000) if ncol >= 20000 else dict(coherent=False, cloudy_fraction=1.0 if ncol == 1 else 0.6)
         st, p, dzv = synth.make_domain(ncol, nz=nz, nx=1024, device="cuda", dz=dz, **kw)
         ppt = torch.zeros((4, ncol), dtype=torch.float32, device="cuda")
@@ -614,11 +611,13 @@ def test_fused_and_split_steps_are_bit_identical(dt, dz, warm, ncol, nz):
             th.sync()
             acc += ppt.double()
             torch.cuda.synchronize()
-        res[mode] = ({k: st[k].cpu().numpy() for k in FIELDS}, acc.cpu().numpy(), th.diag())
+        res[chunk] = ({k: st[k].cpu().numpy() for k in FIELDS}, acc.cpu().numpy(), th.diag())
         th.close()
-    for mode in (2, 1, "u"):
+    ref = res[1 << 20]
+    for chunk, r in res.items():
         for k in FIELDS:
-            assert np.array_equal(res[mode][0][k], res[0][0][k]), (mode, k)
-        assert np.array_equal(res[mode][1], res[0][1]), mode
-        assert np.array_equal(res[mode][2], res[0][2]), mode          # domain sums in column order: same bits too
-    assert res[0][2][6] > 0                                           # some columns were active
+            assert np.array_equal(r[0][k], ref[0][k]), (chunk, k)
+        assert np.array_equal(r[1], ref[1]), chunk
+        assert r[2][6] == ref[2][6] and r[2][7] == ref[2][7]               # active columns, columns
+        assert np.allclose(r[2][:6], ref[2][:6], rtol=1e-12)               # f64 sums: the order of the partial sums changes
+    assert ref[2][6] > 0                                                   # some columns were active

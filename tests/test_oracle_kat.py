@@ -317,3 +317,64 @@ def test_decade_index_shortcut_of_the_kernels_equals_the_reference_search():
             if kernel_index(x, n2, ntb) != L.kor_decade_index(float(x), n2, ntb):
                 bad += 1
     assert bad == 0, bad
+
+
+def _horner_f32(c, x):
+    """The Horner form of RSLF / RSIF (M:4656-4717) in f32, operation by operation like the kernels (no FMA)."""
+    acc = np.full_like(x, np.float32(c[8]))
+    for q in range(7, -1, -1):
+        acc = (np.float32(c[q]) + x * acc).astype(np.float32)
+    return acc
+
+
+def test_saturation_over_ice_not_above_liquid():
+    """k_classify marks a cell busy when it holds a hydrometeor or ssati > 0; the cell code would also run rates for
+    ssatw > eps (M:2780).  At or below 0 C that adds nothing because e_s(ice) <= e_s(liquid) for the two polynomials over
+    their whole argument range [-80, -0.01] C - checked here for EVERY f32 temperature in that range - and
+    0.622 e / (p - e) and q / qvs - 1 are monotone in round-to-nearest arithmetic."""
+    CL = [.611583699E03, .444606896E02, .143177157E01, .264224321E-1, .299291081E-3, .203154182E-5, .702620698E-8,
+          .379534310E-11, -.321582393E-13]
+    CI = [.609868993E03, .499320233E02, .184672631E01, .402737184E-1, .565392987E-3, .521693933E-5, .307839583E-7,
+          .105785160E-9, .161444444E-12]
+    lo, hi = np.float32(193.0).view(np.uint32), np.float32(273.15).view(np.uint32)
+    worst = np.inf
+    for b0 in range(int(lo), int(hi) + 1, 1 << 20):
+        t = np.arange(b0, min(b0 + (1 << 20), int(hi) + 1), dtype=np.uint32).view(np.float32)
+        x = np.maximum(np.float32(-80.0), (t - np.float32(273.16)).astype(np.float32))
+        esl, esi = _horner_f32(CL, x), _horner_f32(CI, x)
+        worst = min(worst, float((esl - esi).min()))
+        assert (esi <= esl).all()
+    assert worst >= 0.0
+    # spot check of the helpers against the oracle's RSLF / RSIF
+    for tt in (200.0, 233.15, 260.0, 273.15):
+        x = np.maximum(np.float32(-80.0), np.float32(tt) - np.float32(273.16))
+        e = float(_horner_f32(CL, np.array([x], np.float32))[0])
+        pp = np.float32(50000.0)
+        e = min(np.float32(e), pp * np.float32(0.15))
+        assert np.float32(np.float32(0.622) * e / (pp - e)) == np.float32(orc.rslf(50000.0, tt))
+
+
+def test_cell_class_rule_covers_every_species_set():
+    """The rule of cell_kernel_class (kid_b200/csrc/kidmp_column.cuh): every (species set, cold, iiwarm) combination goes to a
+    class whose kernel may hold those species (CellTraits of kidmp_cells.cuh)."""
+    QC, QI, QR, QS, QG = 1, 2, 4, 8, 16
+    allowed = {"WARM": QC | QR, "ICE": QI | QS, "MIXNR": QC | QI | QS | QG, "FULL": 31}
+
+    def rule(sp, cold, iiwarm):
+        ice = bool(sp & (QI | QS | QG))
+        if iiwarm:
+            return "FULL" if ice else "WARM"
+        if not cold and not ice:
+            return "WARM"
+        if cold and not (sp & (QC | QR | QG)):
+            return "ICE"
+        return "FULL" if sp & QR else "MIXNR"
+    for sp in range(32):
+        for cold in (False, True):
+            for iiwarm in (False, True):
+                kc = rule(sp, cold, iiwarm)
+                assert sp & ~allowed[kc] == 0, (sp, cold, iiwarm, kc)
+                if kc == "WARM" and not iiwarm:
+                    assert not cold          # no freezing or nucleation can start in a cell of this class (M:2025)
+                if kc == "ICE":
+                    assert cold and not iiwarm
