@@ -38,22 +38,24 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False, extra=()):
-    """Compile if any source is newer than the library.  Returns the library path."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra=(), out=None):
+    """Compile if any source is newer than the library.  Returns the library path.
+    `extra` / `out`: tuning builds with other -D flags into another file (tools/variants.py; loaded through KIDMP_LIB)."""
+    if out is None and not force and not needs_build():
         return LIB
-    tmp = "%s.tmp%d" % (LIB, os.getpid())          # several ranks may build at once: each writes its own file, the rename is atomic
+    out = out or LIB
+    tmp = "%s.tmp%d" % (out, os.getpid())          # several ranks may build at once: each writes its own file, the rename is atomic
     cmd = [nvcc_path(), *flags(extra), "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
     try:
         subprocess.check_call(cmd)
-        os.replace(tmp, LIB)
+        os.replace(tmp, out)
     finally:
         if os.path.exists(tmp):
             os.remove(tmp)
-    return LIB
+    return out
 
 
 HOST_DIR = os.path.join(HERE, "host")

@@ -50,6 +50,7 @@ struct kidmp_handle {
   unsigned* d_cells = nullptr;                            // [nz*cols] busy cells, class after class
   int* d_cellmeta = nullptr;                              // [8 | blocks*KC_N] class totals, per-block bases
   double* d_coldiag = nullptr;                            // [2][cols] per-column water paths for the ordered domain sums
+  int* d_colwork = nullptr;                               // [8 busy words | 8 colint | sub list | 4 pptsub][cols] of the column kernels
   long work_cols = 0; int work_nz = 0;
   long chunk_cols = 1048576;                              // columns per launch of the step kernels ("chunk" option, KIDMP_CHUNK)
   cudaEvent_t ev_done = nullptr;                          // end of the last step, on whatever stream it ran
@@ -233,10 +234,10 @@ int ensure_work(kidmp_handle* h, long cols, int nz) {
   const long C = cols > h->work_cols ? cols : h->work_cols;
   const int Z = nz > h->work_nz ? nz : h->work_nz;
   CK(h, cudaDeviceSynchronize());                    // nothing may still be reading the buffers that go away
-  void* old[] = {h->d_scratch, h->d_cls, h->d_colflag, h->d_work, h->d_cells, h->d_cellmeta, h->d_coldiag};
+  void* old[] = {h->d_scratch, h->d_cls, h->d_colflag, h->d_work, h->d_cells, h->d_cellmeta, h->d_coldiag, h->d_colwork};
   for (void* q : old) if (q) cudaFree(q);
   h->d_scratch = nullptr; h->d_cls = nullptr; h->d_colflag = nullptr; h->d_work = nullptr; h->d_cells = nullptr;
-  h->d_cellmeta = nullptr; h->d_coldiag = nullptr; h->work_cols = 0; h->work_nz = 0;
+  h->d_cellmeta = nullptr; h->d_coldiag = nullptr; h->d_colwork = nullptr; h->work_cols = 0; h->work_nz = 0;
   const size_t cells = (size_t)C * Z;
   const long ngroups = (C + 31) / 32, lblocks = (C + LIST_TILE - 1) / LIST_TILE;
   CK(h, cudaMalloc((void**)&h->d_scratch, cells * SC_NX * 4));
@@ -246,29 +247,56 @@ int ensure_work(kidmp_handle* h, long cols, int nz) {
   CK(h, cudaMalloc((void**)&h->d_cells, cells * 4));
   CK(h, cudaMalloc((void**)&h->d_cellmeta, (size_t)(8 + lblocks * KC_N) * 4));
   CK(h, cudaMalloc((void**)&h->d_coldiag, (size_t)C * 2 * 8));
+  CK(h, cudaMalloc((void**)&h->d_colwork, (size_t)C * 21 * 4));
   h->work_cols = C; h->work_nz = Z;
   return 0;
 }
 
-// launch shape of the cell kernels: threads per block, blocks per SM (kidmp_cells.cuh; measured in profiles/r02_*)
+// launch shape of the cell kernels: threads per block, blocks per SM, stage barriers of the lockstep blocks (bit i =
+// LOCKBAR(i) of kidmp_cells.cuh; 0 = warps run free).  Measured alternatives: profiles/r02_cells_variants.md
 #ifndef KC_WARM_T
-#define KC_WARM_T 128
-#define KC_WARM_B 6
-#define KC_ICE_T 128
+#define KC_WARM_T 256
+#endif
+#ifndef KC_WARM_B
+#define KC_WARM_B 4
+#endif
+#ifndef KC_WARM_BARS
+#define KC_WARM_BARS 11
+#endif
+#ifndef KC_ICE_T
+#define KC_ICE_T 256
+#endif
+#ifndef KC_ICE_B
 #define KC_ICE_B 4
-#define KC_MIXNR_T 128
-#define KC_MIXNR_B 4
-#define KC_FULL_T 128
-#define KC_FULL_B 4
-#define KC_BARS 0
+#endif
+#ifndef KC_ICE_BARS
+#define KC_ICE_BARS 11
+#endif
+#ifndef KC_MIXNR_T
+#define KC_MIXNR_T 256
+#endif
+#ifndef KC_MIXNR_B
+#define KC_MIXNR_B 3
+#endif
+#ifndef KC_MIXNR_BARS
+#define KC_MIXNR_BARS 11
+#endif
+#ifndef KC_FULL_T
+#define KC_FULL_T 256
+#endif
+#ifndef KC_FULL_B
+#define KC_FULL_B 3
+#endif
+#ifndef KC_FULL_BARS
+#define KC_FULL_BARS 11
 #endif
 
 template <bool RATES>
 void launch_cells(const StepArgs& a, int nsm, cudaStream_t s) {
-  k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, 0, RATES><<<nsm * KC_WARM_B, KC_WARM_T, 0, s>>>(a);
-  k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, 0, RATES><<<nsm * KC_ICE_B, KC_ICE_T, 0, s>>>(a);
-  k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_BARS, RATES><<<nsm * KC_MIXNR_B, KC_MIXNR_T, 0, s>>>(a);
-  k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_BARS, RATES><<<nsm * KC_FULL_B, KC_FULL_T, 0, s>>>(a);
+  k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, KC_WARM_BARS, RATES><<<nsm * KC_WARM_B, KC_WARM_T, 0, s>>>(a);
+  k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, KC_ICE_BARS, RATES><<<nsm * KC_ICE_B, KC_ICE_T, 0, s>>>(a);
+  k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES><<<nsm * KC_MIXNR_B, KC_MIXNR_T, 0, s>>>(a);
+  k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES><<<nsm * KC_FULL_B, KC_FULL_T, 0, s>>>(a);
 }
 
 // One step over [ncol] columns whose arrays have row stride ld, in launches of at most chunk_cols columns (the work
@@ -295,7 +323,9 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     a.scratch = h->d_scratch; a.cls = h->d_cls; a.colflag = h->d_colflag;
     a.work_count = h->d_work; a.work_list = h->d_work + 8;
     a.work_mask = (unsigned*)(h->d_work + 8 + a.ncol); a.work_offset = h->d_work + 8 + a.ncol + ngroups;
-    a.cell_list = h->d_cells; a.cell_count = h->d_cellmeta; a.cell_base = h->d_cellmeta + 8;
+    a.cell_list = h->d_cells; a.cell_count = h->d_cellmeta; a.sub_count = h->d_cellmeta + 4; a.cell_base = h->d_cellmeta + 8;
+    a.busy = (unsigned*)h->d_colwork; a.colint = h->d_colwork + 8 * h->work_cols; a.sub_list = h->d_colwork + 16 * h->work_cols;
+    a.pptsub = (float*)(h->d_colwork + 17 * h->work_cols);
     a.coldiag = h->d_coldiag; a.diag_partial = h->d_partial; a.nsm = h->nsm;
     CK(h, cudaMemsetAsync(a.cell_count, 0, 8 * 4, s));
     k_classify<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
@@ -306,11 +336,13 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     k_cell_fill<<<(unsigned)lblocks, LIST_TILE, lsmem, s>>>(a);
     // the number of cloudy columns is only known on the device: grids for the worst case, surplus blocks leave at once
     if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
-    if (a.rates) { launch_cells<true>(a, h->nsm, s); k_finish<true><<<(unsigned)ngroups, 32, 0, s>>>(a); }
-    else { launch_cells<false>(a, h->nsm, s); k_finish<false><<<(unsigned)ngroups, 32, 0, s>>>(a); }
+    if (a.rates) launch_cells<true>(a, h->nsm, s); else launch_cells<false>(a, h->nsm, s);
+    k_carries<<<(unsigned)((a.ncol + 63) / 64), 64, 0, s>>>(a);
+    k_substeps<<<(unsigned)ngroups, 32, 0, s>>>(a);
+    if (a.rates) k_finish<true><<<(unsigned)ngroups, 32, 0, s>>>(a); else k_finish<false><<<(unsigned)ngroups, 32, 0, s>>>(a);
     k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
     k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
-    h->launches += h->kc.iiwarm ? 12 : 13;
+    h->launches += h->kc.iiwarm ? 14 : 15;
   }
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(h->ev_done, s));
@@ -455,6 +487,7 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_cells) cudaFree(h->d_cells);
   if (h->d_cellmeta) cudaFree(h->d_cellmeta);
   if (h->d_coldiag) cudaFree(h->d_coldiag);
+  if (h->d_colwork) cudaFree(h->d_colwork);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->d_pipe) cudaFree(h->d_pipe);
   if (h->d_pipe_dz) cudaFree(h->d_pipe_dz);

@@ -124,10 +124,14 @@ __global__ void __launch_bounds__(LIST_TILE) k_cell_fill(StepArgs a) {
   const unsigned gmask = in_range ? a.work_mask[col >> 5] : 0u;
   const unsigned slot = (unsigned)a.work_offset[in_range ? (col >> 5) : 0] + __popc(gmask & ((1u << lane) - 1u));
   const unsigned char* cp = a.cls + col;
+  const bool cloudy = in_range && ((gmask >> lane) & 1u);
+  unsigned bword = 0;                                     // busy bits of 32 levels of my column, for the column kernels
   for (int k = nz - 1; k >= 0; --k) {
     const unsigned c = in_range ? cp[(long)k * a.ncol] : 0u;
     const bool busy = (c & CLS_BUSY) != 0u;
     const unsigned kc = c >> CLS_KC_SHIFT;
+    if (busy) bword |= 1u << (k & 31);
+    if ((k & 31) == 0) { if (cloudy) a.busy[(size_t)(k >> 5) * count + slot] = bword; bword = 0; }
     int before = 0, level_total = 0;                      // cells of my class at this level in the warps before mine / in all warps
     if (busy) {
       for (int w = 0; w < LIST_TILE / 32; ++w) {
@@ -1126,6 +1130,182 @@ __device__ __forceinline__ void sed_substeps(float* __restrict__ r, float* __res
   }
 }
 
+// busy bit of level k from the words loaded so far (words of 32 levels, [nwords][count])
+#define BUSY_WORD(w) a.busy[(size_t)(w) * count + slot]
+
+// ---- K2a: what runs down the column after the cell kernels: the intercept minimum of S10 (M:2721-2731), the fall speed of a
+// level without the species (M:3235, M:3267, M:3307, M:3333), snow above 0 C and graupel (they need the rain speed after
+// that rule, M:3301, M:3328), the sub-step counts and top sedimenting levels (M:3242, M:3208).  One thread per cloudy
+// column; all the values of a busy cell are loaded in one batch (one memory round trip per level).  Leaves colint
+// [8][count] and the list of the columns that need sedimentation sub-steps.
+__global__ void __launch_bounds__(64, 16) k_carries(StepArgs a) {
+  const int slot = blockIdx.x * 64 + threadIdx.x;
+  const int count = *a.work_count;
+  if (slot >= count) return;
+  const long col = a.work_list[slot];
+  const int nz = a.nz;
+  const long ld = a.ld;
+  const long cs = count;
+  const size_t ps = (size_t)nz * count;
+  const float DT = a.dt;
+  const bool iiwarm = ck.iiwarm != 0;
+  const double n0_empty = g_n0_lo;
+  float* const sc0 = a.scratch + slot;
+  const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;     // one vector shared by all columns (KiD) or this column's own (WRF entry)
+  const long dzs = a.dz_col ? ld : 1;
+  int nstep_r = 0, nstep_i = 0, nstep_s = 0, nstep_g = 0, ksed_r = 1, ksed_i = 1, ksed_s = 1, ksed_g = 1;
+  double n0_min = (double)KP_GONV_MAX;
+  bool warm_b = false;
+  float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_s = 0.f, v_g = 0.f;     // speeds of the level above (the ice number speed sets no count, M:3267)
+  unsigned bw = 0;
+#pragma unroll 1
+  for (int k = nz - 1; k >= 0; --k) {
+    if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
+    float* sc = sc0 + (size_t)k * cs;
+    const float dzq = dzp[k * dzs];
+    if ((bw >> (k & 31)) & 1u) {
+      const float rr = sc[SC_RR * ps], o_vr = sc[SC_VTR * ps], o_vnr = sc[SC_VTNR * ps];
+      if (!iiwarm) {
+        const float ri = sc[SC_RI * ps], rs = sc[SC_RS * ps], rg = sc[SC_RG * ps];
+        const float x1 = sc[SC_N0A * ps], x2 = sc[SC_N0B_SLW * ps];
+        const float o_vi = sc[SC_VTI * ps];
+        const float vts = sc[SC_VTS_RAW * ps], vts_boost = sc[SC_VTS_BOOST * ps], temp = sc[SC_TEMP * ps];
+        const float rho = sc[SC_RHO * ps], s15 = sc[SC_S15 * ps];
+        if (rr > R1) { v_r = o_vr; v_nr = o_vnr; }
+        if (x1 < 0.f) warm_b = true;
+        const double N0_exp = (!warm_b && k > 0) ? (double)x2 : (double)fabsf(x1);
+        n0_min = fmin(N0_exp, n0_min);
+        if (ri > R1) v_i = o_vi;
+        if (rs > R1) {
+          if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * ((v_r - vts * vts_boost) / (temp - T_0)));
+          else v_s = vts * vts_boost;
+          sc[SC_VTS * ps] = v_s;
+        }
+        if (rg > R1) {
+          const float rhof = sqrtf(ck.rho_not / rho);
+          double ilamg = 0., N0_g = 0.;
+          graupel_slope(n0_min, rg, ilamg, N0_g);
+          const float vtg = (float)((double)(rhof * KP_AV_G * ck.cgg[5] * ck.ogg3) * pow_d(ilamg, (double)KP_BV_G));
+          v_g = (s15 > 0.f) ? fmaxf(vtg, v_r) : vtg;         // temp > T_0 is what makes the S15 factor positive
+          sc[SC_VTG * ps] = v_g;
+        }
+      } else if (rr > R1) { v_r = o_vr; v_nr = o_vnr; }
+    } else if (!iiwarm) {
+      if (!warm_b && a.f[F_T][(long)k * ld + col] >= 270.65f) warm_b = true;      // an idle cell keeps its temperature
+      n0_min = fmin(n0_empty, n0_min);
+    }
+    if (fmaxf(v_r, v_nr) > 1.E-3f) {
+      ksed_r = max(ksed_r, k + 1);
+      const float delta_tp = dzq / (fmaxf(v_r, v_nr));
+      nstep_r = max(nstep_r, (int)(DT / delta_tp + 1.f));
+    }
+    if (!iiwarm) {
+      if (v_i > 1.E-3f) { ksed_i = max(ksed_i, k + 1); const float d = dzq / v_i; nstep_i = max(nstep_i, (int)(DT / d + 1.f)); }
+      if (v_s > 1.E-3f) { ksed_s = max(ksed_s, k + 1); const float d = dzq / v_s; nstep_s = max(nstep_s, (int)(DT / d + 1.f)); }
+      if (v_g > 1.E-3f) { ksed_g = max(ksed_g, k + 1); const float d = dzq / v_g; nstep_g = max(nstep_g, (int)(DT / d + 1.f)); }
+    }
+  }
+  // U12: the reference leaves the sub-step count unbounded (M:3242); on non-physical input (dt*v/dz in the
+  // millions) that is a kernel that never ends, so it is capped where no real case comes near
+  nstep_r = min(nstep_r, KP_NSTEP_MAX); nstep_i = min(nstep_i, KP_NSTEP_MAX);
+  nstep_s = min(nstep_s, KP_NSTEP_MAX); nstep_g = min(nstep_g, KP_NSTEP_MAX);
+  int* ci = a.colint + slot;
+  ci[0] = nstep_r; ci[cs] = nstep_i; ci[2 * cs] = nstep_s; ci[3 * cs] = nstep_g;
+  ci[4 * cs] = ksed_r; ci[5 * cs] = ksed_i; ci[6 * cs] = ksed_s; ci[7 * cs] = ksed_g;
+  if (max(max(nstep_r, nstep_i), max(nstep_s, nstep_g)) > 1) a.sub_list[atomicAdd(a.sub_count, 1)] = slot;
+}
+
+// per-column sedimentation parameters out of colint (M:3208, M:3242, M:3365-3578)
+struct SedCounts { int n_r, n_i, n_s, n_g, ksed_r, ksed_i, ksed_s, ksed_g; float on_r, on_i, on_s, on_g; };
+__device__ __forceinline__ SedCounts sed_counts(const int* ci, long cs, int nz) {
+  SedCounts s;
+  const int nstep_r = ci[0], nstep_i = ci[cs], nstep_s = ci[2 * cs], nstep_g = ci[3 * cs];
+  s.ksed_r = ci[4 * cs]; s.ksed_i = ci[5 * cs]; s.ksed_s = ci[6 * cs]; s.ksed_g = ci[7 * cs];
+  const int kte = nz;
+  if (s.ksed_r == kte) s.ksed_r = kte - 1;
+  if (s.ksed_i == kte) s.ksed_i = kte - 1;
+  if (s.ksed_s == kte) s.ksed_s = kte - 1;
+  if (s.ksed_g == kte) s.ksed_g = kte - 1;
+  s.on_r = nstep_r > 0 ? 1.f / (float)nstep_r : 1.0f; s.on_i = nstep_i > 0 ? 1.f / (float)nstep_i : 1.0f;
+  s.on_s = nstep_s > 0 ? 1.f / (float)nstep_s : 1.0f; s.on_g = nstep_g > 0 ? 1.f / (float)nstep_g : 1.0f;
+  s.n_r = nint_f(1.f / s.on_r); s.n_i = nint_f(1.f / s.on_i); s.n_s = nint_f(1.f / s.on_s); s.n_g = nint_f(1.f / s.on_g);
+  return s;
+}
+
+// the record of an idle cell: all rates zero, state unchanged, contents R1 / R2 (speeds: those of the level above)
+__device__ __forceinline__ void idle_record(float temp, float pres, float qv1d, float& rho, float& s15) {
+  const float qv = fmaxf(1.E-10f, qv1d);
+  const float tempc = temp - 273.15f;
+  const float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
+  const float lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
+  rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
+  s15 = 0.0f;
+  if (temp > T_0) s15 = ck.lfus * ocp;
+  else if (temp < KP_HGFR) s15 = -((KP_LSUB - lvap) * ocp);
+}
+
+// ---- K2b: the columns that need sedimentation sub-steps (a compacted list: full warps).  Such a column sediments in place in
+// the hand-off planes, level by level: its idle cells get their records, every level the speeds that k_carries settled, and
+// all but the last sub-step of each species run here (M:3365-3578).  The precipitation of those sub-steps goes to pptsub.
+__global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  if (i >= *a.sub_count) return;
+  const int slot = a.sub_list[i];
+  const int count = *a.work_count;
+  const long col = a.work_list[slot];
+  const int nz = a.nz;
+  const long ld = a.ld;
+  const long cs = count;
+  const size_t ps = (size_t)nz * count;
+  const float DT = a.dt;
+  const bool iiwarm = ck.iiwarm != 0;
+  float* const sc0 = a.scratch + slot;
+  const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;
+  const long dzs = a.dz_col ? ld : 1;
+  const SedCounts s = sed_counts(a.colint + slot, cs, nz);
+  float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;
+  unsigned bw = 0;
+#pragma unroll 1
+  for (int k = nz - 1; k >= 0; --k) {
+    if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
+    float* sc = sc0 + (size_t)k * cs;
+    if ((bw >> (k & 31)) & 1u) {
+      if (sc[SC_RR * ps] > R1) { v_r = sc[SC_VTR * ps]; v_nr = sc[SC_VTNR * ps]; }
+      if (!iiwarm) {
+        if (sc[SC_RI * ps] > R1) { v_i = sc[SC_VTI * ps]; v_ni = sc[SC_VTNI * ps]; }
+        if (sc[SC_RS * ps] > R1) v_s = sc[SC_VTS * ps];
+        if (sc[SC_RG * ps] > R1) v_g = sc[SC_VTG * ps];
+      }
+    } else {
+      const long o = (long)k * ld + col;
+      float rho, s15;
+      idle_record(a.f[F_T][o], a.p[o], a.f[F_QV][o], rho, s15);
+#pragma unroll
+      for (int q = SC_TTEN; q <= SC_NCTEN; ++q) sc[q * ps] = 0.0f;
+      sc[SC_RR * ps] = R1; sc[SC_NR * ps] = R2; sc[SC_RI * ps] = R1; sc[SC_NI * ps] = R2; sc[SC_RS * ps] = R1; sc[SC_RG * ps] = R1;
+      sc[SC_RHO * ps] = rho; sc[SC_S15 * ps] = s15;
+    }
+    sc[SC_VTR * ps] = v_r; sc[SC_VTNR * ps] = v_nr; sc[SC_VTI * ps] = v_i; sc[SC_VTNI * ps] = v_ni;
+    sc[SC_VTS * ps] = v_s; sc[SC_VTG * ps] = v_g;
+  }
+  const float* rhoa = sc0 + SC_RHO * ps;
+  const bool sedi = ck.l_sediment != 0;
+  float ppt_r = 0.f, ppt_i = 0.f, ppt_s = 0.f, ppt_g = 0.f;
+  // all but the last sub-step (rain is never gated by l_sediment, U6; the cloud-water stub M:3414-3425 is a no-op, U2)
+  if (s.n_r > 1) sed_substeps(sc0 + SC_RR * ps, sc0 + SC_QRTEN * ps, sc0 + SC_VTR * ps, sc0 + SC_NR * ps, sc0 + SC_NRTEN * ps,
+                              sc0 + SC_VTNR * ps, rhoa, dzp, dzs, nz, cs, s.n_r - 1, s.ksed_r, s.on_r, DT, true, KP_R2, ppt_r);
+  if (s.n_i > 1) sed_substeps(sc0 + SC_RI * ps, sc0 + SC_QITEN * ps, sc0 + SC_VTI * ps, sc0 + SC_NI * ps, sc0 + SC_NITEN * ps,
+                              sc0 + SC_VTNI * ps, rhoa, dzp, dzs, nz, cs, s.n_i - 1, s.ksed_i, s.on_i, DT, sedi, KP_R2, ppt_i);
+  if (s.n_s > 1) sed_substeps(sc0 + SC_RS * ps, sc0 + SC_QSTEN * ps, sc0 + SC_VTS * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
+                              nz, cs, s.n_s - 1, s.ksed_s, s.on_s, DT, sedi, 0.f, ppt_s);
+  if (s.n_g > 1) sed_substeps(sc0 + SC_RG * ps, sc0 + SC_QGTEN * ps, sc0 + SC_VTG * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
+                              nz, cs, s.n_g - 1, s.ksed_g, s.on_g, DT, sedi, 0.f, ppt_g);
+  float* pp = a.pptsub + slot;
+  pp[0] = ppt_r; pp[cs] = ppt_i; pp[2 * cs] = ppt_s; pp[3 * cs] = ppt_g;
+}
+
+// ---- K2c: the last (or only) sub-step of every species + S15 instant melt / freeze (M:3584-3606) + S16 (M:3623-3686), one
+// top-down sweep per cloudy column, one warp per block.  The ten inputs and the hand-off of a level are loaded in one batch.
 #ifndef K2_MINB
 #define K2_MINB 16
 #endif
@@ -1141,155 +1321,32 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
   const size_t ps = (size_t)nz * count;
   const float DT = a.dt, odt = 1.f / DT;
   const bool iiwarm = ck.iiwarm != 0;
-  const double n0_empty = g_n0_lo;
-  float* const sc0 = a.scratch + slot;
-  const unsigned char* const clsp = a.cls + col;
-  const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;     // one vector shared by all columns (KiD) or this column's own (WRF entry)
+  const float* const sc0 = a.scratch + slot;
+  const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;
   const long dzs = a.dz_col ? ld : 1;
-
-  // ================= sweep A: intercept minimum of S10 (M:2721-2731), fall speeds of levels without the species (M:3235,
-  // M:3267, M:3307, M:3333), snow above 0 C and graupel (M:3301, M:3328), sub-step counts and top levels (M:3242, M:3208)
-  int nstep_r = 0, nstep_i = 0, nstep_s = 0, nstep_g = 0, ksed_r = 1, ksed_i = 1, ksed_s = 1, ksed_g = 1;
-  {
-    double n0_min = (double)KP_GONV_MAX;
-    bool warm_b = false;
-    float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;     // speeds of the level above
-#pragma unroll 1
-    for (int k = nz - 1; k >= 0; --k) {
-      float* sc = sc0 + (size_t)k * cs;
-      const float dzq = dzp[k * dzs];
-      const bool handed = (clsp[(long)k * ncol] & CLS_BUSY) != 0;
-      if (handed) {
-        const float rr = sc[SC_RR * ps];
-        if (rr > R1) { v_r = sc[SC_VTR * ps]; v_nr = sc[SC_VTNR * ps]; }
-        if (!iiwarm) {
-          const float ri = sc[SC_RI * ps], rs = sc[SC_RS * ps], rg = sc[SC_RG * ps];
-          const float x1 = sc[SC_N0A * ps];
-          if (x1 < 0.f) warm_b = true;
-          const double N0_exp = (!warm_b && k > 0) ? (double)sc[SC_N0B_SLW * ps] : (double)fabsf(x1);
-          n0_min = fmin(N0_exp, n0_min);
-          if (ri > R1) { v_i = sc[SC_VTI * ps]; v_ni = sc[SC_VTNI * ps]; }
-          if (rs > R1) {
-            const float vts = sc[SC_VTS_RAW * ps], vts_boost = sc[SC_VTS_BOOST * ps], temp = sc[SC_TEMP * ps];
-            if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * ((v_r - vts * vts_boost) / (temp - T_0)));
-            else v_s = vts * vts_boost;
-            sc[SC_VTS * ps] = v_s;
-          }
-          if (rg > R1) {
-            const float rho = sc[SC_RHO * ps], s15 = sc[SC_S15 * ps];
-            const float rhof = sqrtf(ck.rho_not / rho);
-            double ilamg = 0., N0_g = 0.;
-            graupel_slope(n0_min, rg, ilamg, N0_g);
-            const float vtg = (float)((double)(rhof * KP_AV_G * ck.cgg[5] * ck.ogg3) * pow_d(ilamg, (double)KP_BV_G));
-            v_g = (s15 > 0.f) ? fmaxf(vtg, v_r) : vtg;         // temp > T_0 is what makes the S15 factor positive
-            sc[SC_VTG * ps] = v_g;
-          }
-        }
-      } else if (!iiwarm) {
-        if (a.f[F_T][(long)k * ld + col] >= 270.65f) warm_b = true;
-        n0_min = fmin(n0_empty, n0_min);
-      }
-      if (fmaxf(v_r, v_nr) > 1.E-3f) {
-        ksed_r = max(ksed_r, k + 1);
-        const float delta_tp = dzq / (fmaxf(v_r, v_nr));
-        nstep_r = max(nstep_r, (int)(DT / delta_tp + 1.f));
-      }
-      if (!iiwarm) {
-        if (v_i > 1.E-3f) { ksed_i = max(ksed_i, k + 1); const float d = dzq / v_i; nstep_i = max(nstep_i, (int)(DT / d + 1.f)); }
-        if (v_s > 1.E-3f) { ksed_s = max(ksed_s, k + 1); const float d = dzq / v_s; nstep_s = max(nstep_s, (int)(DT / d + 1.f)); }
-        if (v_g > 1.E-3f) { ksed_g = max(ksed_g, k + 1); const float d = dzq / v_g; nstep_g = max(nstep_g, (int)(DT / d + 1.f)); }
-      }
-    }
-    // U12: the reference leaves the sub-step count unbounded (M:3242); on non-physical input (dt*v/dz in the
-    // millions) that is a kernel that never ends, so it is capped where no real case comes near
-    nstep_r = min(nstep_r, KP_NSTEP_MAX); nstep_i = min(nstep_i, KP_NSTEP_MAX);
-    nstep_s = min(nstep_s, KP_NSTEP_MAX); nstep_g = min(nstep_g, KP_NSTEP_MAX);
-  }
-  const int kte = nz;
-  if (ksed_r == kte) ksed_r = kte - 1;
-  if (ksed_i == kte) ksed_i = kte - 1;
-  if (ksed_s == kte) ksed_s = kte - 1;
-  if (ksed_g == kte) ksed_g = kte - 1;
-  const float on_r = nstep_r > 0 ? 1.f / (float)nstep_r : 1.0f, on_i = nstep_i > 0 ? 1.f / (float)nstep_i : 1.0f;
-  const float on_s = nstep_s > 0 ? 1.f / (float)nstep_s : 1.0f, on_g = nstep_g > 0 ? 1.f / (float)nstep_g : 1.0f;
-  const int n_r = nint_f(1.f / on_r), n_i = nint_f(1.f / on_i), n_s = nint_f(1.f / on_s), n_g = nint_f(1.f / on_g);
-  const bool sedi = ck.l_sediment != 0;
-  const bool substeps = n_r > 1 || n_i > 1 || n_s > 1 || n_g > 1;
-
-  const float* __restrict__ Gp = a.p + col;
-  float* Gqv = a.f[F_QV] + col; float* Gqc = a.f[F_QC] + col; float* Gqi = a.f[F_QI] + col;
-  float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
-  float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
-
-  // the record of an idle cell: all rates zero, state unchanged, contents R1 / R2, speeds of the level above
-  auto idle_record = [&](int k, HandOff& h) {
-    const long o = (long)k * ld;
-    const float temp = Gt[o], pres = Gp[o];
-    const float qv = fmaxf(1.E-10f, Gqv[o]);
-    const float tempc = temp - 273.15f;
-    const float ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
-    const float lvap = KP_LVAP0 + (2106.0f - 4218.0f) * tempc;
-    h.tt = 0.f; h.qvt = 0.f; h.qct = 0.f; h.qit = 0.f; h.qrt = 0.f; h.qst = 0.f; h.qgt = 0.f; h.nit = 0.f; h.nrt = 0.f; h.nct = 0.f;
-    h.rr = R1; h.nr = R2; h.ri = R1; h.ni = R2; h.rs = R1; h.rg = R1;
-    h.rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
-    h.s15 = 0.0f;
-    if (temp > T_0) h.s15 = ck.lfus * ocp;
-    else if (temp < KP_HGFR) h.s15 = -((KP_LSUB - lvap) * ocp);
-  };
-
-  float ppt_r = 0.f, ppt_i = 0.f, ppt_s = 0.f, ppt_g = 0.f;
-  if (substeps) {
-    // A column with sub-steps sediments in place in the hand-off planes, level by level: its idle cells get their
-    // records now, and every level the speeds that sweep A settled (M:3235 ...).
-    float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;
-#pragma unroll 1
-    for (int k = nz - 1; k >= 0; --k) {
-      float* sc = sc0 + (size_t)k * cs;
-      const bool handed = (clsp[(long)k * ncol] & CLS_BUSY) != 0;
-      if (handed) {
-        if (sc[SC_RR * ps] > R1) { v_r = sc[SC_VTR * ps]; v_nr = sc[SC_VTNR * ps]; }
-        if (!iiwarm) {
-          if (sc[SC_RI * ps] > R1) { v_i = sc[SC_VTI * ps]; v_ni = sc[SC_VTNI * ps]; }
-          if (sc[SC_RS * ps] > R1) v_s = sc[SC_VTS * ps];
-          if (sc[SC_RG * ps] > R1) v_g = sc[SC_VTG * ps];
-        }
-      } else {
-        HandOff h;
-        idle_record(k, h);
-#pragma unroll
-        for (int q = SC_TTEN; q <= SC_NCTEN; ++q) sc[q * ps] = 0.0f;
-        sc[SC_RR * ps] = R1; sc[SC_NR * ps] = R2; sc[SC_RI * ps] = R1; sc[SC_NI * ps] = R2; sc[SC_RS * ps] = R1; sc[SC_RG * ps] = R1;
-        sc[SC_RHO * ps] = h.rho; sc[SC_S15 * ps] = h.s15;
-      }
-      sc[SC_VTR * ps] = v_r; sc[SC_VTNR * ps] = v_nr; sc[SC_VTI * ps] = v_i; sc[SC_VTNI * ps] = v_ni;
-      sc[SC_VTS * ps] = v_s; sc[SC_VTG * ps] = v_g;
-    }
-    const float* rhoa = sc0 + SC_RHO * ps;
-    // all but the last sub-step (rain is never gated by l_sediment, U6; the cloud-water stub M:3414-3425 is a no-op, U2)
-    if (n_r > 1) sed_substeps(sc0 + SC_RR * ps, sc0 + SC_QRTEN * ps, sc0 + SC_VTR * ps, sc0 + SC_NR * ps, sc0 + SC_NRTEN * ps,
-                              sc0 + SC_VTNR * ps, rhoa, dzp, dzs, nz, cs, n_r - 1, ksed_r, on_r, DT, true, KP_R2, ppt_r);
-    if (n_i > 1) sed_substeps(sc0 + SC_RI * ps, sc0 + SC_QITEN * ps, sc0 + SC_VTI * ps, sc0 + SC_NI * ps, sc0 + SC_NITEN * ps,
-                              sc0 + SC_VTNI * ps, rhoa, dzp, dzs, nz, cs, n_i - 1, ksed_i, on_i, DT, sedi, KP_R2, ppt_i);
-    if (n_s > 1) sed_substeps(sc0 + SC_RS * ps, sc0 + SC_QSTEN * ps, sc0 + SC_VTS * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
-                              nz, cs, n_s - 1, ksed_s, on_s, DT, sedi, 0.f, ppt_s);
-    if (n_g > 1) sed_substeps(sc0 + SC_RG * ps, sc0 + SC_QGTEN * ps, sc0 + SC_VTG * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
-                              nz, cs, n_g - 1, ksed_g, on_g, DT, sedi, 0.f, ppt_g);
-  }
-
-  // ================= sweep B: last sub-step of every species + S15 + S16, top-down =========================================
+  const SedCounts s = sed_counts(a.colint + slot, cs, nz);
+  const bool substeps = s.n_r > 1 || s.n_i > 1 || s.n_s > 1 || s.n_g > 1;
   SedParams sp;
-  sp.DT = DT; sp.odt = odt; sp.on_r = on_r; sp.on_i = on_i; sp.on_s = on_s; sp.on_g = on_g; sp.Nt_c = ck.Nt_c;
-  sp.top_r = ksed_r; sp.top_i = ksed_i; sp.top_s = ksed_s; sp.top_g = ksed_g; sp.sedi = sedi; sp.iiwarm = iiwarm;
+  sp.DT = DT; sp.odt = odt; sp.on_r = s.on_r; sp.on_i = s.on_i; sp.on_s = s.on_s; sp.on_g = s.on_g; sp.Nt_c = ck.Nt_c;
+  sp.top_r = s.ksed_r; sp.top_i = s.ksed_i; sp.top_s = s.ksed_s; sp.top_g = s.ksed_g; sp.sedi = ck.l_sediment != 0; sp.iiwarm = iiwarm;
   SedCarry c;
   c.sr_up = 0.f; c.snr_up = 0.f; c.si_up = 0.f; c.sni_up = 0.f; c.ss_up = 0.f; c.sg_up = 0.f;
-  c.ppt_r = ppt_r; c.ppt_i = ppt_i; c.ppt_s = ppt_s; c.ppt_g = ppt_g; c.lwp = 0.0; c.iwp = 0.0;
+  c.ppt_r = 0.f; c.ppt_i = 0.f; c.ppt_s = 0.f; c.ppt_g = 0.f; c.lwp = 0.0; c.iwp = 0.0;
+  if (substeps) {
+    const float* pp = a.pptsub + slot;
+    c.ppt_r = pp[0]; c.ppt_i = pp[cs]; c.ppt_s = pp[2 * cs]; c.ppt_g = pp[3 * cs];
+  }
   float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;       // speeds of the level above (no sub-steps)
+  unsigned bw = 0;
 #pragma unroll 1
   for (int k = nz - 1; k >= 0; --k) {
-    const long o = (long)k * ld;
+    if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
+    const long o = (long)k * ld + col;
     const float* q = sc0 + (size_t)k * cs;
-    const bool busy = (clsp[(long)k * ncol] & CLS_BUSY) != 0;
+    const bool busy = ((bw >> (k & 31)) & 1u) != 0;
     const bool handed = substeps || busy;
+    const float t1d = a.f[F_T][o], qv1d = a.f[F_QV][o], qc1d = a.f[F_QC][o], qi1d = a.f[F_QI][o], qr1d = a.f[F_QR][o],
+                qs1d = a.f[F_QS][o], qg1d = a.f[F_QG][o], ni1d = a.f[F_NI][o], nr1d = a.f[F_NR][o], pres = a.p[o];
     HandOff h;
     if (handed) {
       h.tt = q[SC_TTEN * ps]; h.qvt = q[SC_QVTEN * ps]; h.qct = q[SC_QCTEN * ps]; h.qit = q[SC_QITEN * ps];
@@ -1297,32 +1354,37 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
       h.nrt = q[SC_NRTEN * ps]; h.nct = q[SC_NCTEN * ps];
       h.rho = q[SC_RHO * ps]; h.s15 = q[SC_S15 * ps];
       h.rr = q[SC_RR * ps]; h.nr = q[SC_NR * ps]; h.ri = q[SC_RI * ps]; h.ni = q[SC_NI * ps]; h.rs = q[SC_RS * ps]; h.rg = q[SC_RG * ps];
+      // (the snow / graupel speed planes are only written where the species is present: the value is only used there)
+      const float o_vr = q[SC_VTR * ps], o_vnr = q[SC_VTNR * ps], o_vi = q[SC_VTI * ps], o_vni = q[SC_VTNI * ps],
+                  o_vs = q[SC_VTS * ps], o_vg = q[SC_VTG * ps];
       if (substeps) {
-        v_r = q[SC_VTR * ps]; v_nr = q[SC_VTNR * ps]; v_i = q[SC_VTI * ps]; v_ni = q[SC_VTNI * ps];
-        v_s = q[SC_VTS * ps]; v_g = q[SC_VTG * ps];
+        v_r = o_vr; v_nr = o_vnr; v_i = o_vi; v_ni = o_vni; v_s = o_vs; v_g = o_vg;
       } else {
-        if (h.rr > R1) { v_r = q[SC_VTR * ps]; v_nr = q[SC_VTNR * ps]; }
+        if (h.rr > R1) { v_r = o_vr; v_nr = o_vnr; }
         if (!iiwarm) {
-          if (h.ri > R1) { v_i = q[SC_VTI * ps]; v_ni = q[SC_VTNI * ps]; }
-          if (h.rs > R1) v_s = q[SC_VTS * ps];
-          if (h.rg > R1) v_g = q[SC_VTG * ps];
+          if (h.ri > R1) { v_i = o_vi; v_ni = o_vni; }
+          if (h.rs > R1) v_s = o_vs;
+          if (h.rg > R1) v_g = o_vg;
         }
       }
     } else {
-      idle_record(k, h);
+      h.tt = 0.f; h.qvt = 0.f; h.qct = 0.f; h.qit = 0.f; h.qrt = 0.f; h.qst = 0.f; h.qgt = 0.f; h.nit = 0.f; h.nrt = 0.f; h.nct = 0.f;
+      h.rr = R1; h.nr = R2; h.ri = R1; h.ni = R2; h.rs = R1; h.rg = R1;
+      idle_record(t1d, pres, qv1d, h.rho, h.s15);
     }
     if (RATES && !busy) {                                 // an idle cell: every process rate is zero
-      float* rp = a.rates + o + col;
+      float* rp = a.rates + o;
       const long st = (long)nz * ld;
       for (int r = 0; r < KIDMP_NRATES; ++r) rp[r * st] = 0.0f;
     }
     h.v_r = v_r; h.v_nr = v_nr; h.v_i = v_i; h.v_ni = v_ni; h.v_s = v_s; h.v_g = v_g;
-    finish_level(a, sp, c, h, k, nz, o + col, dzp[k * dzs], Gt[o], Gqv[o], Gqc[o], Gqi[o], Gqr[o], Gqs[o], Gqg[o], Gni[o], Gnr[o], Gp[o]);
+    finish_level(a, sp, c, h, k, nz, o, dzp[k * dzs], t1d, qv1d, qc1d, qi1d, qr1d, qs1d, qg1d, ni1d, nr1d, pres);
   }
   // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
   a.ppt[col] = c.ppt_r; a.ppt[ld + col] = c.ppt_i; a.ppt[2 * ld + col] = c.ppt_s; a.ppt[3 * ld + col] = c.ppt_g;
   a.coldiag[col] = c.lwp; a.coldiag[ncol + col] = c.iwp;      // summed in column order by k_diag_columns
 }
+#undef BUSY_WORD
 
 #undef R1
 #undef R2

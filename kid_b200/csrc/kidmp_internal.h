@@ -145,6 +145,11 @@ struct StepArgs {
   unsigned* cell_list;         // [<= nz*ncol] busy cells, class after class, entry = k * count + slot
   int* cell_count;             // [KC_N] busy cells of each class
   int* cell_base;              // [list blocks][KC_N] first entry of a block's cells inside its class segment
+  unsigned* busy;              // [ceil(nz/32)][count] busy bits of every cloudy column (bit k%32 of word k/32)
+  int* colint;                 // [8][count] sub-step counts and top sedimenting levels of rain, ice, snow, graupel
+  int* sub_count;              // columns that need sedimentation sub-steps (nstep > 1, M:3242) ...
+  int* sub_list;               // ... their slots
+  float* pptsub;               // [4][count] precipitation of all but the last sub-step of those columns
   float* rates;                // optional [36][nz][ld]
   double* coldiag;             // [2][ncol] liquid / ice water path of each cloudy column
   double* diag_partial;        // [DIAG_BLOCKS][KIDMP_NDIAG] block sums of k_diag_columns

@@ -1,0 +1,55 @@
+"""Build tuning variants of the library into tools/_ab/ (git-ignored, they travel to the GPU box) and time them there:
+    python tools/variants.py build [names]     (here, no GPU)
+    python tools/variants.py run [names]       (on the GPU box: state hash + ms per step of every variant)
+Each variant is a set of -D flags for kidmp_api.cu (launch shapes of the cell kernels)."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+AB = os.path.join(ROOT, "tools", "_ab")
+CLASSES = ("WARM", "ICE", "MIXNR", "FULL")
+
+
+def shape(t, b, bars, classes=CLASSES):
+    return ["-DKC_%s_T=%d" % (c, t) for c in classes] + ["-DKC_%s_B=%d" % (c, b) for c in classes] + \
+           ["-DKC_%s_BARS=%d" % (c, bars) for c in classes]
+
+
+def per(**kw):
+    """per(WARM=(threads, blocks per SM, bars), ...)"""
+    out = []
+    for c, (t, b, bars) in kw.items():
+        out += ["-DKC_%s_T=%d" % (c, t), "-DKC_%s_B=%d" % (c, b), "-DKC_%s_BARS=%d" % (c, bars)]
+    return out
+
+
+VARIANTS = {
+    "base": [],
+    "fin20": ["-DK2_MINB=20"],
+    "fin24": ["-DK2_MINB=24"],
+    "fin32": ["-DK2_MINB=32"],
+}
+
+if __name__ == "__main__":
+    what = sys.argv[1]
+    names = [a for a in sys.argv[2:] if a in VARIANTS] or list(VARIANTS)
+    if what == "build":
+        from kid_b200 import build as b
+        os.makedirs(AB, exist_ok=True)
+        procs = []
+        for n in names:
+            out = os.path.join(AB, "libkidmp_%s.so" % n)
+            cmd = [b.nvcc_path(), *b.flags(VARIANTS[n]), "-o", out, os.path.join(b.CSRC, "kidmp_api.cu")]
+            procs.append((n, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        for n, p in procs:
+            o, _ = p.communicate()
+            print(n, "rc", p.returncode, o[-400:] if p.returncode else "")
+    else:
+        for n in names:
+            env = dict(os.environ, KIDMP_LIB=os.path.join(AB, "libkidmp_%s.so" % n))
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "state_hash.py"), "--steps", "6"], env=env,
+                               capture_output=True, text=True)
+            line = (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1]
+            print("%-16s %s" % (n, line[line.find("sha256"):]), flush=True)
