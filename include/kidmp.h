@@ -149,6 +149,9 @@ int kidmp_set_option(kidmp_handle* h, const char* name, int value);
 
 /* bookkeeping for benchmarks */
 long kidmp_gpu_launches(const kidmp_handle* h);         /* kernels launched so far          */
+/* counts of the last launch of the step kernels (the last chunk of the last step; waits for it): 0 cloudy columns, 1 busy
+ * cells, 2-5 busy cells of the warm / ice / mixed-without-rain / full cell kernels, 6 columns with sedimentation sub-steps */
+int kidmp_step_stats(kidmp_handle* h, long out[8]);
 int kidmp_sync(kidmp_handle* h);                        /* wait for the handle's stream     */
 int kidmp_last_step_ms(kidmp_handle* h, float* step_ms);  /* CUDA events around the last step */
 int kidmp_tables_from_cache(const kidmp_handle* h);     /* 1 if init read the table cache   */

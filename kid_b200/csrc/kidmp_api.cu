@@ -43,12 +43,16 @@ struct kidmp_handle {
   float* d_stage = nullptr;      // staging for layout conversion, [nz][ncol]
   double* d_partial = nullptr; long partial_blocks = 0;
   // work buffers of one launch (a chunk of at most chunk_cols columns), sized for the worst case of the chunk
-  float* d_scratch = nullptr;                             // [SC_NX][nz][cols] hand-off between the cell kernels and k_finish
+  float* d_scratch = nullptr;                             // [nz*cols][SC_REC] hand-off records of the busy cells
   unsigned char* d_cls = nullptr;                         // [nz][cols] class byte of every cell
   int* d_colflag = nullptr;                               // [cols]
   int* d_work = nullptr;                                  // [count | list | mask | offset] of the cloudy columns
   unsigned* d_cells = nullptr;                            // [nz*cols] busy cells, class after class
-  int* d_cellmeta = nullptr;                              // [8 | blocks*KC_N] class totals, per-block bases
+  int* d_cellmeta = nullptr;                              // [192 | groups*64] class / key totals and starts, per-group bases
+  unsigned* d_cellidx = nullptr;                          // [nz*cols] record number of every busy cell
+  float* d_ws = nullptr;                                  // [24][nz][cols] SoA workspace of the columns with sedimentation sub-steps
+  cudaStream_t aux = nullptr;                             // k_substeps runs beside k_finish
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double* d_coldiag = nullptr;                            // [2][cols] per-column water paths for the ordered domain sums
   int* d_colwork = nullptr;                               // [8 busy words | 8 colint | sub list | 4 pptsub][cols] of the column kernels
   long work_cols = 0; int work_nz = 0;
@@ -234,20 +238,22 @@ int ensure_work(kidmp_handle* h, long cols, int nz) {
   const long C = cols > h->work_cols ? cols : h->work_cols;
   const int Z = nz > h->work_nz ? nz : h->work_nz;
   CK(h, cudaDeviceSynchronize());                    // nothing may still be reading the buffers that go away
-  void* old[] = {h->d_scratch, h->d_cls, h->d_colflag, h->d_work, h->d_cells, h->d_cellmeta, h->d_coldiag, h->d_colwork};
+  void* old[] = {h->d_scratch, h->d_cls, h->d_colflag, h->d_work, h->d_cells, h->d_cellmeta, h->d_coldiag, h->d_colwork, h->d_cellidx, h->d_ws};
   for (void* q : old) if (q) cudaFree(q);
   h->d_scratch = nullptr; h->d_cls = nullptr; h->d_colflag = nullptr; h->d_work = nullptr; h->d_cells = nullptr;
-  h->d_cellmeta = nullptr; h->d_coldiag = nullptr; h->d_colwork = nullptr; h->work_cols = 0; h->work_nz = 0;
+  h->d_cellmeta = nullptr; h->d_coldiag = nullptr; h->d_colwork = nullptr; h->d_cellidx = nullptr; h->d_ws = nullptr; h->work_cols = 0; h->work_nz = 0;
   const size_t cells = (size_t)C * Z;
   const long ngroups = (C + 31) / 32, lblocks = (C + LIST_TILE - 1) / LIST_TILE;
-  CK(h, cudaMalloc((void**)&h->d_scratch, cells * SC_NX * 4));
+  CK(h, cudaMalloc((void**)&h->d_scratch, cells * SC_REC * 4));
   CK(h, cudaMalloc((void**)&h->d_cls, cells));
   CK(h, cudaMalloc((void**)&h->d_colflag, (size_t)C * 4));
   CK(h, cudaMalloc((void**)&h->d_work, (size_t)(C + 8 + 2 * ngroups) * 4));
   CK(h, cudaMalloc((void**)&h->d_cells, cells * 4));
-  CK(h, cudaMalloc((void**)&h->d_cellmeta, (size_t)(8 + lblocks * KC_N) * 4));
+  CK(h, cudaMalloc((void**)&h->d_cellidx, cells * 4));
+  CK(h, cudaMalloc((void**)&h->d_ws, cells * WS_N * 4));
+  CK(h, cudaMalloc((void**)&h->d_cellmeta, (size_t)(192 + lblocks * (LIST_TILE / 32) * 64) * 4));
   CK(h, cudaMalloc((void**)&h->d_coldiag, (size_t)C * 2 * 8));
-  CK(h, cudaMalloc((void**)&h->d_colwork, (size_t)C * 21 * 4));
+  CK(h, cudaMalloc((void**)&h->d_colwork, (size_t)C * 17 * 4));
   h->work_cols = C; h->work_nz = Z;
   return 0;
 }
@@ -320,29 +326,36 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     if (a0.dz_col) a.dz_col = a0.dz_col + c0;
     if (a0.rates) a.rates = a0.rates + c0;
     const long ngroups = (a.ncol + 31) / 32, lblocks = (a.ncol + LIST_TILE - 1) / LIST_TILE;
-    a.scratch = h->d_scratch; a.cls = h->d_cls; a.colflag = h->d_colflag;
+    a.scratch = h->d_scratch; a.cellidx = h->d_cellidx; a.cls = h->d_cls; a.colflag = h->d_colflag;
     a.work_count = h->d_work; a.work_list = h->d_work + 8;
     a.work_mask = (unsigned*)(h->d_work + 8 + a.ncol); a.work_offset = h->d_work + 8 + a.ncol + ngroups;
-    a.cell_list = h->d_cells; a.cell_count = h->d_cellmeta; a.sub_count = h->d_cellmeta + 4; a.cell_base = h->d_cellmeta + 8;
+    a.cell_list = h->d_cells; a.cell_count = h->d_cellmeta; a.sub_count = h->d_cellmeta + 5; a.cell_kstart = h->d_cellmeta + 8;
+    a.cell_hist = h->d_cellmeta + 64; a.cell_start = h->d_cellmeta + 128; a.cell_base = h->d_cellmeta + 192;
     a.busy = (unsigned*)h->d_colwork; a.colint = h->d_colwork + 8 * h->work_cols; a.sub_list = h->d_colwork + 16 * h->work_cols;
-    a.pptsub = (float*)(h->d_colwork + 17 * h->work_cols);
+    a.ws = h->d_ws; a.ws_cols = h->work_cols;
     a.coldiag = h->d_coldiag; a.diag_partial = h->d_partial; a.nsm = h->nsm;
-    CK(h, cudaMemsetAsync(a.cell_count, 0, 8 * 4, s));
+    CK(h, cudaMemsetAsync(h->d_cellmeta, 0, 128 * 4, s));
     k_classify<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
     k_list_scan<<<1, 1024, 0, s>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
     k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
-    const int lsmem = (LIST_TILE / 32) * a.nz * KC_N * 2;
-    k_cell_count<<<(unsigned)lblocks, LIST_TILE, lsmem, s>>>(a);
-    k_cell_fill<<<(unsigned)lblocks, LIST_TILE, lsmem, s>>>(a);
+    k_cell_count<<<(unsigned)lblocks, LIST_TILE, 0, s>>>(a);
+    k_cell_offsets<<<1, 64, 0, s>>>(a);
+    k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, s>>>(a);
     // the number of cloudy columns is only known on the device: grids for the worst case, surplus blocks leave at once
     if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
     if (a.rates) launch_cells<true>(a, h->nsm, s); else launch_cells<false>(a, h->nsm, s);
     k_carries<<<(unsigned)((a.ncol + 63) / 64), 64, 0, s>>>(a);
-    k_substeps<<<(unsigned)ngroups, 32, 0, s>>>(a);
+    // the columns with sedimentation sub-steps on the second stream, the others on this one: disjoint columns
+    CK(h, cudaEventRecord(h->ev_fork, s));
+    CK(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    const unsigned sgrid = (unsigned)(ngroups < h->nsm * 16 ? ngroups : h->nsm * 16);
+    if (a.rates) k_substeps<true><<<sgrid, 32, 0, h->aux>>>(a); else k_substeps<false><<<sgrid, 32, 0, h->aux>>>(a);
+    CK(h, cudaEventRecord(h->ev_join, h->aux));
     if (a.rates) k_finish<true><<<(unsigned)ngroups, 32, 0, s>>>(a); else k_finish<false><<<(unsigned)ngroups, 32, 0, s>>>(a);
+    CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
     k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
     k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
-    h->launches += h->kc.iiwarm ? 14 : 15;
+    h->launches += h->kc.iiwarm ? 15 : 16;
   }
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(h->ev_done, s));
@@ -429,7 +442,10 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
       cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     h->err = "stream/event creation failed"; return bail(1);
   }
   memset(&h->kc, 0, sizeof h->kc);
@@ -488,6 +504,11 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_cellmeta) cudaFree(h->d_cellmeta);
   if (h->d_coldiag) cudaFree(h->d_coldiag);
   if (h->d_colwork) cudaFree(h->d_colwork);
+  if (h->d_cellidx) cudaFree(h->d_cellidx);
+  if (h->d_ws) cudaFree(h->d_ws);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->aux) cudaStreamDestroy(h->aux);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->d_pipe) cudaFree(h->d_pipe);
   if (h->d_pipe_dz) cudaFree(h->d_pipe_dz);
@@ -907,6 +928,21 @@ int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
 }
 
 long kidmp_gpu_launches(const kidmp_handle* h) { return h ? h->launches : 0; }
+
+int kidmp_step_stats(kidmp_handle* h, long out[8]) {
+  if (!h || !out) return 1;
+  for (int q = 0; q < 8; ++q) out[q] = 0;
+  if (!h->d_cellmeta) return 0;
+  cudaSetDevice(h->device);
+  CK(h, cudaEventSynchronize(h->ev_done));
+  int meta[8], cloudy = 0;
+  CK(h, cudaMemcpy(meta, h->d_cellmeta, sizeof meta, cudaMemcpyDeviceToHost));
+  CK(h, cudaMemcpy(&cloudy, h->d_work, 4, cudaMemcpyDeviceToHost));
+  out[0] = cloudy; out[1] = meta[KC_N];
+  for (int q = 0; q < KC_N; ++q) out[2 + q] = meta[q];
+  out[6] = meta[5];
+  return 0;
+}
 
 int kidmp_sync(kidmp_handle* h) {
   if (!h) return 1;

@@ -6,9 +6,8 @@
 // the species M:3235, the sub-step counts M:3242).  A column walk spends its time in dependent instruction chains of
 // cells that mostly differ from their neighbours (profiles/r01: 19 of 32 lanes active, 45 % issue), and half of the
 // cells of a cloudy column are idle.  Here
-//   k_cell_count / k_cell_fill   turn the class bytes of k_classify into one list of busy cells per class, level-major
-//                                inside a 256-column tile, so the lanes of a warp are neighbouring columns of one level
-//                                that hold the same species;
+//   k_cell_count / k_cell_fill   turn the class bytes of k_classify into one list of busy cells, sorted by species set and
+//                                class, so the lanes of a warp are cells of neighbouring columns that hold the same species;
 //   k_n0_sweep                   walks the columns that hold graupel top-down once: running minimum of M:1648;
 //   k_cells<KC>                  one thread per busy cell, one kernel per class.  The class is a template parameter:
 //                                code that cannot run for the class (every ice process for a warm cell, the collection
@@ -24,6 +23,20 @@
 #include "kidmp_column.cuh"
 
 namespace kidmp {
+
+// One sector (32 bytes, 8 floats) of a hand-off record per instruction: the 256-bit global accesses of sm_100
+// (LDG.E.256 / STG.E.256).  A lane then reads or writes whole sectors of its record, never part of one.
+struct Sector { float v[8]; };
+__device__ __forceinline__ void st_sector(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e),
+               "f"(f), "f"(g), "f"(h) : "memory");
+}
+__device__ __forceinline__ Sector ld_sector(const float* p) {
+  Sector s;
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(s.v[0]), "=f"(s.v[1]), "=f"(s.v[2]), "=f"(s.v[3]),
+               "=f"(s.v[4]), "=f"(s.v[5]), "=f"(s.v[6]), "=f"(s.v[7]) : "l"(p));
+  return s;
+}
 
 // M:1649-1653 for a given intercept (the running minimum already taken)
 __device__ __forceinline__ void graupel_slope(double N0_exp, float rg, double& ilamg, double& N0_g) {
@@ -56,101 +69,115 @@ template <int KC> struct CellTraits {
 #define D0s KP_D0S
 #define D0g KP_D0G
 
-// ---- per-class lists of busy cells ------------------------------------------------------------------------------
-// A block owns LIST_TILE consecutive columns; warp w owns 32 of them.  Entries of a class inside the block's range
-// are level-major from the top, then by column: 32 consecutive entries are cells of ONE level (mostly).
-// s_cnt[w][k][c] = cells of class c in warp w's columns at level k.
-__device__ __forceinline__ void list_tile_counts(const StepArgs& a, unsigned short* s_cnt, int nz, long col, bool in_range) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// ---- lists of busy cells ------------------------------------------------------------------------------------------
+// Sort key of a busy cell: its five species bits and whether it is below 0 C (64 keys).  The list holds the cells key after
+// key, the keys of one kernel class next to each other, so a class kernel walks one contiguous range in which the 32
+// cells of a warp hold the SAME species (same branches) and, inside a key, are the cells of 32 neighbouring columns level
+// after level from the top (neighbouring columns of one or a few levels: same table entries, few cache lines per load;
+// the order is the same from run to run).
+// k_cell_count: histogram of the keys per tile and per launch; k_cell_offsets: first entry of every key and class;
+// k_cell_fill: the entries, and the busy bits of every cloudy column for the column kernels.
+__device__ __forceinline__ unsigned cell_key(unsigned c) { return (c & 31u) | ((c >> CLS_COLD_SHIFT) & 1u) << 5; }
+__device__ __forceinline__ bool tile_has_cloud(const StepArgs& a) {
+  const int g0 = blockIdx.x * (LIST_TILE / 32);
+  bool any = false;
+#pragma unroll
+  for (int g = 0; g < LIST_TILE / 32; ++g) if ((long)(g0 + g) * 32 < a.ncol && a.work_mask[g0 + g]) any = true;
+  return any;
+}
+__global__ void __launch_bounds__(LIST_TILE) k_cell_count(StepArgs a) {
+  __shared__ int s_cnt[LIST_TILE / 32][64];               // cells of every key in the 32 columns of every warp
+  const int nz = a.nz;
+  const long col = (long)blockIdx.x * LIST_TILE + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (!tile_has_cloud(a)) return;                         // a tile without a cloudy column has no busy cell
+  s_cnt[warp][lane] = 0; s_cnt[warp][lane + 32] = 0;
+  __syncwarp();
+  const bool in_range = col < a.ncol;
   const unsigned char* cp = a.cls + col;
+#pragma unroll 4
   for (int k = 0; k < nz; ++k) {
     const unsigned c = in_range ? cp[(long)k * a.ncol] : 0u;
     const bool busy = (c & CLS_BUSY) != 0u;
-    const unsigned kc = c >> CLS_KC_SHIFT;
+    const unsigned act = __ballot_sync(0xffffffffu, busy);
+    if (busy) {
+      const unsigned key = cell_key(c);
+      const unsigned m = __match_any_sync(act, key);
+      if (lane == __ffs(m) - 1) s_cnt[warp][key] += __popc(m);      // one leader per key, only this warp writes its row
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int key = threadIdx.x;
+    int total = 0;
 #pragma unroll
-    for (int q = 0; q < KC_N; ++q) {
-      const unsigned m = __ballot_sync(0xffffffffu, busy && kc == (unsigned)q);
-      if (lane == 0) s_cnt[(warp * nz + k) * KC_N + q] = (unsigned short)__popc(m);
+    for (int w = 0; w < LIST_TILE / 32; ++w) total += s_cnt[w][key];
+    if (total) {
+      int run = atomicAdd(&a.cell_hist[key], total);
+#pragma unroll
+      for (int w = 0; w < LIST_TILE / 32; ++w) {
+        a.cell_base[((long)blockIdx.x * (LIST_TILE / 32) + w) * 64 + key] = run;
+        run += s_cnt[w][key];
+      }
     }
   }
 }
-__global__ void __launch_bounds__(LIST_TILE) k_cell_count(StepArgs a) {
-  extern __shared__ unsigned short s_cnt[];               // [8][nz][KC_N]
-  __shared__ int s_tot[KC_N];
-  const int nz = a.nz;
-  const long col = (long)blockIdx.x * LIST_TILE + threadIdx.x;
-  if (threadIdx.x < KC_N) s_tot[threadIdx.x] = 0;
-  // a tile without a cloudy column has no busy cell
-  const int g0 = blockIdx.x * (LIST_TILE / 32);
-  bool any = false;
-  for (int g = 0; g < LIST_TILE / 32; ++g) if ((long)(g0 + g) * 32 < a.ncol && a.work_mask[g0 + g]) any = true;
+__global__ void __launch_bounds__(64) k_cell_offsets(StepArgs a) {
+  __shared__ int s_n[64], s_kc[64];
+  const int t = threadIdx.x;
+  const bool iiwarm = ck.iiwarm != 0;
+  s_n[t] = a.cell_hist[t];
+  s_kc[t] = cell_kernel_class((unsigned)t & 31u, (t >> 5) != 0, iiwarm);
   __syncthreads();
-  if (any) {
-    list_tile_counts(a, s_cnt, nz, col, col < a.ncol);
-    __syncthreads();
-    const int n = (LIST_TILE / 32) * nz * KC_N;
-    int mine = 0;                                         // the stride is a multiple of KC_N: a thread only meets class tid % KC_N
-    for (int i = threadIdx.x; i < n; i += LIST_TILE) mine += s_cnt[i];
-    if (mine) atomicAdd(&s_tot[threadIdx.x & (KC_N - 1)], mine);
-    __syncthreads();
+  int start = 0;
+  for (int j = 0; j < 64; ++j) if (s_kc[j] < s_kc[t] || (s_kc[j] == s_kc[t] && j < t)) start += s_n[j];
+  a.cell_start[t] = start;
+  if (t < KC_N) {
+    int n = 0, first = 0;
+    for (int j = 0; j < 64; ++j) { if (s_kc[j] == t) n += s_n[j]; if (s_kc[j] < t) first += s_n[j]; }
+    a.cell_count[t] = n; a.cell_kstart[t] = first;
   }
-  if (threadIdx.x < KC_N) {
-    const int t = any ? s_tot[threadIdx.x] : 0;
-    a.cell_base[(long)blockIdx.x * KC_N + threadIdx.x] = t ? atomicAdd(&a.cell_count[threadIdx.x], t) : 0;
-  }
+  if (t == 0) { int n = 0; for (int j = 0; j < 64; ++j) n += s_n[j]; a.cell_count[KC_N] = n; }
 }
 __global__ void __launch_bounds__(LIST_TILE) k_cell_fill(StepArgs a) {
-  extern __shared__ unsigned short s_cnt[];               // [8][nz][KC_N]
-  __shared__ int s_lvl[KC_N];
+  __shared__ int s_run[LIST_TILE / 32][64];               // next entry of every key for the cells of this warp
   const int nz = a.nz;
   const long col = (long)blockIdx.x * LIST_TILE + threadIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g0 = blockIdx.x * (LIST_TILE / 32);
-  bool any = false;
-  for (int g = 0; g < LIST_TILE / 32; ++g) if ((long)(g0 + g) * 32 < a.ncol && a.work_mask[g0 + g]) any = true;
-  if (!any) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool in_range = col < a.ncol;
-  list_tile_counts(a, s_cnt, nz, col, in_range);
-  // first entry of every class segment: classes follow each other in the list
-  int seg[KC_N];
-  {
-    int run = 0;
-#pragma unroll
-    for (int q = 0; q < KC_N; ++q) { seg[q] = run + a.cell_base[(long)blockIdx.x * KC_N + q]; run += a.cell_count[q]; }
-  }
-  if (threadIdx.x < KC_N) s_lvl[threadIdx.x] = 0;
-  __syncthreads();
-  const unsigned count = (unsigned)*a.work_count;
   const unsigned gmask = in_range ? a.work_mask[col >> 5] : 0u;
+  if (__shfl_sync(0xffffffffu, gmask, 0) == 0u) return;   // no cloudy column among the 32 of this warp (lane 0 is in range or the warp is empty)
+  {
+    const int* base = a.cell_base + ((long)blockIdx.x * (LIST_TILE / 32) + warp) * 64;
+    s_run[warp][lane] = a.cell_start[lane] + base[lane];                 // (garbage for keys this warp does not hold: never read)
+    s_run[warp][lane + 32] = a.cell_start[lane + 32] + base[lane + 32];
+  }
+  __syncwarp();
+  const unsigned count = (unsigned)*a.work_count;
   const unsigned slot = (unsigned)a.work_offset[in_range ? (col >> 5) : 0] + __popc(gmask & ((1u << lane) - 1u));
-  const unsigned char* cp = a.cls + col;
   const bool cloudy = in_range && ((gmask >> lane) & 1u);
+  const unsigned char* cp = a.cls + col;
   unsigned bword = 0;                                     // busy bits of 32 levels of my column, for the column kernels
+#pragma unroll 2
   for (int k = nz - 1; k >= 0; --k) {
     const unsigned c = in_range ? cp[(long)k * a.ncol] : 0u;
     const bool busy = (c & CLS_BUSY) != 0u;
-    const unsigned kc = c >> CLS_KC_SHIFT;
-    if (busy) bword |= 1u << (k & 31);
-    if ((k & 31) == 0) { if (cloudy) a.busy[(size_t)(k >> 5) * count + slot] = bword; bword = 0; }
-    int before = 0, level_total = 0;                      // cells of my class at this level in the warps before mine / in all warps
+    const unsigned act = __ballot_sync(0xffffffffu, busy);
     if (busy) {
-      for (int w = 0; w < LIST_TILE / 32; ++w) {
-        const int v = s_cnt[(w * nz + k) * KC_N + kc];
-        if (w < warp) before += v;
-      }
+      bword |= 1u << (k & 31);
+      const unsigned key = cell_key(c);
+      const unsigned m = __match_any_sync(act, key);
+      const int leader = __ffs(m) - 1;
+      int base = 0;
+      if (lane == leader) { base = s_run[warp][key]; s_run[warp][key] = base + __popc(m); }
+      base = __shfl_sync(m, base, leader);
+      const unsigned pos = (unsigned)base + __popc(m & ((1u << lane) - 1u));
+      a.cell_list[pos] = (unsigned)k * count + slot;
+      a.cellidx[(size_t)k * count + slot] = pos;             // where the column kernels find the record of this cell
     }
-#pragma unroll
-    for (int q = 0; q < KC_N; ++q) {
-      const unsigned m = __ballot_sync(0xffffffffu, busy && kc == (unsigned)q);
-      if (busy && kc == (unsigned)q)
-        a.cell_list[seg[q] + s_lvl[q] + before + __popc(m & ((1u << lane) - 1u))] = (unsigned)k * count + slot;
-    }
-    __syncthreads();
-    if (threadIdx.x < KC_N) {
-      for (int w = 0; w < LIST_TILE / 32; ++w) level_total += s_cnt[(w * nz + k) * KC_N + threadIdx.x];
-      s_lvl[threadIdx.x] += level_total;
-    }
-    __syncthreads();
+    __syncwarp();
+    if ((k & 31) == 0) { if (cloudy) a.busy[(size_t)(k >> 5) * count + slot] = bword; bword = 0; }
   }
 }
 
@@ -165,38 +192,52 @@ __global__ void __launch_bounds__(128) k_n0_sweep(StepArgs a) {
   if (!(a.colflag[col] & 1)) return;
   const int nz = a.nz;
   const long ld = a.ld;
-  float* n0a = a.scratch + (size_t)SC_N0A * nz * count + slot;
+  float* const n0a = a.scratch + SC_N0A;                      // field of the cell's record
+  const unsigned* const cidx = a.cellidx + slot;
   const double n0_empty = g_n0_lo;
   bool warm_a = false;                                    // a level at or above this one has T >= 270.65 K (k_0, M:1635)
   double n0_min = (double)KP_GONV_MAX;
-#pragma unroll 1
-  for (int k = nz - 1; k >= 0; --k) {
-    const long g = (long)k * ld + col;
-    const float t1d = a.f[F_T][g], qg1d = a.f[F_QG][g], qr1d = a.f[F_QR][g];
-    if (t1d >= 270.65f) warm_a = true;
-    const bool cold_rain = !warm_a && k > 0 && qr1d > R1;
-    if (qg1d > R1 || cold_rain) {
-      const float pres = a.p[g], qv = fmaxf(1.E-10f, a.f[F_QV][g]);
-      const float rho = 0.622f * pres / (KP_R * t1d * (qv + 0.622f));
-      const float rg = (qg1d > R1) ? qg1d * rho : R1;
-      bool slw = false;
-      float mvd_r = 0.f;
-      if (cold_rain) {                                    // the rain of S1 (M:1445-1466) for the xslw1 of M:1640
-        const float rr = qr1d * rho;
-        float nr = fmaxf(R2, a.f[F_NR][g] * rho);
-        if (nr <= R2) { mvd_r = 1.0E-3f; nr = nr_from_mvd(rr, mvd_r); }
-        const double lamr = rain_lam(nr, rr);
-        mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
-        if (mvd_r > 2.5E-3f) mvd_r = 2.5E-3f;
-        else if (mvd_r < D0r * 0.75f) mvd_r = D0r * 0.75f;
-        slw = mvd_r > 100.E-6f;
+  constexpr int B = 6;                                    // levels loaded per batch: the walk is a chain of dependent steps,
+#pragma unroll 1                                          // so the loads of several levels are put in flight together
+  for (int k0 = nz - 1; k0 >= 0; k0 -= B) {
+    float tb[B], gb[B], rb[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int k = k0 - j;
+      const long g = (long)(k >= 0 ? k : 0) * ld + col;
+      tb[j] = a.f[F_T][g]; gb[j] = a.f[F_QG][g]; rb[j] = a.f[F_QR][g];
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int k = k0 - j;
+      if (k < 0) break;
+      const long g = (long)k * ld + col;
+      const float t1d = tb[j], qg1d = gb[j], qr1d = rb[j];
+      if (t1d >= 270.65f) warm_a = true;
+      const bool cold_rain = !warm_a && k > 0 && qr1d > R1;
+      if (qg1d > R1 || cold_rain) {
+        const float pres = a.p[g], qv = fmaxf(1.E-10f, a.f[F_QV][g]);
+        const float rho = 0.622f * pres / (KP_R * t1d * (qv + 0.622f));
+        const float rg = (qg1d > R1) ? qg1d * rho : R1;
+        bool slw = false;
+        float mvd_r = 0.f;
+        if (cold_rain) {                                  // the rain of S1 (M:1445-1466) for the xslw1 of M:1640
+          const float rr = qr1d * rho;
+          float nr = fmaxf(R2, a.f[F_NR][g] * rho);
+          if (nr <= R2) { mvd_r = 1.0E-3f; nr = nr_from_mvd(rr, mvd_r); }
+          const double lamr = rain_lam(nr, rr);
+          mvd_r = (float)((double)(3.0f + 0.f + 0.672f) / lamr);
+          if (mvd_r > 2.5E-3f) mvd_r = 2.5E-3f;
+          else if (mvd_r < D0r * 0.75f) mvd_r = D0r * 0.75f;
+          slw = mvd_r > 100.E-6f;
+        }
+        double N0_exp = n0_empty;
+        if (slw || rg > 5.E-5f) N0_exp = graupel_n0_exp(slw ? 4.01f + log10_f(mvd_r) : 0.01f, rg);
+        n0_min = fmin(N0_exp, n0_min);
+        if (qg1d > R1) n0a[(size_t)cidx[(size_t)k * count] * SC_REC] = (float)n0_min;     // values of M:1646 are f32 numbers: exact
+      } else {
+        n0_min = fmin(n0_empty, n0_min);
       }
-      double N0_exp = n0_empty;
-      if (slw || rg > 5.E-5f) N0_exp = graupel_n0_exp(slw ? 4.01f + log10_f(mvd_r) : 0.01f, rg);
-      n0_min = fmin(N0_exp, n0_min);
-      if (qg1d > R1) n0a[(size_t)k * count] = (float)n0_min;     // values of M:1646 are f32 numbers: exact
-    } else {
-      n0_min = fmin(n0_empty, n0_min);
     }
   }
 }
@@ -209,15 +250,12 @@ template <int KC, int THREADS, int MINB, int BARS, bool RATES>
 __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
   using TR = CellTraits<KC>;
   constexpr bool LOCK = BARS != 0;
-  int seg = 0;
-#pragma unroll
-  for (int q = 0; q < KC; ++q) seg += a.cell_count[q];
   const int n = a.cell_count[KC];
-  const unsigned* __restrict__ list = a.cell_list + seg;
+  const unsigned* __restrict__ list = a.cell_list + a.cell_kstart[KC];
   const int nz = a.nz;
   const long ld = a.ld;
   const unsigned count = (unsigned)*a.work_count;
-  const size_t ps = (size_t)nz * count;                   // plane stride of the hand-off
+  float* const sc_class = a.scratch + (size_t)a.cell_kstart[KC] * SC_REC;    // records in list order
   const float DT = a.dt;
   const float odt = 1.f / DT, odts = 1.f / DT;
   const float Nt_c = ck.Nt_c;
@@ -242,7 +280,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
     float qc1d = TR::C ? a.f[F_QC][o] : 0.0f, qi1d = TR::I ? a.f[F_QI][o] : 0.0f, qr1d = TR::R ? a.f[F_QR][o] : 0.0f,
           qs1d = TR::S ? a.f[F_QS][o] : 0.0f, qg1d = TR::G ? a.f[F_QG][o] : 0.0f;
     float ni1d = TR::I ? a.f[F_NI][o] : 0.0f, nr1d = TR::R ? a.f[F_NR][o] : 0.0f;
-    float* const sc = a.scratch + (size_t)k * count + slot;
+    float* const sc = sc_class + (size_t)(valid ? i : wbase) * SC_REC;
 
     // rates, M:1184-1211 (zeroed M:1282-1363)
     double prw_vcd = 0., pnc_wcd = 0., pnc_wau = 0., pnc_rcw = 0., pnc_scw = 0., pnc_gcw = 0.;
@@ -358,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
         smof = field_moment(tc0, ck.cse[15], smo2);
       }
       // ---- S4, M:1633-1654 graupel intercept: the running minimum of M:1648 comes from k_n0_sweep -----------
-      if (TR::G && L_qg) graupel_slope((double)sc[SC_N0A * ps], rg, ilamg, N0_g);
+      if (TR::G && L_qg) graupel_slope((double)sc[SC_N0A], rg, ilamg, N0_g);
     }
     // M:1661-1666 rain slope and intercept.  Without rain (rr = R1, nr = R2) every reader of lamr, ilamr, N0_r
     // and mvd_r is switched off (L_qr at M:1676, M:1724, M:2880; rr >= r_r(1) at M:1818, M:1964, M:2028, M:2188)
@@ -1081,15 +1119,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       float s15 = 0.0f;
       if (temp > T_0) s15 = ck.lfus * ocp;
       else if (temp < KP_HGFR) s15 = -((KP_LSUB - lvap) * ocp);
-      sc[SC_TTEN * ps] = tt; sc[SC_QVTEN * ps] = qvt; sc[SC_QCTEN * ps] = qct; sc[SC_QITEN * ps] = qit;
-      sc[SC_QRTEN * ps] = qrt; sc[SC_QSTEN * ps] = qst; sc[SC_QGTEN * ps] = qgt; sc[SC_NITEN * ps] = nit;
-      sc[SC_NRTEN * ps] = nrt; sc[SC_NCTEN * ps] = nct;
-      sc[SC_RR * ps] = rr; sc[SC_NR * ps] = nr; sc[SC_RI * ps] = ri; sc[SC_NI * ps] = ni; sc[SC_RS * ps] = rs; sc[SC_RG * ps] = rg;
-      sc[SC_VTR * ps] = v_r; sc[SC_VTNR * ps] = v_nr; sc[SC_VTI * ps] = v_i; sc[SC_VTNI * ps] = v_ni;
-      sc[SC_RHO * ps] = rho; sc[SC_S15 * ps] = s15;
       // the sign of the first intercept carries the k_0 test of this level's updated temperature (intercepts are > 0)
-      sc[SC_N0A * ps] = warm9 ? -(float)n0b_lo : (float)n0b_lo; sc[SC_N0B_SLW * ps] = (float)n0b_slw;
-      sc[SC_VTS_RAW * ps] = vts_h; sc[SC_VTS_BOOST * ps] = vts_boost; sc[SC_TEMP * ps] = temp;
+      const float n0a_out = warm9 ? -(float)n0b_lo : (float)n0b_lo;
+      // one 128-byte record, four whole sectors, SC_* order
+      st_sector(sc, tt, qvt, qct, qit, qrt, qst, qgt, nit);
+      st_sector(sc + 8, nrt, nct, nr, ni, v_ni, 0.f, 0.f, 0.f);
+      st_sector(sc + 16, rr, ri, rs, rg, v_r, v_nr, v_i, rho);
+      st_sector(sc + 24, s15, n0a_out, (float)n0b_slw, vts_h, vts_boost, temp, 0.f, 0.f);
     }
   }
 #undef LOCKBAR
@@ -1097,6 +1133,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
 
 // ---- K2: what runs down the column, then S14 sedimentation (M:3365-3578), S15 instant melt / freeze (M:3584-3606) and
 // S16 (M:3623-3686).  One thread per cloudy column (slot), one warp per block.
+// (SoA workspace of the columns with sub-steps: plane [nz][ws_cols], lane = column)
 __device__ __forceinline__ void sed_substeps(float* __restrict__ r, float* __restrict__ rten, const float* __restrict__ v,
                                              float* __restrict__ n, float* __restrict__ nten, const float* __restrict__ vn,
                                              const float* __restrict__ rhoa, const float* __restrict__ dz, long dzs, int nz, long cs,
@@ -1146,11 +1183,10 @@ __global__ void __launch_bounds__(64, 16) k_carries(StepArgs a) {
   const int nz = a.nz;
   const long ld = a.ld;
   const long cs = count;
-  const size_t ps = (size_t)nz * count;
   const float DT = a.dt;
   const bool iiwarm = ck.iiwarm != 0;
   const double n0_empty = g_n0_lo;
-  float* const sc0 = a.scratch + slot;
+  const unsigned* const cidx = a.cellidx + slot;
   const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;     // one vector shared by all columns (KiD) or this column's own (WRF entry)
   const long dzs = a.dz_col ? ld : 1;
   int nstep_r = 0, nstep_i = 0, nstep_s = 0, nstep_g = 0, ksed_r = 1, ksed_i = 1, ksed_s = 1, ksed_g = 1;
@@ -1158,19 +1194,25 @@ __global__ void __launch_bounds__(64, 16) k_carries(StepArgs a) {
   bool warm_b = false;
   float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_s = 0.f, v_g = 0.f;     // speeds of the level above (the ice number speed sets no count, M:3267)
   unsigned bw = 0;
+  unsigned idx_next = cidx[(size_t)(nz - 1) * cs];        // (the index of an idle cell is never used)
 #pragma unroll 1
   for (int k = nz - 1; k >= 0; --k) {
     if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
-    float* sc = sc0 + (size_t)k * cs;
+    const unsigned idx = idx_next;
+    if (k > 0) idx_next = cidx[(size_t)(k - 1) * cs];     // in flight while this level is worked on
+    float* sc = a.scratch + (size_t)idx * SC_REC;
     const float dzq = dzp[k * dzs];
     if ((bw >> (k & 31)) & 1u) {
-      const float rr = sc[SC_RR * ps], o_vr = sc[SC_VTR * ps], o_vnr = sc[SC_VTNR * ps];
+      // the second half of the record (two sectors) holds everything this kernel reads
+      const Sector s2 = ld_sector(sc + 16);
+      const float rr = s2.v[0], o_vr = s2.v[4], o_vnr = s2.v[5];
       if (!iiwarm) {
-        const float ri = sc[SC_RI * ps], rs = sc[SC_RS * ps], rg = sc[SC_RG * ps];
-        const float x1 = sc[SC_N0A * ps], x2 = sc[SC_N0B_SLW * ps];
-        const float o_vi = sc[SC_VTI * ps];
-        const float vts = sc[SC_VTS_RAW * ps], vts_boost = sc[SC_VTS_BOOST * ps], temp = sc[SC_TEMP * ps];
-        const float rho = sc[SC_RHO * ps], s15 = sc[SC_S15 * ps];
+        const Sector s3 = ld_sector(sc + 24);
+        const float ri = s2.v[1], rs = s2.v[2], rg = s2.v[3];
+        const float x1 = s3.v[1], x2 = s3.v[2];
+        const float o_vi = s2.v[6];
+        const float vts = s3.v[3], vts_boost = s3.v[4], temp = s3.v[5];
+        const float rho = s2.v[7], s15 = s3.v[0];
         if (rr > R1) { v_r = o_vr; v_nr = o_vnr; }
         if (x1 < 0.f) warm_b = true;
         const double N0_exp = (!warm_b && k > 0) ? (double)x2 : (double)fabsf(x1);
@@ -1179,7 +1221,7 @@ __global__ void __launch_bounds__(64, 16) k_carries(StepArgs a) {
         if (rs > R1) {
           if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * ((v_r - vts * vts_boost) / (temp - T_0)));
           else v_s = vts * vts_boost;
-          sc[SC_VTS * ps] = v_s;
+          sc[SC_VTS] = v_s;
         }
         if (rg > R1) {
           const float rhof = sqrtf(ck.rho_not / rho);
@@ -1187,7 +1229,7 @@ __global__ void __launch_bounds__(64, 16) k_carries(StepArgs a) {
           graupel_slope(n0_min, rg, ilamg, N0_g);
           const float vtg = (float)((double)(rhof * KP_AV_G * ck.cgg[5] * ck.ogg3) * pow_d(ilamg, (double)KP_BV_G));
           v_g = (s15 > 0.f) ? fmaxf(vtg, v_r) : vtg;         // temp > T_0 is what makes the S15 factor positive
-          sc[SC_VTG * ps] = v_g;
+          sc[SC_VTG] = v_g;
         }
       } else if (rr > R1) { v_r = o_vr; v_nr = o_vnr; }
     } else if (!iiwarm) {
@@ -1244,138 +1286,175 @@ __device__ __forceinline__ void idle_record(float temp, float pres, float qv1d, 
   else if (temp < KP_HGFR) s15 = -((KP_LSUB - lvap) * ocp);
 }
 
-// ---- K2b: the columns that need sedimentation sub-steps (a compacted list: full warps).  Such a column sediments in place in
-// the hand-off planes, level by level: its idle cells get their records, every level the speeds that k_carries settled, and
-// all but the last sub-step of each species run here (M:3365-3578).  The precipitation of those sub-steps goes to pptsub.
+// ---- K2b: the columns that need sedimentation sub-steps (nstep > 1, M:3242), on their compacted list: full warps.  Such a
+// column needs a record for every level (mass falls into idle cells) and is swept once per sub-step, so it is first
+// gathered into an SoA workspace [WS_N][nz][ws_cols] (lane = column: every access of the sub-steps is one line per warp):
+// the records of its busy cells, the zero record of its idle cells, and at every level the speeds that k_carries settled.
+// Then all but the last sub-step of each species (M:3365-3578), then the last one with S15 / S16 (finish_level), as k_finish
+// does for the other columns.  Runs beside k_finish on a second stream: the two kernels own different columns.
+enum { WS_TTEN = 0, WS_QVTEN, WS_QCTEN, WS_QITEN, WS_QRTEN, WS_QSTEN, WS_QGTEN, WS_NITEN, WS_NRTEN, WS_NCTEN,
+       WS_RR, WS_NR, WS_RI, WS_NI, WS_RS, WS_RG, WS_VTR, WS_VTNR, WS_VTI, WS_VTNI, WS_VTS, WS_VTG, WS_RHO, WS_S15, WS_N };
+template <bool RATES>
 __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
-  const int i = blockIdx.x * 32 + threadIdx.x;
-  if (i >= *a.sub_count) return;
-  const int slot = a.sub_list[i];
-  const int count = *a.work_count;
-  const long col = a.work_list[slot];
+  const int n = *a.sub_count, count = *a.work_count;
   const int nz = a.nz;
-  const long ld = a.ld;
-  const long cs = count;
-  const size_t ps = (size_t)nz * count;
-  const float DT = a.dt;
+  const long ld = a.ld, ncol = a.ncol;
+  const long cs = a.ws_cols;
+  const size_t ps = (size_t)nz * cs;
+  const float DT = a.dt, odt = 1.f / DT;
   const bool iiwarm = ck.iiwarm != 0;
-  float* const sc0 = a.scratch + slot;
-  const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;
-  const long dzs = a.dz_col ? ld : 1;
-  const SedCounts s = sed_counts(a.colint + slot, cs, nz);
-  float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;
-  unsigned bw = 0;
-#pragma unroll 1
-  for (int k = nz - 1; k >= 0; --k) {
-    if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
-    float* sc = sc0 + (size_t)k * cs;
-    if ((bw >> (k & 31)) & 1u) {
-      if (sc[SC_RR * ps] > R1) { v_r = sc[SC_VTR * ps]; v_nr = sc[SC_VTNR * ps]; }
-      if (!iiwarm) {
-        if (sc[SC_RI * ps] > R1) { v_i = sc[SC_VTI * ps]; v_ni = sc[SC_VTNI * ps]; }
-        if (sc[SC_RS * ps] > R1) v_s = sc[SC_VTS * ps];
-        if (sc[SC_RG * ps] > R1) v_g = sc[SC_VTG * ps];
-      }
-    } else {
-      const long o = (long)k * ld + col;
-      float rho, s15;
-      idle_record(a.f[F_T][o], a.p[o], a.f[F_QV][o], rho, s15);
-#pragma unroll
-      for (int q = SC_TTEN; q <= SC_NCTEN; ++q) sc[q * ps] = 0.0f;
-      sc[SC_RR * ps] = R1; sc[SC_NR * ps] = R2; sc[SC_RI * ps] = R1; sc[SC_NI * ps] = R2; sc[SC_RS * ps] = R1; sc[SC_RG * ps] = R1;
-      sc[SC_RHO * ps] = rho; sc[SC_S15 * ps] = s15;
-    }
-    sc[SC_VTR * ps] = v_r; sc[SC_VTNR * ps] = v_nr; sc[SC_VTI * ps] = v_i; sc[SC_VTNI * ps] = v_ni;
-    sc[SC_VTS * ps] = v_s; sc[SC_VTG * ps] = v_g;
-  }
-  const float* rhoa = sc0 + SC_RHO * ps;
   const bool sedi = ck.l_sediment != 0;
-  float ppt_r = 0.f, ppt_i = 0.f, ppt_s = 0.f, ppt_g = 0.f;
-  // all but the last sub-step (rain is never gated by l_sediment, U6; the cloud-water stub M:3414-3425 is a no-op, U2)
-  if (s.n_r > 1) sed_substeps(sc0 + SC_RR * ps, sc0 + SC_QRTEN * ps, sc0 + SC_VTR * ps, sc0 + SC_NR * ps, sc0 + SC_NRTEN * ps,
-                              sc0 + SC_VTNR * ps, rhoa, dzp, dzs, nz, cs, s.n_r - 1, s.ksed_r, s.on_r, DT, true, KP_R2, ppt_r);
-  if (s.n_i > 1) sed_substeps(sc0 + SC_RI * ps, sc0 + SC_QITEN * ps, sc0 + SC_VTI * ps, sc0 + SC_NI * ps, sc0 + SC_NITEN * ps,
-                              sc0 + SC_VTNI * ps, rhoa, dzp, dzs, nz, cs, s.n_i - 1, s.ksed_i, s.on_i, DT, sedi, KP_R2, ppt_i);
-  if (s.n_s > 1) sed_substeps(sc0 + SC_RS * ps, sc0 + SC_QSTEN * ps, sc0 + SC_VTS * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
-                              nz, cs, s.n_s - 1, s.ksed_s, s.on_s, DT, sedi, 0.f, ppt_s);
-  if (s.n_g > 1) sed_substeps(sc0 + SC_RG * ps, sc0 + SC_QGTEN * ps, sc0 + SC_VTG * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
-                              nz, cs, s.n_g - 1, s.ksed_g, s.on_g, DT, sedi, 0.f, ppt_g);
-  float* pp = a.pptsub + slot;
-  pp[0] = ppt_r; pp[cs] = ppt_i; pp[2 * cs] = ppt_s; pp[3 * cs] = ppt_g;
+#pragma unroll 1
+  for (int j = blockIdx.x * 32 + threadIdx.x; j < n; j += gridDim.x * 32) {
+    const int slot = a.sub_list[j];
+    const long col = a.work_list[slot];
+    const SedCounts s = sed_counts(a.colint + slot, count, nz);
+    const unsigned* const cidx = a.cellidx + slot;
+    const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;
+    const long dzs = a.dz_col ? ld : 1;
+    float* const w0 = a.ws + j;
+    {
+      float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;
+      unsigned bw = 0;
+#pragma unroll 1
+      for (int k = nz - 1; k >= 0; --k) {
+        if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
+        float* w = w0 + (size_t)k * cs;
+        if ((bw >> (k & 31)) & 1u) {
+          const float* q = a.scratch + (size_t)cidx[(size_t)k * count] * SC_REC;
+          const Sector s0 = ld_sector(q), s1 = ld_sector(q + 8), s2 = ld_sector(q + 16), s3 = ld_sector(q + 24);
+          w[WS_TTEN * ps] = s0.v[0]; w[WS_QVTEN * ps] = s0.v[1]; w[WS_QCTEN * ps] = s0.v[2]; w[WS_QITEN * ps] = s0.v[3];
+          w[WS_QRTEN * ps] = s0.v[4]; w[WS_QSTEN * ps] = s0.v[5]; w[WS_QGTEN * ps] = s0.v[6]; w[WS_NITEN * ps] = s0.v[7];
+          w[WS_NRTEN * ps] = s1.v[0]; w[WS_NCTEN * ps] = s1.v[1]; w[WS_NR * ps] = s1.v[2]; w[WS_NI * ps] = s1.v[3];
+          w[WS_RR * ps] = s2.v[0]; w[WS_RI * ps] = s2.v[1]; w[WS_RS * ps] = s2.v[2]; w[WS_RG * ps] = s2.v[3];
+          w[WS_RHO * ps] = s2.v[7]; w[WS_S15 * ps] = s3.v[0];
+          if (s2.v[0] > R1) { v_r = s2.v[4]; v_nr = s2.v[5]; }
+          if (!iiwarm) {
+            if (s2.v[1] > R1) { v_i = s2.v[6]; v_ni = s1.v[4]; }
+            if (s2.v[2] > R1) v_s = s3.v[6];
+            if (s2.v[3] > R1) v_g = s3.v[7];
+          }
+        } else {
+          const long o = (long)k * ld + col;
+          float rho, s15;
+          idle_record(a.f[F_T][o], a.p[o], a.f[F_QV][o], rho, s15);
+#pragma unroll
+          for (int q = WS_TTEN; q <= WS_NCTEN; ++q) w[q * ps] = 0.0f;
+          w[WS_RR * ps] = R1; w[WS_NR * ps] = R2; w[WS_RI * ps] = R1; w[WS_NI * ps] = R2; w[WS_RS * ps] = R1; w[WS_RG * ps] = R1;
+          w[WS_RHO * ps] = rho; w[WS_S15 * ps] = s15;
+        }
+        w[WS_VTR * ps] = v_r; w[WS_VTNR * ps] = v_nr; w[WS_VTI * ps] = v_i; w[WS_VTNI * ps] = v_ni;
+        w[WS_VTS * ps] = v_s; w[WS_VTG * ps] = v_g;
+      }
+    }
+    const float* rhoa = w0 + WS_RHO * ps;
+    float ppt_r = 0.f, ppt_i = 0.f, ppt_s = 0.f, ppt_g = 0.f;
+    // all but the last sub-step (rain is never gated by l_sediment, U6; the cloud-water stub M:3414-3425 is a no-op, U2)
+    if (s.n_r > 1) sed_substeps(w0 + WS_RR * ps, w0 + WS_QRTEN * ps, w0 + WS_VTR * ps, w0 + WS_NR * ps, w0 + WS_NRTEN * ps,
+                                w0 + WS_VTNR * ps, rhoa, dzp, dzs, nz, cs, s.n_r - 1, s.ksed_r, s.on_r, DT, true, KP_R2, ppt_r);
+    if (s.n_i > 1) sed_substeps(w0 + WS_RI * ps, w0 + WS_QITEN * ps, w0 + WS_VTI * ps, w0 + WS_NI * ps, w0 + WS_NITEN * ps,
+                                w0 + WS_VTNI * ps, rhoa, dzp, dzs, nz, cs, s.n_i - 1, s.ksed_i, s.on_i, DT, sedi, KP_R2, ppt_i);
+    if (s.n_s > 1) sed_substeps(w0 + WS_RS * ps, w0 + WS_QSTEN * ps, w0 + WS_VTS * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
+                                nz, cs, s.n_s - 1, s.ksed_s, s.on_s, DT, sedi, 0.f, ppt_s);
+    if (s.n_g > 1) sed_substeps(w0 + WS_RG * ps, w0 + WS_QGTEN * ps, w0 + WS_VTG * ps, nullptr, nullptr, nullptr, rhoa, dzp, dzs,
+                                nz, cs, s.n_g - 1, s.ksed_g, s.on_g, DT, sedi, 0.f, ppt_g);
+    // last sub-step of every species + S15 + S16, one top-down sweep
+    SedParams sp;
+    sp.DT = DT; sp.odt = odt; sp.on_r = s.on_r; sp.on_i = s.on_i; sp.on_s = s.on_s; sp.on_g = s.on_g; sp.Nt_c = ck.Nt_c;
+    sp.top_r = s.ksed_r; sp.top_i = s.ksed_i; sp.top_s = s.ksed_s; sp.top_g = s.ksed_g; sp.sedi = sedi; sp.iiwarm = iiwarm;
+    SedCarry c;
+    c.sr_up = 0.f; c.snr_up = 0.f; c.si_up = 0.f; c.sni_up = 0.f; c.ss_up = 0.f; c.sg_up = 0.f;
+    c.ppt_r = ppt_r; c.ppt_i = ppt_i; c.ppt_s = ppt_s; c.ppt_g = ppt_g; c.lwp = 0.0; c.iwp = 0.0;
+    unsigned bw = 0;
+#pragma unroll 1
+    for (int k = nz - 1; k >= 0; --k) {
+      if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
+      const long o = (long)k * ld + col;
+      const float* q = w0 + (size_t)k * cs;
+      HandOff h;
+      h.tt = q[WS_TTEN * ps]; h.qvt = q[WS_QVTEN * ps]; h.qct = q[WS_QCTEN * ps]; h.qit = q[WS_QITEN * ps];
+      h.qrt = q[WS_QRTEN * ps]; h.qst = q[WS_QSTEN * ps]; h.qgt = q[WS_QGTEN * ps]; h.nit = q[WS_NITEN * ps];
+      h.nrt = q[WS_NRTEN * ps]; h.nct = q[WS_NCTEN * ps];
+      h.rho = q[WS_RHO * ps]; h.s15 = q[WS_S15 * ps];
+      h.rr = q[WS_RR * ps]; h.nr = q[WS_NR * ps]; h.ri = q[WS_RI * ps]; h.ni = q[WS_NI * ps]; h.rs = q[WS_RS * ps]; h.rg = q[WS_RG * ps];
+      h.v_r = q[WS_VTR * ps]; h.v_nr = q[WS_VTNR * ps]; h.v_i = q[WS_VTI * ps]; h.v_ni = q[WS_VTNI * ps];
+      h.v_s = q[WS_VTS * ps]; h.v_g = q[WS_VTG * ps];
+      if (RATES && !((bw >> (k & 31)) & 1u)) {           // an idle cell: every process rate is zero
+        float* rp = a.rates + o;
+        const long st = (long)nz * ld;
+        for (int r = 0; r < KIDMP_NRATES; ++r) rp[r * st] = 0.0f;
+      }
+      finish_level(a, sp, c, h, k, nz, o, dzp[k * dzs], a.f[F_T][o], a.f[F_QV][o], a.f[F_QC][o], a.f[F_QI][o], a.f[F_QR][o],
+                   a.f[F_QS][o], a.f[F_QG][o], a.f[F_NI][o], a.f[F_NR][o], a.p[o]);
+    }
+    // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
+    a.ppt[col] = c.ppt_r; a.ppt[ld + col] = c.ppt_i; a.ppt[2 * ld + col] = c.ppt_s; a.ppt[3 * ld + col] = c.ppt_g;
+    a.coldiag[col] = c.lwp; a.coldiag[ncol + col] = c.iwp;      // summed in column order by k_diag_columns
+  }
 }
 
-// ---- K2c: the last (or only) sub-step of every species + S15 instant melt / freeze (M:3584-3606) + S16 (M:3623-3686), one
-// top-down sweep per cloudy column, one warp per block.  The ten inputs and the hand-off of a level are loaded in one batch.
+// ---- K2c: the columns without sub-steps: the only sub-step of every species (M:3365-3578) + S15 instant melt / freeze
+// (M:3584-3606) + S16 (M:3623-3686), one top-down sweep per column, one warp per block.  The ten inputs and the record of a busy
+// level are loaded in one batch; an idle level has no record: its tendencies are zero and its contents R1 / R2.
 #ifndef K2_MINB
-#define K2_MINB 16
+#define K2_MINB 20
 #endif
 template <bool RATES>
 __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
   const int slot = blockIdx.x * 32 + threadIdx.x;
   const int count = *a.work_count;
   if (slot >= count) return;
-  const long col = a.work_list[slot];
   const int nz = a.nz;
-  const long ld = a.ld, ncol = a.ncol;
   const long cs = count;
-  const size_t ps = (size_t)nz * count;
+  const SedCounts s = sed_counts(a.colint + slot, cs, nz);
+  if (s.n_r > 1 || s.n_i > 1 || s.n_s > 1 || s.n_g > 1) return;      // k_substeps has this column
+  const long col = a.work_list[slot];
+  const long ld = a.ld, ncol = a.ncol;
   const float DT = a.dt, odt = 1.f / DT;
   const bool iiwarm = ck.iiwarm != 0;
-  const float* const sc0 = a.scratch + slot;
+  const unsigned* const cidx = a.cellidx + slot;
   const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;
   const long dzs = a.dz_col ? ld : 1;
-  const SedCounts s = sed_counts(a.colint + slot, cs, nz);
-  const bool substeps = s.n_r > 1 || s.n_i > 1 || s.n_s > 1 || s.n_g > 1;
   SedParams sp;
   sp.DT = DT; sp.odt = odt; sp.on_r = s.on_r; sp.on_i = s.on_i; sp.on_s = s.on_s; sp.on_g = s.on_g; sp.Nt_c = ck.Nt_c;
   sp.top_r = s.ksed_r; sp.top_i = s.ksed_i; sp.top_s = s.ksed_s; sp.top_g = s.ksed_g; sp.sedi = ck.l_sediment != 0; sp.iiwarm = iiwarm;
   SedCarry c;
   c.sr_up = 0.f; c.snr_up = 0.f; c.si_up = 0.f; c.sni_up = 0.f; c.ss_up = 0.f; c.sg_up = 0.f;
   c.ppt_r = 0.f; c.ppt_i = 0.f; c.ppt_s = 0.f; c.ppt_g = 0.f; c.lwp = 0.0; c.iwp = 0.0;
-  if (substeps) {
-    const float* pp = a.pptsub + slot;
-    c.ppt_r = pp[0]; c.ppt_i = pp[cs]; c.ppt_s = pp[2 * cs]; c.ppt_g = pp[3 * cs];
-  }
-  float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;       // speeds of the level above (no sub-steps)
+  float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;       // speeds of the level above
   unsigned bw = 0;
+  unsigned idx_next = cidx[(size_t)(nz - 1) * cs];        // (the index of an idle cell is never used)
 #pragma unroll 1
   for (int k = nz - 1; k >= 0; --k) {
     if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
     const long o = (long)k * ld + col;
-    const float* q = sc0 + (size_t)k * cs;
+    const float* q = a.scratch + (size_t)idx_next * SC_REC;
+    if (k > 0) idx_next = cidx[(size_t)(k - 1) * cs];     // in flight while this level is worked on
     const bool busy = ((bw >> (k & 31)) & 1u) != 0;
-    const bool handed = substeps || busy;
     const float t1d = a.f[F_T][o], qv1d = a.f[F_QV][o], qc1d = a.f[F_QC][o], qi1d = a.f[F_QI][o], qr1d = a.f[F_QR][o],
                 qs1d = a.f[F_QS][o], qg1d = a.f[F_QG][o], ni1d = a.f[F_NI][o], nr1d = a.f[F_NR][o], pres = a.p[o];
     HandOff h;
-    if (handed) {
-      h.tt = q[SC_TTEN * ps]; h.qvt = q[SC_QVTEN * ps]; h.qct = q[SC_QCTEN * ps]; h.qit = q[SC_QITEN * ps];
-      h.qrt = q[SC_QRTEN * ps]; h.qst = q[SC_QSTEN * ps]; h.qgt = q[SC_QGTEN * ps]; h.nit = q[SC_NITEN * ps];
-      h.nrt = q[SC_NRTEN * ps]; h.nct = q[SC_NCTEN * ps];
-      h.rho = q[SC_RHO * ps]; h.s15 = q[SC_S15 * ps];
-      h.rr = q[SC_RR * ps]; h.nr = q[SC_NR * ps]; h.ri = q[SC_RI * ps]; h.ni = q[SC_NI * ps]; h.rs = q[SC_RS * ps]; h.rg = q[SC_RG * ps];
-      // (the snow / graupel speed planes are only written where the species is present: the value is only used there)
-      const float o_vr = q[SC_VTR * ps], o_vnr = q[SC_VTNR * ps], o_vi = q[SC_VTI * ps], o_vni = q[SC_VTNI * ps],
-                  o_vs = q[SC_VTS * ps], o_vg = q[SC_VTG * ps];
-      if (substeps) {
-        v_r = o_vr; v_nr = o_vnr; v_i = o_vi; v_ni = o_vni; v_s = o_vs; v_g = o_vg;
-      } else {
-        if (h.rr > R1) { v_r = o_vr; v_nr = o_vnr; }
-        if (!iiwarm) {
-          if (h.ri > R1) { v_i = o_vi; v_ni = o_vni; }
-          if (h.rs > R1) v_s = o_vs;
-          if (h.rg > R1) v_g = o_vg;
-        }
+    if (busy) {
+      const Sector s0 = ld_sector(q), s1 = ld_sector(q + 8), s2 = ld_sector(q + 16), s3 = ld_sector(q + 24);   // the 128-byte record
+      h.tt = s0.v[0]; h.qvt = s0.v[1]; h.qct = s0.v[2]; h.qit = s0.v[3]; h.qrt = s0.v[4]; h.qst = s0.v[5]; h.qgt = s0.v[6]; h.nit = s0.v[7];
+      h.nrt = s1.v[0]; h.nct = s1.v[1]; h.nr = s1.v[2]; h.ni = s1.v[3];
+      h.rr = s2.v[0]; h.ri = s2.v[1]; h.rs = s2.v[2]; h.rg = s2.v[3];
+      h.rho = s2.v[7]; h.s15 = s3.v[0];
+      if (h.rr > R1) { v_r = s2.v[4]; v_nr = s2.v[5]; }
+      if (!iiwarm) {
+        if (h.ri > R1) { v_i = s2.v[6]; v_ni = s1.v[4]; }
+        if (h.rs > R1) v_s = s3.v[6];                     // (written by k_carries where the species is present)
+        if (h.rg > R1) v_g = s3.v[7];
       }
     } else {
       h.tt = 0.f; h.qvt = 0.f; h.qct = 0.f; h.qit = 0.f; h.qrt = 0.f; h.qst = 0.f; h.qgt = 0.f; h.nit = 0.f; h.nrt = 0.f; h.nct = 0.f;
       h.rr = R1; h.nr = R2; h.ri = R1; h.ni = R2; h.rs = R1; h.rg = R1;
       idle_record(t1d, pres, qv1d, h.rho, h.s15);
-    }
-    if (RATES && !busy) {                                 // an idle cell: every process rate is zero
-      float* rp = a.rates + o;
-      const long st = (long)nz * ld;
-      for (int r = 0; r < KIDMP_NRATES; ++r) rp[r * st] = 0.0f;
+      if (RATES) {                                        // an idle cell: every process rate is zero
+        float* rp = a.rates + o;
+        const long st = (long)nz * ld;
+        for (int r = 0; r < KIDMP_NRATES; ++r) rp[r * st] = 0.0f;
+      }
     }
     h.v_r = v_r; h.v_nr = v_nr; h.v_i = v_i; h.v_ni = v_ni; h.v_s = v_s; h.v_g = v_g;
     finish_level(a, sp, c, h, k, nz, o, dzp[k * dzs], t1d, qv1d, qc1d, qi1d, qr1d, qs1d, qg1d, ni1d, nr1d, pres);

@@ -155,7 +155,7 @@ enum { F_QV = 0, F_QC, F_QI, F_QR, F_QS, F_QG, F_NI, F_NR, F_T };
 // `no_micro` (M:1396-1521; the early RETURN at M:1540), writes back the species <= R1 that the
 // reference zeroes in the caller's arrays before returning (M:1412-1489, U9), marks clear-sky columns
 // in colflag and leaves the ballot of the cloudy lanes of every 32-column group for the work list.
-// Every cell also gets its class byte: species present, ice supersaturation, and the cell kernel that takes it.
+// Every cell also gets its class byte: species present, ice supersaturation, below 0 C (k_cell_* sort the busy cells by it).
 // A cell is BUSY (some process rate can be non-zero) when it holds a hydrometeor, or ssati > 0, or ssatw > eps
 // (each rate is gated by a species flag or by ssati / ssatw, M:1676-2286, M:2780, M:2880); at or below 0 C
 // ssatw > eps implies ssati > 0 because e_s(ice) <= e_s(liquid) for both polynomials over their whole range
@@ -173,7 +173,6 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
   const bool in_range = col < a.ncol;
   const int nz = a.nz;
   const long ncol = a.ncol, ld = a.ld;
-  const bool iiwarm = ck.iiwarm != 0;
   bool active = false;
   if (in_range) {
     const float* __restrict__ Gp = a.p + col;
@@ -205,7 +204,8 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
       if (fabsf(ssati) < EPSF) ssati = 0.0f;
       unsigned c = sp;
       if (ssati > 0.0f) c |= CLS_VAP;
-      if (c) { no_micro = false; c |= (unsigned)cell_kernel_class(sp, t < T_0, iiwarm) << CLS_KC_SHIFT; }
+      if (c) no_micro = false;
+      if (t < T_0) c |= 1u << CLS_COLD_SHIFT;
       Gcls[(long)k * ncol] = (unsigned char)c;
     }
     active = !no_micro;

@@ -101,26 +101,29 @@ struct KConst {
   const float* efsw;
 };
 
-// Hand-off between the cell kernels and the column-finish kernel: [SC_NX][nz][count] f32, `count` = cloudy columns of
-// the launch (slot-indexed: lane = slot, so every plane access of the column kernels is one 128-byte line per warp).
-// Written for BUSY cells only (a hydrometeor or supersaturation; every rate of an idle cell is exactly zero).
+// Hand-off between the cell kernels and the column kernels: one 128-byte record (32 f32, SC_* = offset in the record) per
+// BUSY cell (a hydrometeor or supersaturation; every rate of an idle cell is exactly zero), in the order of the cell list.
+// A record is one cache line: the cell kernels write it with eight 16-byte stores, the column kernels read it with
+// 16-byte loads, and the DRAM traffic is the record itself whatever the order of the cells; cellidx[k][slot] is the record
+// number of a cell.  Sector 0-1: what only k_finish reads; sector 2-3: everything k_carries reads.
 //   SC_TTEN..SC_NCTEN  the ten tendencies after S12
-//   SC_RR..SC_RG       contents at tau+1 (M:2602-2656 and the in-place refreshes of S11 / S12)
-//   SC_VTR..SC_VTNI    the cell's own fall speeds (0 without the species: k_finish applies the rule of the level above)
-//   SC_VTS, SC_VTG     written by sweep A of k_finish (final snow / graupel speed of the level)
+//   SC_RR..SC_RG, SC_NR, SC_NI  contents at tau+1 (M:2602-2656 and the in-place refreshes of S11 / S12)
+//   SC_VTR..SC_VTNI    the cell's own fall speeds (0 without the species: k_carries applies the rule of the level above)
+//   SC_VTS, SC_VTG     written by k_carries (final snow / graupel speed of the level)
 //   SC_RHO, SC_S15     air density at tau+1; signed latent-heat factor of S15
 //   SC_N0A             in: running minimum of the graupel intercept of S4 (k_n0_sweep); out: S10's intercept without
 //                      supercooled rain, negated when the level's updated temperature is >= 270.65 K
 //   SC_N0B_SLW         S10's intercept with supercooled rain; SC_VTS_RAW / SC_VTS_BOOST / SC_TEMP for the snow speed rule
-enum { SC_TTEN = 0, SC_QVTEN, SC_QCTEN, SC_QITEN, SC_QRTEN, SC_QSTEN, SC_QGTEN, SC_NITEN, SC_NRTEN, SC_NCTEN,
-       SC_RR, SC_NR, SC_RI, SC_NI, SC_RS, SC_RG, SC_VTR, SC_VTNR, SC_VTI, SC_VTNI, SC_VTS, SC_VTG, SC_RHO, SC_S15, SC_N,
-       SC_N0A = SC_N, SC_N0B_SLW, SC_VTS_RAW, SC_VTS_BOOST, SC_TEMP, SC_NX };
+enum { SC_TTEN = 0, SC_QVTEN, SC_QCTEN, SC_QITEN, SC_QRTEN, SC_QSTEN, SC_QGTEN, SC_NITEN,
+       SC_NRTEN = 8, SC_NCTEN, SC_NR, SC_NI, SC_VTNI,
+       SC_RR = 16, SC_RI, SC_RS, SC_RG, SC_VTR, SC_VTNR, SC_VTI, SC_RHO,
+       SC_S15 = 24, SC_N0A, SC_N0B_SLW, SC_VTS_RAW, SC_VTS_BOOST, SC_TEMP, SC_VTS, SC_VTG, SC_REC = 32 };
 
 // Cell classes: every busy cell goes to the kernel specialised for the smallest species set that covers it
 // (kidmp_cells.cuh).  The class byte of a cell: bits 0-4 qc qi qr qs qg > R1 on input, bit 5 ice supersaturation,
-// bits 6-7 the kernel class; 0 = idle cell.
+// bit 6 T < T_0; (bits 0-5) == 0: idle cell.
 enum { KC_WARM = 0, KC_ICE = 1, KC_MIXNR = 2, KC_FULL = 3, KC_N = 4 };
-enum { CLS_QC = 1, CLS_QI = 2, CLS_QR = 4, CLS_QS = 8, CLS_QG = 16, CLS_VAP = 32, CLS_BUSY = 63, CLS_KC_SHIFT = 6 };
+enum { CLS_QC = 1, CLS_QI = 2, CLS_QR = 4, CLS_QS = 8, CLS_QG = 16, CLS_VAP = 32, CLS_BUSY = 63, CLS_COLD_SHIFT = 6 };
 enum { LIST_TILE = 256 };          // columns per block of the cell-list kernels
 
 enum { DIAG_BLOCKS = 296 };
@@ -135,21 +138,26 @@ struct StepArgs {
   const float* dz;             // [nz] layer depths shared by all columns (KiD, I:63) ...
   const float* dz_col;         // ... or [nz][ld] per column (WRF's dz(i,k,j), M:944); NULL when dz is used
   float* ppt;                  // [4][ld]
-  float* scratch;              // [SC_NX][nz][count] hand-off (see SC_*)
+  float* scratch;              // [records][SC_REC] hand-off (see SC_*): one record per busy cell, in the order of cell_list
+  unsigned* cellidx;           // [nz][count] record number of every busy cell of the cloudy columns
+  float* ws;                   // [WS_N][nz][ws_cols] SoA workspace of the columns with sedimentation sub-steps (k_substeps)
+  long ws_cols;
   unsigned char* cls;          // [nz][ncol] class byte of every cell (0 = idle)
   int* colflag;                // [ncol] -1 clear sky (the early RETURN of M:1540), else bit 0 = graupel somewhere in the column
   int* work_count;             // number of cloudy columns found by the classification kernel
   int* work_list;              // their column indices, compacted in column order (slot -> column)
   unsigned* work_mask;         // [ngroups] ballot of the cloudy lanes of every 32-column group
   int* work_offset;            // [ngroups] exclusive prefix sum of the ballots' popcounts
-  unsigned* cell_list;         // [<= nz*ncol] busy cells, class after class, entry = k * count + slot
-  int* cell_count;             // [KC_N] busy cells of each class
-  int* cell_base;              // [list blocks][KC_N] first entry of a block's cells inside its class segment
+  unsigned* cell_list;         // [<= nz*ncol] busy cells, sort key after sort key, entry = k * count + slot
+  int* cell_hist;              // [64] busy cells of each sort key (species bits, T < T_0)
+  int* cell_start;             // [64] first entry of each key
+  int* cell_count;             // [KC_N] busy cells of each kernel class (+ [KC_N]: all busy cells) ...
+  int* cell_kstart;            // [KC_N] ... and its first entry (the keys of a class are next to each other)
+  int* cell_base;              // [32-column groups][64] first entry of a group's cells inside the segment of their key
   unsigned* busy;              // [ceil(nz/32)][count] busy bits of every cloudy column (bit k%32 of word k/32)
   int* colint;                 // [8][count] sub-step counts and top sedimenting levels of rain, ice, snow, graupel
   int* sub_count;              // columns that need sedimentation sub-steps (nstep > 1, M:3242) ...
   int* sub_list;               // ... their slots
-  float* pptsub;               // [4][count] precipitation of all but the last sub-step of those columns
   float* rates;                // optional [36][nz][ld]
   double* coldiag;             // [2][ncol] liquid / ice water path of each cloudy column
   double* diag_partial;        // [DIAG_BLOCKS][KIDMP_NDIAG] block sums of k_diag_columns

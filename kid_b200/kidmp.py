@@ -53,6 +53,7 @@ SYMBOLS = {
     "kidmp_diag": (C.c_int, [C.c_void_p, _dp]),
     "kidmp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "kidmp_gpu_launches": (C.c_long, [C.c_void_p]),
+    "kidmp_step_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_long)]),
     "kidmp_sync": (C.c_int, [C.c_void_p]),
     "kidmp_last_step_ms": (C.c_int, [C.c_void_p, _fp]),
     "kidmp_tables_from_cache": (C.c_int, [C.c_void_p]),
@@ -310,6 +311,14 @@ class Thompson:
         out = np.zeros(NDIAG, np.float64)
         self._ck(self._L.kidmp_diag(self.h, out.ctypes.data_as(_dp)))
         return out
+
+    def step_stats(self):
+        """Counts of the last launch of the step kernels: cloudy columns, busy cells (total and per cell kernel), columns
+        with sedimentation sub-steps."""
+        out = (C.c_long * 8)()
+        self._ck(self._L.kidmp_step_stats(self.h, out))
+        names = ("cloudy_columns", "busy_cells", "cells_warm", "cells_ice", "cells_mixed_no_rain", "cells_full", "substep_columns")
+        return {n: int(out[i]) for i, n in enumerate(names)}
 
     def sync(self):
         self._ck(self._L.kidmp_sync(self.h))

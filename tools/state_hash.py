@@ -42,4 +42,8 @@ for k in FIELDS:
 h.update(ppt.cpu().numpy().tobytes())
 print("lib", os.environ.get("KIDMP_LIB", "in-tree"), "columns", a.columns, "steps", a.steps, "dt", a.dt, "dz", a.dz,
       "warm", a.warm, "sha256", h.hexdigest()[:32], "ms", " ".join("%.2f" % x for x in ms))
+try:
+    print("   stats", th.step_stats())
+except Exception as e:      # a library of an earlier round
+    pass
 th.close()
