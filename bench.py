@@ -6,13 +6,15 @@
 
 Workload (BASELINE.json configs[3]): synthetic 1024x1024 = 1 048 576 columns x 60 levels per GPU from
 the seeded CONUS-like convective domain of kid_b200/synth.py (about 30 % cloudy columns), dt = 10 s.
-Weak scaling: every rank owns its own 1 048 576 columns [rank*ncol, (rank+1)*ncol) of one global
-domain; columns are independent, so there is no data-path collective - NCCL only reduces the eight
-domain diagnostics once per run.
+Default = weak scaling: every rank owns its own 1 048 576 columns [rank*ncol, (rank+1)*ncol) of one global
+domain.  --total-columns N = strong scaling (BASELINE.json configs[4]: N = 16 777 216 = 4096x4096): the N columns of one
+domain are cut into contiguous shards, one per rank (kid_b200/shard.py).  Columns are independent, so there is no
+data-path collective - NCCL only reduces the eight domain diagnostics once per run.
 
-A "step" = one kidmp_step_device call (seven launches: classification, scan + fill of the work list, column physics
-and sedimentation + final clamps on the compacted list of cloudy columns, ordered domain sums and their reduce) over all resident columns; the state evolves in place from step to step like a model time loop.
-Inputs (2.8 GB per GPU) are far larger than L2, so no flush is needed between steps.
+A "step" = one kidmp_step_device call over all resident columns: classification, work list and sorted list of the busy
+cells, the four cell kernels (S1..S13 of every busy cell), what runs down the columns, sedimentation + final clamps,
+ordered domain sums (16 launches per chunk of 1 048 576 columns); the state evolves in place from step to step like a
+model time loop.  Inputs (2.8 GB per GPU) are far larger than L2, so no flush is needed between steps.
 """
 import argparse
 import json
@@ -32,10 +34,26 @@ UNIT = "column-steps/s"
 ALG_BYTES_PER_COLUMN = 4576          # 10 fields read + 9 written + 4 precip scalars, nz=60
 NZ = 60
 DT = 10.0
-# dram__bytes_read.sum + dram__bytes_write.sum of the step kernels from the ncu --set full captures of the same workload
-# (profiles/r01_ncu_step_kernels.md, reports prof_r1g / prof_r1i): 2.52+0.02 (classify) + 1.24+2.35 (physics) +
-# 3.46+0.71 (sedimentation) + 0.02 (ordered domain sums) GB
-TRAFFIC_BYTES_PER_LAUNCH = 10.15e9
+# dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one step of this workload, from the committed ncu launch
+# list of this round (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the CSV next to it)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
+
+
+def measured_traffic():
+    try:
+        with open(TRAFFIC_FILE) as f:
+            t = json.load(f)
+        return float(t["bytes_per_step"]), {"file": "profiles/r02_traffic.json", "commit": t.get("commit"), "per_kernel_MB": t.get("per_kernel_MB")}
+    except Exception as e:
+        return None, {"file": "profiles/r02_traffic.json", "error": str(e)}
+
+
+def fortran_probe():
+    """Is there a Fortran compiler on this box?  With one, oracle/ref builds the reference itself."""
+    import shutil
+    tried = ("gfortran", "flang", "flang-new", "nvfortran", "ifx", "ifort", "f95", "pgfortran")
+    found = [c for c in tried if shutil.which(c)]
+    return {"found": found, "tried": list(tried)}
 
 
 def peaks():
@@ -125,6 +143,7 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     ncol = args.cpu_columns
+    probe = fortran_probe()
     v, ms, init_s = cpu_reference_run(ncol, args.steps, args.warmup, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -132,14 +151,32 @@ def run_reference(args, rank, world):
         "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": "synthetic 1024x1024 columns x 60 levels, CONUS-like convective domain, dt=10s",
                    "sample_columns": ncol, "nz": NZ, "dt": DT},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "first %d columns of the bench domain x %d steps, OpenMP over columns; C++ restatement "
-                                   "of the reference (no Fortran compiler on the box), table init %.1f s excluded"
-                                   % (ncol, args.steps, init_s)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "fortran_probe": probe,
+                         "sample": "first %d columns of the bench domain x %d steps (a rate: the full workload has 1 048 576), "
+                                   "OpenMP over columns on %d threads; C++ restatement of the reference built -O3 without "
+                                   "fast-math (no Fortran compiler on this box: see fortran_probe), table init %.1f s excluded"
+                                   % (ncol, args.steps, cores, init_s)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def make_resident_domain(synth, ncol, col0, nx, dev, slab=1 << 20):
+    """kid_b200/synth.py domain [col0, col0+ncol) on the device, generated slab by slab into preallocated tensors."""
+    import torch
+    from kid_b200.kidmp import FIELDS
+    st = {k: torch.empty((NZ, ncol), dtype=torch.float32, device=dev) for k in FIELDS}
+    p = torch.empty((NZ, ncol), dtype=torch.float32, device=dev)
+    dz = None
+    for c in range(0, ncol, slab):
+        n = min(slab, ncol - c)
+        s1, p1, dz = synth.make_domain(n, nz=NZ, col0=col0 + c, nx=nx, device=dev)
+        for k in FIELDS:
+            st[k][:, c:c + n] = s1[k]
+        p[:, c:c + n] = p1
+        del s1, p1
+    return st, p, dz
 
 
 def main():
@@ -148,7 +185,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kidmp", choices=["kidmp", "reference"])
-    ap.add_argument("--columns", type=int, default=1024 * 1024, help="columns per GPU")
+    ap.add_argument("--columns", type=int, default=1024 * 1024, help="columns per GPU (weak scaling)")
+    ap.add_argument("--total-columns", type=int, default=0, help="columns of the whole domain, sharded over the GPUs (strong scaling)")
     ap.add_argument("--cpu-columns", type=int, default=262144, help="columns of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -175,10 +213,17 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    ncol = args.columns
+    strong = args.total_columns > 0
+    if strong:
+        from kid_b200.shard import shard_range
+        col0, col1 = shard_range(args.total_columns, rank, world)
+        ncol, nxdom = col1 - col0, int(round(args.total_columns ** 0.5))
+    else:
+        ncol, col0, nxdom = args.columns, rank * args.columns, 1024
+    total_cols = args.total_columns if strong else world * ncol
     th = Thompson(set_Nc=100.0, iiwarm=False, l_sediment=True, device=local)
-    # synthetic state generated directly in HBM, this rank's shard of the global domain
-    st, p, dz = synth.make_domain(ncol, nz=NZ, col0=rank * ncol, nx=1024, device=dev)
+    # synthetic state generated directly in HBM, this rank's shard of the global domain (in slabs: the generator's temporaries)
+    st, p, dz = make_resident_domain(synth, ncol, col0, nxdom, dev)
     presence = synth.stats(st)
     ppt = torch.zeros((4, ncol), dtype=torch.float32, device=dev)
     tstream = torch.cuda.Stream(device=dev)             # the launching stream: kernels and timing events both go here
@@ -226,13 +271,26 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms = float(tmax.item())
     ms_per_step = total_ms / args.steps
-    value = world * ncol * args.steps / (total_ms * 1e-3)
+    value = total_cols * args.steps / (total_ms * 1e-3)
+    stats = th.step_stats()
+    # per-kernel device times: three more steps with the kernels of a launch one after the other and an event after each
+    th.set_option("timing", 1)
+    kms = {}
+    for _ in range(3):
+        one_step()
+        torch.cuda.synchronize()
+        for k, v in th.last_kernel_ms().items():
+            kms[k] = kms.get(k, 0.0) + v / 3.0
+    th.set_option("timing", 0)
 
     # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernel + D2H every step) --------
     e2e = None
     if args.e2e_steps > 0:
+        ncol_full = ncol
+        ncol = min(ncol, 1 << 20)                        # strong scaling with larger shards: the first 1 048 576 columns of the shard
         host = {k: torch.empty((NZ, ncol), dtype=torch.float32).pin_memory() for k in FIELDS}
-        st0, p0, dz0 = synth.make_domain(ncol, nz=NZ, col0=rank * ncol, nx=1024, device=dev)
+        del st, p
+        st0, p0, dz0 = make_resident_domain(synth, ncol, col0, nxdom, dev)
         for k in FIELDS:
             host[k].copy_(st0[k])
         hp = torch.empty((NZ, ncol), dtype=torch.float32).pin_memory()
@@ -253,27 +311,47 @@ def main():
         el = float(tm.item())
         e2e = {"value": world * ncol * args.e2e_steps / el, "unit": UNIT,
                "h2d_bytes_per_step": int(ncol * NZ * 4 * 10 + NZ * 4), "d2h_bytes_per_step": int(ncol * NZ * 4 * 9 + ncol * 16),
-               "steps": args.e2e_steps, "ms_per_step": el / args.e2e_steps * 1e3,
+               "steps": args.e2e_steps, "ms_per_step": el / args.e2e_steps * 1e3, "columns_per_gpu": ncol,
                "api": "kidmp_step (host arrays, COL_FASTEST, pinned)"}
+        ncol = ncol_full
 
     if rank == 0:
         peak, peak_src = peaks()
         kern_ms = float(np.mean(per_step))
         achieved = ALG_BYTES_PER_COLUMN * ncol / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic()
+        if ncol != 1048576:
+            traffic, traffic_src = None, {"note": "measured for the 1 048 576-column workload only"}
+        # algorithmic bytes of the streaming kernels (the cell kernels are bound by instruction issue, not by memory):
+        # classification reads the ten fields of every column; the finish kernels read them again and write nine for the
+        # cloudy columns; per busy cell a 128-byte record is written once and read 1.5 times
+        busy, cloudy = stats["busy_cells"], stats["cloudy_columns"]
+        ksum = sum(kms.values()) or 1.0
+        kalg = {"classify": 40.0 * NZ * ncol, "carries": 64.0 * busy, "finish": (76.0 * NZ + 16.0) * cloudy + 128.0 * busy}
+        kernels = {k: {"ms": round(v, 4), "share": round(v / ksum, 4)} for k, v in kms.items()}
+        for k, b in kalg.items():
+            if kms.get(k):
+                kernels[k]["alg_bytes"] = b
+                kernels[k]["frac"] = round(b / (kms[k] * 1e-3) / 1e9 / peak, 4)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": "synthetic 1024x1024 columns x 60 levels per GPU, CONUS-like convective domain "
+            "config": {"workload": ("synthetic %d columns x 60 levels sharded over the GPUs" % total_cols if strong else
+                                    "synthetic 1024x1024 columns x 60 levels per GPU") + ", CONUS-like convective domain "
                                    "(kid_b200/synth.py seed 20261018), dt=10s, state evolves in place",
-                       "columns_per_gpu": ncol, "nz": NZ, "dt": DT, "l2": "inputs (2.8 GB/GPU) larger than L2, no flush",
-                       "presence": presence,
+                       "columns_per_gpu": ncol, "total_columns": total_cols, "nz": NZ, "dt": DT,
+                       "l2": "inputs (2.8 GB per 1 048 576 columns) larger than L2, no flush",
+                       "presence": presence, "step_stats_rank0_last_chunk": stats,
                        "active_column_fraction": float(diag[6].item() / max(diag[7].item(), 1.0))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src,
-                         "kernel": "one step = k_classify + k_list_scan/fill + k_column_step<24,1,11> + k_sediment + k_diag_columns/reduce (k_column_step is 79 % of it); "
-                                   "achieved and traffic are for the whole step, the unit the algorithmic bytes are defined on",
-                         "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_COLUMN * ncol},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "one step = the sixteen launches of kidmp_step_device (cell kernels k_cells<warm|ice|mixed|full> "
+                                   "are about half of it); achieved and traffic are for the whole step on this rank, the unit the "
+                                   "algorithmic bytes are defined on",
+                         "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_COLUMN * ncol,
+                         "kernels": kernels,
+                         "kernels_note": "timing mode: kernels serialised with an event after each group, mean of 3 steps"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "diag": {"names": ["ppt_rain", "ppt_ice", "ppt_snow", "ppt_graupel", "lwp", "iwp", "active", "columns"],
                      "sum_over_steps": [float(x) for x in diag.tolist()]},
@@ -282,10 +360,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, ms, init_s = cpu_reference_run(args.cpu_columns, 10, 1, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "first %d columns of the bench domain x 10 steps, OpenMP over columns; C++ "
-                                              "restatement of the reference (no Fortran compiler), init %.1f s excluded"
-                                              % (args.cpu_columns, init_s)}
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "fortran_probe": fortran_probe(),
+                                    "sample": "first %d columns of the bench domain x 10 steps (a rate), OpenMP over columns on %d "
+                                              "threads; C++ restatement of the reference built -O3 without fast-math (no Fortran "
+                                              "compiler on this box: see fortran_probe), init %.1f s excluded"
+                                              % (args.cpu_columns, cores, init_s)}
         print(json.dumps(line), flush=True)
     th.close()
     if world > 1:

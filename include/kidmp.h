@@ -137,14 +137,11 @@ typedef struct kidmp_wrf_fields {
 } kidmp_wrf_fields;
 int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in);
 
-/* Tuning knobs; results do not depend on them.  "fuse": how the step treats sedimentation - 0 = physics and
- * sedimentation as two kernels with a hand-off buffer, 2 = sedimentation fused into the physics kernel and the
- * columns that need sub-steps (nstep > 1, M:3242) redone by the two-kernel path, 1 = fused when the step before
- * had no column with sub-steps, else two kernels (default, or the KIDMP_FUSE environment variable), -1 = back to
- * the default.
- * "units": which physics kernel - 1 = the unit-parallel one (a warp's unit of work is 32 neighbouring columns x ONE
- * level, only units with a busy cell run; the better choice up to ~130 000 columns, i.e. for every KiD case), 0 = the
- * column-walk kernel, -1 = by domain size (default, or the KIDMP_UNITS environment variable). */
+/* Tuning knobs; results do not depend on them.
+ * "chunk": columns per launch of the step kernels (default 1 048 576, or the KIDMP_CHUNK environment variable): the work
+ * buffers (128-byte hand-off records, cell lists) are sized for one chunk, whatever the size of the domain.
+ * "timing": 1 = run the kernels of a launch one after the other with an event after each (kidmp_last_kernel_ms), 0 = normal.
+ * "fuse", "units": knobs of the round-1 kernels, accepted and ignored. */
 int kidmp_set_option(kidmp_handle* h, const char* name, int value);
 
 /* bookkeeping for benchmarks */
@@ -152,6 +149,12 @@ long kidmp_gpu_launches(const kidmp_handle* h);         /* kernels launched so f
 /* counts of the last launch of the step kernels (the last chunk of the last step; waits for it): 0 cloudy columns, 1 busy
  * cells, 2-5 busy cells of the warm / ice / mixed-without-rain / full cell kernels, 6 columns with sedimentation sub-steps */
 int kidmp_step_stats(kidmp_handle* h, long out[8]);
+/* per-kernel device times of the last launch of the step kernels, after kidmp_set_option(h, "timing", 1): in that mode the
+ * kernels of a launch run one after the other on one stream with a CUDA event after each group (normally two of them run
+ * beside others on a second stream), so the sum is a little above the time of a normal step.  Names, comma-separated, in
+ * the order of the values: kidmp_kernel_names(). */
+const char* kidmp_kernel_names(void);
+int kidmp_last_kernel_ms(kidmp_handle* h, float* out, int n);
 int kidmp_sync(kidmp_handle* h);                        /* wait for the handle's stream     */
 int kidmp_last_step_ms(kidmp_handle* h, float* step_ms);  /* CUDA events around the last step */
 int kidmp_tables_from_cache(const kidmp_handle* h);     /* 1 if init read the table cache   */

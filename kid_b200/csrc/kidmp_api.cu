@@ -21,6 +21,9 @@
 
 using namespace kidmp;
 
+// kernel groups of one launch, in launch order (kidmp_kernel_names / kidmp_last_kernel_ms)
+enum { KT_CLASSIFY = 0, KT_LISTS, KT_N0, KT_WARM, KT_ICE, KT_MIXNR, KT_FULL, KT_CARRIES, KT_SUBSTEPS, KT_FINISH, KT_DIAG, KT_N };
+
 struct kidmp_handle {
   int nsm = 148;
   kidmp_config cfg;
@@ -50,9 +53,13 @@ struct kidmp_handle {
   unsigned* d_cells = nullptr;                            // [nz*cols] busy cells, class after class
   int* d_cellmeta = nullptr;                              // [192 | groups*64] class / key totals and starts, per-group bases
   unsigned* d_cellidx = nullptr;                          // [nz*cols] record number of every busy cell
+  float* d_n0a = nullptr;                                 // [nz*cols] graupel intercept minima of S4
   float* d_ws = nullptr;                                  // [24][nz][cols] SoA workspace of the columns with sedimentation sub-steps
   cudaStream_t aux = nullptr;                             // k_substeps runs beside k_finish
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_dag[4] = {};
+  // "timing" option: the kernels of a launch run one after the other on one stream with an event after each
+  bool timing = false; bool timing_valid = false;
+  cudaEvent_t ev_k[KT_N + 1] = {};
   double* d_coldiag = nullptr;                            // [2][cols] per-column water paths for the ordered domain sums
   int* d_colwork = nullptr;                               // [8 busy words | 8 colint | sub list | 4 pptsub][cols] of the column kernels
   long work_cols = 0; int work_nz = 0;
@@ -238,10 +245,10 @@ int ensure_work(kidmp_handle* h, long cols, int nz) {
   const long C = cols > h->work_cols ? cols : h->work_cols;
   const int Z = nz > h->work_nz ? nz : h->work_nz;
   CK(h, cudaDeviceSynchronize());                    // nothing may still be reading the buffers that go away
-  void* old[] = {h->d_scratch, h->d_cls, h->d_colflag, h->d_work, h->d_cells, h->d_cellmeta, h->d_coldiag, h->d_colwork, h->d_cellidx, h->d_ws};
+  void* old[] = {h->d_scratch, h->d_cls, h->d_colflag, h->d_work, h->d_cells, h->d_cellmeta, h->d_coldiag, h->d_colwork, h->d_cellidx, h->d_ws, h->d_n0a};
   for (void* q : old) if (q) cudaFree(q);
   h->d_scratch = nullptr; h->d_cls = nullptr; h->d_colflag = nullptr; h->d_work = nullptr; h->d_cells = nullptr;
-  h->d_cellmeta = nullptr; h->d_coldiag = nullptr; h->d_colwork = nullptr; h->d_cellidx = nullptr; h->d_ws = nullptr; h->work_cols = 0; h->work_nz = 0;
+  h->d_cellmeta = nullptr; h->d_coldiag = nullptr; h->d_colwork = nullptr; h->d_cellidx = nullptr; h->d_ws = nullptr; h->d_n0a = nullptr; h->work_cols = 0; h->work_nz = 0;
   const size_t cells = (size_t)C * Z;
   const long ngroups = (C + 31) / 32, lblocks = (C + LIST_TILE - 1) / LIST_TILE;
   CK(h, cudaMalloc((void**)&h->d_scratch, cells * SC_REC * 4));
@@ -251,6 +258,7 @@ int ensure_work(kidmp_handle* h, long cols, int nz) {
   CK(h, cudaMalloc((void**)&h->d_cells, cells * 4));
   CK(h, cudaMalloc((void**)&h->d_cellidx, cells * 4));
   CK(h, cudaMalloc((void**)&h->d_ws, cells * WS_N * 4));
+  CK(h, cudaMalloc((void**)&h->d_n0a, cells * 4));
   CK(h, cudaMalloc((void**)&h->d_cellmeta, (size_t)(192 + lblocks * (LIST_TILE / 32) * 64) * 4));
   CK(h, cudaMalloc((void**)&h->d_coldiag, (size_t)C * 2 * 8));
   CK(h, cudaMalloc((void**)&h->d_colwork, (size_t)C * 17 * 4));
@@ -298,11 +306,16 @@ int ensure_work(kidmp_handle* h, long cols, int nz) {
 #endif
 
 template <bool RATES>
-void launch_cells(const StepArgs& a, int nsm, cudaStream_t s) {
+void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s) {
+  auto mark = [&](int q) { if (h->timing) cudaEventRecord(h->ev_k[q + 1], s); };
   k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, KC_WARM_BARS, RATES><<<nsm * KC_WARM_B, KC_WARM_T, 0, s>>>(a);
+  mark(KT_WARM);
   k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, KC_ICE_BARS, RATES><<<nsm * KC_ICE_B, KC_ICE_T, 0, s>>>(a);
+  mark(KT_ICE);
   k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES><<<nsm * KC_MIXNR_B, KC_MIXNR_T, 0, s>>>(a);
+  mark(KT_MIXNR);
   k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES><<<nsm * KC_FULL_B, KC_FULL_T, 0, s>>>(a);
+  mark(KT_FULL);
 }
 
 // One step over [ncol] columns whose arrays have row stride ld, in launches of at most chunk_cols columns (the work
@@ -332,29 +345,54 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     a.cell_list = h->d_cells; a.cell_count = h->d_cellmeta; a.sub_count = h->d_cellmeta + 5; a.cell_kstart = h->d_cellmeta + 8;
     a.cell_hist = h->d_cellmeta + 64; a.cell_start = h->d_cellmeta + 128; a.cell_base = h->d_cellmeta + 192;
     a.busy = (unsigned*)h->d_colwork; a.colint = h->d_colwork + 8 * h->work_cols; a.sub_list = h->d_colwork + 16 * h->work_cols;
-    a.ws = h->d_ws; a.ws_cols = h->work_cols;
+    a.ws = h->d_ws; a.ws_cols = h->work_cols; a.n0a = h->d_n0a;
     a.coldiag = h->d_coldiag; a.diag_partial = h->d_partial; a.nsm = h->nsm;
+    // second stream of the launch; in timing mode everything runs on `s`, one kernel after the other
+    cudaStream_t x = h->timing ? s : h->aux;
+    auto mark = [&](int q) { if (h->timing) cudaEventRecord(h->ev_k[q + 1], s); };
+    auto fork = [&](cudaEvent_t e, cudaStream_t from, cudaStream_t to) {
+      if (from != to) { cudaEventRecord(e, from); cudaStreamWaitEvent(to, e, 0); }
+    };
     CK(h, cudaMemsetAsync(h->d_cellmeta, 0, 128 * 4, s));
+    if (h->timing) CK(h, cudaEventRecord(h->ev_k[0], s));
     k_classify<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
+    mark(KT_CLASSIFY);
+    // Two independent chains after the classification.  This stream: the work list of the cloudy columns, then the list of
+    // the busy cells.  Second stream: the key histogram of the busy cells (needs the class bytes only), then the graupel
+    // intercept sweep (needs the work list only; the cell kernels wait for it).
+    fork(h->ev_dag[0], s, x);
+    k_cell_count<<<(unsigned)lblocks, LIST_TILE, 0, x>>>(a);
+    k_cell_offsets<<<1, 64, 0, x>>>(a);
     k_list_scan<<<1, 1024, 0, s>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
     k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
-    k_cell_count<<<(unsigned)lblocks, LIST_TILE, 0, s>>>(a);
-    k_cell_offsets<<<1, 64, 0, s>>>(a);
-    k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, s>>>(a);
-    // the number of cloudy columns is only known on the device: grids for the worst case, surplus blocks leave at once
-    if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
-    if (a.rates) launch_cells<true>(a, h->nsm, s); else launch_cells<false>(a, h->nsm, s);
+    if (h->timing) {
+      k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, s>>>(a);
+      mark(KT_LISTS);
+      if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
+      mark(KT_N0);
+    } else {
+      fork(h->ev_dag[1], x, s);                      // (recorded after k_cell_offsets)
+      fork(h->ev_dag[2], s, x);                      // (recorded after k_list_fill)
+      // the number of cloudy columns is only known on the device: grids for the worst case, surplus blocks leave at once
+      if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, x>>>(a);
+      k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, s>>>(a);
+      fork(h->ev_dag[3], x, s);
+    }
+    if (a.rates) launch_cells<true>(h, a, h->nsm, s); else launch_cells<false>(h, a, h->nsm, s);
     k_carries<<<(unsigned)((a.ncol + 63) / 64), 64, 0, s>>>(a);
+    mark(KT_CARRIES);
     // the columns with sedimentation sub-steps on the second stream, the others on this one: disjoint columns
-    CK(h, cudaEventRecord(h->ev_fork, s));
-    CK(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    fork(h->ev_fork, s, x);
     const unsigned sgrid = (unsigned)(ngroups < h->nsm * 16 ? ngroups : h->nsm * 16);
-    if (a.rates) k_substeps<true><<<sgrid, 32, 0, h->aux>>>(a); else k_substeps<false><<<sgrid, 32, 0, h->aux>>>(a);
-    CK(h, cudaEventRecord(h->ev_join, h->aux));
+    if (a.rates) k_substeps<true><<<sgrid, 32, 0, x>>>(a); else k_substeps<false><<<sgrid, 32, 0, x>>>(a);
+    mark(KT_SUBSTEPS);
     if (a.rates) k_finish<true><<<(unsigned)ngroups, 32, 0, s>>>(a); else k_finish<false><<<(unsigned)ngroups, 32, 0, s>>>(a);
-    CK(h, cudaStreamWaitEvent(s, h->ev_join, 0));
+    mark(KT_FINISH);
+    fork(h->ev_join, x, s);
     k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
     k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
+    mark(KT_DIAG);
+    h->timing_valid = h->timing;
     h->launches += h->kc.iiwarm ? 15 : 16;
   }
   CK(h, cudaGetLastError());
@@ -429,6 +467,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   h->device = cfg->device;
   if (getenv("KIDMP_CHUNK") && atol(getenv("KIDMP_CHUNK")) >= 32) h->chunk_cols = atol(getenv("KIDMP_CHUNK"));
   if (cfg->device >= MAX_DEVICES) { delete h; return fail(nullptr, "kidmp_init: device ordinal %d not supported", cfg->device); }
+  if (getenv("KIDMP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("KIDMP_L2_FETCH")));
   if (getenv("KIDMP_PIPE_CHUNK")) h->pipe_chunk = atol(getenv("KIDMP_PIPE_CHUNK")) > 1024 ? atol(getenv("KIDMP_PIPE_CHUNK")) : 1024;
   if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
   h->cfg.table_cache_path = nullptr;
@@ -445,7 +484,14 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
       cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_dag[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_dag[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_dag[2], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_dag[3], cudaEventDisableTiming) != cudaSuccess) {
+    h->err = "stream/event creation failed"; return bail(1);
+  }
+  for (int q = 0; q <= KT_N; ++q) if (cudaEventCreate(&h->ev_k[q]) != cudaSuccess) {
     h->err = "stream/event creation failed"; return bail(1);
   }
   memset(&h->kc, 0, sizeof h->kc);
@@ -506,8 +552,11 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_colwork) cudaFree(h->d_colwork);
   if (h->d_cellidx) cudaFree(h->d_cellidx);
   if (h->d_ws) cudaFree(h->d_ws);
+  if (h->d_n0a) cudaFree(h->d_n0a);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (int q = 0; q < 4; ++q) if (h->ev_dag[q]) cudaEventDestroy(h->ev_dag[q]);
+  for (int q = 0; q <= KT_N; ++q) if (h->ev_k[q]) cudaEventDestroy(h->ev_k[q]);
   if (h->aux) cudaStreamDestroy(h->aux);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->d_pipe) cudaFree(h->d_pipe);
@@ -923,11 +972,25 @@ int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
     if (value < 32) return fail(h, "set_option: chunk must be at least 32 columns");
     h->chunk_cols = value; return 0;
   }
+  if (!strcmp(name, "timing")) { h->timing = value != 0; h->timing_valid = false; return 0; }
   if (!strcmp(name, "fuse") || !strcmp(name, "units")) return 0;      // knobs of the round-1 kernels: accepted, no effect
   return fail(h, "set_option: unknown option '%s'", name);
 }
 
 long kidmp_gpu_launches(const kidmp_handle* h) { return h ? h->launches : 0; }
+
+const char* kidmp_kernel_names(void) {
+  return "classify,lists,n0_sweep,cells_warm,cells_ice,cells_mixed_no_rain,cells_full,carries,substeps,finish,diag";
+}
+
+int kidmp_last_kernel_ms(kidmp_handle* h, float* out, int n) {
+  if (!h || !out) return 1;
+  if (!h->timing_valid) return fail(h, "last_kernel_ms: set_option(\"timing\", 1) before the step");
+  cudaSetDevice(h->device);
+  CK(h, cudaEventSynchronize(h->ev_k[KT_N]));
+  for (int q = 0; q < n && q < KT_N; ++q) CK(h, cudaEventElapsedTime(out + q, h->ev_k[q], h->ev_k[q + 1]));
+  return 0;
+}
 
 int kidmp_step_stats(kidmp_handle* h, long out[8]) {
   if (!h || !out) return 1;

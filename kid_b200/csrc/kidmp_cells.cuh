@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(LIST_TILE) k_cell_fill(StepArgs a) {
 
 // ---- running minimum of the graupel intercept of S4 (M:1633-1648), only for columns that hold graupel: the slope and
 // intercept it feeds (M:1649-1653) are read by graupel processes alone.  One thread per cloudy column, top-down; the value
-// of every graupel cell goes to the SC_N0A plane.  The rain of S1 is needed for the supercooled-drop test of M:1640.
+// of every graupel cell goes to n0a[k][slot].  Needs the work list only: runs beside the cell-list kernels.  The rain of S1 is needed for the supercooled-drop test of M:1640.
 __global__ void __launch_bounds__(128) k_n0_sweep(StepArgs a) {
   const int slot = blockIdx.x * 128 + threadIdx.x;
   const int count = *a.work_count;
@@ -192,8 +192,7 @@ __global__ void __launch_bounds__(128) k_n0_sweep(StepArgs a) {
   if (!(a.colflag[col] & 1)) return;
   const int nz = a.nz;
   const long ld = a.ld;
-  float* const n0a = a.scratch + SC_N0A;                      // field of the cell's record
-  const unsigned* const cidx = a.cellidx + slot;
+  float* const n0a = a.n0a + slot;                         // [nz][count], read by the cell kernels for graupel cells
   const double n0_empty = g_n0_lo;
   bool warm_a = false;                                    // a level at or above this one has T >= 270.65 K (k_0, M:1635)
   double n0_min = (double)KP_GONV_MAX;
@@ -234,7 +233,7 @@ __global__ void __launch_bounds__(128) k_n0_sweep(StepArgs a) {
         double N0_exp = n0_empty;
         if (slw || rg > 5.E-5f) N0_exp = graupel_n0_exp(slw ? 4.01f + log10_f(mvd_r) : 0.01f, rg);
         n0_min = fmin(N0_exp, n0_min);
-        if (qg1d > R1) n0a[(size_t)cidx[(size_t)k * count] * SC_REC] = (float)n0_min;     // values of M:1646 are f32 numbers: exact
+        if (qg1d > R1) n0a[(size_t)k * count] = (float)n0_min;     // values of M:1646 are f32 numbers: exact
       } else {
         n0_min = fmin(n0_empty, n0_min);
       }
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
         smof = field_moment(tc0, ck.cse[15], smo2);
       }
       // ---- S4, M:1633-1654 graupel intercept: the running minimum of M:1648 comes from k_n0_sweep -----------
-      if (TR::G && L_qg) graupel_slope((double)sc[SC_N0A], rg, ilamg, N0_g);
+      if (TR::G && L_qg) graupel_slope((double)a.n0a[e], rg, ilamg, N0_g);
     }
     // M:1661-1666 rain slope and intercept.  Without rain (rr = R1, nr = R2) every reader of lamr, ilamr, N0_r
     // and mvd_r is switched off (L_qr at M:1676, M:1724, M:2880; rr >= r_r(1) at M:1818, M:1964, M:2028, M:2188)

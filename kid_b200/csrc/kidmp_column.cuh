@@ -156,10 +156,11 @@ enum { F_QV = 0, F_QC, F_QI, F_QR, F_QS, F_QG, F_NI, F_NR, F_T };
 // reference zeroes in the caller's arrays before returning (M:1412-1489, U9), marks clear-sky columns
 // in colflag and leaves the ballot of the cloudy lanes of every 32-column group for the work list.
 // Every cell also gets its class byte: species present, ice supersaturation, below 0 C (k_cell_* sort the busy cells by it).
-// A cell is BUSY (some process rate can be non-zero) when it holds a hydrometeor, or ssati > 0, or ssatw > eps
-// (each rate is gated by a species flag or by ssati / ssatw, M:1676-2286, M:2780, M:2880); at or below 0 C
-// ssatw > eps implies ssati > 0 because e_s(ice) <= e_s(liquid) for both polynomials over their whole range
-// (tests/test_oracle_kat.py::test_saturation_over_ice_not_above_liquid), above 0 C the two are the same number.
+// A cell is BUSY (some process rate can be non-zero) when it holds a hydrometeor, or - vapour only - when nucleation
+// or condensation can start (each rate is gated by a species flag or by ssati / ssatw, M:1676-2286, M:2780, M:2880).
+// Both need ssati > 0: at or below 0 C ssatw > eps implies ssati > 0 because e_s(ice) <= e_s(liquid) for both polynomials
+// over their whole range (tests/test_oracle_kat.py::test_saturation_over_ice_not_above_liquid), above 0 C the two are
+// the same number.  The column test of M:1540 is the reference's (any ssati > 0).
 // Light on registers: many warps per SM keep the HBM pipe full for the ~70 % of columns that need nothing else.
 __device__ __forceinline__ int cell_kernel_class(unsigned sp, bool cold, bool iiwarm) {
   const bool icephase = (sp & (CLS_QI | CLS_QS | CLS_QG)) != 0;
@@ -203,8 +204,18 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
       float ssati = qv / qvsi - 1.f;
       if (fabsf(ssati) < EPSF) ssati = 0.0f;
       unsigned c = sp;
-      if (ssati > 0.0f) c |= CLS_VAP;
-      if (c) no_micro = false;
+      if (sp || ssati > 0.0f) no_micro = false;             // the reference's test, M:1540
+      if (!sp && ssati > 0.0f) {
+        // Vapour only.  Without a hydrometeor two things can happen: Cooper nucleation below 0 C at ssati >= 0.25, or at ssatw >
+        // eps below 253.15 K (M:2090), and condensation at ssatw > eps (M:2780: the state at tau+1 is the input when every
+        // other rate is zero).  Every other rate is gated by a species flag: a cell that meets neither is idle.
+        float ssatw = ssati;                                // above 0 C the two are the same number (qvsi = qvs, M:1505)
+        if (tempc <= 0.0f) {
+          ssatw = qv / rslf(pr, t) - 1.f;
+          if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
+        }
+        if ((t < T_0 && ssati >= 0.25f) || ssatw > EPSF) c |= CLS_VAP;
+      }
       if (t < T_0) c |= 1u << CLS_COLD_SHIFT;
       Gcls[(long)k * ncol] = (unsigned char)c;
     }

@@ -111,8 +111,7 @@ struct KConst {
 //   SC_VTR..SC_VTNI    the cell's own fall speeds (0 without the species: k_carries applies the rule of the level above)
 //   SC_VTS, SC_VTG     written by k_carries (final snow / graupel speed of the level)
 //   SC_RHO, SC_S15     air density at tau+1; signed latent-heat factor of S15
-//   SC_N0A             in: running minimum of the graupel intercept of S4 (k_n0_sweep); out: S10's intercept without
-//                      supercooled rain, negated when the level's updated temperature is >= 270.65 K
+//   SC_N0A             S10's intercept without supercooled rain, negated when the level's updated temperature is >= 270.65 K
 //   SC_N0B_SLW         S10's intercept with supercooled rain; SC_VTS_RAW / SC_VTS_BOOST / SC_TEMP for the snow speed rule
 enum { SC_TTEN = 0, SC_QVTEN, SC_QCTEN, SC_QITEN, SC_QRTEN, SC_QSTEN, SC_QGTEN, SC_NITEN,
        SC_NRTEN = 8, SC_NCTEN, SC_NR, SC_NI, SC_VTNI,
@@ -140,6 +139,7 @@ struct StepArgs {
   float* ppt;                  // [4][ld]
   float* scratch;              // [records][SC_REC] hand-off (see SC_*): one record per busy cell, in the order of cell_list
   unsigned* cellidx;           // [nz][count] record number of every busy cell of the cloudy columns
+  float* n0a;                  // [nz][count] running minimum of the graupel intercept of S4 at the graupel cells (k_n0_sweep)
   float* ws;                   // [WS_N][nz][ws_cols] SoA workspace of the columns with sedimentation sub-steps (k_substeps)
   long ws_cols;
   unsigned char* cls;          // [nz][ncol] class byte of every cell (0 = idle)

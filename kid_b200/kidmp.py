@@ -54,6 +54,8 @@ SYMBOLS = {
     "kidmp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "kidmp_gpu_launches": (C.c_long, [C.c_void_p]),
     "kidmp_step_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_long)]),
+    "kidmp_kernel_names": (C.c_char_p, []),
+    "kidmp_last_kernel_ms": (C.c_int, [C.c_void_p, _fp, C.c_int]),
     "kidmp_sync": (C.c_int, [C.c_void_p]),
     "kidmp_last_step_ms": (C.c_int, [C.c_void_p, _fp]),
     "kidmp_tables_from_cache": (C.c_int, [C.c_void_p]),
@@ -244,7 +246,7 @@ class Thompson:
         return [int(x) for x in f], int(p.value), int(dz.value), int(ppt.value)
 
     def set_option(self, name, value):
-        """kidmp_set_option: tuning knobs that do not change results ("fuse": 0 split, 1 adaptive, 2 always fused)."""
+        """kidmp_set_option: tuning knobs that do not change results ("chunk": columns per launch, "timing": 0 / 1)."""
         self._ck(self._L.kidmp_set_option(self.h, name.encode(), int(value)))
 
     def mp_gt_driver(self, dt, f3, pii, p, dz, acc, radii=True):
@@ -319,6 +321,13 @@ class Thompson:
         self._ck(self._L.kidmp_step_stats(self.h, out))
         names = ("cloudy_columns", "busy_cells", "cells_warm", "cells_ice", "cells_mixed_no_rain", "cells_full", "substep_columns")
         return {n: int(out[i]) for i, n in enumerate(names)}
+
+    def last_kernel_ms(self):
+        """{kernel group: ms} of the last launch, after set_option("timing", 1)."""
+        names = self._L.kidmp_kernel_names().decode().split(",")
+        out = (C.c_float * len(names))()
+        self._ck(self._L.kidmp_last_kernel_ms(self.h, out, len(names)))
+        return {n: float(out[i]) for i, n in enumerate(names)}
 
     def sync(self):
         self._ck(self._L.kidmp_sync(self.h))
