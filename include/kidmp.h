@@ -42,6 +42,9 @@ typedef struct kidmp_config {
   int device;              /* CUDA device ordinal                                                */
   int reuse_tables;        /* switches:l_reuse_thompson_lookup (M:3720): read table_cache_path   */
   const char* table_cache_path; /* binary cache of the lookup tables, may be NULL (M:3710-3728)  */
+  int ndev;                /* 0 or 1: one GPU (`device`, or device_ids[0] when ndev == 1 and device_ids is set);
+                              > 1: one handle over ndev GPUs of this process, columns cut into ndev contiguous ranges */
+  const int* device_ids;   /* ndev CUDA device ordinals, NULL = 0 .. ndev-1                       */
 } kidmp_config;
 
 /* replaces thompson_init (M:374-797): constants on the host, every lookup table built by CUDA
@@ -95,10 +98,11 @@ int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt,
 int kidmp_set_rates_buffer(kidmp_handle* h, float* d_rates);
 const char* kidmp_rate_names(void);
 
-/* domain sums accumulated by the sedimentation kernel since the last call (f64, this device):
- * 0 rain 1 ice 2 snow 3 graupel surface precipitation [sum over columns of ppt],
- * 4 liquid water path 5 ice water path [kg m^-2 summed over columns], 6 active columns,
- * 7 columns processed.  Multi-GPU hosts all-reduce these 8 numbers (NCCL, 64 bytes). */
+/* domain sums accumulated by the step since the last call (f64): 0 rain 1 ice 2 snow 3 graupel surface precipitation
+ * [sum over columns of ppt], 4 liquid water path 5 ice water path [kg m^-2 summed over columns], 6 active columns,
+ * 7 columns processed.  A handle over several devices (ndev > 1) returns the sums over ALL its devices: the per-device
+ * sums are all-reduced with NCCL (ncclAllReduce of 8 f64 on a single-process communicator over NVLink), the device twin
+ * of the column means of I:255-275.  With one process per GPU (torchrun) the host all-reduces the 8 numbers itself. */
 int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]);
 
 /* The KiD-facing entry: everything mphys_thompson09_interfacen does for its nx columns except
@@ -143,6 +147,14 @@ int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in);
  * "timing": 1 = run the kernels of a launch one after the other with an event after each (kidmp_last_kernel_ms), 0 = normal.
  * "fuse", "units": knobs of the round-1 kernels, accepted and ignored. */
 int kidmp_set_option(kidmp_handle* h, const char* name, int value);
+
+/* Multi-device handles (kidmp_config::ndev > 1).  kidmp_step, kidmp_kid_interface and the resident-state calls cut the
+ * host arrays into one contiguous column range per device (columns are independent, I:54: no exchange on the data path) and
+ * run the devices side by side; results are bit-identical to a single-device handle, column by column.  kidmp_column and
+ * kidmp_mp_gt_driver run on the first device.  The entry points that take or return DEVICE pointers (kidmp_step_device,
+ * kidmp_set_rates_buffer, kidmp_device_state, kidmp_stream) need a single-device handle.  NCCL (libnccl.so.2, or the file
+ * named by the KIDMP_NCCL_LIB environment variable) is loaded when such a handle is created, not before. */
+int kidmp_num_devices(const kidmp_handle* h);
 
 /* bookkeeping for benchmarks */
 long kidmp_gpu_launches(const kidmp_handle* h);         /* kernels launched so far          */

@@ -76,6 +76,7 @@ struct kidmp_handle {
   cudaEvent_t pipe_ev[3][3] = {};
   float last_ms = 0.f;
   std::map<std::string, std::vector<double>> consts;   // named init constants for parity tests
+  struct MultiCtx* multi = nullptr;                    // a handle over several devices (kidmp_config::ndev > 1): see "multi-device handle"
 };
 
 namespace {
@@ -306,12 +307,13 @@ int ensure_work(kidmp_handle* h, long cols, int nz) {
 #endif
 
 template <bool RATES>
-void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s) {
+void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s, cudaEvent_t n0_done) {
   auto mark = [&](int q) { if (h->timing) cudaEventRecord(h->ev_k[q + 1], s); };
   k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, KC_WARM_BARS, RATES><<<nsm * KC_WARM_B, KC_WARM_T, 0, s>>>(a);
   mark(KT_WARM);
   k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, KC_ICE_BARS, RATES><<<nsm * KC_ICE_B, KC_ICE_T, 0, s>>>(a);
   mark(KT_ICE);
+  if (n0_done) cudaStreamWaitEvent(s, n0_done, 0);     // only the classes with graupel read the intercept minima of k_n0_sweep
   k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES><<<nsm * KC_MIXNR_B, KC_MIXNR_T, 0, s>>>(a);
   mark(KT_MIXNR);
   k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES><<<nsm * KC_FULL_B, KC_FULL_T, 0, s>>>(a);
@@ -327,6 +329,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   if (!(a0.dt > 0.f)) return fail(h, "dt must be positive");
   const long chunk = h->chunk_cols;
   const long cap = a0.ncol < chunk ? a0.ncol : chunk;
+  if (cap > (1L << 24)) return fail(h, "chunk of %ld columns: at most 16 777 216 per launch (set_option \"chunk\")", cap);
   if ((double)cap * a0.nz >= 4.0e9) return fail(h, "chunk of %ld columns x %d levels does not fit the 32-bit cell index", cap, a0.nz);
   if (ensure_work(h, cap, a0.nz)) return 1;
   if (ensure_constants(h, s)) return 1;
@@ -339,7 +342,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     if (a0.dz_col) a.dz_col = a0.dz_col + c0;
     if (a0.rates) a.rates = a0.rates + c0;
     const long ngroups = (a.ncol + 31) / 32, lblocks = (a.ncol + LIST_TILE - 1) / LIST_TILE;
-    a.scratch = h->d_scratch; a.cellidx = h->d_cellidx; a.cls = h->d_cls; a.colflag = h->d_colflag;
+    a.scratch = h->d_scratch; a.scratch_b = h->d_scratch + (size_t)h->work_cols * h->work_nz * SC_HALF; a.cellidx = h->d_cellidx; a.cls = h->d_cls; a.colflag = h->d_colflag;
     a.work_count = h->d_work; a.work_list = h->d_work + 8;
     a.work_mask = (unsigned*)(h->d_work + 8 + a.ncol); a.work_offset = h->d_work + 8 + a.ncol + ngroups;
     a.cell_list = h->d_cells; a.cell_count = h->d_cellmeta; a.sub_count = h->d_cellmeta + 5; a.cell_kstart = h->d_cellmeta + 8;
@@ -376,9 +379,10 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
       // the number of cloudy columns is only known on the device: grids for the worst case, surplus blocks leave at once
       if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, x>>>(a);
       k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, s>>>(a);
-      fork(h->ev_dag[3], x, s);
+      CK(h, cudaEventRecord(h->ev_dag[3], x));       // the sweep runs beside k_cell_fill and the warm and ice cell kernels
     }
-    if (a.rates) launch_cells<true>(h, a, h->nsm, s); else launch_cells<false>(h, a, h->nsm, s);
+    cudaEvent_t n0_done = h->timing ? nullptr : h->ev_dag[3];
+    if (a.rates) launch_cells<true>(h, a, h->nsm, s, n0_done); else launch_cells<false>(h, a, h->nsm, s, n0_done);
     k_carries<<<(unsigned)((a.ncol + 63) / 64), 64, 0, s>>>(a);
     mark(KT_CARRIES);
     // the columns with sedimentation sub-steps on the second stream, the others on this one: disjoint columns
@@ -448,6 +452,224 @@ int get_field(kidmp_handle* h, int layout, const float* src, float* dst) {
   return 0;
 }
 
+
+// ---- multi-device handle -------------------------------------------------------------------------------------------------
+// kidmp_config::ndev > 1: one handle owns a full single-device handle per GPU (streams, tables, constants, work buffers) and
+// a single-process NCCL communicator over them.  Columns are independent (I:54, M:1156-1177), so the host arrays are cut into
+// contiguous column ranges, one per device, with no exchange on the data path; kidmp_diag returns the NCCL all-reduced domain
+// sums (the device twin of the column means of I:255-275).  NCCL is loaded at run time (libnccl.so.2, or KIDMP_NCCL_LIB):
+// a single-device handle needs no NCCL at all.
+}  // namespace
+#include <dlfcn.h>
+#include <thread>
+extern "C" {
+static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* const fields[KIDMP_NFIELDS], const float* p,
+                          const float* dz, float* ppt, long hld);
+}
+struct MultiCtx {
+  std::vector<kidmp_handle*> dev;
+  void* lib = nullptr;
+  std::vector<void*> comms;                          // ncclComm_t
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::vector<double*> d_red;                        // [8] per device: the sums being reduced
+  long ncol = 0; int nz = 0;                         // resident state: columns of the whole domain
+};
+namespace {
+void shard(long ncol, int d, int n, long& c0, long& c1) { c0 = ncol * d / n; c1 = ncol * (d + 1) / n; }
+
+// run fn(d) for every device at the same time (the entry points block until their device is done); returns the first error
+template <class F> int on_all(kidmp_handle* h, F fn) {
+  MultiCtx* m = h->multi;
+  const int n = (int)m->dev.size();
+  std::vector<int> rc(n, 0);
+  std::vector<std::thread> th;
+  for (int d = 1; d < n; ++d) th.emplace_back([&, d] { rc[d] = fn(d); });
+  rc[0] = fn(0);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < n; ++d) if (rc[d]) return fail(h, "device %d: %s", m->dev[d]->device, m->dev[d]->err.c_str());
+  return 0;
+}
+
+int multi_step(kidmp_handle* h, long ncol, int nz, float dt, int layout, float* const fields[KIDMP_NFIELDS], const float* p,
+               const float* dz, float* ppt) {
+  MultiCtx* m = h->multi;
+  const int n = (int)m->dev.size();
+  for (int q = 0; q < KIDMP_NFIELDS; ++q) if (!fields[q]) return fail(h, "step: field %d is null", q);
+  if (ncol < 1 || nz < 2 || nz > 256 || !(dt > 0.f)) return fail(h, "step: ncol=%ld nz=%d dt=%g", ncol, nz, (double)dt);
+  return on_all(h, [&](int d) -> int {
+    kidmp_handle* c = m->dev[d];
+    long c0, c1;
+    shard(ncol, d, n, c0, c1);
+    if (c1 <= c0) return 0;
+    cudaSetDevice(c->device);
+    float* f[KIDMP_NFIELDS];
+    if (layout == KIDMP_COL_FASTEST) {                // a column range of [nz][ncol] arrays: pitched copies
+      for (int q = 0; q < KIDMP_NFIELDS; ++q) f[q] = fields[q] + c0;
+      return step_pipelined(c, c1 - c0, nz, dt, f, p + c0, dz, ppt ? ppt + c0 : nullptr, ncol);
+    }
+    for (int q = 0; q < KIDMP_NFIELDS; ++q) f[q] = fields[q] + (size_t)c0 * nz;   // KiD's (k,i) arrays: a range of columns is contiguous
+    std::vector<float> pp(ppt ? (size_t)(c1 - c0) * 4 : 0);
+    if (kidmp_step(c, c1 - c0, nz, dt, layout, f, p + (size_t)c0 * nz, dz, ppt ? pp.data() : nullptr)) return 1;
+    if (ppt) for (int q = 0; q < 4; ++q) memcpy(ppt + (size_t)q * ncol + c0, pp.data() + (size_t)q * (c1 - c0), (size_t)(c1 - c0) * 4);
+    return 0;
+  });
+}
+
+int multi_kid_interface(kidmp_handle* h, const kidmp_kid_columns* k, float dt, float p0, float r_on_cp) {
+  MultiCtx* m = h->multi;
+  const int n = (int)m->dev.size();
+  if (!k->ppt) return fail(h, "kid_interface: null array");
+  return on_all(h, [&](int d) -> int {
+    long c0, c1;
+    shard(k->nx, d, n, c0, c1);
+    if (c1 <= c0) return 0;
+    const size_t o = (size_t)c0 * k->nz;
+    kidmp_kid_columns s = *k;                          // every array is (k,i): a range of columns is contiguous
+    s.nx = c1 - c0;
+    auto off = [&](const float* a) { return a ? a + o : nullptr; };
+    auto offw = [&](float* a) { return a ? a + o : nullptr; };
+    s.theta = off(k->theta); s.dtheta_adv = off(k->dtheta_adv); s.dtheta_div = off(k->dtheta_div); s.exner = off(k->exner);
+    s.qv = off(k->qv); s.dqv_adv = off(k->dqv_adv); s.dqv_div = off(k->dqv_div);
+    for (int q = 0; q < 7; ++q) {
+      s.hyd[q] = off(k->hyd[q]); s.dhyd_adv[q] = off(k->dhyd_adv[q]); s.dhyd_div[q] = off(k->dhyd_div[q]);
+      s.dhyd_mphys[q] = offw(k->dhyd_mphys[q]);
+    }
+    s.dtheta_mphys = offw(k->dtheta_mphys); s.dqv_mphys = offw(k->dqv_mphys);
+    std::vector<float> pp((size_t)(c1 - c0) * 4);
+    s.ppt = pp.data();
+    if (kidmp_kid_interface(m->dev[d], &s, dt, p0, r_on_cp)) return 1;
+    for (int q = 0; q < 4; ++q) memcpy(k->ppt + (size_t)q * k->nx + c0, pp.data() + (size_t)q * (c1 - c0), (size_t)(c1 - c0) * 4);
+    return 0;
+  });
+}
+
+int multi_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
+  MultiCtx* m = h->multi;
+  const int n = (int)m->dev.size();
+  for (int d = 0; d < n; ++d) {                        // this device's sums, then cleared, as kidmp_diag does
+    kidmp_handle* c = m->dev[d];
+    cudaSetDevice(c->device);
+    CK(h, cudaStreamWaitEvent(c->stream, c->ev_done, 0));
+    CK(h, cudaMemcpyAsync(m->d_red[d], c->d_diag, KIDMP_NDIAG * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CK(h, cudaMemsetAsync(c->d_diag, 0, KIDMP_NDIAG * 8, c->stream));
+  }
+  int rc = m->GroupStart();
+  for (int d = 0; d < n && !rc; ++d)                   // 64 bytes per device over NVLink: sum of the 8 f64 (ncclDouble = 8, ncclSum = 0)
+    rc = m->AllReduce(m->d_red[d], m->d_red[d], KIDMP_NDIAG, 8, 0, m->comms[d], m->dev[d]->stream);
+  const int rc2 = m->GroupEnd();
+  if (rc || rc2) return fail(h, "diag: ncclAllReduce: %s", m->GetErrorString(rc ? rc : rc2));
+  for (int d = 0; d < n; ++d) { cudaSetDevice(m->dev[d]->device); CK(h, cudaStreamSynchronize(m->dev[d]->stream)); }
+  cudaSetDevice(m->dev[0]->device);
+  CK(h, cudaMemcpy(out, m->d_red[0], KIDMP_NDIAG * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int multi_init(const kidmp_config* cfg, kidmp_handle** out) {
+  kidmp_handle* h = new kidmp_handle();
+  h->cfg = *cfg;
+  MultiCtx* m = new MultiCtx();
+  h->multi = m;
+  auto bail = [&](const char* what) { g_init_error = std::string("kidmp_init: ") + what; kidmp_finalize(h); return 1; };
+  std::vector<int> ids(cfg->ndev);
+  for (int d = 0; d < cfg->ndev; ++d) {
+    ids[d] = cfg->device_ids ? cfg->device_ids[d] : d;
+    for (int e = 0; e < d; ++e) if (ids[e] == ids[d]) return bail("device_ids holds a device twice");
+  }
+  for (int d = 0; d < cfg->ndev; ++d) {
+    kidmp_config one = *cfg;
+    one.device = ids[d]; one.ndev = 0; one.device_ids = nullptr;
+    kidmp_handle* c = nullptr;
+    if (kidmp_init(&one, &c)) { const std::string w = g_init_error; return bail(w.c_str()); }
+    m->dev.push_back(c);
+  }
+  h->device = ids[0];
+  const char* path = getenv("KIDMP_NCCL_LIB");
+  m->lib = dlopen(path ? path : "libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!m->lib) return bail("ndev > 1 needs NCCL for the domain diagnostics: libnccl.so.2 not found (set KIDMP_NCCL_LIB)");
+  m->CommInitAll = (int (*)(void**, int, const int*))dlsym(m->lib, "ncclCommInitAll");
+  m->CommDestroy = (int (*)(void*))dlsym(m->lib, "ncclCommDestroy");
+  m->AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(m->lib, "ncclAllReduce");
+  m->GroupStart = (int (*)())dlsym(m->lib, "ncclGroupStart");
+  m->GroupEnd = (int (*)())dlsym(m->lib, "ncclGroupEnd");
+  m->GetErrorString = (const char* (*)(int))dlsym(m->lib, "ncclGetErrorString");
+  if (!m->CommInitAll || !m->CommDestroy || !m->AllReduce || !m->GroupStart || !m->GroupEnd || !m->GetErrorString)
+    return bail("the NCCL library lacks an entry point");
+  m->comms.assign(cfg->ndev, nullptr);
+  const int rc = m->CommInitAll(m->comms.data(), cfg->ndev, ids.data());
+  if (rc) { m->comms.clear(); return bail(m->GetErrorString(rc)); }
+  m->d_red.assign(cfg->ndev, nullptr);
+  for (int d = 0; d < cfg->ndev; ++d) {
+    cudaSetDevice(ids[d]);
+    if (cudaMalloc((void**)&m->d_red[d], KIDMP_NDIAG * 8) != cudaSuccess) return bail("allocation failed");
+  }
+  *out = h;
+  return 0;
+}
+
+void multi_finalize(kidmp_handle* h) {
+  MultiCtx* m = h->multi;
+  for (size_t d = 0; d < m->d_red.size(); ++d) if (m->d_red[d]) { cudaSetDevice(m->dev[d]->device); cudaFree(m->d_red[d]); }
+  for (void* c : m->comms) if (c && m->CommDestroy) m->CommDestroy(c);
+  for (kidmp_handle* c : m->dev) kidmp_finalize(c);
+  if (m->lib) dlclose(m->lib);
+  delete m;
+  delete h;
+}
+
+// resident state of a multi-device handle: every device holds its column range
+int multi_state_alloc(kidmp_handle* h, long ncol, int nz) {
+  MultiCtx* m = h->multi;
+  const int n = (int)m->dev.size();
+  if (ncol < n) return fail(h, "state_alloc: %ld columns over %d devices", ncol, n);
+  for (int d = 0; d < n; ++d) {
+    long c0, c1;
+    shard(ncol, d, n, c0, c1);
+    if (kidmp_state_alloc(m->dev[d], c1 - c0, nz)) return fail(h, "device %d: %s", m->dev[d]->device, m->dev[d]->err.c_str());
+  }
+  m->ncol = ncol; m->nz = nz;
+  return 0;
+}
+int multi_copy(kidmp_handle* h, int layout, float* const fields[KIDMP_NFIELDS], const float* p, const float* dz, float* ppt, bool up) {
+  MultiCtx* m = h->multi;
+  const int n = (int)m->dev.size();
+  if (!m->ncol) return fail(h, "upload / download before state_alloc");
+  const long ncol = m->ncol;
+  const int nz = m->nz;
+  return on_all(h, [&](int d) -> int {
+    kidmp_handle* c = m->dev[d];
+    long c0, c1;
+    shard(ncol, d, n, c0, c1);
+    cudaSetDevice(c->device);
+    const long w = c1 - c0;
+    if (layout != KIDMP_COL_FASTEST) {                 // (k,i) arrays: a column range is contiguous
+      float* f[KIDMP_NFIELDS];
+      for (int q = 0; q < KIDMP_NFIELDS; ++q) f[q] = fields && fields[q] ? fields[q] + (size_t)c0 * nz : nullptr;
+      if (up) return kidmp_upload(c, layout, f, p + (size_t)c0 * nz, dz);
+      std::vector<float> pp(ppt ? (size_t)w * 4 : 0);
+      if (kidmp_download(c, layout, fields ? f : nullptr, ppt ? pp.data() : nullptr)) return 1;
+      if (ppt) for (int q = 0; q < 4; ++q) memcpy(ppt + (size_t)q * ncol + c0, pp.data() + (size_t)q * w, (size_t)w * 4);
+      return 0;
+    }
+    const size_t hp = (size_t)ncol * 4, dp = (size_t)w * 4;
+    for (int q = 0; q <= KIDMP_NFIELDS; ++q) {
+      float* dev = field_ptr(c, q);
+      if (up) {
+        const float* src = (q < KIDMP_NFIELDS ? fields[q] : p) + c0;
+        if (cudaMemcpy2DAsync(dev, dp, src, hp, dp, nz, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return fail(c, "upload failed");
+      } else if (q < KIDMP_NFIELDS && fields && fields[q]) {
+        if (cudaMemcpy2DAsync(fields[q] + c0, hp, dev, dp, dp, nz, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return fail(c, "download failed");
+      }
+    }
+    if (up && cudaMemcpyAsync(c->d_dz, dz, (size_t)nz * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return fail(c, "upload failed");
+    if (!up && ppt && cudaMemcpy2DAsync(ppt + c0, hp, c->d_ppt, dp, dp, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return fail(c, "download failed");
+    return cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : fail(c, "copy failed");
+  });
+}
 }  // namespace
 
 extern "C" {
@@ -460,14 +682,18 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   if (e != cudaSuccess || ndev < 1)
     return fail(nullptr, "kidmp_init: no CUDA device (%s); this library has no CPU path",
                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "kidmp_init: device %d of %d", cfg->device, ndev);
   if (!(cfg->set_Nc > 0.f)) return fail(nullptr, "kidmp_init: set_Nc must be positive");
+  if (cfg->ndev > 1) {
+    if (cfg->ndev > ndev) return fail(nullptr, "kidmp_init: ndev %d of %d devices", cfg->ndev, ndev);
+    return multi_init(cfg, out);
+  }
+  const int dev1 = (cfg->ndev == 1 && cfg->device_ids) ? cfg->device_ids[0] : cfg->device;
+  if (dev1 < 0 || dev1 >= ndev) return fail(nullptr, "kidmp_init: device %d of %d", dev1, ndev);
   kidmp_handle* h = new kidmp_handle();
   h->cfg = *cfg;
-  h->device = cfg->device;
+  h->device = dev1;
   if (getenv("KIDMP_CHUNK") && atol(getenv("KIDMP_CHUNK")) >= 32) h->chunk_cols = atol(getenv("KIDMP_CHUNK"));
-  if (cfg->device >= MAX_DEVICES) { delete h; return fail(nullptr, "kidmp_init: device ordinal %d not supported", cfg->device); }
-  if (getenv("KIDMP_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("KIDMP_L2_FETCH")));
+  if (dev1 >= MAX_DEVICES) { delete h; return fail(nullptr, "kidmp_init: device ordinal %d not supported", dev1); }
   if (getenv("KIDMP_PIPE_CHUNK")) h->pipe_chunk = atol(getenv("KIDMP_PIPE_CHUNK")) > 1024 ? atol(getenv("KIDMP_PIPE_CHUNK")) : 1024;
   if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
   h->cfg.table_cache_path = nullptr;
@@ -530,6 +756,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
 
 int kidmp_finalize(kidmp_handle* h) {
   if (!h) return 0;
+  if (h->multi) { multi_finalize(h); return 0; }
   cudaSetDevice(h->device);
   {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -573,11 +800,12 @@ int kidmp_finalize(kidmp_handle* h) {
 }
 
 const char* kidmp_last_error(const kidmp_handle* h) { return h ? h->err.c_str() : g_init_error.c_str(); }
-double kidmp_table_build_ms(const kidmp_handle* h) { return h ? (double)h->table_ms : -1.0; }
-int kidmp_tables_from_cache(const kidmp_handle* h) { return h && h->tables_from_cache ? 1 : 0; }
+double kidmp_table_build_ms(const kidmp_handle* h) { if (h && h->multi) return kidmp_table_build_ms(h->multi->dev[0]); return h ? (double)h->table_ms : -1.0; }
+int kidmp_tables_from_cache(const kidmp_handle* h) { if (h && h->multi) return kidmp_tables_from_cache(h->multi->dev[0]); return h && h->tables_from_cache ? 1 : 0; }
 
 long kidmp_table_size(const kidmp_handle* h, const char* name) {
   if (!h || !name) return -1;
+  if (h->multi) return kidmp_table_size(h->multi->dev[0], name);
   TabDesc d;
   if (find_table(h, name, d)) return d.n;
   auto it = h->consts.find(name);
@@ -587,6 +815,7 @@ long kidmp_table_size(const kidmp_handle* h, const char* name) {
 int kidmp_get_table(const kidmp_handle* hc, const char* name, double* out, long n) {
   kidmp_handle* h = const_cast<kidmp_handle*>(hc);
   if (!h || !name || !out) return 1;
+  if (h->multi) return kidmp_get_table(h->multi->dev[0], name, out, n);
   TabDesc d;
   if (!find_table(h, name, d)) {
     auto it = h->consts.find(name);
@@ -612,6 +841,7 @@ int kidmp_get_table(const kidmp_handle* hc, const char* name, double* out, long 
 int kidmp_save_tables(const kidmp_handle* hc, const char* path) {
   kidmp_handle* h = const_cast<kidmp_handle*>(hc);
   if (!h || !path) return 1;
+  if (h->multi) return kidmp_save_tables(h->multi->dev[0], path);
   cudaSetDevice(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
   const std::string tmp = std::string(path) + ".tmp";
@@ -676,6 +906,7 @@ bool read_records(FILE* f, std::vector<double>& rec, long n, int members) {
 int kidmp_write_kid_cache(const kidmp_handle* hc, const char* racg_path, const char* racs_path) {
   kidmp_handle* h = const_cast<kidmp_handle*>(hc);
   if (!h || !racg_path || !racs_path) return 1;
+  if (h->multi) return kidmp_write_kid_cache(h->multi->dev[0], racg_path, racs_path);
   if (h->kc.iiwarm) return fail(h, "write_kid_cache: the collection tables are not built when iiwarm (M:773)");
   cudaSetDevice(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
@@ -695,6 +926,10 @@ int kidmp_write_kid_cache(const kidmp_handle* hc, const char* racg_path, const c
 
 int kidmp_read_kid_cache(kidmp_handle* h, const char* racg_path, const char* racs_path) {
   if (!h || !racg_path || !racs_path) return 1;
+  if (h->multi) {
+    for (kidmp_handle* c : h->multi->dev) if (kidmp_read_kid_cache(c, racg_path, racs_path)) return fail(h, "%s", c->err.c_str());
+    return 0;
+  }
   if (h->kc.iiwarm) return fail(h, "read_kid_cache: the collection tables are not used when iiwarm (M:773)");
   cudaSetDevice(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
@@ -714,6 +949,7 @@ int kidmp_read_kid_cache(kidmp_handle* h, const char* racg_path, const char* rac
 
 int kidmp_state_alloc(kidmp_handle* h, long ncol, int nz) {
   if (!h) return 1;
+  if (h->multi) return multi_state_alloc(h, ncol, nz);
   if (ncol < 1 || nz < 2 || nz > 256) return fail(h, "state_alloc: ncol=%ld nz=%d", ncol, nz);
   cudaSetDevice(h->device);
   if (h->ncol == ncol && h->nz == nz && h->d_state) return 0;
@@ -729,6 +965,11 @@ int kidmp_state_alloc(kidmp_handle* h, long ncol, int nz) {
 }
 
 int kidmp_upload(kidmp_handle* h, int layout, const float* const fields[KIDMP_NFIELDS], const float* p, const float* dz) {
+  if (h && h->multi) {
+    if (!fields || !p || !dz) return fail(h, "upload: null pointer");
+    for (int q = 0; q < KIDMP_NFIELDS; ++q) if (!fields[q]) return fail(h, "upload: field %d is null", q);
+    return multi_copy(h, layout, const_cast<float* const*>(fields), p, dz, nullptr, true);
+  }
   if (!h || !h->d_state) return h ? fail(h, "upload before state_alloc") : 1;
   if (!fields || !p || !dz) return fail(h, "upload: null pointer");
   cudaSetDevice(h->device);
@@ -744,6 +985,10 @@ int kidmp_upload(kidmp_handle* h, int layout, const float* const fields[KIDMP_NF
 }
 
 int kidmp_step_resident(kidmp_handle* h, float dt) {
+  if (h && h->multi) {
+    for (kidmp_handle* c : h->multi->dev) if (kidmp_step_resident(c, dt)) return fail(h, "device %d: %s", c->device, c->err.c_str());
+    return 0;                                           // asynchronous on every device, like the single-device call
+  }
   if (!h || !h->d_state) return h ? fail(h, "step before state_alloc") : 1;
   cudaSetDevice(h->device);
   CK(h, cudaEventRecord(h->ev0, h->stream));
@@ -753,6 +998,7 @@ int kidmp_step_resident(kidmp_handle* h, float dt) {
 }
 
 int kidmp_download(kidmp_handle* h, int layout, float* const fields[KIDMP_NFIELDS], float* ppt) {
+  if (h && h->multi) return multi_copy(h, layout, fields, nullptr, nullptr, ppt, false);
   if (!h || !h->d_state) return h ? fail(h, "download before state_alloc") : 1;
   cudaSetDevice(h->device);
   if (fields)
@@ -766,8 +1012,10 @@ int kidmp_download(kidmp_handle* h, int layout, float* const fields[KIDMP_NFIELD
 // Large column-fastest domains: the columns are cut into chunks that flow through three streams
 // (H2D copy, the two step kernels, D2H copy) on double buffers, so both PCIe directions and the
 // SMs work at the same time.  Columns are independent, so chunking does not change any result.
+// `hld`: columns of the caller's host arrays (their row stride): a multi-device handle gives every device a range of columns
+// of the same arrays.
 static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* const fields[KIDMP_NFIELDS],
-                          const float* p, const float* dz, float* ppt) {
+                          const float* p, const float* dz, float* ppt, long hld) {
   const long chunk = h->pipe_chunk;
   const int NB = 3;
   const size_t cells = (size_t)chunk * nz;
@@ -792,7 +1040,7 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
   }
   CK(h, cudaMemcpyAsync(h->d_pipe_dz, dz, (size_t)nz * 4, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaEventRecord(h->ev0, h->stream));
-  const size_t hpitch = (size_t)ncol * 4;
+  const size_t hpitch = (size_t)hld * 4, ppitch = (size_t)ncol * 4;
   long c0 = 0;
   for (int it = 0; c0 < ncol; ++it, c0 += chunk) {
     const int b = it % NB;
@@ -816,13 +1064,13 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
     CK(h, cudaStreamWaitEvent(h->copy_out, h->pipe_ev[b][1], 0));
     for (int q = 0; q < KIDMP_NFIELDS; ++q)
       CK(h, cudaMemcpy2DAsync(fields[q] + c0, hpitch, base + cells * q, dpitch, dpitch, nz, cudaMemcpyDeviceToHost, h->copy_out));
-    if (ppt) CK(h, cudaMemcpy2DAsync(h->h_ppt + c0, hpitch, d_ppt, dpitch, dpitch, 4, cudaMemcpyDeviceToHost, h->copy_out));
+    if (ppt) CK(h, cudaMemcpy2DAsync(h->h_ppt + c0, ppitch, d_ppt, dpitch, dpitch, 4, cudaMemcpyDeviceToHost, h->copy_out));
     CK(h, cudaEventRecord(h->pipe_ev[b][2], h->copy_out));
   }
   CK(h, cudaEventRecord(h->ev1, h->stream));
   CK(h, cudaStreamSynchronize(h->copy_out));
   CK(h, cudaStreamSynchronize(h->stream));
-  if (ppt) memcpy(ppt, h->h_ppt, (size_t)ncol * 16);
+  if (ppt) for (int q = 0; q < 4; ++q) memcpy(ppt + (size_t)q * hld, h->h_ppt + (size_t)q * ncol, (size_t)ncol * 4);
   return 0;
 }
 
@@ -830,11 +1078,12 @@ int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout, float* 
                const float* p, const float* dz, float* ppt) {
   if (!h) return 1;
   if (!fields || !p || !dz) return fail(h, "step: null pointer");
+  if (h->multi) return multi_step(h, ncol, nz, dt, layout, fields, p, dz, ppt);
   // (with a process-rate buffer set the whole domain goes through the resident path: the buffer is [36][nz][ncol] of the domain)
   if (layout == KIDMP_COL_FASTEST && ncol >= 2 * h->pipe_chunk && nz >= 2 && nz <= 256 && dt > 0.f && !h->d_rates) {
     for (int q = 0; q < KIDMP_NFIELDS; ++q) if (!fields[q]) return fail(h, "step: field %d is null", q);
     cudaSetDevice(h->device);
-    return step_pipelined(h, ncol, nz, dt, fields, p, dz, ppt);
+    return step_pipelined(h, ncol, nz, dt, fields, p, dz, ppt, ncol);
   }
   if (kidmp_state_alloc(h, ncol, nz)) return 1;
   if (kidmp_upload(h, layout, fields, p, dz)) return 1;
@@ -845,6 +1094,7 @@ int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout, float* 
 int kidmp_column(kidmp_handle* h, int nz, float dt, float* qv, float* qc, float* qi, float* qr, float* qs, float* qg,
                  float* ni, float* nr, float* t, const float* p, const float* dz, float* ppt4) {
   if (!h) return 1;
+  if (h->multi) return kidmp_column(h->multi->dev[0], nz, dt, qv, qc, qi, qr, qs, qg, ni, nr, t, p, dz, ppt4) ? fail(h, "%s", h->multi->dev[0]->err.c_str()) : 0;
   if (!ppt4) return fail(h, "column: ppt4 is null");
   float* f[KIDMP_NFIELDS] = {qv, qc, qi, qr, qs, qg, ni, nr, t};
   float inc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -856,6 +1106,7 @@ int kidmp_column(kidmp_handle* h, int nz, float dt, float* qv, float* qc, float*
 int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt, float* const d_fields[KIDMP_NFIELDS],
                       const float* d_p, const float* d_dz, float* d_ppt, void* stream) {
   if (!h) return 1;
+  if (h->multi) return fail(h, "step_device: device pointers belong to one device; use a single-device handle per GPU");
   if (!d_fields || !d_p || !d_dz || !d_ppt) return fail(h, "step_device: null pointer");
   cudaSetDevice(h->device);
   StepArgs a{};
@@ -871,6 +1122,7 @@ int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt, float* const
 
 int kidmp_set_rates_buffer(kidmp_handle* h, float* d_rates) {
   if (!h) return 1;
+  if (h->multi) return fail(h, "set_rates_buffer: device pointers belong to one device; use a single-device handle");
   h->d_rates = d_rates;
   return 0;
 }
@@ -883,6 +1135,7 @@ const char* kidmp_rate_names(void) {
 
 int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
   if (!h || !out) return 1;
+  if (h->multi) return multi_diag(h, out);
   cudaSetDevice(h->device);
   CK(h, cudaStreamWaitEvent(h->stream, h->ev_done, 0));   // the last step may have run on a caller's stream
   CK(h, cudaMemcpyAsync(out, h->d_diag, KIDMP_NDIAG * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -894,6 +1147,7 @@ int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
 // mp_gt_driver, M:806-1143 (see kidmp_wrf.cuh)
 int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in) {
   if (!h) return 1;
+  if (h->multi) return kidmp_mp_gt_driver(h->multi->dev[0], w, dt_in) ? fail(h, "%s", h->multi->dev[0]->err.c_str()) : 0;   // one tile, one device
   if (!w) return fail(h, "mp_gt_driver: null argument");
   if (w->ni < 1 || w->nj < 1 || w->nk < 2) return fail(h, "mp_gt_driver: bad dimensions %d x %d x %d", w->ni, w->nk, w->nj);
   float* const io[9] = {w->qv, w->qc, w->qi, w->qr, w->qs, w->qg, w->ni_, w->nr, w->th};      // state-field order
@@ -967,6 +1221,10 @@ int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in) 
 
 int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
   if (!h) return 1;
+  if (h->multi) {
+    for (kidmp_handle* c : h->multi->dev) if (kidmp_set_option(c, name, value)) return fail(h, "%s", c->err.c_str());
+    return 0;
+  }
   if (!name) return fail(h, "set_option: null name");
   if (!strcmp(name, "chunk")) {
     if (value < 32) return fail(h, "set_option: chunk must be at least 32 columns");
@@ -977,7 +1235,10 @@ int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
   return fail(h, "set_option: unknown option '%s'", name);
 }
 
-long kidmp_gpu_launches(const kidmp_handle* h) { return h ? h->launches : 0; }
+long kidmp_gpu_launches(const kidmp_handle* h) {
+  if (h && h->multi) { long n = 0; for (kidmp_handle* c : h->multi->dev) n += c->launches; return n; }
+  return h ? h->launches : 0;
+}
 
 const char* kidmp_kernel_names(void) {
   return "classify,lists,n0_sweep,cells_warm,cells_ice,cells_mixed_no_rain,cells_full,carries,substeps,finish,diag";
@@ -985,6 +1246,7 @@ const char* kidmp_kernel_names(void) {
 
 int kidmp_last_kernel_ms(kidmp_handle* h, float* out, int n) {
   if (!h || !out) return 1;
+  if (h->multi) return kidmp_last_kernel_ms(h->multi->dev[0], out, n);
   if (!h->timing_valid) return fail(h, "last_kernel_ms: set_option(\"timing\", 1) before the step");
   cudaSetDevice(h->device);
   CK(h, cudaEventSynchronize(h->ev_k[KT_N]));
@@ -994,6 +1256,15 @@ int kidmp_last_kernel_ms(kidmp_handle* h, float* out, int n) {
 
 int kidmp_step_stats(kidmp_handle* h, long out[8]) {
   if (!h || !out) return 1;
+  if (h->multi) {                                       // summed over the devices
+    for (int q = 0; q < 8; ++q) out[q] = 0;
+    for (kidmp_handle* c : h->multi->dev) {
+      long one[8];
+      if (kidmp_step_stats(c, one)) return fail(h, "%s", c->err.c_str());
+      for (int q = 0; q < 8; ++q) out[q] += one[q];
+    }
+    return 0;
+  }
   for (int q = 0; q < 8; ++q) out[q] = 0;
   if (!h->d_cellmeta) return 0;
   cudaSetDevice(h->device);
@@ -1009,6 +1280,10 @@ int kidmp_step_stats(kidmp_handle* h, long out[8]) {
 
 int kidmp_sync(kidmp_handle* h) {
   if (!h) return 1;
+  if (h->multi) {
+    for (kidmp_handle* c : h->multi->dev) if (kidmp_sync(c)) return fail(h, "%s", c->err.c_str());
+    return 0;
+  }
   cudaSetDevice(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
   return 0;
@@ -1016,6 +1291,15 @@ int kidmp_sync(kidmp_handle* h) {
 
 int kidmp_last_step_ms(kidmp_handle* h, float* step_ms) {
   if (!h || !step_ms) return 1;
+  if (h->multi) {                                       // the slowest device
+    *step_ms = 0.f;
+    for (kidmp_handle* c : h->multi->dev) {
+      float ms = 0.f;
+      if (kidmp_last_step_ms(c, &ms)) return fail(h, "%s", c->err.c_str());
+      if (ms > *step_ms) *step_ms = ms;
+    }
+    return 0;
+  }
   cudaSetDevice(h->device);
   if (!h->last_on_own_stream) return fail(h, "last_step_ms: the last step ran on a caller's stream; time it there");
   CK(h, cudaEventSynchronize(h->ev1));
@@ -1026,6 +1310,8 @@ int kidmp_last_step_ms(kidmp_handle* h, float* step_ms) {
 int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, float p0, float r_on_cp) {
   if (!h) return 1;
   if (!c) return fail(h, "kid_interface: null argument");
+  if (h->multi && c->nx >= (long)h->multi->dev.size()) return multi_kid_interface(h, c, dt, p0, r_on_cp);
+  if (h->multi) return kidmp_kid_interface(h->multi->dev[0], c, dt, p0, r_on_cp) ? fail(h, "%s", h->multi->dev[0]->err.c_str()) : 0;
   if (!c->theta || !c->dtheta_adv || !c->dtheta_div || !c->exner || !c->qv || !c->dqv_adv || !c->dqv_div || !c->dz ||
       !c->dtheta_mphys || !c->dqv_mphys || !c->ppt)
     return fail(h, "kid_interface: null array");
@@ -1104,9 +1390,11 @@ int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, f
   return 0;
 }
 
-void* kidmp_stream(kidmp_handle* h) { return h ? (void*)h->stream : nullptr; }
+void* kidmp_stream(kidmp_handle* h) { return h && !h->multi ? (void*)h->stream : nullptr; }
+int kidmp_num_devices(const kidmp_handle* h) { return !h ? 0 : h->multi ? (int)h->multi->dev.size() : 1; }
 
 int kidmp_device_state(kidmp_handle* h, float* d_fields[KIDMP_NFIELDS], float** d_p, float** d_dz, float** d_ppt) {
+  if (h && h->multi) return fail(h, "device_state: device pointers belong to one device; use a single-device handle");
   if (!h || !h->d_state) return h ? fail(h, "device_state before state_alloc") : 1;
   for (int q = 0; q < KIDMP_NFIELDS; ++q) if (d_fields) d_fields[q] = field_ptr(h, q);
   if (d_p) *d_p = field_ptr(h, KIDMP_NFIELDS);

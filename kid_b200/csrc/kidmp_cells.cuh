@@ -27,6 +27,8 @@ namespace kidmp {
 // One sector (32 bytes, 8 floats) of a hand-off record per instruction: the 256-bit global accesses of sm_100
 // (LDG.E.256 / STG.E.256).  A lane then reads or writes whole sectors of its record, never part of one.
 struct Sector { float v[8]; };
+// start fetching the line of a record that the next level of a column walk will read
+__device__ __forceinline__ void prefetch_record(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st_sector(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e),
                "f"(f), "f"(g), "f"(h) : "memory");
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(LIST_TILE) k_cell_fill(StepArgs a) {
       if (lane == leader) { base = s_run[warp][key]; s_run[warp][key] = base + __popc(m); }
       base = __shfl_sync(m, base, leader);
       const unsigned pos = (unsigned)base + __popc(m & ((1u << lane) - 1u));
-      a.cell_list[pos] = (unsigned)k * count + slot;
+      a.cell_list[pos] = (unsigned)k << 24 | slot;          // nz <= 256 levels, at most 2^24 columns per launch
       a.cellidx[(size_t)k * count + slot] = pos;             // where the column kernels find the record of this cell
     }
     __syncwarp();
@@ -254,7 +256,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
   const int nz = a.nz;
   const long ld = a.ld;
   const unsigned count = (unsigned)*a.work_count;
-  float* const sc_class = a.scratch + (size_t)a.cell_kstart[KC] * SC_REC;    // records in list order
+  float* const sc_class = a.scratch + (size_t)a.cell_kstart[KC] * SC_HALF;   // records in list order: the half that only k_finish reads ...
+  float* const sb_class = a.scratch_b + (size_t)a.cell_kstart[KC] * SC_HALF; // ... and the half that k_carries reads as well
   const float DT = a.dt;
   const float odt = 1.f / DT, odts = 1.f / DT;
   const float Nt_c = ck.Nt_c;
@@ -270,8 +273,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
     const int i = base + threadIdx.x;
     const bool valid = i < n;                             // lanes past the end shadow the warp's first cell: same branches, nothing stored
     const unsigned e = list[valid ? i : wbase];
-    const int k = (int)(e / count);
-    const unsigned slot = e - (unsigned)k * count;
+    const int k = (int)(e >> 24);
+    const unsigned slot = e & 0xffffffu;
     const long col = a.work_list[slot];
     const long o = (long)k * ld + col;
     LOCKBAR(0);
@@ -279,7 +282,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
     float qc1d = TR::C ? a.f[F_QC][o] : 0.0f, qi1d = TR::I ? a.f[F_QI][o] : 0.0f, qr1d = TR::R ? a.f[F_QR][o] : 0.0f,
           qs1d = TR::S ? a.f[F_QS][o] : 0.0f, qg1d = TR::G ? a.f[F_QG][o] : 0.0f;
     float ni1d = TR::I ? a.f[F_NI][o] : 0.0f, nr1d = TR::R ? a.f[F_NR][o] : 0.0f;
-    float* const sc = sc_class + (size_t)(valid ? i : wbase) * SC_REC;
+    float* const sc = sc_class + (size_t)(valid ? i : wbase) * SC_HALF;
+    float* const sb = sb_class + (size_t)(valid ? i : wbase) * SC_HALF;
 
     // rates, M:1184-1211 (zeroed M:1282-1363)
     double prw_vcd = 0., pnc_wcd = 0., pnc_wau = 0., pnc_rcw = 0., pnc_scw = 0., pnc_gcw = 0.;
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
         smof = field_moment(tc0, ck.cse[15], smo2);
       }
       // ---- S4, M:1633-1654 graupel intercept: the running minimum of M:1648 comes from k_n0_sweep -----------
-      if (TR::G && L_qg) graupel_slope((double)a.n0a[e], rg, ilamg, N0_g);
+      if (TR::G && L_qg) graupel_slope((double)a.n0a[(size_t)k * count + slot], rg, ilamg, N0_g);
     }
     // M:1661-1666 rain slope and intercept.  Without rain (rr = R1, nr = R2) every reader of lamr, ilamr, N0_r
     // and mvd_r is switched off (L_qr at M:1676, M:1724, M:2880; rr >= r_r(1) at M:1818, M:1964, M:2028, M:2188)
@@ -1120,11 +1124,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       else if (temp < KP_HGFR) s15 = -((KP_LSUB - lvap) * ocp);
       // the sign of the first intercept carries the k_0 test of this level's updated temperature (intercepts are > 0)
       const float n0a_out = warm9 ? -(float)n0b_lo : (float)n0b_lo;
-      // one 128-byte record, four whole sectors, SC_* order
+      // two 64-byte half records, four whole sectors, SC_* order
       st_sector(sc, tt, qvt, qct, qit, qrt, qst, qgt, nit);
       st_sector(sc + 8, nrt, nct, nr, ni, v_ni, 0.f, 0.f, 0.f);
-      st_sector(sc + 16, rr, ri, rs, rg, v_r, v_nr, v_i, rho);
-      st_sector(sc + 24, s15, n0a_out, (float)n0b_slw, vts_h, vts_boost, temp, 0.f, 0.f);
+      st_sector(sb, rr, ri, rs, rg, v_r, v_nr, v_i, rho);
+      st_sector(sb + 8, s15, n0a_out, (float)n0b_slw, vts_h, vts_boost, temp, 0.f, 0.f);
     }
   }
 #undef LOCKBAR
@@ -1193,13 +1197,16 @@ __global__ void __launch_bounds__(64, 16) k_carries(StepArgs a) {
   bool warm_b = false;
   float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_s = 0.f, v_g = 0.f;     // speeds of the level above (the ice number speed sets no count, M:3267)
   unsigned bw = 0;
-  unsigned idx_next = cidx[(size_t)(nz - 1) * cs];        // (the index of an idle cell is never used)
+  // record numbers two levels ahead, the record of the next level on its way to L2 (the index of an idle cell is never used)
+  unsigned idx_next = cidx[(size_t)(nz - 1) * cs], idx_next2 = cidx[(size_t)(nz - 2) * cs];
 #pragma unroll 1
   for (int k = nz - 1; k >= 0; --k) {
     if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
     const unsigned idx = idx_next;
-    if (k > 0) idx_next = cidx[(size_t)(k - 1) * cs];     // in flight while this level is worked on
-    float* sc = a.scratch + (size_t)idx * SC_REC;
+    idx_next = idx_next2;
+    if (k > 1) idx_next2 = cidx[(size_t)(k - 2) * cs];
+    if ((k & 31) != 0 && ((bw >> ((k - 1) & 31)) & 1u)) prefetch_record(a.scratch_b + (size_t)idx_next * SC_HALF);
+    float* sc = a.scratch_b + (size_t)idx * SC_HALF - 16;       // (SC_* offsets of the second half start at 16)
     const float dzq = dzp[k * dzs];
     if ((bw >> (k & 31)) & 1u) {
       // the second half of the record (two sectors) holds everything this kernel reads
@@ -1320,8 +1327,9 @@ __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
         if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
         float* w = w0 + (size_t)k * cs;
         if ((bw >> (k & 31)) & 1u) {
-          const float* q = a.scratch + (size_t)cidx[(size_t)k * count] * SC_REC;
-          const Sector s0 = ld_sector(q), s1 = ld_sector(q + 8), s2 = ld_sector(q + 16), s3 = ld_sector(q + 24);
+          const size_t ri = (size_t)cidx[(size_t)k * count] * SC_HALF;
+          const float *q = a.scratch + ri, *qb = a.scratch_b + ri;
+          const Sector s0 = ld_sector(q), s1 = ld_sector(q + 8), s2 = ld_sector(qb), s3 = ld_sector(qb + 8);
           w[WS_TTEN * ps] = s0.v[0]; w[WS_QVTEN * ps] = s0.v[1]; w[WS_QCTEN * ps] = s0.v[2]; w[WS_QITEN * ps] = s0.v[3];
           w[WS_QRTEN * ps] = s0.v[4]; w[WS_QSTEN * ps] = s0.v[5]; w[WS_QGTEN * ps] = s0.v[6]; w[WS_NITEN * ps] = s0.v[7];
           w[WS_NRTEN * ps] = s1.v[0]; w[WS_NCTEN * ps] = s1.v[1]; w[WS_NR * ps] = s1.v[2]; w[WS_NI * ps] = s1.v[3];
@@ -1422,19 +1430,24 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
   c.ppt_r = 0.f; c.ppt_i = 0.f; c.ppt_s = 0.f; c.ppt_g = 0.f; c.lwp = 0.0; c.iwp = 0.0;
   float v_r = 0.f, v_nr = 0.f, v_i = 0.f, v_ni = 0.f, v_s = 0.f, v_g = 0.f;       // speeds of the level above
   unsigned bw = 0;
-  unsigned idx_next = cidx[(size_t)(nz - 1) * cs];        // (the index of an idle cell is never used)
+  // record numbers two levels ahead, the record of the next level on its way to L2 (the index of an idle cell is never used)
+  unsigned idx_next = cidx[(size_t)(nz - 1) * cs], idx_next2 = cidx[(size_t)(nz - 2) * cs];
 #pragma unroll 1
   for (int k = nz - 1; k >= 0; --k) {
     if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
     const long o = (long)k * ld + col;
-    const float* q = a.scratch + (size_t)idx_next * SC_REC;
-    if (k > 0) idx_next = cidx[(size_t)(k - 1) * cs];     // in flight while this level is worked on
+    const float *q = a.scratch + (size_t)idx_next * SC_HALF, *qb = a.scratch_b + (size_t)idx_next * SC_HALF;
+    idx_next = idx_next2;
+    if (k > 1) idx_next2 = cidx[(size_t)(k - 2) * cs];
+    if ((k & 31) != 0 && ((bw >> ((k - 1) & 31)) & 1u)) {
+      prefetch_record(a.scratch + (size_t)idx_next * SC_HALF); prefetch_record(a.scratch_b + (size_t)idx_next * SC_HALF);
+    }
     const bool busy = ((bw >> (k & 31)) & 1u) != 0;
     const float t1d = a.f[F_T][o], qv1d = a.f[F_QV][o], qc1d = a.f[F_QC][o], qi1d = a.f[F_QI][o], qr1d = a.f[F_QR][o],
                 qs1d = a.f[F_QS][o], qg1d = a.f[F_QG][o], ni1d = a.f[F_NI][o], nr1d = a.f[F_NR][o], pres = a.p[o];
     HandOff h;
     if (busy) {
-      const Sector s0 = ld_sector(q), s1 = ld_sector(q + 8), s2 = ld_sector(q + 16), s3 = ld_sector(q + 24);   // the 128-byte record
+      const Sector s0 = ld_sector(q), s1 = ld_sector(q + 8), s2 = ld_sector(qb), s3 = ld_sector(qb + 8);   // the two half records
       h.tt = s0.v[0]; h.qvt = s0.v[1]; h.qct = s0.v[2]; h.qit = s0.v[3]; h.qrt = s0.v[4]; h.qst = s0.v[5]; h.qgt = s0.v[6]; h.nit = s0.v[7];
       h.nrt = s1.v[0]; h.nct = s1.v[1]; h.nr = s1.v[2]; h.ni = s1.v[3];
       h.rr = s2.v[0]; h.ri = s2.v[1]; h.rs = s2.v[2]; h.rg = s2.v[3];

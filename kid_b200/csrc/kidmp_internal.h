@@ -101,11 +101,12 @@ struct KConst {
   const float* efsw;
 };
 
-// Hand-off between the cell kernels and the column kernels: one 128-byte record (32 f32, SC_* = offset in the record) per
-// BUSY cell (a hydrometeor or supersaturation; every rate of an idle cell is exactly zero), in the order of the cell list.
-// A record is one cache line: the cell kernels write it with eight 16-byte stores, the column kernels read it with
-// 16-byte loads, and the DRAM traffic is the record itself whatever the order of the cells; cellidx[k][slot] is the record
-// number of a cell.  Sector 0-1: what only k_finish reads; sector 2-3: everything k_carries reads.
+// Hand-off between the cell kernels and the column kernels: one record of 32 f32 (SC_* = offset in the record) per BUSY
+// cell (a hydrometeor or supersaturation; every rate of an idle cell is exactly zero), in the order of the cell list, kept
+// as two arrays of 64-byte halves: floats 0-15 (what only k_finish reads) in `scratch`, floats 16-31 (everything k_carries
+// reads) in `scratch_b` - DRAM moves whole 128-byte lines, so k_carries would otherwise drag the other half along.  Every
+// access is a whole 32-byte sector (256-bit loads / stores), so the traffic is the records themselves whatever the order
+// of the cells; cellidx[k][slot] is the record number of a cell.
 //   SC_TTEN..SC_NCTEN  the ten tendencies after S12
 //   SC_RR..SC_RG, SC_NR, SC_NI  contents at tau+1 (M:2602-2656 and the in-place refreshes of S11 / S12)
 //   SC_VTR..SC_VTNI    the cell's own fall speeds (0 without the species: k_carries applies the rule of the level above)
@@ -116,7 +117,7 @@ struct KConst {
 enum { SC_TTEN = 0, SC_QVTEN, SC_QCTEN, SC_QITEN, SC_QRTEN, SC_QSTEN, SC_QGTEN, SC_NITEN,
        SC_NRTEN = 8, SC_NCTEN, SC_NR, SC_NI, SC_VTNI,
        SC_RR = 16, SC_RI, SC_RS, SC_RG, SC_VTR, SC_VTNR, SC_VTI, SC_RHO,
-       SC_S15 = 24, SC_N0A, SC_N0B_SLW, SC_VTS_RAW, SC_VTS_BOOST, SC_TEMP, SC_VTS, SC_VTG, SC_REC = 32 };
+       SC_S15 = 24, SC_N0A, SC_N0B_SLW, SC_VTS_RAW, SC_VTS_BOOST, SC_TEMP, SC_VTS, SC_VTG, SC_REC = 32, SC_HALF = 16 };
 
 // Cell classes: every busy cell goes to the kernel specialised for the smallest species set that covers it
 // (kidmp_cells.cuh).  The class byte of a cell: bits 0-4 qc qi qr qs qg > R1 on input, bit 5 ice supersaturation,
@@ -137,7 +138,8 @@ struct StepArgs {
   const float* dz;             // [nz] layer depths shared by all columns (KiD, I:63) ...
   const float* dz_col;         // ... or [nz][ld] per column (WRF's dz(i,k,j), M:944); NULL when dz is used
   float* ppt;                  // [4][ld]
-  float* scratch;              // [records][SC_REC] hand-off (see SC_*): one record per busy cell, in the order of cell_list
+  float* scratch;              // [records][SC_HALF] hand-off (see SC_*): first half of the record of every busy cell, in the order of cell_list
+  float* scratch_b;            // [records][SC_HALF] second half
   unsigned* cellidx;           // [nz][count] record number of every busy cell of the cloudy columns
   float* n0a;                  // [nz][count] running minimum of the graupel intercept of S4 at the graupel cells (k_n0_sweep)
   float* ws;                   // [WS_N][nz][ws_cols] SoA workspace of the columns with sedimentation sub-steps (k_substeps)
@@ -148,7 +150,7 @@ struct StepArgs {
   int* work_list;              // their column indices, compacted in column order (slot -> column)
   unsigned* work_mask;         // [ngroups] ballot of the cloudy lanes of every 32-column group
   int* work_offset;            // [ngroups] exclusive prefix sum of the ballots' popcounts
-  unsigned* cell_list;         // [<= nz*ncol] busy cells, sort key after sort key, entry = k * count + slot
+  unsigned* cell_list;         // [<= nz*ncol] busy cells, sort key after sort key, entry = k << 24 | slot
   int* cell_hist;              // [64] busy cells of each sort key (species bits, T < T_0)
   int* cell_start;             // [64] first entry of each key
   int* cell_count;             // [KC_N] busy cells of each kernel class (+ [KC_N]: all busy cells) ...

@@ -26,7 +26,8 @@ class KidmpError(RuntimeError):
 
 class Config(C.Structure):
     _fields_ = [("set_Nc", C.c_float), ("iiwarm", C.c_int), ("l_sediment", C.c_int), ("wp_double", C.c_int),
-                ("device", C.c_int), ("reuse_tables", C.c_int), ("table_cache_path", C.c_char_p)]
+                ("device", C.c_int), ("reuse_tables", C.c_int), ("table_cache_path", C.c_char_p),
+                ("ndev", C.c_int), ("device_ids", C.POINTER(C.c_int))]
 
 
 # every symbol include/kidmp.h declares: (restype, argtypes)
@@ -53,6 +54,7 @@ SYMBOLS = {
     "kidmp_diag": (C.c_int, [C.c_void_p, _dp]),
     "kidmp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "kidmp_gpu_launches": (C.c_long, [C.c_void_p]),
+    "kidmp_num_devices": (C.c_int, [C.c_void_p]),
     "kidmp_step_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_long)]),
     "kidmp_kernel_names": (C.c_char_p, []),
     "kidmp_last_kernel_ms": (C.c_int, [C.c_void_p, _fp, C.c_int]),
@@ -133,11 +135,22 @@ class Thompson:
     """One handle = thompson_init (M:374-797) done on one GPU, plus the column step entry points."""
 
     def __init__(self, set_Nc=100.0, iiwarm=False, l_sediment=True, wp_double=False, device=0,
-                 table_cache=None, reuse_tables=False):
+                 table_cache=None, reuse_tables=False, devices=None):
+        """devices: list of CUDA ordinals for ONE handle over several GPUs (kidmp_config::ndev), else `device`."""
         L = load()
         self._L = L
+        ids = (C.c_int * len(devices))(*devices) if devices else None
+        if devices and len(devices) > 1 and "KIDMP_NCCL_LIB" not in os.environ:
+            try:                                      # the NCCL that torch ships, when there is no system libnccl.so.2
+                import nvidia.nccl
+                cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["KIDMP_NCCL_LIB"] = cand
+            except Exception:
+                pass
         cfg = Config(float(set_Nc), int(iiwarm), int(l_sediment), int(wp_double), int(device),
-                     int(bool(reuse_tables and table_cache)), table_cache.encode() if table_cache else None)
+                     int(bool(reuse_tables and table_cache)), table_cache.encode() if table_cache else None,
+                     len(devices) if devices else 0, ids)
         h = C.c_void_p()
         rc = L.kidmp_init(C.byref(cfg), C.byref(h))
         if rc:
