@@ -52,6 +52,7 @@ typedef struct kidmp_config {
 int kidmp_init(const kidmp_config* cfg, kidmp_handle** out);
 int kidmp_finalize(kidmp_handle* h);
 const char* kidmp_last_error(const kidmp_handle* h);   /* h may be NULL: last init error */
+const char* kidmp_build_id(void);                      /* hash of the sources and flags the library was built from */
 double kidmp_table_build_ms(const kidmp_handle* h);    /* device time of the table-build kernels */
 
 /* lookup tables and init constants by their reference names ("tcg_racg", "t_Efrw", "crg", ...),
@@ -80,7 +81,10 @@ int kidmp_column(kidmp_handle* h, int nz, float dt,
 int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout,
                float* const fields[KIDMP_NFIELDS], const float* p, const float* dz, float* ppt);
 
-/* device-resident state: upload once, step many times, download when needed */
+/* device-resident state: upload once, step many times, download when needed.  One resident state per handle: the entry
+ * points that take HOST arrays of another size (kidmp_step below the pipeline threshold, kidmp_column, kidmp_kid_interface,
+ * kidmp_mp_gt_driver) re-allocate it.  Calls on one handle are serialised by the caller; a step enqueued on a caller's
+ * stream (kidmp_step_device) is ordered against kidmp_diag and the next step of the same handle by an event. */
 int kidmp_state_alloc(kidmp_handle* h, long ncol, int nz);
 int kidmp_upload(kidmp_handle* h, int layout, const float* const fields[KIDMP_NFIELDS],
                  const float* p, const float* dz);
@@ -97,6 +101,12 @@ int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt,
  * [36][nz][ncol] f32, NULL switches it off (default).  Names: kidmp_rate_names(). */
 int kidmp_set_rates_buffer(kidmp_handle* h, float* d_rates);
 const char* kidmp_rate_names(void);
+/* The same rates for a HOST caller (the Fortran shim's save_dg calls, M:2963-3120): kidmp_enable_rates(h, 1) makes the handle
+ * keep its own [36][nz][ncol] buffer for the resident state (every entry point that steps the resident state fills it:
+ * kidmp_kid_interface, kidmp_step_resident, kidmp_column ...; zero where no process ran), kidmp_get_rates copies it to
+ * `rates`: [36][nz][ncol] for KIDMP_COL_FASTEST, [36][ncol][nz] (KiD's (k,i) order, plane by plane) for KIDMP_K_FASTEST. */
+int kidmp_enable_rates(kidmp_handle* h, int on);
+int kidmp_get_rates(kidmp_handle* h, int layout, float* rates);
 
 /* domain sums accumulated by the step since the last call (f64): 0 rain 1 ice 2 snow 3 graupel surface precipitation
  * [sum over columns of ppt], 4 liquid water path 5 ice water path [kg m^-2 summed over columns], 6 active columns,

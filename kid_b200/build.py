@@ -24,18 +24,40 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+def source_id():
+    """SHA-256 over every source the library is built from (DEPS, in order) and the flags: the build id."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in DEPS:
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(d.encode() + b"\0" + f.read())
+    h.update(" ".join(BASE_FLAGS).encode())
+    return h.hexdigest()[:32]
+
+
+def library_id(path=None):
+    """The build id embedded in a built library (kidmp_build_id()), read from the file without loading it."""
+    import re
+    try:
+        with open(path or LIB, "rb") as f:
+            m = re.search(rb"KIDMP_BUILD_ID=([0-9a-f]{32})", f.read())
+        return m.group(1).decode() if m else None
+    except OSError:
+        return None
+
+
+BASE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fno-fast-math", "-shared", "-lcudart", "-ldl"]
+
+
 def flags(extra=()):
-    return ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-            "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-            "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fno-fast-math", "-shared", "-lcudart",
-            *extra]
+    return [*BASE_FLAGS, "-DKIDMP_BUILD_ID=\"%s\"" % source_id(), *extra]
 
 
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    """The library is tied to the tree by its build id, not by file times: a shipped binary of other sources is rebuilt."""
+    return library_id() != source_id()
 
 
 def build(force=False, verbose=False, extra=(), out=None):

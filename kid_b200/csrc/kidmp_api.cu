@@ -67,7 +67,8 @@ struct kidmp_handle {
   cudaEvent_t ev_done = nullptr;                          // end of the last step, on whatever stream it ran
   bool last_on_own_stream = true;
   double* d_diag = nullptr;
-  float* d_rates = nullptr;
+  float* d_rates = nullptr;                               // caller's device buffer (kidmp_set_rates_buffer) ...
+  bool rates_on = false; float* d_rates_own = nullptr;    // ... or the handle's own, [36][nz][ncol] of the resident state (kidmp_enable_rates)
   float* d_kid = nullptr; size_t kid_floats = 0;   // staging of the KiD (k,i) arrays
   float* h_kid = nullptr; size_t h_kid_floats = 0; // pinned host twin of it
   float* d_pipe = nullptr; size_t pipe_floats = 0; int pipe_nz = 0; float* d_pipe_dz = nullptr;   // chunk pipeline of kidmp_step
@@ -83,6 +84,18 @@ namespace {
 
 std::string g_init_error;
 std::mutex g_mu;
+
+// Every entry point leaves the caller's current CUDA device as it found it (the host may be PyTorch or KiD's own code).
+struct DevGuard {
+  int prev = -1;
+  explicit DevGuard(int d) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != d) cudaSetDevice(d); }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+struct DevRestore {                                    // for functions that walk over several devices
+  int prev = -1;
+  DevRestore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DevRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int fail(kidmp_handle* h, const char* fmt, ...) {
   char buf[512];
@@ -333,6 +346,8 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   if ((double)cap * a0.nz >= 4.0e9) return fail(h, "chunk of %ld columns x %d levels does not fit the 32-bit cell index", cap, a0.nz);
   if (ensure_work(h, cap, a0.nz)) return 1;
   if (ensure_constants(h, s)) return 1;
+  // the handle's own rate buffer starts every step at zero: clear-sky columns have no process at all
+  if (a0.rates && a0.rates == h->d_rates_own) CK(h, cudaMemsetAsync(h->d_rates_own, 0, (size_t)KIDMP_NRATES * a0.nz * a0.ld * 4, s));
   if (!h->d_partial) CK(h, cudaMalloc((void**)&h->d_partial, (size_t)DIAG_BLOCKS * KIDMP_NDIAG * 8));
   for (long c0 = 0; c0 < a0.ncol; c0 += chunk) {
     StepArgs a = a0;
@@ -406,6 +421,8 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
 }
 
 void free_state(kidmp_handle* h) {
+  if (h->d_rates_own) cudaFree(h->d_rates_own);
+  h->d_rates_own = nullptr;
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_dz) cudaFree(h->d_dz);
   if (h->d_ppt) cudaFree(h->d_ppt);
@@ -421,7 +438,7 @@ StepArgs resident_args(kidmp_handle* h, float dt) {
   a.ncol = h->ncol; a.ld = h->ncol; a.nz = h->nz; a.dt = dt;
   for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = field_ptr(h, q);
   a.p = field_ptr(h, KIDMP_NFIELDS);
-  a.dz = h->d_dz; a.ppt = h->d_ppt; a.rates = h->d_rates;
+  a.dz = h->d_dz; a.ppt = h->d_ppt; a.rates = h->d_rates ? h->d_rates : h->d_rates_own;
   return a;
 }
 
@@ -484,6 +501,7 @@ void shard(long ncol, int d, int n, long& c0, long& c1) { c0 = ncol * d / n; c1 
 
 // run fn(d) for every device at the same time (the entry points block until their device is done); returns the first error
 template <class F> int on_all(kidmp_handle* h, F fn) {
+  DevRestore restore_;                                 // (fn(0) runs on the caller's thread)
   MultiCtx* m = h->multi;
   const int n = (int)m->dev.size();
   std::vector<int> rc(n, 0);
@@ -549,6 +567,7 @@ int multi_kid_interface(kidmp_handle* h, const kidmp_kid_columns* k, float dt, f
 }
 
 int multi_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
+  DevRestore restore_;
   MultiCtx* m = h->multi;
   const int n = (int)m->dev.size();
   for (int d = 0; d < n; ++d) {                        // this device's sums, then cleared, as kidmp_diag does
@@ -570,6 +589,7 @@ int multi_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
 }
 
 int multi_init(const kidmp_config* cfg, kidmp_handle** out) {
+  DevRestore restore_;
   kidmp_handle* h = new kidmp_handle();
   h->cfg = *cfg;
   MultiCtx* m = new MultiCtx();
@@ -612,6 +632,7 @@ int multi_init(const kidmp_config* cfg, kidmp_handle** out) {
 }
 
 void multi_finalize(kidmp_handle* h) {
+  DevRestore restore_;
   MultiCtx* m = h->multi;
   for (size_t d = 0; d < m->d_red.size(); ++d) if (m->d_red[d]) { cudaSetDevice(m->dev[d]->device); cudaFree(m->d_red[d]); }
   for (void* c : m->comms) if (c && m->CommDestroy) m->CommDestroy(c);
@@ -698,6 +719,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
   h->cfg.table_cache_path = nullptr;
   auto bail = [&](int) { g_init_error = h->err; kidmp_finalize(h); return 1; };
+  DevRestore restore_;
   if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(1); }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, h->device);
@@ -757,7 +779,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
 int kidmp_finalize(kidmp_handle* h) {
   if (!h) return 0;
   if (h->multi) { multi_finalize(h); return 0; }
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_const_owner[h->device] == h) g_const_owner[h->device] = nullptr;
@@ -799,6 +821,12 @@ int kidmp_finalize(kidmp_handle* h) {
   return 0;
 }
 
+#ifndef KIDMP_BUILD_ID
+#define KIDMP_BUILD_ID "00000000000000000000000000000000"
+#endif
+// hash of the sources and flags this binary was built from (kid_b200/build.py::source_id): ties the library to the tree
+const char* kidmp_build_id(void) { static const char id[] = "KIDMP_BUILD_ID=" KIDMP_BUILD_ID; return id + 15; }
+
 const char* kidmp_last_error(const kidmp_handle* h) { return h ? h->err.c_str() : g_init_error.c_str(); }
 double kidmp_table_build_ms(const kidmp_handle* h) { if (h && h->multi) return kidmp_table_build_ms(h->multi->dev[0]); return h ? (double)h->table_ms : -1.0; }
 int kidmp_tables_from_cache(const kidmp_handle* h) { if (h && h->multi) return kidmp_tables_from_cache(h->multi->dev[0]); return h && h->tables_from_cache ? 1 : 0; }
@@ -823,7 +851,7 @@ int kidmp_get_table(const kidmp_handle* hc, const char* name, double* out, long 
     for (long i = 0; i < n && i < (long)it->second.size(); ++i) out[i] = it->second[i];
     return 0;
   }
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
   const long m = n < d.n ? n : d.n;
   if (d.f32) {
@@ -842,7 +870,7 @@ int kidmp_save_tables(const kidmp_handle* hc, const char* path) {
   kidmp_handle* h = const_cast<kidmp_handle*>(hc);
   if (!h || !path) return 1;
   if (h->multi) return kidmp_save_tables(h->multi->dev[0], path);
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
   const std::string tmp = std::string(path) + ".tmp";
   FILE* f = fopen(tmp.c_str(), "wb");
@@ -908,7 +936,7 @@ int kidmp_write_kid_cache(const kidmp_handle* hc, const char* racg_path, const c
   if (!h || !racg_path || !racs_path) return 1;
   if (h->multi) return kidmp_write_kid_cache(h->multi->dev[0], racg_path, racs_path);
   if (h->kc.iiwarm) return fail(h, "write_kid_cache: the collection tables are not built when iiwarm (M:773)");
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
   const struct { const char* path; const double* dev; long n; int members; } files[2] = {
       {racg_path, h->tabs.racg, (long)N_RACG, G_N}, {racs_path, h->tabs.racs, (long)N_RACS, S_N}};
@@ -931,7 +959,7 @@ int kidmp_read_kid_cache(kidmp_handle* h, const char* racg_path, const char* rac
     return 0;
   }
   if (h->kc.iiwarm) return fail(h, "read_kid_cache: the collection tables are not used when iiwarm (M:773)");
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
   const struct { const char* path; double* dev; long n; int members; } files[2] = {
       {racg_path, h->tabs.racg, (long)N_RACG, G_N}, {racs_path, h->tabs.racs, (long)N_RACS, S_N}};
@@ -951,7 +979,7 @@ int kidmp_state_alloc(kidmp_handle* h, long ncol, int nz) {
   if (!h) return 1;
   if (h->multi) return multi_state_alloc(h, ncol, nz);
   if (ncol < 1 || nz < 2 || nz > 256) return fail(h, "state_alloc: ncol=%ld nz=%d", ncol, nz);
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   if (h->ncol == ncol && h->nz == nz && h->d_state) return 0;
   free_state(h);
   const size_t n = (size_t)ncol * nz;
@@ -960,7 +988,60 @@ int kidmp_state_alloc(kidmp_handle* h, long ncol, int nz) {
   CK(h, cudaMalloc((void**)&h->d_dz, (size_t)nz * 4));
   CK(h, cudaMalloc((void**)&h->d_ppt, (size_t)ncol * 4 * 4));
   CK(h, cudaMemset(h->d_ppt, 0, (size_t)ncol * 4 * 4));
+  if (h->rates_on) CK(h, cudaMalloc((void**)&h->d_rates_own, n * KIDMP_NRATES * 4));
   h->ncol = ncol; h->nz = nz;
+  return 0;
+}
+
+int kidmp_enable_rates(kidmp_handle* h, int on) {
+  if (!h) return 1;
+  if (h->multi) {
+    for (kidmp_handle* c : h->multi->dev) if (kidmp_enable_rates(c, on)) return fail(h, "%s", c->err.c_str());
+    return 0;
+  }
+  DevGuard guard_(h->device);
+  h->rates_on = on != 0;
+  if (!h->rates_on && h->d_rates_own) { CK(h, cudaDeviceSynchronize()); cudaFree(h->d_rates_own); h->d_rates_own = nullptr; }
+  if (h->rates_on && !h->d_rates_own && h->d_state)
+    CK(h, cudaMalloc((void**)&h->d_rates_own, (size_t)h->ncol * h->nz * KIDMP_NRATES * 4));
+  return 0;
+}
+
+int kidmp_get_rates(kidmp_handle* h, int layout, float* rates) {
+  if (!h || !rates) return 1;
+  if (h->multi) {
+    MultiCtx* m = h->multi;
+    if (layout != KIDMP_K_FASTEST) return fail(h, "get_rates: a multi-device handle returns KIDMP_K_FASTEST rates");
+    const int n = (int)m->dev.size();
+    for (int d = 0; d < n; ++d) {
+      kidmp_handle* c = m->dev[d];
+      if (!c->d_rates_own) return fail(h, "get_rates: kidmp_enable_rates and a step first");
+      long c0, c1;
+      shard(m->ncol ? m->ncol : c->ncol, d, n, c0, c1);
+      std::vector<float> part((size_t)KIDMP_NRATES * c->ncol * c->nz);
+      if (kidmp_get_rates(c, layout, part.data())) return fail(h, "%s", c->err.c_str());
+      const long total = m->ncol ? m->ncol : c->ncol;
+      for (int r = 0; r < KIDMP_NRATES; ++r)
+        memcpy(rates + ((size_t)r * total + c0) * c->nz, part.data() + (size_t)r * c->ncol * c->nz, (size_t)c->ncol * c->nz * 4);
+    }
+    return 0;
+  }
+  if (!h->d_rates_own || !h->d_state) return fail(h, "get_rates: kidmp_enable_rates and a step on the resident state first");
+  DevGuard guard_(h->device);
+  const size_t n = (size_t)h->ncol * h->nz;
+  CK(h, cudaStreamWaitEvent(h->stream, h->ev_done, 0));
+  if (layout == KIDMP_COL_FASTEST || h->ncol == 1) {
+    CK(h, cudaMemcpyAsync(rates, h->d_rates_own, n * KIDMP_NRATES * 4, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    dim3 g((unsigned)((h->ncol + 31) / 32), (unsigned)((h->nz + 31) / 32)), b(32, 8);
+    for (int r = 0; r < KIDMP_NRATES; ++r) {           // [nz][ncol] -> KiD's (k,i) order, plane by plane through the staging buffer
+      k_transpose<<<g, b, 0, h->stream>>>(h->d_rates_own + n * r, h->d_stage, h->ncol, h->nz, 0);
+      ++h->launches;
+      CK(h, cudaMemcpyAsync(rates + n * r, h->d_stage, n * 4, cudaMemcpyDeviceToHost, h->stream));
+      CK(h, cudaStreamSynchronize(h->stream));
+    }
+  }
+  CK(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -972,7 +1053,7 @@ int kidmp_upload(kidmp_handle* h, int layout, const float* const fields[KIDMP_NF
   }
   if (!h || !h->d_state) return h ? fail(h, "upload before state_alloc") : 1;
   if (!fields || !p || !dz) return fail(h, "upload: null pointer");
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   for (int q = 0; q < KIDMP_NFIELDS; ++q) {
     if (!fields[q]) return fail(h, "upload: field %d is null", q);
     if (put_field(h, layout, fields[q], field_ptr(h, q))) return 1;
@@ -990,7 +1071,7 @@ int kidmp_step_resident(kidmp_handle* h, float dt) {
     return 0;                                           // asynchronous on every device, like the single-device call
   }
   if (!h || !h->d_state) return h ? fail(h, "step before state_alloc") : 1;
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   CK(h, cudaEventRecord(h->ev0, h->stream));
   if (launch_step(h, resident_args(h, dt), h->stream)) return 1;
   CK(h, cudaEventRecord(h->ev1, h->stream));
@@ -1000,7 +1081,7 @@ int kidmp_step_resident(kidmp_handle* h, float dt) {
 int kidmp_download(kidmp_handle* h, int layout, float* const fields[KIDMP_NFIELDS], float* ppt) {
   if (h && h->multi) return multi_copy(h, layout, fields, nullptr, nullptr, ppt, false);
   if (!h || !h->d_state) return h ? fail(h, "download before state_alloc") : 1;
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   if (fields)
     for (int q = 0; q < KIDMP_NFIELDS; ++q)
       if (fields[q] && get_field(h, layout, field_ptr(h, q), fields[q])) return 1;
@@ -1082,7 +1163,7 @@ int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout, float* 
   // (with a process-rate buffer set the whole domain goes through the resident path: the buffer is [36][nz][ncol] of the domain)
   if (layout == KIDMP_COL_FASTEST && ncol >= 2 * h->pipe_chunk && nz >= 2 && nz <= 256 && dt > 0.f && !h->d_rates) {
     for (int q = 0; q < KIDMP_NFIELDS; ++q) if (!fields[q]) return fail(h, "step: field %d is null", q);
-    cudaSetDevice(h->device);
+    DevGuard guard_(h->device);
     return step_pipelined(h, ncol, nz, dt, fields, p, dz, ppt, ncol);
   }
   if (kidmp_state_alloc(h, ncol, nz)) return 1;
@@ -1108,7 +1189,7 @@ int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt, float* const
   if (!h) return 1;
   if (h->multi) return fail(h, "step_device: device pointers belong to one device; use a single-device handle per GPU");
   if (!d_fields || !d_p || !d_dz || !d_ppt) return fail(h, "step_device: null pointer");
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   StepArgs a{};
   a.ncol = ncol; a.ld = ncol; a.nz = nz; a.dt = dt; a.rates = h->d_rates;
   for (int q = 0; q < KIDMP_NFIELDS; ++q) { if (!d_fields[q]) return fail(h, "step_device: field %d is null", q); a.f[q] = d_fields[q]; }
@@ -1136,7 +1217,7 @@ const char* kidmp_rate_names(void) {
 int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
   if (!h || !out) return 1;
   if (h->multi) return multi_diag(h, out);
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   CK(h, cudaStreamWaitEvent(h->stream, h->ev_done, 0));   // the last step may have run on a caller's stream
   CK(h, cudaMemcpyAsync(out, h->d_diag, KIDMP_NDIAG * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaMemsetAsync(h->d_diag, 0, KIDMP_NDIAG * 8, h->stream));
@@ -1157,7 +1238,7 @@ int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in) 
   const bool radii = w->re_cloud && w->re_ice && w->re_snow;
   const long ncol = (long)w->ni * w->nj;
   if (kidmp_state_alloc(h, ncol, w->nk)) return 1;
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   const size_t n = (size_t)ncol * w->nk, n2 = (size_t)ncol;
   // device staging: 12 three-dimensional inputs, the per-column dz in step layout, 3 radii, 7 two-dimensional arrays
   const size_t dfloats = (12 + 1 + 3) * n + 7 * n2;
@@ -1248,7 +1329,7 @@ int kidmp_last_kernel_ms(kidmp_handle* h, float* out, int n) {
   if (!h || !out) return 1;
   if (h->multi) return kidmp_last_kernel_ms(h->multi->dev[0], out, n);
   if (!h->timing_valid) return fail(h, "last_kernel_ms: set_option(\"timing\", 1) before the step");
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   CK(h, cudaEventSynchronize(h->ev_k[KT_N]));
   for (int q = 0; q < n && q < KT_N; ++q) CK(h, cudaEventElapsedTime(out + q, h->ev_k[q], h->ev_k[q + 1]));
   return 0;
@@ -1267,7 +1348,7 @@ int kidmp_step_stats(kidmp_handle* h, long out[8]) {
   }
   for (int q = 0; q < 8; ++q) out[q] = 0;
   if (!h->d_cellmeta) return 0;
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   CK(h, cudaEventSynchronize(h->ev_done));
   int meta[8], cloudy = 0;
   CK(h, cudaMemcpy(meta, h->d_cellmeta, sizeof meta, cudaMemcpyDeviceToHost));
@@ -1284,7 +1365,7 @@ int kidmp_sync(kidmp_handle* h) {
     for (kidmp_handle* c : h->multi->dev) if (kidmp_sync(c)) return fail(h, "%s", c->err.c_str());
     return 0;
   }
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   CK(h, cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1300,7 +1381,7 @@ int kidmp_last_step_ms(kidmp_handle* h, float* step_ms) {
     }
     return 0;
   }
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   if (!h->last_on_own_stream) return fail(h, "last_step_ms: the last step ran on a caller's stream; time it there");
   CK(h, cudaEventSynchronize(h->ev1));
   CK(h, cudaEventElapsedTime(step_ms, h->ev0, h->ev1));
@@ -1323,7 +1404,7 @@ int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, f
   }
   if (!(r_on_cp > 0.f) || !(dt > 0.f)) return fail(h, "kid_interface: dt and r_on_cp must be positive");
   if (kidmp_state_alloc(h, c->nx, c->nz)) return 1;
-  cudaSetDevice(h->device);
+  DevGuard guard_(h->device);
   const size_t n = (size_t)c->nx * c->nz;
   const int nplanes = 7 + 21 + 9;
   if (h->kid_floats < n * nplanes) {

@@ -29,6 +29,8 @@ module mphys_thompson09n
      real(c_float)  :: set_Nc
      integer(c_int) :: iiwarm, l_sediment, wp_double, device, reuse_tables
      type(c_ptr)    :: table_cache_path
+     integer(c_int) :: ndev                       ! > 1: one handle over ndev GPUs, columns cut into ndev ranges
+     type(c_ptr)    :: device_ids                 ! ndev CUDA ordinals, c_null_ptr = 0 .. ndev-1
   end type kidmp_config
 
   ! include/kidmp.h :: kidmp_kid_columns
@@ -69,7 +71,19 @@ module mphys_thompson09n
        import :: c_int, c_ptr
        type(c_ptr), value :: handle
      end function kidmp_finalize
-     ! tuning knobs that never change a result, e.g. kidmp_set_option(handle, 'units'//c_null_char, 1_c_int)
+     ! the 36 process rates that mp_thompson saves with save_dg (M:2963-3120): the handle keeps them, the host fetches them
+     integer(c_int) function kidmp_enable_rates(handle, on) bind(C, name='kidmp_enable_rates')
+       import :: c_int, c_ptr
+       type(c_ptr), value :: handle
+       integer(c_int), value :: on
+     end function kidmp_enable_rates
+     integer(c_int) function kidmp_get_rates(handle, layout, rates) bind(C, name='kidmp_get_rates')
+       import :: c_int, c_ptr, c_float
+       type(c_ptr), value :: handle
+       integer(c_int), value :: layout
+       real(c_float), intent(out) :: rates(*)
+     end function kidmp_get_rates
+     ! tuning knobs that never change a result, e.g. kidmp_set_option(handle, 'chunk'//c_null_char, 262144_c_int)
      integer(c_int) function kidmp_set_option(handle, name, value) bind(C, name='kidmp_set_option')
        import :: c_int, c_ptr, c_char
        type(c_ptr), value :: handle
@@ -92,6 +106,15 @@ module mphys_thompson09n
   type(c_ptr), save :: kidmp_handle = c_null_ptr
   character(kind=c_char, len=64), target, save :: cache_path = 'run_data/kidmp_tables.bin'//c_null_char
 
+  ! switch for the per-level process-rate diagnostics of M:2963-3120 (36 rates x nz x nx floats back per call)
+  logical :: save_process_rates = .true.
+  integer, save :: kidmp_ndev = 1                 ! set > 1 before the first call to spread the nx columns over several GPUs
+  ! the rates in the order of kidmp_rate_names(): 30 ice-phase rates, then the 6 warm ones (the reference's order)
+  character(7), parameter :: rate_name(36) = (/ 'pri_inu', 'pri_ide', 'prs_ide', 'prs_sde', 'prg_gde', 'pri_wfz', 'prs_scw', &
+       'prg_scw', 'prg_gcw', 'pri_ihm', 'pri_rfz', 'prs_iau', 'prs_sci', 'pri_rci', 'pni_inu', 'pni_ihm', 'pni_wfz', 'pni_rfz', &
+       'pni_ide', 'pni_iau', 'pni_sci', 'pni_rci', 'prr_sml', 'prr_gml', 'pnr_rcs', 'pnr_rcg', 'pnr_rci', 'pnr_sml', 'pnr_gml', &
+       'pnr_rfz', 'prr_wau', 'prr_rcw', 'prv_rev', 'pnr_wau', 'pnr_rev', 'pnr_rcr' /)
+
   ! order of the hydrometeor planes handed to the library: (ih, imom) of hydrometeors(k,i,ih)%moments(1,imom)
   integer, parameter :: plane_ih(7)   = (/1, 2, 2, 3, 3, 4, 5/)   ! cloud, rain, rain, ice, ice, snow, graupel
   integer, parameter :: plane_imom(7) = (/1, 1, 2, 1, 2, 1, 1/)   ! mass, mass, number, mass, number, mass, mass
@@ -102,7 +125,8 @@ contains
 
     real(c_float), target, save, allocatable :: hyd(:,:,:), hyd_adv(:,:,:), hyd_div(:,:,:), hyd_mphys(:,:,:)
     real(c_float), target, save, allocatable :: th(:,:), th_adv(:,:), th_div(:,:), ex(:,:), q(:,:), q_adv(:,:), q_div(:,:)
-    real(c_float), target, save, allocatable :: dth_mphys(:,:), dq_mphys(:,:), ppt(:,:), dzc(:)
+    real(c_float), target, save, allocatable :: dth_mphys(:,:), dq_mphys(:,:), ppt(:,:), dzc(:), rates(:,:,:)
+    integer :: r, r0
     real :: pptrain_2d(nx), pptsnow_2d(nx), pptgraul_2d(nx), pptice_2d(nx), pptrain_2d_prof(nz,nx)
     type(kidmp_config) :: cfg
     type(kidmp_kid_columns) :: c
@@ -117,6 +141,8 @@ contains
        cfg%device = 0
        cfg%reuse_tables = merge(1, 0, l_reuse_thompson_lookup)
        cfg%table_cache_path = c_loc(cache_path)
+       cfg%ndev = kidmp_ndev
+       cfg%device_ids = c_null_ptr
        rc = kidmp_init(cfg, kidmp_handle)
        if (rc /= 0) then
           print *, 'kidmp_init failed'      ! text: kidmp_last_error(c_null_ptr)
@@ -125,6 +151,10 @@ contains
        allocate(hyd(nz,nx,7), hyd_adv(nz,nx,7), hyd_div(nz,nx,7), hyd_mphys(nz,nx,7))
        allocate(th(nz,nx), th_adv(nz,nx), th_div(nz,nx), ex(nz,nx), q(nz,nx), q_adv(nz,nx), q_div(nz,nx))
        allocate(dth_mphys(nz,nx), dq_mphys(nz,nx), ppt(nx,4), dzc(nz))
+       if (save_process_rates) then
+          allocate(rates(nz,nx,36))
+          rc = kidmp_enable_rates(kidmp_handle, 1_c_int)
+       end if
        micro_unset=.False.
     end if
 
@@ -174,6 +204,30 @@ contains
           end do
        end do
     end do
+
+    ! the per-level process rates that mp_thompson itself saves (M:2963-3120): 36 save_dg calls per level, in the
+    ! reference's order (column by column, level by level; the 30 ice-phase rates only when .not. iiwarm), with the
+    ! (k, value) form for a single column and the (k, i, value) form otherwise
+    if (save_process_rates) then
+       rc = kidmp_get_rates(kidmp_handle, 0_c_int, rates)        ! KIDMP_K_FASTEST: rates(k,i,r)
+       if (rc /= 0) then
+          print *, 'kidmp_get_rates failed'
+          stop 1
+       end if
+       r0 = 1
+       if (iiwarm) r0 = 31
+       do i=1,nx
+          do k=1,nz
+             do r=r0,36
+                if (nx == 1) then
+                   call save_dg(k, rates(k,i,r), rate_name(r), i_dgtime, units='/kg/s', dim='z')
+                else
+                   call save_dg(k, i, rates(k,i,r), rate_name(r), i_dgtime, units='/kg/s', dim='z,x')
+                end if
+             end do
+          end do
+       end do
+    end if
 
     ! diagnostics exactly as the reference saves them (I:155-192, I:248-308); ppt(:,1..4) = rain, ice, snow, graupel
     pptrain_2d(:) = ppt(:,1); pptice_2d(:) = ppt(:,2); pptsnow_2d(:) = ppt(:,3); pptgraul_2d(:) = ppt(:,4)

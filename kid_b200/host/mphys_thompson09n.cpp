@@ -36,6 +36,8 @@ int i_dgtime = 0;
 namespace mphys_thompson09n {
 
 bool micro_unset = true;
+bool save_process_rates = true;
+int ndev = 1;
 static kidmp_handle* g_handle = nullptr;
 static std::string g_error;
 // planes handed to the library: (ih, imom) of hydrometeors(k,i,ih)%moments(1,imom), 0-based here
@@ -62,8 +64,11 @@ int mphys_thompson09_interfacen() {
     cfg.device = 0;
     cfg.reuse_tables = switches::l_reuse_thompson_lookup ? 1 : 0;
     cfg.table_cache_path = "run_data/kidmp_tables.bin";
+    cfg.ndev = ndev;
+    cfg.device_ids = nullptr;
     const int rc = kidmp_init(&cfg, &g_handle);
     if (rc) { g_error = kidmp_last_error(nullptr); return rc; }
+    if (save_process_rates && kidmp_enable_rates(g_handle, 1)) { g_error = kidmp_last_error(g_handle); return 1; }
     micro_unset = false;
   }
   const int np = namelists::iiwarm ? 3 : 7;
@@ -95,6 +100,23 @@ int mphys_thompson09_interfacen() {
     for (int i = 0; i < nx; ++i)
       for (int k = 0; k < nz; ++k)
         dhydrometeors_mphys[kih(k, i, plane_ih[m])].moments[0][plane_im[m]] = out[m][ki(k, i)];
+
+  // the per-level process rates that mp_thompson itself saves (M:2963-3120): 36 save_dg calls per level in the reference's
+  // order - column by column, level by level, the 30 ice-phase rates only when not iiwarm
+  if (diagnostics::save_dg && save_process_rates) {
+    static std::vector<float> rates;
+    rates.resize(n * KIDMP_NRATES);
+    if (kidmp_get_rates(g_handle, KIDMP_K_FASTEST, rates.data())) { g_error = kidmp_last_error(g_handle); return 1; }
+    static std::vector<std::string> names;
+    if (names.empty()) {
+      std::string all = kidmp_rate_names();
+      for (size_t a = 0; a < all.size();) { const size_t b = all.find(',', a); names.push_back(all.substr(a, b - a)); a = b == std::string::npos ? all.size() : b + 1; }
+    }
+    for (int i = 0; i < nx; ++i)
+      for (int k = 0; k < nz; ++k)
+        for (int r = namelists::iiwarm ? 30 : 0; r < KIDMP_NRATES; ++r)
+          diagnostics::save_dg(std::vector<float>(1, rates[(size_t)r * n + ki(k, i)]), names[r], "/kg/s", nx == 1 ? "z" : "z,x");
+  }
 
   // diagnostics as the reference saves them (I:155-192 for nx == 1, I:248-308 otherwise); ppt = rain, ice, snow, graupel
   if (diagnostics::save_dg) {

@@ -47,6 +47,8 @@ extern int i_dgtime;
 
 namespace mphys_thompson09n {
 extern bool micro_unset;                                  // I:22
+extern bool save_process_rates;                           // the 36 per-level save_dg rates of M:2963-3120 (default on)
+extern int ndev;                                          // > 1 before the first call: the nx columns over several GPUs
 // returns 0, or the non-zero status of the failing kidmp_* call (text: last_error())
 int mphys_thompson09_interfacen();
 inline int mphys_thompson09_interface() { return mphys_thompson09_interfacen(); }   // spelling used by BASELINE.json

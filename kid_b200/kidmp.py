@@ -35,6 +35,7 @@ SYMBOLS = {
     "kidmp_init": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "kidmp_finalize": (C.c_int, [C.c_void_p]),
     "kidmp_last_error": (C.c_char_p, [C.c_void_p]),
+    "kidmp_build_id": (C.c_char_p, []),
     "kidmp_table_build_ms": (C.c_double, [C.c_void_p]),
     "kidmp_table_size": (C.c_long, [C.c_void_p, C.c_char_p]),
     "kidmp_get_table": (C.c_int, [C.c_void_p, C.c_char_p, _dp, C.c_long]),
@@ -51,6 +52,8 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "kidmp_set_rates_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kidmp_rate_names": (C.c_char_p, []),
+    "kidmp_enable_rates": (C.c_int, [C.c_void_p, C.c_int]),
+    "kidmp_get_rates": (C.c_int, [C.c_void_p, C.c_int, _fp]),
     "kidmp_diag": (C.c_int, [C.c_void_p, _dp]),
     "kidmp_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "kidmp_gpu_launches": (C.c_long, [C.c_void_p]),
@@ -105,12 +108,8 @@ def load(build_if_missing=True):
             # (one build instead of eight, and nobody dlopens a file that is being replaced)
             if os.path.exists(path) and int(os.environ.get("LOCAL_RANK", "0")) != 0:
                 build_if_missing = False
-            if build_if_missing:
-                try:
-                    _build.build()
-                except Exception:
-                    if not os.path.exists(_build.LIB):
-                        raise
+            if build_if_missing and _build.needs_build():
+                _build.build(force=True)            # a compile error is an error: never fall back to a stale binary
         L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)
@@ -317,6 +316,16 @@ class Thompson:
 
     def set_rates_buffer(self, ptr):
         self._ck(self._L.kidmp_set_rates_buffer(self.h, C.c_void_p(int(ptr)) if ptr else None))
+
+    def enable_rates(self, on=True):
+        self._ck(self._L.kidmp_enable_rates(self.h, int(bool(on))))
+
+    def get_rates(self, ncol, nz, layout="k_fastest"):
+        """The 36 save_dg rates of the last step of the resident state: (36, ncol, nz) for 'k_fastest', (36, nz, ncol) else."""
+        lay = K_FASTEST if layout == "k_fastest" else COL_FASTEST
+        out = np.zeros((36, ncol, nz) if lay == K_FASTEST else (36, nz, ncol), np.float32)
+        self._ck(self._L.kidmp_get_rates(self.h, lay, out.ctypes.data_as(_fp)))
+        return out
 
     @property
     def rate_names(self):

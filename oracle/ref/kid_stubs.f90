@@ -41,7 +41,8 @@ module diagnostics
   integer :: i_dgtime = 1
   integer :: n_save_dg = 0                      ! calls seen (the driver reports it)
   interface save_dg
-     module procedure save_dg_scalar, save_dg_level, save_dg_1d, save_dg_2d
+     module procedure save_dg_scalar, save_dg_level_r4, save_dg_level_r8, save_dg_levelx_r4, save_dg_levelx_r8, &
+          save_dg_1d, save_dg_2d
   end interface save_dg
 contains
   subroutine save_dg_scalar(value, name, itime, units, dim)          ! I:162
@@ -51,14 +52,38 @@ contains
     character(*), intent(in), optional :: units, dim
     n_save_dg = n_save_dg + 1
   end subroutine save_dg_scalar
-  subroutine save_dg_level(k, value, name, itime, units, dim)        ! M:2967: one level of a profile
+  subroutine save_dg_level_r8(k, value, name, itime, units, dim)     ! M:2967: one level of a profile (the rates are DOUBLE PRECISION)
     integer, intent(in) :: k
-    class(*), intent(in) :: value                                    ! the rates are DOUBLE PRECISION, some callers pass REAL
+    double precision, intent(in) :: value
     character(*), intent(in) :: name
     integer, intent(in) :: itime
     character(*), intent(in), optional :: units, dim
     n_save_dg = n_save_dg + 1
-  end subroutine save_dg_level
+  end subroutine save_dg_level_r8
+  subroutine save_dg_level_r4(k, value, name, itime, units, dim)     ! the same from a REAL caller (the kidmp shim)
+    integer, intent(in) :: k
+    real, intent(in) :: value
+    character(*), intent(in) :: name
+    integer, intent(in) :: itime
+    character(*), intent(in), optional :: units, dim
+    n_save_dg = n_save_dg + 1
+  end subroutine save_dg_level_r4
+  subroutine save_dg_levelx_r8(k, i, value, name, itime, units, dim) ! M:3046: one level of one column (nx > 1)
+    integer, intent(in) :: k, i
+    double precision, intent(in) :: value
+    character(*), intent(in) :: name
+    integer, intent(in) :: itime
+    character(*), intent(in), optional :: units, dim
+    n_save_dg = n_save_dg + 1
+  end subroutine save_dg_levelx_r8
+  subroutine save_dg_levelx_r4(k, i, value, name, itime, units, dim)
+    integer, intent(in) :: k, i
+    real, intent(in) :: value
+    character(*), intent(in) :: name
+    integer, intent(in) :: itime
+    character(*), intent(in), optional :: units, dim
+    n_save_dg = n_save_dg + 1
+  end subroutine save_dg_levelx_r4
   subroutine save_dg_1d(field, name, itime, units, dim)              ! I:255
     real, intent(in) :: field(:)
     character(*), intent(in) :: name

@@ -88,3 +88,11 @@ def test_cxx_host_twin_builds_and_fails_cleanly_without_a_gpu(tmp_path):
     np.zeros(7 * nx * nz + nz + 21 * nx * nz, np.float32).tofile(src)
     r = subprocess.run([exe, str(src), str(tmp_path / "out.bin"), str(nx), str(nz), "1.0", "0"], capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU path" in r.stderr
+
+
+def test_library_is_built_from_the_sources_in_the_tree():
+    """kidmp_build_id() = hash of the sources and flags (kid_b200/build.py::source_id): a shipped binary of other sources
+    does not pass for the tree."""
+    from kid_b200 import build, kidmp
+    L = kidmp.load()
+    assert L.kidmp_build_id().decode() == build.source_id() == build.library_id()

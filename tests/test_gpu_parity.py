@@ -245,6 +245,64 @@ def test_process_rate_buffer(gpu_mixed, oracle_mixed):
     assert nbad <= 5
 
 
+def test_host_side_process_rates(gpu_mixed):
+    """kidmp_enable_rates / kidmp_get_rates (what the Fortran shim's save_dg calls are fed from): the same numbers as the
+    caller's device buffer, zero for clear-sky columns, in both layouts."""
+    import torch
+    g = np.load(GOLD)
+    ncol, nz = g["in/p"].shape[1], 60
+    dev = torch.full((36, nz, ncol), float("nan"), dtype=torch.float32, device="cuda")
+    gpu_mixed.set_rates_buffer(dev.data_ptr())
+    s = {k: g["in/" + k].copy() for k in FIELDS}
+    gpu_mixed.step(10.0, s, g["in/p"].copy(), g["in/dz"])
+    gpu_mixed.set_rates_buffer(0)
+    want = np.nan_to_num(dev.cpu().numpy(), nan=0.0)          # untouched (clear-sky) columns: no process at all
+    gpu_mixed.enable_rates(True)
+    try:
+        s2 = {k: g["in/" + k].copy() for k in FIELDS}
+        gpu_mixed.step(10.0, s2, g["in/p"].copy(), g["in/dz"])
+        got = gpu_mixed.get_rates(ncol, nz, layout="col_fastest")
+        got_k = gpu_mixed.get_rates(ncol, nz, layout="k_fastest")
+    finally:
+        gpu_mixed.enable_rates(False)
+    for k in FIELDS:
+        assert np.array_equal(s[k], s2[k]), k
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_k, want.transpose(0, 2, 1))
+    assert np.abs(want).max() > 0
+
+
+@pytest.mark.parametrize("layout", ["col_fastest", "k_fastest"])
+def test_multi_device_handle_equals_single_device(layout):
+    """kidmp_config::ndev = 2: one handle, the columns cut into two ranges, one per GPU, no exchange on the data path.  Column
+    by column the same bits as a single-device handle; kidmp_diag returns the NCCL all-reduced sums of both devices."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in this process")
+    from kid_b200 import synth
+    from kid_b200.kidmp import Thompson
+    ncol, nz = (150001, 60) if layout == "col_fastest" else (5003, 60)
+    st, p, dz = synth.make_domain(ncol, nz=nz, col0=250000, nx=1024)
+    conv = (lambda a: a.numpy().copy()) if layout == "col_fastest" else (lambda a: np.ascontiguousarray(a.numpy().T))
+    one, two = Thompson(device=0), Thompson(devices=[0, 1])
+    try:
+        a = {k: conv(v) for k, v in st.items()}
+        b = {k: conv(v) for k, v in st.items()}
+        pa, pb = conv(p), conv(p)
+        for _ in range(2):
+            ppt_a = one.step(10.0, a, pa, dz.numpy(), layout=layout)
+            ppt_b = two.step(10.0, b, pb, dz.numpy(), layout=layout)
+        for k in FIELDS:
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(ppt_a, ppt_b)
+        da, db = one.diag(), two.diag()
+        assert da[6] == db[6] and da[7] == db[7] == 2 * ncol
+        assert np.allclose(da[:6], db[:6], rtol=1e-12)
+        assert two._L.kidmp_num_devices(two.h) == 2
+    finally:
+        one.close(); two.close()
+
+
 def test_step_device_on_a_torch_stream(gpu_mixed, oracle_mixed):
     import torch
     from kid_b200 import synth
@@ -385,7 +443,9 @@ def test_cxx_host_twin(gpu_mixed, tmp_path):
     r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(nx), str(nz), str(dt), "0"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    assert "save_dg_calls=11" in r.stdout          # nx > 1: 5 means + 5 per-column records + total_ppt_level (I:248-308)
+    # nx > 1: 5 means + 5 per-column records + total_ppt_level (I:248-308), and the 36 process rates of every level of every
+    # column that mp_thompson itself saves (M:3046-3120)
+    assert "save_dg_calls=%d" % (11 + 36 * nx * nz) in r.stdout
     out = np.fromfile(tmp_path / "out.bin", np.float32)
     roc = float(np.float32(287.05) / np.float32(1005.0))             # the driver's physconst defaults, evaluated in f32
     ref = gpu_mixed.kid_interface(kid, dt, 1.0e5, roc)
