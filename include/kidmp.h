@@ -77,7 +77,10 @@ int kidmp_column(kidmp_handle* h, int nz, float dt,
                  const float* p, const float* dz, float* ppt4);
 
 /* the body of `do i = 1, nx` (I:54-246) for ncol independent columns: host arrays in, host
- * arrays out (H2D, kernels, D2H inside the call).  dz is one shared vector of nz (I:63). */
+ * arrays out (H2D, kernels, D2H inside the call).  dz is one shared vector of nz (I:63).
+ * Large KIDMP_COL_FASTEST domains flow through the device in chunks on three streams.  When the nine field arrays are
+ * PINNED host memory (cudaHostAlloc / cudaHostRegister), only the columns the step changed travel back - a clear-sky column
+ * is returned bit for bit by the reference too (M:1540) - written by a kernel straight into the host arrays. */
 int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout,
                float* const fields[KIDMP_NFIELDS], const float* p, const float* dz, float* ppt);
 
@@ -169,7 +172,8 @@ int kidmp_num_devices(const kidmp_handle* h);
 /* bookkeeping for benchmarks */
 long kidmp_gpu_launches(const kidmp_handle* h);         /* kernels launched so far          */
 /* counts of the last launch of the step kernels (the last chunk of the last step; waits for it): 0 cloudy columns, 1 busy
- * cells, 2-5 busy cells of the warm / ice / mixed-without-rain / full cell kernels, 6 columns with sedimentation sub-steps */
+ * cells, 2-5 busy cells of the warm / ice / mixed-without-rain / full cell kernels, 6 columns with sedimentation sub-steps,
+ * 7 whether the last kidmp_step returned only the changed columns (pinned host arrays, see kidmp_step) */
 int kidmp_step_stats(kidmp_handle* h, long out[8]);
 /* per-kernel device times of the last launch of the step kernels, after kidmp_set_option(h, "timing", 1): in that mode the
  * kernels of a launch run one after the other on one stream with a CUDA event after each group (normally two of them run

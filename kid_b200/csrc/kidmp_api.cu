@@ -58,6 +58,7 @@ struct kidmp_handle {
   cudaStream_t aux = nullptr;                             // k_substeps runs beside k_finish
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_dag[4] = {};
   // "timing" option: the kernels of a launch run one after the other on one stream with an event after each
+  bool last_zero_copy = false;                            // the last kidmp_step wrote the changed columns straight into pinned host arrays
   bool timing = false; bool timing_valid = false;
   cudaEvent_t ev_k[KT_N + 1] = {};
   double* d_coldiag = nullptr;                            // [2][cols] per-column water paths for the ordered domain sums
@@ -1121,6 +1122,17 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
   }
   CK(h, cudaMemcpyAsync(h->d_pipe_dz, dz, (size_t)nz * 4, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaEventRecord(h->ev0, h->stream));
+  // Pinned output arrays (cudaHostAlloc / cudaHostRegister: what a host that cares about transfer speed uses): only the
+  // columns the step changed go back, written by a kernel straight into the host arrays (k_scatter_host); pageable arrays
+  // get the whole chunk back with a copy.  KIDMP_ZEROCOPY=0 switches the first path off.
+  HostFields hf{};
+  bool zero_copy = !(getenv("KIDMP_ZEROCOPY") && atoi(getenv("KIDMP_ZEROCOPY")) == 0);
+  for (int q = 0; q < KIDMP_NFIELDS && zero_copy; ++q) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, fields[q]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) { zero_copy = false; cudaGetLastError(); }
+    else hf.f[q] = (float*)at.devicePointer;
+  }
+  h->last_zero_copy = zero_copy;
   const size_t hpitch = (size_t)hld * 4, ppitch = (size_t)ncol * 4;
   long c0 = 0;
   for (int it = 0; c0 < ncol; ++it, c0 += chunk) {
@@ -1143,8 +1155,18 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
     if (launch_step(h, a, h->stream)) return 1;
     CK(h, cudaEventRecord(h->pipe_ev[b][1], h->stream));
     CK(h, cudaStreamWaitEvent(h->copy_out, h->pipe_ev[b][1], 0));
-    for (int q = 0; q < KIDMP_NFIELDS; ++q)
-      CK(h, cudaMemcpy2DAsync(fields[q] + c0, hpitch, base + cells * q, dpitch, dpitch, nz, cudaMemcpyDeviceToHost, h->copy_out));
+    if (zero_copy) {
+      HostFields hc = hf;
+      for (int q = 0; q < KIDMP_NFIELDS; ++q) hc.f[q] += c0;
+      StepArgs sa = a;
+      sa.colflag = h->d_colflag;                     // (of this chunk: the next chunk's kernels follow on the same stream)
+      k_scatter_host<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(sa, hc, hld);
+      ++h->launches;
+      CK(h, cudaEventRecord(h->pipe_ev[b][1], h->stream));
+      CK(h, cudaStreamWaitEvent(h->copy_out, h->pipe_ev[b][1], 0));
+    } else
+      for (int q = 0; q < KIDMP_NFIELDS; ++q)
+        CK(h, cudaMemcpy2DAsync(fields[q] + c0, hpitch, base + cells * q, dpitch, dpitch, nz, cudaMemcpyDeviceToHost, h->copy_out));
     if (ppt) CK(h, cudaMemcpy2DAsync(h->h_ppt + c0, ppitch, d_ppt, dpitch, dpitch, 4, cudaMemcpyDeviceToHost, h->copy_out));
     CK(h, cudaEventRecord(h->pipe_ev[b][2], h->copy_out));
   }
@@ -1356,6 +1378,7 @@ int kidmp_step_stats(kidmp_handle* h, long out[8]) {
   out[0] = cloudy; out[1] = meta[KC_N];
   for (int q = 0; q < KC_N; ++q) out[2 + q] = meta[q];
   out[6] = meta[5];
+  out[7] = h->last_zero_copy ? 1 : 0;
   return 0;
 }
 

@@ -97,17 +97,24 @@ __global__ void __launch_bounds__(LIST_TILE) k_cell_count(StepArgs a) {
   __syncwarp();
   const bool in_range = col < a.ncol;
   const unsigned char* cp = a.cls + col;
-#pragma unroll 4
-  for (int k = 0; k < nz; ++k) {
-    const unsigned c = in_range ? cp[(long)k * a.ncol] : 0u;
-    const bool busy = (c & CLS_BUSY) != 0u;
-    const unsigned act = __ballot_sync(0xffffffffu, busy);
-    if (busy) {
-      const unsigned key = cell_key(c);
-      const unsigned m = __match_any_sync(act, key);
-      if (lane == __ffs(m) - 1) s_cnt[warp][key] += __popc(m);      // one leader per key, only this warp writes its row
+  constexpr int LB = 16;                                  // class bytes of 16 levels in flight at a time (the walk is latency-bound)
+#pragma unroll 1
+  for (int k0 = 0; k0 < nz; k0 += LB) {
+    unsigned cb[LB];
+#pragma unroll
+    for (int j = 0; j < LB; ++j) cb[j] = (in_range && k0 + j < nz) ? cp[(long)(k0 + j) * a.ncol] : 0u;
+#pragma unroll
+    for (int j = 0; j < LB; ++j) {
+      const unsigned c = cb[j];
+      const bool busy = (c & CLS_BUSY) != 0u;
+      const unsigned act = __ballot_sync(0xffffffffu, busy);
+      if (busy) {
+        const unsigned key = cell_key(c);
+        const unsigned m = __match_any_sync(act, key);
+        if (lane == __ffs(m) - 1) s_cnt[warp][key] += __popc(m);    // one leader per key, only this warp writes its row
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   __syncthreads();
   if (threadIdx.x < 64) {
@@ -161,9 +168,17 @@ __global__ void __launch_bounds__(LIST_TILE) k_cell_fill(StepArgs a) {
   const bool cloudy = in_range && ((gmask >> lane) & 1u);
   const unsigned char* cp = a.cls + col;
   unsigned bword = 0;                                     // busy bits of 32 levels of my column, for the column kernels
-#pragma unroll 2
-  for (int k = nz - 1; k >= 0; --k) {
-    const unsigned c = in_range ? cp[(long)k * a.ncol] : 0u;
+  constexpr int LB = 16;                                  // class bytes of 16 levels in flight at a time
+#pragma unroll 1
+  for (int k0 = nz - 1; k0 >= 0; k0 -= LB) {
+    unsigned cb[LB];
+#pragma unroll
+    for (int j = 0; j < LB; ++j) cb[j] = (in_range && k0 - j >= 0) ? cp[(long)(k0 - j) * a.ncol] : 0u;
+#pragma unroll
+  for (int j = 0; j < LB; ++j) {
+    const int k = k0 - j;
+    if (k < 0) break;
+    const unsigned c = cb[j];
     const bool busy = (c & CLS_BUSY) != 0u;
     const unsigned act = __ballot_sync(0xffffffffu, busy);
     if (busy) {
@@ -180,6 +195,7 @@ __global__ void __launch_bounds__(LIST_TILE) k_cell_fill(StepArgs a) {
     }
     __syncwarp();
     if ((k & 31) == 0) { if (cloudy) a.busy[(size_t)(k >> 5) * count + slot] = bword; bword = 0; }
+  }
   }
 }
 

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
     float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
     float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
     unsigned char* Gcls = a.cls + col;
-    bool no_micro = true, graupel = false;
+    bool no_micro = true, graupel = false, zeroed = false;
 #pragma unroll 4
     for (int k = 0; k < nz; ++k) {
       const long o = (long)k * ld;
@@ -194,11 +194,11 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
       if (qr > R1) sp |= CLS_QR;
       if (qs > R1) sp |= CLS_QS;
       if (qg > R1) { sp |= CLS_QG; graupel = true; }
-      if (!(qc > R1) && qc != 0.0f) Gqc[o] = 0.0f;
-      if (!(qi > R1) && (qi != 0.0f || ni != 0.0f)) { Gqi[o] = 0.0f; Gni[o] = 0.0f; }
-      if (!(qr > R1) && (qr != 0.0f || nr != 0.0f)) { Gqr[o] = 0.0f; Gnr[o] = 0.0f; }
-      if (!(qs > R1) && qs != 0.0f) Gqs[o] = 0.0f;
-      if (!(qg > R1) && qg != 0.0f) Gqg[o] = 0.0f;
+      if (!(qc > R1) && qc != 0.0f) { Gqc[o] = 0.0f; zeroed = true; }
+      if (!(qi > R1) && (qi != 0.0f || ni != 0.0f)) { Gqi[o] = 0.0f; Gni[o] = 0.0f; zeroed = true; }
+      if (!(qr > R1) && (qr != 0.0f || nr != 0.0f)) { Gqr[o] = 0.0f; Gnr[o] = 0.0f; zeroed = true; }
+      if (!(qs > R1) && qs != 0.0f) { Gqs[o] = 0.0f; zeroed = true; }
+      if (!(qg > R1) && qg != 0.0f) { Gqg[o] = 0.0f; zeroed = true; }
       const float tempc = t - 273.15f;
       const float qvsi = (tempc <= 0.0f) ? rsif(pr, t) : rslf(pr, t);
       float ssati = qv / qvsi - 1.f;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
       Gcls[(long)k * ncol] = (unsigned char)c;
     }
     active = !no_micro;
-    a.colflag[col] = active ? (graupel ? 1 : 0) : -1;
+    a.colflag[col] = active ? (graupel ? 1 : 0) : (zeroed ? -2 : -1);     // -1: the step leaves this column bit for bit as it was
     if (!active) {                                 // clear-sky column: nothing left to do
       a.ppt[col] = 0.f; a.ppt[ld + col] = 0.f; a.ppt[2 * ld + col] = 0.f; a.ppt[3 * ld + col] = 0.f;   // I:55-58
     }
@@ -424,6 +424,23 @@ __global__ void k_diag_reduce(const double* __restrict__ partial, int nblocks, d
     __syncthreads();
   }
   if (threadIdx.x == 0) diag[q] += s[0];
+}
+
+// The columns that the step changed, written straight into the caller's PINNED host arrays over PCIe (zero copy): a clear-sky
+// column comes back bit for bit as it went in (the early RETURN of M:1540), so only the cloudy columns - and the rare
+// clear one in which a species <= R1 was zeroed - need to travel.  One thread per column, lanes = neighbouring columns:
+// runs of changed columns become full 128-byte writes.
+struct HostFields { float* f[KIDMP_NFIELDS]; };
+__global__ void __launch_bounds__(128) k_scatter_host(StepArgs a, HostFields hf, long hld) {
+  const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.ncol || a.colflag[col] == -1) return;
+  const int nz = a.nz;
+#pragma unroll 2
+  for (int k = 0; k < nz; ++k) {
+    const long o = (long)k * a.ld + col, ho = (long)k * hld + col;
+#pragma unroll
+    for (int q = 0; q < KIDMP_NFIELDS; ++q) hf.f[q][ho] = a.f[q][o];
+  }
 }
 
 // layout conversion between KiD's (k,i) arrays [col][nz] and the device layout [nz][ncol]

@@ -145,7 +145,7 @@ struct StepArgs {
   float* ws;                   // [WS_N][nz][ws_cols] SoA workspace of the columns with sedimentation sub-steps (k_substeps)
   long ws_cols;
   unsigned char* cls;          // [nz][ncol] class byte of every cell (0 = idle)
-  int* colflag;                // [ncol] -1 clear sky (the early RETURN of M:1540), else bit 0 = graupel somewhere in the column
+  int* colflag;                // [ncol] < 0 clear sky (the early RETURN of M:1540; -2: a species <= R1 was zeroed, -1: untouched), else bit 0 = graupel somewhere in the column
   int* work_count;             // number of cloudy columns found by the classification kernel
   int* work_list;              // their column indices, compacted in column order (slot -> column)
   unsigned* work_mask;         // [ngroups] ballot of the cloudy lanes of every 32-column group

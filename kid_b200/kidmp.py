@@ -341,7 +341,8 @@ class Thompson:
         with sedimentation sub-steps."""
         out = (C.c_long * 8)()
         self._ck(self._L.kidmp_step_stats(self.h, out))
-        names = ("cloudy_columns", "busy_cells", "cells_warm", "cells_ice", "cells_mixed_no_rain", "cells_full", "substep_columns")
+        names = ("cloudy_columns", "busy_cells", "cells_warm", "cells_ice", "cells_mixed_no_rain", "cells_full", "substep_columns",
+                 "zero_copy_return")
         return {n: int(out[i]) for i, n in enumerate(names)}
 
     def last_kernel_ms(self):

@@ -303,6 +303,31 @@ def test_multi_device_handle_equals_single_device(layout):
         one.close(); two.close()
 
 
+def test_pinned_host_arrays_get_only_the_changed_columns_back(gpu_mixed):
+    """kidmp_step with pinned host arrays: the chunk pipeline writes the changed columns straight into them (k_scatter_host)
+    instead of copying every column back.  Same bits as with pageable arrays, clear-sky columns untouched, and a clear-sky
+    column in which a species <= R1 is zeroed (M:1412-1489) does come back."""
+    import torch
+    from kid_b200 import synth
+    ncol, nz = 140000, 60
+    st, p, dz = synth.make_domain(ncol, nz=nz, col0=200000, nx=1024)
+    clear = np.flatnonzero(~(sum(st[k] for k in ("qc", "qi", "qr", "qs", "qg")) > 0).any(0).numpy())
+    st["qs"][7, int(clear[5])] = 5e-13                       # below R1 in a clear-sky column: must come back as 0
+    a = {k: v.numpy().copy() for k, v in st.items()}
+    b = {k: v.clone().pin_memory() for k, v in st.items()}
+    bn = {k: v.numpy() for k, v in b.items()}
+    ppt_a = gpu_mixed.step(10.0, a, p.numpy().copy(), dz.numpy())
+    assert gpu_mixed.step_stats()["zero_copy_return"] == 0
+    ppt_b = gpu_mixed.step(10.0, bn, p.numpy().copy(), dz.numpy())
+    assert gpu_mixed.step_stats()["zero_copy_return"] == 1
+    for k in FIELDS:
+        assert np.array_equal(a[k], bn[k]), k
+    assert np.array_equal(ppt_a, ppt_b)
+    assert bn["qs"][7, int(clear[5])] == 0.0 and a["qs"][7, int(clear[5])] == 0.0
+    j = int(clear[9])
+    assert all(np.array_equal(bn[k][:, j], st[k][:, j].numpy()) for k in FIELDS)
+
+
 def test_step_device_on_a_torch_stream(gpu_mixed, oracle_mixed):
     import torch
     from kid_b200 import synth
