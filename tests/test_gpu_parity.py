@@ -121,6 +121,34 @@ def test_mixed_domain_one_step(gpu_mixed, oracle_mixed):
         np.testing.assert_allclose(pa, pb, rtol=1e-5, atol=1e-10)
 
 
+def test_cells_outside_tolerance_are_condensation_residuals(gpu_mixed, oracle_mixed):
+    """Decision U13.  The handful of cells per million whose hydrometeor content differs from the oracle by
+    more than 1e-5 are all of one kind: cloud water (once: rain) left over after condensation or evaporation took almost all of
+    it.  The Newton iteration of S11 (M:2784-2789) works in f32 on numbers of the size of qv, so its result carries one ulp
+    of qv (~5e-10 kg/kg) of rounding freedom (expf of the host's libm vs the f64-evaluated one here); a residual of 1e-5 ... 1e-7
+    kg/kg inherits that absolute difference.  Checked: every such cell is qc or qr, its difference is below two ulp of qv,
+    and temperature, vapour and total water of the cell agree to rounding."""
+    seen = 0
+    for kw, dt in ((dict(col0=7, cloudy_fraction=1.0, coherent=False), 1.0), (dict(col0=1000, cloudy_fraction=1.0, coherent=False), 20.0),
+                   (dict(col0=0, cloudy_fraction=0.6, coherent=False), 60.0)):
+        st, p, dz = _domain(4096, **kw)
+        a, pa, b, pb = _both(gpu_mixed, oracle_mixed, dt, st, p, dz)
+        for f in FIELDS:
+            den = np.maximum(np.abs(b[f].astype(np.float64)), 1e-12 if f.startswith("q") else (1e-3 if f.startswith("n") else 1.0))
+            rel = np.abs(a[f].astype(np.float64) - b[f]) / den
+            bad = np.argwhere(rel > 1e-5)
+            if len(bad) and f not in ("qc", "qr"):
+                assert f in ("nr",) and len(bad) <= 2, (f, len(bad))         # the number that belongs to such a rain residual
+                continue
+            for k, j in bad:
+                seen += 1
+                qv = float(b["qv"][k, j])
+                assert abs(float(a[f][k, j]) - float(b[f][k, j])) <= 2.5e-7 * qv + 1e-11, (f, k, j)
+                assert abs(float(a["t"][k, j]) - float(b["t"][k, j])) <= 1e-4
+                assert abs(float(a["qv"][k, j]) - float(b["qv"][k, j])) <= 2.5e-7 * qv
+    assert seen <= 30
+
+
 def test_conus_domain_one_step(gpu_mixed, oracle_mixed):
     st, p, dz = _domain(8192, col0=300000, nx=1024)            # the bench domain: ~30 % cloudy, coherent
     a, pa, b, pb = _both(gpu_mixed, oracle_mixed, 10.0, st, p, dz)

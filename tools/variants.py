@@ -27,9 +27,13 @@ def per(**kw):
 
 VARIANTS = {
     "base": [],
-    "fin20": ["-DK2_MINB=20"],
-    "fin24": ["-DK2_MINB=24"],
-    "fin32": ["-DK2_MINB=32"],
+    "free": per(WARM=(256, 4, 0), ICE=(256, 4, 0), MIXNR=(256, 3, 0), FULL=(256, 3, 0)),
+    "free128": per(WARM=(128, 8, 0), ICE=(128, 8, 0), MIXNR=(128, 6, 0), FULL=(128, 6, 0)),
+    "ice5": per(ICE=(256, 5, 11), WARM=(256, 5, 11)),
+    "ice3": per(ICE=(256, 3, 11)),
+    "mix4": per(MIXNR=(256, 4, 11), FULL=(256, 4, 11)),
+    "lock512": per(WARM=(512, 2, 11), ICE=(512, 2, 11), MIXNR=(384, 2, 11), FULL=(384, 2, 11)),
+    "bars63": per(WARM=(256, 4, 63), ICE=(256, 4, 63), MIXNR=(256, 3, 63), FULL=(256, 3, 63)),
 }
 
 if __name__ == "__main__":
@@ -51,5 +55,5 @@ if __name__ == "__main__":
             env = dict(os.environ, KIDMP_LIB=os.path.join(AB, "libkidmp_%s.so" % n))
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "state_hash.py"), "--steps", "6"], env=env,
                                capture_output=True, text=True)
-            line = (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1]
-            print("%-16s %s" % (n, line[line.find("sha256"):]), flush=True)
+            lines = [l for l in r.stdout.strip().splitlines() if "sha256" in l] or [r.stderr[-300:]]
+            print("%-16s %s" % (n, lines[-1][lines[-1].find("sha256"):]), flush=True)
