@@ -24,6 +24,27 @@ using namespace kidmp;
 // kernel groups of one launch, in launch order (kidmp_kernel_names / kidmp_last_kernel_ms)
 enum { KT_CLASSIFY = 0, KT_LISTS, KT_N0, KT_WARM, KT_ICE, KT_MIXNR, KT_FULL, KT_CARRIES, KT_SUBSTEPS, KT_FINISH, KT_DIAG, KT_N };
 
+constexpr int MAX_LANES = 8;
+struct WorkSet {
+  float* d_scratch = nullptr;                             // [nz*cols][SC_REC] hand-off records of the busy cells
+  unsigned char* d_cls = nullptr;                         // [nz][cols] class byte of every cell
+  int* d_colflag = nullptr;                               // [cols]
+  int* d_work = nullptr;                                  // [count | list | mask | offset] of the cloudy columns
+  unsigned* d_cells = nullptr;                            // [nz*cols] busy cells, class after class
+  int* d_cellmeta = nullptr;                              // [192 | groups*64] class / key totals and starts, per-group bases
+  unsigned* d_cellidx = nullptr;                          // [nz*cols] record number of every busy cell
+  float* d_n0a = nullptr;                                 // [nz*cols] graupel intercept minima of S4
+  float* d_ws = nullptr;                                  // [24][nz][cols] SoA workspace of the columns with sedimentation sub-steps
+  double* d_coldiag = nullptr;                            // [2][cols] per-column water paths for the ordered domain sums
+  int* d_colwork = nullptr;                               // [8 busy words | 8 colint | sub list | 4 pptsub][cols] of the column kernels
+  long cols = 0; int nz = 0;
+  cudaStream_t s = nullptr;                               // this lane's stream (a single-lane step runs on the caller's stream instead)
+  cudaStream_t aux = nullptr;                             // second stream of a launch: k_n0_sweep, k_substeps
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_dag[4] = {}, ev_done = nullptr;
+  cudaEvent_t ev_lists = nullptr;                         // the cell list of this set's current launch is complete (its cell kernels come next)
+  bool used = false;                                      // by the last step
+};
+
 struct kidmp_handle {
   int nsm = 148;
   kidmp_config cfg;
@@ -44,26 +65,21 @@ struct kidmp_handle {
   float* d_dz = nullptr;         // [nz]
   float* d_ppt = nullptr;        // [4][ncol]
   float* d_stage = nullptr;      // staging for layout conversion, [nz][ncol]
-  double* d_partial = nullptr; long partial_blocks = 0;
-  // work buffers of one launch (a chunk of at most chunk_cols columns), sized for the worst case of the chunk
-  float* d_scratch = nullptr;                             // [nz*cols][SC_REC] hand-off records of the busy cells
-  unsigned char* d_cls = nullptr;                         // [nz][cols] class byte of every cell
-  int* d_colflag = nullptr;                               // [cols]
-  int* d_work = nullptr;                                  // [count | list | mask | offset] of the cloudy columns
-  unsigned* d_cells = nullptr;                            // [nz*cols] busy cells, class after class
-  int* d_cellmeta = nullptr;                              // [192 | groups*64] class / key totals and starts, per-group bases
-  unsigned* d_cellidx = nullptr;                          // [nz*cols] record number of every busy cell
-  float* d_n0a = nullptr;                                 // [nz*cols] graupel intercept minima of S4
-  float* d_ws = nullptr;                                  // [24][nz][cols] SoA workspace of the columns with sedimentation sub-steps
-  cudaStream_t aux = nullptr;                             // k_substeps runs beside k_finish
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_dag[4] = {};
+  double* d_partial = nullptr; long partial_chunks = 0;   // [chunks of one step][DIAG_BLOCKS][KIDMP_NDIAG] block sums of the domain diagnostics
+  // Work buffers of one launch (a chunk of at most chunk_cols columns), sized for the worst case of the chunk.  A step over a
+  // large domain is cut into sub-chunks that run on `lanes` work sets, each with its own streams: the HBM-bound kernels of
+  // one sub-chunk (classification, lists, carries, finish) run beside the issue-bound cell kernels of another.
+  WorkSet ws[MAX_LANES];
+  int lanes = 2;                                          // work sets used side by side ("lanes" option, KIDMP_LANES)
+  long lane_min_cols = 131072;                            // no sub-chunk smaller than this ("lane_min" option)
+  int cell_blocks = 0;                                    // blocks per SM of the cell kernels when several lanes run (0: the kernel's own)
+  int stagger = 0;                                        // "stagger" option: see launch_step
+  int lanes_used = 1;                                     // work sets of the last step
+  cudaEvent_t ev_start = nullptr;                         // the lanes of a step start after this point of the caller's stream
   // "timing" option: the kernels of a launch run one after the other on one stream with an event after each
   bool last_zero_copy = false;                            // the last kidmp_step wrote the changed columns straight into pinned host arrays
   bool timing = false; bool timing_valid = false;
   cudaEvent_t ev_k[KT_N + 1] = {};
-  double* d_coldiag = nullptr;                            // [2][cols] per-column water paths for the ordered domain sums
-  int* d_colwork = nullptr;                               // [8 busy words | 8 colint | sub list | 4 pptsub][cols] of the column kernels
-  long work_cols = 0; int work_nz = 0;
   long chunk_cols = 1048576;                              // columns per launch of the step kernels ("chunk" option, KIDMP_CHUNK)
   cudaEvent_t ev_done = nullptr;                          // end of the last step, on whatever stream it ran
   bool last_on_own_stream = true;
@@ -255,29 +271,42 @@ int ensure_constants(kidmp_handle* h, cudaStream_t s) {
   return 0;
 }
 
-int ensure_work(kidmp_handle* h, long cols, int nz) {
-  if (cols <= h->work_cols && nz <= h->work_nz) return 0;
-  const long C = cols > h->work_cols ? cols : h->work_cols;
-  const int Z = nz > h->work_nz ? nz : h->work_nz;
-  CK(h, cudaDeviceSynchronize());                    // nothing may still be reading the buffers that go away
-  void* old[] = {h->d_scratch, h->d_cls, h->d_colflag, h->d_work, h->d_cells, h->d_cellmeta, h->d_coldiag, h->d_colwork, h->d_cellidx, h->d_ws, h->d_n0a};
+void free_work(WorkSet& w) {
+  void* old[] = {w.d_scratch, w.d_cls, w.d_colflag, w.d_work, w.d_cells, w.d_cellmeta, w.d_coldiag, w.d_colwork, w.d_cellidx, w.d_ws, w.d_n0a};
   for (void* q : old) if (q) cudaFree(q);
-  h->d_scratch = nullptr; h->d_cls = nullptr; h->d_colflag = nullptr; h->d_work = nullptr; h->d_cells = nullptr;
-  h->d_cellmeta = nullptr; h->d_coldiag = nullptr; h->d_colwork = nullptr; h->d_cellidx = nullptr; h->d_ws = nullptr; h->d_n0a = nullptr; h->work_cols = 0; h->work_nz = 0;
+  w.d_scratch = nullptr; w.d_cls = nullptr; w.d_colflag = nullptr; w.d_work = nullptr; w.d_cells = nullptr;
+  w.d_cellmeta = nullptr; w.d_coldiag = nullptr; w.d_colwork = nullptr; w.d_cellidx = nullptr; w.d_ws = nullptr; w.d_n0a = nullptr; w.cols = 0; w.nz = 0;
+}
+int ensure_work(kidmp_handle* h, WorkSet& w, long cols, int nz) {
+  if (!w.aux) {
+    bool ok = cudaStreamCreateWithFlags(&w.s, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&w.aux, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&w.ev_lists, cudaEventDisableTiming) == cudaSuccess;
+    for (int q = 0; q < 4 && ok; ++q) ok = cudaEventCreateWithFlags(&w.ev_dag[q], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return fail(h, "stream/event creation failed");
+  }
+  if (cols <= w.cols && nz <= w.nz) return 0;
+  const long C = cols > w.cols ? cols : w.cols;
+  const int Z = nz > w.nz ? nz : w.nz;
+  CK(h, cudaDeviceSynchronize());                    // nothing may still be reading the buffers that go away
+  free_work(w);
   const size_t cells = (size_t)C * Z;
   const long ngroups = (C + 31) / 32, lblocks = (C + LIST_TILE - 1) / LIST_TILE;
-  CK(h, cudaMalloc((void**)&h->d_scratch, cells * SC_REC * 4));
-  CK(h, cudaMalloc((void**)&h->d_cls, cells));
-  CK(h, cudaMalloc((void**)&h->d_colflag, (size_t)C * 4));
-  CK(h, cudaMalloc((void**)&h->d_work, (size_t)(C + 8 + 2 * ngroups) * 4));
-  CK(h, cudaMalloc((void**)&h->d_cells, cells * 4));
-  CK(h, cudaMalloc((void**)&h->d_cellidx, cells * 4));
-  CK(h, cudaMalloc((void**)&h->d_ws, cells * WS_N * 4));
-  CK(h, cudaMalloc((void**)&h->d_n0a, cells * 4));
-  CK(h, cudaMalloc((void**)&h->d_cellmeta, (size_t)(192 + lblocks * (LIST_TILE / 32) * 64) * 4));
-  CK(h, cudaMalloc((void**)&h->d_coldiag, (size_t)C * 2 * 8));
-  CK(h, cudaMalloc((void**)&h->d_colwork, (size_t)C * 17 * 4));
-  h->work_cols = C; h->work_nz = Z;
+  CK(h, cudaMalloc((void**)&w.d_scratch, cells * SC_REC * 4));
+  CK(h, cudaMalloc((void**)&w.d_cls, cells));
+  CK(h, cudaMalloc((void**)&w.d_colflag, (size_t)C * 4));
+  CK(h, cudaMalloc((void**)&w.d_work, (size_t)(C + 8 + 2 * ngroups) * 4));
+  CK(h, cudaMalloc((void**)&w.d_cells, cells * 4));
+  CK(h, cudaMalloc((void**)&w.d_cellidx, cells * 4));
+  CK(h, cudaMalloc((void**)&w.d_ws, cells * WS_N * 4));
+  CK(h, cudaMalloc((void**)&w.d_n0a, cells * 4));
+  CK(h, cudaMalloc((void**)&w.d_cellmeta, (size_t)(192 + lblocks * (LIST_TILE / 32) * 64) * 4));
+  CK(h, cudaMalloc((void**)&w.d_coldiag, (size_t)C * 2 * 8));
+  CK(h, cudaMalloc((void**)&w.d_colwork, (size_t)C * 17 * 4));
+  w.cols = C; w.nz = Z;
   return 0;
 }
 
@@ -320,37 +349,67 @@ int ensure_work(kidmp_handle* h, long cols, int nz) {
 #define KC_FULL_BARS 11
 #endif
 
+// `bps`: blocks per SM (0: as many as the kernel's launch bounds allow).  With several lanes a cell kernel that left no
+// register of an SM free would keep the other lanes' HBM-bound kernels out until its last block retires.
 template <bool RATES>
-void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s, cudaEvent_t n0_done) {
+void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s, cudaEvent_t n0_done, int bps) {
   auto mark = [&](int q) { if (h->timing) cudaEventRecord(h->ev_k[q + 1], s); };
-  k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, KC_WARM_BARS, RATES><<<nsm * KC_WARM_B, KC_WARM_T, 0, s>>>(a);
+  auto grid = [&](int own) { return (unsigned)(nsm * (bps > 0 && bps < own ? bps : own)); };
+  k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, KC_WARM_BARS, RATES><<<grid(KC_WARM_B), KC_WARM_T, 0, s>>>(a);
   mark(KT_WARM);
-  k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, KC_ICE_BARS, RATES><<<nsm * KC_ICE_B, KC_ICE_T, 0, s>>>(a);
+  k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, KC_ICE_BARS, RATES><<<grid(KC_ICE_B), KC_ICE_T, 0, s>>>(a);
   mark(KT_ICE);
   if (n0_done) cudaStreamWaitEvent(s, n0_done, 0);     // only the classes with graupel read the intercept minima of k_n0_sweep
-  k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES><<<nsm * KC_MIXNR_B, KC_MIXNR_T, 0, s>>>(a);
+  k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES><<<grid(KC_MIXNR_B), KC_MIXNR_T, 0, s>>>(a);
   mark(KT_MIXNR);
-  k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES><<<nsm * KC_FULL_B, KC_FULL_T, 0, s>>>(a);
+  k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES><<<grid(KC_FULL_B), KC_FULL_T, 0, s>>>(a);
   mark(KT_FULL);
 }
 
 // One step over [ncol] columns whose arrays have row stride ld, in launches of at most chunk_cols columns (the work
-// buffers are sized for one chunk: 29 hand-off planes would otherwise grow with the domain).  Columns are independent,
-// so the chunking changes no result.
+// buffers are sized for one launch: 29 hand-off planes would otherwise grow with the domain).  Columns are independent,
+// so the chunking changes no result.  A large domain is cut into at least `lanes` launches that run on as many work sets
+// and streams: the kernels of a launch alternate between HBM-bound (classification, carries, finish) and issue-bound
+// (cells), and side by side they fill each other's idle resource.  A small domain or a timing-mode step is one launch
+// after the other on the caller's stream.
 int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   if (a0.nz < 2 || a0.nz > 256) return fail(h, "nz=%d outside [2,256]", a0.nz);
   if (a0.ncol < 1) return fail(h, "ncol=%ld", a0.ncol);
   if (!(a0.dt > 0.f)) return fail(h, "dt must be positive");
-  const long chunk = h->chunk_cols;
+  long chunk = h->chunk_cols;
+  if (!h->timing && h->lanes > 1 && a0.ncol >= 2 * h->lane_min_cols) {
+    long sub = (a0.ncol + h->lanes - 1) / h->lanes;
+    sub = (sub + 1023) / 1024 * 1024;                  // launches start on whole 128-byte lines of the caller's rows
+    if (sub < h->lane_min_cols) sub = h->lane_min_cols;
+    if (sub < chunk) chunk = sub;
+  }
   const long cap = a0.ncol < chunk ? a0.ncol : chunk;
+  const long nchunks = (a0.ncol + chunk - 1) / chunk;
+  const int nl = (h->timing || h->lanes <= 1 || nchunks < 2) ? 1 : (int)(nchunks < h->lanes ? nchunks : h->lanes);
   if (cap > (1L << 24)) return fail(h, "chunk of %ld columns: at most 16 777 216 per launch (set_option \"chunk\")", cap);
   if ((double)cap * a0.nz >= 4.0e9) return fail(h, "chunk of %ld columns x %d levels does not fit the 32-bit cell index", cap, a0.nz);
-  if (ensure_work(h, cap, a0.nz)) return 1;
+  for (int l = 0; l < nl; ++l) if (ensure_work(h, h->ws[l], cap, a0.nz)) return 1;
+  // the work sets are the handle's: a step on another stream than the last one starts after it
+  CK(h, cudaStreamWaitEvent(s, h->ev_done, 0));
   if (ensure_constants(h, s)) return 1;
   // the handle's own rate buffer starts every step at zero: clear-sky columns have no process at all
   if (a0.rates && a0.rates == h->d_rates_own) CK(h, cudaMemsetAsync(h->d_rates_own, 0, (size_t)KIDMP_NRATES * a0.nz * a0.ld * 4, s));
-  if (!h->d_partial) CK(h, cudaMalloc((void**)&h->d_partial, (size_t)DIAG_BLOCKS * KIDMP_NDIAG * 8));
-  for (long c0 = 0; c0 < a0.ncol; c0 += chunk) {
+  if (h->partial_chunks < nchunks) {
+    if (h->d_partial) { CK(h, cudaDeviceSynchronize()); cudaFree(h->d_partial); h->d_partial = nullptr; h->partial_chunks = 0; }
+    CK(h, cudaMalloc((void**)&h->d_partial, (size_t)nchunks * DIAG_BLOCKS * KIDMP_NDIAG * 8));
+    h->partial_chunks = nchunks;
+  }
+  if (nl > 1) {
+    CK(h, cudaEventRecord(h->ev_start, s));
+    for (int l = 0; l < nl; ++l) CK(h, cudaStreamWaitEvent(h->ws[l].s, h->ev_start, 0));
+  }
+  for (int l = 0; l < MAX_LANES; ++l) h->ws[l].used = l < nl;
+  h->lanes_used = nl;
+  const int bps = nl > 1 ? h->cell_blocks : 0;
+  long ci = 0;
+  for (long c0 = 0; c0 < a0.ncol; c0 += chunk, ++ci) {
+    WorkSet& w = h->ws[ci % nl];
+    cudaStream_t cs = nl > 1 ? w.s : s;
     StepArgs a = a0;
     a.ncol = (a0.ncol - c0 < chunk) ? (a0.ncol - c0) : chunk;
     for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = a0.f[q] + c0;
@@ -358,63 +417,71 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     if (a0.dz_col) a.dz_col = a0.dz_col + c0;
     if (a0.rates) a.rates = a0.rates + c0;
     const long ngroups = (a.ncol + 31) / 32, lblocks = (a.ncol + LIST_TILE - 1) / LIST_TILE;
-    a.scratch = h->d_scratch; a.scratch_b = h->d_scratch + (size_t)h->work_cols * h->work_nz * SC_HALF; a.cellidx = h->d_cellidx; a.cls = h->d_cls; a.colflag = h->d_colflag;
-    a.work_count = h->d_work; a.work_list = h->d_work + 8;
-    a.work_mask = (unsigned*)(h->d_work + 8 + a.ncol); a.work_offset = h->d_work + 8 + a.ncol + ngroups;
-    a.cell_list = h->d_cells; a.cell_count = h->d_cellmeta; a.sub_count = h->d_cellmeta + 5; a.cell_kstart = h->d_cellmeta + 8;
-    a.cell_hist = h->d_cellmeta + 64; a.cell_start = h->d_cellmeta + 128; a.cell_base = h->d_cellmeta + 192;
-    a.busy = (unsigned*)h->d_colwork; a.colint = h->d_colwork + 8 * h->work_cols; a.sub_list = h->d_colwork + 16 * h->work_cols;
-    a.ws = h->d_ws; a.ws_cols = h->work_cols; a.n0a = h->d_n0a;
-    a.coldiag = h->d_coldiag; a.diag_partial = h->d_partial; a.nsm = h->nsm;
-    // second stream of the launch; in timing mode everything runs on `s`, one kernel after the other
-    cudaStream_t x = h->timing ? s : h->aux;
-    auto mark = [&](int q) { if (h->timing) cudaEventRecord(h->ev_k[q + 1], s); };
+    a.scratch = w.d_scratch; a.scratch_b = w.d_scratch + (size_t)w.cols * w.nz * SC_HALF; a.cellidx = w.d_cellidx; a.cls = w.d_cls; a.colflag = w.d_colflag;
+    a.work_count = w.d_work; a.work_list = w.d_work + 8;
+    a.work_mask = (unsigned*)(w.d_work + 8 + a.ncol); a.work_offset = w.d_work + 8 + a.ncol + ngroups;
+    a.cell_list = w.d_cells; a.cell_count = w.d_cellmeta; a.sub_count = w.d_cellmeta + 5; a.cell_kstart = w.d_cellmeta + 8;
+    a.cell_hist = w.d_cellmeta + 64; a.cell_start = w.d_cellmeta + 128; a.cell_base = w.d_cellmeta + 192;
+    a.busy = (unsigned*)w.d_colwork; a.colint = w.d_colwork + 8 * w.cols; a.sub_list = w.d_colwork + 16 * w.cols;
+    a.ws = w.d_ws; a.ws_cols = w.cols; a.n0a = w.d_n0a;
+    a.coldiag = w.d_coldiag; a.diag_partial = h->d_partial + (size_t)ci * DIAG_BLOCKS * KIDMP_NDIAG; a.nsm = h->nsm;
+    // second stream of the launch; in timing mode everything runs on one stream, one kernel after the other
+    cudaStream_t x = h->timing ? cs : w.aux;
+    auto mark = [&](int q) { if (h->timing) cudaEventRecord(h->ev_k[q + 1], cs); };
     auto fork = [&](cudaEvent_t e, cudaStream_t from, cudaStream_t to) {
       if (from != to) { cudaEventRecord(e, from); cudaStreamWaitEvent(to, e, 0); }
     };
-    CK(h, cudaMemsetAsync(h->d_cellmeta, 0, 128 * 4, s));
-    if (h->timing) CK(h, cudaEventRecord(h->ev_k[0], s));
-    k_classify<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
+    // Stagger the lanes: a launch starts its classification when the launch before it (on the neighbouring lane) has
+    // its cell list, i.e. its HBM-bound front runs beside that launch's cell kernels instead of beside its front.
+    if (nl > 1 && ci > 0 && h->stagger) CK(h, cudaStreamWaitEvent(cs, h->ws[(ci - 1) % nl].ev_lists, 0));
+    CK(h, cudaMemsetAsync(w.d_cellmeta, 0, 128 * 4, cs));
+    if (h->timing) CK(h, cudaEventRecord(h->ev_k[0], cs));
+    k_classify<<<(unsigned)((a.ncol + 127) / 128), 128, 0, cs>>>(a);
     mark(KT_CLASSIFY);
-    // Two independent chains after the classification.  This stream: the work list of the cloudy columns, then the list of
-    // the busy cells.  Second stream: the key histogram of the busy cells (needs the class bytes only), then the graupel
-    // intercept sweep (needs the work list only; the cell kernels wait for it).
-    fork(h->ev_dag[0], s, x);
-    k_cell_count<<<(unsigned)lblocks, LIST_TILE, 0, x>>>(a);
-    k_cell_offsets<<<1, 64, 0, x>>>(a);
-    k_list_scan<<<1, 1024, 0, s>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
-    k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, s>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
+    // The classification left the key histogram of the busy cells: first entry of every key and class, the work list of
+    // the cloudy columns, then the list of the busy cells.  Second stream: the graupel intercept sweep (needs the work list
+    // only; the cell kernels with graupel wait for it).
+    k_cell_offsets<<<1, 64, 0, cs>>>(a);
+    k_list_scan<<<1, 1024, 0, cs>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
+    k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, cs>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
     if (h->timing) {
-      k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, s>>>(a);
+      k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, cs>>>(a);
       mark(KT_LISTS);
-      if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, s>>>(a);
+      if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, cs>>>(a);
       mark(KT_N0);
     } else {
-      fork(h->ev_dag[1], x, s);                      // (recorded after k_cell_offsets)
-      fork(h->ev_dag[2], s, x);                      // (recorded after k_list_fill)
+      fork(w.ev_dag[2], cs, x);                      // (recorded after k_list_fill)
       // the number of cloudy columns is only known on the device: grids for the worst case, surplus blocks leave at once
       if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, x>>>(a);
-      k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, s>>>(a);
-      CK(h, cudaEventRecord(h->ev_dag[3], x));       // the sweep runs beside k_cell_fill and the warm and ice cell kernels
+      k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, cs>>>(a);
+      CK(h, cudaEventRecord(w.ev_dag[3], x));        // the sweep runs beside k_cell_fill and the warm and ice cell kernels
     }
-    cudaEvent_t n0_done = h->timing ? nullptr : h->ev_dag[3];
-    if (a.rates) launch_cells<true>(h, a, h->nsm, s, n0_done); else launch_cells<false>(h, a, h->nsm, s, n0_done);
-    k_carries<<<(unsigned)((a.ncol + 63) / 64), 64, 0, s>>>(a);
+    if (nl > 1) CK(h, cudaEventRecord(w.ev_lists, cs));
+    cudaEvent_t n0_done = h->timing ? nullptr : w.ev_dag[3];
+    if (a.rates) launch_cells<true>(h, a, h->nsm, cs, n0_done, bps); else launch_cells<false>(h, a, h->nsm, cs, n0_done, bps);
+    k_carries<<<(unsigned)((a.ncol + 63) / 64), 64, 0, cs>>>(a);
     mark(KT_CARRIES);
     // the columns with sedimentation sub-steps on the second stream, the others on this one: disjoint columns
-    fork(h->ev_fork, s, x);
+    fork(w.ev_fork, cs, x);
     const unsigned sgrid = (unsigned)(ngroups < h->nsm * 16 ? ngroups : h->nsm * 16);
     if (a.rates) k_substeps<true><<<sgrid, 32, 0, x>>>(a); else k_substeps<false><<<sgrid, 32, 0, x>>>(a);
     mark(KT_SUBSTEPS);
-    if (a.rates) k_finish<true><<<(unsigned)ngroups, 32, 0, s>>>(a); else k_finish<false><<<(unsigned)ngroups, 32, 0, s>>>(a);
+    if (a.rates) k_finish<true><<<(unsigned)ngroups, 32, 0, cs>>>(a); else k_finish<false><<<(unsigned)ngroups, 32, 0, cs>>>(a);
     mark(KT_FINISH);
-    fork(h->ev_join, x, s);
-    k_diag_columns<<<DIAG_BLOCKS, 256, 0, s>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
-    k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, DIAG_BLOCKS, h->d_diag);
-    mark(KT_DIAG);
-    h->timing_valid = h->timing;
-    h->launches += h->kc.iiwarm ? 15 : 16;
+    fork(w.ev_join, x, cs);
+    k_diag_columns<<<DIAG_BLOCKS, 256, 0, cs>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
+    h->launches += h->kc.iiwarm ? 13 : 14;
   }
+  if (nl > 1)
+    for (int l = 0; l < nl; ++l) {
+      CK(h, cudaEventRecord(h->ws[l].ev_done, h->ws[l].s));
+      CK(h, cudaStreamWaitEvent(s, h->ws[l].ev_done, 0));
+    }
+  // the block sums of all launches, in column order
+  k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)(nchunks * DIAG_BLOCKS), h->d_diag);
+  ++h->launches;
+  if (h->timing) cudaEventRecord(h->ev_k[KT_DIAG + 1], s);
+  h->timing_valid = h->timing;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(h->ev_done, s));
   h->last_on_own_stream = (s == h->stream);
@@ -716,6 +783,10 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   h->device = dev1;
   if (getenv("KIDMP_CHUNK") && atol(getenv("KIDMP_CHUNK")) >= 32) h->chunk_cols = atol(getenv("KIDMP_CHUNK"));
   if (dev1 >= MAX_DEVICES) { delete h; return fail(nullptr, "kidmp_init: device ordinal %d not supported", dev1); }
+  if (getenv("KIDMP_LANES")) { const int v = atoi(getenv("KIDMP_LANES")); h->lanes = v < 1 ? 1 : v > MAX_LANES ? MAX_LANES : v; }
+  if (getenv("KIDMP_LANE_MIN") && atol(getenv("KIDMP_LANE_MIN")) >= 1024) h->lane_min_cols = atol(getenv("KIDMP_LANE_MIN"));
+  if (getenv("KIDMP_CELL_BLOCKS")) h->cell_blocks = atoi(getenv("KIDMP_CELL_BLOCKS"));
+  if (getenv("KIDMP_STAGGER")) h->stagger = atoi(getenv("KIDMP_STAGGER"));
   if (getenv("KIDMP_PIPE_CHUNK")) h->pipe_chunk = atol(getenv("KIDMP_PIPE_CHUNK")) > 1024 ? atol(getenv("KIDMP_PIPE_CHUNK")) : 1024;
   if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
   h->cfg.table_cache_path = nullptr;
@@ -731,13 +802,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
       cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_dag[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_dag[1], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_dag[2], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_dag[3], cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) != cudaSuccess) {
     h->err = "stream/event creation failed"; return bail(1);
   }
   for (int q = 0; q <= KT_N; ++q) if (cudaEventCreate(&h->ev_k[q]) != cudaSuccess) {
@@ -792,22 +857,18 @@ int kidmp_finalize(kidmp_handle* h) {
   if (h->d_diag) cudaFree(h->d_diag);
   if (h->d_kid) cudaFree(h->d_kid);
   if (h->h_kid) cudaFreeHost(h->h_kid);
-  if (h->d_scratch) cudaFree(h->d_scratch);
-  if (h->d_cls) cudaFree(h->d_cls);
-  if (h->d_colflag) cudaFree(h->d_colflag);
-  if (h->d_work) cudaFree(h->d_work);
-  if (h->d_cells) cudaFree(h->d_cells);
-  if (h->d_cellmeta) cudaFree(h->d_cellmeta);
-  if (h->d_coldiag) cudaFree(h->d_coldiag);
-  if (h->d_colwork) cudaFree(h->d_colwork);
-  if (h->d_cellidx) cudaFree(h->d_cellidx);
-  if (h->d_ws) cudaFree(h->d_ws);
-  if (h->d_n0a) cudaFree(h->d_n0a);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
-  for (int q = 0; q < 4; ++q) if (h->ev_dag[q]) cudaEventDestroy(h->ev_dag[q]);
+  for (WorkSet& w : h->ws) {
+    free_work(w);
+    if (w.ev_fork) cudaEventDestroy(w.ev_fork);
+    if (w.ev_join) cudaEventDestroy(w.ev_join);
+    if (w.ev_done) cudaEventDestroy(w.ev_done);
+    if (w.ev_lists) cudaEventDestroy(w.ev_lists);
+    for (int q = 0; q < 4; ++q) if (w.ev_dag[q]) cudaEventDestroy(w.ev_dag[q]);
+    if (w.aux) cudaStreamDestroy(w.aux);
+    if (w.s) cudaStreamDestroy(w.s);
+  }
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
   for (int q = 0; q <= KT_N; ++q) if (h->ev_k[q]) cudaEventDestroy(h->ev_k[q]);
-  if (h->aux) cudaStreamDestroy(h->aux);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->d_pipe) cudaFree(h->d_pipe);
   if (h->d_pipe_dz) cudaFree(h->d_pipe_dz);
@@ -1159,7 +1220,7 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
       HostFields hc = hf;
       for (int q = 0; q < KIDMP_NFIELDS; ++q) hc.f[q] += c0;
       StepArgs sa = a;
-      sa.colflag = h->d_colflag;                     // (of this chunk: the next chunk's kernels follow on the same stream)
+      sa.colflag = h->ws[0].d_colflag;               // (of this chunk, a single launch on work set 0: the next chunk's kernels follow on the same stream)
       k_scatter_host<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(sa, hc, hld);
       ++h->launches;
       CK(h, cudaEventRecord(h->pipe_ev[b][1], h->stream));
@@ -1333,6 +1394,19 @@ int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
     if (value < 32) return fail(h, "set_option: chunk must be at least 32 columns");
     h->chunk_cols = value; return 0;
   }
+  if (!strcmp(name, "lanes")) {
+    if (value < 1 || value > MAX_LANES) return fail(h, "set_option: lanes must be 1..%d", MAX_LANES);
+    h->lanes = value; return 0;
+  }
+  if (!strcmp(name, "lane_min")) {
+    if (value < 1024) return fail(h, "set_option: lane_min must be at least 1024 columns");
+    h->lane_min_cols = value; return 0;
+  }
+  if (!strcmp(name, "stagger")) { h->stagger = value != 0; return 0; }
+  if (!strcmp(name, "cell_blocks")) {
+    if (value < 0 || value > 8) return fail(h, "set_option: cell_blocks must be 0..8");
+    h->cell_blocks = value; return 0;
+  }
   if (!strcmp(name, "timing")) { h->timing = value != 0; h->timing_valid = false; return 0; }
   if (!strcmp(name, "fuse") || !strcmp(name, "units")) return 0;      // knobs of the round-1 kernels: accepted, no effect
   return fail(h, "set_option: unknown option '%s'", name);
@@ -1369,15 +1443,17 @@ int kidmp_step_stats(kidmp_handle* h, long out[8]) {
     return 0;
   }
   for (int q = 0; q < 8; ++q) out[q] = 0;
-  if (!h->d_cellmeta) return 0;
   DevGuard guard_(h->device);
   CK(h, cudaEventSynchronize(h->ev_done));
-  int meta[8], cloudy = 0;
-  CK(h, cudaMemcpy(meta, h->d_cellmeta, sizeof meta, cudaMemcpyDeviceToHost));
-  CK(h, cudaMemcpy(&cloudy, h->d_work, 4, cudaMemcpyDeviceToHost));
-  out[0] = cloudy; out[1] = meta[KC_N];
-  for (int q = 0; q < KC_N; ++q) out[2 + q] = meta[q];
-  out[6] = meta[5];
+  for (const WorkSet& w : h->ws) {                     // the last launch of every work set the last step used
+    if (!w.used || !w.d_cellmeta) continue;
+    int meta[8], cloudy = 0;
+    CK(h, cudaMemcpy(meta, w.d_cellmeta, sizeof meta, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(&cloudy, w.d_work, 4, cudaMemcpyDeviceToHost));
+    out[0] += cloudy; out[1] += meta[KC_N];
+    for (int q = 0; q < KC_N; ++q) out[2 + q] += meta[q];
+    out[6] += meta[5];
+  }
   out[7] = h->last_zero_copy ? 1 : 0;
   return 0;
 }

@@ -6,7 +6,7 @@
 // the species M:3235, the sub-step counts M:3242).  A column walk spends its time in dependent instruction chains of
 // cells that mostly differ from their neighbours (profiles/r01: 19 of 32 lanes active, 45 % issue), and half of the
 // cells of a cloudy column are idle.  Here
-//   k_cell_count / k_cell_fill   turn the class bytes of k_classify into one list of busy cells, sorted by species set and
+//   k_classify / k_cell_fill     turn the class bytes into one list of busy cells, sorted by species set and
 //                                class, so the lanes of a warp are cells of neighbouring columns that hold the same species;
 //   k_n0_sweep                   walks the columns that hold graupel top-down once: running minimum of M:1648;
 //   k_cells<KC>                  one thread per busy cell, one kernel per class.  The class is a template parameter:
@@ -77,61 +77,9 @@ template <int KC> struct CellTraits {
 // cells of a warp hold the SAME species (same branches) and, inside a key, are the cells of 32 neighbouring columns level
 // after level from the top (neighbouring columns of one or a few levels: same table entries, few cache lines per load;
 // the order is the same from run to run).
-// k_cell_count: histogram of the keys per tile and per launch; k_cell_offsets: first entry of every key and class;
-// k_cell_fill: the entries, and the busy bits of every cloudy column for the column kernels.
-__device__ __forceinline__ unsigned cell_key(unsigned c) { return (c & 31u) | ((c >> CLS_COLD_SHIFT) & 1u) << 5; }
-__device__ __forceinline__ bool tile_has_cloud(const StepArgs& a) {
-  const int g0 = blockIdx.x * (LIST_TILE / 32);
-  bool any = false;
-#pragma unroll
-  for (int g = 0; g < LIST_TILE / 32; ++g) if ((long)(g0 + g) * 32 < a.ncol && a.work_mask[g0 + g]) any = true;
-  return any;
-}
-__global__ void __launch_bounds__(LIST_TILE) k_cell_count(StepArgs a) {
-  __shared__ int s_cnt[LIST_TILE / 32][64];               // cells of every key in the 32 columns of every warp
-  const int nz = a.nz;
-  const long col = (long)blockIdx.x * LIST_TILE + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (!tile_has_cloud(a)) return;                         // a tile without a cloudy column has no busy cell
-  s_cnt[warp][lane] = 0; s_cnt[warp][lane + 32] = 0;
-  __syncwarp();
-  const bool in_range = col < a.ncol;
-  const unsigned char* cp = a.cls + col;
-  constexpr int LB = 16;                                  // class bytes of 16 levels in flight at a time (the walk is latency-bound)
-#pragma unroll 1
-  for (int k0 = 0; k0 < nz; k0 += LB) {
-    unsigned cb[LB];
-#pragma unroll
-    for (int j = 0; j < LB; ++j) cb[j] = (in_range && k0 + j < nz) ? cp[(long)(k0 + j) * a.ncol] : 0u;
-#pragma unroll
-    for (int j = 0; j < LB; ++j) {
-      const unsigned c = cb[j];
-      const bool busy = (c & CLS_BUSY) != 0u;
-      const unsigned act = __ballot_sync(0xffffffffu, busy);
-      if (busy) {
-        const unsigned key = cell_key(c);
-        const unsigned m = __match_any_sync(act, key);
-        if (lane == __ffs(m) - 1) s_cnt[warp][key] += __popc(m);    // one leader per key, only this warp writes its row
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    const int key = threadIdx.x;
-    int total = 0;
-#pragma unroll
-    for (int w = 0; w < LIST_TILE / 32; ++w) total += s_cnt[w][key];
-    if (total) {
-      int run = atomicAdd(&a.cell_hist[key], total);
-#pragma unroll
-      for (int w = 0; w < LIST_TILE / 32; ++w) {
-        a.cell_base[((long)blockIdx.x * (LIST_TILE / 32) + w) * 64 + key] = run;
-        run += s_cnt[w][key];
-      }
-    }
-  }
-}
+// k_classify (kidmp_column.cuh) counts the keys per 32-column group and per launch while it writes the class bytes;
+// k_cell_offsets: first entry of every key and class; k_cell_fill: the entries, and the busy bits of every cloudy column
+// for the column kernels.
 __global__ void __launch_bounds__(64) k_cell_offsets(StepArgs a) {
   __shared__ int s_n[64], s_kc[64];
   const int t = threadIdx.x;

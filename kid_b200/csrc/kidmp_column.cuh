@@ -169,18 +169,34 @@ __device__ __forceinline__ int cell_kernel_class(unsigned sp, bool cold, bool ii
   if (cold && !(sp & (CLS_QC | CLS_QR | CLS_QG))) return KC_ICE;
   return (sp & CLS_QR) ? KC_FULL : KC_MIXNR;
 }
+// Sort key of a busy cell: its five species bits and whether it is below 0 C (64 keys, kidmp_cells.cuh).
+__device__ __forceinline__ unsigned cell_key(unsigned c) { return (c & 31u) | ((c >> CLS_COLD_SHIFT) & 1u) << 5; }
+
+// e_s of the two Flatau polynomials without the division of RSLF / RSIF: for the screening test below
+__device__ __forceinline__ float esat_poly(float P, float T, bool ice) {
+  const float X = fmaxf(-80.f, T - 273.16f);
+  const float E = ice ? .609868993E03f + X * (.499320233E02f + X * (.184672631E01f + X * (.402737184E-1f + X * (.565392987E-3f + X * (.521693933E-5f + X * (.307839583E-7f + X * (.105785160E-9f + X * .161444444E-12f)))))))
+                      : .611583699E03f + X * (.444606896E02f + X * (.143177157E01f + X * (.264224321E-1f + X * (.299291081E-3f + X * (.203154182E-5f + X * (.702620698E-8f + X * (.379534310E-11f + X * -.321582393E-13f)))))));
+  return fminf(E, P * 0.15f);
+}
+
 __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
+  __shared__ int s_cnt[4][64];                              // busy cells of every sort key in the 32 columns of every warp
   const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = col < a.ncol;
   const int nz = a.nz;
   const long ncol = a.ncol, ld = a.ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  s_cnt[warp][lane] = 0; s_cnt[warp][lane + 32] = 0;
+  __syncwarp();
   bool active = false;
-  if (in_range) {
-    const float* __restrict__ Gp = a.p + col;
-    float* Gqv = a.f[F_QV] + col; float* Gqc = a.f[F_QC] + col; float* Gqi = a.f[F_QI] + col;
-    float* Gqr = a.f[F_QR] + col; float* Gqs = a.f[F_QS] + col; float* Gqg = a.f[F_QG] + col;
-    float* Gni = a.f[F_NI] + col; float* Gnr = a.f[F_NR] + col; float* Gt = a.f[F_T] + col;
-    unsigned char* Gcls = a.cls + col;
+  {
+    const long c = in_range ? col : 0;                      // lanes past the end shadow column 0 and store nothing
+    const float* __restrict__ Gp = a.p + c;
+    float* Gqv = a.f[F_QV] + c; float* Gqc = a.f[F_QC] + c; float* Gqi = a.f[F_QI] + c;
+    float* Gqr = a.f[F_QR] + c; float* Gqs = a.f[F_QS] + c; float* Gqg = a.f[F_QG] + c;
+    float* Gni = a.f[F_NI] + c; float* Gnr = a.f[F_NR] + c; float* Gt = a.f[F_T] + c;
+    unsigned char* Gcls = a.cls + c;
     bool no_micro = true, graupel = false, zeroed = false;
 #pragma unroll 4
     for (int k = 0; k < nz; ++k) {
@@ -194,63 +210,112 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
       if (qr > R1) sp |= CLS_QR;
       if (qs > R1) sp |= CLS_QS;
       if (qg > R1) { sp |= CLS_QG; graupel = true; }
-      if (!(qc > R1) && qc != 0.0f) { Gqc[o] = 0.0f; zeroed = true; }
-      if (!(qi > R1) && (qi != 0.0f || ni != 0.0f)) { Gqi[o] = 0.0f; Gni[o] = 0.0f; zeroed = true; }
-      if (!(qr > R1) && (qr != 0.0f || nr != 0.0f)) { Gqr[o] = 0.0f; Gnr[o] = 0.0f; zeroed = true; }
-      if (!(qs > R1) && qs != 0.0f) { Gqs[o] = 0.0f; zeroed = true; }
-      if (!(qg > R1) && qg != 0.0f) { Gqg[o] = 0.0f; zeroed = true; }
-      const float tempc = t - 273.15f;
-      const float qvsi = (tempc <= 0.0f) ? rsif(pr, t) : rslf(pr, t);
-      float ssati = qv / qvsi - 1.f;
-      if (fabsf(ssati) < EPSF) ssati = 0.0f;
-      unsigned c = sp;
-      if (sp || ssati > 0.0f) no_micro = false;             // the reference's test, M:1540
-      if (!sp && ssati > 0.0f) {
-        // Vapour only.  Without a hydrometeor two things can happen: Cooper nucleation below 0 C at ssati >= 0.25, or at ssatw >
-        // eps below 253.15 K (M:2090), and condensation at ssatw > eps (M:2780: the state at tau+1 is the input when every
-        // other rate is zero).  Every other rate is gated by a species flag: a cell that meets neither is idle.
-        float ssatw = ssati;                                // above 0 C the two are the same number (qvsi = qvs, M:1505)
-        if (tempc <= 0.0f) {
-          ssatw = qv / rslf(pr, t) - 1.f;
-          if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
-        }
-        if ((t < T_0 && ssati >= 0.25f) || ssatw > EPSF) c |= CLS_VAP;
+      if (in_range) {
+        if (!(qc > R1) && qc != 0.0f) { Gqc[o] = 0.0f; zeroed = true; }
+        if (!(qi > R1) && (qi != 0.0f || ni != 0.0f)) { Gqi[o] = 0.0f; Gni[o] = 0.0f; zeroed = true; }
+        if (!(qr > R1) && (qr != 0.0f || nr != 0.0f)) { Gqr[o] = 0.0f; Gnr[o] = 0.0f; zeroed = true; }
+        if (!(qs > R1) && qs != 0.0f) { Gqs[o] = 0.0f; zeroed = true; }
+        if (!(qg > R1) && qg != 0.0f) { Gqg[o] = 0.0f; zeroed = true; }
       }
-      if (t < T_0) c |= 1u << CLS_COLD_SHIFT;
-      Gcls[(long)k * ncol] = (unsigned char)c;
+      const float tempc = t - 273.15f;
+      unsigned c8 = sp;
+      // Screening: qv / qvsi - 1 > 0 needs qv > qvsi = .622 e / (P - e).  A cell whose qv (P - e) stays 0.1 % below .622 e
+      // is sub-saturated whatever the roundings of the exact expressions (each is good to 1e-7; P - e >= 0.85 P > 0):
+      // the two divisions of the exact test are only paid near and above saturation.
+      const float e_i = esat_poly(pr, t, tempc <= 0.0f);
+      const bool sub_saturated = pr > 0.f && e_i > 0.f && qv * (pr - e_i) <= 0.999f * (.622f * e_i);
+      if (!sub_saturated) {
+        const float qvsi = (tempc <= 0.0f) ? rsif(pr, t) : rslf(pr, t);
+        float ssati = qv / qvsi - 1.f;
+        if (fabsf(ssati) < EPSF) ssati = 0.0f;
+        if (ssati > 0.0f) {
+          no_micro = false;                                   // the reference's test, M:1540
+          if (!sp) {
+            // Vapour only.  Without a hydrometeor two things can happen: Cooper nucleation below 0 C at ssati >= 0.25, or at ssatw >
+            // eps below 253.15 K (M:2090), and condensation at ssatw > eps (M:2780: the state at tau+1 is the input when every
+            // other rate is zero).  Every other rate is gated by a species flag: a cell that meets neither is idle.
+            float ssatw = ssati;                              // above 0 C the two are the same number (qvsi = qvs, M:1505)
+            if (tempc <= 0.0f) {
+              ssatw = qv / rslf(pr, t) - 1.f;
+              if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
+            }
+            if ((t < T_0 && ssati >= 0.25f) || ssatw > EPSF) c8 |= CLS_VAP;
+          }
+        }
+      }
+      if (sp) no_micro = false;
+      if (t < T_0) c8 |= 1u << CLS_COLD_SHIFT;
+      if (in_range) Gcls[(long)k * ncol] = (unsigned char)c8;
+      // key histogram of the busy cells of this warp's 32 columns (k_cell_fill turns it into list positions)
+      const bool busy = in_range && (c8 & CLS_BUSY) != 0u;
+      const unsigned act = __ballot_sync(0xffffffffu, busy);
+      if (act) {
+        if (busy) {
+          const unsigned key = cell_key(c8);
+          const unsigned m = __match_any_sync(act, key);
+          if (lane == __ffs(m) - 1) s_cnt[warp][key] += __popc(m);      // one leader per key, only this warp writes its row
+        }
+        __syncwarp();
+      }
     }
-    active = !no_micro;
-    a.colflag[col] = active ? (graupel ? 1 : 0) : (zeroed ? -2 : -1);     // -1: the step leaves this column bit for bit as it was
-    if (!active) {                                 // clear-sky column: nothing left to do
-      a.ppt[col] = 0.f; a.ppt[ld + col] = 0.f; a.ppt[2 * ld + col] = 0.f; a.ppt[3 * ld + col] = 0.f;   // I:55-58
+    active = in_range && !no_micro;
+    if (in_range) {
+      a.colflag[col] = active ? (graupel ? 1 : 0) : (zeroed ? -2 : -1);     // -1: the step leaves this column bit for bit as it was
+      if (!active) {                                 // clear-sky column: nothing left to do
+        a.ppt[col] = 0.f; a.ppt[ld + col] = 0.f; a.ppt[2 * ld + col] = 0.f; a.ppt[3 * ld + col] = 0.f;   // I:55-58
+      }
     }
   }
   // ballot of the cloudy lanes of this 32-column group; k_list_scan / k_list_fill turn the ballots into the
   // compacted work list IN COLUMN ORDER (neighbouring lanes of the column kernels are neighbouring columns: coalesced
-  // accesses, similar branches, and a list that is identical from run to run)
+  // accesses, similar branches)
   const unsigned mask = __ballot_sync(0xffffffffu, active);
-  if ((threadIdx.x & 31) == 0 && in_range) a.work_mask[col >> 5] = mask;
+  if (lane == 0 && in_range) a.work_mask[col >> 5] = mask;
+  // first entry of this warp's cells inside the segment of every key (the segments are laid out by k_cell_offsets)
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int key = threadIdx.x;
+    const int n0 = s_cnt[0][key], n1 = s_cnt[1][key], n2 = s_cnt[2][key], n3 = s_cnt[3][key];
+    const int total = n0 + n1 + n2 + n3;
+    if (total) {
+      const int run = atomicAdd(&a.cell_hist[key], total);
+      int* base = a.cell_base + (size_t)blockIdx.x * 4 * 64 + key;
+      base[0] = run; base[64] = run + n0; base[128] = run + n0 + n1; base[192] = run + n0 + n1 + n2;
+    }
+  }
 }
 
-// exclusive prefix sum of the per-group cloudy-column counts (one block; ngroups is at most a few 10^5)
+// exclusive prefix sum of the per-group cloudy-column counts (one block; ngroups is at most 2^19: 16 777 216 columns per launch)
 __global__ void __launch_bounds__(1024) k_list_scan(const unsigned* __restrict__ mask, int ngroups, int* __restrict__ offset,
                                                     int* __restrict__ count) {
-  __shared__ int s_sum[1024];
-  const int per = (ngroups + 1023) / 1024;
-  const int g0 = threadIdx.x * per, g1 = min(g0 + per, ngroups);
-  int sum = 0;
-  for (int g = g0; g < g1; ++g) sum += __popc(mask[g]);
-  s_sum[threadIdx.x] = sum;
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_run = 0;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {                     // Hillis-Steele inclusive scan
-    const int v = (int)threadIdx.x >= d ? s_sum[threadIdx.x - d] : 0;
+  for (int g0 = 0; g0 < ngroups; g0 += 1024) {              // 1024 groups per round, coalesced
+    const int g = g0 + threadIdx.x;
+    const int n = g < ngroups ? __popc(mask[g]) : 0;
+    int v = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+    if (lane == 31) s_warp[warp] = v;
     __syncthreads();
-    s_sum[threadIdx.x] += v;
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += u; }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int run = s_run;
+    const int incl = v + (warp ? s_warp[warp - 1] : 0);
+    if (g < ngroups) offset[g] = run + incl - n;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_run = run + incl;
     __syncthreads();
   }
-  int run = s_sum[threadIdx.x] - sum;
-  for (int g = g0; g < g1; ++g) { offset[g] = run; run += __popc(mask[g]); }
-  if (threadIdx.x == 1023) *count = s_sum[1023];
+  if (threadIdx.x == 0) *count = s_run;
 }
 
 __global__ void __launch_bounds__(256) k_list_fill(const unsigned* __restrict__ mask, const int* __restrict__ offset, int ngroups,

@@ -94,6 +94,9 @@ KIDMP_MATH_FN double dpow(double x, double y) {
     if (fm_exp_fast(e)) return fm_exp_core(e);
     return exp(e);
   }
+  // x = 0 (a rate or a content that is exactly zero) is the one special base the step meets in numbers: log(0) = -inf,
+  // so exp(y * log(0)) is 0 for y > 0, +inf for y < 0 and NaN for y = 0 - without the two library calls
+  if (x == 0.0) return y > 0.0 ? 0.0 : (y < 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0x7ff8000000000000LL));
   return exp(y * log(x));
 }
 __device__ __forceinline__ double pow_d(double x, double y) { return dpow(x, y); }
