@@ -70,7 +70,7 @@ struct kidmp_handle {
   // large domain is cut into sub-chunks that run on `lanes` work sets, each with its own streams: the HBM-bound kernels of
   // one sub-chunk (classification, lists, carries, finish) run beside the issue-bound cell kernels of another.
   WorkSet ws[MAX_LANES];
-  int lanes = 2;                                          // work sets used side by side ("lanes" option, KIDMP_LANES)
+  int lanes = 1;                                          // work sets used side by side ("lanes" option, KIDMP_LANES)
   long lane_min_cols = 131072;                            // no sub-chunk smaller than this ("lane_min" option)
   int cell_blocks = 0;                                    // blocks per SM of the cell kernels when several lanes run (0: the kernel's own)
   int stagger = 0;                                        // "stagger" option: see launch_step
@@ -78,7 +78,7 @@ struct kidmp_handle {
   cudaEvent_t ev_start = nullptr;                         // the lanes of a step start after this point of the caller's stream
   // "timing" option: the kernels of a launch run one after the other on one stream with an event after each
   bool last_zero_copy = false;                            // the last kidmp_step wrote the changed columns straight into pinned host arrays
-  bool timing = false; bool timing_valid = false;
+  int timing = 0; bool timing_valid = false;             // 1: kernels serialised on one stream; 2: the normal schedule, events on the main stream only
   cudaEvent_t ev_k[KT_N + 1] = {};
   long chunk_cols = 1048576;                              // columns per launch of the step kernels ("chunk" option, KIDMP_CHUNK)
   cudaEvent_t ev_done = nullptr;                          // end of the last step, on whatever stream it ran
@@ -277,10 +277,12 @@ void free_work(WorkSet& w) {
   w.d_scratch = nullptr; w.d_cls = nullptr; w.d_colflag = nullptr; w.d_work = nullptr; w.d_cells = nullptr;
   w.d_cellmeta = nullptr; w.d_coldiag = nullptr; w.d_colwork = nullptr; w.d_cellidx = nullptr; w.d_ws = nullptr; w.d_n0a = nullptr; w.cols = 0; w.nz = 0;
 }
-int ensure_work(kidmp_handle* h, WorkSet& w, long cols, int nz) {
+// The streams of the work sets are made at init, before the host makes its own: measured on the bench (a PyTorch stream made
+// after kidmp_init), a second stream made at the first step instead left k_substeps running 0.2 ms past k_finish.
+int ensure_streams(kidmp_handle* h, WorkSet& w, bool own_stream) {
+  if (own_stream && !w.s) CK(h, cudaStreamCreateWithFlags(&w.s, cudaStreamNonBlocking));
   if (!w.aux) {
-    bool ok = cudaStreamCreateWithFlags(&w.s, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&w.aux, cudaStreamNonBlocking) == cudaSuccess &&
+    bool ok = cudaStreamCreateWithFlags(&w.aux, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&w.ev_join, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming) == cudaSuccess &&
@@ -288,6 +290,10 @@ int ensure_work(kidmp_handle* h, WorkSet& w, long cols, int nz) {
     for (int q = 0; q < 4 && ok; ++q) ok = cudaEventCreateWithFlags(&w.ev_dag[q], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) return fail(h, "stream/event creation failed");
   }
+  return 0;
+}
+int ensure_work(kidmp_handle* h, WorkSet& w, long cols, int nz, bool own_stream) {
+  if (ensure_streams(h, w, own_stream)) return 1;
   if (cols <= w.cols && nz <= w.nz) return 0;
   const long C = cols > w.cols ? cols : w.cols;
   const int Z = nz > w.nz ? nz : w.nz;
@@ -388,7 +394,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   const int nl = (h->timing || h->lanes <= 1 || nchunks < 2) ? 1 : (int)(nchunks < h->lanes ? nchunks : h->lanes);
   if (cap > (1L << 24)) return fail(h, "chunk of %ld columns: at most 16 777 216 per launch (set_option \"chunk\")", cap);
   if ((double)cap * a0.nz >= 4.0e9) return fail(h, "chunk of %ld columns x %d levels does not fit the 32-bit cell index", cap, a0.nz);
-  for (int l = 0; l < nl; ++l) if (ensure_work(h, h->ws[l], cap, a0.nz)) return 1;
+  for (int l = 0; l < nl; ++l) if (ensure_work(h, h->ws[l], cap, a0.nz, l > 0)) return 1;   // (lane 0 runs on the caller's stream)
   // the work sets are the handle's: a step on another stream than the last one starts after it
   CK(h, cudaStreamWaitEvent(s, h->ev_done, 0));
   if (ensure_constants(h, s)) return 1;
@@ -401,7 +407,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   }
   if (nl > 1) {
     CK(h, cudaEventRecord(h->ev_start, s));
-    for (int l = 0; l < nl; ++l) CK(h, cudaStreamWaitEvent(h->ws[l].s, h->ev_start, 0));
+    for (int l = 1; l < nl; ++l) CK(h, cudaStreamWaitEvent(h->ws[l].s, h->ev_start, 0));
   }
   for (int l = 0; l < MAX_LANES; ++l) h->ws[l].used = l < nl;
   h->lanes_used = nl;
@@ -409,7 +415,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   long ci = 0;
   for (long c0 = 0; c0 < a0.ncol; c0 += chunk, ++ci) {
     WorkSet& w = h->ws[ci % nl];
-    cudaStream_t cs = nl > 1 ? w.s : s;
+    cudaStream_t cs = (ci % nl) ? w.s : s;
     StepArgs a = a0;
     a.ncol = (a0.ncol - c0 < chunk) ? (a0.ncol - c0) : chunk;
     for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = a0.f[q] + c0;
@@ -426,7 +432,8 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     a.ws = w.d_ws; a.ws_cols = w.cols; a.n0a = w.d_n0a;
     a.coldiag = w.d_coldiag; a.diag_partial = h->d_partial + (size_t)ci * DIAG_BLOCKS * KIDMP_NDIAG; a.nsm = h->nsm;
     // second stream of the launch; in timing mode everything runs on one stream, one kernel after the other
-    cudaStream_t x = h->timing ? cs : w.aux;
+    const bool serial = h->timing == 1;
+    cudaStream_t x = serial ? cs : w.aux;
     auto mark = [&](int q) { if (h->timing) cudaEventRecord(h->ev_k[q + 1], cs); };
     auto fork = [&](cudaEvent_t e, cudaStream_t from, cudaStream_t to) {
       if (from != to) { cudaEventRecord(e, from); cudaStreamWaitEvent(to, e, 0); }
@@ -444,7 +451,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     k_cell_offsets<<<1, 64, 0, cs>>>(a);
     k_list_scan<<<1, 1024, 0, cs>>>(a.work_mask, (int)ngroups, a.work_offset, a.work_count);
     k_list_fill<<<(unsigned)((ngroups * 32 + 255) / 256), 256, 0, cs>>>(a.work_mask, a.work_offset, (int)ngroups, a.work_list);
-    if (h->timing) {
+    if (serial) {
       k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, cs>>>(a);
       mark(KT_LISTS);
       if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, cs>>>(a);
@@ -455,9 +462,10 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
       if (!h->kc.iiwarm) k_n0_sweep<<<(unsigned)((a.ncol + 127) / 128), 128, 0, x>>>(a);
       k_cell_fill<<<(unsigned)lblocks, LIST_TILE, 0, cs>>>(a);
       CK(h, cudaEventRecord(w.ev_dag[3], x));        // the sweep runs beside k_cell_fill and the warm and ice cell kernels
+      mark(KT_LISTS); mark(KT_N0);
     }
     if (nl > 1) CK(h, cudaEventRecord(w.ev_lists, cs));
-    cudaEvent_t n0_done = h->timing ? nullptr : w.ev_dag[3];
+    cudaEvent_t n0_done = serial ? nullptr : w.ev_dag[3];
     if (a.rates) launch_cells<true>(h, a, h->nsm, cs, n0_done, bps); else launch_cells<false>(h, a, h->nsm, cs, n0_done, bps);
     k_carries<<<(unsigned)((a.ncol + 63) / 64), 64, 0, cs>>>(a);
     mark(KT_CARRIES);
@@ -473,7 +481,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     h->launches += h->kc.iiwarm ? 13 : 14;
   }
   if (nl > 1)
-    for (int l = 0; l < nl; ++l) {
+    for (int l = 1; l < nl; ++l) {
       CK(h, cudaEventRecord(h->ws[l].ev_done, h->ws[l].s));
       CK(h, cudaStreamWaitEvent(s, h->ws[l].ev_done, 0));
     }
@@ -481,7 +489,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   k_diag_reduce<<<KIDMP_NDIAG, 256, 0, s>>>(h->d_partial, (int)(nchunks * DIAG_BLOCKS), h->d_diag);
   ++h->launches;
   if (h->timing) cudaEventRecord(h->ev_k[KT_DIAG + 1], s);
-  h->timing_valid = h->timing;
+  h->timing_valid = h->timing != 0;
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(h->ev_done, s));
   h->last_on_own_stream = (s == h->stream);
@@ -798,13 +806,12 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   h->nsm = prop.multiProcessorCount;
   if (prop.major < 10) { fail(h, "kidmp_init: built for sm_100a, device is sm_%d%d", prop.major, prop.minor); return bail(1); }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) != cudaSuccess) {
     h->err = "stream/event creation failed"; return bail(1);
   }
+  for (int l = 0; l < h->lanes; ++l) if (ensure_streams(h, h->ws[l], l > 0)) return bail(1);
   for (int q = 0; q <= KT_N; ++q) if (cudaEventCreate(&h->ev_k[q]) != cudaSuccess) {
     h->err = "stream/event creation failed"; return bail(1);
   }
@@ -1161,6 +1168,10 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
                           const float* p, const float* dz, float* ppt, long hld) {
   const long chunk = h->pipe_chunk;
   const int NB = 3;
+  // (streams are made when they are first needed: the device has few hardware queues, and streams that share one
+  // serialise kernels that could run side by side)
+  if (!h->copy_in) CK(h, cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+  if (!h->copy_out) CK(h, cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
   const size_t cells = (size_t)chunk * nz;
   const size_t per_buf = cells * (KIDMP_NFIELDS + 1) + (size_t)chunk * 4;
   if (h->pipe_floats < per_buf * NB || h->pipe_nz != nz) {
@@ -1407,7 +1418,7 @@ int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
     if (value < 0 || value > 8) return fail(h, "set_option: cell_blocks must be 0..8");
     h->cell_blocks = value; return 0;
   }
-  if (!strcmp(name, "timing")) { h->timing = value != 0; h->timing_valid = false; return 0; }
+  if (!strcmp(name, "timing")) { h->timing = value < 0 ? 0 : value > 2 ? 2 : value; h->timing_valid = false; return 0; }
   if (!strcmp(name, "fuse") || !strcmp(name, "units")) return 0;      // knobs of the round-1 kernels: accepted, no effect
   return fail(h, "set_option: unknown option '%s'", name);
 }

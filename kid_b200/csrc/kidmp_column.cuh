@@ -172,14 +172,6 @@ __device__ __forceinline__ int cell_kernel_class(unsigned sp, bool cold, bool ii
 // Sort key of a busy cell: its five species bits and whether it is below 0 C (64 keys, kidmp_cells.cuh).
 __device__ __forceinline__ unsigned cell_key(unsigned c) { return (c & 31u) | ((c >> CLS_COLD_SHIFT) & 1u) << 5; }
 
-// e_s of the two Flatau polynomials without the division of RSLF / RSIF: for the screening test below
-__device__ __forceinline__ float esat_poly(float P, float T, bool ice) {
-  const float X = fmaxf(-80.f, T - 273.16f);
-  const float E = ice ? .609868993E03f + X * (.499320233E02f + X * (.184672631E01f + X * (.402737184E-1f + X * (.565392987E-3f + X * (.521693933E-5f + X * (.307839583E-7f + X * (.105785160E-9f + X * .161444444E-12f)))))))
-                      : .611583699E03f + X * (.444606896E02f + X * (.143177157E01f + X * (.264224321E-1f + X * (.299291081E-3f + X * (.203154182E-5f + X * (.702620698E-8f + X * (.379534310E-11f + X * -.321582393E-13f)))))));
-  return fminf(E, P * 0.15f);
-}
-
 __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
   __shared__ int s_cnt[4][64];                              // busy cells of every sort key in the 32 columns of every warp
   const long col = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,8 +182,8 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
   s_cnt[warp][lane] = 0; s_cnt[warp][lane + 32] = 0;
   __syncwarp();
   bool active = false;
-  {
-    const long c = in_range ? col : 0;                      // lanes past the end shadow column 0 and store nothing
+  if (in_range) {
+    const long c = col;
     const float* __restrict__ Gp = a.p + c;
     float* Gqv = a.f[F_QV] + c; float* Gqc = a.f[F_QC] + c; float* Gqi = a.f[F_QI] + c;
     float* Gqr = a.f[F_QR] + c; float* Gqs = a.f[F_QS] + c; float* Gqg = a.f[F_QG] + c;
@@ -219,44 +211,31 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
       }
       const float tempc = t - 273.15f;
       unsigned c8 = sp;
-      // Screening: qv / qvsi - 1 > 0 needs qv > qvsi = .622 e / (P - e).  A cell whose qv (P - e) stays 0.1 % below .622 e
-      // is sub-saturated whatever the roundings of the exact expressions (each is good to 1e-7; P - e >= 0.85 P > 0):
-      // the two divisions of the exact test are only paid near and above saturation.
-      const float e_i = esat_poly(pr, t, tempc <= 0.0f);
-      const bool sub_saturated = pr > 0.f && e_i > 0.f && qv * (pr - e_i) <= 0.999f * (.622f * e_i);
-      if (!sub_saturated) {
-        const float qvsi = (tempc <= 0.0f) ? rsif(pr, t) : rslf(pr, t);
-        float ssati = qv / qvsi - 1.f;
-        if (fabsf(ssati) < EPSF) ssati = 0.0f;
-        if (ssati > 0.0f) {
-          no_micro = false;                                   // the reference's test, M:1540
-          if (!sp) {
-            // Vapour only.  Without a hydrometeor two things can happen: Cooper nucleation below 0 C at ssati >= 0.25, or at ssatw >
-            // eps below 253.15 K (M:2090), and condensation at ssatw > eps (M:2780: the state at tau+1 is the input when every
-            // other rate is zero).  Every other rate is gated by a species flag: a cell that meets neither is idle.
-            float ssatw = ssati;                              // above 0 C the two are the same number (qvsi = qvs, M:1505)
-            if (tempc <= 0.0f) {
-              ssatw = qv / rslf(pr, t) - 1.f;
-              if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
-            }
-            if ((t < T_0 && ssati >= 0.25f) || ssatw > EPSF) c8 |= CLS_VAP;
+      // (a screening test that skips the two divisions for clearly sub-saturated cells was measured: 8 % slower, the
+      // polynomial and the divisions hide behind the loads)
+      const float qvsi = (tempc <= 0.0f) ? rsif(pr, t) : rslf(pr, t);
+      float ssati = qv / qvsi - 1.f;
+      if (fabsf(ssati) < EPSF) ssati = 0.0f;
+      if (ssati > 0.0f) {
+        no_micro = false;                                     // the reference's test, M:1540
+        if (!sp) {
+          // Vapour only.  Without a hydrometeor two things can happen: Cooper nucleation below 0 C at ssati >= 0.25, or at ssatw >
+          // eps below 253.15 K (M:2090), and condensation at ssatw > eps (M:2780: the state at tau+1 is the input when every
+          // other rate is zero).  Every other rate is gated by a species flag: a cell that meets neither is idle.
+          float ssatw = ssati;                                // above 0 C the two are the same number (qvsi = qvs, M:1505)
+          if (tempc <= 0.0f) {
+            ssatw = qv / rslf(pr, t) - 1.f;
+            if (fabsf(ssatw) < EPSF) ssatw = 0.0f;
           }
+          if ((t < T_0 && ssati >= 0.25f) || ssatw > EPSF) c8 |= CLS_VAP;
         }
       }
       if (sp) no_micro = false;
       if (t < T_0) c8 |= 1u << CLS_COLD_SHIFT;
       if (in_range) Gcls[(long)k * ncol] = (unsigned char)c8;
-      // key histogram of the busy cells of this warp's 32 columns (k_cell_fill turns it into list positions)
-      const bool busy = in_range && (c8 & CLS_BUSY) != 0u;
-      const unsigned act = __ballot_sync(0xffffffffu, busy);
-      if (act) {
-        if (busy) {
-          const unsigned key = cell_key(c8);
-          const unsigned m = __match_any_sync(act, key);
-          if (lane == __ffs(m) - 1) s_cnt[warp][key] += __popc(m);      // one leader per key, only this warp writes its row
-        }
-        __syncwarp();
-      }
+      // key histogram of the busy cells of this warp's 32 columns (k_cell_fill turns it into list positions): a shared-memory
+      // reduction per busy cell, no warp-wide step in the loop - the loads of the next levels stay in flight
+      if (in_range && (c8 & CLS_BUSY) != 0u) atomicAdd(&s_cnt[warp][cell_key(c8)], 1);
     }
     active = in_range && !no_micro;
     if (in_range) {

@@ -20,6 +20,7 @@ ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--dt", type=float, default=10.0)
 ap.add_argument("--dz", type=float, default=250.0)
 ap.add_argument("--warm", action="store_true")
+ap.add_argument("--timing", type=int, default=0, help="after the timed steps, three more in timing mode 1 (kernels serialised) or 2 (normal schedule): ms of every kernel group")
 a = ap.parse_args()
 th = Thompson(set_Nc=100.0, iiwarm=a.warm, l_sediment=True)
 st, p, dz = synth.make_domain(a.columns, nz=60, nx=1024, device="cuda", dz=a.dz)
@@ -42,6 +43,17 @@ for k in FIELDS:
 h.update(ppt.cpu().numpy().tobytes())
 print("lib", os.environ.get("KIDMP_LIB", "in-tree"), "columns", a.columns, "steps", a.steps, "dt", a.dt, "dz", a.dz,
       "warm", a.warm, "sha256", h.hexdigest()[:32], "ms", " ".join("%.2f" % x for x in ms))
+if a.timing:
+    th.set_option("timing", a.timing)
+    acc = {}
+    with torch.cuda.stream(s):
+        for i in range(3):
+            th.step_device(a.columns, 60, a.dt, [st[k].data_ptr() for k in FIELDS], p.data_ptr(), dz.data_ptr(), ppt.data_ptr(),
+                           stream=s.cuda_stream)
+            s.synchronize()
+            for k, v in th.last_kernel_ms().items():
+                acc[k] = acc.get(k, 0.0) + v / 3
+    print("   kernels", " ".join("%s %.3f" % kv for kv in acc.items()), "sum %.3f" % sum(acc.values()))
 try:
     print("   stats", th.step_stats())
 except Exception as e:      # a library of an earlier round
