@@ -209,6 +209,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the kidmp arm has no CPU path (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from kid_b200.shard import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local)                       # before any pinned allocation: the staging arrays go to the GPU's node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -316,7 +318,7 @@ def main():
                "h2d_bytes_per_step": int(ncol * NZ * 4 * 10 + NZ * 4),
                "d2h_bytes_per_step": int((changed if zc else ncol) * NZ * 4 * 9 + ncol * 16),
                "steps": args.e2e_steps, "ms_per_step": el / args.e2e_steps * 1e3, "columns_per_gpu": ncol,
-               "api": "kidmp_step (host arrays, COL_FASTEST, pinned)",
+               "api": "kidmp_step (host arrays, COL_FASTEST, pinned)", "numa": numa,
                "d2h": ("only the %d columns the step changed come back (clear-sky columns return bit for bit as they went in, M:1540), "
                        "written by a kernel into the pinned host arrays" % changed) if zc else "all columns copied back"}
         ncol = ncol_full

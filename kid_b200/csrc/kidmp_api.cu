@@ -36,7 +36,7 @@ struct WorkSet {
   float* d_n0a = nullptr;                                 // [nz*cols] graupel intercept minima of S4
   float* d_ws = nullptr;                                  // [24][nz][cols] SoA workspace of the columns with sedimentation sub-steps
   double* d_coldiag = nullptr;                            // [2][cols] per-column water paths for the ordered domain sums
-  int* d_colwork = nullptr;                               // [8 busy words | 8 colint | sub list | 4 pptsub][cols] of the column kernels
+  int* d_colwork = nullptr;                               // [8 busy words | 8 colint | sub list | 2 colvmax][cols] of the column kernels
   long cols = 0; int nz = 0;
   cudaStream_t s = nullptr;                               // this lane's stream (a single-lane step runs on the caller's stream instead)
   cudaStream_t aux = nullptr;                             // second stream of a launch: k_n0_sweep, k_substeps
@@ -55,6 +55,8 @@ struct kidmp_handle {
   KConst kc;
   HostBins hb;
   TableSet tabs{};
+  char* d_tables = nullptr; size_t tables_bytes = 0;   // the slab behind tabs
+  size_t l2_window_bytes = 0; float l2_hit_ratio = 0.f; // L2 access-policy window over the slab (0: none)
   float table_ms = 0.f;
   bool tables_from_cache = false;
   long launches = 0;
@@ -73,6 +75,8 @@ struct kidmp_handle {
   int lanes = 1;                                          // work sets used side by side ("lanes" option, KIDMP_LANES)
   long lane_min_cols = 131072;                            // no sub-chunk smaller than this ("lane_min" option)
   int cell_blocks = 0;                                    // blocks per SM of the cell kernels when several lanes run (0: the kernel's own)
+  int simple = 1;                                         // "simple" option: columns without sub-steps skip k_carries (kidmp_cells.cuh)
+  int l2_window = 1;                                      // "l2_window" option: the cell kernels that gather from the tables carry the window
   int stagger = 0;                                        // "stagger" option: see launch_step
   int lanes_used = 1;                                     // work sets of the last step
   cudaEvent_t ev_start = nullptr;                         // the lanes of a step start after this point of the caller's stream
@@ -311,7 +315,7 @@ int ensure_work(kidmp_handle* h, WorkSet& w, long cols, int nz, bool own_stream)
   CK(h, cudaMalloc((void**)&w.d_n0a, cells * 4));
   CK(h, cudaMalloc((void**)&w.d_cellmeta, (size_t)(192 + lblocks * (LIST_TILE / 32) * 64) * 4));
   CK(h, cudaMalloc((void**)&w.d_coldiag, (size_t)C * 2 * 8));
-  CK(h, cudaMalloc((void**)&w.d_colwork, (size_t)C * 17 * 4));
+  CK(h, cudaMalloc((void**)&w.d_colwork, (size_t)C * 19 * 4));
   w.cols = C; w.nz = Z;
   return 0;
 }
@@ -366,9 +370,22 @@ void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s, c
   k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, KC_ICE_BARS, RATES><<<grid(KC_ICE_B), KC_ICE_T, 0, s>>>(a);
   mark(KT_ICE);
   if (n0_done) cudaStreamWaitEvent(s, n0_done, 0);     // only the classes with graupel read the intercept minima of k_n0_sweep
-  k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES><<<grid(KC_MIXNR_B), KC_MIXNR_T, 0, s>>>(a);
+  // The two classes that gather from the big tables (qcfz / iaus: mixed; racs, racg, qrfz: full) run with an L2
+  // access-policy window over the table slab: table lines persist, the streamed state and records do not evict them.
+  cudaLaunchAttribute att[1];
+  att[0].id = cudaLaunchAttributeAccessPolicyWindow;
+  att[0].val.accessPolicyWindow.base_ptr = h->d_tables;
+  att[0].val.accessPolicyWindow.num_bytes = h->l2_window_bytes;
+  att[0].val.accessPolicyWindow.hitRatio = h->l2_hit_ratio;
+  att[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  att[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(KC_MIXNR_T); cfg.gridDim = dim3(grid(KC_MIXNR_B)); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cfg.attrs = att; cfg.numAttrs = (h->l2_window_bytes && h->l2_window) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES>, a);
   mark(KT_MIXNR);
-  k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES><<<grid(KC_FULL_B), KC_FULL_T, 0, s>>>(a);
+  cfg.blockDim = dim3(KC_FULL_T); cfg.gridDim = dim3(grid(KC_FULL_B));
+  cudaLaunchKernelEx(&cfg, k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES>, a);
   mark(KT_FULL);
 }
 
@@ -428,9 +445,9 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     a.work_mask = (unsigned*)(w.d_work + 8 + a.ncol); a.work_offset = w.d_work + 8 + a.ncol + ngroups;
     a.cell_list = w.d_cells; a.cell_count = w.d_cellmeta; a.sub_count = w.d_cellmeta + 5; a.cell_kstart = w.d_cellmeta + 8;
     a.cell_hist = w.d_cellmeta + 64; a.cell_start = w.d_cellmeta + 128; a.cell_base = w.d_cellmeta + 192;
-    a.busy = (unsigned*)w.d_colwork; a.colint = w.d_colwork + 8 * w.cols; a.sub_list = w.d_colwork + 16 * w.cols;
+    a.busy = (unsigned*)w.d_colwork; a.colint = w.d_colwork + 8 * w.cols; a.sub_list = w.d_colwork + 16 * w.cols; a.colvmax = w.d_colwork + 17 * w.cols;
     a.ws = w.d_ws; a.ws_cols = w.cols; a.n0a = w.d_n0a;
-    a.coldiag = w.d_coldiag; a.diag_partial = h->d_partial + (size_t)ci * DIAG_BLOCKS * KIDMP_NDIAG; a.nsm = h->nsm;
+    a.coldiag = w.d_coldiag; a.diag_partial = h->d_partial + (size_t)ci * DIAG_BLOCKS * KIDMP_NDIAG; a.nsm = h->nsm; a.no_simple = h->simple ? 0 : 1;
     // second stream of the launch; in timing mode everything runs on one stream, one kernel after the other
     const bool serial = h->timing == 1;
     cudaStream_t x = serial ? cs : w.aux;
@@ -444,6 +461,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     CK(h, cudaMemsetAsync(w.d_cellmeta, 0, 128 * 4, cs));
     if (h->timing) CK(h, cudaEventRecord(h->ev_k[0], cs));
     k_classify<<<(unsigned)((a.ncol + 127) / 128), 128, 0, cs>>>(a);
+    CK(h, cudaMemsetAsync(a.colvmax, 0, (size_t)2 * w.cols * 4, cs));
     mark(KT_CLASSIFY);
     // The classification left the key histogram of the busy cells: first entry of every key and class, the work list of
     // the cloudy columns, then the list of the busy cells.  Second stream: the graupel intercept sweep (needs the work list
@@ -795,6 +813,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   if (getenv("KIDMP_LANE_MIN") && atol(getenv("KIDMP_LANE_MIN")) >= 1024) h->lane_min_cols = atol(getenv("KIDMP_LANE_MIN"));
   if (getenv("KIDMP_CELL_BLOCKS")) h->cell_blocks = atoi(getenv("KIDMP_CELL_BLOCKS"));
   if (getenv("KIDMP_STAGGER")) h->stagger = atoi(getenv("KIDMP_STAGGER"));
+  if (getenv("KIDMP_SIMPLE")) h->simple = atoi(getenv("KIDMP_SIMPLE")) != 0;
   if (getenv("KIDMP_PIPE_CHUNK")) h->pipe_chunk = atol(getenv("KIDMP_PIPE_CHUNK")) > 1024 ? atol(getenv("KIDMP_PIPE_CHUNK")) : 1024;
   if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
   h->cfg.table_cache_path = nullptr;
@@ -820,10 +839,32 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   hostinit::Prep pp;
   hostinit::compute(h->cfg, h->kc, h->hb, pp);
   publish_constants(h);
-  for (auto& a : table_allocs(h)) {
-    if (cudaMalloc(a.p, a.bytes) != cudaSuccess || cudaMemset(*a.p, 0, a.bytes) != cudaSuccess) {
+  {
+    // one slab for all lookup tables (the gathered ones first): one L2 access-policy window covers them
+    size_t total = 0;
+    for (auto& a : table_allocs(h)) total += (a.bytes + 255) / 256 * 256;
+    if (cudaMalloc((void**)&h->d_tables, total) != cudaSuccess || cudaMemset(h->d_tables, 0, total) != cudaSuccess) {
       h->err = "table allocation failed"; return bail(1);
     }
+    h->tables_bytes = total;
+    size_t off = 0;
+    for (auto& a : table_allocs(h)) { *a.p = h->d_tables + off; off += (a.bytes + 255) / 256 * 256; }
+    // L2 set-aside for the window (north_star: "lookup tables staged in ... L2-persisting windows"): as much of the slab as
+    // the device allows.  Only the cell kernels that gather from the collection / freezing tables carry the window.
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+    size_t want = total < (size_t)max_persist ? total : (size_t)max_persist;
+    // MEASURED (profiles/r02_l2_window.md): with the set-aside (the device grants ~3/5 of L2) the step goes from 3.51 to 5.1 ms -
+    // k_finish 0.68 -> 1.46 ms, k_carries 0.33 -> 0.62, even k_cells<FULL> 0.35 -> 0.48: the records and the state stream
+    // through what is left of L2, and only ~2 % of the busy cells gather from the big tables.  So the window is OFF unless
+    // KIDMP_L2_WINDOW=1 asks for it at init.
+    if (!(getenv("KIDMP_L2_WINDOW") && atoi(getenv("KIDMP_L2_WINDOW")) != 0)) want = 0;
+    if (want && max_window > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+      h->l2_window_bytes = total < (size_t)max_window ? total : (size_t)max_window;
+      h->l2_hit_ratio = h->l2_window_bytes <= want ? 1.0f : (float)want / (float)h->l2_window_bytes;
+    }
+    cudaGetLastError();
   }
   if (cudaMalloc((void**)&h->d_diag, KIDMP_NDIAG * 8) != cudaSuccess || cudaMemset(h->d_diag, 0, KIDMP_NDIAG * 8) != cudaSuccess) {
     h->err = "diag allocation failed"; return bail(1);
@@ -859,7 +900,7 @@ int kidmp_finalize(kidmp_handle* h) {
   }
   cudaDeviceSynchronize();                           // steps may have run on caller streams
   free_state(h);
-  for (auto& a : table_allocs(h)) if (*a.p) cudaFree(*a.p);
+  if (h->d_tables) cudaFree(h->d_tables);
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_diag) cudaFree(h->d_diag);
   if (h->d_kid) cudaFree(h->d_kid);
@@ -1206,6 +1247,10 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
   }
   h->last_zero_copy = zero_copy;
   const size_t hpitch = (size_t)hld * 4, ppitch = (size_t)ncol * 4;
+  // KIDMP_PIPE_TRACE=1: device timeline of every chunk (H2D, step kernels, return path) on stderr after the step
+  const bool trace = getenv("KIDMP_PIPE_TRACE") && atoi(getenv("KIDMP_PIPE_TRACE")) != 0;
+  std::vector<cudaEvent_t> tev;
+  auto tmark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
   long c0 = 0;
   for (int it = 0; c0 < ncol; ++it, c0 += chunk) {
     const int b = it % NB;
@@ -1214,17 +1259,21 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
     float* d_ppt = base + cells * (KIDMP_NFIELDS + 1);
     const size_t dpitch = (size_t)n * 4;
     if (it >= NB) CK(h, cudaStreamWaitEvent(h->copy_in, h->pipe_ev[b][2], 0));     // buffer drained by its D2H
+    tmark(h->copy_in);
     for (int q = 0; q <= KIDMP_NFIELDS; ++q) {
       const float* src = (q < KIDMP_NFIELDS ? fields[q] : p) + c0;
       CK(h, cudaMemcpy2DAsync(base + cells * q, dpitch, src, hpitch, dpitch, nz, cudaMemcpyHostToDevice, h->copy_in));
     }
     CK(h, cudaEventRecord(h->pipe_ev[b][0], h->copy_in));
+    tmark(h->copy_in);
     CK(h, cudaStreamWaitEvent(h->stream, h->pipe_ev[b][0], 0));
+    tmark(h->stream);
     StepArgs a{};
     a.ncol = n; a.ld = n; a.nz = nz; a.dt = dt;
     for (int q = 0; q < KIDMP_NFIELDS; ++q) a.f[q] = base + cells * q;
     a.p = base + cells * KIDMP_NFIELDS; a.dz = h->d_pipe_dz; a.ppt = d_ppt;
     if (launch_step(h, a, h->stream)) return 1;
+    tmark(h->stream);
     CK(h, cudaEventRecord(h->pipe_ev[b][1], h->stream));
     CK(h, cudaStreamWaitEvent(h->copy_out, h->pipe_ev[b][1], 0));
     if (zero_copy) {
@@ -1241,10 +1290,21 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
         CK(h, cudaMemcpy2DAsync(fields[q] + c0, hpitch, base + cells * q, dpitch, dpitch, nz, cudaMemcpyDeviceToHost, h->copy_out));
     if (ppt) CK(h, cudaMemcpy2DAsync(h->h_ppt + c0, ppitch, d_ppt, dpitch, dpitch, 4, cudaMemcpyDeviceToHost, h->copy_out));
     CK(h, cudaEventRecord(h->pipe_ev[b][2], h->copy_out));
+    tmark(h->stream);
+    tmark(h->copy_out);
   }
   CK(h, cudaEventRecord(h->ev1, h->stream));
   CK(h, cudaStreamSynchronize(h->copy_out));
   CK(h, cudaStreamSynchronize(h->stream));
+  if (trace) {
+    fprintf(stderr, "chunk  h2d_start h2d_end  step_start step_end  return_end(stream) return_end(copy_out)   [ms from the first H2D]\n");
+    for (size_t i = 0; i + 5 < tev.size() + 1 && i + 5 < tev.size() + 6 && i + 6 <= tev.size(); i += 6) {
+      float t[6];
+      for (int j = 0; j < 6; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[i + j]);
+      fprintf(stderr, "%5zu  %8.2f %8.2f  %8.2f %8.2f  %8.2f %8.2f\n", i / 6, t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  }
   if (ppt) for (int q = 0; q < 4; ++q) memcpy(ppt + (size_t)q * hld, h->h_ppt + (size_t)q * ncol, (size_t)ncol * 4);
   return 0;
 }
@@ -1413,6 +1473,8 @@ int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
     if (value < 1024) return fail(h, "set_option: lane_min must be at least 1024 columns");
     h->lane_min_cols = value; return 0;
   }
+  if (!strcmp(name, "simple")) { h->simple = value != 0; return 0; }
+  if (!strcmp(name, "l2_window")) { h->l2_window = value != 0; return 0; }
   if (!strcmp(name, "stagger")) { h->stagger = value != 0; return 0; }
   if (!strcmp(name, "cell_blocks")) {
     if (value < 0 || value > 8) return fail(h, "set_option: cell_blocks must be 0..8");

@@ -1093,6 +1093,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       st_sector(sc + 8, nrt, nct, nr, ni, v_ni, 0.f, 0.f, 0.f);
       st_sector(sb, rr, ri, rs, rg, v_r, v_nr, v_i, rho);
       st_sector(sb + 8, s15, n0a_out, (float)n0b_slw, vts_h, vts_boost, temp, 0.f, 0.f);
+      // An upper bound of every fall speed this cell can hand a level of its column, for the test "no species of this column
+      // needs a second sedimentation sub-step" (k_carries): its own speeds (a level without the species inherits them, M:3235);
+      // melting snow (M:3301) through the factor vts / (T - T_0) that multiplies the inherited rain speed.  Graupel takes its
+      // speed from the running intercept minimum of the column (M:2731, M:3328): a column with graupel is never simple.
+      float vb = fmaxf(fmaxf(v_r, v_nr), v_i);
+      if (TR::S9 && rs > R1) {
+        vb = fmaxf(vb, vts_h * vts_boost);
+        if (temp > (T_0 + 0.1f)) atomicMax(a.colvmax + a.ncol + slot, __float_as_int(vts_h / (temp - T_0)));
+      }
+      if (TR::G9 && rg > R1) vb = __int_as_float(0x7f800000);
+      if (vb > 1.E-3f) atomicMax(a.colvmax + slot, __float_as_int(vb));
     }
   }
 #undef LOCKBAR
@@ -1156,6 +1167,17 @@ __global__ void __launch_bounds__(64, 16) k_carries(StepArgs a) {
   const unsigned* const cidx = a.cellidx + slot;
   const float* const dzp = a.dz_col ? a.dz_col + col : a.dz;     // one vector shared by all columns (KiD) or this column's own (WRF entry)
   const long dzs = a.dz_col ? ld : 1;
+  {
+    // A SIMPLE column: no fall speed of the column can cross its thinnest layer in one step (bounds left by the cell kernels),
+    // so every sub-step count of M:3242 is 0 or 1 - k_finish then settles what runs down the column on its own single sweep
+    // and this kernel has nothing to read.  (v DT < 0.99 dz makes INT(DT / (dz / v) + 1.) = 1 whatever the roundings.)
+    const float vmax = __int_as_float(a.colvmax[slot]), sfac = __int_as_float(a.colvmax[a.ncol + slot]);
+    if (vmax <= 3.0e38f && !a.no_simple) {                // (+inf: graupel in the column)
+      float dzmin = dzp[0];
+      for (int k = 1; k < nz; ++k) dzmin = fminf(dzmin, dzp[k * dzs]);
+      if (fmaxf(vmax, sfac * vmax) * DT < 0.99f * dzmin) { a.colint[slot] = -1; return; }
+    }
+  }
   int nstep_r = 0, nstep_i = 0, nstep_s = 0, nstep_g = 0, ksed_r = 1, ksed_i = 1, ksed_s = 1, ksed_g = 1;
   double n0_min = (double)KP_GONV_MAX;
   bool warm_b = false;
@@ -1377,8 +1399,18 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
   if (slot >= count) return;
   const int nz = a.nz;
   const long cs = count;
-  const SedCounts s = sed_counts(a.colint + slot, cs, nz);
-  if (s.n_r > 1 || s.n_i > 1 || s.n_s > 1 || s.n_g > 1) return;      // k_substeps has this column
+  // A simple column (k_carries: no graupel, every sub-step count 0 or 1) has no counts: what runs down the column - the speed
+  // of snow above 0 C (M:3301), the top sedimenting levels (M:3208) - is settled level by level on this sweep, with the
+  // expressions of k_carries.
+  const bool simple = a.colint[slot] < 0;
+  SedCounts s;
+  if (simple) {
+    s.n_r = s.n_i = s.n_s = s.n_g = 1; s.on_r = s.on_i = s.on_s = s.on_g = 1.0f;
+    s.ksed_r = s.ksed_i = s.ksed_s = s.ksed_g = 1;                    // (M:3208: ksed1 starts at 1; raised below as the sweep meets the species)
+  } else {
+    s = sed_counts(a.colint + slot, cs, nz);
+    if (s.n_r > 1 || s.n_i > 1 || s.n_s > 1 || s.n_g > 1) return;    // k_substeps has this column
+  }
   const long col = a.work_list[slot];
   const long ld = a.ld, ncol = a.ncol;
   const float DT = a.dt, odt = 1.f / DT;
@@ -1419,8 +1451,14 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
       if (h.rr > R1) { v_r = s2.v[4]; v_nr = s2.v[5]; }
       if (!iiwarm) {
         if (h.ri > R1) { v_i = s2.v[6]; v_ni = s1.v[4]; }
-        if (h.rs > R1) v_s = s3.v[6];                     // (written by k_carries where the species is present)
-        if (h.rg > R1) v_g = s3.v[7];
+        if (!simple) {
+          if (h.rs > R1) v_s = s3.v[6];                   // (written by k_carries where the species is present)
+          if (h.rg > R1) v_g = s3.v[7];
+        } else if (h.rs > R1) {                           // (a simple column holds no graupel)
+          const float vts = s3.v[3], vts_boost = s3.v[4], temp = s3.v[5];
+          if (temp > (T_0 + 0.1f)) v_s = fmaxf(vts * vts_boost, vts * ((v_r - vts * vts_boost) / (temp - T_0)));
+          else v_s = vts * vts_boost;
+        }
       }
     } else {
       h.tt = 0.f; h.qvt = 0.f; h.qct = 0.f; h.qit = 0.f; h.qrt = 0.f; h.qst = 0.f; h.qgt = 0.f; h.nit = 0.f; h.nrt = 0.f; h.nct = 0.f;
@@ -1433,6 +1471,13 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
       }
     }
     h.v_r = v_r; h.v_nr = v_nr; h.v_i = v_i; h.v_ni = v_ni; h.v_s = v_s; h.v_g = v_g;
+    if (simple) {                                         // M:3208: the highest level with a fall speed, this level included
+      if (fmaxf(v_r, v_nr) > 1.E-3f) sp.top_r = nz;
+      if (!iiwarm) {
+        if (v_i > 1.E-3f) sp.top_i = nz;
+        if (v_s > 1.E-3f) sp.top_s = nz;
+      }
+    }
     finish_level(a, sp, c, h, k, nz, o, dzp[k * dzs], t1d, qv1d, qc1d, qi1d, qr1d, qs1d, qg1d, ni1d, nr1d, pres);
   }
   // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)

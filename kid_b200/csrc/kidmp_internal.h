@@ -157,13 +157,15 @@ struct StepArgs {
   int* cell_kstart;            // [KC_N] ... and its first entry (the keys of a class are next to each other)
   int* cell_base;              // [32-column groups][64] first entry of a group's cells inside the segment of their key
   unsigned* busy;              // [ceil(nz/32)][count] busy bits of every cloudy column (bit k%32 of word k/32)
-  int* colint;                 // [8][count] sub-step counts and top sedimenting levels of rain, ice, snow, graupel
+  int* colint;                 // [8][count] sub-step counts and top sedimenting levels of rain, ice, snow, graupel ([0] < 0: a simple column, see colvmax)
+  int* colvmax;                // [2][ncol] by slot, float bits: largest fall speed any cell of the column can hand a level; largest vts / (T - T_0) of its melting snow
   int* sub_count;              // columns that need sedimentation sub-steps (nstep > 1, M:3242) ...
   int* sub_list;               // ... their slots
   float* rates;                // optional [36][nz][ld]
   double* coldiag;             // [2][ncol] liquid / ice water path of each cloudy column
   double* diag_partial;        // [DIAG_BLOCKS][KIDMP_NDIAG] block sums of k_diag_columns
   int nsm;                     // SMs of the device
+  int no_simple;               // 1: every cloudy column goes through the counts of k_carries ("simple" option off: for A/B runs)
 };
 
 // device tables (kidmp_tables.cuh fills them)

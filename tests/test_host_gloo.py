@@ -69,3 +69,16 @@ def test_shard_range_edges():
         assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
         sizes = [b - a for a, b in r]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_numa_helpers_parse_and_report():
+    """kid_b200/shard.py: the cpulist parser, and the binding helper reports instead of raising on a box without GPUs."""
+    from kid_b200 import shard
+    assert shard._parse_list("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert shard._parse_list("") == []
+    assert shard.gpu_numa_node("ffff:ff:1f.0") == -1
+    before = os.sched_getaffinity(0)
+    info = shard.bind_to_gpu_numa(0)
+    assert info["gpu"] == 0 and "node" in info and "mem_policy" in info
+    if info["node"] < 0:
+        assert os.sched_getaffinity(0) == before
