@@ -157,8 +157,21 @@ int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in);
 /* Tuning knobs; results do not depend on them.
  * "chunk": columns per launch of the step kernels (default 1 048 576, or the KIDMP_CHUNK environment variable): the work
  * buffers (128-byte hand-off records, cell lists) are sized for one chunk, whatever the size of the domain.
- * "timing": 1 = run the kernels of a launch one after the other with an event after each (kidmp_last_kernel_ms), 0 = normal.
- * "fuse", "units": knobs of the round-1 kernels, accepted and ignored. */
+ * "timing": 1 = run the kernels of a launch one after the other with an event after each (kidmp_last_kernel_ms), 2 = the
+ *   normal schedule (second stream in use) with the same events on the main stream, 0 = normal.
+ * "simple": 1 (default) = a column that holds no graupel and in which no fall speed can cross the thinnest layer in one step
+ *   (every sub-step count of M:3242 is 0 or 1) skips the column kernel that settles those counts; 0 = every cloudy column
+ *   goes through it.  KIDMP_SIMPLE.
+ * "lanes" (1..8, default 1, KIDMP_LANES), "lane_min" (columns, KIDMP_LANE_MIN), "stagger", "cell_blocks": a step over at least
+ *   2 x lane_min columns is cut into launches that run side by side on `lanes` work sets and streams.  Measured on the
+ *   bench domain: no gain over one lane (profiles/r02_ncu_step_kernels.md), so the default is one.
+ * "l2_window": the cell kernels that gather from the collection tables carry an L2 access-policy window over the table slab;
+ *   only has an effect when the handle was created with KIDMP_L2_WINDOW=1 in the environment (the L2 set-aside is made at
+ *   init).  Measured: the step slows from 3.5 to 5.1 ms, so it is off.
+ * "fuse", "units": knobs of the round-1 kernels, accepted and ignored.
+ * Environment only: KIDMP_PIPE_CHUNK (columns per chunk of kidmp_step's host pipeline), KIDMP_ZEROCOPY=0 (copy whole chunks
+ *   back instead of writing the changed columns into pinned host arrays), KIDMP_PIPE_TRACE=1 (device timeline of every chunk
+ *   of kidmp_step on stderr). */
 int kidmp_set_option(kidmp_handle* h, const char* name, int value);
 
 /* Multi-device handles (kidmp_config::ndev > 1).  kidmp_step, kidmp_kid_interface and the resident-state calls cut the
@@ -171,7 +184,7 @@ int kidmp_num_devices(const kidmp_handle* h);
 
 /* bookkeeping for benchmarks */
 long kidmp_gpu_launches(const kidmp_handle* h);         /* kernels launched so far          */
-/* counts of the last launch of the step kernels (the last chunk of the last step; waits for it): 0 cloudy columns, 1 busy
+/* counts of the last launch of the step kernels on every work set the last step used (waits for it): 0 cloudy columns, 1 busy
  * cells, 2-5 busy cells of the warm / ice / mixed-without-rain / full cell kernels, 6 columns with sedimentation sub-steps,
  * 7 whether the last kidmp_step returned only the changed columns (pinned host arrays, see kidmp_step) */
 int kidmp_step_stats(kidmp_handle* h, long out[8]);

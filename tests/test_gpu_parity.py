@@ -734,3 +734,48 @@ def test_chunked_steps_are_bit_identical(dt, dz, warm, ncol, nz):
         assert r[2][6] == ref[2][6] and r[2][7] == ref[2][7]               # active columns, columns
         assert np.allclose(r[2][:6], ref[2][:6], rtol=1e-12)               # f64 sums: the order of the partial sums changes
     assert ref[2][6] > 0                                                   # some columns were active
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,dz", [(10.0, 250.0), (60.0, 100.0)])
+def test_schedule_options_are_bit_identical(dt, dz):
+    """The knobs that only change how a step is scheduled leave every bit of the result alone: "lanes" (a large step cut into
+    launches on several work sets and streams), "simple" (columns in which no fall speed can cross the thinnest layer in one
+    step skip k_carries: k_finish settles the snow speed of M:3301 and the top sedimenting levels of M:3208 on its own sweep),
+    "timing" 1 / 2 (kernels one after the other / the normal schedule with events).  dt=60/dz=100 makes most precipitating
+    columns non-simple, dt=10/dz=250 nearly all of them simple: both paths meet the same numbers."""
+    import torch
+    from kid_b200 import synth
+    from kid_b200.kidmp import Thompson
+    ncol, nz = 40000, 60
+    res = {}
+    for name, opts in (("default", {}), ("no_simple", {"simple": 0}), ("lanes3", {"lanes": 3, "lane_min": 4096}),
+                       ("lanes2_stagger", {"lanes": 2, "lane_min": 8192, "stagger": 1, "cell_blocks": 2}),
+                       ("timing1", {"timing": 1}), ("timing2", {"timing": 2})):
+        th = Thompson(set_Nc=100.0, iiwarm=False, l_sediment=True)
+        for k, v in opts.items():
+            th.set_option(k, v)
+        st, p, dzv = synth.make_domain(ncol, nz=nz, nx=1024, device="cuda", dz=dz, col0=300000)
+        ppt = torch.zeros((4, ncol), dtype=torch.float32, device="cuda")
+        acc = torch.zeros((4, ncol), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        for _ in range(3):
+            th.step_device(ncol, nz, dt, [st[k].data_ptr() for k in FIELDS], p.data_ptr(), dzv.data_ptr(), ppt.data_ptr())
+            th.sync()
+            acc += ppt.double()
+        if name.startswith("timing"):
+            ms = th.last_kernel_ms()
+            assert set(ms) >= {"classify", "cells_ice", "finish"} and all(v >= 0.0 for v in ms.values())
+        res[name] = ({k: st[k].cpu().numpy() for k in FIELDS}, acc.cpu().numpy(), th.diag(), th.step_stats())
+        th.close()
+    ref = res["default"]
+    assert ref[2][6] > 0 and ref[1][0].sum() > 0                              # active columns, rain at the surface
+    for name, r in res.items():
+        for k in FIELDS:
+            assert np.array_equal(r[0][k], ref[0][k]), (name, k)
+        assert np.array_equal(r[1], ref[1]), name
+        assert r[2][6] == ref[2][6] and r[2][7] == ref[2][7], name
+        assert np.allclose(r[2][:6], ref[2][:6], rtol=1e-12), name
+        assert r[3]["busy_cells"] == ref[3]["busy_cells"] and r[3]["cloudy_columns"] == ref[3]["cloudy_columns"], name
+    if dt > 30.0:
+        assert ref[3]["substep_columns"] > 0                                    # the sub-stepped path ran
