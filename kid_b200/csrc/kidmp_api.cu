@@ -855,7 +855,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
     size_t want = total < (size_t)max_persist ? total : (size_t)max_persist;
-    // MEASURED (profiles/r02_l2_window.md): with the set-aside (the device grants ~3/5 of L2) the step goes from 3.51 to 5.1 ms -
+    // MEASURED (profiles/r02_ncu_step_kernels.md, "What did not pay"): with the set-aside (the device grants ~3/5 of L2) the step goes from 3.51 to 5.1 ms -
     // k_finish 0.68 -> 1.46 ms, k_carries 0.33 -> 0.62, even k_cells<FULL> 0.35 -> 0.48: the records and the state stream
     // through what is left of L2, and only ~2 % of the busy cells gather from the big tables.  So the window is OFF unless
     // KIDMP_L2_WINDOW=1 asks for it at init.

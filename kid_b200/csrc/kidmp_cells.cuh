@@ -30,12 +30,17 @@ struct Sector { float v[8]; };
 // start fetching the line of a record that the next level of a column walk will read
 __device__ __forceinline__ void prefetch_record(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st_sector(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
-  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e),
+#ifdef KIDMP_EVICT_FIRST
+#define KIDMP_REC_HINT ".L1::no_allocate.L2::evict_first"
+#else
+#define KIDMP_REC_HINT ""
+#endif
+  asm volatile("st.global" KIDMP_REC_HINT ".v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e),
                "f"(f), "f"(g), "f"(h) : "memory");
 }
 __device__ __forceinline__ Sector ld_sector(const float* p) {
   Sector s;
-  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(s.v[0]), "=f"(s.v[1]), "=f"(s.v[2]), "=f"(s.v[3]),
+  asm volatile("ld.global" KIDMP_REC_HINT ".v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(s.v[0]), "=f"(s.v[1]), "=f"(s.v[2]), "=f"(s.v[3]),
                "=f"(s.v[4]), "=f"(s.v[5]), "=f"(s.v[6]), "=f"(s.v[7]) : "l"(p));
   return s;
 }

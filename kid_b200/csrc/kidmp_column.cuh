@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(128, 8) k_classify(StepArgs a) {
   }
 }
 
-// exclusive prefix sum of the per-group cloudy-column counts (one block; ngroups is at most 2^19: 16 777 216 columns per launch)
+// exclusive prefix sum of the per-group cloudy-column counts (one block; ngroups is at most 2^19: 16 777 216 columns per launch).
+// 4096 groups per round: every thread takes four neighbouring ballots (the array is padded to a multiple of four by its allocation).
 __global__ void __launch_bounds__(1024) k_list_scan(const unsigned* __restrict__ mask, int ngroups, int* __restrict__ offset,
                                                     int* __restrict__ count) {
   __shared__ int s_warp[32];
@@ -272,10 +273,13 @@ __global__ void __launch_bounds__(1024) k_list_scan(const unsigned* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_run = 0;
   __syncthreads();
-  for (int g0 = 0; g0 < ngroups; g0 += 1024) {              // 1024 groups per round, coalesced
-    const int g = g0 + threadIdx.x;
-    const int n = g < ngroups ? __popc(mask[g]) : 0;
-    int v = n;
+  for (int g0 = 0; g0 < ngroups; g0 += 4096) {
+    const int g = g0 + threadIdx.x * 4;
+    int n[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) n[j] = g + j < ngroups ? __popc(mask[g + j]) : 0;
+    const int mine = n[0] + n[1] + n[2] + n[3];
+    int v = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
     if (lane == 31) s_warp[warp] = v;
@@ -289,7 +293,9 @@ __global__ void __launch_bounds__(1024) k_list_scan(const unsigned* __restrict__
     __syncthreads();
     const int run = s_run;
     const int incl = v + (warp ? s_warp[warp - 1] : 0);
-    if (g < ngroups) offset[g] = run + incl - n;
+    int e = run + incl - mine;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { if (g + j < ngroups) offset[g + j] = e; e += n[j]; }
     __syncthreads();
     if (threadIdx.x == 1023) s_run = run + incl;
     __syncthreads();

@@ -100,12 +100,21 @@ KIDMP_MATH_FN double dpow(double x, double y) {
   return exp(y * log(x));
 }
 __device__ __forceinline__ double pow_d(double x, double y) { return dpow(x, y); }
+#ifdef KIDMP_NATIVE_F32
+// EXPERIMENT ONLY (tools/variants.py "native32", never the shipped build): the f32 transcendentals on the special-function
+// unit (ex2 / lg2, ~2 ulp) instead of rule 2 of DESIGN.md section 4 - measures what bit-exactness costs and how many cells flip.
+__device__ __forceinline__ float pow_f(float x, float y) { return x == 0.f ? (y > 0.f ? 0.f : __powf(x, y)) : exp2f(y * __log2f(x)); }
+__device__ __forceinline__ float exp_f(float x) { return __expf(x); }
+__device__ __forceinline__ float log10_f(float x) { return __log10f(x); }
+__device__ __forceinline__ float pow10_f(float y) { return exp2f(y * 3.3219280948873623f); }
+#else
 // f32 result: REAL ** REAL of the reference (a libm powf call under gfortran)
 __device__ __forceinline__ float pow_f(float x, float y) { return (float)dpow((double)x, (double)y); }
 __device__ __forceinline__ float exp_f(float x) { return (float)dexp((double)x); }
 __device__ __forceinline__ float log10_f(float x) { return (float)(dlog((double)x) * 0.43429448190325182765); }
 // 10.**y with REAL y (M:1560, M:1646, M:2242 ...)
 __device__ __forceinline__ float pow10_f(float y) { return (float)dexp((double)y * 2.302585092994046); }
+#endif
 __device__ __forceinline__ float cube_f(float x) { double d = x; return (float)(d * d * d); }   // x**bm_r etc.
 __device__ __forceinline__ double cube_d(double x) { return x * x * x; }
 __device__ __forceinline__ double sq_d(double x) { return x * x; }

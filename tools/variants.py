@@ -27,6 +27,8 @@ def per(**kw):
 
 VARIANTS = {
     "base": [],
+    "evict": ["-DKIDMP_EVICT_FIRST"],              # hand-off records stored and loaded with L1 no-allocate / L2 evict-first
+    "native32": ["-DKIDMP_NATIVE_F32"],          # f32 transcendentals on the SFU: what rule 2 of DESIGN.md section 4 costs
     "free": per(WARM=(256, 4, 0), ICE=(256, 4, 0), MIXNR=(256, 3, 0), FULL=(256, 3, 0)),
     "free128": per(WARM=(128, 8, 0), ICE=(128, 8, 0), MIXNR=(128, 6, 0), FULL=(128, 6, 0)),
     "ice5": per(ICE=(256, 5, 11), WARM=(256, 5, 11)),
