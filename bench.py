@@ -13,7 +13,7 @@ data-path collective - NCCL only reduces the eight domain diagnostics once per r
 
 A "step" = one kidmp_step_device call over all resident columns: classification, work list and sorted list of the busy
 cells, the four cell kernels (S1..S13 of every busy cell), what runs down the columns, sedimentation + final clamps,
-ordered domain sums (16 launches per chunk of 1 048 576 columns); the state evolves in place from step to step like a
+ordered domain sums (15 launches per chunk of 1 048 576 columns); the state evolves in place from step to step like a
 model time loop.  Inputs (2.8 GB per GPU) are far larger than L2, so no flush is needed between steps.
 """
 import argparse
@@ -354,7 +354,7 @@ def main():
                        "active_column_fraction": float(diag[6].item() / max(diag[7].item(), 1.0))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": "one step = the sixteen launches of kidmp_step_device (cell kernels k_cells<warm|ice|mixed|full> "
+                         "kernel": "one step = the fifteen launches of kidmp_step_device (cell kernels k_cells<warm|ice|mixed|full> "
                                    "are about half of it); achieved and traffic are for the whole step on this rank, the unit the "
                                    "algorithmic bytes are defined on",
                          "kernel_ms": kern_ms, "alg_bytes_per_launch": ALG_BYTES_PER_COLUMN * ncol,
