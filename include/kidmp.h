@@ -80,7 +80,8 @@ int kidmp_column(kidmp_handle* h, int nz, float dt,
  * arrays out (H2D, kernels, D2H inside the call).  dz is one shared vector of nz (I:63).
  * Large KIDMP_COL_FASTEST domains flow through the device in chunks on three streams.  When the nine field arrays are
  * PINNED host memory (cudaHostAlloc / cudaHostRegister), only the columns the step changed travel back - a clear-sky column
- * is returned bit for bit by the reference too (M:1540) - written by a kernel straight into the host arrays. */
+ * is returned bit for bit by the reference too (M:1540) - written by a kernel straight into the host arrays.
+ * ncol = 0 (here, in kidmp_step_device and as kidmp_kid_columns::nx) is the empty loop of I:54: success, nothing touched. */
 int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout,
                float* const fields[KIDMP_NFIELDS], const float* p, const float* dz, float* ppt);
 

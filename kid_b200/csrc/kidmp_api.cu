@@ -1312,6 +1312,7 @@ static int step_pipelined(kidmp_handle* h, long ncol, int nz, float dt, float* c
 int kidmp_step(kidmp_handle* h, long ncol, int nz, float dt, int layout, float* const fields[KIDMP_NFIELDS],
                const float* p, const float* dz, float* ppt) {
   if (!h) return 1;
+  if (ncol == 0) return 0;                               // `do i = 1, nx` with nx = 0 (I:54): nothing to do, nothing touched
   if (!fields || !p || !dz) return fail(h, "step: null pointer");
   if (h->multi) return multi_step(h, ncol, nz, dt, layout, fields, p, dz, ppt);
   // (with a process-rate buffer set the whole domain goes through the resident path: the buffer is [36][nz][ncol] of the domain)
@@ -1342,6 +1343,7 @@ int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt, float* const
                       const float* d_p, const float* d_dz, float* d_ppt, void* stream) {
   if (!h) return 1;
   if (h->multi) return fail(h, "step_device: device pointers belong to one device; use a single-device handle per GPU");
+  if (ncol == 0) return 0;
   if (!d_fields || !d_p || !d_dz || !d_ppt) return fail(h, "step_device: null pointer");
   DevGuard guard_(h->device);
   StepArgs a{};
@@ -1563,6 +1565,7 @@ int kidmp_last_step_ms(kidmp_handle* h, float* step_ms) {
 int kidmp_kid_interface(kidmp_handle* h, const kidmp_kid_columns* c, float dt, float p0, float r_on_cp) {
   if (!h) return 1;
   if (!c) return fail(h, "kid_interface: null argument");
+  if (c->nx == 0) return 0;                              // an empty domain is not an error (I:54)
   if (h->multi && c->nx >= (long)h->multi->dev.size()) return multi_kid_interface(h, c, dt, p0, r_on_cp);
   if (h->multi) return kidmp_kid_interface(h->multi->dev[0], c, dt, p0, r_on_cp) ? fail(h, "%s", h->multi->dev[0]->err.c_str()) : 0;
   if (!c->theta || !c->dtheta_adv || !c->dtheta_div || !c->exner || !c->qv || !c->dqv_adv || !c->dqv_div || !c->dz ||

@@ -221,6 +221,12 @@ def test_errors_are_returned_not_raised_across_the_abi(gpu_mixed):
     assert "nz" in str(e.value)
     with pytest.raises(KeyError):
         gpu_mixed.get("no_such_table")
+    # an empty domain is the reference's `do i = 1, nx` with nx = 0 (I:54): a successful no-op, nothing is touched
+    empty = {k: np.zeros((60, 0), np.float32) for k in FIELDS}
+    ppt = gpu_mixed.step(10.0, empty, np.zeros((60, 0), np.float32), np.full(60, 250.0, np.float32))
+    assert ppt.shape == (4, 0)
+    with pytest.raises(KidmpError):
+        gpu_mixed._ck(gpu_mixed._L.kidmp_step(gpu_mixed.h, -3, 60, 10.0, 1, None, None, None, None))
 
 
 def test_resident_time_series(gpu_mixed, oracle_mixed):
