@@ -101,6 +101,19 @@ int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt,
                       float* const d_fields[KIDMP_NFIELDS], const float* d_p, const float* d_dz,
                       float* d_ppt, void* stream);
 
+/* Aerosol-aware step (is_aerosol_aware = .true., M:28, with dustyIce = homogIce = .true., M:30-31): the second half of
+ * SURVEY.md section 8f-4.  Device pointers like kidmp_step_device; in addition the cloud droplet number nc and the numbers
+ * of water-friendly and ice-friendly aerosols nwfa, nifa [kg^-1] are prognostic (INOUT, [nz][ncol]; mp_gt_driver's
+ * nc / nwfa / nifa, M:950-956, M:1003-1007), w is the vertical velocity [m s^-1] that feeds the droplet activation
+ * (activ_ncloud, M:2797), d_nwfa2d [ncol] (or NULL) the surface aerosol emission added to the lowest level after the step
+ * (M:1001).  Rain, snow and graupel scavenge aerosols (Eff_aero, M:1729-1740, M:1938-1959), ice nucleates on dust (iceDeMott,
+ * M:2092) and freezes homogeneously from deliquesced aerosols (iceKoop, M:2104-2111), evaporating cloud loses the droplets
+ * smaller than D-star (table_dropEvap, M:2804-2851).  The evaporation table is made by the first such step.  No process-rate
+ * buffer in this mode. */
+int kidmp_step_device_aero(kidmp_handle* h, long ncol, int nz, float dt, float* const d_fields[KIDMP_NFIELDS], float* d_nc,
+                           float* d_nwfa, float* d_nifa, const float* d_p, const float* d_w, const float* d_dz,
+                           const float* d_nwfa2d, float* d_ppt, void* stream);
+
 /* optional per-level process-rate buffer (the 36 save_dg rates of M:2963-3120): device buffer
  * [36][nz][ncol] f32, NULL switches it off (default).  Names: kidmp_rate_names(). */
 int kidmp_set_rates_buffer(kidmp_handle* h, float* d_rates);
@@ -154,6 +167,15 @@ typedef struct kidmp_wrf_fields {
   float *re_cloud, *re_ice, *re_snow;                      /* (i,k,j), optional                               */
 } kidmp_wrf_fields;
 int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in);
+/* the same entry with is_aerosol_aware = .true. (M:28): mp_gt_driver's optional arguments nc, nwfa, nifa (i,k,j, INOUT), the
+ * vertical velocity w (i,k,j, IN) and the surface aerosol emission nwfa2d (i,j, IN, may be NULL) (M:807-832, M:950-956,
+ * M:999-1007); re_cloud then follows the prognostic droplet number (M:4874).  See kidmp_step_device_aero. */
+typedef struct kidmp_wrf_aerosols {
+  float *nc, *nwfa, *nifa;
+  const float* w;
+  const float* nwfa2d;
+} kidmp_wrf_aerosols;
+int kidmp_mp_gt_driver_aero(kidmp_handle* h, const kidmp_wrf_fields* w, const kidmp_wrf_aerosols* ae, float dt_in);
 
 /* Tuning knobs; results do not depend on them.
  * "chunk": columns per launch of the step kernels (default 1 048 576, or the KIDMP_CHUNK environment variable): the work

@@ -56,6 +56,8 @@ struct kidmp_handle {
   HostBins hb;
   TableSet tabs{};
   char* d_tables = nullptr; size_t tables_bytes = 0;   // the slab behind tabs
+  double* d_tnc_wev = nullptr;                          // table_dropEvap (M:4400-4439), made by the first aerosol-aware step
+  float* d_aero = nullptr; size_t aero_floats = 0;      // staging of kidmp_mp_gt_driver_aero
   size_t l2_window_bytes = 0; float l2_hit_ratio = 0.f; // L2 access-policy window over the slab (0: none)
   float table_ms = 0.f;
   bool tables_from_cache = false;
@@ -361,13 +363,13 @@ int ensure_work(kidmp_handle* h, WorkSet& w, long cols, int nz, bool own_stream)
 
 // `bps`: blocks per SM (0: as many as the kernel's launch bounds allow).  With several lanes a cell kernel that left no
 // register of an SM free would keep the other lanes' HBM-bound kernels out until its last block retires.
-template <bool RATES>
+template <bool RATES, bool AERO>
 void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s, cudaEvent_t n0_done, int bps) {
   auto mark = [&](int q) { if (h->timing) cudaEventRecord(h->ev_k[q + 1], s); };
   auto grid = [&](int own) { return (unsigned)(nsm * (bps > 0 && bps < own ? bps : own)); };
-  k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, KC_WARM_BARS, RATES><<<grid(KC_WARM_B), KC_WARM_T, 0, s>>>(a);
+  k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, KC_WARM_BARS, RATES, AERO><<<grid(KC_WARM_B), KC_WARM_T, 0, s>>>(a);
   mark(KT_WARM);
-  k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, KC_ICE_BARS, RATES><<<grid(KC_ICE_B), KC_ICE_T, 0, s>>>(a);
+  k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, KC_ICE_BARS, RATES, AERO><<<grid(KC_ICE_B), KC_ICE_T, 0, s>>>(a);
   mark(KT_ICE);
   if (n0_done) cudaStreamWaitEvent(s, n0_done, 0);     // only the classes with graupel read the intercept minima of k_n0_sweep
   // The two classes that gather from the big tables (qcfz / iaus: mixed; racs, racg, qrfz: full) run with an L2
@@ -382,10 +384,10 @@ void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s, c
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(KC_MIXNR_T); cfg.gridDim = dim3(grid(KC_MIXNR_B)); cfg.dynamicSmemBytes = 0; cfg.stream = s;
   cfg.attrs = att; cfg.numAttrs = (h->l2_window_bytes && h->l2_window) ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES>, a);
+  cudaLaunchKernelEx(&cfg, k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES, AERO>, a);
   mark(KT_MIXNR);
   cfg.blockDim = dim3(KC_FULL_T); cfg.gridDim = dim3(grid(KC_FULL_B));
-  cudaLaunchKernelEx(&cfg, k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES>, a);
+  cudaLaunchKernelEx(&cfg, k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES, AERO>, a);
   mark(KT_FULL);
 }
 
@@ -439,6 +441,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     a.p = a0.p + c0; a.ppt = a0.ppt + c0;
     if (a0.dz_col) a.dz_col = a0.dz_col + c0;
     if (a0.rates) a.rates = a0.rates + c0;
+    if (a0.nc) { a.nc = a0.nc + c0; a.nwfa = a0.nwfa + c0; a.nifa = a0.nifa + c0; a.w = a0.w + c0; }
     const long ngroups = (a.ncol + 31) / 32, lblocks = (a.ncol + LIST_TILE - 1) / LIST_TILE;
     a.scratch = w.d_scratch; a.scratch_b = w.d_scratch + (size_t)w.cols * w.nz * SC_HALF; a.cellidx = w.d_cellidx; a.cls = w.d_cls; a.colflag = w.d_colflag;
     a.work_count = w.d_work; a.work_list = w.d_work + 8;
@@ -484,15 +487,20 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     }
     if (nl > 1) CK(h, cudaEventRecord(w.ev_lists, cs));
     cudaEvent_t n0_done = serial ? nullptr : w.ev_dag[3];
-    if (a.rates) launch_cells<true>(h, a, h->nsm, cs, n0_done, bps); else launch_cells<false>(h, a, h->nsm, cs, n0_done, bps);
+    const bool aero = a.nc != nullptr;                  // (an aerosol-aware step has no process-rate buffer: checked by its entry point)
+    if (aero) launch_cells<false, true>(h, a, h->nsm, cs, n0_done, bps);
+    else if (a.rates) launch_cells<true, false>(h, a, h->nsm, cs, n0_done, bps);
+    else launch_cells<false, false>(h, a, h->nsm, cs, n0_done, bps);
     k_carries<<<(unsigned)((a.ncol + 63) / 64), 64, 0, cs>>>(a);
     mark(KT_CARRIES);
     // the columns with sedimentation sub-steps on the second stream, the others on this one: disjoint columns
     fork(w.ev_fork, cs, x);
     const unsigned sgrid = (unsigned)(ngroups < h->nsm * 16 ? ngroups : h->nsm * 16);
-    if (a.rates) k_substeps<true><<<sgrid, 32, 0, x>>>(a); else k_substeps<false><<<sgrid, 32, 0, x>>>(a);
+    if (aero) k_substeps<false, true><<<sgrid, 32, 0, x>>>(a);
+    else if (a.rates) k_substeps<true, false><<<sgrid, 32, 0, x>>>(a); else k_substeps<false, false><<<sgrid, 32, 0, x>>>(a);
     mark(KT_SUBSTEPS);
-    if (a.rates) k_finish<true><<<(unsigned)ngroups, 32, 0, cs>>>(a); else k_finish<false><<<(unsigned)ngroups, 32, 0, cs>>>(a);
+    if (aero) k_finish<false, true><<<(unsigned)ngroups, 32, 0, cs>>>(a);
+    else if (a.rates) k_finish<true, false><<<(unsigned)ngroups, 32, 0, cs>>>(a); else k_finish<false, false><<<(unsigned)ngroups, 32, 0, cs>>>(a);
     mark(KT_FINISH);
     fork(w.ev_join, x, cs);
     k_diag_columns<<<DIAG_BLOCKS, 256, 0, cs>>>(a, (a.ncol + DIAG_BLOCKS - 1) / DIAG_BLOCKS);
@@ -838,6 +846,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   memset(&h->hb, 0, sizeof h->hb);
   hostinit::Prep pp;
   hostinit::compute(h->cfg, h->kc, h->hb, pp);
+  h->kc.t_Nc1 = h->hb.t_Nc[0];
   publish_constants(h);
   {
     // one slab for all lookup tables (the gathered ones first): one L2 access-policy window covers them
@@ -901,6 +910,8 @@ int kidmp_finalize(kidmp_handle* h) {
   cudaDeviceSynchronize();                           // steps may have run on caller streams
   free_state(h);
   if (h->d_tables) cudaFree(h->d_tables);
+  if (h->d_tnc_wev) cudaFree(h->d_tnc_wev);
+  if (h->d_aero) cudaFree(h->d_aero);
   if (h->d_partial) cudaFree(h->d_partial);
   if (h->d_diag) cudaFree(h->d_diag);
   if (h->d_kid) cudaFree(h->d_kid);
@@ -1357,6 +1368,60 @@ int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt, float* const
   return 0;
 }
 
+// table_dropEvap, M:4400-4439: number of the cloud droplets smaller than D-star for every (D-star bin, cloud water node,
+// droplet number node).  Only an aerosol-aware run reads it (M:2850): made by the first such step, on the host with the
+// expressions and the libm of the reference's own table builder (3.7e5 entries), and the constants re-published.
+int ensure_wev_table(kidmp_handle* h) {
+  if (h->d_tnc_wev) return 0;
+  const HostBins& b = h->hb;
+  const KConst& kc = h->kc;
+  std::vector<double> tnc((size_t)NBINS * NTB_C * NBINS), N_c(NBINS);
+  for (int k = 0; k < NBINS; ++k) {
+    const int nu_c = std::min(15, (int)std::lround((double)1000.E6f / b.t_Nc[k]) + 2);
+    for (int j = 0; j < NTB_C; ++j) {
+      const double lamc = std::pow(b.t_Nc[k] * (double)kc.am_r * (double)kc.ccg[1][nu_c - 1] * (double)kc.ocg1[nu_c - 1] / (double)b.r_c[j], (double)kc.obmr);
+      const double N0_c = b.t_Nc[k] * (double)kc.ocg1[nu_c - 1] * std::pow(lamc, (double)kc.cce[0][nu_c - 1]);
+      for (int i = 0; i < NBINS; ++i) {
+        double dp = 1.0;                                  // Dc(i)**nu_c, integer power: by squaring like libgcc's powi
+        { double x = b.Dc[i]; int n = nu_c; while (n) { if (n & 1) dp *= x; n >>= 1; if (n) x *= x; } }
+        N_c[i] = N0_c * dp * std::exp(-lamc * b.Dc[i]) * b.dtc[i];
+        double summ2 = 0.0;
+        for (int n = 0; n <= i; ++n) summ2 = summ2 + N_c[n];
+        tnc[(size_t)i + (size_t)NBINS * (j + (size_t)NTB_C * k)] = summ2;
+      }
+    }
+  }
+  CK(h, cudaMalloc((void**)&h->d_tnc_wev, tnc.size() * 8));
+  CK(h, cudaMemcpy(h->d_tnc_wev, tnc.data(), tnc.size() * 8, cudaMemcpyHostToDevice));
+  h->kc.tnc_wev = h->d_tnc_wev;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_const_owner[h->device] == h) g_const_owner[h->device] = nullptr;      // the next step uploads the constants again
+  return 0;
+}
+
+int kidmp_step_device_aero(kidmp_handle* h, long ncol, int nz, float dt, float* const d_fields[KIDMP_NFIELDS], float* d_nc,
+                           float* d_nwfa, float* d_nifa, const float* d_p, const float* d_w, const float* d_dz,
+                           const float* d_nwfa2d, float* d_ppt, void* stream) {
+  if (!h) return 1;
+  if (h->multi) return fail(h, "step_device_aero: device pointers belong to one device; use a single-device handle per GPU");
+  if (ncol == 0) return 0;
+  if (!d_fields || !d_nc || !d_nwfa || !d_nifa || !d_p || !d_w || !d_dz || !d_ppt) return fail(h, "step_device_aero: null pointer");
+  if (h->d_rates || h->rates_on) return fail(h, "step_device_aero: the process-rate buffer is not available in an aerosol-aware step");
+  DevGuard guard_(h->device);
+  if (ensure_wev_table(h)) return 1;
+  StepArgs a{};
+  a.ncol = ncol; a.ld = ncol; a.nz = nz; a.dt = dt;
+  for (int q = 0; q < KIDMP_NFIELDS; ++q) { if (!d_fields[q]) return fail(h, "step_device_aero: field %d is null", q); a.f[q] = d_fields[q]; }
+  a.p = d_p; a.dz = d_dz; a.ppt = d_ppt; a.nc = d_nc; a.nwfa = d_nwfa; a.nifa = d_nifa; a.w = d_w;
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  if (s == h->stream) CK(h, cudaEventRecord(h->ev0, s));
+  if (launch_step(h, a, s)) return 1;
+  // what mp_gt_driver does after the call (M:1001): surface emission into the lowest level, every column
+  if (d_nwfa2d) { k_nwfa_surface<<<(unsigned)((ncol + 255) / 256), 256, 0, s>>>(d_nwfa, d_nwfa2d, ncol, dt); ++h->launches; CK(h, cudaEventRecord(h->ev_done, s)); }
+  if (s == h->stream) CK(h, cudaEventRecord(h->ev1, s));
+  return 0;
+}
+
 int kidmp_set_rates_buffer(kidmp_handle* h, float* d_rates) {
   if (!h) return 1;
   if (h->multi) return fail(h, "set_rates_buffer: device pointers belong to one device; use a single-device handle");
@@ -1382,9 +1447,16 @@ int kidmp_diag(kidmp_handle* h, double out[KIDMP_NDIAG]) {
 }
 
 // mp_gt_driver, M:806-1143 (see kidmp_wrf.cuh)
-int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in) {
+static int wrf_driver(kidmp_handle* h, const kidmp_wrf_fields* w, const kidmp_wrf_aerosols* ae, float dt_in);
+int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in) { return wrf_driver(h, w, nullptr, dt_in); }
+int kidmp_mp_gt_driver_aero(kidmp_handle* h, const kidmp_wrf_fields* w, const kidmp_wrf_aerosols* ae, float dt_in) {
   if (!h) return 1;
-  if (h->multi) return kidmp_mp_gt_driver(h->multi->dev[0], w, dt_in) ? fail(h, "%s", h->multi->dev[0]->err.c_str()) : 0;   // one tile, one device
+  if (!ae || !ae->nc || !ae->nwfa || !ae->nifa || !ae->w) return fail(h, "mp_gt_driver_aero: null aerosol array");
+  return wrf_driver(h, w, ae, dt_in);
+}
+static int wrf_driver(kidmp_handle* h, const kidmp_wrf_fields* w, const kidmp_wrf_aerosols* ae, float dt_in) {
+  if (!h) return 1;
+  if (h->multi) return wrf_driver(h->multi->dev[0], w, ae, dt_in) ? fail(h, "%s", h->multi->dev[0]->err.c_str()) : 0;   // one tile, one device
   if (!w) return fail(h, "mp_gt_driver: null argument");
   if (w->ni < 1 || w->nj < 1 || w->nk < 2) return fail(h, "mp_gt_driver: bad dimensions %d x %d x %d", w->ni, w->nk, w->nj);
   float* const io[9] = {w->qv, w->qc, w->qi, w->qr, w->qs, w->qg, w->ni_, w->nr, w->th};      // state-field order
@@ -1437,9 +1509,39 @@ int kidmp_mp_gt_driver(kidmp_handle* h, const kidmp_wrf_fields* w, float dt_in) 
   CK(h, cudaEventRecord(h->ev0, h->stream));
   StepArgs sa = resident_args(h, dt_in);
   sa.dz_col = a.dz_col;
+  float* d_ae = nullptr;                                // aerosol-aware run: 4 (i,k,j) arrays, their 4 planes, nwfa2d
+  if (ae) {
+    if (sa.rates) return fail(h, "mp_gt_driver_aero: the process-rate buffer is not available in an aerosol-aware step");
+    if (ensure_wev_table(h)) return 1;
+    if (h->aero_floats < 8 * n + n2) {
+      if (h->d_aero) cudaFree(h->d_aero);
+      h->d_aero = nullptr; h->aero_floats = 0;
+      CK(h, cudaMalloc((void**)&h->d_aero, (8 * n + n2) * 4));
+      h->aero_floats = 8 * n + n2;
+    }
+    d_ae = h->d_aero;
+    const float* const in4[4] = {ae->nc, ae->nwfa, ae->nifa, ae->w};
+    for (int q = 0; q < 4; ++q) {
+      CK(h, cudaMemcpyAsync(d_ae + n * q, in4[q], n * 4, cudaMemcpyHostToDevice, h->stream));
+      k_ikj_planes<<<g, b, 0, h->stream>>>(d_ae + n * q, d_ae + n * (4 + q), w->ni, w->nk, w->nj, 1);
+    }
+    if (ae->nwfa2d) CK(h, cudaMemcpyAsync(d_ae + 8 * n, ae->nwfa2d, n2 * 4, cudaMemcpyHostToDevice, h->stream));
+    sa.nc = d_ae + 4 * n; sa.nwfa = d_ae + 5 * n; sa.nifa = d_ae + 6 * n; sa.w = d_ae + 7 * n;
+    a.nc_plane = sa.nc;
+    h->launches += 4;
+  }
   if (launch_step(h, sa, h->stream)) return 1;
+  if (ae && ae->nwfa2d) { k_nwfa_surface<<<(unsigned)((ncol + 255) / 256), 256, 0, h->stream>>>(sa.nwfa, d_ae + 8 * n, ncol, dt_in); ++h->launches; }   // M:1001
   CK(h, cudaEventRecord(h->ev1, h->stream));
   k_wrf_scatter<<<g, b, 0, h->stream>>>(a, h->kc.Nt_c);
+  if (ae) {
+    float* const out3[3] = {ae->nc, ae->nwfa, ae->nifa};
+    for (int q = 0; q < 3; ++q) {
+      k_ikj_planes<<<g, b, 0, h->stream>>>(d_ae + n * q, d_ae + n * (4 + q), w->ni, w->nk, w->nj, 0);
+      CK(h, cudaMemcpyAsync(out3[q], d_ae + n * q, n * 4, cudaMemcpyDeviceToHost, h->stream));   // (synchronised with the stream below)
+    }
+    h->launches += 3;
+  }
   k_wrf_accumulate<<<(unsigned)((ncol + 255) / 256), 256, 0, h->stream>>>(a);
   h->launches += 3;
   CK(h, cudaGetLastError());

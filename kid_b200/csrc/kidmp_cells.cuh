@@ -21,6 +21,7 @@
 // every class kernel computes bit for bit what the general code (KC_FULL) computes for the same cell.
 #pragma once
 #include "kidmp_column.cuh"
+#include "kidmp_aero.cuh"
 
 namespace kidmp {
 
@@ -216,7 +217,9 @@ __global__ void __launch_bounds__(128) k_n0_sweep(StepArgs a) {
 // LOCK: the warps of a block meet at named barriers between the stages, so they run the same straight-line code at the
 // same time and share its instruction-cache lines (the full cell code is ~100 KB of SASS; profiles/r01).  Used for the
 // classes with the long bodies; the short ones run free.
-template <int KC, int THREADS, int MINB, int BARS, bool RATES>
+// AERO: is_aerosol_aware = .true. (M:28): cloud droplet number, water-friendly and ice-friendly aerosol numbers are prognostic
+// (a.nc, a.nwfa, a.nifa), a.w feeds the droplet activation; every aerosol block is compiled out of the default kernels.
+template <int KC, int THREADS, int MINB, int BARS, bool RATES, bool AERO>
 __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
   using TR = CellTraits<KC>;
   constexpr bool LOCK = BARS != 0;
@@ -251,6 +254,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
     float qc1d = TR::C ? a.f[F_QC][o] : 0.0f, qi1d = TR::I ? a.f[F_QI][o] : 0.0f, qr1d = TR::R ? a.f[F_QR][o] : 0.0f,
           qs1d = TR::S ? a.f[F_QS][o] : 0.0f, qg1d = TR::G ? a.f[F_QG][o] : 0.0f;
     float ni1d = TR::I ? a.f[F_NI][o] : 0.0f, nr1d = TR::R ? a.f[F_NR][o] : 0.0f;
+    float nc1d_in = 0.f, nwfa1d = 0.f, nifa1d = 0.f, w1d = 0.f;
+    if (AERO) { nc1d_in = TR::C ? a.nc[o] : 0.0f; nwfa1d = a.nwfa[o]; nifa1d = a.nifa[o]; w1d = a.w[o]; }
     float* const sc = sc_class + (size_t)(valid ? i : wbase) * SC_HALF;
     float* const sb = sb_class + (size_t)(valid ? i : wbase) * SC_HALF;
 
@@ -271,6 +276,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
     // number tendencies are summed as their terms appear (M:2417, M:2453, M:2503 add them up later): the
     // 22 individual number rates need not stay in registers until S8
     double nc_acc = 0., ni_acc = 0., nr_acc = 0.;
+    double na_acc = 0., nd_acc = 0., pri_iha = 0., pni_iha = 0.;   // AERO: pna_rca + pna_sca + pna_gca (+ pni_iha at S8), pnd_rcd + pnd_scd + pnd_gcd (M:2399-2402)
+    float nwfa = 0.f, nifa = 0.f;
     // lamr / lami hold rain_lam(nr, rr) / ice_lam(ni, ri) of the current nr, rr / ni, ri unless the number was
     // re-diagnosed after they were evaluated: the reference evaluates the same power again at M:1661, M:2118,
     // M:2750 and M:3227 from unchanged arguments, which is the same number
@@ -282,12 +289,25 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
     float rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
     float rc, nc, ri, ni, rr, nr, rs, rg;
     bool L_qc, L_qi, L_qr, L_qs, L_qg;
+    if (AERO) {                                            // M:1392-1393
+      nwfa = fmaxf(11.1E6f, fminf(9999.E6f, nwfa1d * rho));
+      nifa = fmaxf(KP_NAIN1 * 0.01f, fminf(9999.E6f, nifa1d * rho));
+    }
     if (TR::C && qc1d > R1) {
       rc = qc1d * rho;
       L_qc = true;
-      nc = Nt_c;   // the lamc/xDc clamps of M:1399-1408 only feed nc, overwritten at M:1410
+      nc = Nt_c;   // the lamc/xDc clamps of M:1399-1408 only feed nc, overwritten at M:1410 ...
+      if (AERO) {  // ... unless the scheme is aerosol aware
+        nc = fmaxf(2.f, nc1d_in * rho);
+        const int nu = min(15, nint_f(1000.E6f / nc) + 2);
+        double lc = (double)pow_f(nc * ck.am_r * ck.ccg[1][nu - 1] * ck.ocg1[nu - 1] / rc, ck.obmr);
+        const float xD = (float)((double)(3.f + (float)nu + 1.f) / lc);
+        if (xD < D0c) lc = (double)(ck.cce[1][nu - 1] / D0c);
+        else if (xD > D0r * 2.f) lc = (double)(ck.cce[1][nu - 1] / (D0r * 2.f));
+        nc = (float)fmin((double)KP_NT_C_MAX, (double)(ck.ccg[0][nu - 1] * ck.ocg2[nu - 1] * rc / ck.am_r) * cube_d(lc));
+      }
     } else {
-      qc1d = 0.0f; rc = R1; nc = 2.f; L_qc = false;
+      qc1d = 0.0f; nc1d_in = 0.0f; rc = R1; nc = 2.f; L_qc = false;
     }
     if (TR::I && qi1d > R1) {
       ri = qi1d * rho;
@@ -423,6 +443,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       pnc_rcw = fmin((double)(nc * odts), pnc_rcw);
       nc_acc -= pnc_rcw;
     }
+    // M:1729-1740 rain collecting aerosols, wet scavenging
+    if (AERO && TR::R && L_qr && mvd_r > D0r) {
+      lamr = (double)1.f / ilamr;
+      const double lf4 = 1.0 / sq_d(sq_d(lamr + (double)KP_FV_R));          // (lamr+fv_r)**(-cre(9)), cre(9) = 4
+      float Ef_ra = eff_aero<'r'>(mvd_r, 0.04E-6f, visco, rho, temp);
+      const double pna_rca = fmin((double)(nwfa * odts), (double)(rhof * ck.t1_qr_qc * Ef_ra * nwfa) * N0_r * lf4);
+      Ef_ra = eff_aero<'r'>(mvd_r, 0.8E-6f, visco, rho, temp);
+      const double pnd_rcd = fmin((double)(nifa * odts), (double)(rhof * ck.t1_qr_qc * Ef_ra * nifa) * N0_r * lf4);
+      na_acc += pna_rca; nd_acc += pnd_rcd;
+    }
 
     LOCKBAR(1);
     // ---- S6, M:1749-2286 ice-phase processes --------------------------------------------------
@@ -506,6 +536,27 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
         }
       }
 
+      // M:1938-1959 snow and graupel collecting aerosols, wet scavenging
+      if (AERO && TR::S && rs > ck.r_s1) {
+        const float tc0 = fminf(-0.1f, temp - 273.15f);
+        const float smoc_a = field_moment(tc0, ck.cse[0], smob), smoe_a = field_moment(tc0, ck.cse[12], smob);
+        const float xDs = smoc_a / smob;
+        float Ef_sa = eff_aero<'s'>(xDs, 0.04E-6f, visco, rho, temp);
+        const double pna_sca = fmin((double)(nwfa * odts), (double)(rhof * ck.t1_qs_qc * Ef_sa * nwfa * smoe_a));
+        Ef_sa = eff_aero<'s'>(xDs, 0.8E-6f, visco, rho, temp);
+        const double pnd_scd = fmin((double)(nifa * odts), (double)(rhof * ck.t1_qs_qc * Ef_sa * nifa * smoe_a));
+        na_acc += pna_sca; nd_acc += pnd_scd;
+      }
+      if (AERO && TR::G && rg > ck.r_g1) {
+        const float xDg = (float)((double)(3.f + 0.f + 1.f) * ilamg);
+        const double il9 = pow_d(ilamg, (double)ck.cge[8]);
+        float Ef_ga = eff_aero<'g'>(xDg, 0.04E-6f, visco, rho, temp);
+        const double pna_gca = fmin((double)(nwfa * odts), (double)(rhof * ck.t1_qg_qc * Ef_ga * nwfa) * N0_g * il9);
+        Ef_ga = eff_aero<'g'>(xDg, 0.8E-6f, visco, rho, temp);
+        const double pnd_gcd = fmin((double)(nifa * odts), (double)(rhof * ck.t1_qg_qc * Ef_ga * nifa) * N0_g * il9);
+        na_acc += pna_gca; nd_acc += pnd_gcd;
+      }
+
       // M:1964-2019 rain-snow and rain-graupel collection tables (interleaved records)
       if (TR::R && rr >= ck.r_r1) {
         if (rs >= ck.r_s1) {
@@ -580,12 +631,32 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
         }
         // M:2090-2101 Cooper nucleation
         if ((ssati >= 0.25f) || (ssatw > EPSF && temp < 253.15f)) {
-          const float xnc = fminf(250.E3f, KP_TNO * exp_f(KP_ATO * (T_0 - temp)));
+          const float xnc = AERO ? ice_demott(tempc, rho, nifa)                       // dustyIce, M:2092-2093
+                                 : fminf(250.E3f, KP_TNO * exp_f(KP_ATO * (T_0 - temp)));
           const float xni = (float)((double)ni + (pni_rfz + pni_wfz) * (double)DT);
           pni_inu = (double)(0.5f * (xnc - xni + fabsf(xnc - xni)) * odts);
           pri_inu = fmin((double)rate_max, (double)KP_XM0I * pni_inu);
           pni_inu = (pri_inu == 0.0) ? pri_inu : pri_inu / (double)KP_XM0I;      // (a zero keeps its sign either way)
           ni_acc += pni_inu;
+        }
+        // M:2104-2111 freezing of aqueous aerosols (Koop et al. 2001); the 0th snow moment as at M:1557-1560
+        if (AERO && temp < 238.f && ssati >= 0.4f) {
+          float smo0_a = 0.f;
+          if (L_qs) {
+            const float tc0 = fminf(-0.1f, temp - 273.15f);
+            const float* sa = c_sa; const float* sb = c_sb;
+            const float loga_ = sa[1] + sa[2] * tc0 + sa[5] * tc0 * tc0 + sa[9] * tc0 * tc0 * tc0;
+            const float b_ = sb[1] + sb[2] * tc0 + sb[5] * tc0 * tc0 + sb[9] * tc0 * tc0 * tc0;
+            smo0_a = pow10_f(loga_) * pow_f(smob, b_);
+          }
+          const float xni = (float)((double)(smo0_a + ni) + (pni_rfz + pni_wfz + pni_inu) * (double)DT);
+          if (xni <= 500.E3f) {
+            const float xnc = ice_koop(temp, qv, qvs, nwfa, DT);
+            pni_iha = (double)(xnc * odts);
+            pri_iha = fmin((double)rate_max, (double)(KP_XM0I * 0.1f) * pni_iha);
+            pni_iha = pri_iha / (double)(KP_XM0I * 0.1f);
+            ni_acc += pni_iha;
+          }
         }
         // M:2116-2149 deposition / sublimation of cloud ice, ice -> snow
         float oxmi = 0.f, xDi = 0.f;
@@ -726,12 +797,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
     {
       float sump, rate_max;
       if (TR::ICEPROC) {
-        sump = (float)(pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + 0.0);
+        sump = (float)(pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + pri_iha);
         rate_max = (qv - qvsi) * odts * 0.999f;                                // U7: no rho factor here
         if ((sump > EPSF && sump > rate_max) || (sump < -EPSF && sump < rate_max)) {
           const double ratio = (double)(rate_max / sump);
           pri_inu *= ratio; pri_ide *= ratio; pni_ide *= ratio; prs_ide *= ratio; prs_sde *= ratio;
           if (TR::G) prg_gde *= ratio;
+          if (AERO) pri_iha *= ratio;
         }
       }
       if (TR::C) {
@@ -794,13 +866,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
     }
 
     // U1 again (nc1d = 0 without cloud water, M:1409)
-    const float nc1d = (qc1d > R1) ? Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f))) : 0.0f;
+    const float nc1d = AERO ? nc1d_in : ((qc1d > R1) ? Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f))) : 0.0f);
+    float nwfat = 0.f, nifat = 0.f;
     // ---- S8, M:2393-2569 tendencies and number/mass balances ------------------------------------
     float tt, qvt, qct, qit, qrt, qst, qgt, nit, nrt, nct;
     {
       const float orho = 1.f / rho;
       const float lfus2 = KP_LSUB - lvap;
-      qvt = (float)((-pri_inu - pri_ide - prs_ide - prs_sde - prg_gde) * (double)orho);
+      if (AERO) {                                          // M:2398-2408 (dustyIce)
+        nwfat = (float)((double)0.f - (na_acc + pni_iha) * (double)orho);
+        nifat = (float)((double)0.f - nd_acc * (double)orho);
+        nifat = (float)((double)nifat - pni_inu * (double)orho);
+      }
+      qvt = (float)((-pri_inu - pri_iha - pri_ide - prs_ide - prs_sde - prg_gde) * (double)orho);
       qct = (float)((-prr_wau - pri_wfz - prr_rcw - prs_scw - prg_scw - prg_gcw) * (double)orho);
       nct = (float)(nc_acc * (double)orho);
       float xrc = fmaxf(R1, (qc1d + qct * DT) * rho);
@@ -824,7 +902,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       xnc = fmaxf(0.f, (nc1d + nct * DT) * rho);
       if (xnc > KP_NT_C_MAX) nct = (KP_NT_C_MAX - nc1d * rho) * odts * orho;
 
-      qit = (float)((pri_inu + pri_ihm + pri_wfz + pri_rfz + pri_ide - prs_iau - prs_sci - pri_rci) * (double)orho);
+      qit = (float)((pri_inu + pri_iha + pri_ihm + pri_wfz + pri_rfz + pri_ide - prs_iau - prs_sci - pri_rci) * (double)orho);
       nit = (float)((ni_acc + pni_ide) * (double)orho);
       const float xri = fmaxf(R1, (qi1d + qit * DT) * rho);
       float xni = fmaxf(R2, (ni1d + nit * DT) * rho);
@@ -870,7 +948,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       qst = (float)((prs_iau + prs_sde + prs_sci + prs_scw + prs_rcs + prs_ide - prs_ihm - prr_sml) * (double)orho);
       qgt = (float)((prg_scw + prg_rfz + prg_gde + prg_rcg + prg_gcw + prg_rci + prg_rcs - prg_ihm - prr_gml) * (double)orho);
       if (TR::COLD || temp < T_0) {
-        tt = (float)(((double)(KP_LSUB * ocp) * (pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + 0.0)
+        tt = (float)(((double)(KP_LSUB * ocp) * (pri_inu + pri_ide + prs_ide + prs_sde + prg_gde + pri_iha)
                       + (double)(lfus2 * ocp) * (pri_wfz + pri_rfz + prg_rfz + prs_scw + prg_scw + prg_gcw + prg_rcs
                                                  + prs_rcs + prr_rci + prg_rcg))
                      * (double)orho * (double)1);
@@ -913,7 +991,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       ocp = 1.f / (KP_CP * (1.f + 0.887f * qv));
       lvt2 = lvap * lvap * ocp * ck.oRv * otemp * otemp;
 
-      if (TR::C9 && (qc1d + qct * DT) > R1) { rc = (qc1d + qct * DT) * rho; nc = Nt_c; L_qc = true; }
+      if (AERO) nwfa = fmaxf(11.1E6f, (nwfa1d + nwfat * DT) * rho);                          // M:2597
+      if (TR::C9 && (qc1d + qct * DT) > R1) { rc = (qc1d + qct * DT) * rho; nc = AERO ? fmaxf(2.f, (nc1d + nct * DT) * rho) : Nt_c; L_qc = true; }
       else { rc = R1; nc = 2.f; L_qc = false; }
       if (TR::I9 && (qi1d + qit * DT) > R1) { ri = (qi1d + qit * DT) * rho; ni = fmaxf(R2, (ni1d + nit * DT) * rho); L_qi = true; }
       else { ri = R1; ni = R2; L_qi = false; }
@@ -971,8 +1050,33 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       if (xrc > R1) {
         prw_vcd = (double)(clap * odt);
         if (clap > EPSF) {
-          const float xnc = Nt_c;
+          const float xnc = AERO ? fmaxf(2.f, activ_ncloud(temp, w1d, nwfa)) : Nt_c;
           pnc_wcd = (double)(0.5f * (xnc - nc + fabsf(xnc - nc)) * odts * orho);
+        } else if (AERO && clap < -EPSF && ssatw < -1.E-6f) {
+          // M:2804-2851 the droplets smaller than Dc_star evaporate (table_dropEvap); diffu, tcond of S9 (M:2588-2593)
+          const float tc9 = temp - 273.15f, otemp = 1.f / temp, oRv = ck.oRv;
+          const float diffu9 = 2.11E-5f * pow_f(temp / 273.15f, 1.94f) * (101325.f / pres);
+          const float tcond9 = (5.69f + 0.0168f * tc9) * 1.0E-5f * 418.936f;
+          const float rvs = rho * qvs;
+          const float rvs_p = rvs * otemp * (lvap * otemp * oRv - 1.f);
+          const float rvs_pp = rvs * (otemp * (lvap * otemp * oRv - 1.f) * otemp * (lvap * otemp * oRv - 1.f)
+                                      + (-2.f * lvap * otemp * otemp * otemp * oRv) + otemp * otemp);
+          const float gamsc = lvap * diffu9 / tcond9 * rvs_p;
+          float alphsc = 0.5f * (gamsc / (1.f + gamsc)) * (gamsc / (1.f + gamsc)) * rvs_pp / rvs_p * rvs / rvs_p;
+          alphsc = fmaxf(1.E-9f, alphsc);
+          float xsat = ssatw;
+          if (fabsf(xsat) < 1.E-9f) xsat = 0.f;
+          const float t1_evap = 2.f * KP_PI * (1.0f - alphsc * xsat + 2.f * alphsc * alphsc * xsat * xsat
+                                               - 5.f * alphsc * alphsc * alphsc * xsat * xsat * xsat) / (1.f + gamsc);
+          const double Dc_star = sqrt(-2.0 * (double)DT * (double)t1_evap / (double)(2.f * KP_PI) * 4.0 * (double)diffu9 * (double)ssatw
+                                      * (double)rvs / (double)KP_RHO_W);
+          const int idx_d = max(1, min((int)(1.E6 * Dc_star), (int)NBINS));
+          int idx_n = nint_d(1.0 + (double)(float)NBINS * dlog((double)nc / ck.t_Nc1) / (double)ck.nic1);
+          idx_n = max(1, min(idx_n, (int)NBINS));
+          const int idx_c = (rc > ck.r_c1) ? decade_idx_f(rc, ck.nic2, NTB_C) : 1;
+          prw_vcd = fmax((double)(-rc * 0.99f * orho * odt), prw_vcd);
+          const double tnc = ck.tnc_wev[(size_t)(idx_d - 1) + (size_t)NBINS * ((idx_c - 1) + (size_t)NTB_C * (idx_n - 1))];
+          pnc_wcd = fmax((double)(-nc * 0.99f * orho * odt), (double)(-tnc * (double)orho * (double)odt));
         }
       } else {
         prw_vcd = (double)(-rc * orho * odt);
@@ -981,9 +1085,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       qvt = (float)((double)qvt - prw_vcd);
       qct = (float)((double)qct + prw_vcd);
       nct = (float)((double)nct + pnc_wcd);
+      if (AERO) nwfat = (float)((double)nwfat - pnc_wcd);
       tt = (float)((double)tt + (double)(lvap * ocp) * prw_vcd * (double)1);
       rc = fmaxf(R1, (qc1d + DT * qct) * rho);
-      nc = Nt_c;
+      nc = AERO ? fmaxf(2.f, (nc1d + DT * nct) * rho) : Nt_c;
       qv = fmaxf(1.E-10f, qv1d + DT * qvt);
       temp = t1d + DT * tt;
       rho = 0.622f * pres / (KP_R * temp * (qv + 0.622f));
@@ -1035,6 +1140,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       qrt = (float)((double)qrt - prv_rev);
       qvt = (float)((double)qvt + prv_rev);
       nrt = (float)((double)nrt - pnr_rev);
+      if (AERO) nwfat = (float)((double)nwfat + pnr_rev);                                   // M:2952
       tt = (float)((double)tt - (double)(lvap * ocp) * prv_rev * (double)1);
       rr = fmaxf(R1, (qr1d + DT * qrt) * rho);
       qv = fmaxf(1.E-10f, qv1d + DT * qvt);
@@ -1095,7 +1201,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       const float n0a_out = warm9 ? -(float)n0b_lo : (float)n0b_lo;
       // two 64-byte half records, four whole sectors, SC_* order
       st_sector(sc, tt, qvt, qct, qit, qrt, qst, qgt, nit);
-      st_sector(sc + 8, nrt, nct, nr, ni, v_ni, 0.f, 0.f, 0.f);
+      st_sector(sc + 8, nrt, nct, nr, ni, v_ni, nwfat, nifat, 0.f);
       st_sector(sb, rr, ri, rs, rg, v_r, v_nr, v_i, rho);
       st_sector(sb + 8, s15, n0a_out, (float)n0b_slw, vts_h, vts_boost, temp, 0.f, 0.f);
       // An upper bound of every fall speed this cell can hand a level of its column, for the test "no species of this column
@@ -1290,8 +1396,8 @@ __device__ __forceinline__ void idle_record(float temp, float pres, float qv1d, 
 // Then all but the last sub-step of each species (M:3365-3578), then the last one with S15 / S16 (finish_level), as k_finish
 // does for the other columns.  Runs beside k_finish on a second stream: the two kernels own different columns.
 enum { WS_TTEN = 0, WS_QVTEN, WS_QCTEN, WS_QITEN, WS_QRTEN, WS_QSTEN, WS_QGTEN, WS_NITEN, WS_NRTEN, WS_NCTEN,
-       WS_RR, WS_NR, WS_RI, WS_NI, WS_RS, WS_RG, WS_VTR, WS_VTNR, WS_VTI, WS_VTNI, WS_VTS, WS_VTG, WS_RHO, WS_S15, WS_N };
-template <bool RATES>
+       WS_RR, WS_NR, WS_RI, WS_NI, WS_RS, WS_RG, WS_VTR, WS_VTNR, WS_VTI, WS_VTNI, WS_VTS, WS_VTG, WS_RHO, WS_S15, WS_NWFAT, WS_NIFAT, WS_N };
+template <bool RATES, bool AERO>
 __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
   const int n = *a.sub_count, count = *a.work_count;
   const int nz = a.nz;
@@ -1326,6 +1432,7 @@ __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
           w[WS_NRTEN * ps] = s1.v[0]; w[WS_NCTEN * ps] = s1.v[1]; w[WS_NR * ps] = s1.v[2]; w[WS_NI * ps] = s1.v[3];
           w[WS_RR * ps] = s2.v[0]; w[WS_RI * ps] = s2.v[1]; w[WS_RS * ps] = s2.v[2]; w[WS_RG * ps] = s2.v[3];
           w[WS_RHO * ps] = s2.v[7]; w[WS_S15 * ps] = s3.v[0];
+          if (AERO) { w[WS_NWFAT * ps] = s1.v[5]; w[WS_NIFAT * ps] = s1.v[6]; }
           if (s2.v[0] > R1) { v_r = s2.v[4]; v_nr = s2.v[5]; }
           if (!iiwarm) {
             if (s2.v[1] > R1) { v_i = s2.v[6]; v_ni = s1.v[4]; }
@@ -1340,6 +1447,7 @@ __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
           for (int q = WS_TTEN; q <= WS_NCTEN; ++q) w[q * ps] = 0.0f;
           w[WS_RR * ps] = R1; w[WS_NR * ps] = R2; w[WS_RI * ps] = R1; w[WS_NI * ps] = R2; w[WS_RS * ps] = R1; w[WS_RG * ps] = R1;
           w[WS_RHO * ps] = rho; w[WS_S15 * ps] = s15;
+          if (AERO) { w[WS_NWFAT * ps] = 0.0f; w[WS_NIFAT * ps] = 0.0f; }
         }
         w[WS_VTR * ps] = v_r; w[WS_VTNR * ps] = v_nr; w[WS_VTI * ps] = v_i; w[WS_VTNI * ps] = v_ni;
         w[WS_VTS * ps] = v_s; w[WS_VTG * ps] = v_g;
@@ -1374,6 +1482,7 @@ __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
       h.qrt = q[WS_QRTEN * ps]; h.qst = q[WS_QSTEN * ps]; h.qgt = q[WS_QGTEN * ps]; h.nit = q[WS_NITEN * ps];
       h.nrt = q[WS_NRTEN * ps]; h.nct = q[WS_NCTEN * ps];
       h.rho = q[WS_RHO * ps]; h.s15 = q[WS_S15 * ps];
+      h.nwfat = AERO ? q[WS_NWFAT * ps] : 0.f; h.nifat = AERO ? q[WS_NIFAT * ps] : 0.f;
       h.rr = q[WS_RR * ps]; h.nr = q[WS_NR * ps]; h.ri = q[WS_RI * ps]; h.ni = q[WS_NI * ps]; h.rs = q[WS_RS * ps]; h.rg = q[WS_RG * ps];
       h.v_r = q[WS_VTR * ps]; h.v_nr = q[WS_VTNR * ps]; h.v_i = q[WS_VTI * ps]; h.v_ni = q[WS_VTNI * ps];
       h.v_s = q[WS_VTS * ps]; h.v_g = q[WS_VTG * ps];
@@ -1382,7 +1491,7 @@ __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
         const long st = (long)nz * ld;
         for (int r = 0; r < KIDMP_NRATES; ++r) rp[r * st] = 0.0f;
       }
-      finish_level(a, sp, c, h, k, nz, o, dzp[k * dzs], a.f[F_T][o], a.f[F_QV][o], a.f[F_QC][o], a.f[F_QI][o], a.f[F_QR][o],
+      finish_level<AERO>(a, sp, c, h, k, nz, o, dzp[k * dzs], a.f[F_T][o], a.f[F_QV][o], a.f[F_QC][o], a.f[F_QI][o], a.f[F_QR][o],
                    a.f[F_QS][o], a.f[F_QG][o], a.f[F_NI][o], a.f[F_NR][o], a.p[o]);
     }
     // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
@@ -1397,7 +1506,7 @@ __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
 #ifndef K2_MINB
 #define K2_MINB 20
 #endif
-template <bool RATES>
+template <bool RATES, bool AERO>
 __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
   const int slot = blockIdx.x * 32 + threadIdx.x;
   const int count = *a.work_count;
@@ -1453,6 +1562,7 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
       h.nrt = s1.v[0]; h.nct = s1.v[1]; h.nr = s1.v[2]; h.ni = s1.v[3];
       h.rr = s2.v[0]; h.ri = s2.v[1]; h.rs = s2.v[2]; h.rg = s2.v[3];
       h.rho = s2.v[7]; h.s15 = s3.v[0];
+      h.nwfat = s1.v[5]; h.nifat = s1.v[6];
       if (h.rr > R1) { v_r = s2.v[4]; v_nr = s2.v[5]; }
       if (!iiwarm) {
         if (h.ri > R1) { v_i = s2.v[6]; v_ni = s1.v[4]; }
@@ -1468,6 +1578,7 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
     } else {
       h.tt = 0.f; h.qvt = 0.f; h.qct = 0.f; h.qit = 0.f; h.qrt = 0.f; h.qst = 0.f; h.qgt = 0.f; h.nit = 0.f; h.nrt = 0.f; h.nct = 0.f;
       h.rr = R1; h.nr = R2; h.ri = R1; h.ni = R2; h.rs = R1; h.rg = R1;
+      h.nwfat = 0.f; h.nifat = 0.f;
       idle_record(t1d, pres, qv1d, h.rho, h.s15);
       if (RATES) {                                        // an idle cell: every process rate is zero
         float* rp = a.rates + o;
@@ -1483,7 +1594,7 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
         if (v_s > 1.E-3f) sp.top_s = nz;
       }
     }
-    finish_level(a, sp, c, h, k, nz, o, dzp[k * dzs], t1d, qv1d, qc1d, qi1d, qr1d, qs1d, qg1d, ni1d, nr1d, pres);
+    finish_level<AERO>(a, sp, c, h, k, nz, o, dzp[k * dzs], t1d, qv1d, qc1d, qi1d, qr1d, qs1d, qg1d, ni1d, nr1d, pres);
   }
   // ppt is overwritten with this step's amounts: rain, ice, snow, graupel (I:55-58, I:162-177)
   a.ppt[col] = c.ppt_r; a.ppt[ld + col] = c.ppt_i; a.ppt[2 * ld + col] = c.ppt_s; a.ppt[3 * ld + col] = c.ppt_g;

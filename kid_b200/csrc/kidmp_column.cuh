@@ -327,7 +327,10 @@ struct SedCarry {             // carried down the column
 };
 struct HandOff {              // what S1..S13 leave for a level (SC_* order)
   float tt, qvt, qct, qit, qrt, qst, qgt, nit, nrt, nct, rr, nr, ri, ni, rs, rg, v_r, v_nr, v_i, v_ni, v_s, v_g, rho, s15;
+  float nwfat, nifat;           // aerosol-aware runs only (M:2398-2408, M:2863, M:2952)
 };
+// AERO: is_aerosol_aware = .true.: the droplet number and the two aerosol numbers are state (a.nc, a.nwfa, a.nifa, M:3626-3647)
+template <bool AERO = false>
 __device__ __forceinline__ void finish_level(const StepArgs& a, const SedParams& p, SedCarry& c, const HandOff& h, int k, int nz,
                                              long g, float dzk, float t1d, float qv1d, float qc1d, float qi1d, float qr1d,
                                              float qs1d, float qg1d, float ni1d, float nr1d, float pres) {
@@ -370,7 +373,7 @@ __device__ __forceinline__ void finish_level(const StepArgs& a, const SedParams&
   }
 
   // ---- S15 + S16 for this level ----------------------------------------------------------------
-  float nc1d = p.Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));   // U1
+  float nc1d = AERO ? a.nc[g] : p.Nt_c / (0.622f * pres / (KP_R * t1d * (qv1d + 0.622f)));   // U1
   if (!(qc1d > KP_R1)) { qc1d = 0.f; nc1d = 0.f; }
   if (!(qi1d > KP_R1)) { qi1d = 0.f; ni1d = 0.f; }
   if (!(qr1d > KP_R1)) { qr1d = 0.f; nr1d = 0.f; }
@@ -398,7 +401,23 @@ __device__ __forceinline__ void finish_level(const StepArgs& a, const SedParams&
   t1d = t1d + tt * p.DT;
   qv1d = fmaxf(1.E-10f, qv1d + qvt * p.DT);
   qc1d = qc1d + qct * p.DT;
-  if (qc1d <= KP_R1) qc1d = 0.0f;              // nc1d is not returned to the host (I:143-152, I:198-245)
+  if (AERO) {                                  // M:3626-3647
+    nc1d = fmaxf(2.f / rho, nc1d + nct * p.DT);
+    a.nwfa[g] = fmaxf(11.1E6f / rho, fminf(9999.E6f / rho, (a.nwfa[g] + h.nwfat * p.DT)));
+    a.nifa[g] = fmaxf(0.5E6f * 0.01f, fminf(9999.E6f / rho, (a.nifa[g] + h.nifat * p.DT)));
+    if (qc1d <= KP_R1) {
+      nc1d = 0.0f;
+    } else {
+      const int nu = min(15, nint_f(1000.E6f / (nc1d * rho)) + 2);
+      double lc = (double)pow_f(ck.am_r * ck.ccg[1][nu - 1] * ck.ocg1[nu - 1] * nc1d / qc1d, ck.obmr);
+      const float xD = (float)((double)(3.f + (float)nu + 1.f) / lc);
+      if (xD < KP_D0C) lc = (double)(ck.cce[1][nu - 1] / KP_D0C);
+      else if (xD > KP_D0R * 2.f) lc = (double)(ck.cce[1][nu - 1] / (KP_D0R * 2.f));
+      nc1d = (float)fmin((double)(ck.ccg[0][nu - 1] * ck.ocg2[nu - 1] * qc1d / ck.am_r) * cube_d(lc), (double)KP_NT_C_MAX / (double)rho);
+    }
+    a.nc[g] = nc1d;
+  }
+  if (qc1d <= KP_R1) qc1d = 0.0f;              // (not aerosol aware: nc1d is not returned to the host, I:143-152, I:198-245)
   qi1d = qi1d + qit * p.DT;
   ni1d = fmaxf(KP_R2 / rho, ni1d + nit * p.DT);
   if (qi1d <= KP_R1) {
@@ -474,6 +493,12 @@ __global__ void k_diag_reduce(const double* __restrict__ partial, int nblocks, d
     __syncthreads();
   }
   if (threadIdx.x == 0) diag[q] += s[0];
+}
+
+// mp_gt_driver after the column call of an aerosol-aware run, M:1001: nwfa1d(kts) = nwfa1d(kts) + nwfa2d(i,j)*dt_in
+__global__ void k_nwfa_surface(float* __restrict__ nwfa, const float* __restrict__ nwfa2d, long ncol, float dt) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncol) nwfa[c] = nwfa[c] + nwfa2d[c] * dt;
 }
 
 // The columns that the step changed, written straight into the caller's PINNED host arrays over PCIe (zero copy): a clear-sky

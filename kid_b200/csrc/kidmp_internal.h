@@ -91,6 +91,8 @@ struct KConst {
   // M:1888, (cgg(3)*ogg2*ogg1)**obmg M:1651, (ccg(3,nu_c)*ocg2(nu_c))**obmr M:1701
   float n0r_fac, n0g_fac, lamg_fac, dcg_fac[15];
   double Dr1, Ds1, lnDr, lnDs;                      // Dr(1), Ds(1), DLOG(Dr(nbr)/Dr(1)), DLOG(Ds(nbs)/Ds(1))
+  double t_Nc1;                                     // t_Nc(1), M:668
+  const double* tnc_wev;                            // [NBINS][NTB_C][NBINS] (idx_d fastest), table_dropEvap M:4400-4439; NULL until an aerosol-aware step asks for it
   // device tables
   const double* racg;   // [N_RACG][G_N]
   const double* racs;   // [N_RACS][S_N]
@@ -164,6 +166,9 @@ struct StepArgs {
   float* rates;                // optional [36][nz][ld]
   double* coldiag;             // [2][ncol] liquid / ice water path of each cloudy column
   double* diag_partial;        // [DIAG_BLOCKS][KIDMP_NDIAG] block sums of k_diag_columns
+  // aerosol-aware runs (is_aerosol_aware = .true., M:28): prognostic droplet number and aerosol numbers, vertical velocity
+  float* nc; float* nwfa; float* nifa;   // [nz][ld] INOUT
+  const float* w;                        // [nz][ld] IN
   int nsm;                     // SMs of the device
   int no_simple;               // 1: every cloudy column goes through the counts of k_carries ("simple" option off: for A/B runs)
 };

@@ -7,8 +7,9 @@
 // A WRF array a(i,k,j) sits at a[i + ni*(k + nk*j)]; the step's layout is [k][col] with col = i + ni*j, so a row of ni
 // floats moves as a whole and both sides of every copy are coalesced.
 //
-// Not restated (dead in the KiD build of the reference): the is_aerosol_aware branches (M:950-956, M:1005-1012; the
-// switch is .false., M:28), WRF_CHEM arguments, refl_10cm / calc_refl10cm (never called), and the negative-qv repair of
+// The is_aerosol_aware branches (M:950-956, M:999-1007, M:4875) are served by kidmp_mp_gt_driver_aero: nc, nwfa, nifa and w
+// travel through k_ikj_planes, the surface emission is k_nwfa_surface, the cloud radius reads the prognostic droplet number.
+// Not restated (dead in the reference): WRF_CHEM arguments, refl_10cm / calc_refl10cm (never called), and the negative-qv repair of
 // M:1096-1107, which cannot trigger: mp_thompson returns qv1d = MAX(1.E-10, ...) (M:3629).
 #pragma once
 #include "kidmp_internal.h"
@@ -26,7 +27,16 @@ struct WrfArgs {
   const float* ppt;             // [4][ni*nj] rain, ice, snow, graupel of this step
   float *rainnc, *rainncv, *sr, *snownc, *snowncv, *graupelnc, *graupelncv;   // (i,j); the last four may be NULL
   float *re_cloud, *re_ice, *re_snow;   // (i,k,j), all three or none (has_reqc, has_reqi, has_reqs, M:1110)
+  const float* nc_plane;                // [nk][ni*nj] prognostic droplet number of an aerosol-aware run, else NULL (nc = Nt_c, M:4875)
 };
+
+// one (i,k,j) array <-> one [k][col] plane of the step (col = i + ni*j); x: i, y: k, z: j
+__global__ void k_ikj_planes(float* a3, float* plane, int ni, int nk, int nj, int to_planes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y, j = blockIdx.z;
+  if (i >= ni) return;
+  const long x = (long)i + (long)ni * (k + (long)nk * j), y = (long)k * ni * nj + (long)j * ni + i;
+  if (to_planes) plane[y] = a3[x]; else a3[x] = plane[y];
+}
 
 // one thread per cell; x: i, y: k, z: j
 __global__ void k_wrf_gather(WrfArgs a) {
@@ -61,7 +71,7 @@ __global__ void k_wrf_scatter(WrfArgs a, float Nt_c) {
     float re_qc = 2.49E-6f, re_qi = 4.99E-6f, re_qs = 9.99E-6f;          // M:1112-1114
     const float rho = 0.622f * p1d / (KP_R * t1d * (qv1d + 0.622f));
     const float rc = fmaxf(KP_R1, qc1d * rho);
-    const float nc = Nt_c;                                  // .NOT. is_aerosol_aware, M:4875
+    const float nc = a.nc_plane ? fmaxf(KP_R2, a.nc_plane[src] * rho) : Nt_c;       // M:4874-4875
     const float ri = fmaxf(KP_R1, qi1d * rho);
     const float ni = fmaxf(KP_R2, ni1d * rho);
     const float rs = fmaxf(KP_R1, qs1d * rho);

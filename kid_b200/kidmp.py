@@ -50,6 +50,7 @@ SYMBOLS = {
     "kidmp_download": (C.c_int, [C.c_void_p, C.c_int, _fpp, _fp]),
     "kidmp_step_device": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_float, C.POINTER(C.c_void_p), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kidmp_step_device_aero": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_float, C.POINTER(C.c_void_p)] + [C.c_void_p] * 9),
     "kidmp_set_rates_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kidmp_rate_names": (C.c_char_p, []),
     "kidmp_enable_rates": (C.c_int, [C.c_void_p, C.c_int]),
@@ -86,7 +87,13 @@ class WrfFields(C.Structure):
         "snownc", "snowncv", "graupelnc", "graupelncv", "re_cloud", "re_ice", "re_snow")]
 
 
+class WrfAerosols(C.Structure):
+    """kidmp_wrf_aerosols of include/kidmp.h."""
+    _fields_ = [(n, _fp) for n in ("nc", "nwfa", "nifa", "w", "nwfa2d")]
+
+
 SYMBOLS["kidmp_mp_gt_driver"] = (C.c_int, [C.c_void_p, C.POINTER(WrfFields), C.c_float])
+SYMBOLS["kidmp_mp_gt_driver_aero"] = (C.c_int, [C.c_void_p, C.POINTER(WrfFields), C.POINTER(WrfAerosols), C.c_float])
 SYMBOLS["kidmp_kid_interface"] = (C.c_int, [C.c_void_p, C.POINTER(KidColumns), C.c_float, C.c_float, C.c_float])
 HYD_PLANES = ("qc", "qr", "nr", "qi", "ni", "qs", "qg")
 
@@ -112,7 +119,12 @@ def load(build_if_missing=True):
                 _build.build(force=True)            # a compile error is an error: never fall back to a stale binary
         L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
-            fn = getattr(L, name)
+            try:
+                fn = getattr(L, name)
+            except AttributeError:
+                if os.environ.get("KIDMP_LIB"):         # an earlier build in an A/B run: it simply lacks the newer entry points
+                    continue
+                raise
             fn.restype = res
             fn.argtypes = args
         _lib = L
@@ -251,6 +263,14 @@ class Thompson:
                                            C.c_void_p(int(dz_ptr)), C.c_void_p(int(ppt_ptr)),
                                            C.c_void_p(int(stream)) if stream else None))
 
+    def step_device_aero(self, ncol, nz, dt, field_ptrs, nc_ptr, nwfa_ptr, nifa_ptr, p_ptr, w_ptr, dz_ptr, ppt_ptr, nwfa2d_ptr=None,
+                         stream=None):
+        """kidmp_step_device_aero: the aerosol-aware step (is_aerosol_aware = .true.); device pointers, COL_FASTEST."""
+        fp = (C.c_void_p * NFIELDS)(*[C.c_void_p(int(x)) for x in field_ptrs])
+        v = lambda x: C.c_void_p(int(x)) if x else None
+        self._ck(self._L.kidmp_step_device_aero(self.h, int(ncol), int(nz), float(dt), fp, v(nc_ptr), v(nwfa_ptr), v(nifa_ptr),
+                                                v(p_ptr), v(w_ptr), v(dz_ptr), v(nwfa2d_ptr), v(ppt_ptr), v(stream)))
+
     def device_state(self):
         f = (C.c_void_p * NFIELDS)()
         p, dz, ppt = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -261,10 +281,12 @@ class Thompson:
         """kidmp_set_option: tuning knobs that do not change results ("chunk": columns per launch, "timing": 0 / 1)."""
         self._ck(self._L.kidmp_set_option(self.h, name.encode(), int(value)))
 
-    def mp_gt_driver(self, dt, f3, pii, p, dz, acc, radii=True):
+    def mp_gt_driver(self, dt, f3, pii, p, dz, acc, radii=True, aerosols=None):
         """mp_gt_driver (M:806-1143) through kidmp_mp_gt_driver.  f3: dict qv qc qr qi qs qg ni nr th of (nj, nk, ni)
         float32 arrays (C order = WRF's (i,k,j) Fortran order), updated in place; pii, p, dz the same shape; acc: dict
         rainnc rainncv sr [snownc snowncv graupelnc graupelncv] of (nj, ni) arrays, updated in place.
+        aerosols: dict nc nwfa nifa w of (nj, nk, ni) arrays [+ nwfa2d (nj, ni)]: is_aerosol_aware = .true. through
+        kidmp_mp_gt_driver_aero (nc, nwfa, nifa updated in place).
         Returns dict re_cloud re_ice re_snow (empty when radii is False)."""
         nj, nk, ni = f3["qv"].shape
         w = WrfFields()
@@ -289,6 +311,14 @@ class Thompson:
         re = {k: np.zeros((nj, nk, ni), np.float32) for k in ("re_cloud", "re_ice", "re_snow")} if radii else {}
         for name, a in re.items():
             setattr(w, name, ptr(a, (nj, nk, ni)))
+        if aerosols is not None:
+            ae = WrfAerosols()
+            for name in ("nc", "nwfa", "nifa", "w"):
+                setattr(ae, name, ptr(aerosols[name], (nj, nk, ni)))
+            if aerosols.get("nwfa2d") is not None:
+                ae.nwfa2d = ptr(aerosols["nwfa2d"], (nj, ni))
+            self._ck(self._L.kidmp_mp_gt_driver_aero(self.h, C.byref(w), C.byref(ae), float(dt)))
+            return re
         self._ck(self._L.kidmp_mp_gt_driver(self.h, C.byref(w), float(dt)))
         return re
 

@@ -196,3 +196,21 @@ def stats(state):
     out["cells_any"] = float(anyhyd.float().mean())
     out["columns_any"] = float(anyhyd.any(0).float().mean())
     return out
+
+
+def make_aerosols(state, p, seed=20261018):
+    """Aerosol-aware inputs for the columns of `state` (dict of (nz, ncol) float32 arrays, torch or numpy) and pressure `p`:
+    cloud droplet number nc [kg^-1] where there is cloud water, numbers of water-friendly and ice-friendly aerosols nwfa, nifa
+    [kg^-1] decaying with height, vertical velocity w [m s^-1].  Seeded numpy; returns numpy float32 arrays (nc, nwfa, nifa, w)."""
+    import numpy as np
+    f = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)
+    t, qv, qc, pp = f(state["t"]), f(state["qv"]), f(state["qc"]), f(p)
+    nz, ncol = t.shape
+    rng = np.random.default_rng(seed)
+    rho = (np.float32(0.622) * pp / (np.float32(287.04) * t * (qv + np.float32(0.622)))).astype(np.float32)
+    height = (1.0 - pp / pp.max()).astype(np.float32)                                   # 0 at the surface .. ~0.8 aloft
+    nwfa = (10.0 ** rng.uniform(7.3, 9.3, (1, ncol)) * np.exp(-3.0 * height) / rho).astype(np.float32)
+    nifa = (10.0 ** rng.uniform(3.5, 6.5, (1, ncol)) * np.exp(-2.0 * height) / rho).astype(np.float32)
+    nc = np.where(qc > 1e-12, 10.0 ** rng.uniform(7.0, 8.9, (nz, ncol)) / rho, 0.0).astype(np.float32)
+    w = (rng.normal(0.3, 1.5, (nz, ncol)) * (rng.random((1, ncol)) < 0.8)).astype(np.float32)
+    return nc, nwfa, nifa, w

@@ -45,6 +45,12 @@ def lib():
         L.kor_get_table.argtypes = [C.c_void_p, C.c_char_p, _dp, C.c_long]
         L.kor_mp_thompson.restype = C.c_int
         L.kor_mp_thompson.argtypes = [C.c_void_p, C.c_int, C.c_float] + [_fp] * 10 + [_fp, _fp, _fp, _dp]
+        L.kor_step_aero.restype = C.c_int
+        L.kor_step_aero.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_float] + [_fp] * 17 + [C.c_int]
+        for name, args in (("kor_eff_aero", [C.c_float] * 5 + [C.c_char]), ("kor_ice_demott", [C.c_float] * 3),
+                           ("kor_ice_koop", [C.c_float] * 5), ("kor_activ_ncloud", [C.c_float] * 3)):
+            getattr(L, name).restype = C.c_float
+            getattr(L, name).argtypes = args
         L.kor_step.restype = C.c_int
         L.kor_step.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_int] + [_fp] * 9 + [_fp, _fp, _fp, C.c_int]
         L.kor_kid_interface.restype = C.c_int
@@ -61,6 +67,8 @@ def lib():
         L.kor_gammp.argtypes = [C.c_float, C.c_float]
         L.kor_calc_effect_rad.restype = C.c_int
         L.kor_calc_effect_rad.argtypes = [C.c_void_p, C.c_int] + [_fp] * 11
+        L.kor_calc_effect_rad_aero.restype = C.c_int
+        L.kor_calc_effect_rad_aero.argtypes = [C.c_void_p, C.c_int] + [_fp] * 11
         L.kor_mp_gt_driver.restype = C.c_int
         L.kor_mp_gt_driver.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float] + [_fp] * 22
         L.kor_decade_index.restype = C.c_int
@@ -128,13 +136,20 @@ class Oracle:
             out = out.reshape(TABLE_SHAPES[name], order="F")
         return out
 
-    def effect_rad(self, t, p, qv, qc, qi, ni, qs):
-        """calc_effectRad (M:4834-4935) for one column preset as at M:1112-1114; returns (re_qc, re_qi, re_qs)."""
+    def effect_rad(self, t, p, qv, qc, qi, ni, qs, nc=None):
+        """calc_effectRad (M:4834-4935) for one column preset as at M:1112-1114; returns (re_qc, re_qi, re_qs).
+        nc given: is_aerosol_aware = .true., the droplet number is read (M:4874)."""
         nz = len(t)
         arrs = [np.ascontiguousarray(v, dtype=np.float32) for v in (t, p, qv, qc, qi, ni, qs)]
         t, p, qv, qc, qi, ni, qs = arrs
         rc, ri, rs = (np.full(nz, v, np.float32) for v in (2.49e-6, 4.99e-6, 9.99e-6))
         P = lambda a: a.ctypes.data_as(_fp)
+        if nc is not None:
+            ncc = np.ascontiguousarray(nc, dtype=np.float32)
+            r = lib().kor_calc_effect_rad_aero(self.h, nz, P(t), P(p), P(qv), P(qc), P(ncc), P(qi), P(ni), P(qs), P(rc), P(ri), P(rs))
+            if r:
+                raise RuntimeError("kor_calc_effect_rad_aero failed")
+            return rc, ri, rs
         r = lib().kor_calc_effect_rad(self.h, nz, P(t), P(p), P(qv), P(qc), None, P(qi), P(ni), P(qs), P(rc), P(ri), P(rs))
         if r:
             raise RuntimeError("kor_calc_effect_rad failed")
@@ -200,6 +215,42 @@ class Oracle:
         if rc:
             raise RuntimeError("kor_step rc=%d" % rc)
         return ppt
+
+
+    def step_aero(self, dt, state, nc, nwfa, nifa, p, w, dz, nwfa2d=None, nthreads=None):
+        """mp_thompson with is_aerosol_aware = .true. (M:28) over the columns of (nz, ncol) float32 arrays, in place on
+        `state` (dict by FIELDS), nc, nwfa, nifa; w: vertical velocity; nwfa2d (ncol) or None: the surface emission that
+        mp_gt_driver adds to the lowest level after the step (M:1001).  Returns ppt[4, ncol]."""
+        t = state["t"]
+        nz, ncol = t.shape
+        for a in list(state.values()) + [nc, nwfa, nifa, p, w]:
+            assert a.dtype == np.float32 and a.flags.c_contiguous and a.shape == t.shape
+        dz = np.ascontiguousarray(dz, np.float32)
+        ppt = np.zeros((4, ncol), np.float32)
+        n2 = np.ascontiguousarray(nwfa2d, np.float32) if nwfa2d is not None else None
+        rc = lib().kor_step_aero(self.h, ncol, nz, float(dt), *[state[k].ctypes.data_as(_fp) for k in FIELDS],
+                                 nc.ctypes.data_as(_fp), nwfa.ctypes.data_as(_fp), nifa.ctypes.data_as(_fp), p.ctypes.data_as(_fp),
+                                 w.ctypes.data_as(_fp), dz.ctypes.data_as(_fp), n2.ctypes.data_as(_fp) if n2 is not None else None,
+                                 ppt.ctypes.data_as(_fp), int(nthreads or self.nthreads))
+        if rc:
+            raise RuntimeError("kor_step_aero rc=%d" % rc)
+        return ppt
+
+
+def eff_aero(D, Da, visc, rhoa, temp, species):
+    return float(lib().kor_eff_aero(D, Da, visc, rhoa, temp, species.encode()))
+
+
+def ice_demott(tempc, rho, nifa):
+    return float(lib().kor_ice_demott(tempc, rho, nifa))
+
+
+def ice_koop(temp, qv, qvs, naero, dt):
+    return float(lib().kor_ice_koop(temp, qv, qvs, naero, dt))
+
+
+def activ_ncloud(Tt, Ww, NCCN):
+    return float(lib().kor_activ_ncloud(Tt, Ww, NCCN))
 
 
 HYD_PLANES = ("qc", "qr", "nr", "qi", "ni", "qs", "qg")

@@ -218,6 +218,7 @@ struct kor_handle {
       tms_sacr2, tnr_racs1, tnr_racs2, tnr_sacr1, tnr_sacr2;
   std::vector<r8> tpi_qcfz, tni_qcfz, tpi_qrfz, tpg_qrfz, tni_qrfz, tnr_qrfz;
   std::vector<r8> tps_iaus, tni_iaus, tpi_ide, t_Efrw, t_Efsw;
+  std::vector<r8> tpc_wev, tnc_wev;          // (nbc, ntb_c, nbc), table_dropEvap M:4400-4439 (read under is_aerosol_aware only)
   double init_seconds;
   int nthreads;
   std::map<std::string, std::vector<r8>*> tabs;
@@ -531,6 +532,27 @@ void freezeH2O(H& h) {
   }
 }
 
+// M:4400-4439: mass and number of the cloud droplets smaller than D-star (they evaporate in one step)
+#define WEV(t, i, j, k) t[((i) - 1) + (size_t)nbc * (((j) - 1) + (size_t)ntb_c * ((k) - 1))]
+void table_dropEvap(H& h) {
+  r8 N_c[nbc + 1], massc[nbc + 1];
+  for (int n = 1; n <= nbc; ++n) massc[n] = (r8)am_r * pow(h.Dc[n], (r8)bm_r);
+  for (int k = 1; k <= nbc; ++k) {
+    const int nu_c = std::min(15, nint_d((r8)1000.E6f / h.t_Nc[k]) + 2);
+    for (int j = 1; j <= ntb_c; ++j) {
+      const r8 lamc = pow(h.t_Nc[k] * (r8)am_r * (r8)h.ccg[2][nu_c] * (r8)h.ocg1[nu_c] / (r8)h.r_c[j], (r8)h.obmr);
+      const r8 N0_c = h.t_Nc[k] * (r8)h.ocg1[nu_c] * pow(lamc, (r8)h.cce[1][nu_c]);
+      for (int i = 1; i <= nbc; ++i) {
+        N_c[i] = N0_c * powi_d(h.Dc[i], nu_c) * exp(-lamc * h.Dc[i]) * h.dtc[i];
+        r8 summ = 0., summ2 = 0.;
+        for (int n = 1; n <= i; ++n) { summ = summ + massc[n] * N_c[n]; summ2 = summ2 + N_c[n]; }
+        WEV(h.tpc_wev, i, j, k) = summ;
+        WEV(h.tnc_wev, i, j, k) = summ2;
+      }
+    }
+  }
+}
+
 // M:4190-4233
 void qi_aut_qs(H& h) {
   for (int j = 1; j <= ntb_i1; ++j)
@@ -724,7 +746,9 @@ void thompson_init(H& h, const char* cache_path) {
 
   table_Efrw(h);
   table_Efsw(h);
-  // table_dropEvap (M:4400-4439) is only read under is_aerosol_aware (M:2804,2850): not built.
+  h.tpc_wev.assign((size_t)nbc * ntb_c * nbc, 0.0); h.tnc_wev.assign((size_t)nbc * ntb_c * nbc, 0.0);
+  h.tabs["tpc_wev"] = &h.tpc_wev; h.tabs["tnc_wev"] = &h.tnc_wev;
+  table_dropEvap(h);                                   // M:771 (only read under is_aerosol_aware, M:2804, M:2850)
   if (!h.iiwarm) {
     // binary cache of the two 4-D families (stand-in for run_data/*.data, M:3717-3728): keyed by
     // a hash of everything the builders read.

@@ -40,6 +40,17 @@ int kor_step(const kor_handle*, long ncol, int nz, float dt, int layout,
              float* ni, float* nr, float* t, const float* p, const float* dz,
              float* ppt, int nthreads);
 
+// mp_thompson with is_aerosol_aware = .true. (M:28) and mp_gt_driver's handling of the aerosol arrays around it (M:950-956,
+// M:999-1007), COL_FASTEST arrays a[k*ncol+col]: nc, nwfa, nifa INOUT, w IN, nwfa2d [ncol] or NULL.
+int kor_step_aero(const kor_handle*, long ncol, int nz, float dt, float* qv, float* qc, float* qi, float* qr, float* qs,
+                  float* qg, float* ni, float* nr, float* t, float* nc, float* nwfa, float* nifa, const float* p,
+                  const float* w, const float* dz, const float* nwfa2d, float* ppt, int nthreads);
+// M:4354-4390 Eff_aero, M:4720-4756 iceDeMott, M:4764-4789 iceKoop, M:4451-4526 activ_ncloud
+float kor_eff_aero(float D, float Da, float visc, float rhoa, float temp, char species);
+float kor_ice_demott(float tempc, float rho, float nifa);
+float kor_ice_koop(float temp, float qv, float qvs, float naero, float dt);
+float kor_activ_ncloud(float Tt, float Ww, float NCCN);
+
 // I:28-246 mphys_thompson09_interfacen (gather, mp_thompson per column, tendencies back) without
 // save_dg.  KiD (k,i) arrays a[i*nz+k]; hyd planes: qc, qr, nr, qi, ni, qs, qg; ppt [4][nx].
 int kor_kid_interface(const kor_handle*, long nx, int nz, float dt, float p0, float r_on_cp,
@@ -53,6 +64,10 @@ int kor_kid_interface(const kor_handle*, long nx, int nz, float dt, float p0, fl
 int kor_calc_effect_rad(const kor_handle*, int nz, const float* t1d, const float* p1d, const float* qv1d,
                         const float* qc1d, const float* nc1d, const float* qi1d, const float* ni1d, const float* qs1d,
                         float* re_qc1d, float* re_qi1d, float* re_qs1d);
+
+int kor_calc_effect_rad_aero(const kor_handle*, int nz, const float* t1d, const float* p1d, const float* qv1d,
+                             const float* qc1d, const float* nc1d, const float* qi1d, const float* ni1d, const float* qs1d,
+                             float* re_qc1d, float* re_qi1d, float* re_qs1d);   // is_aerosol_aware = .true.: nc1d is read (M:4874)
 
 // M:806-1143 mp_gt_driver over ni x nj columns; 3-D arrays a[i + ni*(k + nk*j)], 2-D a[i + ni*j]; the snow / graupel
 // accumulators and the three radii may be NULL.

@@ -16,7 +16,7 @@ FLIP_FRACTION = 2e-4
 # threshold for masses, and one particle per 1000 m^3 for numbers); differences there are
 # compared absolutely
 FLOOR = {"qv": 1e-10, "qc": 1e-12, "qi": 1e-12, "qr": 1e-12, "qs": 1e-12, "qg": 1e-12, "ni": 1e-3, "nr": 1e-3,
-         "t": 1.0}
+         "t": 1.0, "nc": 1e-3, "nwfa": 1e-3, "nifa": 1e-3}
 
 
 def compare_field(name, got, ref):

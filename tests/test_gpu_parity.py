@@ -785,3 +785,93 @@ def test_schedule_options_are_bit_identical(dt, dz):
         assert r[3]["busy_cells"] == ref[3]["busy_cells"] and r[3]["cloudy_columns"] == ref[3]["cloudy_columns"], name
     if dt > 30.0:
         assert ref[3]["substep_columns"] > 0                                    # the sub-stepped path ran
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,dz,ncol", [(10.0, 250.0, 6000), (60.0, 100.0, 3000), (1.0, 250.0, 2000)])
+def test_aerosol_aware_step(dt, dz, ncol, gpu_mixed, oracle_mixed):
+    """The second half of SURVEY section 8f-4: is_aerosol_aware = .true. (M:28).  kidmp_step_device_aero against the oracle's
+    restatement of the same switch on the same columns: prognostic nc / nwfa / nifa, aerosol scavenging by rain, snow and graupel
+    (Eff_aero), dust nucleation (iceDeMott), homogeneous freezing of aerosols (iceKoop), droplet activation (activ_ncloud) and the
+    evaporation of the smallest droplets (table_dropEvap), the surface emission of mp_gt_driver (M:1001).  Three steps, so the
+    prognostic numbers of one step feed the next.  Tolerance as everywhere: 1e-5 relative, a few flipped cells allowed."""
+    import torch
+    from kid_b200 import synth
+    st, p, dzv = synth.make_domain(ncol, nz=60, nx=1024, dz=dz, col0=123456, cloudy_fraction=0.7, coherent=False)
+    nc, nwfa, nifa, w = synth.make_aerosols(st, p)
+    nwfa2d = (np.random.default_rng(5).uniform(0.0, 1.0e5, ncol)).astype(np.float32)
+    ref = {k: v.numpy().copy() for k, v in st.items()}
+    rnc, rnwfa, rnifa = nc.copy(), nwfa.copy(), nifa.copy()
+    pn, dzn = p.numpy().copy(), dzv.numpy().copy()
+    dev = {k: v.cuda() for k, v in st.items()}
+    dnc, dnwfa, dnifa, dw = (torch.from_numpy(x).cuda() for x in (nc, nwfa, nifa, w))
+    dp, ddz, dn2 = p.cuda(), dzv.cuda(), torch.from_numpy(nwfa2d).cuda()
+    dppt = torch.zeros((4, ncol), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for step in range(3):
+        ppt_ref = oracle_mixed.step_aero(dt, ref, rnc, rnwfa, rnifa, pn, w, dzn, nwfa2d=nwfa2d)
+        gpu_mixed.step_device_aero(ncol, 60, dt, [dev[k].data_ptr() for k in FIELDS], dnc.data_ptr(), dnwfa.data_ptr(), dnifa.data_ptr(),
+                                   dp.data_ptr(), dw.data_ptr(), ddz.data_ptr(), dppt.data_ptr(), nwfa2d_ptr=dn2.data_ptr())
+        gpu_mixed.sync()
+        got = {k: dev[k].cpu().numpy() for k in FIELDS}
+        got.update(nc=dnc.cpu().numpy(), nwfa=dnwfa.cpu().numpy(), nifa=dnifa.cpu().numpy())
+        want = dict(ref, nc=rnc, nwfa=rnwfa, nifa=rnifa)
+        assert_parity(got, want, fields=FIELDS + ("nc", "nwfa", "nifa"), what="aerosol-aware step %d dt=%g" % (step, dt), flip_fraction=1e-3)
+        np.testing.assert_allclose(dppt.cpu().numpy(), ppt_ref, rtol=1e-4, atol=1e-9)
+        # the next step starts from the oracle's state on both sides: flipped cells do not accumulate
+        for k in FIELDS:
+            dev[k].copy_(torch.from_numpy(ref[k]))
+        dnc.copy_(torch.from_numpy(rnc)); dnwfa.copy_(torch.from_numpy(rnwfa)); dnifa.copy_(torch.from_numpy(rnifa))
+    # the switch does something: the droplet number is no longer Nt_c / rho where there is cloud
+    cloud = ref["qc"] > 1e-9
+    rho = 0.622 * pn / (287.04 * ref["t"] * (ref["qv"] + 0.622))
+    assert cloud.any() and np.abs(rnc[cloud] * rho[cloud] / 100.0e6 - 1.0).max() > 0.05
+    # and the default path of the same handle is untouched by it
+    a, pa, b, pb = _both(gpu_mixed, oracle_mixed, 10.0, *_domain(512, cloudy_fraction=1.0, coherent=False))
+    assert_parity(a, b, what="default step after aerosol-aware steps", flip_fraction=1e-3)
+
+
+@pytest.mark.gpu
+def test_wrf_driver_entry_aerosol_aware(gpu_mixed, oracle_mixed):
+    """kidmp_mp_gt_driver_aero: mp_gt_driver with is_aerosol_aware = .true. (M:807-832, M:950-956, M:999-1007, M:4874).  The
+    reference side is put together from the oracle's pieces exactly as mp_gt_driver does: t = th*pii, mp_thompson per column
+    with the aerosol arrays, surface emission into the lowest level, th = t/pii, calc_effectRad with the prognostic nc."""
+    ni, nk, nj = 40, 60, 6
+    f3, pii, p3, dz3, acc = _wrf_case(ni, nk, nj)
+    dz_same = np.ascontiguousarray(np.broadcast_to(dz3[0, :, 0].reshape(1, nk, 1), (nj, nk, ni))).astype(np.float32)
+    planes = lambda a: np.ascontiguousarray(a.transpose(1, 0, 2).reshape(nk, nj * ni))
+    cube = lambda a: np.ascontiguousarray(a.reshape(nk, nj, ni).transpose(1, 0, 2))
+    st = {k: planes(f3[k]) for k in f3 if k != "th"}
+    st["t"] = planes(f3["th"] * pii)
+    pcol = planes(p3)
+    from kid_b200 import synth
+    nc, nwfa, nifa, w = synth.make_aerosols(st, pcol, seed=99)
+    nwfa2d = np.random.default_rng(7).uniform(0.0, 2.0e5, (nj, ni)).astype(np.float32)
+    ae = {"nc": cube(nc), "nwfa": cube(nwfa), "nifa": cube(nifa), "w": cube(w), "nwfa2d": nwfa2d.copy()}
+    a3 = {k: v.copy() for k, v in f3.items()}
+    aa = {k: v.copy() for k, v in acc.items()}
+    ra = gpu_mixed.mp_gt_driver(20.0, a3, pii, p3, dz_same, aa, aerosols=ae)
+    # the oracle, piece by piece
+    ppt = oracle_mixed.step_aero(20.0, st, nc, nwfa, nifa, pcol, w, np.ascontiguousarray(dz3[0, :, 0]), nwfa2d=nwfa2d.reshape(-1))
+    want = {k: st[k] for k in ("qv", "qc", "qi", "qr", "qs", "qg", "ni", "nr")}
+    want["th"] = planes(cube(st["t"]) / pii)
+    want.update(nc=nc, nwfa=nwfa, nifa=nifa)
+    got = {k: planes(a3[k]) for k in a3}
+    got.update(nc=planes(ae["nc"]), nwfa=planes(ae["nwfa"]), nifa=planes(ae["nifa"]))
+    assert_parity(got, want, fields=("qv", "qc", "qi", "qr", "qs", "qg", "ni", "nr", "th", "nc", "nwfa", "nifa"),
+                  what="mp_gt_driver_aero", flip_fraction=1e-3)
+    tot = ppt.sum(0).reshape(nj, ni)
+    np.testing.assert_allclose(aa["rainncv"], tot, rtol=1e-4, atol=1e-9)
+    # the cloud radius follows the prognostic droplet number: equal to the oracle's calc_effectRad fed with nc, and
+    # different from what the fixed Nt_c gives
+    rc_want = np.zeros((nk, nj * ni), np.float32)
+    rc_fixed = np.zeros((nk, nj * ni), np.float32)
+    for c in range(0, nj * ni, 7):
+        args = (st["t"][:, c], pcol[:, c], st["qv"][:, c], st["qc"][:, c], st["qi"][:, c], st["ni"][:, c], st["qs"][:, c])
+        rc_want[:, c] = np.clip(oracle_mixed.effect_rad(*args, nc=nc[:, c])[0], np.float32(2.49e-6), np.float32(50e-6))
+        rc_fixed[:, c] = np.clip(oracle_mixed.effect_rad(*args)[0], np.float32(2.49e-6), np.float32(50e-6))
+    sel = slice(0, nj * ni, 7)
+    same_state = (got["qc"][:, sel] == want["qc"][:, sel]) & (got["nc"][:, sel] == want["nc"][:, sel]) & (got["th"][:, sel] == want["th"][:, sel]) \
+        & (got["qv"][:, sel] == want["qv"][:, sel])
+    np.testing.assert_allclose(planes(ra["re_cloud"])[:, sel][same_state], rc_want[:, sel][same_state], rtol=2e-5)
+    assert (np.abs(rc_want[:, sel] - rc_fixed[:, sel]) > 1e-7).any()
