@@ -50,6 +50,10 @@ module mphys_thompson09n
      type(c_ptr) :: rainnc, rainncv, sr, snownc, snowncv, graupelnc, graupelncv
      type(c_ptr) :: re_cloud, re_ice, re_snow
   end type kidmp_wrf_fields
+  ! mp_gt_driver's optional aerosol arguments (M:807-832) for is_aerosol_aware = .true. (M:28)
+  type, bind(C) :: kidmp_wrf_aerosols
+     type(c_ptr) :: nc, nwfa, nifa, w, nwfa2d
+  end type kidmp_wrf_aerosols
 
   interface
      integer(c_int) function kidmp_init(cfg, handle) bind(C, name='kidmp_init')
@@ -97,6 +101,14 @@ module mphys_thompson09n
        type(kidmp_wrf_fields), intent(in) :: w
        real(c_float), value :: dt_in
      end function kidmp_mp_gt_driver
+     ! ... and with is_aerosol_aware = .true. (prognostic nc, nwfa, nifa; w; surface emission nwfa2d)
+     integer(c_int) function kidmp_mp_gt_driver_aero(handle, w, ae, dt_in) bind(C, name='kidmp_mp_gt_driver_aero')
+       import :: c_int, c_ptr, c_float, kidmp_wrf_fields, kidmp_wrf_aerosols
+       type(c_ptr), value :: handle
+       type(kidmp_wrf_fields), intent(in) :: w
+       type(kidmp_wrf_aerosols), intent(in) :: ae
+       real(c_float), value :: dt_in
+     end function kidmp_mp_gt_driver_aero
   end interface
 
   !Logical switches

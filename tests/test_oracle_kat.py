@@ -378,3 +378,116 @@ def test_cell_class_rule_covers_every_species_set():
                     assert not cold          # no freezing or nucleation can start in a cell of this class (M:2025)
                 if kc == "ICE":
                     assert cold and not iiwarm
+
+
+# ---- the aerosol-aware half (is_aerosol_aware = .true., M:28): functions and table, from the source text --------------------
+def test_aerosol_functions_known_answers():
+    """Eff_aero M:4354-4390, iceDeMott M:4720-4756, iceKoop M:4764-4789, activ_ncloud M:4451-4526 against the same formulas
+    written out in float64 numpy (independent arithmetic: agreement to f32 rounding, 1e-5)."""
+    PI, meanPath, boltz = 3.1415926536, 0.0256e-6, 1.3806503e-23
+
+    def eff(D, Da, visc, rhoa, T, sp):
+        vt = {"r": -0.1021 + 4.932e3 * D - 0.9551e6 * D**2 + 0.07934e9 * D**3 - 0.002362e12 * D**4,
+              "s": 40.0 * D**0.55, "g": 442.0 * D**0.89}[sp]
+        Cc = 1.0 + 2.0 * meanPath / Da * (1.257 + 0.4 * np.exp(-0.55 * Da / meanPath))
+        diff = boltz * T * Cc / (3.0 * PI * visc * Da)
+        Re, Sc = 0.5 * rhoa * D * vt / visc, visc / (rhoa * diff)
+        St = Da * Da * vt * 1000.0 / (9.0 * visc * D)
+        aval = 1.0 + np.log(1.0 + Re)
+        St2 = (1.2 + 1.0 / 12.0 * aval) / (1.0 + aval)
+        E = 4.0 / (Re * Sc) * (1.0 + 0.4 * np.sqrt(Re) * Sc**0.3333 + 0.16 * np.sqrt(Re) * np.sqrt(Sc)) \
+            + 4.0 * Da / D * (0.02 + Da / D * (1.0 + 2.0 * np.sqrt(Re)))
+        if St > St2:
+            E += ((St - St2) / (St - St2 + 0.666667))**1.5
+        return max(1e-5, min(E, 1.0))
+
+    for D, Da, visc, rhoa, T, sp in ((1.0e-3, 0.04e-6, 1.7e-5, 1.0, 280.0, "r"), (3.0e-3, 0.8e-6, 1.8e-5, 1.1, 290.0, "r"),
+                                     (5.0e-4, 0.04e-6, 1.6e-5, 0.8, 260.0, "s"), (2.0e-3, 0.8e-6, 1.6e-5, 0.7, 255.0, "s"),
+                                     (2.0e-3, 0.04e-6, 1.6e-5, 0.8, 260.0, "g"), (6.0e-3, 0.8e-6, 1.5e-5, 0.6, 250.0, "g")):
+        got = orc.eff_aero(D, Da, visc, rhoa, T, sp)
+        assert 1e-5 <= got <= 1.0
+        np.testing.assert_allclose(got, eff(D, Da, visc, rhoa, T, sp), rtol=2e-5, err_msg=str((D, Da, sp)))
+    # the big, slow-diffusing aerosol is collected more efficiently by large drops than the small one is by Brownian motion here
+    assert orc.eff_aero(3.0e-3, 0.8e-6, 1.8e-5, 1.1, 290.0, "r") > orc.eff_aero(3.0e-3, 0.04e-6, 1.8e-5, 1.1, 290.0, "r") * 0.1
+
+    rho_not0 = 101325.0 / (287.05 * 273.15)
+    for tempc, rho, nifa in ((-20.0, 0.8, 1.0e6), (-35.0, 0.5, 5.0e4), (-10.0, 1.0, 2.0e6)):
+        cc = nifa * rho_not0 * 1e-6 / rho
+        want = 5.94e-5 * (-tempc)**3.33 * cc**(-0.0264 * tempc + 0.0033) * rho / rho_not0 * 1000.0
+        np.testing.assert_allclose(orc.ice_demott(tempc, rho, nifa), want, rtol=2e-5)
+    assert orc.ice_demott(-20.0, 0.8, 1.0e6) > orc.ice_demott(-10.0, 0.8, 1.0e6) > 0.0          # colder: more nuclei
+
+    def koop(temp, qv, qvs, naero, dt):
+        satw = qv / qvs
+        mu = 210368.0 + 131.438 * temp - 3.32373e6 / temp - 41729.1 * np.log(temp)
+        a_w_i = np.exp(mu / (8.314 * temp))
+        d = satw - a_w_i
+        logJ = min(20.0, -906.7 + 8502.0 * d - 26924.0 * d * d + 29180.0 * d**3)
+        prob = min(1.0 - np.exp(-(10.0**logJ) * (4.0 / 3.0 * PI * 2.5e-6**3) * dt), 1.0)
+        return max(0.0, min(prob * naero, 1000.0e3)) if prob > 0 else 0.0
+
+    # (the rate goes from 0 to the cap over a few hundredths of saturation ratio: cases on the ramp, below and above it)
+    a_w_i_230 = float(np.exp((210368.0 + 131.438 * 230.0 - 3.32373e6 / 230.0 - 41729.1 * np.log(230.0)) / (8.314 * 230.0)))
+    for temp, satw, naero, dt in ((230.0, a_w_i_230 + 0.30, 3.0e8, 10.0), (230.0, a_w_i_230 + 0.305, 3.0e8, 10.0),
+                                  (230.0, a_w_i_230 + 0.20, 3.0e8, 10.0), (225.0, 1.05, 1.0e8, 60.0)):
+        want = koop(temp, satw * 1.0e-4, 1.0e-4, naero, dt)
+        got = orc.ice_koop(temp, np.float32(satw * 1.0e-4), 1.0e-4, naero, dt)
+        if 0.0 < want < 1000.0e3:
+            # log_J_rate is a difference of f32 terms of size 900 (rounding 6e-5 each) and satw an f32 quotient: 10**x turns a few
+            # hundredths of log_J_rate into tens of per cent, on a ramp that spans thirty decades
+            np.testing.assert_allclose(got, want, rtol=0.3)
+        else:
+            assert got == want
+    assert orc.ice_koop(230.0, 0.5e-4, 1.0e-4, 3.0e8, 10.0) == 0.0                                # far below the activity threshold
+
+    # tnccn_act is all ones in this reference (M:752-762): the activated number is the CCN number up to the rounding of the
+    # bilinear weights
+    for T, W, N in ((280.0, 0.5, 3.0e8), (250.0, 0.001, 5.0e6), (300.0, 50.0, 2.0e10), (270.0, -1.0, 1.0e8)):
+        np.testing.assert_allclose(orc.activ_ncloud(T, W, N), N, rtol=3e-6)
+
+
+def test_drop_evaporation_table(oracle_mixed):
+    """table_dropEvap M:4400-4439: tnc_wev(i,j,k) is the running sum over the first i diameter bins of the droplet spectrum with
+    number t_Nc(k) and content r_c(j): non-decreasing in i, and its last entry is (nearly) the whole number."""
+    o = oracle_mixed
+    tnc = o.get("tnc_wev").reshape(100, 37, 100, order="F")
+    tpc = o.get("tpc_wev").reshape(100, 37, 100, order="F")
+    assert np.isfinite(tnc).all() and (tnc >= 0).all() and (np.diff(tnc, axis=0) >= 0).all()
+    assert (np.diff(tpc, axis=0) >= 0).all()
+    t_Nc = o.get("t_Nc")
+    # droplet spectra that lie inside the bin range integrate to their number and to their mass
+    j, k = 20, 50
+    np.testing.assert_allclose(tnc[-1, j, k], t_Nc[k], rtol=2e-2)
+    r_c = 10.0 ** np.floor(np.arange(37) / 9.0 - 6.0) * (np.arange(37) % 9 + 1)                      # M:215-221 (1e-6 .. 1e-2)
+    np.testing.assert_allclose(tpc[-1, j, k], r_c[j], rtol=3e-2)
+
+
+def test_aerosol_aware_oracle_properties(oracle_mixed):
+    """mp_thompson with is_aerosol_aware = .true. on the oracle: clear-sky columns stay bit for bit as they were (M:1540, the
+    aerosol arrays too), the aerosol numbers stay inside their clamps (M:3628-3631), nc is zero exactly where there is no cloud
+    water (M:3633-3635) and below Nt_c_max / rho elsewhere (M:3646), and without any aerosol-specific process active (no cloud,
+    rain, snow, graupel; warm) the other fields are those of the default scheme."""
+    st, p, dz = synth.make_domain(1500, nz=60, nx=1024, col0=123456, cloudy_fraction=0.5, coherent=False)
+    nc, nwfa, nifa, w = synth.make_aerosols(st, p)
+    ref = {k: v.numpy().copy() for k, v in st.items()}
+    before = {k: v.copy() for k, v in ref.items()}
+    a0 = (nc.copy(), nwfa.copy(), nifa.copy())
+    pn = p.numpy().copy()
+    oracle_mixed.step_aero(10.0, ref, nc, nwfa, nifa, pn, w, dz.numpy().copy())
+    base = {k: v.copy() for k, v in before.items()}
+    oracle_mixed.step(10.0, base, pn, dz.numpy().copy())
+    clear = np.ones(1500, bool)
+    for k in FIELDS:
+        clear &= (base[k] == before[k]).all(0)
+    assert clear.sum() > 100
+    for k in FIELDS:
+        assert np.array_equal(ref[k][:, clear], before[k][:, clear]), k
+    for got, was in zip((nc, nwfa, nifa), a0):
+        assert np.array_equal(got[:, clear], was[:, clear])
+    rho = (np.float32(0.622) * pn / (np.float32(287.04) * ref["t"] * (ref["qv"] + np.float32(0.622))))
+    cloudy = ~clear
+    assert (nwfa[:, cloudy] * rho[:, cloudy] >= 11.1e6 * 0.999).all() and (nwfa[:, cloudy] * rho[:, cloudy] <= 9999.0e6 * 1.001).all()
+    assert (nifa[:, cloudy] >= 0.5e6 * 0.01 * 0.999).all() and (nifa[:, cloudy] * rho[:, cloudy] <= 9999.0e6 * 1.001).all()
+    assert ((nc == 0) == (ref["qc"] == 0))[:, cloudy].all()
+    assert (nc[:, cloudy] * rho[:, cloudy] <= 1999.0e6 * 1.001).all()
+    assert not any(np.isnan(ref[k]).any() for k in FIELDS)
