@@ -363,13 +363,25 @@ int ensure_work(kidmp_handle* h, WorkSet& w, long cols, int nz, bool own_stream)
 
 // `bps`: blocks per SM (0: as many as the kernel's launch bounds allow).  With several lanes a cell kernel that left no
 // register of an SM free would keep the other lanes' HBM-bound kernels out until its last block retires.
+#ifndef KC_AERO_WARM_B
+#define KC_AERO_WARM_B 3
+#endif
+#ifndef KC_AERO_ICE_B
+#define KC_AERO_ICE_B 3
+#endif
+#ifndef KC_AERO_MIX_B
+#define KC_AERO_MIX_B 2
+#endif
 template <bool RATES, bool AERO>
 void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s, cudaEvent_t n0_done, int bps) {
   auto mark = [&](int q) { if (h->timing) cudaEventRecord(h->ev_k[q + 1], s); };
   auto grid = [&](int own) { return (unsigned)(nsm * (bps > 0 && bps < own ? bps : own)); };
-  k_cells<KC_WARM, KC_WARM_T, KC_WARM_B, KC_WARM_BARS, RATES, AERO><<<grid(KC_WARM_B), KC_WARM_T, 0, s>>>(a);
+  // (the aerosol-aware instantiations carry more live values: one block per SM less keeps them out of local memory)
+  constexpr int WB = AERO ? KC_AERO_WARM_B : KC_WARM_B, IB = AERO ? KC_AERO_ICE_B : KC_ICE_B, MB = AERO ? KC_AERO_MIX_B : KC_MIXNR_B,
+                FB = AERO ? KC_AERO_MIX_B : KC_FULL_B;
+  k_cells<KC_WARM, KC_WARM_T, WB, KC_WARM_BARS, RATES, AERO><<<grid(WB), KC_WARM_T, 0, s>>>(a);
   mark(KT_WARM);
-  k_cells<KC_ICE, KC_ICE_T, KC_ICE_B, KC_ICE_BARS, RATES, AERO><<<grid(KC_ICE_B), KC_ICE_T, 0, s>>>(a);
+  k_cells<KC_ICE, KC_ICE_T, IB, KC_ICE_BARS, RATES, AERO><<<grid(IB), KC_ICE_T, 0, s>>>(a);
   mark(KT_ICE);
   if (n0_done) cudaStreamWaitEvent(s, n0_done, 0);     // only the classes with graupel read the intercept minima of k_n0_sweep
   // The two classes that gather from the big tables (qcfz / iaus: mixed; racs, racg, qrfz: full) run with an L2
@@ -382,12 +394,12 @@ void launch_cells(kidmp_handle* h, const StepArgs& a, int nsm, cudaStream_t s, c
   att[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
   att[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(KC_MIXNR_T); cfg.gridDim = dim3(grid(KC_MIXNR_B)); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cfg.blockDim = dim3(KC_MIXNR_T); cfg.gridDim = dim3(grid(MB)); cfg.dynamicSmemBytes = 0; cfg.stream = s;
   cfg.attrs = att; cfg.numAttrs = (h->l2_window_bytes && h->l2_window) ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, k_cells<KC_MIXNR, KC_MIXNR_T, KC_MIXNR_B, KC_MIXNR_BARS, RATES, AERO>, a);
+  cudaLaunchKernelEx(&cfg, k_cells<KC_MIXNR, KC_MIXNR_T, MB, KC_MIXNR_BARS, RATES, AERO>, a);
   mark(KT_MIXNR);
-  cfg.blockDim = dim3(KC_FULL_T); cfg.gridDim = dim3(grid(KC_FULL_B));
-  cudaLaunchKernelEx(&cfg, k_cells<KC_FULL, KC_FULL_T, KC_FULL_B, KC_FULL_BARS, RATES, AERO>, a);
+  cfg.blockDim = dim3(KC_FULL_T); cfg.gridDim = dim3(grid(FB));
+  cudaLaunchKernelEx(&cfg, k_cells<KC_FULL, KC_FULL_T, FB, KC_FULL_BARS, RATES, AERO>, a);
   mark(KT_FULL);
 }
 

@@ -28,6 +28,8 @@ def per(**kw):
 VARIANTS = {
     "base": [],
     "evict": ["-DKIDMP_EVICT_FIRST"],              # hand-off records stored and loaded with L1 no-allocate / L2 evict-first
+    "aero443": ["-DKC_AERO_WARM_B=4", "-DKC_AERO_ICE_B=4", "-DKC_AERO_MIX_B=3"],     # launch shapes of the aerosol-aware cell kernels
+    "aero442": ["-DKC_AERO_WARM_B=4", "-DKC_AERO_ICE_B=4", "-DKC_AERO_MIX_B=2"],
     "native32": ["-DKIDMP_NATIVE_F32"],          # f32 transcendentals on the SFU: what rule 2 of DESIGN.md section 4 costs
     "free": per(WARM=(256, 4, 0), ICE=(256, 4, 0), MIXNR=(256, 3, 0), FULL=(256, 3, 0)),
     "free128": per(WARM=(128, 8, 0), ICE=(128, 8, 0), MIXNR=(128, 6, 0), FULL=(128, 6, 0)),
