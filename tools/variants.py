@@ -35,6 +35,8 @@ VARIANTS = {
     "free128": per(WARM=(128, 8, 0), ICE=(128, 8, 0), MIXNR=(128, 6, 0), FULL=(128, 6, 0)),
     "ice5": per(ICE=(256, 5, 11), WARM=(256, 5, 11)),
     "ice3": per(ICE=(256, 3, 11)),
+    "mix2": per(MIXNR=(256, 2, 11), FULL=(256, 2, 11)),
+    "full2": per(FULL=(256, 2, 11)),
     "mix4": per(MIXNR=(256, 4, 11), FULL=(256, 4, 11)),
     "lock512": per(WARM=(512, 2, 11), ICE=(512, 2, 11), MIXNR=(384, 2, 11), FULL=(384, 2, 11)),
     "bars63": per(WARM=(256, 4, 63), ICE=(256, 4, 63), MIXNR=(256, 3, 63), FULL=(256, 3, 63)),
