@@ -77,6 +77,10 @@ struct kidmp_handle {
   int lanes = 1;                                          // work sets used side by side ("lanes" option, KIDMP_LANES)
   long lane_min_cols = 131072;                            // no sub-chunk smaller than this ("lane_min" option)
   int cell_blocks = 0;                                    // blocks per SM of the cell kernels when several lanes run (0: the kernel's own)
+  // a small domain is launch-bound (fifteen kernels of a few microseconds): its launches are captured once in a CUDA graph and
+  // replayed while the arguments stay the same ("graphs" option, KIDMP_GRAPHS; domains of at most graph_max_cols columns)
+  int graphs = 1; long graph_max_cols = 32768;
+  cudaGraphExec_t graph_exec = nullptr; StepArgs graph_args{}; long graph_key[6] = {}; long graph_launches = 0;
   int simple = 1;                                         // "simple" option: columns without sub-steps skip k_carries (kidmp_cells.cuh)
   int l2_window = 1;                                      // "l2_window" option: the cell kernels that gather from the tables carry the window
   int stagger = 0;                                        // "stagger" option: see launch_step
@@ -429,17 +433,41 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   // the work sets are the handle's: a step on another stream than the last one starts after it
   CK(h, cudaStreamWaitEvent(s, h->ev_done, 0));
   if (ensure_constants(h, s)) return 1;
-  // the handle's own rate buffer starts every step at zero: clear-sky columns have no process at all
-  if (a0.rates && a0.rates == h->d_rates_own) CK(h, cudaMemsetAsync(h->d_rates_own, 0, (size_t)KIDMP_NRATES * a0.nz * a0.ld * 4, s));
   if (h->partial_chunks < nchunks) {
     if (h->d_partial) { CK(h, cudaDeviceSynchronize()); cudaFree(h->d_partial); h->d_partial = nullptr; h->partial_chunks = 0; }
     CK(h, cudaMalloc((void**)&h->d_partial, (size_t)nchunks * DIAG_BLOCKS * KIDMP_NDIAG * 8));
     h->partial_chunks = nchunks;
   }
+  // Small domain: replay the captured graph of this very step, or capture it now.
+  const bool graphable = h->graphs && !h->timing && nchunks == 1 && nl == 1 && a0.ncol <= h->graph_max_cols;
+  const long gkey[6] = {(long)(size_t)h->ws[0].d_scratch, h->ws[0].cols, (long)h->ws[0].nz, (long)h->simple, (long)(size_t)h->d_partial, (long)h->l2_window};
+  if (graphable && h->graph_exec && !memcmp(&h->graph_args, &a0, sizeof a0) && !memcmp(h->graph_key, gkey, sizeof gkey)) {
+    CK(h, cudaGraphLaunch(h->graph_exec, s));
+    h->launches += h->graph_launches;
+    for (int l = 0; l < MAX_LANES; ++l) h->ws[l].used = l == 0;
+    h->lanes_used = 1;
+    h->timing_valid = false;
+    CK(h, cudaEventRecord(h->ev_done, s));
+    h->last_on_own_stream = (s == h->stream);
+    return 0;
+  }
+  bool capturing = false;
+  const long launches_before = h->launches;
+  if (graphable) {
+    if (h->graph_exec) { cudaEventSynchronize(h->ev_done); cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // (its last replay has ended)
+    capturing = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (!capturing) cudaGetLastError();                 // (a stream that cannot be captured: plain launches)
+  }
+  struct CaptureGuard {                                 // an error path must not leave the stream in capture mode
+    cudaStream_t s; bool* on;
+    ~CaptureGuard() { if (*on) { cudaGraph_t g = nullptr; cudaStreamEndCapture(s, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); } }
+  } capture_guard{s, &capturing};
   if (nl > 1) {
     CK(h, cudaEventRecord(h->ev_start, s));
     for (int l = 1; l < nl; ++l) CK(h, cudaStreamWaitEvent(h->ws[l].s, h->ev_start, 0));
   }
+  // the handle's own rate buffer starts every step at zero: clear-sky columns have no process at all
+  if (a0.rates && a0.rates == h->d_rates_own) CK(h, cudaMemsetAsync(h->d_rates_own, 0, (size_t)KIDMP_NRATES * a0.nz * a0.ld * 4, s));
   for (int l = 0; l < MAX_LANES; ++l) h->ws[l].used = l < nl;
   h->lanes_used = nl;
   const int bps = nl > 1 ? h->cell_blocks : 0;
@@ -528,6 +556,17 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   ++h->launches;
   if (h->timing) cudaEventRecord(h->ev_k[KT_DIAG + 1], s);
   h->timing_valid = h->timing != 0;
+  if (capturing) {
+    cudaGraph_t g = nullptr;
+    capturing = false;                                  // (the guard has nothing left to end)
+    CK(h, cudaStreamEndCapture(s, &g));
+    const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) { h->graph_exec = nullptr; return fail(h, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+    h->graph_args = a0; memcpy(h->graph_key, gkey, sizeof gkey);
+    h->graph_launches = h->launches - launches_before;
+    CK(h, cudaGraphLaunch(h->graph_exec, s));
+  }
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(h->ev_done, s));
   h->last_on_own_stream = (s == h->stream);
@@ -834,6 +873,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   if (getenv("KIDMP_CELL_BLOCKS")) h->cell_blocks = atoi(getenv("KIDMP_CELL_BLOCKS"));
   if (getenv("KIDMP_STAGGER")) h->stagger = atoi(getenv("KIDMP_STAGGER"));
   if (getenv("KIDMP_SIMPLE")) h->simple = atoi(getenv("KIDMP_SIMPLE")) != 0;
+  if (getenv("KIDMP_GRAPHS")) h->graphs = atoi(getenv("KIDMP_GRAPHS")) != 0;
   if (getenv("KIDMP_PIPE_CHUNK")) h->pipe_chunk = atol(getenv("KIDMP_PIPE_CHUNK")) > 1024 ? atol(getenv("KIDMP_PIPE_CHUNK")) : 1024;
   if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
   h->cfg.table_cache_path = nullptr;
@@ -921,6 +961,7 @@ int kidmp_finalize(kidmp_handle* h) {
   }
   cudaDeviceSynchronize();                           // steps may have run on caller streams
   free_state(h);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->d_tables) cudaFree(h->d_tables);
   if (h->d_tnc_wev) cudaFree(h->d_tnc_wev);
   if (h->d_aero) cudaFree(h->d_aero);
@@ -1589,6 +1630,7 @@ int kidmp_set_option(kidmp_handle* h, const char* name, int value) {
     if (value < 1024) return fail(h, "set_option: lane_min must be at least 1024 columns");
     h->lane_min_cols = value; return 0;
   }
+  if (!strcmp(name, "graphs")) { h->graphs = value != 0; return 0; }
   if (!strcmp(name, "simple")) { h->simple = value != 0; return 0; }
   if (!strcmp(name, "l2_window")) { h->l2_window = value != 0; return 0; }
   if (!strcmp(name, "stagger")) { h->stagger = value != 0; return 0; }

@@ -875,3 +875,35 @@ def test_wrf_driver_entry_aerosol_aware(gpu_mixed, oracle_mixed):
         & (got["qv"][:, sel] == want["qv"][:, sel])
     np.testing.assert_allclose(planes(ra["re_cloud"])[:, sel][same_state], rc_want[:, sel][same_state], rtol=2e-5)
     assert (np.abs(rc_want[:, sel] - rc_fixed[:, sel]) > 1e-7).any()
+
+
+@pytest.mark.gpu
+def test_graph_replay_of_small_domains_is_bit_identical():
+    """A domain of at most 32 768 columns is launch-bound: its fifteen launches are captured once in a CUDA graph and replayed
+    while the arguments stay the same ("graphs" option).  Same bits as plain launches, over several steps, also when the
+    arguments change in between (another dt: a new capture) and when the handle's work buffers grow (a larger domain)."""
+    import torch
+    from kid_b200 import synth
+    from kid_b200.kidmp import Thompson
+    res = {}
+    for graphs in (1, 0):
+        th = Thompson(set_Nc=100.0, iiwarm=False, l_sediment=True)
+        th.set_option("graphs", graphs)
+        out = []
+        for ncol, dts in ((700, (10.0, 10.0, 10.0, 30.0, 30.0, 10.0)), (3000, (20.0, 20.0)), (700, (10.0, 10.0))):
+            st, p, dzv = synth.make_domain(ncol, nz=60, nx=1024, device="cuda", col0=4242, cloudy_fraction=0.8, coherent=False)
+            ppt = torch.zeros((4, ncol), dtype=torch.float32, device="cuda")
+            acc = torch.zeros((4, ncol), dtype=torch.float64, device="cuda")
+            for dt in dts:
+                th.step_device(ncol, 60, dt, [st[k].data_ptr() for k in FIELDS], p.data_ptr(), dzv.data_ptr(), ppt.data_ptr())
+                th.sync()
+                acc += ppt.double()
+            out.append(({k: st[k].cpu().numpy() for k in FIELDS}, acc.cpu().numpy()))
+        res[graphs] = (out, th.diag(), th.gpu_launches)
+        th.close()
+    for (sa, pa), (sb, pb) in zip(res[1][0], res[0][0]):
+        for k in FIELDS:
+            assert np.array_equal(sa[k], sb[k]), k
+        assert np.array_equal(pa, pb) and pa.sum() > 0
+    assert np.array_equal(res[1][1], res[0][1])                                 # the domain sums too
+    assert res[1][2] == res[0][2]                                               # and the launch count is the kernels' either way
