@@ -13,10 +13,14 @@
 //                                code that cannot run for the class (every ice process for a warm cell, the collection
 //                                tables without rain ...) is not compiled into its kernel, so ptxas needs neither the
 //                                registers of the 35 f64 rates nor the 120 KB of instructions where they do not apply;
-//   k_finish                     one thread per cloudy column: sweep A settles what runs down the column (intercept
-//                                minimum of S10, fall speeds, sub-step counts), then S14 sedimentation (M:3365-3578),
-//                                S15 and S16 (finish_level).  Idle cells never had a hand-off record: their
-//                                tendencies are zero and their contents R1 / R2 by construction.
+//   k_carries                    one thread per cloudy column that is not SIMPLE (graupel, or a fall speed that can cross a
+//                                layer in one step): what runs down the column - intercept minimum of S10, fall speeds of the
+//                                levels without the species, sub-step counts; columns with sub-steps go to k_substeps;
+//   k_finish                     one thread per cloudy column: the only sedimentation sub-step (M:3365-3578), S15 and S16
+//                                (finish_level); for a simple column also the snow speed of M:3301 and the top sedimenting
+//                                levels.  Idle cells never had a hand-off record: their tendencies are zero and their
+//                                contents R1 / R2 by construction.
+// AERO (template parameter of k_cells, k_finish, k_substeps): is_aerosol_aware = .true., M:28 (kidmp_aero.cuh).
 // Pruning rule: a block is compiled out of a class kernel only when it cannot execute for any cell of the class, so
 // every class kernel computes bit for bit what the general code (KC_FULL) computes for the same cell.
 #pragma once
