@@ -77,9 +77,10 @@ struct kidmp_handle {
   int lanes = 1;                                          // work sets used side by side ("lanes" option, KIDMP_LANES)
   long lane_min_cols = 131072;                            // no sub-chunk smaller than this ("lane_min" option)
   int cell_blocks = 0;                                    // blocks per SM of the cell kernels when several lanes run (0: the kernel's own)
-  // a small domain is launch-bound (fifteen kernels of a few microseconds): its launches are captured once in a CUDA graph and
-  // replayed while the arguments stay the same ("graphs" option, KIDMP_GRAPHS; domains of at most graph_max_cols columns)
-  int graphs = 1; long graph_max_cols = 32768;
+  // The launches of a step that is one chunk on one lane are captured once in a CUDA graph and replayed while the arguments stay
+  // the same ("graphs" option, KIDMP_GRAPHS; KIDMP_GRAPH_MAX: largest domain): a small domain is launch-bound (fifteen kernels of
+  // a few microseconds: 0.297 -> 0.277 ms for one column), the 1 048 576-column step loses its launch gaps (3.45 -> 3.425 ms)
+  int graphs = 1; long graph_max_cols = 1L << 24;
   cudaGraphExec_t graph_exec = nullptr; StepArgs graph_args{}; long graph_key[6] = {}; long graph_launches = 0;
   int simple = 1;                                         // "simple" option: columns without sub-steps skip k_carries (kidmp_cells.cuh)
   int l2_window = 1;                                      // "l2_window" option: the cell kernels that gather from the tables carry the window
@@ -438,7 +439,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     CK(h, cudaMalloc((void**)&h->d_partial, (size_t)nchunks * DIAG_BLOCKS * KIDMP_NDIAG * 8));
     h->partial_chunks = nchunks;
   }
-  // Small domain: replay the captured graph of this very step, or capture it now.
+  // One chunk on one lane: replay the captured graph of this very step, or capture it now.
   const bool graphable = h->graphs && !h->timing && nchunks == 1 && nl == 1 && a0.ncol <= h->graph_max_cols;
   const long gkey[6] = {(long)(size_t)h->ws[0].d_scratch, h->ws[0].cols, (long)h->ws[0].nz, (long)h->simple, (long)(size_t)h->d_partial, (long)h->l2_window};
   if (graphable && h->graph_exec && !memcmp(&h->graph_args, &a0, sizeof a0) && !memcmp(h->graph_key, gkey, sizeof gkey)) {
@@ -874,6 +875,7 @@ int kidmp_init(const kidmp_config* cfg, kidmp_handle** out) {
   if (getenv("KIDMP_STAGGER")) h->stagger = atoi(getenv("KIDMP_STAGGER"));
   if (getenv("KIDMP_SIMPLE")) h->simple = atoi(getenv("KIDMP_SIMPLE")) != 0;
   if (getenv("KIDMP_GRAPHS")) h->graphs = atoi(getenv("KIDMP_GRAPHS")) != 0;
+  if (getenv("KIDMP_GRAPH_MAX") && atol(getenv("KIDMP_GRAPH_MAX")) > 0) h->graph_max_cols = atol(getenv("KIDMP_GRAPH_MAX"));
   if (getenv("KIDMP_PIPE_CHUNK")) h->pipe_chunk = atol(getenv("KIDMP_PIPE_CHUNK")) > 1024 ? atol(getenv("KIDMP_PIPE_CHUNK")) : 1024;
   if (cfg->table_cache_path) h->cache_path = cfg->table_cache_path;
   h->cfg.table_cache_path = nullptr;

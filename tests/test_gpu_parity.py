@@ -755,7 +755,7 @@ def test_schedule_options_are_bit_identical(dt, dz):
     from kid_b200.kidmp import Thompson
     ncol, nz = 40000, 60
     res = {}
-    for name, opts in (("default", {}), ("no_simple", {"simple": 0}), ("lanes3", {"lanes": 3, "lane_min": 4096}),
+    for name, opts in (("default", {}), ("no_graph", {"graphs": 0}), ("no_simple", {"simple": 0}), ("lanes3", {"lanes": 3, "lane_min": 4096}),
                        ("lanes2_stagger", {"lanes": 2, "lane_min": 8192, "stagger": 1, "cell_blocks": 2}),
                        ("timing1", {"timing": 1}), ("timing2", {"timing": 2})):
         th = Thompson(set_Nc=100.0, iiwarm=False, l_sediment=True)
@@ -879,8 +879,8 @@ def test_wrf_driver_entry_aerosol_aware(gpu_mixed, oracle_mixed):
 
 @pytest.mark.gpu
 def test_graph_replay_of_small_domains_is_bit_identical():
-    """A domain of at most 32 768 columns is launch-bound: its fifteen launches are captured once in a CUDA graph and replayed
-    while the arguments stay the same ("graphs" option).  Same bits as plain launches, over several steps, also when the
+    """The fifteen launches of a step that fits one chunk are captured once in a CUDA graph and replayed while the arguments stay
+    the same ("graphs" option): small domains are launch-bound.  Same bits as plain launches, over several steps, also when the
     arguments change in between (another dt: a new capture) and when the handle's work buffers grow (a larger domain)."""
     import torch
     from kid_b200 import synth
