@@ -182,7 +182,7 @@ int kidmp_mp_gt_driver_aero(kidmp_handle* h, const kidmp_wrf_fields* w, const ki
  * buffers (128-byte hand-off records, cell lists) are sized for one chunk, whatever the size of the domain.
  * "timing": 1 = run the kernels of a launch one after the other with an event after each (kidmp_last_kernel_ms), 2 = the
  *   normal schedule (second stream in use) with the same events on the main stream, 0 = normal.
- * "graphs": 1 (default, KIDMP_GRAPHS) = the launches of a step that fits one chunk are captured once in a CUDA graph and replayed
+ * "graphs": 1 (default, KIDMP_GRAPHS) = the launches of a step (up to 64 chunks on one lane) are captured once in a CUDA graph (a cache of eight) and replayed
  *   while the arguments stay the same (KiD's own cases of 1 to 14 400 columns are launch-bound; the 1 048 576-column step loses its
  *   launch gaps); 0 = plain launches.
  * "simple": 1 (default) = a column that holds no graupel and in which no fall speed can cross the thinnest layer in one step

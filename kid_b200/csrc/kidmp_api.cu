@@ -81,7 +81,8 @@ struct kidmp_handle {
   // the same ("graphs" option, KIDMP_GRAPHS; KIDMP_GRAPH_MAX: largest domain): a small domain is launch-bound (fifteen kernels of
   // a few microseconds: 0.297 -> 0.277 ms for one column), the 1 048 576-column step loses its launch gaps (3.45 -> 3.425 ms)
   int graphs = 1; long graph_max_cols = 1L << 24;
-  cudaGraphExec_t graph_exec = nullptr; StepArgs graph_args{}; long graph_key[6] = {}; long graph_launches = 0;
+  struct StepGraph { cudaGraphExec_t exec = nullptr; StepArgs args{}; long key[6] = {}; long launches = 0; };
+  StepGraph graph_cache[8]; int graph_next = 0;        // a few steps at a time: the three rotating buffers of kidmp_step's pipeline, resident state, a caller's arrays
   int simple = 1;                                         // "simple" option: columns without sub-steps skip k_carries (kidmp_cells.cuh)
   int l2_window = 1;                                      // "l2_window" option: the cell kernels that gather from the tables carry the window
   int stagger = 0;                                        // "stagger" option: see launch_step
@@ -439,12 +440,16 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     CK(h, cudaMalloc((void**)&h->d_partial, (size_t)nchunks * DIAG_BLOCKS * KIDMP_NDIAG * 8));
     h->partial_chunks = nchunks;
   }
-  // One chunk on one lane: replay the captured graph of this very step, or capture it now.
-  const bool graphable = h->graphs && !h->timing && nchunks == 1 && nl == 1 && a0.ncol <= h->graph_max_cols;
+  // One lane: replay the captured graph of this very step (all its chunks), or capture it now.
+  const bool graphable = h->graphs && !h->timing && nchunks <= 64 && nl == 1 && a0.ncol <= h->graph_max_cols;
   const long gkey[6] = {(long)(size_t)h->ws[0].d_scratch, h->ws[0].cols, (long)h->ws[0].nz, (long)h->simple, (long)(size_t)h->d_partial, (long)h->l2_window};
-  if (graphable && h->graph_exec && !memcmp(&h->graph_args, &a0, sizeof a0) && !memcmp(h->graph_key, gkey, sizeof gkey)) {
-    CK(h, cudaGraphLaunch(h->graph_exec, s));
-    h->launches += h->graph_launches;
+  kidmp_handle::StepGraph* hit = nullptr;
+  if (graphable)
+    for (auto& g : h->graph_cache)
+      if (g.exec && !memcmp(&g.args, &a0, sizeof a0) && !memcmp(g.key, gkey, sizeof gkey)) { hit = &g; break; }
+  if (hit) {
+    CK(h, cudaGraphLaunch(hit->exec, s));
+    h->launches += hit->launches;
     for (int l = 0; l < MAX_LANES; ++l) h->ws[l].used = l == 0;
     h->lanes_used = 1;
     h->timing_valid = false;
@@ -454,8 +459,10 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   }
   bool capturing = false;
   const long launches_before = h->launches;
+  kidmp_handle::StepGraph& slot = h->graph_cache[h->graph_next];
   if (graphable) {
-    if (h->graph_exec) { cudaEventSynchronize(h->ev_done); cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // (its last replay has ended)
+    h->graph_next = (h->graph_next + 1) % 8;
+    if (slot.exec) { cudaEventSynchronize(h->ev_done); cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }   // (its last replay has ended)
     capturing = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
     if (!capturing) cudaGetLastError();                 // (a stream that cannot be captured: plain launches)
   }
@@ -561,12 +568,12 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
     cudaGraph_t g = nullptr;
     capturing = false;                                  // (the guard has nothing left to end)
     CK(h, cudaStreamEndCapture(s, &g));
-    const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, g, 0);
+    const cudaError_t ie = cudaGraphInstantiate(&slot.exec, g, 0);
     cudaGraphDestroy(g);
-    if (ie != cudaSuccess) { h->graph_exec = nullptr; return fail(h, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
-    h->graph_args = a0; memcpy(h->graph_key, gkey, sizeof gkey);
-    h->graph_launches = h->launches - launches_before;
-    CK(h, cudaGraphLaunch(h->graph_exec, s));
+    if (ie != cudaSuccess) { slot.exec = nullptr; return fail(h, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+    slot.args = a0; memcpy(slot.key, gkey, sizeof gkey);
+    slot.launches = h->launches - launches_before;
+    CK(h, cudaGraphLaunch(slot.exec, s));
   }
   CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(h->ev_done, s));
@@ -963,7 +970,7 @@ int kidmp_finalize(kidmp_handle* h) {
   }
   cudaDeviceSynchronize();                           // steps may have run on caller streams
   free_state(h);
-  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  for (auto& g : h->graph_cache) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->d_tables) cudaFree(h->d_tables);
   if (h->d_tnc_wev) cudaFree(h->d_tnc_wev);
   if (h->d_aero) cudaFree(h->d_aero);
