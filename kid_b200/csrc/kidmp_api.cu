@@ -442,7 +442,7 @@ int launch_step(kidmp_handle* h, const StepArgs& a0, cudaStream_t s) {
   }
   // One lane: replay the captured graph of this very step (all its chunks), or capture it now.
   const bool graphable = h->graphs && !h->timing && nchunks <= 64 && nl == 1 && a0.ncol <= h->graph_max_cols;
-  const long gkey[6] = {(long)(size_t)h->ws[0].d_scratch, h->ws[0].cols, (long)h->ws[0].nz, (long)h->simple, (long)(size_t)h->d_partial, (long)h->l2_window};
+  const long gkey[6] = {(long)(size_t)h->ws[0].d_scratch, h->ws[0].cols, (long)h->ws[0].nz, (long)h->simple, (long)(size_t)h->d_partial, (long)h->l2_window * 2 + chunk * 4};
   kidmp_handle::StepGraph* hit = nullptr;
   if (graphable)
     for (auto& g : h->graph_cache)
