@@ -5,6 +5,7 @@ the UNMODIFIED reference scheme compiled with the stub host modules of kid_stubs
     probe()      -> {"compiler": path or None, "tried": [...]}     (recorded in bench.py's cpu_baseline)
     build()      -> path of the driver, or None when it cannot be built here
     run_columns(state, p, dz, dt, ...)    one mp_thompson call per column (U1 inputs), returns (state after, ppt[4, nx], tables)
+    run_columns_aero(state, nc, nwfa, nifa, w, p, dz, dt, ...)   the same with is_aerosol_aware = .true. (M:28)
     run_interface(kid, dt, ...)           one mphys_thompson09_interfacen call, returns the KiD tendencies
 Arrays are KiD's (k, i) order: numpy shape (nx, nz), float32.
 """
@@ -87,6 +88,18 @@ def run_columns(state, p, dz, dt, set_Nc=100.0, iiwarm=False, l_sediment=True):
     out = body[:9 * nx * nz].reshape(9, nx, nz)
     ppt = body[9 * nx * nz:].reshape(nx, 4).T.copy()                                     # Fortran (4, nx)
     return {k: out[i].copy() for i, k in enumerate(FIELDS)}, ppt, tables
+
+
+def run_columns_aero(state, nc, nwfa, nifa, w, p, dz, dt, set_Nc=100.0, iiwarm=False, l_sediment=True):
+    """mp_thompson per column with is_aerosol_aware = .true.; returns (state after, ppt[4, nx], (nc, nwfa, nifa) after, tables)."""
+    nx, nz = np.asarray(state["t"]).shape
+    arrays = [np.stack([np.asarray(state[k], np.float32) for k in FIELDS]), p,
+              np.stack([np.asarray(a, np.float32) for a in (nc, nwfa, nifa, w)]), dz]
+    body, tables = _run(_header(3, nx, nz, iiwarm, l_sediment, dt, set_Nc), arrays, 9 * nx * nz + 4 * nx + 3 * nx * nz)
+    out = body[:9 * nx * nz].reshape(9, nx, nz)
+    ppt = body[9 * nx * nz:9 * nx * nz + 4 * nx].reshape(nx, 4).T.copy()
+    ae = body[9 * nx * nz + 4 * nx:].reshape(3, nx, nz)
+    return {k: out[i].copy() for i, k in enumerate(FIELDS)}, ppt, tuple(ae[i].copy() for i in range(3)), tables
 
 
 def run_interface(kid, dt, set_Nc=100.0, iiwarm=False, l_sediment=True):

@@ -9,6 +9,9 @@
 !   mode 2 "interface": theta dtheta_adv dtheta_div exner qv dqv_adv dqv_div (nz, nx), dz (nz), then for the seven prognostic
 !                       moments qc qr nr qi ni qs qg: value, advective and divergence tendency (nz, nx) each.  One call of
 !                       mphys_thompson09_interfacen (I:28).
+!   mode 3 "aerosol"  : mode 1 with is_aerosol_aware = .true. (M:28 is a module VARIABLE: set before thompson_init): after p, the
+!                       planes nc nwfa nifa w (nz, nx) are read, passed as nc1d nwfa1d nifa1d w1d, and nc nwfa nifa are written
+!                       after ppt.
 ! Output: mode 1: the nine fields after the step, ppt (4, nx) rain ice snow graupel.  mode 2: dtheta_mphys, dqv_mphys, the
 !   seven moment tendencies.  Both: 64 table words = sum and a strided checksum of every lookup table (real64), and the
 !   number of save_dg calls.
@@ -25,7 +28,7 @@ program ref_driver
   integer :: mode, inx, inz, iwarm, ised, i, k, m, ih, im
   real :: rdt, rnc
   real, allocatable :: f(:, :, :), p(:, :), dzq(:), ppt(:, :), plane(:, :)
-  real, allocatable :: nc1d(:), nwfa1d(:), nifa1d(:), w1d(:), col(:, :)
+  real, allocatable :: nc1d(:), nwfa1d(:), nifa1d(:), w1d(:), col(:, :), ae(:, :, :)
   real :: rho, pptrain, pptsnow, pptgraul, pptice
   real(8) :: tw(64)
   integer, parameter :: mh(7) = (/1, 2, 2, 3, 3, 4, 5/), mm(7) = (/1, 1, 2, 1, 2, 1, 1/)
@@ -39,10 +42,15 @@ program ref_driver
   iiwarm = iwarm /= 0; l_sediment = ised /= 0; set_Nc = rnc; l_reuse_thompson_lookup = .false.
   open(22, file=trim(fout), access='stream', form='unformatted', status='replace')
 
-  if (mode == 1) then
+  if (mode == 1 .or. mode == 3) then
      allocate(f(nz, nx, 9), p(nz, nx), dzq(nz), ppt(4, nx), nc1d(nz), nwfa1d(nz), nifa1d(nz), w1d(nz), col(nz, 9))
      read(21) f
      read(21) p
+     if (mode == 3) then
+        allocate(ae(nz, nx, 4))
+        read(21) ae
+        is_aerosol_aware = .true.
+     end if
      read(21) dzq
      call thompson_init                                     ! I:100-103
      do i = 1, nx
@@ -55,14 +63,21 @@ program ref_driver
            nifa1d(k) = 0.5E6 * 0.01 / rho
            w1d(k) = 0.
         end do
+        if (mode == 3) then
+           nc1d = ae(:, i, 1); nwfa1d = ae(:, i, 2); nifa1d = ae(:, i, 3); w1d = ae(:, i, 4)
+        end if
         ! field order of the file: qv qc qi qr qs qg ni nr t
         call mp_thompson(col(:, 1), col(:, 2), col(:, 3), col(:, 4), col(:, 5), col(:, 6), col(:, 7), col(:, 8), nc1d, nwfa1d, &
              nifa1d, col(:, 9), p(:, i), w1d, dzq, pptrain, pptsnow, pptgraul, pptice, 1, nz, dt, i, 1)
         f(:, i, :) = col
         ppt(1, i) = pptrain; ppt(2, i) = pptice; ppt(3, i) = pptsnow; ppt(4, i) = pptgraul
+        if (mode == 3) then
+           ae(:, i, 1) = nc1d; ae(:, i, 2) = nwfa1d; ae(:, i, 3) = nifa1d
+        end if
      end do
      write(22) f
      write(22) ppt
+     if (mode == 3) write(22) ae(:, :, 1:3)
   else
      call allocate_columns(nz, nx)
      allocate(plane(nz, nx))

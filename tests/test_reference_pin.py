@@ -67,3 +67,24 @@ def test_oracle_equals_the_committed_reference_columns(oracle_mixed):
         den = np.maximum(np.abs(g["out_" + k]), 1e-12 if k.startswith("q") else 1e-3)
         assert (np.abs(mine[k] - g["out_" + k]) / den).max() <= 1e-5, k
     assert np.allclose(ppt_o, g["ppt"], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.skipif(not ref.available() and ref.build() is None, reason="no Fortran compiler / reference sources here")
+def test_oracle_equals_the_fortran_reference_with_the_aerosol_switch_on(oracle_mixed):
+    """The aerosol-aware half: ref_driver mode 3 sets the module variable is_aerosol_aware (M:28) before thompson_init and passes
+    nc1d, nwfa1d, nifa1d, w1d to mp_thompson; the oracle's restatement of the switch must give the same columns."""
+    from kid_b200 import synth
+    st, p, dz = synth.make_domain(256, nz=60, cloudy_fraction=1.0, coherent=False)
+    nc, nwfa, nifa, w = synth.make_aerosols(st, p)
+    a = {k: np.ascontiguousarray(v.numpy().T) for k, v in st.items()}           # (nx, nz)
+    pk = np.ascontiguousarray(p.numpy().T)
+    T = lambda x: np.ascontiguousarray(x.T)
+    got, ppt, (gnc, gnwfa, gnifa), _ = ref.run_columns_aero(a, T(nc), T(nwfa), T(nifa), T(w), pk, dz.numpy(), 10.0, set_Nc=100.0)
+    mine = {k: v.numpy().copy() for k, v in st.items()}                        # (nz, nx)
+    ppt_o = oracle_mixed.step_aero(10.0, mine, nc, nwfa, nifa, p.numpy().copy(), w, dz.numpy())
+    want = dict({k: got[k].T for k in FIELDS}, nc=gnc.T, nwfa=gnwfa.T, nifa=gnifa.T)
+    have = dict(mine, nc=nc, nwfa=nwfa, nifa=nifa)
+    for k in FIELDS + ("nc", "nwfa", "nifa"):
+        den = np.maximum(np.abs(want[k]), 1e-12 if k.startswith("q") else 1e-3)
+        assert (np.abs(have[k] - want[k]) / den).max() <= 1e-5, k
+    assert np.allclose(ppt_o, ppt, rtol=1e-5, atol=1e-12)
