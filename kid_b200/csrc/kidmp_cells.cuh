@@ -50,6 +50,41 @@ __device__ __forceinline__ Sector ld_sector(const float* p) {
   return s;
 }
 
+// First half of the hand-off record of the cell at list position `idx`: the ten tendencies and the numbers at tau+1.  A cell
+// of the warm class has seven of those words that are not a constant of the class, a cell of the ice class eight (its ice
+// number speed rides in the rain-number-speed word of the second half, which its class cannot use): the records of these two
+// classes - four fifths of the busy cells, first in the list - keep ONE sector here, the mixed classes two.  An aerosol-aware
+// run keeps two sectors everywhere (two more tendencies).  k1, k2: first list entries of the ice and of the mixed classes.
+struct RecA { float tt, qvt, qct, qit, qrt, qst, qgt, nit, nrt, nct, nr, ni, v_ni, nwfat, nifat; };
+template <bool AERO>
+__device__ __forceinline__ float* rec_a_ptr(const StepArgs& a, unsigned idx, unsigned k2) {
+  if (AERO) return a.scratch + (size_t)idx * SC_HALF;
+  return idx < k2 ? a.scratch + (size_t)idx * 8 : a.scratch + ((size_t)idx * SC_HALF - (size_t)k2 * 8);
+}
+template <bool AERO>
+__device__ __forceinline__ RecA load_rec_a(const StepArgs& a, unsigned idx, unsigned k1, unsigned k2, const Sector& s2) {
+  RecA r;
+  const float* q = rec_a_ptr<AERO>(a, idx, k2);
+  const Sector s0 = ld_sector(q);
+  r.nwfat = 0.f; r.nifat = 0.f;
+  if (!AERO && idx < k2) {
+    r.tt = s0.v[0]; r.qvt = s0.v[1]; r.qct = s0.v[2]; r.qgt = 0.0f;
+    if (idx < k1) {          // warm: no ice-phase tendency (the zeros as S8 leaves them: nit = -ni1d * odts with ni1d = 0)
+      r.qrt = s0.v[3]; r.nrt = s0.v[4]; r.nct = s0.v[5]; r.nr = s0.v[6];
+      r.qit = 0.0f; r.qst = 0.0f; r.nit = -0.0f; r.ni = KP_R2; r.v_ni = 0.0f;
+    } else {                 // ice: no rain (qrt = -qr1d * odts, nrt = -nr1d * odts with zero inputs), no graupel
+      r.qit = s0.v[3]; r.qst = s0.v[4]; r.nit = s0.v[5]; r.nct = s0.v[6]; r.ni = s0.v[7];
+      r.qrt = -0.0f; r.nrt = -0.0f; r.nr = KP_R2; r.v_ni = s2.v[5];
+    }
+  } else {
+    const Sector s1 = ld_sector(q + 8);
+    r.tt = s0.v[0]; r.qvt = s0.v[1]; r.qct = s0.v[2]; r.qit = s0.v[3]; r.qrt = s0.v[4]; r.qst = s0.v[5]; r.qgt = s0.v[6]; r.nit = s0.v[7];
+    r.nrt = s1.v[0]; r.nct = s1.v[1]; r.nr = s1.v[2]; r.ni = s1.v[3]; r.v_ni = s1.v[4];
+    if (AERO) { r.nwfat = s1.v[5]; r.nifat = s1.v[6]; }
+  }
+  return r;
+}
+
 // M:1649-1653 for a given intercept (the running minimum already taken)
 __device__ __forceinline__ void graupel_slope(double N0_exp, float rg, double& ilamg, double& N0_g) {
   const double lam_exp = sqrt(sqrt(N0_exp * (double)ck.am_g * (double)ck.cgg[0] / (double)rg));   // **oge1, oge1 = 1/4
@@ -232,8 +267,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
   const int nz = a.nz;
   const long ld = a.ld;
   const unsigned count = (unsigned)*a.work_count;
-  float* const sc_class = a.scratch + (size_t)a.cell_kstart[KC] * SC_HALF;   // records in list order: the half that only k_finish reads ...
-  float* const sb_class = a.scratch_b + (size_t)a.cell_kstart[KC] * SC_HALF; // ... and the half that k_carries reads as well
+  const unsigned kstart = (unsigned)a.cell_kstart[KC], k2_list = (unsigned)a.cell_kstart[KC_MIXNR];
+  float* const sb_class = a.scratch_b + (size_t)kstart * SC_HALF;            // records in list order: the half that k_carries reads as well ...
+  constexpr bool COMPACT = !AERO && (KC == KC_WARM || KC == KC_ICE);         // ... and the half that only k_finish reads (RecA)
   const float DT = a.dt;
   const float odt = 1.f / DT, odts = 1.f / DT;
   const float Nt_c = ck.Nt_c;
@@ -260,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
     float ni1d = TR::I ? a.f[F_NI][o] : 0.0f, nr1d = TR::R ? a.f[F_NR][o] : 0.0f;
     float nc1d_in = 0.f, nwfa1d = 0.f, nifa1d = 0.f, w1d = 0.f;
     if (AERO) { nc1d_in = TR::C ? a.nc[o] : 0.0f; nwfa1d = a.nwfa[o]; nifa1d = a.nifa[o]; w1d = a.w[o]; }
-    float* const sc = sc_class + (size_t)(valid ? i : wbase) * SC_HALF;
+    float* const sc = rec_a_ptr<AERO>(a, kstart + (unsigned)(valid ? i : wbase), k2_list);
     float* const sb = sb_class + (size_t)(valid ? i : wbase) * SC_HALF;
 
     // rates, M:1184-1211 (zeroed M:1282-1363)
@@ -1204,9 +1240,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_cells(StepArgs a) {
       // the sign of the first intercept carries the k_0 test of this level's updated temperature (intercepts are > 0)
       const float n0a_out = warm9 ? -(float)n0b_lo : (float)n0b_lo;
       // two 64-byte half records, four whole sectors, SC_* order
-      st_sector(sc, tt, qvt, qct, qit, qrt, qst, qgt, nit);
-      st_sector(sc + 8, nrt, nct, nr, ni, v_ni, nwfat, nifat, 0.f);
-      st_sector(sb, rr, ri, rs, rg, v_r, v_nr, v_i, rho);
+      if (COMPACT && KC == KC_WARM) {
+        st_sector(sc, tt, qvt, qct, qrt, nrt, nct, nr, 0.f);
+        st_sector(sb, rr, ri, rs, rg, v_r, v_nr, v_i, rho);
+      } else if (COMPACT) {
+        st_sector(sc, tt, qvt, qct, qit, qst, nit, nct, ni);
+        st_sector(sb, rr, ri, rs, rg, v_r, v_ni, v_i, rho);     // (no rain in this class: the word of its number speed carries v_ni)
+      } else {
+        st_sector(sc, tt, qvt, qct, qit, qrt, qst, qgt, nit);
+        st_sector(sc + 8, nrt, nct, nr, ni, v_ni, nwfat, nifat, 0.f);
+        st_sector(sb, rr, ri, rs, rg, v_r, v_nr, v_i, rho);
+      }
       st_sector(sb + 8, s15, n0a_out, (float)n0b_slw, vts_h, vts_boost, temp, 0.f, 0.f);
       // An upper bound of every fall speed this cell can hand a level of its column, for the test "no species of this column
       // needs a second sedimentation sub-step" (k_carries): its own speeds (a level without the species inherits them, M:3235);
@@ -1404,6 +1448,7 @@ enum { WS_TTEN = 0, WS_QVTEN, WS_QCTEN, WS_QITEN, WS_QRTEN, WS_QSTEN, WS_QGTEN, 
 template <bool RATES, bool AERO>
 __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
   const int n = *a.sub_count, count = *a.work_count;
+  const unsigned k1_list = (unsigned)a.cell_kstart[KC_ICE], k2_list = (unsigned)a.cell_kstart[KC_MIXNR];
   const int nz = a.nz;
   const long ld = a.ld, ncol = a.ncol;
   const long cs = a.ws_cols;
@@ -1428,18 +1473,19 @@ __global__ void __launch_bounds__(32, 16) k_substeps(StepArgs a) {
         if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
         float* w = w0 + (size_t)k * cs;
         if ((bw >> (k & 31)) & 1u) {
-          const size_t ri = (size_t)cidx[(size_t)k * count] * SC_HALF;
-          const float *q = a.scratch + ri, *qb = a.scratch_b + ri;
-          const Sector s0 = ld_sector(q), s1 = ld_sector(q + 8), s2 = ld_sector(qb), s3 = ld_sector(qb + 8);
-          w[WS_TTEN * ps] = s0.v[0]; w[WS_QVTEN * ps] = s0.v[1]; w[WS_QCTEN * ps] = s0.v[2]; w[WS_QITEN * ps] = s0.v[3];
-          w[WS_QRTEN * ps] = s0.v[4]; w[WS_QSTEN * ps] = s0.v[5]; w[WS_QGTEN * ps] = s0.v[6]; w[WS_NITEN * ps] = s0.v[7];
-          w[WS_NRTEN * ps] = s1.v[0]; w[WS_NCTEN * ps] = s1.v[1]; w[WS_NR * ps] = s1.v[2]; w[WS_NI * ps] = s1.v[3];
+          const unsigned idx = cidx[(size_t)k * count];
+          const float* qb = a.scratch_b + (size_t)idx * SC_HALF;
+          const Sector s2 = ld_sector(qb), s3 = ld_sector(qb + 8);
+          const RecA ra = load_rec_a<AERO>(a, idx, k1_list, k2_list, s2);
+          w[WS_TTEN * ps] = ra.tt; w[WS_QVTEN * ps] = ra.qvt; w[WS_QCTEN * ps] = ra.qct; w[WS_QITEN * ps] = ra.qit;
+          w[WS_QRTEN * ps] = ra.qrt; w[WS_QSTEN * ps] = ra.qst; w[WS_QGTEN * ps] = ra.qgt; w[WS_NITEN * ps] = ra.nit;
+          w[WS_NRTEN * ps] = ra.nrt; w[WS_NCTEN * ps] = ra.nct; w[WS_NR * ps] = ra.nr; w[WS_NI * ps] = ra.ni;
           w[WS_RR * ps] = s2.v[0]; w[WS_RI * ps] = s2.v[1]; w[WS_RS * ps] = s2.v[2]; w[WS_RG * ps] = s2.v[3];
           w[WS_RHO * ps] = s2.v[7]; w[WS_S15 * ps] = s3.v[0];
-          if (AERO) { w[WS_NWFAT * ps] = s1.v[5]; w[WS_NIFAT * ps] = s1.v[6]; }
+          if (AERO) { w[WS_NWFAT * ps] = ra.nwfat; w[WS_NIFAT * ps] = ra.nifat; }
           if (s2.v[0] > R1) { v_r = s2.v[4]; v_nr = s2.v[5]; }
           if (!iiwarm) {
-            if (s2.v[1] > R1) { v_i = s2.v[6]; v_ni = s1.v[4]; }
+            if (s2.v[1] > R1) { v_i = s2.v[6]; v_ni = ra.v_ni; }
             if (s2.v[2] > R1) v_s = s3.v[6];
             if (s2.v[3] > R1) v_g = s3.v[7];
           }
@@ -1515,6 +1561,7 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
   const int slot = blockIdx.x * 32 + threadIdx.x;
   const int count = *a.work_count;
   if (slot >= count) return;
+  const unsigned k1_list = (unsigned)a.cell_kstart[KC_ICE], k2_list = (unsigned)a.cell_kstart[KC_MIXNR];
   const int nz = a.nz;
   const long cs = count;
   // A simple column (k_carries: no graupel, every sub-step count 0 or 1) has no counts: what runs down the column - the speed
@@ -1550,26 +1597,28 @@ __global__ void __launch_bounds__(32, K2_MINB) k_finish(StepArgs a) {
   for (int k = nz - 1; k >= 0; --k) {
     if (k == nz - 1 || (k & 31) == 31) bw = BUSY_WORD(k >> 5);
     const long o = (long)k * ld + col;
-    const float *q = a.scratch + (size_t)idx_next * SC_HALF, *qb = a.scratch_b + (size_t)idx_next * SC_HALF;
+    const unsigned idx = idx_next;
+    const float* qb = a.scratch_b + (size_t)idx * SC_HALF;
     idx_next = idx_next2;
     if (k > 1) idx_next2 = cidx[(size_t)(k - 2) * cs];
     if ((k & 31) != 0 && ((bw >> ((k - 1) & 31)) & 1u)) {
-      prefetch_record(a.scratch + (size_t)idx_next * SC_HALF); prefetch_record(a.scratch_b + (size_t)idx_next * SC_HALF);
+      prefetch_record(rec_a_ptr<AERO>(a, idx_next, k2_list)); prefetch_record(a.scratch_b + (size_t)idx_next * SC_HALF);
     }
     const bool busy = ((bw >> (k & 31)) & 1u) != 0;
     const float t1d = a.f[F_T][o], qv1d = a.f[F_QV][o], qc1d = a.f[F_QC][o], qi1d = a.f[F_QI][o], qr1d = a.f[F_QR][o],
                 qs1d = a.f[F_QS][o], qg1d = a.f[F_QG][o], ni1d = a.f[F_NI][o], nr1d = a.f[F_NR][o], pres = a.p[o];
     HandOff h;
     if (busy) {
-      const Sector s0 = ld_sector(q), s1 = ld_sector(q + 8), s2 = ld_sector(qb), s3 = ld_sector(qb + 8);   // the two half records
-      h.tt = s0.v[0]; h.qvt = s0.v[1]; h.qct = s0.v[2]; h.qit = s0.v[3]; h.qrt = s0.v[4]; h.qst = s0.v[5]; h.qgt = s0.v[6]; h.nit = s0.v[7];
-      h.nrt = s1.v[0]; h.nct = s1.v[1]; h.nr = s1.v[2]; h.ni = s1.v[3];
+      const Sector s2 = ld_sector(qb), s3 = ld_sector(qb + 8);   // the two half records
+      const RecA ra = load_rec_a<AERO>(a, idx, k1_list, k2_list, s2);
+      h.tt = ra.tt; h.qvt = ra.qvt; h.qct = ra.qct; h.qit = ra.qit; h.qrt = ra.qrt; h.qst = ra.qst; h.qgt = ra.qgt; h.nit = ra.nit;
+      h.nrt = ra.nrt; h.nct = ra.nct; h.nr = ra.nr; h.ni = ra.ni;
       h.rr = s2.v[0]; h.ri = s2.v[1]; h.rs = s2.v[2]; h.rg = s2.v[3];
       h.rho = s2.v[7]; h.s15 = s3.v[0];
-      h.nwfat = s1.v[5]; h.nifat = s1.v[6];
+      h.nwfat = ra.nwfat; h.nifat = ra.nifat;
       if (h.rr > R1) { v_r = s2.v[4]; v_nr = s2.v[5]; }
       if (!iiwarm) {
-        if (h.ri > R1) { v_i = s2.v[6]; v_ni = s1.v[4]; }
+        if (h.ri > R1) { v_i = s2.v[6]; v_ni = ra.v_ni; }
         if (!simple) {
           if (h.rs > R1) v_s = s3.v[6];                   // (written by k_carries where the species is present)
           if (h.rg > R1) v_g = s3.v[7];
