@@ -177,6 +177,7 @@ bool find_table(const kidmp_handle* h, const std::string& name, TabDesc& d) {
   for (int q = 0; q < I_N; ++q) if (name == i3[q]) { d = {h->tabs.iaus, N_IAUS, I_N, q, false}; return true; }
   if (name == "t_Efrw") { d = {h->tabs.efrw, N_EF, 1, 0, true}; return true; }
   if (name == "t_Efsw") { d = {h->tabs.efsw, N_EF, 1, 0, true}; return true; }
+  if (name == "tnc_wev" && h->d_tnc_wev) { d = {h->d_tnc_wev, (long)NBINS * NTB_C * NBINS, 1, 0, false}; return true; }   // (after the first aerosol-aware step)
   return false;
 }
 
@@ -1431,30 +1432,41 @@ int kidmp_step_device(kidmp_handle* h, long ncol, int nz, float dt, float* const
 }
 
 // table_dropEvap, M:4400-4439: number of the cloud droplets smaller than D-star for every (D-star bin, cloud water node,
-// droplet number node).  Only an aerosol-aware run reads it (M:2850): made by the first such step, on the host with the
-// expressions and the libm of the reference's own table builder (3.7e5 entries), and the constants re-published.
+// droplet number node).  Only an aerosol-aware run reads it (M:2850): built by the first such step - slope and intercept of the
+// 3 700 spectra on the host (two powers each, like the per-node scalars of the other tables), the 370 000 bin sums by
+// k_table_wev - and the constants re-published.
 int ensure_wev_table(kidmp_handle* h) {
   if (h->d_tnc_wev) return 0;
   const HostBins& b = h->hb;
   const KConst& kc = h->kc;
-  std::vector<double> tnc((size_t)NBINS * NTB_C * NBINS), N_c(NBINS);
+  std::vector<double> lamc((size_t)NTB_C * NBINS), N0_c((size_t)NTB_C * NBINS);
+  std::vector<int> nu(NBINS);
   for (int k = 0; k < NBINS; ++k) {
     const int nu_c = std::min(15, (int)std::lround((double)1000.E6f / b.t_Nc[k]) + 2);
+    nu[k] = nu_c;
     for (int j = 0; j < NTB_C; ++j) {
-      const double lamc = std::pow(b.t_Nc[k] * (double)kc.am_r * (double)kc.ccg[1][nu_c - 1] * (double)kc.ocg1[nu_c - 1] / (double)b.r_c[j], (double)kc.obmr);
-      const double N0_c = b.t_Nc[k] * (double)kc.ocg1[nu_c - 1] * std::pow(lamc, (double)kc.cce[0][nu_c - 1]);
-      for (int i = 0; i < NBINS; ++i) {
-        double dp = 1.0;                                  // Dc(i)**nu_c, integer power: by squaring like libgcc's powi
-        { double x = b.Dc[i]; int n = nu_c; while (n) { if (n & 1) dp *= x; n >>= 1; if (n) x *= x; } }
-        N_c[i] = N0_c * dp * std::exp(-lamc * b.Dc[i]) * b.dtc[i];
-        double summ2 = 0.0;
-        for (int n = 0; n <= i; ++n) summ2 = summ2 + N_c[n];
-        tnc[(size_t)i + (size_t)NBINS * (j + (size_t)NTB_C * k)] = summ2;
-      }
+      const double l = std::pow(b.t_Nc[k] * (double)kc.am_r * (double)kc.ccg[1][nu_c - 1] * (double)kc.ocg1[nu_c - 1] / (double)b.r_c[j], (double)kc.obmr);
+      lamc[j + (size_t)NTB_C * k] = l;
+      N0_c[j + (size_t)NTB_C * k] = b.t_Nc[k] * (double)kc.ocg1[nu_c - 1] * std::pow(l, (double)kc.cce[0][nu_c - 1]);
     }
   }
-  CK(h, cudaMalloc((void**)&h->d_tnc_wev, tnc.size() * 8));
-  CK(h, cudaMemcpy(h->d_tnc_wev, tnc.data(), tnc.size() * 8, cudaMemcpyHostToDevice));
+  std::vector<void*> keep;
+  const double *d_lamc = nullptr, *d_N0 = nullptr, *d_Dc = nullptr, *d_dtc = nullptr;
+  const int* d_nu = nullptr;
+  cudaError_t e = to_dev(lamc, &d_lamc, keep);
+  if (e == cudaSuccess) e = to_dev(N0_c, &d_N0, keep);
+  if (e == cudaSuccess) e = to_dev(nu, &d_nu, keep);
+  if (e == cudaSuccess) e = to_dev(b.Dc, NBINS, &d_Dc, keep);
+  if (e == cudaSuccess) e = to_dev(b.dtc, NBINS, &d_dtc, keep);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_tnc_wev, (size_t)NBINS * NTB_C * NBINS * 8);
+  if (e == cudaSuccess) {
+    k_table_wev<<<NTB_C * NBINS, 128, 0, h->stream>>>(d_lamc, d_N0, d_nu, d_Dc, d_dtc, h->d_tnc_wev);
+    ++h->launches;
+    e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  for (void* q : keep) cudaFree(q);
+  if (e != cudaSuccess) { if (h->d_tnc_wev) { cudaFree(h->d_tnc_wev); h->d_tnc_wev = nullptr; } return fail(h, "table_dropEvap: %s", cudaGetErrorString(e)); }
   h->kc.tnc_wev = h->d_tnc_wev;
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_const_owner[h->device] == h) g_const_owner[h->device] = nullptr;      // the next step uploads the constants again

@@ -321,4 +321,26 @@ inline cudaError_t build_tables_dev(const TablePrep& tp, const TableSet& t, cons
   return err;
 }
 
+// table_dropEvap, M:4400-4439 (only an aerosol-aware run reads it, M:2850): tnc_wev(i, j, k) = number of the cloud droplets of
+// the spectrum with number t_Nc(k) and content r_c(j) that are smaller than the i-th diameter bin edge.  One block per (j, k): the
+// hundred bin numbers N_c(i) = N0_c Dc(i)**nu_c exp(-lamc Dc(i)) dtc(i) in shared memory, then every thread its running sum in the
+// reference's order (summ2 = summ2 + N_c(n), n = 1..i).  lamc, N0_c (one pair of powers per block) and nu_c come from the host
+// like the other per-axis-node scalars (TablePrep).
+__global__ void __launch_bounds__(128) k_table_wev(const double* __restrict__ lamc, const double* __restrict__ N0_c, const int* __restrict__ nu_c,
+                                                   const double* __restrict__ Dc, const double* __restrict__ dtc, double* __restrict__ tnc) {
+  __shared__ double s_N[NBINS];
+  const int jk = blockIdx.x, k = jk / NTB_C, i = threadIdx.x;
+  if (i < NBINS) {
+    double dp = 1.0;                                    // Dc(i)**nu_c, integer power: by squaring like libgcc's powi
+    { double x = Dc[i]; int n = nu_c[k]; while (n) { if (n & 1) dp *= x; n >>= 1; if (n) x *= x; } }
+    s_N[i] = N0_c[jk] * dp * exp(-lamc[jk] * Dc[i]) * dtc[i];
+  }
+  __syncthreads();
+  if (i < NBINS) {
+    double summ2 = 0.0;
+    for (int n = 0; n <= i; ++n) summ2 = summ2 + s_N[n];
+    tnc[(size_t)i + (size_t)NBINS * jk] = summ2;
+  }
+}
+
 }  // namespace kidmp

@@ -826,6 +826,8 @@ def test_aerosol_aware_step(dt, dz, ncol, gpu_mixed, oracle_mixed):
     cloud = ref["qc"] > 1e-9
     rho = 0.622 * pn / (287.04 * ref["t"] * (ref["qv"] + 0.622))
     assert cloud.any() and np.abs(rnc[cloud] * rho[cloud] / 100.0e6 - 1.0).max() > 0.05
+    # the drop-evaporation table of the first aerosol-aware step (k_table_wev) against the oracle's table_dropEvap, M:4400-4439
+    np.testing.assert_allclose(gpu_mixed.get("tnc_wev"), oracle_mixed.get("tnc_wev").ravel(order="F"), rtol=1e-12, atol=1e-300)
     # and the default path of the same handle is untouched by it
     a, pa, b, pb = _both(gpu_mixed, oracle_mixed, 10.0, *_domain(512, cloudy_fraction=1.0, coherent=False))
     assert_parity(a, b, what="default step after aerosol-aware steps", flip_fraction=1e-3)
