@@ -96,3 +96,52 @@ def test_library_is_built_from_the_sources_in_the_tree():
     from kid_b200 import build, kidmp
     L = kidmp.load()
     assert L.kidmp_build_id().decode() == build.source_id() == build.library_id()
+
+
+def test_fortran_shim_binds_only_what_the_header_declares():
+    """kid_b200/fortran/mphys_thompson09n.f90 cannot be compiled here (no Fortran compiler), so its iso_c_binding side is checked on
+    the text: every bind(C, name=...) is a function of include/kidmp.h, and the bind(C) derived types list the members of the C
+    structs in the same order (kidmp_config, kidmp_kid_columns, kidmp_wrf_fields, kidmp_wrf_aerosols)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    f90 = open(os.path.join(root, "kid_b200", "fortran", "mphys_thompson09n.f90")).read()
+    hdr = open(os.path.join(root, "include", "kidmp.h")).read()
+    declared = set(re.findall(r"\b(kidmp_[a-z0-9_]+)\s*\(", hdr))
+    bound = re.findall(r"bind\(C,\s*name='(kidmp_[a-z0-9_]+)'\)", f90)
+    assert len(bound) >= 8
+    for name in bound:
+        assert name in declared, name
+    # the module keeps the reference's names (I:9, I:28)
+    assert re.search(r"(?i)^\s*module\s+mphys_thompson09n\b", f90, re.M) and re.search(r"(?i)subroutine\s+mphys_thompson09_interfacen\b", f90)
+
+    def c_members(struct):
+        body = re.search(r"typedef struct %s\s*\{(.*?)\}\s*%s;" % (struct, struct), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = re.sub(r"^(const\s+)?(float|int|long|char)\s*", "", decl.replace("\n", " "))
+            for n in names.split(","):
+                n = n.strip().lstrip("*").strip()
+                n = re.sub(r"^(const\s+)?(float|int|long|char)\s*\**\s*", "", n)
+                n = re.sub(r"\[.*\]", "", n)
+                if n:
+                    out.append(n)
+        return out
+
+    def f_members(struct):
+        body = re.search(r"type, bind\(C\) :: %s(.*?)end type %s" % (struct, struct), f90, re.S).group(1)
+        out = []
+        for line in body.split("\n"):
+            line = line.split("!")[0]
+            if "::" in line:
+                for n in line.split("::")[1].split(","):
+                    n = re.sub(r"\(.*\)", "", n).strip()
+                    if n:
+                        out.append(n)
+        return out
+
+    for struct in ("kidmp_config", "kidmp_kid_columns", "kidmp_wrf_fields", "kidmp_wrf_aerosols"):
+        assert [m.lower() for m in f_members(struct)] == [m.lower() for m in c_members(struct)], struct
